@@ -1,0 +1,179 @@
+/*
+ * okl.h - C ABI of libokl_b200.so: the B200-native (sm_100a) implementation of okrolearn's
+ * Conv/Dense train-step hot path (BASELINE.json north_star).
+ *
+ * The reference (okrolearn 0.2.7, pure Python + NumPy) has no FFI; its boundary is the duck-typed
+ * layer protocol `forward(Tensor)->Tensor`, `backward(Tensor, lr)->Tensor` (okrolearn.py:2887-2888,
+ * 2910-2911).  The Python package okrolearn_b200 re-implements that protocol and calls ONLY the
+ * functions below through ctypes.  Each entry point cites the reference code it replaces
+ * ("okl.py" = src/okrolearn/okrolearn.py, "tensor.py", "optimizers.py" under /root/reference).
+ *
+ * Conventions
+ *   - every function returns an okl_status (0 = OK, < 0 = error) and never throws;
+ *     okl_last_error() returns a NUL-terminated message owned by the library (thread-local).
+ *   - device pointers are plain `void*` obtained from okl_malloc (sub-ranges are allowed);
+ *     all device tensors are dense fp32 unless stated (bf16 shadows are internal).
+ *   - host pointers are borrowed for the duration of the call only.
+ *   - all work is enqueued on the context's compute stream; only okl_d2h, okl_ctx_sync,
+ *     okl_timer_stop and okl_read_scalar block the host.
+ *   - one okl_ctx <-> one CUDA device <-> one compute stream + one comm stream; a ctx is used from
+ *     one host thread at a time.  Multi-GPU = one process per GPU (okl_comm_*).
+ *   - tensors use the reference's layouts: Dense X (M,K) row-major, W (K,N) row-major, b (N);
+ *     conv x (N,C,*spatial), filters (O,C,*k), biases (O); `layout` OKL_NCX is that channels-first
+ *     layout, OKL_NXC is the channels-last layout the tensor-core kernels use internally.
+ */
+#ifndef OKL_H
+#define OKL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct okl_ctx okl_ctx;
+typedef struct okl_graph okl_graph;
+
+typedef enum {
+  OKL_OK = 0,
+  OKL_ERR_INVALID = -1,      /* bad argument / shape (Python raises ValueError) */
+  OKL_ERR_CUDA = -2,         /* CUDA runtime / driver failure (Python raises RuntimeError) */
+  OKL_ERR_NCCL = -3,
+  OKL_ERR_OOM = -4,
+  OKL_ERR_UNSUPPORTED = -5
+} okl_status;
+
+/* arithmetic mode of the GEMM-shaped kernels (north_star: 1e-5 rel in FP32, 2e-2 in TF32/BF16) */
+typedef enum { OKL_FP32 = 0, OKL_TF32 = 1, OKL_BF16 = 2 } okl_precision;
+typedef enum { OKL_ACT_NONE = 0, OKL_ACT_RELU = 1, OKL_ACT_SIGMOID = 2, OKL_ACT_TANH = 3 } okl_act;
+typedef enum { OKL_F32 = 0, OKL_F64 = 1, OKL_I64 = 2, OKL_I32 = 3, OKL_U8 = 4 } okl_dtype;
+typedef enum { OKL_NCX = 0, OKL_NXC = 1 } okl_layout;
+typedef enum { OKL_POOL_MAX = 0, OKL_POOL_AVG = 1 } okl_pool_kind;
+
+/* ------------------------------------------------------------------ context / errors */
+const char* okl_version(void);
+const char* okl_last_error(void);
+int okl_ctx_create(int device, int precision, okl_ctx** out);
+int okl_ctx_destroy(okl_ctx* ctx);
+int okl_ctx_sync(okl_ctx* ctx);
+int okl_ctx_set_precision(okl_ctx* ctx, int precision);
+int okl_ctx_get_precision(okl_ctx* ctx, int* precision);
+/* sm_count, total HBM bytes, compute capability major*10+minor */
+int okl_device_info(okl_ctx* ctx, int* sm_count, size_t* total_mem, int* cc);
+/* number of kernels this library has launched on ctx (graph replays count their captured nodes) */
+int okl_launch_count(okl_ctx* ctx, unsigned long long* out);
+
+/* ------------------------------------------------------------------ memory (replaces Tensor.data ndarray storage, tensor.py:6-10) */
+int okl_malloc(okl_ctx* ctx, size_t bytes, void** out);      /* caching pool; safe during graph capture on a hit */
+int okl_free(okl_ctx* ctx, void* p);
+int okl_pool_reserve(okl_ctx* ctx, size_t bytes);            /* pre-grow the pool with one block of `bytes` */
+int okl_memset(okl_ctx* ctx, void* p, int byte, size_t bytes);
+int okl_pinned_alloc(size_t bytes, void** out);
+int okl_pinned_free(void* p);
+/* host -> device fp32, converting from src_dtype on the device; n = element count */
+int okl_h2d(okl_ctx* ctx, void* dst_f32, const void* host, size_t n, int src_dtype);
+/* same, host buffer must be pinned (okl_pinned_alloc), fully asynchronous, f32 / i32 only (raw copy) */
+int okl_h2d_async_raw(okl_ctx* ctx, void* dst, const void* pinned_host, size_t bytes);
+/* device fp32 -> host dst_dtype (F32 or F64); blocks until the data is in `host` */
+int okl_d2h(okl_ctx* ctx, void* host, const void* src_f32, size_t n, int dst_dtype);
+int okl_d2h_async_raw(okl_ctx* ctx, void* pinned_host, const void* src, size_t bytes);
+int okl_d2d(okl_ctx* ctx, void* dst, const void* src, size_t bytes);
+/* host int64/int32 class targets -> device int32 */
+int okl_h2d_i32(okl_ctx* ctx, void* dst_i32, const void* host, size_t n, int src_dtype);
+/* channels-first (N,C,S) <-> channels-last (N,S,C) permutation, S = prod(spatial) */
+int okl_permute(okl_ctx* ctx, void* dst, const void* src, int N, int C, long long S, int src_layout);
+/* dst[r,:] = src[idx[r],:]  (epoch shuffle okl.py:2957-2960 as a device gather); idx int32 on device */
+int okl_gather_rows(okl_ctx* ctx, void* dst, const void* src, const void* idx_i32, long long rows, long long row_elems);
+
+/* ------------------------------------------------------------------ Dense (okl.py:18-54; tensor.py:57-67)
+ * fwd: Y[M,N] = act(X[M,K] . W[K,N] + b[N])                       okl.py:31 (+ fused activation epilogue)
+ * bwd: dW[K,N] = X^T . G ; db[N] = sum_rows G ; dX[M,K] = G . W^T  okl.py:35-37   (dX may be NULL)            */
+int okl_dense_fwd(okl_ctx* ctx, const void* X, const void* W, const void* b, void* Y, int M, int K, int N, int act);
+int okl_dense_bwd(okl_ctx* ctx, const void* X, const void* W, const void* G, void* dX, void* dW, void* db,
+                  int M, int K, int N);
+
+/* ------------------------------------------------------------------ Conv1D/2D/3D (okl.py:669-764, 767-883, 936-1049)
+ * nd = 1,2,3; unused trailing entries of in/k/s/p are ignored.  Cross-correlation, zero padding both sides,
+ * output extent (in + 2p - k) / s + 1 (floor).  filters (O,C,*k) and biases (O) are always in the reference layout. */
+typedef struct {
+  int nd;
+  int N, C, O;
+  int in[3];
+  int k[3];
+  int s[3];
+  int p[3];
+  int act;          /* okl_act fused into fprop's epilogue (bias first) */
+  int x_layout;     /* okl_layout of x / dx */
+  int y_layout;     /* okl_layout of y / g  */
+} okl_conv_desc;
+
+int okl_conv_out_extent(const okl_conv_desc* d, int out[3]);
+/* y = act(conv(x, W) + b)                      okl.py:691-715 / 790-813 / 948-985 */
+int okl_conv_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* W, const void* b, void* y);
+/* dx = conv_transpose(g, W)                    okl.py:736-739 / 867-868 / 1017-1020 (+ repairs R1,R3) */
+int okl_conv_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* g, const void* W, void* dx);
+/* dW = x (*) g ; db = sum_{n,pos} g            okl.py:729-735 / 865-866,870 / 1013-1016,991 (+ repairs R1,R2); db may be NULL */
+int okl_conv_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* g, void* dW, void* db);
+
+/* ------------------------------------------------------------------ activations (okl.py:94-120, 500-522, 2070-2108) */
+int okl_act_fwd(okl_ctx* ctx, int act, const void* x, void* y, size_t n);
+/* relu: ref = x (g * (x>0), okl.py:107) [y works too]; sigmoid: ref = y (okl.py:514); tanh: ref = x (okl.py:2092) */
+int okl_act_bwd(okl_ctx* ctx, int act, const void* ref, const void* g, void* dx, size_t n);
+/* out[i] = a[i] (op) b[i % nb]; op 0 = add (Tensor.__add__, tensor.py:12-22), 1 = mul (Tensor.__mul__, tensor.py:24-39).
+ * nb = n for same-shape operands, the row length for a (1,N) row broadcast, 1 for a scalar held on the device. */
+int okl_binary(okl_ctx* ctx, int op, const void* a, const void* b, void* out, size_t n, size_t nb);
+/* x *= alpha   (final `inputs.data / temperature`, okl.py:2890) */
+int okl_scale(okl_ctx* ctx, void* x, size_t n, float alpha);
+
+/* ------------------------------------------------------------------ pooling (okl.py:1715-1831 + repairs R4,R5) */
+int okl_pool_fwd(okl_ctx* ctx, int kind, const void* x, void* y, int N, int C, int H, int W, int pool, int stride, int layout);
+int okl_pool_bwd(okl_ctx* ctx, int kind, const void* x, const void* g, void* dx, int N, int C, int H, int W, int pool,
+                 int stride, int layout);
+
+/* ------------------------------------------------------------------ softmax + losses (okl.py:355-399, 1380-1409, 1833-1839) */
+int okl_softmax_fwd(okl_ctx* ctx, const void* x, void* p, int rows, int cols);
+int okl_softmax_bwd(okl_ctx* ctx, const void* p, const void* g, void* dx, int rows, int cols);
+/* loss[0] = mean_r(-log(clip(p)[r,t_r])) over `rows`; grad = (clip(p) - onehot) / denom  (denom = global batch) */
+int okl_ce_fwd_bwd(okl_ctx* ctx, const void* p, const void* targets_i32, void* loss, void* grad, int rows, int cols, float denom);
+/* loss[0] = sum((o-t)^2) / n ; grad = 2 (o - t) / denom   (denom = global element count) */
+int okl_mse_fwd_bwd(okl_ctx* ctx, const void* o, const void* t, void* loss, void* grad, size_t n, float denom);
+int okl_read_scalar(okl_ctx* ctx, const void* dev_f32, float* out);
+
+/* ------------------------------------------------------------------ parameter updates
+ * reference rule (okl.py:39-45, 744-748, 872-878, 1029-1033): gacc += g ; w -= lr * gacc  (gacc never reset).
+ * lr_dev, when non-NULL, is a device fp32 scalar read at run time (lets a captured CUDA graph follow the scheduler). */
+int okl_accum_update(okl_ctx* ctx, void* w, void* gacc, const void* g, size_t n, float lr, const void* lr_dev);
+/* optimizers.py:140-144: v = mu v - lr g ; w += v */
+int okl_sgd_update(okl_ctx* ctx, void* w, void* v, const void* g, size_t n, float lr, float momentum);
+/* optimizers.py:28-42 with t supplied by the caller (it increments per update call) */
+int okl_adam_update(okl_ctx* ctx, void* w, void* m, void* v, const void* g, size_t n, float lr, float beta1, float beta2,
+                    float eps, int t);
+
+/* ------------------------------------------------------------------ CUDA graphs (train-step capture) */
+int okl_graph_begin(okl_ctx* ctx);
+int okl_graph_end(okl_ctx* ctx, okl_graph** out);
+int okl_graph_launch(okl_ctx* ctx, okl_graph* g);
+int okl_graph_destroy(okl_graph* g);
+
+/* ------------------------------------------------------------------ timing on the compute stream */
+int okl_timer_start(okl_ctx* ctx);
+int okl_timer_stop(okl_ctx* ctx, float* ms);     /* records, synchronises, returns elapsed ms */
+/* write `bytes` of a scratch buffer larger than L2 (between timed iterations) */
+int okl_flush_l2(okl_ctx* ctx);
+
+/* ------------------------------------------------------------------ data-parallel gradient exchange (NCCL over NVLink) */
+int okl_comm_unique_id(void* out128);
+int okl_comm_init(okl_ctx* ctx, const void* id128, int rank, int nranks);
+int okl_comm_destroy(okl_ctx* ctx);
+/* sum-allreduce `count` fp32 at p on the comm stream, ordered after everything enqueued so far on the compute stream */
+int okl_allreduce_async(okl_ctx* ctx, void* p, size_t count);
+/* make the compute stream wait for every allreduce issued so far */
+int okl_comm_wait(okl_ctx* ctx);
+int okl_allreduce_max_host(okl_ctx* ctx, double* value);   /* small host-value reduction for max-over-ranks timing */
+int okl_barrier(okl_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OKL_H */

@@ -1,0 +1,116 @@
+// Internal shared declarations for libokl_b200 (context, error plumbing, launch accounting).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/okl.h"
+
+struct okl_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  unsigned long long launches = 0;
+};
+
+struct okl_ctx {
+  int device = 0;
+  int precision = OKL_FP32;
+  int sm_count = 148;
+  int cc = 100;
+  size_t total_mem = 0;
+  cudaStream_t stream = nullptr;        // compute
+  cudaStream_t comm_stream = nullptr;   // NCCL
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  unsigned long long launches = 0;      // kernels launched eagerly + graph replays
+  bool capturing = false;
+  unsigned long long capture_launches = 0;
+  // caching device allocator
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;
+  std::map<void*, size_t> live;         // every block handed out or cached -> rounded size
+  // scratch
+  void* workspace = nullptr;            // split-K partials etc.
+  size_t workspace_bytes = 0;
+  void* staging = nullptr;              // dtype conversion staging for h2d / d2h
+  size_t staging_bytes = 0;
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  // comm
+  void* nccl_comm = nullptr;
+  int rank = 0, nranks = 1;
+  bool comm_pending = false;
+};
+
+void okl_set_error(const char* fmt, ...);
+
+#define OKL_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      okl_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return OKL_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define OKL_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      okl_set_error(__VA_ARGS__);       \
+      return OKL_ERR_INVALID;           \
+    }                                   \
+  } while (0)
+
+// account one kernel launch and surface launch-configuration errors immediately
+static inline int okl_post_launch(okl_ctx* ctx, const char* what) {
+  if (ctx->capturing) ctx->capture_launches++; else ctx->launches++;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    okl_set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+    return OKL_ERR_CUDA;
+  }
+  return OKL_OK;
+}
+#define OKL_LAUNCHED(ctx, what)                          \
+  do {                                                   \
+    int _s = okl_post_launch(ctx, what);                 \
+    if (_s != OKL_OK) return _s;                         \
+  } while (0)
+
+int okl_ensure_workspace(okl_ctx* ctx, size_t bytes);   // grows ctx->workspace (not during capture)
+int okl_ensure_staging(okl_ctx* ctx, size_t bytes);
+
+static inline int okl_grid_1d(const okl_ctx* ctx, size_t work_items, int block, int max_waves = 8) {
+  size_t blocks = (work_items + block - 1) / block;
+  size_t cap = (size_t)ctx->sm_count * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---- entry points implemented in other translation units -------------------------------------
+// FFMA (exact fp32) GEMM-shaped kernels: okl_ffma.cu
+int okl_ffma_dense_fwd(okl_ctx*, const float* X, const float* W, const float* b, float* Y, int M, int K, int N, int act);
+int okl_ffma_dense_dw(okl_ctx*, const float* X, const float* G, float* dW, int M, int K, int N);
+int okl_ffma_dense_dx(okl_ctx*, const float* G, const float* W, float* dX, int M, int K, int N);
+int okl_ffma_conv_fprop(okl_ctx*, const okl_conv_desc*, const float* x, const float* W, const float* b, float* y);
+int okl_ffma_conv_dgrad(okl_ctx*, const okl_conv_desc*, const float* g, const float* W, float* dx);
+int okl_ffma_conv_wgrad(okl_ctx*, const okl_conv_desc*, const float* x, const float* g, float* dW);
+// reductions: okl_elementwise.cu
+int okl_colsum(okl_ctx*, const float* G, float* out, long long rows, int cols);                       // out[c] = sum_r G[r,c]
+int okl_channel_sum(okl_ctx*, const float* g, float* out, int N, int C, long long S, int layout);    // out[c] = sum_{n,s}
+// tcgen05 tensor-core kernels (TF32 / BF16 operands, fp32 accumulate in TMEM): okl_tc_gemm.cu / okl_tc_conv.cu
+bool okl_tc_dense_supported(okl_ctx*, int M, int K, int N);
+int okl_tc_dense_fwd(okl_ctx*, const float* X, const float* W, const float* b, float* Y, int M, int K, int N, int act);
+int okl_tc_dense_dw(okl_ctx*, const float* X, const float* G, float* dW, int M, int K, int N);
+int okl_tc_dense_dx(okl_ctx*, const float* G, const float* W, float* dX, int M, int K, int N);
+bool okl_tc_conv_supported(okl_ctx*, const okl_conv_desc*);
+int okl_tc_conv_fprop(okl_ctx*, const okl_conv_desc*, const float* x, const float* W, const float* b, float* y);
+int okl_tc_conv_dgrad(okl_ctx*, const okl_conv_desc*, const float* g, const float* W, float* dx);
+int okl_tc_conv_wgrad(okl_ctx*, const okl_conv_desc*, const float* x, const float* g, float* dW);

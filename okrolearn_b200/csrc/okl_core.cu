@@ -1,0 +1,545 @@
+// Context, memory pool, host<->device transfer with dtype conversion, CUDA graphs, timing and the
+// NCCL data-parallel exchange of libokl_b200.  See include/okl.h for the contract of each entry point.
+#include "common.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void okl_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* okl_last_error(void) { return g_err; }
+extern "C" const char* okl_version(void) { return "okl_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" int okl_ctx_create(int device, int precision, okl_ctx** out) {
+  OKL_REQUIRE(out != nullptr, "okl_ctx_create: out is NULL");
+  OKL_REQUIRE(precision >= OKL_FP32 && precision <= OKL_BF16, "okl_ctx_create: bad precision %d", precision);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    okl_set_error("okl_ctx_create: no CUDA device available (%s); this library has no CPU fallback",
+                  e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+    cudaGetLastError();
+    return OKL_ERR_CUDA;
+  }
+  OKL_REQUIRE(device >= 0 && device < ndev, "okl_ctx_create: device %d out of range [0,%d)", device, ndev);
+  OKL_CHECK_CUDA(cudaSetDevice(device));
+  okl_ctx* c = new okl_ctx();
+  c->device = device;
+  c->precision = precision;
+  cudaDeviceProp prop;
+  OKL_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  c->cc = prop.major * 10 + prop.minor;
+  c->total_mem = prop.totalGlobalMem;
+  OKL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  OKL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  OKL_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  OKL_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  OKL_CHECK_CUDA(cudaEventCreate(&c->ev_t0));
+  OKL_CHECK_CUDA(cudaEventCreate(&c->ev_t1));
+  *out = c;
+  return OKL_OK;
+}
+
+extern "C" int okl_comm_destroy(okl_ctx* ctx);
+
+extern "C" int okl_ctx_destroy(okl_ctx* ctx) {
+  if (!ctx) return OKL_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->comm_stream);
+  okl_comm_destroy(ctx);
+  for (auto& kv : ctx->live) cudaFree(kv.first);
+  if (ctx->workspace) cudaFree(ctx->workspace);
+  if (ctx->staging) cudaFree(ctx->staging);
+  if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  cudaEventDestroy(ctx->ev_fork);
+  cudaEventDestroy(ctx->ev_join);
+  cudaEventDestroy(ctx->ev_t0);
+  cudaEventDestroy(ctx->ev_t1);
+  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->comm_stream);
+  delete ctx;
+  return OKL_OK;
+}
+
+extern "C" int okl_ctx_sync(okl_ctx* ctx) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  OKL_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  OKL_CHECK_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+  return OKL_OK;
+}
+
+extern "C" int okl_ctx_set_precision(okl_ctx* ctx, int precision) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  OKL_REQUIRE(precision >= OKL_FP32 && precision <= OKL_BF16, "bad precision %d", precision);
+  ctx->precision = precision;
+  return OKL_OK;
+}
+
+extern "C" int okl_ctx_get_precision(okl_ctx* ctx, int* precision) {
+  OKL_REQUIRE(ctx && precision, "NULL argument");
+  *precision = ctx->precision;
+  return OKL_OK;
+}
+
+extern "C" int okl_device_info(okl_ctx* ctx, int* sm_count, size_t* total_mem, int* cc) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (total_mem) *total_mem = ctx->total_mem;
+  if (cc) *cc = ctx->cc;
+  return OKL_OK;
+}
+
+extern "C" int okl_launch_count(okl_ctx* ctx, unsigned long long* out) {
+  OKL_REQUIRE(ctx && out, "NULL argument");
+  *out = ctx->launches;
+  return OKL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// caching device allocator.  Blocks are rounded to 512 B (small) / 2 MiB (>= 1 MiB) and recycled by
+// exact rounded size, so a steady-state train step never calls cudaMalloc (and a captured graph's
+// buffers stay where they are).
+// ------------------------------------------------------------------------------------------------
+static size_t round_size(size_t b) {
+  if (b == 0) b = 1;
+  if (b < (1u << 20)) return (b + 511) & ~size_t(511);
+  return (b + (2u << 20) - 1) & ~size_t((2u << 20) - 1);
+}
+
+extern "C" int okl_malloc(okl_ctx* ctx, size_t bytes, void** out) {
+  OKL_REQUIRE(ctx && out, "NULL argument");
+  size_t r = round_size(bytes);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto it = ctx->free_blocks.find(r);
+  if (it != ctx->free_blocks.end()) {
+    *out = it->second;
+    ctx->free_blocks.erase(it);
+    return OKL_OK;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, r);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    // release the cache and retry once
+    for (auto& kv : ctx->free_blocks) {
+      cudaFree(kv.second);
+      ctx->live.erase(kv.second);
+    }
+    ctx->free_blocks.clear();
+    e = cudaMalloc(&p, r);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    okl_set_error("okl_malloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? OKL_ERR_OOM : OKL_ERR_CUDA;
+  }
+  ctx->live[p] = r;
+  *out = p;
+  return OKL_OK;
+}
+
+extern "C" int okl_free(okl_ctx* ctx, void* p) {
+  if (!p) return OKL_OK;
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto it = ctx->live.find(p);
+  OKL_REQUIRE(it != ctx->live.end(), "okl_free: %p was not returned by okl_malloc", p);
+  // stream-ordered reuse: every consumer runs on ctx->stream (the comm stream is joined before reuse)
+  ctx->free_blocks.emplace(it->second, p);
+  return OKL_OK;
+}
+
+extern "C" int okl_pool_reserve(okl_ctx* ctx, size_t bytes) {
+  void* p = nullptr;
+  int s = okl_malloc(ctx, bytes, &p);
+  if (s != OKL_OK) return s;
+  return okl_free(ctx, p);
+}
+
+int okl_ensure_workspace(okl_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->workspace_bytes) return OKL_OK;
+  if (ctx->capturing) {
+    okl_set_error("workspace of %zu bytes needed during graph capture but only %zu reserved (run one eager step first)",
+                  bytes, ctx->workspace_bytes);
+    return OKL_ERR_INVALID;
+  }
+  OKL_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->workspace) cudaFree(ctx->workspace);
+  size_t nb = round_size(bytes + bytes / 4);
+  OKL_CHECK_CUDA(cudaMalloc(&ctx->workspace, nb));
+  ctx->workspace_bytes = nb;
+  return OKL_OK;
+}
+
+int okl_ensure_staging(okl_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->staging_bytes) return OKL_OK;
+  OKL_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->staging) cudaFree(ctx->staging);
+  size_t nb = round_size(bytes);
+  OKL_CHECK_CUDA(cudaMalloc(&ctx->staging, nb));
+  ctx->staging_bytes = nb;
+  return OKL_OK;
+}
+
+extern "C" int okl_memset(okl_ctx* ctx, void* p, int byte, size_t bytes) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  if (bytes == 0) return OKL_OK;
+  OKL_CHECK_CUDA(cudaMemsetAsync(p, byte, bytes, ctx->stream));
+  return OKL_OK;
+}
+
+extern "C" int okl_pinned_alloc(size_t bytes, void** out) {
+  OKL_REQUIRE(out, "out is NULL");
+  OKL_CHECK_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+  return OKL_OK;
+}
+
+extern "C" int okl_pinned_free(void* p) {
+  if (p) OKL_CHECK_CUDA(cudaFreeHost(p));
+  return OKL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// transfers with on-device dtype conversion
+// ------------------------------------------------------------------------------------------------
+template <typename S, typename D>
+__global__ void convert_kernel(const S* __restrict__ src, D* __restrict__ dst, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = (D)src[i];
+}
+
+static size_t dtype_size(int dt) {
+  switch (dt) {
+    case OKL_F32: return 4;
+    case OKL_F64: return 8;
+    case OKL_I64: return 8;
+    case OKL_I32: return 4;
+    case OKL_U8: return 1;
+  }
+  return 0;
+}
+
+template <typename D>
+static int h2d_convert(okl_ctx* ctx, D* dst, const void* host, size_t n, int src_dtype, bool dst_is_same_raw) {
+  size_t es = dtype_size(src_dtype);
+  OKL_REQUIRE(es != 0, "bad src dtype %d", src_dtype);
+  if (n == 0) return OKL_OK;
+  if (dst_is_same_raw) {
+    OKL_CHECK_CUDA(cudaMemcpyAsync(dst, host, n * es, cudaMemcpyHostToDevice, ctx->stream));
+    OKL_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));   // host buffer is borrowed for this call only
+    return OKL_OK;
+  }
+  int s = okl_ensure_staging(ctx, n * es);
+  if (s != OKL_OK) return s;
+  OKL_CHECK_CUDA(cudaMemcpyAsync(ctx->staging, host, n * es, cudaMemcpyHostToDevice, ctx->stream));
+  int grid = okl_grid_1d(ctx, n, 256);
+  switch (src_dtype) {
+    case OKL_F32: convert_kernel<float, D><<<grid, 256, 0, ctx->stream>>>((const float*)ctx->staging, dst, n); break;
+    case OKL_F64: convert_kernel<double, D><<<grid, 256, 0, ctx->stream>>>((const double*)ctx->staging, dst, n); break;
+    case OKL_I64: convert_kernel<long long, D><<<grid, 256, 0, ctx->stream>>>((const long long*)ctx->staging, dst, n); break;
+    case OKL_I32: convert_kernel<int, D><<<grid, 256, 0, ctx->stream>>>((const int*)ctx->staging, dst, n); break;
+    case OKL_U8: convert_kernel<unsigned char, D><<<grid, 256, 0, ctx->stream>>>((const unsigned char*)ctx->staging, dst, n); break;
+  }
+  OKL_LAUNCHED(ctx, "convert_kernel");
+  OKL_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return OKL_OK;
+}
+
+extern "C" int okl_h2d(okl_ctx* ctx, void* dst_f32, const void* host, size_t n, int src_dtype) {
+  OKL_REQUIRE(ctx && (n == 0 || (dst_f32 && host)), "NULL argument");
+  return h2d_convert<float>(ctx, (float*)dst_f32, host, n, src_dtype, src_dtype == OKL_F32);
+}
+
+extern "C" int okl_h2d_i32(okl_ctx* ctx, void* dst_i32, const void* host, size_t n, int src_dtype) {
+  OKL_REQUIRE(ctx && (n == 0 || (dst_i32 && host)), "NULL argument");
+  return h2d_convert<int>(ctx, (int*)dst_i32, host, n, src_dtype, src_dtype == OKL_I32);
+}
+
+extern "C" int okl_h2d_async_raw(okl_ctx* ctx, void* dst, const void* pinned_host, size_t bytes) {
+  OKL_REQUIRE(ctx && (bytes == 0 || (dst && pinned_host)), "NULL argument");
+  if (bytes) OKL_CHECK_CUDA(cudaMemcpyAsync(dst, pinned_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return OKL_OK;
+}
+
+extern "C" int okl_d2h_async_raw(okl_ctx* ctx, void* pinned_host, const void* src, size_t bytes) {
+  OKL_REQUIRE(ctx && (bytes == 0 || (src && pinned_host)), "NULL argument");
+  if (bytes) OKL_CHECK_CUDA(cudaMemcpyAsync(pinned_host, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return OKL_OK;
+}
+
+extern "C" int okl_d2h(okl_ctx* ctx, void* host, const void* src_f32, size_t n, int dst_dtype) {
+  OKL_REQUIRE(ctx && (n == 0 || (src_f32 && host)), "NULL argument");
+  OKL_REQUIRE(dst_dtype == OKL_F32 || dst_dtype == OKL_F64, "okl_d2h: dst dtype must be F32 or F64");
+  if (n == 0) return OKL_OK;
+  if (ctx->comm_pending) {
+    int s = okl_comm_wait(ctx);
+    if (s != OKL_OK) return s;
+  }
+  if (dst_dtype == OKL_F32) {
+    OKL_CHECK_CUDA(cudaMemcpyAsync(host, src_f32, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    int s = okl_ensure_staging(ctx, n * 8);
+    if (s != OKL_OK) return s;
+    convert_kernel<float, double><<<okl_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>((const float*)src_f32,
+                                                                                   (double*)ctx->staging, n);
+    OKL_LAUNCHED(ctx, "convert_kernel");
+    OKL_CHECK_CUDA(cudaMemcpyAsync(host, ctx->staging, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  OKL_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return OKL_OK;
+}
+
+extern "C" int okl_d2d(okl_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  OKL_REQUIRE(ctx && (bytes == 0 || (dst && src)), "NULL argument");
+  if (bytes) OKL_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return OKL_OK;
+}
+
+extern "C" int okl_read_scalar(okl_ctx* ctx, const void* dev_f32, float* out) {
+  OKL_REQUIRE(ctx && dev_f32 && out, "NULL argument");
+  OKL_CHECK_CUDA(cudaMemcpyAsync(out, dev_f32, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  OKL_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return OKL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA graphs
+// ------------------------------------------------------------------------------------------------
+extern "C" int okl_graph_begin(okl_ctx* ctx) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  OKL_REQUIRE(!ctx->capturing, "okl_graph_begin: already capturing");
+  OKL_CHECK_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+  ctx->capturing = true;
+  ctx->capture_launches = 0;
+  return OKL_OK;
+}
+
+extern "C" int okl_graph_end(okl_ctx* ctx, okl_graph** out) {
+  OKL_REQUIRE(ctx && out, "NULL argument");
+  OKL_REQUIRE(ctx->capturing, "okl_graph_end: not capturing");
+  if (ctx->comm_pending) {                         // join the comm stream back before ending the capture
+    int s = okl_comm_wait(ctx);
+    if (s != OKL_OK) return s;
+  }
+  ctx->capturing = false;
+  okl_graph* g = new okl_graph();
+  cudaError_t e = cudaStreamEndCapture(ctx->stream, &g->graph);
+  if (e != cudaSuccess) {
+    okl_set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    delete g;
+    return OKL_ERR_CUDA;
+  }
+  e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+  if (e != cudaSuccess) {
+    okl_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    cudaGraphDestroy(g->graph);
+    delete g;
+    return OKL_ERR_CUDA;
+  }
+  g->launches = ctx->capture_launches;
+  *out = g;
+  return OKL_OK;
+}
+
+extern "C" int okl_graph_launch(okl_ctx* ctx, okl_graph* g) {
+  OKL_REQUIRE(ctx && g && g->exec, "NULL argument");
+  OKL_CHECK_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+  ctx->launches += g->launches;
+  return OKL_OK;
+}
+
+extern "C" int okl_graph_destroy(okl_graph* g) {
+  if (!g) return OKL_OK;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+  return OKL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// timing
+// ------------------------------------------------------------------------------------------------
+extern "C" int okl_timer_start(okl_ctx* ctx) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+  return OKL_OK;
+}
+
+extern "C" int okl_timer_stop(okl_ctx* ctx, float* ms) {
+  OKL_REQUIRE(ctx && ms, "NULL argument");
+  if (ctx->comm_pending) {
+    int s = okl_comm_wait(ctx);
+    if (s != OKL_OK) return s;
+  }
+  OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_t1, ctx->stream));
+  OKL_CHECK_CUDA(cudaEventSynchronize(ctx->ev_t1));
+  OKL_CHECK_CUDA(cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));
+  return OKL_OK;
+}
+
+__global__ void flush_kernel(float4* __restrict__ p, size_t n4, float v) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) p[i] = make_float4(v, v, v, v);
+}
+
+extern "C" int okl_flush_l2(okl_ctx* ctx) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  if (!ctx->flush_buf) {
+    ctx->flush_bytes = (size_t)256 << 20;   // 256 MiB > 126 MB L2
+    OKL_CHECK_CUDA(cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
+  }
+  flush_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((float4*)ctx->flush_buf, ctx->flush_bytes / 16, 1.0f);
+  cudaError_t e = cudaPeekAtLastError();          // not counted: not part of the product path
+  if (e != cudaSuccess) {
+    okl_set_error("flush kernel: %s", cudaGetErrorString(e));
+    return OKL_ERR_CUDA;
+  }
+  return OKL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL (resolved with dlopen so the library loads on machines without NCCL; one rank per process)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+
+void load_nccl() {
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.handle) break;
+  }
+  if (!g_nccl.handle) return;
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.handle, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.handle, "ncclCommInitRank");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.handle, "ncclCommDestroy");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.handle, "ncclAllReduce");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.handle, "ncclGetErrorString");
+  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce && g_nccl.GetErrorString;
+}
+
+int need_nccl() {
+  std::call_once(g_nccl_once, load_nccl);
+  if (!g_nccl.ok) {
+    okl_set_error("NCCL (libnccl.so.2) could not be loaded: %s", dlerror() ? dlerror() : "missing symbols");
+    return OKL_ERR_NCCL;
+  }
+  return OKL_OK;
+}
+}  // namespace
+
+#define OKL_CHECK_NCCL(expr)                                                              \
+  do {                                                                                    \
+    ncclResult_t _r = (expr);                                                             \
+    if (_r != ncclSuccess) {                                                              \
+      okl_set_error("%s failed: %s", #expr, g_nccl.GetErrorString(_r));                   \
+      return OKL_ERR_NCCL;                                                                \
+    }                                                                                     \
+  } while (0)
+
+extern "C" int okl_comm_unique_id(void* out128) {
+  OKL_REQUIRE(out128, "out128 is NULL");
+  int s = need_nccl();
+  if (s != OKL_OK) return s;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  OKL_CHECK_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(out128, &id, 128);
+  return OKL_OK;
+}
+
+extern "C" int okl_comm_init(okl_ctx* ctx, const void* id128, int rank, int nranks) {
+  OKL_REQUIRE(ctx && id128, "NULL argument");
+  OKL_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank %d / nranks %d", rank, nranks);
+  int s = need_nccl();
+  if (s != OKL_OK) return s;
+  OKL_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  ncclComm_t comm;
+  OKL_CHECK_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+  ctx->nccl_comm = comm;
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  return OKL_OK;
+}
+
+extern "C" int okl_comm_destroy(okl_ctx* ctx) {
+  if (ctx && ctx->nccl_comm && g_nccl.ok) {
+    g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+    ctx->nranks = 1;
+  }
+  return OKL_OK;
+}
+
+extern "C" int okl_allreduce_async(okl_ctx* ctx, void* p, size_t count) {
+  OKL_REQUIRE(ctx && p, "NULL argument");
+  if (ctx->nranks == 1 || count == 0) return OKL_OK;
+  OKL_REQUIRE(ctx->nccl_comm, "okl_allreduce_async: communicator not initialised");
+  // fork: comm stream waits for everything enqueued so far on the compute stream (works under capture too)
+  OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  OKL_CHECK_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_fork, 0));
+  OKL_CHECK_NCCL(g_nccl.AllReduce(p, p, count, ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->comm_stream));
+  ctx->comm_pending = true;
+  return OKL_OK;
+}
+
+extern "C" int okl_comm_wait(okl_ctx* ctx) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  if (!ctx->comm_pending) return OKL_OK;
+  OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_join, ctx->comm_stream));
+  OKL_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  ctx->comm_pending = false;
+  return OKL_OK;
+}
+
+extern "C" int okl_allreduce_max_host(okl_ctx* ctx, double* value) {
+  OKL_REQUIRE(ctx && value, "NULL argument");
+  if (ctx->nranks == 1) return OKL_OK;
+  OKL_REQUIRE(ctx->nccl_comm, "communicator not initialised");
+  double* d = nullptr;
+  int s = okl_malloc(ctx, sizeof(double), (void**)&d);
+  if (s != OKL_OK) return s;
+  OKL_CHECK_CUDA(cudaMemcpyAsync(d, value, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  OKL_CHECK_NCCL(g_nccl.AllReduce(d, d, 1, ncclFloat64, ncclMax, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  OKL_CHECK_CUDA(cudaMemcpyAsync(value, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  OKL_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return okl_free(ctx, d);
+}
+
+extern "C" int okl_barrier(okl_ctx* ctx) {
+  double v = 0.0;
+  int s = okl_ctx_sync(ctx);
+  if (s != OKL_OK) return s;
+  return okl_allreduce_max_host(ctx, &v);
+}

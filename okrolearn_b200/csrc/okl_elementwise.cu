@@ -1,0 +1,557 @@
+// Memory-bound kernels of the train step: activations, pooling, softmax, losses, bias-gradient reductions, layout
+// permutation, dataset gather and the parameter updates.  All are coalesced along the contiguous dimension, use
+// 128-bit accesses where alignment allows, grid-stride over a grid capped at a few waves of the 148 SMs, and
+// reduce with warp shuffles in a fixed order (deterministic).  Reference citations per entry point are in okl.h.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float act_f(float v, int act) {
+  switch (act) {
+    case OKL_ACT_RELU: return v > 0.f ? v : 0.f;                       // okl.py:103  max(0, x)
+    case OKL_ACT_SIGMOID: return 1.f / (1.f + expf(-v));               // okl.py:509
+    case OKL_ACT_TANH: return tanhf(v);                                // okl.py:2088
+    default: return v;
+  }
+}
+__device__ __forceinline__ float act_b(float ref, float g, int act) {
+  switch (act) {
+    case OKL_ACT_RELU: return ref > 0.f ? g : 0.f;                     // okl.py:107  g * (x > 0)
+    case OKL_ACT_SIGMOID: return g * (ref * (1.f - ref));              // okl.py:514  ref = y
+    case OKL_ACT_TANH: { float t = tanhf(ref); return g * (1.f - t * t); }   // okl.py:2092 ref = x
+    default: return g;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// sum over the block; result valid in every thread.  blockDim.x multiple of 32, <= 1024.
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = l < nw ? sh[l] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ------------------------------------------------------------------------------------------------ activations
+template <bool VEC>
+__global__ void act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, int act) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  if (VEC) {
+    size_t n4 = n >> 2;
+    for (size_t j = i; j < n4; j += st) {
+      float4 v = reinterpret_cast<const float4*>(x)[j];
+      v.x = act_f(v.x, act); v.y = act_f(v.y, act); v.z = act_f(v.z, act); v.w = act_f(v.w, act);
+      reinterpret_cast<float4*>(y)[j] = v;
+    }
+    for (size_t j = (n4 << 2) + i; j < n; j += st) y[j] = act_f(x[j], act);
+  } else {
+    for (; i < n; i += st) y[i] = act_f(x[i], act);
+  }
+}
+template <bool VEC>
+__global__ void act_bwd_kernel(const float* __restrict__ ref, const float* __restrict__ g, float* __restrict__ dx, size_t n, int act) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  if (VEC) {
+    size_t n4 = n >> 2;
+    for (size_t j = i; j < n4; j += st) {
+      float4 r = reinterpret_cast<const float4*>(ref)[j], q = reinterpret_cast<const float4*>(g)[j], o;
+      o.x = act_b(r.x, q.x, act); o.y = act_b(r.y, q.y, act); o.z = act_b(r.z, q.z, act); o.w = act_b(r.w, q.w, act);
+      reinterpret_cast<float4*>(dx)[j] = o;
+    }
+    for (size_t j = (n4 << 2) + i; j < n; j += st) dx[j] = act_b(ref[j], g[j], act);
+  } else {
+    for (; i < n; i += st) dx[i] = act_b(ref[i], g[i], act);
+  }
+}
+__global__ void binary_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, size_t n, size_t nb, int op) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) {
+    float bv = b[nb == n ? i : i % nb];
+    o[i] = op == 0 ? a[i] + bv : a[i] * bv;
+  }
+}
+__global__ void scale_kernel(float* __restrict__ x, size_t n, float a) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) x[i] *= a;
+}
+
+// ------------------------------------------------------------------------------------------------ permute / gather
+// per image: src is (R x Cc) row-major, dst is (Cc x R) row-major
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, long long Cc) {
+  __shared__ float tile[32][33];
+  const float* s = src + (size_t)blockIdx.z * R * Cc;
+  float* d = dst + (size_t)blockIdx.z * R * Cc;
+  long long c0 = (long long)blockIdx.x * 32;
+  int r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int r = r0 + j; long long c = c0 + threadIdx.x;
+    if (r < R && c < Cc) tile[j][threadIdx.x] = s[(size_t)r * Cc + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    long long c = c0 + j; int r = r0 + threadIdx.x;
+    if (r < R && c < Cc) d[(size_t)c * R + r] = tile[threadIdx.x][j];
+  }
+}
+__global__ void gather_rows_kernel(float* __restrict__ dst, const float* __restrict__ src, const int* __restrict__ idx,
+                                   long long rows, long long row_elems) {
+  size_t total = (size_t)rows * row_elems;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i / row_elems, c = i - r * row_elems;
+    dst[i] = src[(size_t)idx[r] * row_elems + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pooling
+struct PoolGeom { int N, C, H, W, OH, OW, ps, st; long long xs[4], ys[4]; bool cl; };   // strides for (n,c,h,w)
+
+__device__ __forceinline__ void pool_decomp(size_t i, int C, int H, int W, bool cl, int& n, int& c, int& h, int& w) {
+  if (cl) { c = (int)(i % C); i /= C; w = (int)(i % W); i /= W; h = (int)(i % H); n = (int)(i / H); }
+  else { w = (int)(i % W); i /= W; h = (int)(i % H); i /= H; c = (int)(i % C); n = (int)(i / C); }
+}
+
+__global__ void pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, PoolGeom g, int kind) {
+  size_t total = (size_t)g.N * g.C * g.OH * g.OW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int n, c, oh, ow;
+    pool_decomp(i, g.C, g.OH, g.OW, g.cl, n, c, oh, ow);
+    const float* base = x + n * g.xs[0] + c * g.xs[1] + (long long)(oh * g.st) * g.xs[2] + (long long)(ow * g.st) * g.xs[3];
+    float acc = kind == OKL_POOL_MAX ? -INFINITY : 0.f;
+    for (int a = 0; a < g.ps; a++)
+      for (int b = 0; b < g.ps; b++) {
+        float v = __ldg(base + a * g.xs[2] + b * g.xs[3]);
+        acc = kind == OKL_POOL_MAX ? fmaxf(acc, v) : acc + v;
+      }
+    if (kind == OKL_POOL_AVG) acc /= (float)(g.ps * g.ps);            // np.mean, okl.py:1803
+    y[i] = acc;                                                        // y is dense in its layout order
+  }
+}
+
+// Gather form of okl.py:1753-1766 [R4] / 1809-1819 [R5]: each input position looks at the windows that contain it,
+// in the reference's raster order (i then j).  Max: the last window whose max equals x assigns its gradient
+// (ties -> every maximum of a window receives it; overlapping windows overwrite).  Avg: contributions add.
+__global__ void pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gr, float* __restrict__ dx, PoolGeom g, int kind) {
+  size_t total = (size_t)g.N * g.C * g.H * g.W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int n, c, h, w;
+    pool_decomp(i, g.C, g.H, g.W, g.cl, n, c, h, w);
+    int i_lo = h - g.ps + 1 <= 0 ? 0 : (h - g.ps + 1 + g.st - 1) / g.st, i_hi = min(h / g.st, g.OH - 1);
+    int j_lo = w - g.ps + 1 <= 0 ? 0 : (w - g.ps + 1 + g.st - 1) / g.st, j_hi = min(w / g.st, g.OW - 1);
+    const float* xb = x + n * g.xs[0] + c * g.xs[1];
+    const float* gb = gr + n * g.ys[0] + c * g.ys[1];
+    float out = 0.f;
+    if (kind == OKL_POOL_AVG) {
+      for (int oi = i_lo; oi <= i_hi; oi++)
+        for (int oj = j_lo; oj <= j_hi; oj++) out += __ldg(gb + oi * g.ys[2] + oj * g.ys[3]) / (float)(g.ps * g.ps);
+    } else {
+      float xv = __ldg(xb + h * g.xs[2] + w * g.xs[3]);
+      for (int oi = i_lo; oi <= i_hi; oi++)
+        for (int oj = j_lo; oj <= j_hi; oj++) {
+          const float* wb = xb + (long long)(oi * g.st) * g.xs[2] + (long long)(oj * g.st) * g.xs[3];
+          float m = -INFINITY;
+          for (int a = 0; a < g.ps; a++)
+            for (int b = 0; b < g.ps; b++) m = fmaxf(m, __ldg(wb + a * g.xs[2] + b * g.xs[3]));
+          if (xv == m) out = __ldg(gb + oi * g.ys[2] + oj * g.ys[3]);
+        }
+    }
+    dx[i] = out;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ softmax / losses
+// one warp per row
+__global__ void softmax_fwd_kernel(const float* __restrict__ x, float* __restrict__ p, int rows, int cols) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < rows; r += nwarps) {
+    const float* xr = x + (size_t)r * cols;
+    float m = -INFINITY;
+    for (int c = lane; c < cols; c += 32) m = fmaxf(m, xr[c]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s += expf(xr[c] - m);
+    s = warp_sum(s);
+    for (int c = lane; c < cols; c += 32) {
+      float v = expf(xr[c] - m) / s;
+      if (isnan(v)) v = 0.f;                                           // np.nan_to_num, okl.py:370
+      p[(size_t)r * cols + c] = v;
+    }
+  }
+}
+// dx = p * (g - sum_k g_k p_k)    == einsum('ijk,ik->ij', J, g) of okl.py:376-393
+__global__ void softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ g, float* __restrict__ dx, int rows, int cols) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < rows; r += nwarps) {
+    const float* pr = p + (size_t)r * cols;
+    const float* gr = g + (size_t)r * cols;
+    float d = 0.f;
+    for (int c = lane; c < cols; c += 32) d += gr[c] * pr[c];
+    d = warp_sum(d);
+    for (int c = lane; c < cols; c += 32) dx[(size_t)r * cols + c] = pr[c] * (gr[c] - d);
+  }
+}
+
+__device__ __forceinline__ float clip_p(float v) {
+  // np.clip(p, 1e-12, 1 - 1e-12) (okl.py:1391); in fp32 the upper bound rounds to 1.0f
+  return fminf(fmaxf(v, 1e-12f), 1.0f);
+}
+// grad over the whole grid; block 0 additionally reduces the loss (rows is at most a few thousand per step)
+__global__ void ce_kernel(const float* __restrict__ p, const int* __restrict__ t, float* __restrict__ loss, float* __restrict__ grad,
+                          int rows, int cols, float inv_denom) {
+  __shared__ float sh[32];
+  size_t total = (size_t)rows * cols;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / cols), c = (int)(i - (size_t)r * cols);
+    float v = clip_p(p[i]);
+    if (c == t[r]) v -= 1.f;
+    grad[i] = v * inv_denom;
+  }
+  if (blockIdx.x == 0) {
+    float s = 0.f;
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+      int tc = t[r];
+      float v = (tc >= 0 && tc < cols) ? clip_p(p[(size_t)r * cols + tc]) : 1.f;
+      s += -logf(v);
+    }
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) loss[0] = rows > 0 ? s / (float)rows : 0.f;
+  }
+}
+
+__global__ void mse_kernel(const float* __restrict__ o, const float* __restrict__ t, float* __restrict__ partial, float* __restrict__ grad,
+                           size_t n, float scale) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float d = o[i] - t[i];
+    s += d * d;
+    grad[i] = d * scale;                                               // 2 (o - t) / denom, okl.py:1838
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+__global__ void final_sum_kernel(const float* __restrict__ partial, int count, float* __restrict__ out, float scale) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) s += partial[i];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) out[0] = s * scale;
+}
+
+// ------------------------------------------------------------------------------------------------ reductions for bias gradients
+// stage 1: partial[chunk][c] = sum over the chunk's rows of G[r, c]  (G row-major rows x cols); 32 cols x 8 row-lanes per block
+__global__ void colsum_stage1(const float* __restrict__ G, float* __restrict__ partial, long long rows, int cols, long long rows_per_chunk) {
+  __shared__ float sh[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  long long r0 = (long long)blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+  float s = 0.f;
+  if (c < cols)
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) s += G[(size_t)r * cols + c];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) a += sh[j][threadIdx.x];
+    partial[(size_t)blockIdx.y * cols + c] = a;
+  }
+}
+// stage 1 for channels-first (N, C, S): partial[chunk][c] = sum_{n in chunk, s} g[n, c, s]
+__global__ void chansum_stage1(const float* __restrict__ g, float* __restrict__ partial, int N, int C, long long S, int n_per_chunk) {
+  __shared__ float sh[32];
+  int c = blockIdx.x;
+  int n0 = blockIdx.y * n_per_chunk, n1 = min(N, n0 + n_per_chunk);
+  float s = 0.f;
+  for (int n = n0; n < n1; n++) {
+    const float* b = g + ((size_t)n * C + c) * S;
+    for (long long i = threadIdx.x; i < S; i += blockDim.x) s += b[i];
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) partial[(size_t)blockIdx.y * C + c] = s;
+}
+__global__ void colsum_stage2(const float* __restrict__ partial, float* __restrict__ out, int chunks, int cols) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int k = 0; k < chunks; k++) s += partial[(size_t)k * cols + c];
+  out[c] = s;
+}
+
+// ------------------------------------------------------------------------------------------------ parameter updates
+template <bool VEC>
+__global__ void accum_update_kernel(float* __restrict__ w, float* __restrict__ gacc, const float* __restrict__ g, size_t n, float lr,
+                                    const float* __restrict__ lr_dev) {
+  if (lr_dev) lr = __ldg(lr_dev);
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  if (VEC) {
+    size_t n4 = n >> 2;
+    for (size_t j = i; j < n4; j += st) {
+      float4 a = reinterpret_cast<float4*>(gacc)[j], q = reinterpret_cast<const float4*>(g)[j], ww = reinterpret_cast<float4*>(w)[j];
+      a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;                   // grad = grad + g      okl.py:39
+      ww.x -= lr * a.x; ww.y -= lr * a.y; ww.z -= lr * a.z; ww.w -= lr * a.w;   // w -= lr * grad   okl.py:44
+      reinterpret_cast<float4*>(gacc)[j] = a;
+      reinterpret_cast<float4*>(w)[j] = ww;
+    }
+    for (size_t j = (n4 << 2) + i; j < n; j += st) { float a = gacc[j] + g[j]; gacc[j] = a; w[j] -= lr * a; }
+  } else {
+    for (; i < n; i += st) { float a = gacc[i] + g[i]; gacc[i] = a; w[i] -= lr * a; }
+  }
+}
+__global__ void sgd_kernel(float* __restrict__ w, float* __restrict__ v, const float* __restrict__ g, size_t n, float lr, float mu) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) { float nv = mu * v[i] - lr * g[i]; v[i] = nv; w[i] += nv; }   // optimizers.py:143-144
+}
+__global__ void adam_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g, size_t n,
+                            float lr, float b1, float b2, float eps, float c1, float c2) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) {
+    float gi = g[i];
+    float mi = b1 * m[i] + (1.f - b1) * gi;                             // optimizers.py:35
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;                        // optimizers.py:36
+    m[i] = mi; v[i] = vi;
+    float mh = mi / c1, vh = vi / c2;                                   // optimizers.py:38-39
+    w[i] -= lr * mh / (sqrtf(vh) + eps);                                // optimizers.py:41-42
+  }
+}
+
+}  // namespace
+
+// ================================================================================================ entry points
+extern "C" int okl_act_fwd(okl_ctx* ctx, int act, const void* x, void* y, size_t n) {
+  OKL_REQUIRE(ctx && (n == 0 || (x && y)), "NULL argument");
+  OKL_REQUIRE(act >= OKL_ACT_NONE && act <= OKL_ACT_TANH, "bad activation %d", act);
+  if (n == 0) return OKL_OK;
+  bool vec = aligned16(x) && aligned16(y);
+  int grid = okl_grid_1d(ctx, vec ? (n + 3) / 4 : n, 256);
+  if (vec) act_fwd_kernel<true><<<grid, 256, 0, ctx->stream>>>((const float*)x, (float*)y, n, act);
+  else act_fwd_kernel<false><<<grid, 256, 0, ctx->stream>>>((const float*)x, (float*)y, n, act);
+  OKL_LAUNCHED(ctx, "act_fwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_act_bwd(okl_ctx* ctx, int act, const void* ref, const void* g, void* dx, size_t n) {
+  OKL_REQUIRE(ctx && (n == 0 || (ref && g && dx)), "NULL argument");
+  OKL_REQUIRE(act >= OKL_ACT_NONE && act <= OKL_ACT_TANH, "bad activation %d", act);
+  if (n == 0) return OKL_OK;
+  bool vec = aligned16(ref) && aligned16(g) && aligned16(dx);
+  int grid = okl_grid_1d(ctx, vec ? (n + 3) / 4 : n, 256);
+  if (vec) act_bwd_kernel<true><<<grid, 256, 0, ctx->stream>>>((const float*)ref, (const float*)g, (float*)dx, n, act);
+  else act_bwd_kernel<false><<<grid, 256, 0, ctx->stream>>>((const float*)ref, (const float*)g, (float*)dx, n, act);
+  OKL_LAUNCHED(ctx, "act_bwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_binary(okl_ctx* ctx, int op, const void* a, const void* b, void* out, size_t n, size_t nb) {
+  OKL_REQUIRE(ctx && (n == 0 || (a && b && out)), "NULL argument");
+  OKL_REQUIRE(op == 0 || op == 1, "bad binary op %d", op);
+  OKL_REQUIRE(n == 0 || (nb >= 1 && nb <= n), "bad broadcast length");
+  if (n == 0) return OKL_OK;
+  binary_kernel<<<okl_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>((const float*)a, (const float*)b, (float*)out, n, nb, op);
+  OKL_LAUNCHED(ctx, "binary");
+  return OKL_OK;
+}
+
+extern "C" int okl_scale(okl_ctx* ctx, void* x, size_t n, float alpha) {
+  OKL_REQUIRE(ctx && (n == 0 || x), "NULL argument");
+  if (n == 0) return OKL_OK;
+  scale_kernel<<<okl_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>((float*)x, n, alpha);
+  OKL_LAUNCHED(ctx, "scale");
+  return OKL_OK;
+}
+
+extern "C" int okl_permute(okl_ctx* ctx, void* dst, const void* src, int N, int C, long long S, int src_layout) {
+  OKL_REQUIRE(ctx && dst && src, "NULL argument");
+  OKL_REQUIRE(src_layout == OKL_NCX || src_layout == OKL_NXC, "bad layout");
+  if (N <= 0 || C <= 0 || S <= 0) return OKL_OK;
+  if (C == 1 || S == 1) return okl_d2d(ctx, dst, src, (size_t)N * C * S * sizeof(float));
+  OKL_REQUIRE(N <= 65535, "okl_permute: N > 65535");
+  // NCX -> NXC: per image (C x S) -> (S x C);  NXC -> NCX: (S x C) -> (C x S)
+  int R = src_layout == OKL_NCX ? C : 0;
+  long long Cc = src_layout == OKL_NCX ? S : C;
+  long long Rl = src_layout == OKL_NCX ? C : S;
+  OKL_REQUIRE(Rl < (1LL << 31), "okl_permute: dimension too large");
+  R = (int)Rl;
+  dim3 grid((unsigned)((Cc + 31) / 32), (unsigned)((R + 31) / 32), N);
+  OKL_REQUIRE(grid.y <= 65535, "okl_permute: too many row tiles");
+  transpose_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>((const float*)src, (float*)dst, R, Cc);
+  OKL_LAUNCHED(ctx, "permute");
+  return OKL_OK;
+}
+
+extern "C" int okl_gather_rows(okl_ctx* ctx, void* dst, const void* src, const void* idx, long long rows, long long row_elems) {
+  OKL_REQUIRE(ctx && (rows == 0 || (dst && src && idx)), "NULL argument");
+  if (rows <= 0 || row_elems <= 0) return OKL_OK;
+  gather_rows_kernel<<<okl_grid_1d(ctx, (size_t)rows * row_elems, 256), 256, 0, ctx->stream>>>((float*)dst, (const float*)src,
+                                                                                           (const int*)idx, rows, row_elems);
+  OKL_LAUNCHED(ctx, "gather_rows");
+  return OKL_OK;
+}
+
+static int make_pool_geom(PoolGeom& g, int N, int C, int H, int W, int pool, int stride, int layout) {
+  OKL_REQUIRE(N >= 0 && C >= 1 && H >= 1 && W >= 1 && pool >= 1 && stride >= 1, "bad pooling shape");
+  OKL_REQUIRE(H >= pool && W >= pool, "pool window larger than input");
+  OKL_REQUIRE(layout == OKL_NCX || layout == OKL_NXC, "bad layout");
+  g.N = N; g.C = C; g.H = H; g.W = W; g.ps = pool; g.st = stride;
+  g.OH = (H - pool) / stride + 1; g.OW = (W - pool) / stride + 1;       // okl.py:1736-1737
+  g.cl = layout == OKL_NXC;
+  if (!g.cl) {
+    g.xs[0] = (long long)C * H * W; g.xs[1] = (long long)H * W; g.xs[2] = W; g.xs[3] = 1;
+    g.ys[0] = (long long)C * g.OH * g.OW; g.ys[1] = (long long)g.OH * g.OW; g.ys[2] = g.OW; g.ys[3] = 1;
+  } else {
+    g.xs[0] = (long long)C * H * W; g.xs[1] = 1; g.xs[2] = (long long)W * C; g.xs[3] = C;
+    g.ys[0] = (long long)C * g.OH * g.OW; g.ys[1] = 1; g.ys[2] = (long long)g.OW * C; g.ys[3] = C;
+  }
+  return OKL_OK;
+}
+
+extern "C" int okl_pool_fwd(okl_ctx* ctx, int kind, const void* x, void* y, int N, int C, int H, int W, int pool, int stride, int layout) {
+  OKL_REQUIRE(ctx && x && y, "NULL argument");
+  OKL_REQUIRE(kind == OKL_POOL_MAX || kind == OKL_POOL_AVG, "bad pool kind");
+  PoolGeom g;
+  int s = make_pool_geom(g, N, C, H, W, pool, stride, layout);
+  if (s != OKL_OK) return s;
+  size_t total = (size_t)N * C * g.OH * g.OW;
+  if (total == 0) return OKL_OK;
+  pool_fwd_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)x, (float*)y, g, kind);
+  OKL_LAUNCHED(ctx, "pool_fwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_pool_bwd(okl_ctx* ctx, int kind, const void* x, const void* gr, void* dx, int N, int C, int H, int W, int pool,
+                            int stride, int layout) {
+  OKL_REQUIRE(ctx && x && gr && dx, "NULL argument");
+  OKL_REQUIRE(kind == OKL_POOL_MAX || kind == OKL_POOL_AVG, "bad pool kind");
+  PoolGeom g;
+  int s = make_pool_geom(g, N, C, H, W, pool, stride, layout);
+  if (s != OKL_OK) return s;
+  size_t total = (size_t)N * C * H * W;
+  if (total == 0) return OKL_OK;
+  pool_bwd_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)x, (const float*)gr, (float*)dx, g, kind);
+  OKL_LAUNCHED(ctx, "pool_bwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_softmax_fwd(okl_ctx* ctx, const void* x, void* p, int rows, int cols) {
+  OKL_REQUIRE(ctx && (rows == 0 || (x && p)), "NULL argument");
+  OKL_REQUIRE(rows >= 0 && cols >= 1, "bad softmax shape");
+  if (rows == 0) return OKL_OK;
+  softmax_fwd_kernel<<<okl_grid_1d(ctx, (size_t)rows * 32, 256), 256, 0, ctx->stream>>>((const float*)x, (float*)p, rows, cols);
+  OKL_LAUNCHED(ctx, "softmax_fwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_softmax_bwd(okl_ctx* ctx, const void* p, const void* g, void* dx, int rows, int cols) {
+  OKL_REQUIRE(ctx && (rows == 0 || (p && g && dx)), "NULL argument");
+  OKL_REQUIRE(rows >= 0 && cols >= 1, "bad softmax shape");
+  if (rows == 0) return OKL_OK;
+  softmax_bwd_kernel<<<okl_grid_1d(ctx, (size_t)rows * 32, 256), 256, 0, ctx->stream>>>((const float*)p, (const float*)g, (float*)dx,
+                                                                                    rows, cols);
+  OKL_LAUNCHED(ctx, "softmax_bwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_ce_fwd_bwd(okl_ctx* ctx, const void* p, const void* t, void* loss, void* grad, int rows, int cols, float denom) {
+  OKL_REQUIRE(ctx && p && t && loss && grad, "NULL argument");
+  OKL_REQUIRE(rows >= 1 && cols >= 1 && denom > 0.f, "bad cross-entropy shape");
+  ce_kernel<<<okl_grid_1d(ctx, (size_t)rows * cols, 256), 256, 0, ctx->stream>>>((const float*)p, (const int*)t, (float*)loss,
+                                                                             (float*)grad, rows, cols, 1.f / denom);
+  OKL_LAUNCHED(ctx, "ce_fwd_bwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_mse_fwd_bwd(okl_ctx* ctx, const void* o, const void* t, void* loss, void* grad, size_t n, float denom) {
+  OKL_REQUIRE(ctx && o && t && loss && grad, "NULL argument");
+  OKL_REQUIRE(n >= 1 && denom > 0.f, "bad mse shape");
+  int grid = okl_grid_1d(ctx, n, 256, 4);
+  int s = okl_ensure_workspace(ctx, (size_t)grid * sizeof(float));
+  if (s != OKL_OK) return s;
+  mse_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)o, (const float*)t, (float*)ctx->workspace, (float*)grad, n, 2.f / denom);
+  OKL_LAUNCHED(ctx, "mse_fwd_bwd");
+  final_sum_kernel<<<1, 256, 0, ctx->stream>>>((const float*)ctx->workspace, grid, (float*)loss, 1.f / (float)n);
+  OKL_LAUNCHED(ctx, "final_sum");
+  return OKL_OK;
+}
+
+int okl_colsum(okl_ctx* ctx, const float* G, float* out, long long rows, int cols) {
+  if (cols <= 0) return OKL_OK;
+  int col_blocks = (cols + 31) / 32;
+  long long want = (2LL * ctx->sm_count + col_blocks - 1) / col_blocks;
+  long long chunks = rows / 64 < 1 ? 1 : rows / 64;
+  if (chunks > want) chunks = want;
+  if (chunks > 65535) chunks = 65535;
+  long long rpc = (rows + chunks - 1) / chunks;
+  if (rpc < 1) rpc = 1;
+  chunks = rows > 0 ? (rows + rpc - 1) / rpc : 1;
+  int s = okl_ensure_workspace(ctx, (size_t)chunks * cols * sizeof(float));
+  if (s != OKL_OK) return s;
+  colsum_stage1<<<dim3(col_blocks, (unsigned)chunks), dim3(32, 8), 0, ctx->stream>>>(G, (float*)ctx->workspace, rows, cols, rpc);
+  OKL_LAUNCHED(ctx, "colsum_stage1");
+  colsum_stage2<<<(cols + 255) / 256, 256, 0, ctx->stream>>>((const float*)ctx->workspace, out, (int)chunks, cols);
+  OKL_LAUNCHED(ctx, "colsum_stage2");
+  return OKL_OK;
+}
+
+int okl_channel_sum(okl_ctx* ctx, const float* g, float* out, int N, int C, long long S, int layout) {
+  if (layout == OKL_NXC) return okl_colsum(ctx, g, out, (long long)N * S, C);
+  int want = (2 * ctx->sm_count + C - 1) / C;
+  int chunks = N < want ? N : want;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 65535) chunks = 65535;
+  int npc = (N + chunks - 1) / chunks;
+  if (npc < 1) npc = 1;
+  chunks = N > 0 ? (N + npc - 1) / npc : 1;
+  int s = okl_ensure_workspace(ctx, (size_t)chunks * C * sizeof(float));
+  if (s != OKL_OK) return s;
+  chansum_stage1<<<dim3(C, chunks), 256, 0, ctx->stream>>>(g, (float*)ctx->workspace, N, C, S, npc);
+  OKL_LAUNCHED(ctx, "chansum_stage1");
+  colsum_stage2<<<(C + 255) / 256, 256, 0, ctx->stream>>>((const float*)ctx->workspace, out, chunks, C);
+  OKL_LAUNCHED(ctx, "colsum_stage2");
+  return OKL_OK;
+}
+
+extern "C" int okl_accum_update(okl_ctx* ctx, void* w, void* gacc, const void* g, size_t n, float lr, const void* lr_dev) {
+  OKL_REQUIRE(ctx && (n == 0 || (w && gacc && g)), "NULL argument");
+  if (n == 0) return OKL_OK;
+  bool vec = aligned16(w) && aligned16(gacc) && aligned16(g);
+  int grid = okl_grid_1d(ctx, vec ? (n + 3) / 4 : n, 256);
+  if (vec) accum_update_kernel<true><<<grid, 256, 0, ctx->stream>>>((float*)w, (float*)gacc, (const float*)g, n, lr, (const float*)lr_dev);
+  else accum_update_kernel<false><<<grid, 256, 0, ctx->stream>>>((float*)w, (float*)gacc, (const float*)g, n, lr, (const float*)lr_dev);
+  OKL_LAUNCHED(ctx, "accum_update");
+  return OKL_OK;
+}
+
+extern "C" int okl_sgd_update(okl_ctx* ctx, void* w, void* v, const void* g, size_t n, float lr, float momentum) {
+  OKL_REQUIRE(ctx && (n == 0 || (w && v && g)), "NULL argument");
+  if (n == 0) return OKL_OK;
+  sgd_kernel<<<okl_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>((float*)w, (float*)v, (const float*)g, n, lr, momentum);
+  OKL_LAUNCHED(ctx, "sgd_update");
+  return OKL_OK;
+}
+
+extern "C" int okl_adam_update(okl_ctx* ctx, void* w, void* m, void* v, const void* g, size_t n, float lr, float beta1, float beta2,
+                               float eps, int t) {
+  OKL_REQUIRE(ctx && (n == 0 || (w && m && v && g)), "NULL argument");
+  OKL_REQUIRE(t >= 1, "adam step t must be >= 1");
+  if (n == 0) return OKL_OK;
+  float c1 = (float)(1.0 - pow((double)beta1, (double)t)), c2 = (float)(1.0 - pow((double)beta2, (double)t));
+  adam_kernel<<<okl_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>((float*)w, (float*)m, (float*)v, (const float*)g, n, lr, beta1, beta2,
+                                                              eps, c1, c2);
+  OKL_LAUNCHED(ctx, "adam_update");
+  return OKL_OK;
+}

@@ -1,0 +1,559 @@
+"""Layers of the hot path with the reference's names, constructor signatures, attributes and ``forward`` /
+``backward(dL_dout, lr)`` protocol (reference: src/okrolearn/okrolearn.py, cited per class as okl.py:lines).  Every
+``forward``/``backward`` enqueues CUDA kernels through the C ABI (include/okl.h) on device-resident tensors; nothing is
+computed on the host.  Where the shipped reference backward raises ``ValueError`` for every shape (Conv1D/2D/3D, pooling)
+the semantics are those of the repaired loops R1-R5, which is what oracle/okl_oracle.py states.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check, get_ctx, ConvDesc, NCX, NXC, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, POOL_MAX, POOL_AVG
+from .tensor import Tensor, _DevBuf, _numel
+
+_ALIGN = 64          # floats: parameter sub-tensors start on 256-byte boundaries inside a bucket
+
+
+def _as_tensor(x):
+    return x if isinstance(x, Tensor) else Tensor(x)
+
+
+def _lr_args(lr):
+    """(float lr, device pointer or None): a captured CUDA graph reads the learning rate from device memory."""
+    ctx = get_ctx()
+    dev = getattr(ctx, "lr_dev", None)
+    return float(lr), (dev if (ctx.capturing and dev) else None)
+
+
+def _set_input_grad(inputs, dx):
+    """Several reference layers also accumulate dL/dinputs into ``inputs.grad`` (okl.py:110, 751, 1035, 1768, 2094)."""
+    if not inputs.requires_grad:
+        return
+    if inputs._grad is None:
+        inputs._grad = dx
+    else:
+        prev = inputs._grad if isinstance(inputs._grad, Tensor) else Tensor(inputs._grad)
+        inputs._grad = prev + dx
+
+
+class _ParamBucket:
+    """All parameters of one layer in ONE device block (params | gacc | grads share the same offsets), so the layer's
+    gradient exchange is one NCCL allreduce and its update is one kernel.
+
+    The update is the reference's effective rule (okl.py:39-45, 744-748, 872-878, 1029-1033):
+    ``grad = grad + g`` (never reset) ; ``w -= lr * grad``."""
+
+    def __init__(self, tensors):
+        self.tensors = tensors           # list of host-initialised Tensor objects (weights, biases)
+        self.ready = False
+
+    def materialize(self):
+        if self.ready:
+            return
+        ctx = get_ctx()
+        offs, total = [], 0
+        for t in self.tensors:
+            offs.append(total)
+            total += (t.size + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.total = total
+        self.offs = offs
+        self.param = _DevBuf(ctx, total * 4)
+        self.gacc = _DevBuf(ctx, total * 4)
+        self.grad = _DevBuf(ctx, total * 4)
+        for b in (self.param, self.gacc, self.grad):
+            check(lib.okl_memset(ctx.h, b.ptr, 0, total * 4))
+        self.gviews = []
+        for t, off in zip(self.tensors, offs):
+            pending = None if t._dev_valid else t._host
+            t._buf, t._off, t._bound = self.param, off * 4, True
+            t._dev_valid = False if pending is not None else True
+            if pending is not None:
+                t._upload()
+            self.gviews.append(Tensor._view(self.gacc, off * 4, t._shape, t._np_dtype))
+        self.ready = True
+
+    def ptr(self, i):
+        """Device pointer of parameter i (re-uploading if the user assigned ``.data``)."""
+        return self.tensors[i]._dptr(NCX)
+
+    def grad_ptr(self, i):
+        return self.grad.ptr + self.offs[i] * 4
+
+    def _sync_user_grads(self):
+        """``layer.weights.grad = None`` / ``= ndarray`` by the user replaces the accumulator."""
+        ctx = get_ctx()
+        for t, gv, off in zip(self.tensors, self.gviews, self.offs):
+            if t._grad is gv:
+                continue
+            if t._grad is None:
+                if getattr(self, "_stepped", False):
+                    check(lib.okl_memset(ctx.h, self.gacc.ptr + off * 4, 0, t.size * 4))
+            else:
+                arr = np.ascontiguousarray(np.asarray(t._grad, dtype=np.float64).reshape(-1))
+                if arr.size != t.size:
+                    raise ValueError("assigned .grad has the wrong number of elements")
+                check(lib.okl_h2d(ctx.h, self.gacc.ptr + off * 4, arr.ctypes.data, arr.size, _lib.F64))
+            gv._touch()
+
+    def step(self, lr, deferred=False):
+        """Exchange (data parallel) and apply the accumulated-gradient update for the whole bucket."""
+        ctx = get_ctx()
+        self._sync_user_grads()
+        if ctx.nranks > 1:
+            check(lib.okl_allreduce_async(ctx.h, self.grad.ptr, self.total))
+        if deferred:
+            self._pending_lr = lr
+            return
+        self.apply(lr)
+
+    def apply(self, lr):
+        ctx = get_ctx()
+        if ctx.nranks > 1:
+            check(lib.okl_comm_wait(ctx.h))
+        lrf, lrp = _lr_args(lr)
+        for t in self.tensors:
+            t._dptr(NCX)                         # flush a pending host-side assignment before updating in place
+        check(lib.okl_accum_update(ctx.h, self.param.ptr, self.gacc.ptr, self.grad.ptr, self.total, lrf, lrp))
+        self._stepped = True
+        for t, gv in zip(self.tensors, self.gviews):
+            t._touch()
+            gv._touch()
+            t._grad = gv
+        self._pending_lr = None
+
+
+class _ParamLayer:
+    _defer_update = False          # set by NeuralNetwork when updates are applied after the whole backward (DP overlap)
+    _fused_act = ACT_NONE          # set by NeuralNetwork's planner: activation fused into this layer's epilogue
+
+    def _finish_update(self):
+        b = self._bucket
+        if getattr(b, "_pending_lr", None) is not None:
+            b.apply(b._pending_lr)
+
+
+# ====================================================================================================== Dense
+class DenseLayer(_ParamLayer):
+    """okl.py:18-54.  weights (in,out) = randn*0.1 float64, biases (1,out) zeros; Y = X.W + b;
+    backward: dW = X^T.G, db = sum_rows G, dX = G.W^T (pre-update W), then the in-layer accumulated update."""
+
+    def __init__(self, input_size, output_size):
+        self.weights = Tensor(np.random.randn(input_size, output_size) * 0.1)
+        self.biases = Tensor(np.zeros((1, output_size)))
+        self._bucket = _ParamBucket([self.weights, self.biases])
+
+    def forward(self, inputs: Tensor):
+        inputs = _as_tensor(inputs)
+        ctx = get_ctx()
+        self._bucket.materialize()
+        K, N = self.weights.shape
+        if inputs.ndim != 2 or inputs.shape[1] != K:
+            raise ValueError(f"shapes {inputs.shape} and {self.weights.shape} not aligned")
+        self.inputs = inputs
+        M = inputs.shape[0]
+        out = Tensor._empty((M, N), np.float64)
+        check(lib.okl_dense_fwd(ctx.h, inputs._dptr(NCX), self._bucket.ptr(0), self._bucket.ptr(1), out._ptr_raw(), M, K, N,
+                                self._fused_act))
+        self.outputs = out
+        return out
+
+    def backward(self, dL_dout: Tensor, lr: float):
+        dL_dout = _as_tensor(dL_dout)
+        ctx = get_ctx()
+        K, N = self.weights.shape
+        M = self.inputs.shape[0]
+        if dL_dout.shape != (M, N):
+            raise ValueError(f"dL_dout shape {dL_dout.shape} does not match the layer output {(M, N)}")
+        need_dx = getattr(self, "_need_dx", True)
+        dX = Tensor._empty((M, K), np.float64) if need_dx else None
+        b = self._bucket
+        check(lib.okl_dense_bwd(ctx.h, self.inputs._dptr(NCX), b.ptr(0), dL_dout._dptr(NCX), dX._ptr_raw() if need_dx else None,
+                                b.grad_ptr(0), b.grad_ptr(1), M, K, N))
+        b.step(lr, self._defer_update)
+        return dX
+
+    def get_params(self):
+        return {'weights': self.weights.data, 'biases': self.biases.data}
+
+    def set_params(self, params):
+        self.weights.data = params['weights']
+        self.biases.data = params['biases']
+
+
+# ====================================================================================================== Conv
+def _tup(v, nd):
+    return tuple(int(a) for a in v) if isinstance(v, (tuple, list)) else (int(v),) * nd
+
+
+class _ConvBase(_ParamLayer):
+    _nd = 2
+    _np_dtype = np.float64
+
+    def _init(self, in_channels, out_channels, kernel_size, stride, padding):
+        nd = self._nd
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self._k, self._s, self._p = _tup(kernel_size, nd), _tup(stride, nd), _tup(padding, nd)
+
+    def _desc(self, x_shape, x_layout, y_layout, act=ACT_NONE):
+        nd = self._nd
+        if len(x_shape) != nd + 2:
+            raise ValueError(f"expected a {nd + 2}-D input (N, C, *spatial), got shape {x_shape}")
+        if x_shape[1] != self.in_channels:
+            raise ValueError(f"input has {x_shape[1]} channels, layer expects {self.in_channels}")
+        d = ConvDesc()
+        d.nd, d.N, d.C, d.O = nd, x_shape[0], self.in_channels, self.out_channels
+        for i in range(nd):
+            d.inp[i], d.k[i], d.s[i], d.p[i] = x_shape[2 + i], self._k[i], self._s[i], self._p[i]
+        d.act, d.x_layout, d.y_layout = act, x_layout, y_layout
+        out = (C.c_int * 3)()
+        check(lib.okl_conv_out_extent(C.byref(d), out))
+        return d, tuple(out[i] for i in range(nd))
+
+    def _forward(self, inputs):
+        inputs = _as_tensor(inputs)
+        ctx = get_ctx()
+        self._bucket.materialize()
+        self.inputs = inputs
+        xl = inputs._layout if inputs.ndim >= 3 and inputs._dev_valid else NCX
+        yl = getattr(self, "_out_layout", NCX)
+        d, oe = self._desc(inputs.shape, xl, yl, self._fused_act)
+        out = Tensor._empty((inputs.shape[0], self.out_channels) + oe, self._np_dtype, layout=yl)
+        check(lib.okl_conv_fprop(ctx.h, C.byref(d), inputs._dptr(xl), self._bucket.ptr(0), self._bucket.ptr(1), out._ptr_raw()))
+        self._fwd_layouts = (xl, yl)
+        return out
+
+    def _backward(self, dL_dout, lr):
+        dL_dout = _as_tensor(dL_dout)
+        ctx = get_ctx()
+        x = self.inputs
+        xl, yl = self._fwd_layouts
+        d, oe = self._desc(x.shape, xl, yl)
+        if dL_dout.shape != (x.shape[0], self.out_channels) + oe:
+            raise ValueError(f"dL_dout shape {dL_dout.shape} does not match the layer output {(x.shape[0], self.out_channels) + oe}")
+        b = self._bucket
+        g = dL_dout._dptr(yl)
+        check(lib.okl_conv_wgrad(ctx.h, C.byref(d), x._dptr(xl), g, b.grad_ptr(0), b.grad_ptr(1)))
+        dX = None
+        if getattr(self, "_need_dx", True):
+            dX = Tensor._empty(x.shape, self._dx_dtype(x), layout=xl)
+            check(lib.okl_conv_dgrad(ctx.h, C.byref(d), g, b.ptr(0), dX._ptr_raw()))      # uses the pre-update filters
+        b.step(lr, self._defer_update)
+        return dX
+
+    def _dx_dtype(self, x):
+        return np.float64 if self._nd == 2 else (x._np_dtype if x._np_dtype in (np.float32, np.float64) else np.float64)
+
+
+class Conv1DLayer(_ConvBase):
+    """okl.py:669-764.  weights (O,C,k) float32 * 0.1, biases (O,1) float32; output float32."""
+    _nd, _np_dtype = 1, np.float32
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0):
+        self._init(in_channels, out_channels, kernel_size, stride, padding)
+        self.kernel_size, self.stride, self.padding = kernel_size, stride, padding
+        self.weights = Tensor(np.random.randn(out_channels, in_channels, kernel_size).astype(np.float32) * 0.1)
+        self.biases = Tensor(np.zeros((out_channels, 1), dtype=np.float32))
+        self._bucket = _ParamBucket([self.weights, self.biases])
+
+    def forward(self, inputs: Tensor):
+        self.output = self._forward(inputs)
+        return self.output
+
+    def backward(self, dL_dout: Tensor, lr: float):
+        dX = self._backward(dL_dout, lr)
+        if dX is not None:
+            _set_input_grad(self.inputs, dX)            # okl.py:750
+        return dX
+
+    def get_params(self):
+        return {'weights': self.weights.data, 'biases': self.biases.data}
+
+    def set_params(self, params):
+        self.weights.data = params['weights']
+        self.biases.data = params['biases']
+
+
+class Conv2DLayer(_ConvBase):
+    """okl.py:767-933 (normal mode).  filters (O,C,kh,kw) float64 * 0.1, biases (O,1); int-or-tuple kernel/stride/padding;
+    output float64.  ``transposed=True`` (okl.py:815-840) is outside the hot path."""
+    _nd, _np_dtype = 2, np.float64
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, transposed=False):
+        self._init(in_channels, out_channels, kernel_size, stride, padding)
+        self.kernel_size, self.stride, self.padding = self._k, self._s, self._p
+        self.transposed = transposed
+        if transposed:
+            raise NotImplementedError("Conv2DLayer(transposed=True) is not part of the B200 hot path (SURVEY.md 8(f) N3)")
+        self.filters = Tensor(np.random.randn(out_channels, in_channels, *self._k) * 0.1)
+        self.biases = Tensor(np.zeros((out_channels, 1)))
+        self._bucket = _ParamBucket([self.filters, self.biases])
+
+    def forward(self, inputs: Tensor):
+        self.outputs = self._forward(inputs)
+        return self.outputs
+
+    def forward_normal(self, inputs: Tensor):
+        return self.forward(inputs)
+
+    def backward(self, dL_dout: Tensor, lr: float):
+        return self._backward(dL_dout, lr)
+
+    def backward_normal(self, dL_dout: Tensor, lr: float):
+        return self._backward(dL_dout, lr)
+
+    def get_params(self):
+        return {'filters': self.filters.data, 'biases': self.biases.data}
+
+    def set_params(self, params):
+        self.filters.data = params['filters']
+        self.biases.data = params['biases']
+
+
+class Conv3DLayer(_ConvBase):
+    """okl.py:936-1049.  filters (O,C,kd,kh,kw) float32 * 0.1, biases (O,1) float32; output float32."""
+    _nd, _np_dtype = 3, np.float32
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0):
+        self._init(in_channels, out_channels, kernel_size, stride, padding)
+        self.kernel_size, self.stride, self.padding = self._k, self._s, self._p
+        self.filters = Tensor(np.random.randn(out_channels, in_channels, *self._k).astype(np.float32) * 0.1)
+        self.biases = Tensor(np.zeros((out_channels, 1), dtype=np.float32))
+        self._bucket = _ParamBucket([self.filters, self.biases])
+
+    def forward(self, inputs: Tensor):
+        self.output = self._forward(inputs)
+        return self.output
+
+    def backward(self, dL_dout: Tensor, lr: float):
+        dX = self._backward(dL_dout, lr)
+        if dX is not None:
+            _set_input_grad(self.inputs, dX)            # okl.py:1035
+        return dX
+
+    def get_params(self):
+        return {'filters': self.filters.data, 'biases': self.biases.data}
+
+    def set_params(self, params):
+        self.filters.data = params['filters']
+        self.biases.data = params['biases']
+
+
+# ====================================================================================================== activations
+def _float_dtype(t):
+    return t._np_dtype if t._np_dtype in (np.dtype(np.float32), np.dtype(np.float64)) else np.dtype(np.float64)
+
+
+class _Activation:
+    _act = ACT_NONE
+    _bwd_ref = "inputs"          # which stored tensor the derivative is evaluated from
+    _fused_into_prev = False     # NeuralNetwork planner: the producing layer's epilogue already applied this activation
+
+    def _fwd(self, inputs):
+        inputs = _as_tensor(inputs)
+        self.inputs = inputs
+        if self._fused_into_prev:
+            return inputs                      # the tensor already holds act(x); relu backward uses y > 0 <=> x > 0
+        ctx = get_ctx()
+        out = Tensor._empty(inputs.shape, _float_dtype(inputs), layout=inputs._layout if inputs._dev_valid else NCX)
+        src = inputs._dptr()
+        out._layout = inputs._layout
+        check(lib.okl_act_fwd(ctx.h, self._act, src, out._ptr_raw(), inputs.size))
+        return out
+
+    def _bwd(self, dL_dout, ref):
+        dL_dout = _as_tensor(dL_dout)
+        ctx = get_ctx()
+        if dL_dout.shape != ref.shape:
+            raise ValueError(f"operands could not be broadcast together with shapes {dL_dout.shape} {ref.shape}")
+        lay = ref._layout if ref._dev_valid else NCX
+        rp = ref._dptr()
+        lay = ref._layout
+        dx = Tensor._empty(ref.shape, np.result_type(_float_dtype(dL_dout), _float_dtype(ref)), layout=lay)
+        check(lib.okl_act_bwd(ctx.h, self._act, rp, dL_dout._dptr(lay), dx._ptr_raw(), ref.size))
+        return dx
+
+    def get_params(self):
+        return None
+
+    def set_params(self, params):
+        pass
+
+
+class ReLUActivationLayer(_Activation):
+    """okl.py:94-120: max(0, x); backward g * (x > 0), also accumulated into inputs.grad.
+    The shipped forward goes through np.vectorize, which truncates the whole output to int64 when x.flat[0] <= 0
+    (SURVEY.md fact 5); this implementation always returns the intended float max(0, x)."""
+    _act = ACT_RELU
+
+    def forward(self, inputs: Tensor):
+        self.outputs = self._fwd(inputs)
+        return self.outputs
+
+    def backward(self, dL_dout: Tensor, lr: float):
+        dx = self._bwd(dL_dout, self.inputs)
+        _set_input_grad(self.inputs, dx)
+        return dx
+
+
+class SigmoidActivationLayer(_Activation):
+    """okl.py:500-522: 1/(1+exp(-x)); backward g * y * (1 - y) from the stored output."""
+    _act = ACT_SIGMOID
+
+    def forward(self, inputs: Tensor):
+        self.outputs = self._fwd(inputs)
+        return self.outputs
+
+    def backward(self, dL_dout: Tensor, lr: float = None):
+        return self._bwd(dL_dout, self.outputs)
+
+
+class TanhActivationLayer(_Activation):
+    """okl.py:2070-2108: tanh(x); backward g * (1 - tanh(x)^2) recomputed from the input; sets inputs.grad."""
+    _act = ACT_TANH
+
+    def forward(self, inputs: Tensor):
+        self.output = self._fwd(inputs)
+        return self.output
+
+    def backward(self, dL_dout: Tensor, lr: float):
+        if self._fused_into_prev:
+            raise RuntimeError("tanh cannot be fused: its backward needs the pre-activation input")
+        dx = self._bwd(dL_dout, self.inputs)
+        _set_input_grad(self.inputs, dx)
+        return dx
+
+
+class SoftmaxActivationLayer:
+    """okl.py:355-399: stable softmax over axis 1 (+ nan_to_num); backward = Jacobian product, computed in closed form
+    p * (g - sum_k g_k p_k) instead of the reference's B x C x C Python triple loop."""
+
+    def forward(self, inputs: Tensor):
+        inputs = _as_tensor(inputs)
+        ctx = get_ctx()
+        if inputs.ndim != 2:
+            raise ValueError(f"softmax expects a 2-D (batch, classes) input, got shape {inputs.shape}")
+        self.inputs = inputs
+        out = Tensor._empty(inputs.shape, _float_dtype(inputs))
+        check(lib.okl_softmax_fwd(ctx.h, inputs._dptr(NCX), out._ptr_raw(), inputs.shape[0], inputs.shape[1]))
+        self.outputs = out
+        return out
+
+    def backward(self, dL_dout: Tensor, lr: float = None):
+        dL_dout = _as_tensor(dL_dout)
+        ctx = get_ctx()
+        p = self.outputs
+        if dL_dout.shape != p.shape:
+            raise ValueError(f"operands could not be broadcast together with shapes {dL_dout.shape} {p.shape}")
+        dx = Tensor._empty(p.shape, np.float64)
+        check(lib.okl_softmax_bwd(ctx.h, p._dptr(NCX), dL_dout._dptr(NCX), dx._ptr_raw(), p.shape[0], p.shape[1]))
+        return dx
+
+    def get_params(self):
+        return None
+
+    def set_params(self, params: dict):
+        pass
+
+
+# ====================================================================================================== pooling / flatten
+class _Pool:
+    _kind = POOL_MAX
+
+    def __init__(self, pool_size=2, stride=2):
+        self.pool_size = pool_size
+        self.stride = stride
+
+    def forward(self, inputs):
+        inputs = _as_tensor(inputs)
+        ctx = get_ctx()
+        if inputs.ndim != 4:
+            raise ValueError(f"not enough values to unpack (expected 4, got {inputs.ndim})")      # okl.py:1732
+        N, Cc, H, W = inputs.shape
+        ps, st = int(self.pool_size), int(self.stride)
+        if H < ps or W < ps:
+            raise ValueError("pooling window larger than the input")
+        OH, OW = (H - ps) // st + 1, (W - ps) // st + 1
+        src = inputs._dptr()
+        lay = inputs._layout
+        out = Tensor._empty((N, Cc, OH, OW), np.float64, layout=lay)
+        check(lib.okl_pool_fwd(ctx.h, self._kind, src, out._ptr_raw(), N, Cc, H, W, ps, st, lay))
+        self.inputs = inputs
+        self.output = out
+        return out
+
+    def backward(self, dL_dout: Tensor, lr: float = None):
+        dL_dout = _as_tensor(dL_dout)
+        ctx = get_ctx()
+        x = self.inputs
+        N, Cc, H, W = x.shape
+        if dL_dout.shape != self.output.shape:
+            raise ValueError(f"dL_dout shape {dL_dout.shape} does not match the layer output {self.output.shape}")
+        xp = x._dptr()
+        lay = x._layout
+        dx = Tensor._empty(x.shape, np.float64, layout=lay)
+        check(lib.okl_pool_bwd(ctx.h, self._kind, xp, dL_dout._dptr(lay), dx._ptr_raw(), N, Cc, H, W, int(self.pool_size),
+                               int(self.stride), lay))
+        _set_input_grad(x, dx)                         # okl.py:1768 / 1821
+        return dx
+
+    def get_params(self):
+        return None
+
+    def set_params(self, params):
+        pass
+
+
+class MaxPoolingLayer(_Pool):
+    """okl.py:1715-1778.  Window max on NCHW, no padding, float64 output.  Backward (R4): every position equal to its
+    window's max receives that window's gradient (ties -> all maxima; overlapping windows overwrite in raster order)."""
+    _kind = POOL_MAX
+
+
+class AveragePoolingLayer(_Pool):
+    """okl.py:1781-1831.  Window mean; backward (R5): dX[window] += g / pool^2."""
+    _kind = POOL_AVG
+
+
+class FlattenLayer:
+    """okl.py:639-651: (N, ...) -> (N, -1) and back; a zero-copy view of the device block."""
+
+    def __init__(self):
+        self.inputs_shape = None
+
+    def forward(self, inputs: Tensor):
+        inputs = _as_tensor(inputs)
+        self.inputs_shape = inputs.shape
+        return inputs.reshape((inputs.shape[0], -1))
+
+    def backward(self, dL_dout: Tensor, lr: float):
+        return _as_tensor(dL_dout).reshape(self.inputs_shape)
+
+    def get_params(self):           # the reference lacks this (NeuralNetwork.save breaks on CNNs, okl.py:3022); harmless to add
+        return None
+
+    def set_params(self, params):
+        pass
+
+
+class UnflattenLayer:
+    """okl.py:654-666."""
+
+    def __init__(self, output_shape):
+        self.output_shape = tuple(output_shape)
+
+    def forward(self, inputs: Tensor):
+        inputs = _as_tensor(inputs)
+        return inputs.reshape((inputs.shape[0],) + self.output_shape)
+
+    def backward(self, dL_dout: Tensor, lr: float):
+        dL_dout = _as_tensor(dL_dout)
+        return dL_dout.reshape((dL_dout.shape[0], -1))
+
+    def get_params(self):
+        return None
+
+    def set_params(self, params):
+        pass

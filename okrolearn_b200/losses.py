@@ -1,0 +1,154 @@
+"""CrossEntropyLoss / MSELoss with the reference's call protocol (okl.py:1380-1409, 1833-1839): ``forward(outputs, targets)``
+returns the loss value, ``backward(outputs, targets)`` returns dL/doutputs as a Tensor.  The value is computed on the device
+together with the gradient (one kernel) and is returned as a ``LossValue`` - a float-like object that reads the device scalar
+only when something actually looks at it, so a training loop does not synchronise with the host every batch.
+
+Data parallel: the gradient is divided by the GLOBAL batch (local rows x ranks) so that the sum of the ranks' parameter
+gradients equals the single-GPU gradient."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check, get_ctx, NCX
+from .tensor import Tensor, _DevBuf
+
+
+class LossValue:
+    """Float-like view of a device fp32 scalar (mean loss of one batch)."""
+    __slots__ = ("_buf", "_val", "_epoch")
+
+    def __init__(self, buf):
+        self._buf, self._val, self._epoch = buf, None, -1
+
+    def _get(self):
+        ctx = get_ctx()
+        if self._val is None or self._epoch != ctx.epoch:
+            v = C.c_float()
+            check(lib.okl_read_scalar(ctx.h, self._buf.ptr, C.byref(v)))
+            self._val, self._epoch = np.float64(v.value), ctx.epoch
+        return self._val
+
+    @property
+    def data(self):                       # okl.py:2973 does float(np.sum(loss.data))
+        return np.array(self._get())
+
+    def item(self):
+        return float(self._get())
+
+    def __float__(self):
+        return float(self._get())
+
+    def __repr__(self):
+        return repr(self._get())
+
+    def __format__(self, spec):
+        return format(float(self._get()), spec)
+
+    def __add__(self, o):
+        return float(self) + o
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return float(self) - o
+
+    def __rsub__(self, o):
+        return o - float(self)
+
+    def __mul__(self, o):
+        return float(self) * o
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        return float(self) / o
+
+    def __lt__(self, o):
+        return float(self) < o
+
+    def __le__(self, o):
+        return float(self) <= o
+
+    def __gt__(self, o):
+        return float(self) > o
+
+    def __ge__(self, o):
+        return float(self) >= o
+
+    def __eq__(self, o):
+        return float(self) == o
+
+    def __hash__(self):
+        return hash(float(self))
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self._get(), dtype=dtype)
+
+
+def _targets_i32(targets: Tensor, rows: int):
+    """Class indices as an int32 device vector (okl.py:1392 does targets.data.astype(int))."""
+    ctx = get_ctx()
+    cached = getattr(targets, "_i32", None)
+    if cached is not None and cached[1] == (targets._dev_ver, id(targets._host)):
+        return cached[0]
+    if targets.size != rows:
+        raise ValueError(f"targets has {targets.size} entries for {rows} samples")
+    buf = _DevBuf(ctx, rows * 4)
+    host = np.ascontiguousarray(np.asarray(targets.data).reshape(-1).astype(np.int64))
+    check(lib.okl_h2d_i32(ctx.h, buf.ptr, host.ctypes.data, rows, _lib.I64))
+    targets._i32 = (buf, (targets._dev_ver, id(targets._host)))
+    return buf
+
+
+class CrossEntropyLoss:
+    """okl.py:1380-1409: expects probabilities (after softmax) and integer class targets.
+    forward: mean(-log(clip(p, 1e-12, 1-1e-12)[i, t_i]));  backward: (clip(p) - onehot) / samples.
+    As in the reference, ``backward`` ignores its arguments and uses what ``forward`` stashed (okl.py:1399-1403)."""
+
+    def forward(self, outputs: Tensor, targets: Tensor):
+        ctx = get_ctx()
+        if outputs.ndim != 2:
+            raise ValueError(f"CrossEntropyLoss expects (batch, classes) probabilities, got shape {outputs.shape}")
+        rows, cols = outputs.shape
+        tbuf = targets._i32_dev if hasattr(targets, "_i32_dev") else _targets_i32(targets, rows)
+        self._tbuf = tbuf
+        loss = _DevBuf(ctx, 4)
+        grad = Tensor._empty((rows, cols), np.float64)
+        tptr = tbuf if isinstance(tbuf, int) else tbuf.ptr
+        check(lib.okl_ce_fwd_bwd(ctx.h, outputs._dptr(NCX), tptr, loss.ptr, grad._ptr_raw(), rows, cols, float(rows * ctx.nranks)))
+        self.outputs, self.targets = outputs, targets
+        self._grad = grad
+        self._loss = LossValue(loss)
+        return self._loss
+
+    def backward(self, dL_dloss=None, lr=None):
+        g = self._grad
+        if self.outputs.requires_grad:                      # okl.py:1405
+            self.outputs._grad = g if self.outputs._grad is None else (
+                (self.outputs._grad if isinstance(self.outputs._grad, Tensor) else Tensor(self.outputs._grad)) + g)
+        return g
+
+
+class MSELoss:
+    """okl.py:1833-1839: mean((o - t)^2); gradient 2 (o - t) / t.size."""
+
+    def forward(self, outputs: Tensor, targets: Tensor):
+        ctx = get_ctx()
+        if outputs.shape != targets.shape:
+            raise ValueError(f"operands could not be broadcast together with shapes {outputs.shape} {targets.shape}")
+        loss = _DevBuf(ctx, 4)
+        grad = Tensor._empty(outputs.shape, np.float64)
+        n = outputs.size
+        check(lib.okl_mse_fwd_bwd(ctx.h, outputs._dptr(NCX), targets._dptr(NCX), loss.ptr, grad._ptr_raw(), n, float(n * ctx.nranks)))
+        self._grad = grad
+        self._key = (id(outputs), id(targets))
+        self._loss = LossValue(loss)
+        return self._loss
+
+    def backward(self, outputs: Tensor, targets: Tensor):
+        if getattr(self, "_key", None) != (id(outputs), id(targets)):
+            self.forward(outputs, targets)
+        return self._grad

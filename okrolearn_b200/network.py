@@ -1,0 +1,503 @@
+"""``NeuralNetwork``: the container and train loop of the reference (okl.py:2764-3041) driving device-resident layers.
+
+Same public methods and hook names.  What is different underneath (BASELINE.json north_star: "the training-step loop and
+the optimizer update" are rebuilt):
+  * the dataset is uploaded to HBM once; the per-epoch shuffle (okl.py:2957-2960, same host RNG call so the permutation is
+    identical) is a device gather; batches are zero-copy views.  ``stream_inputs = True`` keeps the dataset in pinned host
+    memory instead and copies each batch host->device inside the step (the end-to-end measurement mode).
+  * with no hooks / debug mode / breakpoints / profiler attached (nothing can observe intermediate Python objects), a full
+    batch's forward + loss + backward + update is captured once into a CUDA graph and replayed: one launch per step, the
+    learning rate read from a device scalar.  ``use_graph = False`` (or OKL_GRAPH=0) disables this.
+  * in that fast path a parametric layer directly followed by ReLU/Sigmoid applies the activation in its GEMM/conv epilogue
+    (``fuse_activations``), and the gradient w.r.t. the *dataset* of the first layer is not computed (nothing can read it).
+  * per-batch losses are accumulated on the device and read back once per epoch.
+  * data parallel (one process per GPU): each layer's gradient bucket is all-reduced on the comm stream as soon as its
+    backward has been enqueued, and all updates are applied after the last layer's backward (overlap with backward).
+"""
+from __future__ import annotations
+
+import cProfile
+import ctypes as C
+import io
+import logging
+import os
+import pdb
+import pickle
+import pstats
+import time
+from typing import Callable
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check, get_ctx, NCX, ACT_NONE
+from .tensor import Tensor, _DevBuf, _numel
+from .layers import (_ParamLayer, _Activation, ReLUActivationLayer, SigmoidActivationLayer, DenseLayer, _ConvBase)
+from .losses import CrossEntropyLoss, MSELoss, LossValue
+
+
+class _StepState:
+    """Static device buffers a captured train step reads its batch from, plus the graph itself."""
+
+    def __init__(self, ctx, batch_size, sample_shape, t_row):
+        self.xin = Tensor._empty((batch_size,) + tuple(sample_shape), np.float32)
+        self.tin = _DevBuf(ctx, max(batch_size * t_row, 1) * 4)
+        self.eloss = _DevBuf(ctx, 4)
+        self.graph = None
+        self.warm = False
+
+
+class _StepGraph:
+    def __init__(self, handle, keep, launches):
+        self.handle, self.keep, self.launches = handle, keep, launches
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib.okl_graph_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class NeuralNetwork:
+    def __init__(self, temperature=1.0):
+        self.layers = []
+        self.hooks = {'pre_forward': [], 'post_forward': [], 'pre_backward': [], 'post_backward': [], 'pre_epoch': [],
+                      'post_epoch': []}
+        self.temperature = temperature
+        self.profiler = cProfile.Profile()
+        self.is_profiling = False
+        self.debug_mode = False
+        self.layer_outputs = []
+        self.gradients = []
+        self.parameter_history = []
+        self.logger = self._setup_logger()
+        self.breakpoints = {}
+        self.error_history = []
+        # B200 path knobs
+        self.use_graph = os.environ.get("OKL_GRAPH", "1") != "0"
+        self.fuse_activations = os.environ.get("OKL_FUSE", "1") != "0"
+        self.skip_input_grad = os.environ.get("OKL_SKIP_INPUT_GRAD", "1") != "0"
+        self.stream_inputs = False          # keep the dataset on the host, copy each batch inside the step
+        self.sync_loss_every_step = False   # read the loss back to the host after every step (end-to-end mode)
+        self.last_step_losses = []
+        self._graphs = {}
+        self._plan_key = None
+
+    # ------------------------------------------------------------------ logging / debug (okl.py:2787-2869)
+    def _setup_logger(self):
+        logger = logging.getLogger('NeuralNetwork')
+        logger.setLevel(logging.DEBUG)
+        if not logger.handlers:              # the reference adds one handler per instance (duplicated lines); one is enough
+            handler = logging.StreamHandler()
+            handler.setFormatter(logging.Formatter('%(asctime)s - %(name)s - %(levelname)s - %(message)s'))
+            logger.addHandler(handler)
+        return logger
+
+    def set_debug_mode(self, mode: bool):
+        self.debug_mode = mode
+        self.logger.info(f"Debug mode set to: {mode}")
+
+    def set_breakpoint(self, method_name: str, condition: Callable = None):
+        self.breakpoints[method_name] = condition
+        self.logger.info(f"Breakpoint set for method: {method_name}")
+
+    def remove_breakpoint(self, method_name: str):
+        if method_name in self.breakpoints:
+            del self.breakpoints[method_name]
+            self.logger.info(f"Breakpoint removed for method: {method_name}")
+        else:
+            self.logger.warning(f"No breakpoint found for method: {method_name}")
+
+    def _check_breakpoint(self, method_name: str, *args, **kwargs):
+        if method_name in self.breakpoints:
+            condition = self.breakpoints[method_name]
+            if condition is None or condition(*args, **kwargs):
+                self.logger.info(f"Breakpoint hit in method: {method_name}")
+                pdb.set_trace()
+
+    def add(self, layer):
+        self._check_breakpoint('add', layer)
+        self.layers.append(layer)
+        self._graphs.clear()
+
+    def remove(self, index):
+        self._check_breakpoint('remove', index)
+        del self.layers[index]
+        self._graphs.clear()
+
+    def add_hook(self, hook_type: str, hook_fn: Callable):
+        if hook_type in self.hooks:
+            self.hooks[hook_type].append(hook_fn)
+        else:
+            raise ValueError(f"Invalid hook type: {hook_type}")
+
+    def remove_hook(self, hook_type: str, hook_fn: Callable):
+        if hook_type in self.hooks and hook_fn in self.hooks[hook_type]:
+            self.hooks[hook_type].remove(hook_fn)
+
+    def _run_hooks(self, hook_type: str, *args, **kwargs):
+        for hook in self.hooks[hook_type]:
+            hook(*args, **kwargs)
+
+    def start_profiling(self):
+        self.profiler.enable()
+        self.is_profiling = True
+
+    def stop_profiling(self):
+        self.profiler.disable()
+        self.is_profiling = False
+
+    def print_profile_stats(self, sort_by='cumulative', lines=20):
+        if not self.is_profiling:
+            print("Profiling was not started. Use start_profiling() first.")
+            return
+        s = io.StringIO()
+        pstats.Stats(self.profiler, stream=s).sort_stats(sort_by).print_stats(lines)
+        print(s.getvalue())
+
+    def _log_layer_output(self, layer_index: int, output: 'Tensor'):
+        if self.debug_mode:
+            self.layer_outputs.append((layer_index, output.copy()))
+
+    def _log_gradient(self, layer_index: int, gradient: 'Tensor'):
+        if self.debug_mode and gradient is not None:
+            self.gradients.append((layer_index, gradient.copy()))
+
+    def _log_parameters(self):
+        if self.debug_mode:
+            self.parameter_history.append([layer.get_params() for layer in self.layers])
+
+    def get_layer_outputs(self):
+        return self.layer_outputs
+
+    def get_gradients(self):
+        return self.gradients
+
+    def parameters(self):
+        return []                                        # okl.py:3018-3019
+
+    def get_parameter_history(self):
+        return [param.data.copy() for param in self.parameters()]
+
+    # ------------------------------------------------------------------ planning (fast path only)
+    def _observed(self):
+        """True when user code can observe per-layer Python objects during a step."""
+        return bool(self.debug_mode or self.breakpoints or self.is_profiling or any(self.hooks[k] for k in
+                    ('pre_forward', 'post_forward', 'pre_backward', 'post_backward')))
+
+    def _plan(self, fast: bool):
+        key = (fast, self.fuse_activations, self.skip_input_grad, tuple(id(l) for l in self.layers), get_ctx().nranks)
+        if key == self._plan_key:
+            return
+        self._plan_key = key
+        ls = self.layers
+        for l in ls:
+            if isinstance(l, _ParamLayer):
+                l._fused_act, l._need_dx = ACT_NONE, True
+                l._defer_update = get_ctx().nranks > 1
+            if isinstance(l, _Activation):
+                l._fused_into_prev = False
+        if not fast:
+            return
+        if self.fuse_activations:
+            for a, b in zip(ls, ls[1:]):
+                if isinstance(a, _ParamLayer) and isinstance(b, (ReLUActivationLayer, SigmoidActivationLayer)):
+                    a._fused_act, b._fused_into_prev = b._act, True
+        if self.skip_input_grad and ls and isinstance(ls[0], _ParamLayer):
+            ls[0]._need_dx = False
+
+    # ------------------------------------------------------------------ forward / backward (okl.py:2871-2914)
+    def forward(self, inputs: 'Tensor'):
+        self._check_breakpoint('forward', inputs)
+        if self.is_profiling:
+            return self._profiled_forward(inputs)
+        return self._forward(inputs)
+
+    def _profiled_forward(self, inputs: 'Tensor'):
+        self.profiler.enable()
+        result = self._forward(inputs)
+        self.profiler.disable()
+        return result
+
+    def _forward(self, inputs: 'Tensor', _fast=False):
+        self._plan(_fast)
+        self._run_hooks('pre_forward', inputs)
+        self.layer_outputs = []
+        for i, layer in enumerate(self.layers):
+            inputs = layer.forward(inputs)
+            self._log_layer_output(i, inputs)
+        if self.temperature != 1.0:
+            # okl.py:2890 `inputs.data = inputs.data / self.temperature` - in place on the last layer's output Tensor
+            ctx = get_ctx()
+            check(lib.okl_scale(ctx.h, inputs._dptr(), inputs.size, 1.0 / float(self.temperature)))
+            inputs._touch()
+        self._run_hooks('post_forward', inputs)
+        return inputs
+
+    def backward(self, loss_gradient: 'Tensor', lr: float):
+        self._check_breakpoint('backward', loss_gradient, lr)
+        if self.is_profiling:
+            return self._profiled_backward(loss_gradient, lr)
+        return self._backward(loss_gradient, lr)
+
+    def _profiled_backward(self, loss_gradient: 'Tensor', lr: float):
+        self.profiler.enable()
+        result = self._backward(loss_gradient, lr)
+        self.profiler.disable()
+        return result
+
+    def _backward(self, loss_gradient: 'Tensor', lr: float):
+        self._run_hooks('pre_backward', loss_gradient, lr)
+        self.gradients = []
+        for i, layer in reversed(list(enumerate(self.layers))):
+            loss_gradient = layer.backward(loss_gradient, lr)
+            self._log_gradient(i, loss_gradient)
+        for layer in self.layers:                          # deferred (data-parallel) updates: after the whole backward
+            if isinstance(layer, _ParamLayer):
+                layer._finish_update()
+        self._run_hooks('post_backward', loss_gradient, lr)
+        self._log_parameters()
+
+    # ------------------------------------------------------------------ train (okl.py:2916-3001)
+    def train(self, inputs: 'Tensor', targets: 'Tensor', epochs: int, lr_scheduler, optimizer, batch_size: int, loss_function):
+        self._check_breakpoint('train', inputs, targets, epochs, lr_scheduler.get_lr(), optimizer, batch_size, loss_function)
+        if self.is_profiling:
+            return self._profiled_train(inputs, targets, epochs, lr_scheduler, optimizer, batch_size, loss_function)
+        return self._train(inputs, targets, epochs, lr_scheduler, optimizer, batch_size, loss_function)
+
+    def _profiled_train(self, inputs, targets, epochs, lr_scheduler, optimizer, batch_size, loss_function):
+        self.profiler.enable()
+        result = self._train(inputs, targets, epochs, lr_scheduler, optimizer, batch_size, loss_function)
+        self.profiler.disable()
+        return result
+
+    def _one_step(self, batch_inputs, batch_targets, loss_function, lr, optimizer, fast):
+        """forward + loss + backward (+ optimizer for layers exposing parameters/gradients): okl.py:2969-2988."""
+        outputs = self._forward(batch_inputs, _fast=fast) if fast else self.forward(batch_inputs)
+        loss = loss_function.forward(outputs, batch_targets)
+        loss_gradient = loss_function.backward(outputs, batch_targets)
+        if fast:
+            self._backward(loss_gradient, lr)
+        else:
+            self.backward(loss_gradient, lr)
+        for i, layer in enumerate(self.layers):
+            if hasattr(layer, 'parameters'):
+                for key, param in layer.parameters.items():
+                    optimizer.update(param, layer.gradients[key], f"layer_{i}_{key}")
+        return outputs, loss
+
+    def _train(self, inputs: 'Tensor', targets: 'Tensor', epochs: int, lr_scheduler, optimizer, batch_size: int,
+               loss_function, clip_grad: float = None):
+        ctx = get_ctx()
+        num_samples = inputs.shape[0]
+        num_batches = int(np.ceil(num_samples / batch_size))
+        losses = []
+        fast = not self._observed()
+        graph_ok = fast and self.use_graph and not any(hasattr(l, 'parameters') for l in self.layers) and clip_grad is None
+        is_ce = isinstance(loss_function, CrossEntropyLoss)
+        sample_shape = tuple(inputs.shape[1:])
+        t_shape = tuple(targets.shape[1:])
+        row_elems = _numel(sample_shape)
+        t_row = _numel(t_shape)
+        stream = bool(self.stream_inputs)
+
+        # ---- dataset placement
+        if stream:
+            cur_x = np.ascontiguousarray(inputs.data, dtype=np.float32).reshape(num_samples, row_elems)
+            cur_t = np.ascontiguousarray(targets.data).reshape(num_samples, t_row)
+            cur_t = cur_t.astype(np.int32) if is_ce else cur_t.astype(np.float32)
+            pins_x = [self._pinned((num_samples, row_elems), np.float32) for _ in range(2)]
+            pins_t = [self._pinned((num_samples, t_row), cur_t.dtype) for _ in range(2)]
+        else:
+            x_dev = _DevBuf(ctx, max(inputs.size, 1) * 4)
+            check(lib.okl_d2d(ctx.h, x_dev.ptr, inputs._dptr(NCX), inputs.size * 4))
+            x_alt = _DevBuf(ctx, max(inputs.size, 1) * 4)
+            t_dev = _DevBuf(ctx, max(targets.size, 1) * 4)
+            t_alt = _DevBuf(ctx, max(targets.size, 1) * 4)
+            if is_ce:
+                th = np.ascontiguousarray(np.asarray(targets.data).reshape(-1).astype(np.int64))
+                check(lib.okl_h2d_i32(ctx.h, t_dev.ptr, th.ctypes.data, th.size, _lib.I64))
+            else:
+                check(lib.okl_d2d(ctx.h, t_dev.ptr, targets._dptr(NCX), targets.size * 4))
+            idx_dev = _DevBuf(ctx, max(num_samples, 1) * 4)
+            perm_total = np.arange(num_samples)
+
+        # ---- per-(batch shape, loss) step state: static input buffers + the captured graph
+        skey = (batch_size, sample_shape, t_shape, id(loss_function), tuple(id(l) for l in self.layers), fast,
+                self.fuse_activations, self.skip_input_grad)
+        st = self._graphs.get(skey)
+        if st is None:
+            st = _StepState(ctx, batch_size, sample_shape, t_row)
+            self._graphs[skey] = st
+        if not hasattr(ctx, "lr_buf"):
+            ctx.lr_buf = _DevBuf(ctx, 4)
+        ctx.lr_dev = ctx.lr_buf.ptr
+        self.last_step_losses = []
+
+        def make_targets(rows):
+            if is_ce:
+                t = Tensor(np.zeros((0,)), requires_grad=False)
+                t._shape = (rows,) + t_shape
+                t._i32_dev = st.tin.ptr
+                return t
+            return Tensor._view(st.tin, 0, (rows,) + t_shape, np.float32, bound=False)
+
+        for epoch in range(epochs):
+            self._run_hooks('pre_epoch', epoch, epochs)
+            epoch_start_time = time.time()
+            current_lr = lr_scheduler.step(epoch)
+            if hasattr(optimizer, 'param_groups'):
+                for param_group in optimizer.param_groups:
+                    param_group['lr'] = current_lr
+            elif hasattr(optimizer, 'lr'):
+                optimizer.lr = current_lr
+            elif hasattr(optimizer, 'set_lr'):
+                optimizer.set_lr(current_lr)
+            else:
+                self.logger.warning("Unable to update optimizer's learning rate. Scheduler may not have an effect.")
+            lr32 = np.array([current_lr], dtype=np.float32)
+            check(lib.okl_h2d(ctx.h, ctx.lr_dev, lr32.ctypes.data, 1, _lib.F32))
+            check(lib.okl_memset(ctx.h, st.eloss.ptr, 0, 4))
+
+            # shuffle (same host RNG call as okl.py:2957-2958)
+            indices = np.arange(num_samples)
+            np.random.shuffle(indices)
+            if stream:
+                np.take(cur_x, indices, axis=0, out=pins_x[epoch % 2][1])
+                np.take(cur_t, indices, axis=0, out=pins_t[epoch % 2][1])
+                cur_x, cur_t = pins_x[epoch % 2][1], pins_t[epoch % 2][1]    # shuffled and pinned
+            else:
+                i32 = np.ascontiguousarray(indices.astype(np.int32))
+                check(lib.okl_h2d_i32(ctx.h, idx_dev.ptr, i32.ctypes.data, i32.size, _lib.I32))
+                check(lib.okl_gather_rows(ctx.h, x_alt.ptr, x_dev.ptr, idx_dev.ptr, num_samples, row_elems))
+                check(lib.okl_gather_rows(ctx.h, t_alt.ptr, t_dev.ptr, idx_dev.ptr, num_samples, t_row))
+                x_dev, x_alt = x_alt, x_dev
+                t_dev, t_alt = t_alt, t_dev
+                perm_total = perm_total[indices]
+
+            for batch in range(num_batches):
+                b0 = batch * batch_size
+                b1 = min(b0 + batch_size, num_samples)
+                rows = b1 - b0
+                full = rows == batch_size
+                if stream:
+                    check(lib.okl_h2d_async_raw(ctx.h, st.xin._ptr_raw(), cur_x[b0:b1].ctypes.data, rows * row_elems * 4))
+                    check(lib.okl_h2d_async_raw(ctx.h, st.tin.ptr, cur_t[b0:b1].ctypes.data, rows * t_row * 4))
+                else:
+                    check(lib.okl_d2d(ctx.h, st.xin._ptr_raw(), x_dev.ptr + b0 * row_elems * 4, rows * row_elems * 4))
+                    check(lib.okl_d2d(ctx.h, st.tin.ptr, t_dev.ptr + b0 * t_row * 4, rows * t_row * 4))
+                if graph_ok and full and st.graph is not None:
+                    ctx.graph_launch(st.graph.handle)
+                    loss = st.graph.loss
+                else:
+                    st.xin._touch()
+                    bx = st.xin if full else Tensor._view(st.xin._buf, 0, (rows,) + sample_shape, np.float32, bound=False)
+                    bt = make_targets(rows)
+                    if graph_ok and full and st.warm:
+                        keep = []
+                        ctx._capture_keep = keep
+                        ctx.graph_begin()
+                        try:
+                            outputs, loss = self._one_step(bx, bt, loss_function, current_lr, optimizer, fast)
+                            check(lib.okl_binary(ctx.h, 0, st.eloss.ptr, loss._buf.ptr, st.eloss.ptr, 1, 1))
+                        finally:
+                            handle = ctx.graph_end()
+                            ctx._capture_keep = None
+                        keep.extend([outputs, loss, bx, bt])
+                        st.graph = _StepGraph(handle, keep, 0)
+                        st.graph.loss = loss
+                        ctx.graph_launch(st.graph.handle)
+                    else:
+                        outputs, loss = self._one_step(bx, bt, loss_function, current_lr, optimizer, fast)
+                        check(lib.okl_binary(ctx.h, 0, st.eloss.ptr, loss._buf.ptr, st.eloss.ptr, 1, 1))
+                        if full:
+                            st.warm = True
+                    if clip_grad is not None:
+                        self._clip_gradients(clip_grad)
+                if self.sync_loss_every_step:
+                    self.last_step_losses.append(float(loss))
+
+            v = C.c_float()
+            check(lib.okl_read_scalar(ctx.h, st.eloss.ptr, C.byref(v)))
+            avg_loss = float(v.value) / num_batches
+            losses.append(avg_loss)
+            self.parameter_history.append(self.get_parameter_history())
+            epoch_end_time = time.time()
+            self.logger.info(f"Epoch {epoch + 1}/{epochs} - Loss: {avg_loss:.4f} - LR: {current_lr:.6f} - "
+                             f"Time: {epoch_end_time - epoch_start_time:.2f}s")
+            self._run_hooks('post_epoch', epoch, epochs, avg_loss)
+
+        # the reference reorders the caller's tensors in place every epoch (okl.py:2959-2960)
+        if epochs and stream:
+            inputs.data = np.array(cur_x).reshape(inputs.shape).astype(inputs._np_dtype, copy=False)
+            targets.data = np.array(cur_t).reshape(targets.shape).astype(targets._np_dtype, copy=False)
+        elif epochs:
+            ctx.sync()
+            if inputs._bound:
+                check(lib.okl_d2d(ctx.h, inputs._ptr_raw(), x_dev.ptr, inputs.size * 4))
+            else:
+                inputs._buf, inputs._off, inputs._layout = x_dev, 0, NCX
+            inputs._touch()
+            targets.data = np.asarray(targets.data)[perm_total]
+        if stream:
+            ctx.sync()
+            for p, _ in pins_x + pins_t:
+                lib.okl_pinned_free(p)
+        return losses
+
+    @staticmethod
+    def _pinned(shape, dtype):
+        """(pointer, ndarray view) of a page-locked host buffer."""
+        nbytes = max(int(_numel(shape) * np.dtype(dtype).itemsize), 1)
+        p = C.c_void_p()
+        check(lib.okl_pinned_alloc(nbytes, C.byref(p)))
+        raw = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_ubyte)), shape=(nbytes,))
+        return (p, raw[:_numel(shape) * np.dtype(dtype).itemsize].view(dtype).reshape(shape))
+
+    def _clip_gradients(self, max_norm):
+        """okl.py:3003-3016 - a no-op in the reference too, because parameters() returns []."""
+        total_norm = 0.0
+        for param in self.parameters():
+            if param.grad is not None:
+                total_norm += np.linalg.norm(param.grad.data) ** 2
+        total_norm = np.sqrt(total_norm)
+        if total_norm > max_norm:
+            clip_coef = max_norm / (total_norm + 1e-6)
+            for param in self.parameters():
+                if param.grad is not None:
+                    param.grad.data *= clip_coef
+
+    # ------------------------------------------------------------------ save / load (okl.py:3021-3044)
+    def save(self, file_path: str):
+        params = [layer.get_params() for layer in self.layers]
+        with open(file_path, 'wb') as f:
+            pickle.dump((params, self.temperature), f)
+
+    def load(self, file_path: str):
+        with open(file_path, 'rb') as f:
+            params, self.temperature = pickle.load(f)
+        for layer, param in zip(self.layers, params):
+            layer.set_params(param)
+
+    def save_weights(self, file_path: str):
+        params = [layer.get_params() for layer in self.layers]
+        with open(file_path, 'wb') as f:
+            pickle.dump(params, f)
+
+    def load_weights(self, file_path: str):
+        with open(file_path, 'rb') as f:
+            params = pickle.load(f)
+        for layer, param in zip(self.layers, params):
+            layer.set_params(param)
+
+    def set_temperature(self, temperature: float):
+        self.temperature = temperature
+
+
+class _BorrowedBuf:
+    """Non-owning stand-in for _DevBuf (a pointer into a buffer someone else keeps alive)."""
+    __slots__ = ("ptr", "nbytes")
+
+    def __init__(self, ptr, nbytes=0):
+        self.ptr, self.nbytes = ptr, nbytes

@@ -1,0 +1,200 @@
+"""GPU tests of the train-step loop (NeuralNetwork) against the reference-generated golden run, the oracle network,
+and size-independent properties at BASELINE.json's full configuration sizes."""
+import logging
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import golden, rel_err
+from oracle import okl_oracle as O
+
+pytestmark = pytest.mark.gpu
+logging.getLogger("NeuralNetwork").setLevel(logging.CRITICAL)
+TOL32 = 1e-5
+
+
+@pytest.fixture(autouse=True)
+def _fp32(okl):
+    okl.set_precision("fp32")
+    yield
+
+
+def dense_net(okl, g):
+    net = okl.NeuralNetwork(temperature=1.0)
+    d1, d2 = okl.DenseLayer(6, 8), okl.DenseLayer(8, 3)
+    d1.weights.data, d2.weights.data = g["Wa"].copy(), g["Wb"].copy()
+    net.add(d1)
+    net.add(okl.TanhActivationLayer())
+    net.add(d2)
+    net.add(okl.SoftmaxActivationLayer())
+    return net, d1, d2
+
+
+@pytest.mark.parametrize("mode", ["graph", "eager", "hooks", "stream"])
+def test_train_dense_matches_reference_run(okl, mode):
+    """tests/golden/train_dense.npz was produced by the shipped reference NeuralNetwork.train (3 epochs, batch 10 of 25
+    samples incl. a short last batch, StepLR, CE loss, host shuffle with np.random.seed(11))."""
+    g = golden("train_dense")
+    net, d1, d2 = dense_net(okl, g)
+    net.use_graph = mode in ("graph", "stream")
+    net.stream_inputs = mode == "stream"
+    seen = []
+    if mode == "hooks":
+        net.add_hook("post_forward", lambda out: seen.append(out.shape))
+        net.add_hook("post_epoch", lambda e, n, l: seen.append(("epoch", e, round(l, 3))))
+    X, T = okl.Tensor(g["X"].copy()), okl.Tensor(g["T"].copy())
+    np.random.seed(int(g["seed"]))
+    losses = net.train(X, T, epochs=3, lr_scheduler=okl.StepLRScheduler(0.05, 1, 0.5), optimizer=okl.SGDOptimizer(lr=0.05),
+                       batch_size=10, loss_function=okl.CrossEntropyLoss())
+    assert rel_err(losses, g["losses"]) < 2e-5
+    assert rel_err(d1.weights.data, g["W1"]) < TOL32 and rel_err(d1.biases.data, g["b1"]) < 2e-5
+    assert rel_err(d2.weights.data, g["W2"]) < TOL32 and rel_err(d2.biases.data, g["b2"]) < 2e-5
+    # the caller's tensors are reordered in place, as okl.py:2959-2960 does
+    assert rel_err(X.data, g["X_after"]) < 1e-6 and np.array_equal(np.asarray(T.data).astype(int), g["T_after"])
+    if mode == "hooks":
+        assert (10, 3) in seen and (5, 3) in seen and ("epoch", 2, round(float(g["losses"][2]), 3)) in seen
+
+
+def cnn_small(okl, g):
+    net = okl.NeuralNetwork()
+    conv = okl.Conv2DLayer(1, 4, 3)
+    conv.filters.data = g["Wc1"].copy()
+    d1, d2 = okl.DenseLayer(100, 16), okl.DenseLayer(16, 10)
+    d1.weights.data, d2.weights.data = g["Wd1"].copy(), g["Wd2"].copy()
+    for l in (conv, okl.ReLUActivationLayer(), okl.MaxPoolingLayer(2, 2), okl.FlattenLayer(), d1, okl.ReLUActivationLayer(), d2,
+              okl.SoftmaxActivationLayer()):
+        net.add(l)
+    return net, conv, d1, d2
+
+
+@pytest.mark.parametrize("fuse", [False, True])
+def test_cnn_two_steps_layer_api(okl, fuse):
+    """MNIST-shaped CNN (Conv2D->ReLU->MaxPool->Flatten->Dense->ReLU->Dense->Softmax + CE), two steps through the
+    reference-shaped forward/backward calls; golden from the oracle (repaired conv/pool backward) cross-checked with torch."""
+    g = golden("train_cnn_small")
+    net, conv, d1, d2 = cnn_small(okl, g)
+    net.fuse_activations = fuse
+    ce = okl.CrossEntropyLoss()
+    losses = []
+    for _ in range(2):
+        out = net._forward(okl.Tensor(g["X"]), _fast=fuse)
+        losses.append(float(ce.forward(out, okl.Tensor(g["T"]))))
+        net._backward(ce.backward(out, None), float(g["lr"]))
+    assert rel_err(losses, g["losses"]) < 2e-5
+    assert rel_err(conv.filters.data, g["conv_W"]) < TOL32 and rel_err(conv.biases.data, g["conv_b"]) < 2e-5
+    assert rel_err(d1.weights.data, g["d1_W"]) < TOL32 and rel_err(d2.weights.data, g["d2_W"]) < TOL32
+    assert rel_err(d1.biases.data, g["d1_b"]) < 2e-5 and rel_err(d2.biases.data, g["d2_b"]) < 2e-5
+
+
+def test_cnn_train_graph_equals_eager_and_oracle(okl):
+    """Full-batch train() with CUDA-graph replay == eager == oracle network, on an MNIST-shaped CNN (batch 16, 6 steps)."""
+    rng = np.random.default_rng(21)
+    N, B = 48, 16
+    X = rng.standard_normal((N, 1, 12, 12)).astype(np.float32)
+    T = rng.integers(0, 10, N)
+    Wc, W1, W2 = rng.standard_normal((4, 1, 3, 3)) * 0.3, rng.standard_normal((100, 16)) * 0.1, rng.standard_normal((16, 10)) * 0.1
+    g = {"Wc1": Wc, "Wd1": W1, "Wd2": W2}
+    results = {}
+    for mode in ("graph", "eager"):
+        net, conv, d1, d2 = cnn_small(okl, g)
+        net.use_graph = mode == "graph"
+        np.random.seed(5)
+        ls = net.train(okl.Tensor(X.copy()), okl.Tensor(T.copy()), epochs=2, lr_scheduler=okl.LearningRateScheduler(0.05),
+                       optimizer=okl.SGDOptimizer(), batch_size=B, loss_function=okl.CrossEntropyLoss())
+        results[mode] = (ls, conv.filters.data.copy(), d1.weights.data.copy(), d2.weights.data.copy())
+    on = O.OracleNetwork([O.OracleConv(Wc, np.zeros((4, 1)), fast=True), O.OracleReLU(), O.OracleMaxPool(2, 2), O.OracleFlatten(),
+                          O.OracleDense(W1, np.zeros((1, 16))), O.OracleReLU(), O.OracleDense(W2, np.zeros((1, 10))),
+                          O.OracleSoftmax()])
+    np.random.seed(5)
+    Xo, To, ol = X.astype(np.float64), T.copy(), []
+    for ep in range(2):
+        idx = np.arange(N)
+        np.random.shuffle(idx)
+        Xo, To = Xo[idx], To[idx]
+        ol.append(sum(on.train_step(Xo[s:s + B], To[s:s + B], O.OracleCrossEntropy(), 0.05) for s in range(0, N, B)) / (N // B))
+    for mode in ("graph", "eager"):
+        ls, cw, w1, w2 = results[mode]
+        assert rel_err(ls, ol) < 2e-5, mode
+        assert rel_err(cw, on.layers[0].W) < TOL32 and rel_err(w1, on.layers[4].W) < TOL32 and rel_err(w2, on.layers[6].W) < TOL32
+    assert rel_err(results["graph"][2], results["eager"][2]) < 1e-6
+
+
+def test_mse_regression_net_and_temperature(okl):
+    rng = np.random.default_rng(8)
+    X, Y = rng.standard_normal((32, 5)), rng.standard_normal((32, 2))
+    W1, W2 = rng.standard_normal((5, 7)) * 0.3, rng.standard_normal((7, 2)) * 0.3
+    net = okl.NeuralNetwork(temperature=2.0)
+    a, b = okl.DenseLayer(5, 7), okl.DenseLayer(7, 2)
+    a.weights.data, b.weights.data = W1.copy(), W2.copy()
+    net.add(a)
+    net.add(okl.SigmoidActivationLayer())
+    net.add(b)
+    np.random.seed(1)
+    ls = net.train(okl.Tensor(X.copy()), okl.Tensor(Y.copy()), 2, okl.LearningRateScheduler(0.1), okl.AdamOptimizer(), 8, okl.MSELoss())
+    on = O.OracleNetwork([O.OracleDense(W1, np.zeros((1, 7))), O.OracleSigmoid(), O.OracleDense(W2, np.zeros((1, 2)))], temperature=2.0)
+    np.random.seed(1)
+    Xo, Yo, ol = X.copy(), Y.copy(), []
+    for ep in range(2):
+        idx = np.arange(32)
+        np.random.shuffle(idx)
+        Xo, Yo = Xo[idx], Yo[idx]
+        ol.append(sum(on.train_step(Xo[s:s + 8], Yo[s:s + 8], O.OracleMSE(), 0.1) for s in range(0, 32, 8)) / 4)
+    assert rel_err(ls, ol) < 2e-5
+    assert rel_err(a.weights.data, on.layers[0].W) < TOL32 and rel_err(b.weights.data, on.layers[2].W) < TOL32
+    out = net.forward(okl.Tensor(X))
+    assert rel_err(out.data, on.forward(X)) < TOL32              # final output divided by temperature (okl.py:2890)
+
+
+def test_save_load_roundtrip_and_debug_mode(okl):
+    rng = np.random.default_rng(9)
+    net = okl.NeuralNetwork()
+    net.add(okl.Conv2DLayer(1, 2, 3))
+    net.add(okl.ReLUActivationLayer())
+    net.add(okl.FlattenLayer())
+    net.add(okl.DenseLayer(2 * 4 * 4, 3))
+    x = okl.Tensor(rng.standard_normal((2, 1, 6, 6)))
+    y0 = net.forward(x).data.copy()
+    with tempfile.TemporaryDirectory() as d:
+        net.save(os.path.join(d, "m.pkl"))
+        net2 = okl.NeuralNetwork()
+        net2.add(okl.Conv2DLayer(1, 2, 3))
+        net2.add(okl.ReLUActivationLayer())
+        net2.add(okl.FlattenLayer())
+        net2.add(okl.DenseLayer(2 * 4 * 4, 3))
+        net2.load(os.path.join(d, "m.pkl"))
+        assert rel_err(net2.forward(x).data, y0) < 1e-6
+    net.set_debug_mode(True)
+    net.forward(x)
+    net.backward(okl.Tensor(np.ones((2, 3))), 0.01)
+    assert len(net.get_layer_outputs()) == 4 and len(net.get_gradients()) == 4 and len(net.parameter_history) == 1
+
+
+def test_full_size_mnist_cnn_step_properties(okl):
+    """BASELINE config 2 at full size (batch 256): properties that need no CPU reference at that size -
+    probabilities sum to 1, the loss decreases under repeated steps on one batch, update linearity
+    (W2 - W1 == 2 (W1 - W0) + lr * (g2 - g1) is implied by the accumulate rule: checked as gacc consistency)."""
+    rng = np.random.default_rng(1234)
+    X = rng.standard_normal((256, 1, 28, 28)).astype(np.float32)
+    T = rng.integers(0, 10, 256)
+    np.random.seed(0)
+    net = okl.NeuralNetwork()
+    conv, d1, d2 = okl.Conv2DLayer(1, 32, 3), okl.DenseLayer(5408, 128), okl.DenseLayer(128, 10)
+    for l in (conv, okl.ReLUActivationLayer(), okl.MaxPoolingLayer(2, 2), okl.FlattenLayer(), d1, okl.ReLUActivationLayer(), d2,
+              okl.SoftmaxActivationLayer()):
+        net.add(l)
+    W0 = d1.weights.data.copy()
+    ls = net.train(okl.Tensor(X), okl.Tensor(T), epochs=4, lr_scheduler=okl.LearningRateScheduler(0.01),
+                   optimizer=okl.SGDOptimizer(), batch_size=256, loss_function=okl.CrossEntropyLoss())
+    assert all(np.isfinite(ls)) and ls[-1] < ls[0]
+    p = net.forward(okl.Tensor(X)).data
+    assert p.shape == (256, 10) and np.allclose(p.sum(1), 1.0, atol=1e-5) and (p >= 0).all()
+    # accumulated rule: W4 = W0 - lr * (4 g1 + 3 g2 + 2 g3 + g4)  =>  gacc = g1+g2+g3+g4 is finite and non-trivial
+    assert np.isfinite(d1.weights.grad).all() and np.abs(d1.weights.grad).max() > 0
+    assert np.abs(d1.weights.data - W0).max() > 0
+    # one oracle-checked slice at full width: the first 8 samples through the same weights
+    on = O.OracleNetwork([O.OracleConv(conv.filters.data, conv.biases.data, fast=True), O.OracleReLU(), O.OracleMaxPool(2, 2),
+                          O.OracleFlatten(), O.OracleDense(d1.weights.data, d1.biases.data), O.OracleReLU(),
+                          O.OracleDense(d2.weights.data, d2.biases.data), O.OracleSoftmax()])
+    assert rel_err(p[:8], on.forward(X[:8].astype(np.float64))) < 1e-4

@@ -1,0 +1,296 @@
+"""GPU parity tests (run with ``-m gpu`` on the B200): the CUDA path, called through the C ABI by the reference-shaped
+Python layers, against (1) the committed golden vectors generated from the reference and (2) the oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): 1e-5 relative (max|a-b| / max|b|) in FP32 mode, 2e-2 in TF32/BF16 mode.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, rel_err
+from oracle import okl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 1e-5
+CONV_CASES = ["conv2d_cfg1_small", "conv2d_s2p1", "conv2d_rect", "conv2d_c16", "conv1d_p0", "conv1d_s2p2",
+              "conv3d_p0", "conv3d_p1", "conv3d_s2"]
+
+
+@pytest.fixture(autouse=True)
+def _fp32(okl):
+    okl.set_precision("fp32")
+    yield
+
+
+def make_conv(okl, g):
+    W = g["W"]
+    nd = W.ndim - 2
+    s, p = tuple(int(v) for v in g["stride"]), tuple(int(v) for v in g["padding"])
+    k = tuple(W.shape[2:])
+    if nd == 1:
+        lay = okl.Conv1DLayer(W.shape[1], W.shape[0], k[0], s[0], p[0])
+        lay.weights.data = W.copy()
+    elif nd == 2:
+        lay = okl.Conv2DLayer(W.shape[1], W.shape[0], k, s, p)
+        lay.filters.data = W.copy()
+    else:
+        lay = okl.Conv3DLayer(W.shape[1], W.shape[0], k, s, p)
+        lay.filters.data = W.copy()
+    lay.biases.data = g["b"].copy()
+    return lay
+
+
+def test_dense_golden(okl):
+    g = golden("dense")
+    lay = okl.DenseLayer(12, 7)
+    lay.weights.data = g["W"].copy()
+    lay.biases.data = g["b"].copy()
+    y = lay.forward(okl.Tensor(g["x"]))
+    assert y.data.dtype == np.float64 and rel_err(y.data, g["y"]) < TOL32
+    dx1 = lay.backward(okl.Tensor(g["g1"]), float(g["lr"]))
+    assert rel_err(dx1.data, g["dx1"]) < TOL32
+    assert rel_err(lay.weights.data, g["W1"]) < TOL32 and rel_err(lay.biases.data, g["b1"]) < TOL32
+    lay.forward(okl.Tensor(g["x"]))
+    dx2 = lay.backward(okl.Tensor(g["g2"]), float(g["lr"]))
+    assert rel_err(dx2.data, g["dx2"]) < TOL32
+    # accumulated-gradient rule: W2 = W1 - lr (g1 + g2)
+    assert rel_err(lay.weights.data, g["W2"]) < TOL32 and rel_err(lay.biases.data, g["b2"]) < TOL32
+    assert lay.weights.grad.shape == (12, 7) and lay.biases.grad.shape == (1, 7)
+    assert sorted(lay.get_params()) == ["biases", "weights"]
+
+
+@pytest.mark.parametrize("name", CONV_CASES)
+def test_conv_golden(okl, name):
+    g = golden(name)
+    lay = make_conv(okl, g)
+    y = lay.forward(okl.Tensor(g["x"]))
+    assert y.data.dtype == g["y"].dtype                      # float64 for Conv2D, float32 for Conv1D/3D
+    assert rel_err(y.data, g["y"]) < TOL32
+    W0, b0 = g["W"].astype(np.float64), g["b"].astype(np.float64)
+    dX = lay.backward(okl.Tensor(g["g"]), 0.1)
+    assert rel_err(dX.data, g["dX"]) < TOL32
+    Wt = lay.weights if hasattr(lay, "weights") else lay.filters
+    assert rel_err(Wt.grad, g["dW"]) < TOL32
+    assert lay.biases.grad.shape == (g["W"].shape[0], 1) and rel_err(lay.biases.grad, g["db"]) < TOL32
+    assert rel_err(Wt.data, W0 - 0.1 * g["dW"]) < TOL32
+    assert rel_err(lay.biases.data, b0 - 0.1 * g["db"]) < TOL32
+
+
+def test_conv_kat_inputs_of_reference_tests(okl):
+    g = golden("kat_conv_reference_tests")
+    c2 = okl.Conv2DLayer(3, 2, (3, 3), stride=1, padding=0)
+    c2.filters.data = g["W2"]                                 # int64 arrays, as tests/conv2d.py:11-19 assigns
+    c2.biases.data = g["b2"]
+    y2 = c2.forward(okl.Tensor(g["x2"])).data
+    assert np.allclose(y2, g["y2"], rtol=1e-6)
+    dX = c2.backward(okl.Tensor(np.ones_like(y2)), lr=0.01)   # the part of tests/conv2d.py:54-60 the reference never reaches
+    assert c2.filters.grad is not None and c2.biases.grad is not None and dX.data.shape == g["x2"].shape
+    c1 = okl.Conv1DLayer(3, 2, 3, stride=1, padding=0)
+    c1.weights.data = g["W1"]
+    c1.biases.data = g["b1"]
+    assert np.allclose(c1.forward(okl.Tensor(g["x1"])).data, g["y1"], rtol=1e-6)
+
+
+def test_activations_golden(okl):
+    g = golden("activations")
+    x, gr = g["x"], g["g"]
+    r = okl.ReLUActivationLayer()
+    assert rel_err(r.forward(okl.Tensor(x)).data, g["relu_y"]) < 1e-7
+    xin = okl.Tensor(x)
+    r.forward(xin)
+    assert rel_err(r.backward(okl.Tensor(gr), 0.0).data, g["relu_dx"]) < 1e-7
+    assert rel_err(xin.grad, g["relu_dx"]) < 1e-7            # okl.py:110 also sets inputs.grad
+    s = okl.SigmoidActivationLayer()
+    assert rel_err(s.forward(okl.Tensor(x)).data, g["sigmoid_y"]) < 1e-6
+    assert rel_err(s.backward(okl.Tensor(gr)).data, g["sigmoid_dx"]) < 1e-6
+    t = okl.TanhActivationLayer()
+    assert rel_err(t.forward(okl.Tensor(x)).data, g["tanh_y"]) < 1e-6
+    assert rel_err(t.backward(okl.Tensor(gr), 0.0).data, g["tanh_dx"]) < 1e-6
+    sm = okl.SoftmaxActivationLayer()
+    assert rel_err(sm.forward(okl.Tensor(x)).data, g["softmax_y"]) < 1e-6
+    assert rel_err(sm.backward(okl.Tensor(gr)).data, g["softmax_dx"]) < 1e-5
+    kat = okl.SoftmaxActivationLayer().forward(okl.Tensor(g["softmax_kat_x"])).data        # tests/dot_test.py:28-32
+    assert np.allclose(kat, [[0.09003057, 0.24472847, 0.66524096]], atol=1e-6)
+    # x.flat[0] <= 0: the shipped np.vectorize path truncates to int64; this path returns the intended max(0, x)
+    xn = x.copy()
+    xn.flat[0] = -0.5
+    yn = okl.ReLUActivationLayer().forward(okl.Tensor(xn)).data
+    assert yn.dtype == np.float64 and rel_err(yn, np.maximum(xn, 0)) < 1e-7
+
+
+def test_pooling_golden(okl):
+    g = golden("pooling")
+    x = g["x"]
+    for kind, cls in (("max", okl.MaxPoolingLayer), ("avg", okl.AveragePoolingLayer)):
+        for ps, st in ((2, 2), (3, 2), (2, 1), (3, 3)):
+            k = f"{kind}_{ps}_{st}_"
+            lay = cls(ps, st)
+            y = lay.forward(okl.Tensor(x))
+            assert y.data.dtype == np.float64 and rel_err(y.data, g[k + "y"]) < 1e-6
+            dx = lay.backward(okl.Tensor(g[k + "g"]))
+            assert rel_err(dx.data, g[k + "dx"]) < 1e-6, k
+    assert okl.MaxPoolingLayer(2, 2).forward(okl.Tensor(g["kat_x"])).data.reshape(2, 2).tolist() == g["kat_max"].tolist()
+    assert okl.AveragePoolingLayer(2, 2).forward(okl.Tensor(g["kat_x"])).data.reshape(2, 2).tolist() == g["kat_avg"].tolist()
+    # ties: every maximum of a window receives the gradient (R4)
+    mp = okl.MaxPoolingLayer(2, 2)
+    mp.forward(okl.Tensor(np.zeros((1, 1, 2, 2))))
+    assert mp.backward(okl.Tensor(np.full((1, 1, 1, 1), 3.0))).data.tolist() == [[[[3.0, 3.0], [3.0, 3.0]]]]
+    assert okl.MaxPoolingLayer(3, 2).forward(okl.Tensor(np.zeros((1, 2, 7, 7)))).shape == (1, 2, 3, 3)
+
+
+def test_losses_golden(okl):
+    g = golden("losses")
+    ce = okl.CrossEntropyLoss()
+    p, t = okl.Tensor(g["p"]), okl.Tensor(g["t"])
+    v = ce.forward(p, t)
+    assert abs(float(v) - float(g["ce"])) < 1e-5 * abs(float(g["ce"]))
+    assert rel_err(ce.backward(p, t).data, g["ce_grad"]) < 1e-6
+    ms = okl.MSELoss()
+    o, tt = okl.Tensor(g["o"]), okl.Tensor(g["tt"])
+    assert abs(float(ms.forward(o, tt)) - float(g["mse"])) < 1e-5 * float(g["mse"])
+    assert rel_err(ms.backward(o, tt).data, g["mse_grad"]) < 1e-6
+
+
+def test_optimizers_golden(okl):
+    g = golden("optim_sched")
+    ad, sg = okl.AdamOptimizer(lr=0.01), okl.SGDOptimizer(lr=0.01, momentum=0.9)
+    wa, ws = g["w0"].copy(), g["w0"].copy()
+    for gr in g["g"]:
+        ad.update(wa, gr, "k")
+        sg.update(ws, gr, "k")
+    assert ad.t == 3
+    assert rel_err(wa, g["adam_w"]) < 1e-5 and rel_err(ws, g["sgd_w"]) < 1e-6
+
+
+def test_tensor_ops(okl):
+    rng = np.random.default_rng(3)
+    a, b = rng.standard_normal((5, 7)), rng.standard_normal((7, 4))
+    ta, tb = okl.Tensor(a), okl.Tensor(b)
+    assert rel_err(ta.dot(tb).data, a @ b) < TOL32
+    assert rel_err((ta + okl.Tensor(a * 2)).data, 3 * a) < 1e-6
+    assert rel_err((ta + okl.Tensor(b[:1, :1] * 0 + 1.5)).data, a + 1.5) < 1e-6
+    assert rel_err((ta + okl.Tensor(a[:1])).data, a + a[:1]) < 1e-6
+    assert rel_err((ta * okl.Tensor(a)).data, a * a) < 1e-6
+    assert rel_err((ta * 2.5).data, a * 2.5) < 1e-6
+    assert rel_err(ta.transpose().data, a.T) < 1e-7
+    assert rel_err(ta.reshape(7, 5).data, a.reshape(7, 5)) < 1e-7 and ta.reshape((35,)).shape == (35,)
+    out = ta.dot(tb)
+    out.backward()
+    assert rel_err(ta.grad, np.ones((5, 4)) @ b.T) < TOL32 and rel_err(tb.grad, a.T @ np.ones((5, 4))) < TOL32
+    c = ta.copy()
+    assert c is not ta and np.array_equal(c.data, ta.data)
+    assert repr(okl.Tensor([1, 2])) == "Tensor([1 2])"
+    with pytest.raises(RuntimeError):
+        okl.Tensor([1.0]).backward()
+    # write-through of assignments and augmented assignments; in-place edits of a snapshot are re-uploaded
+    t = okl.Tensor(a)
+    t.data = a * 2
+    t.data -= a
+    assert rel_err(t.dot(tb).data, a @ b) < TOL32
+    snap = t.data
+    snap[0, 0] += 100.0
+    assert abs(t.dot(tb).data[0, 0] - ((a @ b)[0, 0] + 100.0 * b[0, 0])) < 1e-3
+
+
+def test_shape_errors_are_valueerrors(okl):
+    with pytest.raises(ValueError):
+        okl.DenseLayer(4, 3).forward(okl.Tensor(np.zeros((2, 5))))
+    with pytest.raises(ValueError):
+        okl.Conv2DLayer(3, 2, 3).forward(okl.Tensor(np.zeros((2, 4, 8, 8))))
+    with pytest.raises(ValueError):
+        okl.Conv2DLayer(3, 2, 5).forward(okl.Tensor(np.zeros((2, 3, 4, 4))))
+    with pytest.raises(ValueError):
+        okl.MaxPoolingLayer().forward(okl.Tensor(np.zeros((4, 4, 3))))
+    d = okl.DenseLayer(4, 3)
+    d.forward(okl.Tensor(np.zeros((2, 4))))
+    with pytest.raises(ValueError):
+        d.backward(okl.Tensor(np.zeros((2, 5))), 0.1)
+
+
+@pytest.mark.parametrize("M,K,N", [(1, 1, 1), (3, 5, 2), (64, 64, 64), (65, 129, 67), (256, 5408, 128), (256, 128, 10),
+                                   (300, 1000, 200), (1024, 1024, 1024)])
+def test_dense_vs_oracle_sizes(okl, M, K, N):
+    rng = np.random.default_rng(M * 7 + K * 3 + N)
+    x, W, b = rng.standard_normal((M, K)), rng.standard_normal((K, N)) * 0.1, rng.standard_normal((1, N))
+    g = rng.standard_normal((M, N))
+    lay = okl.DenseLayer(K, N)
+    lay.weights.data, lay.biases.data = W, b
+    y = lay.forward(okl.Tensor(x))
+    assert rel_err(y.data, O.dense_forward(x, W, b)) < TOL32
+    dX = lay.backward(okl.Tensor(g), 0.01)
+    dW, db, dXo = O.dense_backward(x, W, g)
+    assert rel_err(dX.data, dXo) < TOL32
+    assert rel_err(lay.weights.grad, dW) < TOL32 and rel_err(lay.biases.grad, db) < TOL32
+
+
+CONV_SEEDED = [
+    # nd, N, C, spatial, O, k, s, p
+    (2, 32, 1, (28, 28), 16, 3, 1, 0),          # BASELINE config 1 at full size
+    (2, 8, 3, (32, 32), 64, 3, 1, 1),           # CIFAR layer 1
+    (2, 4, 64, (16, 16), 64, 3, 1, 1),
+    (2, 2, 32, (9, 9), 48, 3, 2, 1),
+    (2, 3, 5, (12, 10), 7, (5, 3), (2, 1), (2, 0)),
+    (1, 4, 64, (128,), 64, 3, 1, 1),            # Conv1D sequence shape, shortened
+    (1, 2, 3, (50,), 5, 7, 3, 3),
+    (3, 1, 3, (6, 20, 20), 8, 3, 1, 1),         # Conv3D video block, shortened
+    (3, 2, 2, (5, 9, 8), 4, (2, 3, 3), (1, 2, 2), (0, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("nd,N,C,sp,Oc,k,s,p", CONV_SEEDED)
+def test_conv_vs_oracle_seeded(okl, nd, N, C, sp, Oc, k, s, p):
+    rng = np.random.default_rng(1234 + N + C + Oc)
+    kt = O._tup(k, nd)
+    x = rng.standard_normal((N, C) + sp).astype(np.float32)
+    W = rng.standard_normal((Oc, C) + kt) * 0.1
+    b = rng.standard_normal((Oc, 1)) * 0.1
+    g = {"W": W.astype(np.float64 if nd == 2 else np.float32), "b": b, "stride": np.array(O._tup(s, nd)),
+         "padding": np.array(O._tup(p, nd))}
+    lay = make_conv(okl, g)
+    x64 = x.astype(np.float64)
+    W64 = g["W"].astype(np.float64)
+    y = lay.forward(okl.Tensor(x))
+    yo = O.conv_forward_fast(x64, W64, b, s, p, dtype=np.float64)
+    assert rel_err(y.data, yo) < TOL32
+    gr = rng.standard_normal(yo.shape).astype(np.float32)
+    dX = lay.backward(okl.Tensor(gr), 0.05)
+    dW, db, dXo = O.conv_backward_fast(x64, W64, gr.astype(np.float64), s, p)
+    assert rel_err(dX.data, dXo) < TOL32
+    Wt = lay.weights if hasattr(lay, "weights") else lay.filters
+    assert rel_err(Wt.grad, dW) < TOL32 and rel_err(lay.biases.grad, db) < TOL32
+    assert rel_err(Wt.data, W64 - 0.05 * dW) < TOL32
+
+
+def test_empty_batch(okl):
+    assert okl.DenseLayer(4, 2).forward(okl.Tensor(np.zeros((0, 4)))).data.shape == (0, 2)
+    assert okl.Conv2DLayer(2, 3, 3).forward(okl.Tensor(np.zeros((0, 2, 5, 5)))).data.shape == (0, 3, 3, 3)
+
+
+def test_layouts_channels_last_roundtrip(okl):
+    """The channels-last (NXC) physical layout is invisible at the host boundary."""
+    from okrolearn_b200 import _lib
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((3, 6, 5, 7))
+    t = okl.Tensor(x)
+    t._dptr(_lib.NXC)
+    assert t._layout == _lib.NXC
+    t._host = None
+    assert rel_err(t.data, x) < 1e-7
+    # pooling and activations work in either layout and agree
+    a = okl.Tensor(x)
+    a._dptr(_lib.NXC)
+    y1 = okl.MaxPoolingLayer(2, 2).forward(a).data
+    assert rel_err(y1, O.maxpool_forward(x, 2, 2)) < 1e-7
+    # conv through the strided FFMA kernel with channels-last input and output
+    lay = okl.Conv2DLayer(6, 4, 3, 1, 1)
+    lay._out_layout = _lib.NXC
+    W, b = lay.filters.data.copy(), lay.biases.data.copy()
+    c = okl.Tensor(x)
+    c._dptr(_lib.NXC)
+    y = lay.forward(c)
+    assert y._layout == _lib.NXC
+    assert rel_err(y.data, O.conv_forward_fast(x, W, b, 1, 1)) < TOL32
+    gr = rng.standard_normal(y.shape)
+    dX = lay.backward(okl.Tensor(gr), 0.0)
+    dW, db, dXo = O.conv_backward_fast(x, W, gr, 1, 1)
+    assert rel_err(dX.data, dXo) < TOL32 and rel_err(lay.filters.grad, dW) < TOL32
