@@ -386,6 +386,7 @@ def main():
         ctx.comm_init(uid, rank, world)
     np.random.seed(1234)                       # identical initial weights on every rank
     net = build_net(okl, name)
+    logging.getLogger("NeuralNetwork").setLevel(logging.CRITICAL)      # NeuralNetwork() re-arms the logger at DEBUG
     loss_fn = okl.CrossEntropyLoss() if w["loss"] == "ce" else okl.MSELoss()
     sched, opt = okl.LearningRateScheduler(0.01), okl.SGDOptimizer(lr=0.01)
 
