@@ -93,6 +93,13 @@ int okl_dense_fwd(okl_ctx* ctx, const void* X, const void* W, const void* b, voi
 int okl_dense_bwd(okl_ctx* ctx, const void* X, const void* W, const void* G, void* dX, void* dW, void* db,
                   int M, int K, int N);
 
+/* The tcgen05 GEMM the Dense products run on in TF32/BF16 mode, exposed for tests and benchmarks (reference: np.dot in
+ * Tensor.dot, tensor.py:58).  D[M,N] (row-major, ldd) = act(A . B + bias[N]); A, B, D, bias are fp32 device tensors.
+ *   a_mn = 0: A stored [M][K] (lda);  a_mn = 1: A stored [K][M] (lda)   -  b_mn = 0: B stored [N][K];  b_mn = 1: B stored [K][N]
+ *   kind 0 = TF32 operands, 1 = BF16 operands (converted on the device); accumulation is fp32 in tensor memory. */
+int okl_tc_gemm(okl_ctx* ctx, int kind, int a_mn, int b_mn, int M, int N, int K, const void* A, long long lda, const void* B,
+                long long ldb, void* D, long long ldd, const void* bias, int act);
+
 /* ------------------------------------------------------------------ Conv1D/2D/3D (okl.py:669-764, 767-883, 936-1049)
  * nd = 1,2,3; unused trailing entries of in/k/s/p are ignored.  Cross-correlation, zero padding both sides,
  * output extent (in + 2p - k) / s + 1 (floor).  filters (O,C,*k) and biases (O) are always in the reference layout. */

@@ -41,6 +41,8 @@ struct okl_ctx {
   size_t staging_bytes = 0;
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
+  void* bf16_scratch = nullptr;         // bf16 copies of GEMM operands (OKL_BF16 mode)
+  size_t bf16_scratch_bytes = 0;
   // comm
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;

@@ -66,6 +66,7 @@ extern "C" int okl_ctx_destroy(okl_ctx* ctx) {
   if (ctx->workspace) cudaFree(ctx->workspace);
   if (ctx->staging) cudaFree(ctx->staging);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  if (ctx->bf16_scratch) cudaFree(ctx->bf16_scratch);
   cudaEventDestroy(ctx->ev_fork);
   cudaEventDestroy(ctx->ev_join);
   cudaEventDestroy(ctx->ev_t0);

@@ -1,0 +1,667 @@
+// tcgen05 tensor-core GEMM for sm_100a: D[M,N] = act(A . B + bias), TF32 or BF16 operands, FP32 accumulation in TMEM.
+//
+// Used for DenseLayer forward / dgrad / wgrad (okl.py:29-47) in the OKL_TF32 / OKL_BF16 modes.  All three products run
+// on the tensors exactly as the reference lays them out (X (M,K), W (K,N), G (M,N), all row-major) - the operand
+// "major-ness" is expressed in the UMMA descriptors instead of transposing anything:
+//     fwd   Y  = X  . W      A = X  K-major,   B = W  MN-major
+//     dgrad dX = G  . W^T    A = G  K-major,   B = W  K-major
+//     wgrad dW = X^T . G     A = X  MN-major,  B = G  MN-major
+//
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+//     warp 0    TMA producer : cp.async.bulk.tensor (128B-swizzled boxes) into a multi-stage smem ring, mbarrier expect_tx
+//     warp 1    MMA issuer   : one elected thread issues tcgen05.mma (M=128, N=BN, K=8 tf32 / 16 bf16) into TMEM,
+//                              tcgen05.commit releases smem stages and publishes the accumulator
+//     warp 2    TMEM allocator (2 x BN columns: the epilogue of tile i overlaps the main loop of tile i+1)
+//     warps 4-7 epilogue     : tcgen05.ld -> registers -> bias + activation -> 128-bit global stores
+// Small problems are split along K over CTAs (fp32 partials in a workspace, reduced in fixed order by a second kernel
+// that applies the epilogue) so that e.g. the 256x5408x128 DenseLayer of the MNIST CNN still fills the 148 SMs.
+#include "common.cuh"
+
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 256;
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU (a wedged device costs everyone a box) - trap after ~2 s instead.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("okl tc kernel: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (KIND == 0) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// make the mbarrier track completion of all tcgen05 ops issued so far by this thread (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ descriptors
+// shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
+// version 1 <<46 | layout SWIZZLE_128B (2) <<61
+// layout: 2 = SWIZZLE_128B (16-byte swizzle atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms: the only layout the hardware
+// accepts for MN-major 32-bit (tf32) operands; pairs with the TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1)<<4 | a_format<<7 | b_format<<10 | a_major<<15 |
+// b_major<<16 | (N>>3)<<17 | (M>>4)<<24
+__host__ __device__ constexpr uint32_t make_idesc(int kind, bool a_mn, bool b_mn, int M, int N) {
+  uint32_t fmt = kind == 0 ? 2u : 1u;      // TF32 = 2, BF16 = 1
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case OKL_ACT_RELU: return v > 0.f ? v : 0.f;
+    case OKL_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case OKL_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+struct TcGemmParams {
+  int M, N, K;
+  int tiles_m, tiles_n, splits, kb_per_split, kb_total;
+  float* D;            // output (ldd) when splits == 1
+  long long ldd;
+  const float* bias;   // per-column bias or nullptr
+  int act;
+  float* ws;           // [splits][M][N] partials when splits > 1
+  __nv_bfloat16* D16;  // optional bf16 shadow of D (same ld), or nullptr
+};
+
+template <int KIND, int BN>
+struct TcCfg {
+  static constexpr int ELEM = KIND == 0 ? 4 : 2;
+  static constexpr int BK = 128 / ELEM;                 // elements of K per stage (one 128-byte swizzle row)
+  static constexpr int UMMA_K = 32 / ELEM;              // 8 (tf32) / 16 (bf16)
+  static constexpr int EPC = 128 / ELEM;                // elements per 128-byte chunk along MN (MN-major operands)
+  static constexpr int A_BYTES = TC_BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int KIND, bool A_MN, bool B_MN, int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmParams p) {
+  using Cfg = TcCfg<KIND, BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < Cfg::STAGES; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);      // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_work = p.tiles_m * p.tiles_n * p.splits;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w / (p.tiles_m * p.tiles_n);
+        const int t = w - split * (p.tiles_m * p.tiles_n);
+        const int tm = t % p.tiles_m, tn = t / p.tiles_m;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int m0 = tm * TC_BM, n0 = tn * BN;
+        for (int kb = kb0; kb < kb1; kb++) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const int k0 = kb * Cfg::BK;
+          if (!A_MN) {
+            tma_load_2d(&tmA, &full_bar[stage], sa, k0, m0);                       // box {BK, 128}: rows = m
+          } else {
+#pragma unroll
+            for (int c = 0; c < TC_BM / Cfg::EPC; c++)                             // box {EPC, BK}: rows = k
+              tma_load_2d(&tmA, &full_bar[stage], sa + c * (Cfg::BK * 128), m0 + c * Cfg::EPC, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(&tmB, &full_bar[stage], sb, k0, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / Cfg::EPC; c++)
+              tma_load_2d(&tmB, &full_bar[stage], sb + c * (Cfg::BK * 128), n0 + c * Cfg::EPC, k0);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(KIND, A_MN, B_MN, TC_BM, BN);
+      // K-major: rows 128 B apart, 8-row groups 1024 B apart.  MN-major: 8 k-rows per 1024 B atom (SBO), next 128-byte
+      // chunk along MN one region (BK rows x 128 B) further (LBO).
+      constexpr uint32_t a_lbo = A_MN ? Cfg::BK * 128 : 16, b_lbo = B_MN ? Cfg::BK * 128 : 16;
+      // MN-major tf32 uses the 32-byte-atom swizzle: 4 k-rows (512 B) per atom instead of 8 (1024 B)
+      constexpr uint32_t a_lay = (A_MN && KIND == 0) ? 1 : 2, b_lay = (B_MN && KIND == 0) ? 1 : 2;
+      constexpr uint32_t a_sbo = (A_MN && KIND == 0) ? 512 : 1024, b_sbo = (B_MN && KIND == 0) ? 512 : 1024;
+      constexpr uint32_t a_adv = A_MN ? (Cfg::UMMA_K * 128) >> 4 : 32 >> 4, b_adv = B_MN ? (Cfg::UMMA_K * 128) >> 4 : 32 >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w / (p.tiles_m * p.tiles_n);
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; kb++) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, a_lay);
+          const uint64_t bdesc = make_smem_desc(sa + Cfg::A_BYTES, b_lbo, b_sbo, b_lay);
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / Cfg::UMMA_K; k++)
+            umma<KIND>(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);                 // smem stage reusable once these MMAs have read it
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);                      // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue (warps 4..7 <-> TMEM lanes 0..127)
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = (p.splits > 1) ? ((p.N & 3) == 0) : ((p.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int split = w / (p.tiles_m * p.tiles_n);
+      const int t = w - split * (p.tiles_m * p.tiles_n);
+      const int tm = t % p.tiles_m, tn = t / p.tiles_m;
+      const int m = tm * TC_BM + q * 32 + lane;
+      const int n0 = tn * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      float* out_row;
+      long long ld;
+      if (p.splits > 1) { ld = p.N; out_row = p.ws + ((size_t)split * p.M + m) * (size_t)p.N; }
+      else { ld = p.ldd; out_row = p.D + (size_t)m * (size_t)p.ldd; }
+      (void)ld;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
+        tmem_ld_wait();
+        if (m < p.M) {
+          const int nb = n0 + c;
+          if (p.splits > 1) {
+            if (vec_ok && nb + 32 <= p.N) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(out_row + nb + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                           __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (nb + j < p.N) out_row[nb + j] = __uint_as_float(v[j]);
+            }
+          } else {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              float x = __uint_as_float(v[j]);
+              if (p.bias && nb + j < p.N) x += __ldg(p.bias + nb + j);
+              f[j] = act_apply(x, p.act);
+            }
+            if (vec_ok && nb + 32 <= p.N) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out_row + nb + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (nb + j < p.N) out_row[nb + j] = f[j];
+            }
+            if (p.D16) {
+              __nv_bfloat16* o16 = p.D16 + (size_t)m * (size_t)p.ldd;
+#pragma unroll
+              for (int j = 0; j < 32; j++)
+                if (nb + j < p.N) o16[nb + j] = __float2bfloat16(f[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// fixed-order reduction of split-K partials + bias + activation
+__global__ void tc_splitk_reduce(const float* __restrict__ ws, float* __restrict__ D, long long ldd, const float* __restrict__ bias,
+                                 int act, int M, int N, int splits, __nv_bfloat16* __restrict__ D16) {
+  size_t total = (size_t)M * N;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; z++) s += ws[(size_t)z * total + i];
+    int m = (int)(i / N), n = (int)(i - (size_t)m * N);
+    if (bias) s += __ldg(bias + n);
+    s = act_apply(s, act);
+    D[(size_t)m * ldd + n] = s;
+    if (D16) D16[(size_t)m * ldd + n] = __float2bfloat16(s);
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  size_t n2 = n >> 1;
+  for (size_t j = i; j < n2; j += st) {
+    float2 v = reinterpret_cast<const float2*>(s)[j];
+    reinterpret_cast<__nv_bfloat162*>(d)[j] = __floats2bfloat162_rn(v.x, v.y);
+  }
+  if (i == 0 && (n & 1)) d[n - 1] = __float2bfloat16(s[n - 1]);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D tensor map over a row-major matrix [outer][inner] with 128-byte swizzle
+int make_map_2d(CUtensorMap* map, int kind, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems, uint32_t box_inner,
+                uint32_t box_outer, bool atom32 = false) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    okl_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return OKL_ERR_CUDA;
+  }
+  const int es = kind == 0 ? 4 : 2;
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {ld_elems * es};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                  gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    okl_set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu box=%ux%u)", (int)r,
+                  (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_elems, box_inner, box_outer);
+    return OKL_ERR_CUDA;
+  }
+  return OKL_OK;
+}
+
+template <int KIND, bool A_MN, bool B_MN, int BN>
+int launch_cfg(okl_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const TcGemmParams& p) {
+  using Cfg = TcCfg<KIND, BN>;
+  auto kern = tc_gemm_kernel<KIND, A_MN, B_MN, BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OKL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  int total = p.tiles_m * p.tiles_n * p.splits;
+  int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(ta, tb, p);
+  OKL_LAUNCHED(ctx, "tc_gemm_kernel");
+  return OKL_OK;
+}
+
+template <int KIND, bool A_MN, bool B_MN>
+int launch_bn(okl_ctx* ctx, int bn, const CUtensorMap& ta, const CUtensorMap& tb, const TcGemmParams& p) {
+  switch (bn) {
+    case 32: return launch_cfg<KIND, A_MN, B_MN, 32>(ctx, ta, tb, p);
+    case 64: return launch_cfg<KIND, A_MN, B_MN, 64>(ctx, ta, tb, p);
+    case 128: return launch_cfg<KIND, A_MN, B_MN, 128>(ctx, ta, tb, p);
+    case 256: return launch_cfg<KIND, A_MN, B_MN, 256>(ctx, ta, tb, p);
+  }
+  okl_set_error("unsupported BN %d", bn);
+  return OKL_ERR_INVALID;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s && *s ? atoi(s) : dflt;
+}
+
+}  // namespace
+
+namespace {
+struct Bf16Scratch {
+  void* a = nullptr;
+  void* b = nullptr;
+};
+int bf16_operands(okl_ctx* ctx, const float* A, size_t na, const float* B, size_t nb, Bf16Scratch& out);
+}  // namespace
+int okl_f32_to_bf16(okl_ctx* ctx, const float* src, void* dst, size_t n);
+
+// Generic entry: D[M,N] (row-major, ldd) = act(A . B + bias).
+//   a_mn == 0: A stored [M][K] (lda, K contiguous);  a_mn == 1: A stored [K][M] (lda, M contiguous)
+//   b_mn == 0: B stored [N][K] (ldb, K contiguous);  b_mn == 1: B stored [K][N] (ldb, N contiguous)
+// kind 0 = TF32 (A,B are fp32), kind 1 = BF16 (A,B are bf16).
+int okl_tc_gemm_raw(okl_ctx* ctx, int kind, int a_mn, int b_mn, int M, int N, int K, const void* A, long long lda, const void* B,
+                    long long ldb, float* D, long long ldd, const float* bias, int act, void* D16) {
+  const int es = kind == 0 ? 4 : 2;
+  const int bk = 128 / es, epc = 128 / es;
+  OKL_REQUIRE(M >= 1 && N >= 1 && K >= 1, "tc_gemm: bad shape");
+  OKL_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "tc_gemm: operands must be 16-byte aligned");
+  OKL_REQUIRE((lda * es) % 16 == 0 && (ldb * es) % 16 == 0, "tc_gemm: leading dimensions must be multiples of 16 bytes");
+  // tile / split selection
+  int bn = env_int("OKL_TC_BN", 0);
+  const int tiles_m = (M + TC_BM - 1) / TC_BM;
+  const int kb_total = (K + bk - 1) / bk;
+  if (bn == 0) {
+    auto tiles = [&](int b) { return (long long)tiles_m * ((N + b - 1) / b); };
+    if (N > 128 && tiles(256) >= ctx->sm_count) bn = 256;
+    else if (N > 64 && tiles(128) >= ctx->sm_count / 2) bn = 128;
+    else if (N > 32 && (tiles(64) >= ctx->sm_count / 2 || N > 64)) bn = N > 128 ? 128 : 64;
+    else bn = N > 32 ? 64 : 32;
+  }
+  if (b_mn && bn < epc) bn = epc;                            // an MN-major B tile is loaded in 128-byte chunks along N
+  // keep every TMA box inside the tensor's inner extent (tiny operands are the FFMA kernels' job)
+  if ((a_mn ? M : K) < (a_mn ? epc : bk) || (b_mn ? N : K) < (b_mn ? epc : bk)) {
+    okl_set_error("tc_gemm: operand smaller than one 128-byte TMA box (M=%d N=%d K=%d)", M, N, K);
+    return OKL_ERR_UNSUPPORTED;
+  }
+  const int tiles_n = (N + bn - 1) / bn;
+  int splits = env_int("OKL_TC_SPLITS", 0);
+  if (splits == 0) {
+    long long tiles = (long long)tiles_m * tiles_n;
+    splits = 1;
+    if (tiles < ctx->sm_count && kb_total >= 8) {
+      splits = (int)((ctx->sm_count + tiles - 1) / tiles);
+      int max_splits = kb_total / 4;
+      if (splits > max_splits) splits = max_splits;
+      if (splits > 64) splits = 64;
+      if (splits < 1) splits = 1;
+    }
+  }
+  int kb_per_split = (kb_total + splits - 1) / splits;
+  splits = (kb_total + kb_per_split - 1) / kb_per_split;
+
+  CUtensorMap ta, tb;
+  int s;
+  if (!a_mn) s = make_map_2d(&ta, kind, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, bk, TC_BM);
+  else s = make_map_2d(&ta, kind, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, epc, bk, kind == 0);
+  if (s != OKL_OK) return s;
+  if (!b_mn) s = make_map_2d(&tb, kind, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, bk, bn);
+  else s = make_map_2d(&tb, kind, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, epc, bk, kind == 0);
+  if (s != OKL_OK) return s;
+
+  TcGemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.splits = splits; p.kb_per_split = kb_per_split; p.kb_total = kb_total;
+  p.D = D; p.ldd = ldd; p.bias = bias; p.act = act; p.ws = nullptr; p.D16 = (__nv_bfloat16*)D16;
+  if (splits > 1) {
+    s = okl_ensure_workspace(ctx, (size_t)splits * M * N * sizeof(float));
+    if (s != OKL_OK) return s;
+    p.ws = (float*)ctx->workspace;
+  }
+  if (kind == 0) {
+    if (!a_mn && !b_mn) s = launch_bn<0, false, false>(ctx, bn, ta, tb, p);
+    else if (!a_mn && b_mn) s = launch_bn<0, false, true>(ctx, bn, ta, tb, p);
+    else if (a_mn && !b_mn) s = launch_bn<0, true, false>(ctx, bn, ta, tb, p);
+    else s = launch_bn<0, true, true>(ctx, bn, ta, tb, p);
+  } else {
+    if (!a_mn && !b_mn) s = launch_bn<1, false, false>(ctx, bn, ta, tb, p);
+    else if (!a_mn && b_mn) s = launch_bn<1, false, true>(ctx, bn, ta, tb, p);
+    else if (a_mn && !b_mn) s = launch_bn<1, true, false>(ctx, bn, ta, tb, p);
+    else s = launch_bn<1, true, true>(ctx, bn, ta, tb, p);
+  }
+  if (s != OKL_OK) return s;
+  if (splits > 1) {
+    size_t total = (size_t)M * N;
+    tc_splitk_reduce<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>(p.ws, D, ldd, bias, act, M, N, splits, p.D16);
+    OKL_LAUNCHED(ctx, "tc_splitk_reduce");
+  }
+  return OKL_OK;
+}
+
+extern "C" int okl_tc_gemm(okl_ctx* ctx, int kind, int a_mn, int b_mn, int M, int N, int K, const void* A, long long lda, const void* B,
+                           long long ldb, void* D, long long ldd, const void* bias, int act) {
+  OKL_REQUIRE(ctx && A && B && D, "NULL argument");
+  OKL_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (tf32) or 1 (bf16)");
+  OKL_REQUIRE(ctx->cc >= 100, "tcgen05 kernels need compute capability 10.x");
+  if (kind == 0)
+    return okl_tc_gemm_raw(ctx, 0, a_mn, b_mn, M, N, K, A, lda, B, ldb, (float*)D, ldd, (const float*)bias, act, nullptr);
+  // bf16: convert the fp32 operands (dense, ld == inner extent) into scratch first
+  size_t na = (size_t)(a_mn ? K : M) * lda, nb = (size_t)(b_mn ? K : N) * ldb;
+  Bf16Scratch sc;
+  int s = bf16_operands(ctx, (const float*)A, na, (const float*)B, nb, sc);
+  if (s != OKL_OK) return s;
+  return okl_tc_gemm_raw(ctx, 1, a_mn, b_mn, M, N, K, sc.a, lda, sc.b, ldb, (float*)D, ldd, (const float*)bias, act, nullptr);
+}
+
+int okl_f32_to_bf16(okl_ctx* ctx, const float* src, void* dst, size_t n) {
+  if (n == 0) return OKL_OK;
+  f32_to_bf16_kernel<<<okl_grid_1d(ctx, (n + 1) / 2, 256), 256, 0, ctx->stream>>>(src, (__nv_bfloat16*)dst, n);
+  OKL_LAUNCHED(ctx, "f32_to_bf16");
+  return OKL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ dense entry points
+bool okl_tc_dense_supported(okl_ctx* ctx, int M, int K, int N) {
+  if (ctx->cc < 100) return false;
+  if (env_int("OKL_TC_DISABLE", 0)) return false;
+  // TMA needs 16-byte multiples for every leading dimension used: X ld = K, W ld = N, G ld = N (fp32: multiples of 4;
+  // bf16 shadows: multiples of 8)
+  const int q = ctx->precision == OKL_BF16 ? 8 : 4;
+  if (K % q || N % q) return false;
+  if (M < 64 || K < 64 || N < 64) return false;              // every TMA box must fit inside its operand
+  if ((long long)M * K * N < (1LL << 18)) return false;     // tiny products: launch-bound either way, keep FFMA
+  return true;
+}
+
+namespace {
+// BF16 mode, first cut: operands are converted into a scratch area per call (the fp32 tensors stay the storage of record).
+int bf16_operands(okl_ctx* ctx, const float* A, size_t na, const float* B, size_t nb, Bf16Scratch& out) {
+  size_t abytes = ((na * 2 + 255) / 256) * 256, bbytes = ((nb * 2 + 255) / 256) * 256;
+  if (ctx->bf16_scratch_bytes < abytes + bbytes) {
+    if (ctx->capturing) {
+      okl_set_error("bf16 scratch must be sized before graph capture (run one eager step first)");
+      return OKL_ERR_INVALID;
+    }
+    OKL_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->bf16_scratch) cudaFree(ctx->bf16_scratch);
+    OKL_CHECK_CUDA(cudaMalloc(&ctx->bf16_scratch, abytes + bbytes));
+    ctx->bf16_scratch_bytes = abytes + bbytes;
+  }
+  out.a = ctx->bf16_scratch;
+  out.b = (uint8_t*)ctx->bf16_scratch + abytes;
+  int s = okl_f32_to_bf16(ctx, A, out.a, na);
+  if (s != OKL_OK) return s;
+  return okl_f32_to_bf16(ctx, B, out.b, nb);
+}
+}  // namespace
+
+int okl_tc_dense_fwd(okl_ctx* ctx, const float* X, const float* W, const float* b, float* Y, int M, int K, int N, int act) {
+  if (ctx->precision == OKL_BF16) {
+    Bf16Scratch sc;
+    int s = bf16_operands(ctx, X, (size_t)M * K, W, (size_t)K * N, sc);
+    if (s != OKL_OK) return s;
+    return okl_tc_gemm_raw(ctx, 1, 0, 1, M, N, K, sc.a, K, sc.b, N, Y, N, b, act, nullptr);
+  }
+  return okl_tc_gemm_raw(ctx, 0, 0, 1, M, N, K, X, K, W, N, Y, N, b, act, nullptr);
+}
+
+int okl_tc_dense_dx(okl_ctx* ctx, const float* G, const float* W, float* dX, int M, int K, int N) {
+  // dX[M,K] = G[M,N] . W^T : reduction over N; B'(n'=kin, k'=nout) = W[kin][nout] is K-major as stored
+  if (ctx->precision == OKL_BF16) {
+    Bf16Scratch sc;
+    int s = bf16_operands(ctx, G, (size_t)M * N, W, (size_t)K * N, sc);
+    if (s != OKL_OK) return s;
+    return okl_tc_gemm_raw(ctx, 1, 0, 0, M, K, N, sc.a, N, sc.b, N, dX, K, nullptr, OKL_ACT_NONE, nullptr);
+  }
+  return okl_tc_gemm_raw(ctx, 0, 0, 0, M, K, N, G, N, W, N, dX, K, nullptr, OKL_ACT_NONE, nullptr);
+}
+
+int okl_tc_dense_dw(okl_ctx* ctx, const float* X, const float* G, float* dW, int M, int K, int N) {
+  // dW[K,N] = X^T . G : reduction over the batch M; both operands MN-major as stored
+  if (ctx->precision == OKL_BF16) {
+    Bf16Scratch sc;
+    int s = bf16_operands(ctx, X, (size_t)M * K, G, (size_t)M * N, sc);
+    if (s != OKL_OK) return s;
+    return okl_tc_gemm_raw(ctx, 1, 1, 1, K, N, M, sc.a, K, sc.b, N, dW, N, nullptr, OKL_ACT_NONE, nullptr);
+  }
+  return okl_tc_gemm_raw(ctx, 0, 1, 1, K, N, M, X, K, G, N, dW, N, nullptr, OKL_ACT_NONE, nullptr);
+}
