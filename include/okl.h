@@ -135,22 +135,31 @@ int okl_scale(okl_ctx* ctx, void* x, size_t n, float alpha);
 
 /* ------------------------------------------------------------------ pooling (okl.py:1715-1831 + repairs R4,R5) */
 int okl_pool_fwd(okl_ctx* ctx, int kind, const void* x, void* y, int N, int C, int H, int W, int pool, int stride, int layout);
+/* relu_mask != 0 additionally zeroes dx where x <= 0: the fused backward of a ReLU placed right before the pooling layer
+ * (g * (x > 0), okl.py:107), so that Conv -> ReLU -> MaxPool needs one backward pass over the conv output, not two. */
 int okl_pool_bwd(okl_ctx* ctx, int kind, const void* x, const void* g, void* dx, int N, int C, int H, int W, int pool,
-                 int stride, int layout);
+                 int stride, int layout, int relu_mask);
 
 /* ------------------------------------------------------------------ softmax + losses (okl.py:355-399, 1380-1409, 1833-1839) */
 int okl_softmax_fwd(okl_ctx* ctx, const void* x, void* p, int rows, int cols);
 int okl_softmax_bwd(okl_ctx* ctx, const void* p, const void* g, void* dx, int rows, int cols);
-/* loss[0] = mean_r(-log(clip(p)[r,t_r])) over `rows`; grad = (clip(p) - onehot) / denom  (denom = global batch) */
-int okl_ce_fwd_bwd(okl_ctx* ctx, const void* p, const void* targets_i32, void* loss, void* grad, int rows, int cols, float denom);
+/* loss[0] = mean_r(-log(clip(p)[r,t_r])) over `rows`; grad = (clip(p) - onehot) / denom  (denom = global batch).
+ * loss_accum (optional): device scalar that gets += loss[0] (per-epoch loss sum, okl.py:2973, without a host round trip).
+ * softmax_dx (optional): also writes p * (grad - sum_k grad_k p_k), the backward of the softmax layer that produced p
+ * (okl.py:376-393), so a Softmax + CrossEntropy head costs one kernel for loss, loss gradient and softmax gradient. */
+int okl_ce_fwd_bwd(okl_ctx* ctx, const void* p, const void* targets_i32, void* loss, void* grad, int rows, int cols, float denom,
+                   void* loss_accum, void* softmax_dx);
 /* loss[0] = sum((o-t)^2) / n ; grad = 2 (o - t) / denom   (denom = global element count) */
-int okl_mse_fwd_bwd(okl_ctx* ctx, const void* o, const void* t, void* loss, void* grad, size_t n, float denom);
+int okl_mse_fwd_bwd(okl_ctx* ctx, const void* o, const void* t, void* loss, void* grad, size_t n, float denom, void* loss_accum);
 int okl_read_scalar(okl_ctx* ctx, const void* dev_f32, float* out);
 
 /* ------------------------------------------------------------------ parameter updates
  * reference rule (okl.py:39-45, 744-748, 872-878, 1029-1033): gacc += g ; w -= lr * gacc  (gacc never reset).
  * lr_dev, when non-NULL, is a device fp32 scalar read at run time (lets a captured CUDA graph follow the scheduler). */
 int okl_accum_update(okl_ctx* ctx, void* w, void* gacc, const void* g, size_t n, float lr, const void* lr_dev);
+/* the same rule applied to `count` parameter buckets in one launch (host arrays of device pointers / element counts) */
+int okl_accum_update_multi(okl_ctx* ctx, int count, void* const* w, void* const* gacc, const void* const* g, const size_t* n,
+                           float lr, const void* lr_dev);
 /* optimizers.py:140-144: v = mu v - lr g ; w += v */
 int okl_sgd_update(okl_ctx* ctx, void* w, void* v, const void* g, size_t n, float lr, float momentum);
 /* optimizers.py:28-42 with t supplied by the caller (it increments per update call) */

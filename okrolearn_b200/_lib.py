@@ -74,13 +74,14 @@ SIGNATURES = {
     "okl_binary": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _sz]),
     "okl_scale": (_i, [_vp, _vp, _sz, _f]),
     "okl_pool_fwd": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i]),
-    "okl_pool_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i]),
+    "okl_pool_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i]),
     "okl_softmax_fwd": (_i, [_vp, _vp, _vp, _i, _i]),
     "okl_softmax_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i]),
-    "okl_ce_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f]),
-    "okl_mse_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _f]),
+    "okl_ce_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp]),
+    "okl_mse_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _f, _vp]),
     "okl_read_scalar": (_i, [_vp, _vp, _P(_f)]),
     "okl_accum_update": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _vp]),
+    "okl_accum_update_multi": (_i, [_vp, _i, _P(_vp), _P(_vp), _P(_vp), _P(_sz), _f, _vp]),
     "okl_sgd_update": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f]),
     "okl_adam_update": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _i]),
     "okl_graph_begin": (_i, [_vp]),

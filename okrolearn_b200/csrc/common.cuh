@@ -41,6 +41,8 @@ struct okl_ctx {
   size_t staging_bytes = 0;
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
+  void* tc_dbg = nullptr;               // debug: timestamp buffer for the tcgen05 GEMM
+  int* tile_counters = nullptr;         // split-K arrival counters of the tcgen05 GEMM (all zero between launches)
   void* bf16_scratch = nullptr;         // bf16 copies of GEMM operands (OKL_BF16 mode)
   size_t bf16_scratch_bytes = 0;
   // comm
@@ -116,3 +118,8 @@ bool okl_tc_conv_supported(okl_ctx*, const okl_conv_desc*);
 int okl_tc_conv_fprop(okl_ctx*, const okl_conv_desc*, const float* x, const float* W, const float* b, float* y);
 int okl_tc_conv_dgrad(okl_ctx*, const okl_conv_desc*, const float* g, const float* W, float* dx);
 int okl_tc_conv_wgrad(okl_ctx*, const okl_conv_desc*, const float* x, const float* g, float* dW);
+// direct fp32 kernels for tiny reduction dims (first layers): okl_conv_small.cu
+bool okl_conv_small_fprop_ok(const okl_conv_desc*);
+bool okl_conv_small_wgrad_ok(const okl_conv_desc*);
+int okl_conv_small_fprop(okl_ctx*, const okl_conv_desc*, const float* x, const float* W, const float* b, float* y);
+int okl_conv_small_wgrad(okl_ctx*, const okl_conv_desc*, const float* x, const float* g, float* dW, float* db);

@@ -67,6 +67,7 @@ extern "C" int okl_ctx_destroy(okl_ctx* ctx) {
   if (ctx->staging) cudaFree(ctx->staging);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   if (ctx->bf16_scratch) cudaFree(ctx->bf16_scratch);
+  if (ctx->tile_counters) cudaFree(ctx->tile_counters);
   cudaEventDestroy(ctx->ev_fork);
   cudaEventDestroy(ctx->ev_join);
   cudaEventDestroy(ctx->ev_t0);

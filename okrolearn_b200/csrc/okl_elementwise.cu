@@ -145,7 +145,8 @@ __global__ void pool_fwd_kernel(const float* __restrict__ x, float* __restrict__
 // Gather form of okl.py:1753-1766 [R4] / 1809-1819 [R5]: each input position looks at the windows that contain it,
 // in the reference's raster order (i then j).  Max: the last window whose max equals x assigns its gradient
 // (ties -> every maximum of a window receives it; overlapping windows overwrite).  Avg: contributions add.
-__global__ void pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gr, float* __restrict__ dx, PoolGeom g, int kind) {
+__global__ void pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gr, float* __restrict__ dx, PoolGeom g, int kind,
+                                int relu_mask) {
   size_t total = (size_t)g.N * g.C * g.H * g.W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int n, c, h, w;
@@ -169,7 +170,38 @@ __global__ void pool_bwd_kernel(const float* __restrict__ x, const float* __rest
           if (xv == m) out = __ldg(gb + oi * g.ys[2] + oj * g.ys[3]);
         }
     }
+    if (relu_mask && !(__ldg(xb + h * g.xs[2] + w * g.xs[3]) > 0.f)) out = 0.f;
     dx[i] = out;
+  }
+}
+
+// 2x2 / stride 2 windows on channels-first tensors with even H, W: one thread per window, 64-bit accesses, no index math
+// beyond one division per thread.  relu_mask fuses the backward of a ReLU that precedes the pooling layer
+// (dx = 0 where x <= 0), saving one full pass over the largest activation tensor of the network.
+__global__ void maxpool2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t total, int OW, int W) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i / OW;                       // r = (n*C + c)*OH + oh
+    int ow = (int)(i - r * OW);
+    const float* p = x + (r * 2) * (size_t)W + 2 * ow;
+    float2 a = *reinterpret_cast<const float2*>(p), b = *reinterpret_cast<const float2*>(p + W);
+    y[i] = fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y));
+  }
+}
+__global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dx, size_t total, int OW,
+                                    int W, int relu_mask) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i / OW;
+    int ow = (int)(i - r * OW);
+    size_t off = (r * 2) * (size_t)W + 2 * ow;
+    float2 a = *reinterpret_cast<const float2*>(x + off), b = *reinterpret_cast<const float2*>(x + off + W);
+    float m = fmaxf(fmaxf(a.x, a.y), fmaxf(b.x, b.y));
+    float gv = g[i];
+    if (relu_mask && !(m > 0.f)) gv = 0.f;   // the window maximum is the only candidate; y <= 0 => relu'(x) = 0
+    float2 da, db;
+    da.x = a.x == m ? gv : 0.f; da.y = a.y == m ? gv : 0.f;
+    db.x = b.x == m ? gv : 0.f; db.y = b.y == m ? gv : 0.f;
+    *reinterpret_cast<float2*>(dx + off) = da;
+    *reinterpret_cast<float2*>(dx + off + W) = db;
   }
 }
 
@@ -234,6 +266,87 @@ __global__ void ce_kernel(const float* __restrict__ p, const int* __restrict__ t
   }
 }
 
+// Small problems (rows*cols <= 64K): ONE block does the loss, the CE gradient and - when asked - the backward of the softmax
+// layer that produced p (dz = p * (g - sum_k g_k p_k), okl.py:376-393), one warp per row, and adds the batch loss to the
+// epoch accumulator.  Fixed reduction order, no second launch.
+__global__ void ce_fused_small_kernel(const float* __restrict__ p, const int* __restrict__ t, float* __restrict__ loss, float* __restrict__ grad,
+                                      float* __restrict__ dz, float* __restrict__ loss_acc, int rows, int cols, float inv_denom) {
+  __shared__ float sh[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float lsum = 0.f;
+  for (int r = warp; r < rows; r += nw) {
+    const int tc = t[r];
+    const float* pr = p + (size_t)r * cols;
+    float dot = 0.f;
+    for (int c = lane; c < cols; c += 32) {
+      const float pv = pr[c];
+      float gv = clip_p(pv);
+      if (c == tc) gv -= 1.f;
+      gv *= inv_denom;
+      grad[(size_t)r * cols + c] = gv;
+      dot += gv * pv;
+    }
+    if (dz) {
+      dot = warp_sum(dot);
+      for (int c = lane; c < cols; c += 32) {
+        const float pv = pr[c];
+        float gv = clip_p(pv);
+        if (c == tc) gv -= 1.f;
+        gv *= inv_denom;
+        dz[(size_t)r * cols + c] = pv * (gv - dot);
+      }
+    }
+    if (lane == 0) lsum += -logf((tc >= 0 && tc < cols) ? clip_p(pr[tc]) : 1.f);
+  }
+  lsum = block_sum(lsum, sh);
+  if (threadIdx.x == 0) {
+    const float l = rows > 0 ? lsum / (float)rows : 0.f;
+    loss[0] = l;
+    if (loss_acc) loss_acc[0] += l;
+  }
+}
+
+// Same contract for few classes (cols <= 32): one THREAD per row keeps the whole row in registers, so the 256 rows of a batch
+// are 256 independent two-load chains instead of 8 sequential rows per warp.
+template <int MAXC>
+__global__ void ce_fused_rowthread_kernel(const float* __restrict__ p, const int* __restrict__ t, float* __restrict__ loss,
+                                          float* __restrict__ grad, float* __restrict__ dz, float* __restrict__ loss_acc, int rows, int cols,
+                                          float inv_denom) {
+  __shared__ float sh[32];
+  float lsum = 0.f;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    const int tc = t[r];
+    const float* pr = p + (size_t)r * cols;
+    float pv[MAXC], gv[MAXC];
+    float dot = 0.f, pt = 1.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; c++)
+      if (c < cols) pv[c] = pr[c];
+#pragma unroll
+    for (int c = 0; c < MAXC; c++)
+      if (c < cols) {
+        float g = clip_p(pv[c]);
+        if (c == tc) { pt = g; g -= 1.f; }
+        g *= inv_denom;
+        gv[c] = g;
+        dot += g * pv[c];
+        grad[(size_t)r * cols + c] = g;
+      }
+    if (dz) {
+#pragma unroll
+      for (int c = 0; c < MAXC; c++)
+        if (c < cols) dz[(size_t)r * cols + c] = pv[c] * (gv[c] - dot);
+    }
+    lsum += -logf(pt);
+  }
+  lsum = block_sum(lsum, sh);
+  if (threadIdx.x == 0) {
+    const float l = rows > 0 ? lsum / (float)rows : 0.f;
+    loss[0] = l;
+    if (loss_acc) loss_acc[0] += l;
+  }
+}
+
 __global__ void mse_kernel(const float* __restrict__ o, const float* __restrict__ t, float* __restrict__ partial, float* __restrict__ grad,
                            size_t n, float scale) {
   __shared__ float sh[32];
@@ -246,13 +359,17 @@ __global__ void mse_kernel(const float* __restrict__ o, const float* __restrict_
   s = block_sum(s, sh);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
-__global__ void final_sum_kernel(const float* __restrict__ partial, int count, float* __restrict__ out, float scale) {
+__global__ void final_sum_kernel(const float* __restrict__ partial, int count, float* __restrict__ out, float scale, float* __restrict__ acc) {
   __shared__ float sh[32];
   float s = 0.f;
   for (int i = threadIdx.x; i < count; i += blockDim.x) s += partial[i];
   s = block_sum(s, sh);
-  if (threadIdx.x == 0) out[0] = s * scale;
+  if (threadIdx.x == 0) {
+    out[0] = s * scale;
+    if (acc) acc[0] += s * scale;
+  }
 }
+__global__ void add_scalar_kernel(float* __restrict__ acc, const float* __restrict__ v) { acc[0] += v[0]; }
 
 // ------------------------------------------------------------------------------------------------ reductions for bias gradients
 // stage 1: partial[chunk][c] = sum over the chunk's rows of G[r, c]  (G row-major rows x cols); 32 cols x 8 row-lanes per block
@@ -270,6 +387,22 @@ __global__ void colsum_stage1(const float* __restrict__ G, float* __restrict__ p
 #pragma unroll
     for (int j = 0; j < 8; j++) a += sh[j][threadIdx.x];
     partial[(size_t)blockIdx.y * cols + c] = a;
+  }
+}
+// single pass (rows small, or enough column blocks to fill the chip): out[c] = sum_r G[r, c]; 32 cols x 32 row-lanes per block
+__global__ void colsum_single(const float* __restrict__ G, float* __restrict__ out, long long rows, int cols) {
+  __shared__ float sh[32][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < cols)
+    for (long long r = threadIdx.y; r < rows; r += 32) s += G[(size_t)r * cols + c];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j++) a += sh[j][threadIdx.x];
+    out[c] = a;
   }
 }
 // stage 1 for channels-first (N, C, S): partial[chunk][c] = sum_{n in chunk, s} g[n, c, s]
@@ -312,6 +445,30 @@ __global__ void accum_update_kernel(float* __restrict__ w, float* __restrict__ g
   } else {
     for (; i < n; i += st) { float a = gacc[i] + g[i]; gacc[i] = a; w[i] -= lr * a; }
   }
+}
+struct MultiUpd {
+  float* w[16];
+  float* gacc[16];
+  const float* g[16];
+  unsigned long long n[16];
+};
+// every parameter bucket of the network in one launch: blockIdx.y selects the bucket
+__global__ void accum_update_multi_kernel(const MultiUpd mu, float lr, const float* __restrict__ lr_dev) {
+  if (lr_dev) lr = __ldg(lr_dev);
+  const int b = blockIdx.y;
+  float* __restrict__ w = mu.w[b];
+  float* __restrict__ ga = mu.gacc[b];
+  const float* __restrict__ g = mu.g[b];
+  const size_t n = mu.n[b], n4 = n >> 2;
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+  for (size_t j = i; j < n4; j += st) {
+    float4 a = reinterpret_cast<float4*>(ga)[j], q = reinterpret_cast<const float4*>(g)[j], ww = reinterpret_cast<float4*>(w)[j];
+    a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+    ww.x -= lr * a.x; ww.y -= lr * a.y; ww.z -= lr * a.z; ww.w -= lr * a.w;
+    reinterpret_cast<float4*>(ga)[j] = a;
+    reinterpret_cast<float4*>(w)[j] = ww;
+  }
+  for (size_t j = (n4 << 2) + i; j < n; j += st) { float a = ga[j] + g[j]; ga[j] = a; w[j] -= lr * a; }
 }
 __global__ void sgd_kernel(float* __restrict__ w, float* __restrict__ v, const float* __restrict__ g, size_t n, float lr, float mu) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
@@ -428,13 +585,19 @@ extern "C" int okl_pool_fwd(okl_ctx* ctx, int kind, const void* x, void* y, int 
   if (s != OKL_OK) return s;
   size_t total = (size_t)N * C * g.OH * g.OW;
   if (total == 0) return OKL_OK;
+  if (kind == OKL_POOL_MAX && layout == OKL_NCX && pool == 2 && stride == 2 && (H & 1) == 0 && (W & 1) == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & 7) == 0) {
+    maxpool2_fwd_kernel<<<okl_grid_1d(ctx, total, 256, 16), 256, 0, ctx->stream>>>((const float*)x, (float*)y, total, g.OW, W);
+    OKL_LAUNCHED(ctx, "maxpool2_fwd");
+    return OKL_OK;
+  }
   pool_fwd_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)x, (float*)y, g, kind);
   OKL_LAUNCHED(ctx, "pool_fwd");
   return OKL_OK;
 }
 
 extern "C" int okl_pool_bwd(okl_ctx* ctx, int kind, const void* x, const void* gr, void* dx, int N, int C, int H, int W, int pool,
-                            int stride, int layout) {
+                            int stride, int layout, int relu_mask) {
   OKL_REQUIRE(ctx && x && gr && dx, "NULL argument");
   OKL_REQUIRE(kind == OKL_POOL_MAX || kind == OKL_POOL_AVG, "bad pool kind");
   PoolGeom g;
@@ -442,7 +605,15 @@ extern "C" int okl_pool_bwd(okl_ctx* ctx, int kind, const void* x, const void* g
   if (s != OKL_OK) return s;
   size_t total = (size_t)N * C * H * W;
   if (total == 0) return OKL_OK;
-  pool_bwd_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)x, (const float*)gr, (float*)dx, g, kind);
+  if (kind == OKL_POOL_MAX && layout == OKL_NCX && pool == 2 && stride == 2 && (H & 1) == 0 && (W & 1) == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(dx) & 7) == 0) {
+    size_t nwin = (size_t)N * C * g.OH * g.OW;
+    maxpool2_bwd_kernel<<<okl_grid_1d(ctx, nwin, 256, 16), 256, 0, ctx->stream>>>((const float*)x, (const float*)gr, (float*)dx, nwin, g.OW,
+                                                                              W, relu_mask);
+    OKL_LAUNCHED(ctx, "maxpool2_bwd");
+    return OKL_OK;
+  }
+  pool_bwd_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)x, (const float*)gr, (float*)dx, g, kind, relu_mask);
   OKL_LAUNCHED(ctx, "pool_bwd");
   return OKL_OK;
 }
@@ -466,16 +637,36 @@ extern "C" int okl_softmax_bwd(okl_ctx* ctx, const void* p, const void* g, void*
   return OKL_OK;
 }
 
-extern "C" int okl_ce_fwd_bwd(okl_ctx* ctx, const void* p, const void* t, void* loss, void* grad, int rows, int cols, float denom) {
+extern "C" int okl_ce_fwd_bwd(okl_ctx* ctx, const void* p, const void* t, void* loss, void* grad, int rows, int cols, float denom,
+                              void* loss_accum, void* softmax_dx) {
   OKL_REQUIRE(ctx && p && t && loss && grad, "NULL argument");
   OKL_REQUIRE(rows >= 1 && cols >= 1 && denom > 0.f, "bad cross-entropy shape");
+  if (cols <= 16 && rows <= 16384) {
+    int threads = rows >= 1024 ? 1024 : ((rows + 31) / 32) * 32;
+    ce_fused_rowthread_kernel<16><<<1, threads, 0, ctx->stream>>>((const float*)p, (const int*)t, (float*)loss, (float*)grad,
+                                                                (float*)softmax_dx, (float*)loss_accum, rows, cols, 1.f / denom);
+    OKL_LAUNCHED(ctx, "ce_fused_rowthread");
+    return OKL_OK;
+  }
+  if ((long long)rows * cols <= 65536) {
+    ce_fused_small_kernel<<<1, 1024, 0, ctx->stream>>>((const float*)p, (const int*)t, (float*)loss, (float*)grad, (float*)softmax_dx,
+                                                      (float*)loss_accum, rows, cols, 1.f / denom);
+    OKL_LAUNCHED(ctx, "ce_fused_small");
+    return OKL_OK;
+  }
   ce_kernel<<<okl_grid_1d(ctx, (size_t)rows * cols, 256), 256, 0, ctx->stream>>>((const float*)p, (const int*)t, (float*)loss,
                                                                              (float*)grad, rows, cols, 1.f / denom);
   OKL_LAUNCHED(ctx, "ce_fwd_bwd");
+  if (loss_accum) {
+    add_scalar_kernel<<<1, 1, 0, ctx->stream>>>((float*)loss_accum, (const float*)loss);
+    OKL_LAUNCHED(ctx, "add_scalar");
+  }
+  if (softmax_dx) return okl_softmax_bwd(ctx, p, grad, softmax_dx, rows, cols);
   return OKL_OK;
 }
 
-extern "C" int okl_mse_fwd_bwd(okl_ctx* ctx, const void* o, const void* t, void* loss, void* grad, size_t n, float denom) {
+extern "C" int okl_mse_fwd_bwd(okl_ctx* ctx, const void* o, const void* t, void* loss, void* grad, size_t n, float denom,
+                               void* loss_accum) {
   OKL_REQUIRE(ctx && o && t && loss && grad, "NULL argument");
   OKL_REQUIRE(n >= 1 && denom > 0.f, "bad mse shape");
   int grid = okl_grid_1d(ctx, n, 256, 4);
@@ -483,7 +674,7 @@ extern "C" int okl_mse_fwd_bwd(okl_ctx* ctx, const void* o, const void* t, void*
   if (s != OKL_OK) return s;
   mse_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)o, (const float*)t, (float*)ctx->workspace, (float*)grad, n, 2.f / denom);
   OKL_LAUNCHED(ctx, "mse_fwd_bwd");
-  final_sum_kernel<<<1, 256, 0, ctx->stream>>>((const float*)ctx->workspace, grid, (float*)loss, 1.f / (float)n);
+  final_sum_kernel<<<1, 256, 0, ctx->stream>>>((const float*)ctx->workspace, grid, (float*)loss, 1.f / (float)n, (float*)loss_accum);
   OKL_LAUNCHED(ctx, "final_sum");
   return OKL_OK;
 }
@@ -491,6 +682,11 @@ extern "C" int okl_mse_fwd_bwd(okl_ctx* ctx, const void* o, const void* t, void*
 int okl_colsum(okl_ctx* ctx, const float* G, float* out, long long rows, int cols) {
   if (cols <= 0) return OKL_OK;
   int col_blocks = (cols + 31) / 32;
+  if (rows <= 4096 || col_blocks >= ctx->sm_count) {
+    colsum_single<<<col_blocks, dim3(32, 32), 0, ctx->stream>>>(G, out, rows, cols);
+    OKL_LAUNCHED(ctx, "colsum_single");
+    return OKL_OK;
+  }
   long long want = (2LL * ctx->sm_count + col_blocks - 1) / col_blocks;
   long long chunks = rows / 64 < 1 ? 1 : rows / 64;
   if (chunks > want) chunks = want;
@@ -533,6 +729,28 @@ extern "C" int okl_accum_update(okl_ctx* ctx, void* w, void* gacc, const void* g
   if (vec) accum_update_kernel<true><<<grid, 256, 0, ctx->stream>>>((float*)w, (float*)gacc, (const float*)g, n, lr, (const float*)lr_dev);
   else accum_update_kernel<false><<<grid, 256, 0, ctx->stream>>>((float*)w, (float*)gacc, (const float*)g, n, lr, (const float*)lr_dev);
   OKL_LAUNCHED(ctx, "accum_update");
+  return OKL_OK;
+}
+
+extern "C" int okl_accum_update_multi(okl_ctx* ctx, int count, void* const* w, void* const* gacc, const void* const* g, const size_t* n,
+                                      float lr, const void* lr_dev) {
+  OKL_REQUIRE(ctx && (count == 0 || (w && gacc && g && n)), "NULL argument");
+  OKL_REQUIRE(count >= 0, "bad count");
+  for (int base = 0; base < count; base += 16) {
+    MultiUpd mu;
+    int c = count - base < 16 ? count - base : 16;
+    size_t nmax = 0;
+    for (int i = 0; i < 16; i++) {
+      int j = base + (i < c ? i : 0);
+      mu.w[i] = (float*)w[j]; mu.gacc[i] = (float*)gacc[j]; mu.g[i] = (const float*)g[j]; mu.n[i] = i < c ? n[j] : 0;
+      OKL_REQUIRE(aligned16(mu.w[i]) && aligned16(mu.gacc[i]) && aligned16(mu.g[i]), "okl_accum_update_multi: buckets must be 16-byte aligned");
+      if (mu.n[i] > nmax) nmax = mu.n[i];
+    }
+    if (nmax == 0) continue;
+    dim3 grid(okl_grid_1d(ctx, (nmax + 3) / 4, 256, 4), c);
+    accum_update_multi_kernel<<<grid, 256, 0, ctx->stream>>>(mu, lr, (const float*)lr_dev);
+    OKL_LAUNCHED(ctx, "accum_update_multi");
+  }
   return OKL_OK;
 }
 

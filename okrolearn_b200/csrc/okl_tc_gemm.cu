@@ -65,6 +65,11 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -177,6 +182,8 @@ struct TcGemmParams {
   const float* bias;   // per-column bias or nullptr
   int act;
   float* ws;           // [splits][M][N] partials when splits > 1
+  int* counters;       // [tiles] arrival counters (zero on entry, reset by the last arriver) when splits > 1
+  unsigned long long* dbg;   // optional per-CTA phase timestamps (globaltimer ns): start, setup, first full, acc ready, done
   __nv_bfloat16* D16;  // optional bf16 shadow of D (same ld), or nullptr
 };
 
@@ -191,7 +198,7 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue staging*/;
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -207,9 +214,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
   uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+  float* stage_base = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);   // 4 warps x 32 rows x 36 floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 0] = gtime();
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -231,6 +240,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 1] = gtime();
 
   const int total_work = p.tiles_m * p.tiles_n * p.splits;
 
@@ -293,6 +303,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; kb++) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (p.dbg && kb == kb0) p.dbg[blockIdx.x * 8 + 2] = gtime();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, a_lay);
           const uint64_t bdesc = make_smem_desc(sa + Cfg::A_BYTES, b_lbo, b_sbo, b_lay);
@@ -316,86 +327,154 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int split = w / (p.tiles_m * p.tiles_n);
       const int t = w - split * (p.tiles_m * p.tiles_n);
       const int tm = t % p.tiles_m, tn = t / p.tiles_m;
-      const int m = tm * TC_BM + q * 32 + lane;
       const int n0 = tn * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      float* out_row;
-      long long ld;
-      if (p.splits > 1) { ld = p.N; out_row = p.ws + ((size_t)split * p.M + m) * (size_t)p.N; }
-      else { ld = p.ldd; out_row = p.D + (size_t)m * (size_t)p.ldd; }
-      (void)ld;
+      if (p.dbg && threadIdx.x == 128) p.dbg[blockIdx.x * 8 + 3] = gtime();
+      // TMEM -> registers -> per-warp smem staging (padded rows, conflict-free 128-bit accesses) -> global, so that every
+      // store instruction writes four full 128-byte row segments instead of 32 scattered 16-byte pieces.
+      float* stg = stage_base + (warp - 4) * (32 * 36);
+      const int m_base = tm * TC_BM + q * 32;
+      const int c4 = (lane & 7) * 4, rsub = lane >> 3;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
         tmem_ld_wait();
-        if (m < p.M) {
-          const int nb = n0 + c;
-          if (p.splits > 1) {
-            if (vec_ok && nb + 32 <= p.N) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(out_row + nb + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                           __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stg + lane * 36 + j) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        __syncwarp();
+        const int nn = n0 + c + c4;
+        float bz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.splits == 1 && p.bias) {
+#pragma unroll
+          for (int e = 0; e < 4; e++)
+            if (nn + e < p.N) bz[e] = __ldg(p.bias + nn + e);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int r = 4 * i + rsub;
+          const int mm = m_base + r;
+          float4 o = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
+          if (mm < p.M && nn < p.N) {
+            if (p.splits > 1) {
+              float* dst = p.ws + ((size_t)split * p.M + mm) * (size_t)p.N + nn;
+              if (vec_ok && nn + 4 <= p.N) *reinterpret_cast<float4*>(dst) = o;
+              else {
+                const float f[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                  if (nn + e < p.N) dst[e] = f[e];
+              }
             } else {
+              float f[4] = {o.x + bz[0], o.y + bz[1], o.z + bz[2], o.w + bz[3]};
 #pragma unroll
-              for (int j = 0; j < 32; j++)
-                if (nb + j < p.N) out_row[nb + j] = __uint_as_float(v[j]);
-            }
-          } else {
-            float f[32];
+              for (int e = 0; e < 4; e++) f[e] = act_apply(f[e], p.act);
+              float* dst = p.D + (size_t)mm * (size_t)p.ldd + nn;
+              if (vec_ok && nn + 4 <= p.N) *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+              else {
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-              float x = __uint_as_float(v[j]);
-              if (p.bias && nb + j < p.N) x += __ldg(p.bias + nb + j);
-              f[j] = act_apply(x, p.act);
-            }
-            if (vec_ok && nb + 32 <= p.N) {
+                for (int e = 0; e < 4; e++)
+                  if (nn + e < p.N) dst[e] = f[e];
+              }
+              if (p.D16) {
+                __nv_bfloat16* d16 = p.D16 + (size_t)mm * (size_t)p.ldd + nn;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out_row + nb + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j++)
-                if (nb + j < p.N) out_row[nb + j] = f[j];
-            }
-            if (p.D16) {
-              __nv_bfloat16* o16 = p.D16 + (size_t)m * (size_t)p.ldd;
-#pragma unroll
-              for (int j = 0; j < 32; j++)
-                if (nb + j < p.N) o16[nb + j] = __float2bfloat16(f[j]);
+                for (int e = 0; e < 4; e++)
+                  if (nn + e < p.N) d16[e] = __float2bfloat16(f[e]);
+              }
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (p.splits > 1) {
+        // Split-K fix-up without a second kernel.  All CTAs of a launch are co-resident (grid <= #SMs, one work item each
+        // when splits > 1), so the `splits` CTAs of a tile meet at a counter, then EACH reduces 1/splits of the tile over
+        // all partials in fixed split order (deterministic) and applies bias + activation.
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 128) {
+          atomicAdd(p.counters + 2 * t, 1);
+          const long long t0 = clock64();
+          while (*reinterpret_cast<volatile int*>(p.counters + 2 * t) < p.splits) {
+            __nanosleep(64);
+            if (clock64() - t0 > 4000000000LL) {
+              printf("okl tc kernel: split-K rendezvous timed out (block %d)\n", blockIdx.x);
+              __trap();
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        __threadfence();
+        {
+          const int te = threadIdx.x - 128;
+          const int m0 = tm * TC_BM;
+          const size_t plane = (size_t)p.M * p.N;
+          constexpr int C4 = BN / 4;
+          constexpr int TOTAL4 = TC_BM * C4;
+          const int chunk = (TOTAL4 + p.splits - 1) / p.splits;
+          const int beg = split * chunk, end = min(TOTAL4, beg + chunk);
+          for (int idx = beg + te; idx < end; idx += 128) {
+            const int r = idx / C4, c = (idx - r * C4) * 4;
+            const int mm = m0 + r, nn = n0 + c;
+            if (mm >= p.M || nn >= p.N) continue;
+            const float* src = p.ws + (size_t)mm * p.N + nn;
+            float4 a[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            int z = 0;
+            for (; z + 3 < p.splits; z += 4) {
+              float4 v[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) v[u] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(z + u) * plane));
+#pragma unroll
+              for (int u = 0; u < 4; u++) { a[u].x += v[u].x; a[u].y += v[u].y; a[u].z += v[u].z; a[u].w += v[u].w; }
+            }
+            for (; z < p.splits; z++) {
+              const float4 v0 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)z * plane));
+              a[0].x += v0.x; a[0].y += v0.y; a[0].z += v0.z; a[0].w += v0.w;
+            }
+            float f[4] = {(a[0].x + a[1].x) + (a[2].x + a[3].x), (a[0].y + a[1].y) + (a[2].y + a[3].y),
+                          (a[0].z + a[1].z) + (a[2].z + a[3].z), (a[0].w + a[1].w) + (a[2].w + a[3].w)};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              if (p.bias) f[j] += __ldg(p.bias + nn + j);
+              f[j] = act_apply(f[j], p.act);
+            }
+            *reinterpret_cast<float4*>(p.D + (size_t)mm * p.ldd + nn) = make_float4(f[0], f[1], f[2], f[3]);
+            if (p.D16) {
+#pragma unroll
+              for (int j = 0; j < 4; j++) p.D16[(size_t)mm * p.ldd + nn + j] = __float2bfloat16(f[j]);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 128) {
+          const int old = atomicAdd(p.counters + 2 * t + 1, 1);
+          if (old == p.splits - 1) {          // last CTA to leave: every reader is done, re-arm both counters
+            p.counters[2 * t] = 0;
+            p.counters[2 * t + 1] = 0;
+          }
+        }
+      }
     }
   }
 
+  if (p.dbg && threadIdx.x == 128) p.dbg[blockIdx.x * 8 + 4] = gtime();
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
-}
-
-// fixed-order reduction of split-K partials + bias + activation
-__global__ void tc_splitk_reduce(const float* __restrict__ ws, float* __restrict__ D, long long ldd, const float* __restrict__ bias,
-                                 int act, int M, int N, int splits, __nv_bfloat16* __restrict__ D16) {
-  size_t total = (size_t)M * N;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int z = 0; z < splits; z++) s += ws[(size_t)z * total + i];
-    int m = (int)(i / N), n = (int)(i - (size_t)m * N);
-    if (bias) s += __ldg(bias + n);
-    s = act_apply(s, act);
-    D[(size_t)m * ldd + n] = s;
-    if (D16) D16[(size_t)m * ldd + n] = __float2bfloat16(s);
-  }
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 5] = gtime();
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, size_t n) {
@@ -525,16 +604,17 @@ int okl_tc_gemm_raw(okl_ctx* ctx, int kind, int a_mn, int b_mn, int M, int N, in
   }
   const int tiles_n = (N + bn - 1) / bn;
   int splits = env_int("OKL_TC_SPLITS", 0);
-  if (splits == 0) {
-    long long tiles = (long long)tiles_m * tiles_n;
-    splits = 1;
-    if (tiles < ctx->sm_count && kb_total >= 8) {
-      splits = (int)((ctx->sm_count + tiles - 1) / tiles);
-      int max_splits = kb_total / 4;
-      if (splits > max_splits) splits = max_splits;
-      if (splits > 64) splits = 64;
-      if (splits < 1) splits = 1;
-    }
+  {
+    // split-K only when every (tile, split) work item gets its own co-resident CTA (single round) and the fix-up can use
+    // 128-bit accesses
+    const long long tiles = (long long)tiles_m * tiles_n;
+    const bool can_split = (N & 3) == 0 && (ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0 && tiles <= 2048;
+    int max_splits = (int)(ctx->sm_count / tiles);
+    if (max_splits > kb_total / 4) max_splits = kb_total / 4;
+    if (max_splits > 32) max_splits = 32;
+    if (max_splits < 1 || !can_split) max_splits = 1;
+    if (splits == 0) splits = max_splits;
+    if (splits > max_splits) splits = max_splits;
   }
   int kb_per_split = (kb_total + splits - 1) / splits;
   splits = (kb_total + kb_per_split - 1) / kb_per_split;
@@ -552,10 +632,17 @@ int okl_tc_gemm_raw(okl_ctx* ctx, int kind, int a_mn, int b_mn, int M, int N, in
   p.M = M; p.N = N; p.K = K;
   p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.splits = splits; p.kb_per_split = kb_per_split; p.kb_total = kb_total;
   p.D = D; p.ldd = ldd; p.bias = bias; p.act = act; p.ws = nullptr; p.D16 = (__nv_bfloat16*)D16;
+  p.counters = nullptr;
+  p.dbg = (unsigned long long*)ctx->tc_dbg;
   if (splits > 1) {
     s = okl_ensure_workspace(ctx, (size_t)splits * M * N * sizeof(float));
     if (s != OKL_OK) return s;
     p.ws = (float*)ctx->workspace;
+    if (!ctx->tile_counters) {
+      OKL_CHECK_CUDA(cudaMalloc(&ctx->tile_counters, 4096 * sizeof(int)));
+      OKL_CHECK_CUDA(cudaMemsetAsync(ctx->tile_counters, 0, 4096 * sizeof(int), ctx->stream));
+    }
+    p.counters = ctx->tile_counters;
   }
   if (kind == 0) {
     if (!a_mn && !b_mn) s = launch_bn<0, false, false>(ctx, bn, ta, tb, p);
@@ -568,13 +655,7 @@ int okl_tc_gemm_raw(okl_ctx* ctx, int kind, int a_mn, int b_mn, int M, int N, in
     else if (a_mn && !b_mn) s = launch_bn<1, true, false>(ctx, bn, ta, tb, p);
     else s = launch_bn<1, true, true>(ctx, bn, ta, tb, p);
   }
-  if (s != OKL_OK) return s;
-  if (splits > 1) {
-    size_t total = (size_t)M * N;
-    tc_splitk_reduce<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>(p.ws, D, ldd, bias, act, M, N, splits, p.D16);
-    OKL_LAUNCHED(ctx, "tc_splitk_reduce");
-  }
-  return OKL_OK;
+  return s;
 }
 
 extern "C" int okl_tc_gemm(okl_ctx* ctx, int kind, int a_mn, int b_mn, int M, int N, int K, const void* A, long long lda, const void* B,
@@ -590,6 +671,12 @@ extern "C" int okl_tc_gemm(okl_ctx* ctx, int kind, int a_mn, int b_mn, int M, in
   int s = bf16_operands(ctx, (const float*)A, na, (const float*)B, nb, sc);
   if (s != OKL_OK) return s;
   return okl_tc_gemm_raw(ctx, 1, a_mn, b_mn, M, N, K, sc.a, lda, sc.b, ldb, (float*)D, ldd, (const float*)bias, act, nullptr);
+}
+
+// debug hook (not in okl.h): per-CTA phase timestamps of the next tcgen05 GEMM launches are written to `buf` (8 u64 per CTA)
+extern "C" int okl_debug_tc_timestamps(okl_ctx* ctx, void* buf) {
+  ctx->tc_dbg = buf;
+  return OKL_OK;
 }
 
 int okl_f32_to_bf16(okl_ctx* ctx, const float* src, void* dst, size_t n) {

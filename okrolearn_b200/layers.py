@@ -135,6 +135,36 @@ class _ParamLayer:
             b.apply(b._pending_lr)
 
 
+def apply_pending_updates(layers):
+    """All deferred bucket updates of a network in ONE kernel launch (after the data-parallel exchange has been joined)."""
+    ctx = get_ctx()
+    bs = [l._bucket for l in layers if isinstance(l, _ParamLayer) and getattr(l._bucket, "_pending_lr", None) is not None]
+    if not bs:
+        return
+    if len(bs) == 1:
+        bs[0].apply(bs[0]._pending_lr)
+        return
+    if ctx.nranks > 1:
+        check(lib.okl_comm_wait(ctx.h))
+    lrf, lrp = _lr_args(bs[0]._pending_lr)
+    n = len(bs)
+    for b in bs:
+        for t in b.tensors:
+            t._dptr(NCX)
+    w = (C.c_void_p * n)(*[b.param.ptr for b in bs])
+    ga = (C.c_void_p * n)(*[b.gacc.ptr for b in bs])
+    g = (C.c_void_p * n)(*[b.grad.ptr for b in bs])
+    cnt = (C.c_size_t * n)(*[b.total for b in bs])
+    check(lib.okl_accum_update_multi(ctx.h, n, w, ga, g, cnt, lrf, lrp))
+    for b in bs:
+        b._stepped = True
+        for t, gv in zip(b.tensors, b.gviews):
+            t._touch()
+            gv._touch()
+            t._grad = gv
+        b._pending_lr = None
+
+
 # ====================================================================================================== Dense
 class DenseLayer(_ParamLayer):
     """okl.py:18-54.  weights (in,out) = randn*0.1 float64, biases (1,out) zeros; Y = X.W + b;
@@ -350,6 +380,7 @@ class _Activation:
     _act = ACT_NONE
     _bwd_ref = "inputs"          # which stored tensor the derivative is evaluated from
     _fused_into_prev = False     # NeuralNetwork planner: the producing layer's epilogue already applied this activation
+    _bwd_fused_into_next = False # NeuralNetwork planner: the following pooling layer's backward already applied relu'
 
     def _fwd(self, inputs):
         inputs = _as_tensor(inputs)
@@ -393,8 +424,9 @@ class ReLUActivationLayer(_Activation):
         return self.outputs
 
     def backward(self, dL_dout: Tensor, lr: float):
-        dx = self._bwd(dL_dout, self.inputs)
-        _set_input_grad(self.inputs, dx)
+        dx = _as_tensor(dL_dout) if self._bwd_fused_into_next else self._bwd(dL_dout, self.inputs)
+        if not self._fused_into_prev:            # fused: `inputs` IS the post-activation tensor, no separate pre-activation
+            _set_input_grad(self.inputs, dx)
         return dx
 
 
@@ -441,7 +473,12 @@ class SoftmaxActivationLayer:
         self.outputs = out
         return out
 
+    _precomputed = None        # (loss gradient, dz) filled by CrossEntropyLoss.forward in NeuralNetwork's fast path
+
     def backward(self, dL_dout: Tensor, lr: float = None):
+        pre, self._precomputed = self._precomputed, None
+        if pre is not None and dL_dout is pre[0]:
+            return pre[1]
         dL_dout = _as_tensor(dL_dout)
         ctx = get_ctx()
         p = self.outputs
@@ -461,6 +498,7 @@ class SoftmaxActivationLayer:
 # ====================================================================================================== pooling / flatten
 class _Pool:
     _kind = POOL_MAX
+    _fused_relu_bwd = False      # NeuralNetwork planner: the ReLU right before this layer gets its backward applied here
 
     def __init__(self, pool_size=2, stride=2):
         self.pool_size = pool_size
@@ -495,7 +533,7 @@ class _Pool:
         lay = x._layout
         dx = Tensor._empty(x.shape, np.float64, layout=lay)
         check(lib.okl_pool_bwd(ctx.h, self._kind, xp, dL_dout._dptr(lay), dx._ptr_raw(), N, Cc, H, W, int(self.pool_size),
-                               int(self.stride), lay))
+                               int(self.stride), lay, 1 if self._fused_relu_bwd else 0))
         _set_input_grad(x, dx)                         # okl.py:1768 / 1821
         return dx
 

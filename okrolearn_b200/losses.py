@@ -107,6 +107,8 @@ class CrossEntropyLoss:
     """okl.py:1380-1409: expects probabilities (after softmax) and integer class targets.
     forward: mean(-log(clip(p, 1e-12, 1-1e-12)[i, t_i]));  backward: (clip(p) - onehot) / samples.
     As in the reference, ``backward`` ignores its arguments and uses what ``forward`` stashed (okl.py:1399-1403)."""
+    _fuse_softmax = None       # set by NeuralNetwork's fast path
+    _loss_accum = None         # device scalar accumulating the epoch loss (set by NeuralNetwork.train)
 
     def forward(self, outputs: Tensor, targets: Tensor):
         ctx = get_ctx()
@@ -118,7 +120,12 @@ class CrossEntropyLoss:
         loss = _DevBuf(ctx, 4)
         grad = Tensor._empty((rows, cols), np.float64)
         tptr = tbuf if isinstance(tbuf, int) else tbuf.ptr
-        check(lib.okl_ce_fwd_bwd(ctx.h, outputs._dptr(NCX), tptr, loss.ptr, grad._ptr_raw(), rows, cols, float(rows * ctx.nranks)))
+        sm = self._fuse_softmax          # NeuralNetwork fast path: the softmax layer whose backward is computed right here
+        dz = Tensor._empty((rows, cols), np.float64) if (sm is not None and sm.outputs is outputs) else None
+        check(lib.okl_ce_fwd_bwd(ctx.h, outputs._dptr(NCX), tptr, loss.ptr, grad._ptr_raw(), rows, cols, float(rows * ctx.nranks),
+                                 self._loss_accum, dz._ptr_raw() if dz is not None else None))
+        if dz is not None:
+            sm._precomputed = (grad, dz)
         self.outputs, self.targets = outputs, targets
         self._grad = grad
         self._loss = LossValue(loss)
@@ -134,6 +141,7 @@ class CrossEntropyLoss:
 
 class MSELoss:
     """okl.py:1833-1839: mean((o - t)^2); gradient 2 (o - t) / t.size."""
+    _loss_accum = None
 
     def forward(self, outputs: Tensor, targets: Tensor):
         ctx = get_ctx()
@@ -142,7 +150,8 @@ class MSELoss:
         loss = _DevBuf(ctx, 4)
         grad = Tensor._empty(outputs.shape, np.float64)
         n = outputs.size
-        check(lib.okl_mse_fwd_bwd(ctx.h, outputs._dptr(NCX), targets._dptr(NCX), loss.ptr, grad._ptr_raw(), n, float(n * ctx.nranks)))
+        check(lib.okl_mse_fwd_bwd(ctx.h, outputs._dptr(NCX), targets._dptr(NCX), loss.ptr, grad._ptr_raw(), n, float(n * ctx.nranks),
+                                  self._loss_accum))
         self._grad = grad
         self._key = (id(outputs), id(targets))
         self._loss = LossValue(loss)

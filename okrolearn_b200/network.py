@@ -32,7 +32,9 @@ import numpy as np
 from . import _lib
 from ._lib import lib, check, get_ctx, NCX, ACT_NONE
 from .tensor import Tensor, _DevBuf, _numel
-from .layers import (_ParamLayer, _Activation, ReLUActivationLayer, SigmoidActivationLayer, DenseLayer, _ConvBase)
+from .layers import (apply_pending_updates, _ParamLayer, _Activation, _Pool, ReLUActivationLayer, SigmoidActivationLayer, SoftmaxActivationLayer,
+                     MaxPoolingLayer, DenseLayer,
+                     _ConvBase)
 from .losses import CrossEntropyLoss, MSELoss, LossValue
 
 
@@ -195,15 +197,21 @@ class NeuralNetwork:
         for l in ls:
             if isinstance(l, _ParamLayer):
                 l._fused_act, l._need_dx = ACT_NONE, True
-                l._defer_update = get_ctx().nranks > 1
+                l._defer_update = fast or get_ctx().nranks > 1
             if isinstance(l, _Activation):
                 l._fused_into_prev = False
+                l._bwd_fused_into_next = False
+            if isinstance(l, _Pool):
+                l._fused_relu_bwd = False
         if not fast:
             return
         if self.fuse_activations:
             for a, b in zip(ls, ls[1:]):
                 if isinstance(a, _ParamLayer) and isinstance(b, (ReLUActivationLayer, SigmoidActivationLayer)):
                     a._fused_act, b._fused_into_prev = b._act, True
+            for a, b in zip(ls, ls[1:]):                 # ReLU -> MaxPool: relu' applied inside the pooling backward
+                if isinstance(a, ReLUActivationLayer) and isinstance(b, MaxPoolingLayer):
+                    a._bwd_fused_into_next, b._fused_relu_bwd = True, True
         if self.skip_input_grad and ls and isinstance(ls[0], _ParamLayer):
             ls[0]._need_dx = False
 
@@ -253,9 +261,7 @@ class NeuralNetwork:
         for i, layer in reversed(list(enumerate(self.layers))):
             loss_gradient = layer.backward(loss_gradient, lr)
             self._log_gradient(i, loss_gradient)
-        for layer in self.layers:                          # deferred (data-parallel) updates: after the whole backward
-            if isinstance(layer, _ParamLayer):
-                layer._finish_update()
+        apply_pending_updates(self.layers)                 # deferred updates (fast path / data parallel): one launch
         self._run_hooks('post_backward', loss_gradient, lr)
         self._log_parameters()
 
@@ -275,6 +281,9 @@ class NeuralNetwork:
     def _one_step(self, batch_inputs, batch_targets, loss_function, lr, optimizer, fast):
         """forward + loss + backward (+ optimizer for layers exposing parameters/gradients): okl.py:2969-2988."""
         outputs = self._forward(batch_inputs, _fast=fast) if fast else self.forward(batch_inputs)
+        if isinstance(loss_function, CrossEntropyLoss):
+            last = self.layers[-1] if self.layers else None
+            loss_function._fuse_softmax = last if (fast and isinstance(last, SoftmaxActivationLayer)) else None
         loss = loss_function.forward(outputs, batch_targets)
         loss_gradient = loss_function.backward(outputs, batch_targets)
         if fast:
@@ -294,7 +303,8 @@ class NeuralNetwork:
         num_batches = int(np.ceil(num_samples / batch_size))
         losses = []
         fast = not self._observed()
-        graph_ok = fast and self.use_graph and not any(hasattr(l, 'parameters') for l in self.layers) and clip_grad is None
+        graph_ok = (fast and self.use_graph and not any(hasattr(l, 'parameters') for l in self.layers) and clip_grad is None
+                    and hasattr(type(loss_function), "_loss_accum"))
         is_ce = isinstance(loss_function, CrossEntropyLoss)
         sample_shape = tuple(inputs.shape[1:])
         t_shape = tuple(targets.shape[1:])
@@ -334,6 +344,9 @@ class NeuralNetwork:
             ctx.lr_buf = _DevBuf(ctx, 4)
         ctx.lr_dev = ctx.lr_buf.ptr
         self.last_step_losses = []
+        custom_loss = not hasattr(type(loss_function), "_loss_accum")
+        if not custom_loss:
+            loss_function._loss_accum = st.eloss.ptr
 
         def make_targets(rows):
             if is_ce:
@@ -359,6 +372,7 @@ class NeuralNetwork:
             lr32 = np.array([current_lr], dtype=np.float32)
             check(lib.okl_h2d(ctx.h, ctx.lr_dev, lr32.ctypes.data, 1, _lib.F32))
             check(lib.okl_memset(ctx.h, st.eloss.ptr, 0, 4))
+            host_losses = []
 
             # shuffle (same host RNG call as okl.py:2957-2958)
             indices = np.arange(num_samples)
@@ -400,7 +414,6 @@ class NeuralNetwork:
                         ctx.graph_begin()
                         try:
                             outputs, loss = self._one_step(bx, bt, loss_function, current_lr, optimizer, fast)
-                            check(lib.okl_binary(ctx.h, 0, st.eloss.ptr, loss._buf.ptr, st.eloss.ptr, 1, 1))
                         finally:
                             handle = ctx.graph_end()
                             ctx._capture_keep = None
@@ -410,17 +423,21 @@ class NeuralNetwork:
                         ctx.graph_launch(st.graph.handle)
                     else:
                         outputs, loss = self._one_step(bx, bt, loss_function, current_lr, optimizer, fast)
-                        check(lib.okl_binary(ctx.h, 0, st.eloss.ptr, loss._buf.ptr, st.eloss.ptr, 1, 1))
                         if full:
                             st.warm = True
                     if clip_grad is not None:
                         self._clip_gradients(clip_grad)
+                if custom_loss:                      # duck-typed user loss: its value lives on the host (okl.py:2973)
+                    host_losses.append(float(np.sum(getattr(loss, "data", loss))))
                 if self.sync_loss_every_step:
                     self.last_step_losses.append(float(loss))
 
-            v = C.c_float()
-            check(lib.okl_read_scalar(ctx.h, st.eloss.ptr, C.byref(v)))
-            avg_loss = float(v.value) / num_batches
+            if custom_loss:
+                avg_loss = float(np.sum(host_losses)) / num_batches
+            else:
+                v = C.c_float()
+                check(lib.okl_read_scalar(ctx.h, st.eloss.ptr, C.byref(v)))
+                avg_loss = float(v.value) / num_batches
             losses.append(avg_loss)
             self.parameter_history.append(self.get_parameter_history())
             epoch_end_time = time.time()
@@ -444,6 +461,8 @@ class NeuralNetwork:
             ctx.sync()
             for p, _ in pins_x + pins_t:
                 lib.okl_pinned_free(p)
+        if not custom_loss:
+            loss_function._loss_accum = None
         return losses
 
     @staticmethod
