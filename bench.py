@@ -417,9 +417,13 @@ def main():
     e2e = None
     if not args.no_e2e:
         net.stream_inputs, net.sync_loss_every_step = True, True
-        hXw, hTw = okl.Tensor(Xw), okl.Tensor(Tw)
+        def host_dataset(X, T):                      # the dataset as a user would hold it for streaming: page-locked host arrays
+            pX = okl.pinned_empty(X.shape, np.float32)
+            pX[...] = X
+            return okl.Tensor.wrap(pX), okl.Tensor(T)
+        hXw, hTw = host_dataset(Xw, Tw)
         net.train(hXw, hTw, 1, sched, opt, B, loss_fn)
-        hX, hT = okl.Tensor(Xk), okl.Tensor(Tk)
+        hX, hT = host_dataset(Xk, Tk)
         ctx.sync()
         _lib.check(_lib.lib.okl_barrier(ctx.h))
         t0 = time.perf_counter()
@@ -433,8 +437,9 @@ def main():
         t_bytes = B * 4 if w["loss"] == "ce" else int(np.prod(out_shape(name, B))) * 4
         e2e = {"value": round(world * B * K / dt, 1), "unit": "samples/s", "h2d_bytes_per_step": int(B * np.prod(w["sample"]) * 4 + t_bytes),
                "d2h_bytes_per_step": 4, "ms_per_step": round(dt / K * 1e3, 4),
-               "api": "NeuralNetwork.train(Tensor(host ndarray), ...) with stream_inputs (pinned host -> device copy of every batch "
-                      "inside the step) and sync_loss_every_step (loss read back after every step)"}
+               "api": "NeuralNetwork.train(Tensor.wrap(pinned host ndarray), ...) with stream_inputs (every step gathers its shuffled "
+                      "batch rows host->device from the pinned dataset inside the step) and sync_loss_every_step (loss read back to "
+                      "the host after every step)"}
 
     if rank != 0:
         return 0

@@ -31,7 +31,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import lib, check, get_ctx, NCX, ACT_NONE
-from .tensor import Tensor, _DevBuf, _numel
+from .tensor import Tensor, _DevBuf, _numel, pinned_empty, pinned_base
 from .layers import (apply_pending_updates, _ParamLayer, _Activation, _Pool, ReLUActivationLayer, SigmoidActivationLayer, SoftmaxActivationLayer,
                      MaxPoolingLayer, DenseLayer,
                      _ConvBase)
@@ -314,11 +314,22 @@ class NeuralNetwork:
 
         # ---- dataset placement
         if stream:
-            cur_x = np.ascontiguousarray(inputs.data, dtype=np.float32).reshape(num_samples, row_elems)
-            cur_t = np.ascontiguousarray(targets.data).reshape(num_samples, t_row)
-            cur_t = cur_t.astype(np.int32) if is_ce else cur_t.astype(np.float32)
-            pins_x = [self._pinned((num_samples, row_elems), np.float32) for _ in range(2)]
-            pins_t = [self._pinned((num_samples, t_row), cur_t.dtype) for _ in range(2)]
+            # the dataset stays in page-locked host memory; every step gathers its (shuffled) rows straight from there over
+            # PCIe/NVLink-C2C into the step's static input buffer (the host->device copy is inside the step)
+            if getattr(inputs, "_lazy_perm", None) is not None:
+                _ = inputs.data                                          # apply a reordering left pending by an earlier train()
+            hx = inputs._host if (inputs._host is not None and not inputs._dev_valid) else inputs.data
+            hx = np.asarray(hx)
+            if hx.dtype == np.float32 and pinned_base(hx) is not None:
+                pin_x = hx.reshape(num_samples, row_elems)               # zero-copy: already pinned
+            else:
+                pin_x = pinned_empty((num_samples, row_elems), np.float32)
+                np.copyto(pin_x, np.asarray(hx, dtype=np.float32).reshape(num_samples, row_elems))
+            ht = np.asarray(targets.data).reshape(num_samples, t_row)
+            pin_t = pinned_empty((num_samples, t_row), np.int32 if is_ce else np.float32)
+            np.copyto(pin_t, ht.astype(pin_t.dtype))
+            idx_dev = _DevBuf(ctx, max(num_samples, 1) * 4)
+            perm_total = np.arange(num_samples)
         else:
             x_dev = _DevBuf(ctx, max(inputs.size, 1) * 4)
             check(lib.okl_d2d(ctx.h, x_dev.ptr, inputs._dptr(NCX), inputs.size * 4))
@@ -378,9 +389,9 @@ class NeuralNetwork:
             indices = np.arange(num_samples)
             np.random.shuffle(indices)
             if stream:
-                np.take(cur_x, indices, axis=0, out=pins_x[epoch % 2][1])
-                np.take(cur_t, indices, axis=0, out=pins_t[epoch % 2][1])
-                cur_x, cur_t = pins_x[epoch % 2][1], pins_t[epoch % 2][1]    # shuffled and pinned
+                perm_total = perm_total[indices]
+                i32 = np.ascontiguousarray(perm_total.astype(np.int32))
+                check(lib.okl_h2d_i32(ctx.h, idx_dev.ptr, i32.ctypes.data, i32.size, _lib.I32))
             else:
                 i32 = np.ascontiguousarray(indices.astype(np.int32))
                 check(lib.okl_h2d_i32(ctx.h, idx_dev.ptr, i32.ctypes.data, i32.size, _lib.I32))
@@ -396,8 +407,8 @@ class NeuralNetwork:
                 rows = b1 - b0
                 full = rows == batch_size
                 if stream:
-                    check(lib.okl_h2d_async_raw(ctx.h, st.xin._ptr_raw(), cur_x[b0:b1].ctypes.data, rows * row_elems * 4))
-                    check(lib.okl_h2d_async_raw(ctx.h, st.tin.ptr, cur_t[b0:b1].ctypes.data, rows * t_row * 4))
+                    check(lib.okl_gather_rows(ctx.h, st.xin._ptr_raw(), pin_x.ctypes.data, idx_dev.ptr + b0 * 4, rows, row_elems))
+                    check(lib.okl_gather_rows(ctx.h, st.tin.ptr, pin_t.ctypes.data, idx_dev.ptr + b0 * 4, rows, t_row))
                 else:
                     check(lib.okl_d2d(ctx.h, st.xin._ptr_raw(), x_dev.ptr + b0 * row_elems * 4, rows * row_elems * 4))
                     check(lib.okl_d2d(ctx.h, st.tin.ptr, t_dev.ptr + b0 * t_row * 4, rows * t_row * 4))
@@ -447,8 +458,9 @@ class NeuralNetwork:
 
         # the reference reorders the caller's tensors in place every epoch (okl.py:2959-2960)
         if epochs and stream:
-            inputs.data = np.array(cur_x).reshape(inputs.shape).astype(inputs._np_dtype, copy=False)
-            targets.data = np.array(cur_t).reshape(targets.shape).astype(targets._np_dtype, copy=False)
+            ctx.sync()
+            inputs._lazy_perm = perm_total if getattr(inputs, "_lazy_perm", None) is None else inputs._lazy_perm[perm_total]
+            targets._lazy_perm = perm_total if getattr(targets, "_lazy_perm", None) is None else targets._lazy_perm[perm_total]
         elif epochs:
             ctx.sync()
             if inputs._bound:
@@ -457,22 +469,9 @@ class NeuralNetwork:
                 inputs._buf, inputs._off, inputs._layout = x_dev, 0, NCX
             inputs._touch()
             targets.data = np.asarray(targets.data)[perm_total]
-        if stream:
-            ctx.sync()
-            for p, _ in pins_x + pins_t:
-                lib.okl_pinned_free(p)
         if not custom_loss:
             loss_function._loss_accum = None
         return losses
-
-    @staticmethod
-    def _pinned(shape, dtype):
-        """(pointer, ndarray view) of a page-locked host buffer."""
-        nbytes = max(int(_numel(shape) * np.dtype(dtype).itemsize), 1)
-        p = C.c_void_p()
-        check(lib.okl_pinned_alloc(nbytes, C.byref(p)))
-        raw = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_ubyte)), shape=(nbytes,))
-        return (p, raw[:_numel(shape) * np.dtype(dtype).itemsize].view(dtype).reshape(shape))
 
     def _clip_gradients(self, max_norm):
         """okl.py:3003-3016 - a no-op in the reference too, because parameters() returns []."""

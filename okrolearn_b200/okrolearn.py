@@ -3,7 +3,7 @@ reference (README.md:20-28) for the Conv/Dense train-step hot path (SURVEY.md se
 import numpy as np  # noqa: F401  (the reference's star-import also exposes np)
 
 from ._lib import get_ctx, set_precision, FP32, TF32, BF16  # noqa: F401
-from .tensor import Tensor  # noqa: F401
+from .tensor import Tensor, pinned_empty  # noqa: F401
 from .layers import (DenseLayer, Conv1DLayer, Conv2DLayer, Conv3DLayer, ReLUActivationLayer, SigmoidActivationLayer,  # noqa: F401
                      TanhActivationLayer, SoftmaxActivationLayer, MaxPoolingLayer, AveragePoolingLayer, FlattenLayer,
                      UnflattenLayer)

@@ -42,6 +42,51 @@ class _DevBuf:
             pass
 
 
+_PINNED = {}        # base address -> (nbytes, owner) of page-locked host arrays handed out by pinned_empty()
+
+
+class _PinnedBlock:
+    def __init__(self, nbytes):
+        p = C.c_void_p()
+        check(lib.okl_pinned_alloc(max(int(nbytes), 1), C.byref(p)))
+        self.ptr, self.nbytes = p.value, int(nbytes)
+        _PINNED[self.ptr] = self
+
+    def __del__(self):
+        try:
+            _PINNED.pop(self.ptr, None)
+            lib.okl_pinned_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """NumPy array in page-locked (DMA-able, GPU-mapped) host memory: the source format of ``stream_inputs`` training."""
+    dtype = np.dtype(dtype)
+    n = _numel(shape) * dtype.itemsize
+    blk = _PinnedBlock(n)
+    raw = (C.c_ubyte * max(n, 1)).from_address(blk.ptr)
+    arr = np.frombuffer(raw, dtype=np.uint8, count=n).view(dtype).reshape(shape)
+    _KEEP[id(raw)] = blk
+    import weakref
+    weakref.finalize(raw, _KEEP.pop, id(raw), None)
+    return arr
+
+
+_KEEP = {}
+
+
+def pinned_base(arr):
+    """Address of ``arr``'s data if it lies inside a pinned_empty() block and is C-contiguous, else None."""
+    if not isinstance(arr, np.ndarray) or not arr.flags.c_contiguous:
+        return None
+    a = arr.ctypes.data
+    for base, blk in _PINNED.items():
+        if base <= a and a + arr.nbytes <= base + blk.nbytes:
+            return a
+    return None
+
+
 def _numel(shape):
     n = 1
     for s in shape:
@@ -150,8 +195,19 @@ class Tensor:
         self._host_stamp = (self._dev_ver, ctx.epoch)
         del tmp
 
+    @classmethod
+    def wrap(cls, array, requires_grad=True):
+        """Tensor over ``array`` WITHOUT the defensive copy of ``Tensor(array)`` (e.g. a pinned_empty() dataset)."""
+        t = cls(np.zeros((0,)), requires_grad=requires_grad)
+        t.data = array
+        return t
+
     @property
     def data(self):
+        perm = getattr(self, "_lazy_perm", None)
+        if perm is not None:                 # train() reordered the caller's dataset (okl.py:2959-2960); applied on first read
+            self._lazy_perm = None
+            self.data = np.asarray(self.data)[perm]
         if self._dev_valid:
             ctx = get_ctx()
             if self._host is None or self._host_stamp != (self._dev_ver, ctx.epoch):
