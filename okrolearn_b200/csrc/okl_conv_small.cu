@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) conv_smallk_fprop(const float* __restrict
     const int n = (int)t;
     const int id0 = (int)od * g.S[0] - g.P[0], ih0 = (int)oh * g.S[1] - g.P[1], iw0 = (int)ow * g.S[2] - g.P[2];
     const float* xn = x + n * g.xs[0];
-    float* yp = y + n * g.ys[0] + od * g.ys[2] + oh * g.ys[3] + ow * g.ys[4];
+    float* yp = y + n * g.ys[0] + od * g.ys[2] + oh * g.ys[3] + ow * g.ys[4];   // any output layout
     for (int oc = 0; oc < Opad; oc += FP_OT) {
       float acc[FP_OT];
 #pragma unroll
@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(256, 2) conv_smallk_fprop2(const float* __rest
   }
   for (int i = threadIdx.x; i < Opad; i += blockDim.x) bs[i] = (b && i < g.O) ? __ldg(b + i) : 0.f;
   __syncthreads();
-  const bool pair_store = (g.Oe[2] & 1) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0;
+  const bool nxc_out = g.ys[1] == 1;                       // channels-last output: 32 channels of a pixel are contiguous
+  const bool pair_store = !nxc_out && (g.Oe[2] & 1) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0;
+  const bool vec_out = nxc_out && (g.O & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
 
   for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
     unsigned t, wp, oh, od;
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(256, 2) conv_smallk_fprop2(const float* __rest
     const bool has2 = ow0 + 1 < g.Oe[2];
     const int id0 = (int)od * g.S[0] - g.P[0], ih0 = (int)oh * g.S[1] - g.P[1], iw0 = ow0 - g.P[2];
     const float* xn = x + n * g.xs[0];
-    float* yp = y + n * g.ys[0] + od * g.ys[2] + oh * g.ys[3] + ow0;
+    float* yp = y + n * g.ys[0] + od * g.ys[2] + oh * g.ys[3] + ow0 * g.ys[4];
     for (int oc = 0; oc < Opad; oc += OT) {
       float a0[OT], a1[OT];
 #pragma unroll
@@ -153,13 +155,26 @@ __global__ void __launch_bounds__(256, 2) conv_smallk_fprop2(const float* __rest
           }
         }
       }
+      if (vec_out) {
 #pragma unroll
-      for (int j = 0; j < OT; j++) {
-        if (oc + j < g.O) {
-          float* dst = yp + (long long)(oc + j) * g.ys[1];
-          const float v0 = act_apply(a0[j], act), v1 = act_apply(a1[j], act);
-          if (pair_store) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
-          else { dst[0] = v0; if (has2) dst[1] = v1; }
+        for (int j = 0; j < OT; j += 4) {
+          if (oc + j < g.O) {
+            *reinterpret_cast<float4*>(yp + oc + j) =
+                make_float4(act_apply(a0[j], act), act_apply(a0[j + 1], act), act_apply(a0[j + 2], act), act_apply(a0[j + 3], act));
+            if (has2)
+              *reinterpret_cast<float4*>(yp + g.ys[4] + oc + j) =
+                  make_float4(act_apply(a1[j], act), act_apply(a1[j + 1], act), act_apply(a1[j + 2], act), act_apply(a1[j + 3], act));
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < OT; j++) {
+          if (oc + j < g.O) {
+            float* dst = yp + (long long)(oc + j) * g.ys[1];
+            const float v0 = act_apply(a0[j], act), v1 = act_apply(a1[j], act);
+            if (pair_store) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+            else { dst[0] = v0; if (has2) dst[g.ys[4]] = v1; }
+          }
         }
       }
     }
@@ -290,7 +305,7 @@ __global__ void conv_smallk_wgrad_reduce(const float* __restrict__ partial, floa
 }  // namespace
 
 bool okl_conv_small_fprop_ok(const okl_conv_desc* d) {
-  if (d->x_layout != OKL_NCX || d->y_layout != OKL_NCX) return false;
+  if (d->x_layout != OKL_NCX && d->C != 1) return false;
   long long K = d->C;
   for (int i = 0; i < d->nd; i++) K *= d->k[i];
   int Opad = (d->O + FP_OT - 1) / FP_OT * FP_OT;
@@ -298,7 +313,7 @@ bool okl_conv_small_fprop_ok(const okl_conv_desc* d) {
 }
 
 bool okl_conv_small_wgrad_ok(const okl_conv_desc* d) {
-  if (d->x_layout != OKL_NCX || d->y_layout != OKL_NCX) return false;
+  if (d->x_layout != OKL_NCX && d->C != 1) return false;
   long long K = d->C;
   for (int i = 0; i < d->nd; i++) K *= d->k[i];
   return K + 1 <= 28;

@@ -161,7 +161,9 @@ extern "C" int okl_free(okl_ctx* ctx, void* p) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   auto it = ctx->live.find(p);
   OKL_REQUIRE(it != ctx->live.end(), "okl_free: %p was not returned by okl_malloc", p);
-  // stream-ordered reuse: every consumer runs on ctx->stream (the comm stream is joined before reuse)
+  // stream-ordered reuse: every consumer runs on ctx->stream (the comm stream is joined before reuse).  A block released while
+  // a CUDA graph is being captured stays out of the pool: the graph's kernels keep writing to it on every replay.
+  if (ctx->capturing) return OKL_OK;
   ctx->free_blocks.emplace(it->second, p);
   return OKL_OK;
 }

@@ -205,6 +205,52 @@ __global__ void maxpool2_bwd_kernel(const float* __restrict__ x, const float* __
   }
 }
 
+// channels-last 2x2 / stride 2: one thread per (window, 4 channels), 128-bit accesses along C
+__global__ void maxpool2_nxc_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t total4, int C4, int OW, int OH, int W, int H) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    size_t r = i / C4;
+    const int ow = (int)(r % OW); r /= OW;
+    const int oh = (int)(r % OH);
+    const size_t n = r / OH;
+    const float4* p = reinterpret_cast<const float4*>(x) + ((n * H + 2 * oh) * W + 2 * ow) * C4 + c;
+    const float4 a = p[0], b = p[C4], d = p[(size_t)W * C4], e = p[(size_t)W * C4 + C4];
+    float4 m;
+    m.x = fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)); m.y = fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y));
+    m.z = fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)); m.w = fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w));
+    reinterpret_cast<float4*>(y)[i] = m;
+  }
+}
+__device__ __forceinline__ float4 pool_route(float4 v, float4 m, float4 g) {
+  return make_float4(v.x == m.x ? g.x : 0.f, v.y == m.y ? g.y : 0.f, v.z == m.z ? g.z : 0.f, v.w == m.w ? g.w : 0.f);
+}
+__global__ void maxpool2_nxc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dx, size_t total4, int C4,
+                                        int OW, int OH, int W, int H, int relu_mask) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    size_t r = i / C4;
+    const int ow = (int)(r % OW); r /= OW;
+    const int oh = (int)(r % OH);
+    const size_t n = r / OH;
+    const size_t off = ((n * H + 2 * oh) * W + 2 * ow) * C4 + c;
+    const float4* p = reinterpret_cast<const float4*>(x) + off;
+    const float4 a = p[0], b = p[C4], d = p[(size_t)W * C4], e = p[(size_t)W * C4 + C4];
+    float4 m;
+    m.x = fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)); m.y = fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y));
+    m.z = fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)); m.w = fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w));
+    float4 gv = reinterpret_cast<const float4*>(g)[i];
+    if (relu_mask) {
+      if (!(m.x > 0.f)) gv.x = 0.f;
+      if (!(m.y > 0.f)) gv.y = 0.f;
+      if (!(m.z > 0.f)) gv.z = 0.f;
+      if (!(m.w > 0.f)) gv.w = 0.f;
+    }
+    float4* q = reinterpret_cast<float4*>(dx) + off;
+    q[0] = pool_route(a, m, gv); q[C4] = pool_route(b, m, gv);
+    q[(size_t)W * C4] = pool_route(d, m, gv); q[(size_t)W * C4 + C4] = pool_route(e, m, gv);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ softmax / losses
 // one warp per row
 __global__ void softmax_fwd_kernel(const float* __restrict__ x, float* __restrict__ p, int rows, int cols) {
@@ -591,6 +637,13 @@ extern "C" int okl_pool_fwd(okl_ctx* ctx, int kind, const void* x, void* y, int 
     OKL_LAUNCHED(ctx, "maxpool2_fwd");
     return OKL_OK;
   }
+  if (kind == OKL_POOL_MAX && layout == OKL_NXC && pool == 2 && stride == 2 && (H & 1) == 0 && (W & 1) == 0 && (C & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    maxpool2_nxc_fwd_kernel<<<okl_grid_1d(ctx, total / 4, 256, 16), 256, 0, ctx->stream>>>((const float*)x, (float*)y, total / 4, C / 4, g.OW,
+                                                                                      g.OH, W, H);
+    OKL_LAUNCHED(ctx, "maxpool2_nxc_fwd");
+    return OKL_OK;
+  }
   pool_fwd_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)x, (float*)y, g, kind);
   OKL_LAUNCHED(ctx, "pool_fwd");
   return OKL_OK;
@@ -611,6 +664,14 @@ extern "C" int okl_pool_bwd(okl_ctx* ctx, int kind, const void* x, const void* g
     maxpool2_bwd_kernel<<<okl_grid_1d(ctx, nwin, 256, 16), 256, 0, ctx->stream>>>((const float*)x, (const float*)gr, (float*)dx, nwin, g.OW,
                                                                               W, relu_mask);
     OKL_LAUNCHED(ctx, "maxpool2_bwd");
+    return OKL_OK;
+  }
+  if (kind == OKL_POOL_MAX && layout == OKL_NXC && pool == 2 && stride == 2 && (H & 1) == 0 && (W & 1) == 0 && (C & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && (reinterpret_cast<uintptr_t>(gr) & 15) == 0) {
+    size_t nwin4 = (size_t)N * g.OH * g.OW * (C / 4);
+    maxpool2_nxc_bwd_kernel<<<okl_grid_1d(ctx, nwin4, 256, 16), 256, 0, ctx->stream>>>((const float*)x, (const float*)gr, (float*)dx, nwin4,
+                                                                                  C / 4, g.OW, g.OH, W, H, relu_mask);
+    OKL_LAUNCHED(ctx, "maxpool2_nxc_bwd");
     return OKL_OK;
   }
   pool_bwd_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)x, (const float*)gr, (float*)dx, g, kind, relu_mask);

@@ -88,6 +88,13 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
                "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -183,6 +190,12 @@ struct TcGemmParams {
   int act;
   float* ws;           // [splits][M][N] partials when splits > 1
   int* counters;       // [tiles] arrival counters (zero on entry, reset by the last arriver) when splits > 1
+  // implicit-GEMM convolution (MODE 1 = fprop/dgrad, MODE 2 = wgrad); activations are channels-last (N, H, W, C)
+  int cv_TW, cv_TH, cv_TN;         // spatial tile: TW x TH pixels of TN images (128 pixels = an M tile in MODE 1, 32 = a k-block in MODE 2)
+  int cv_tw_sh, cv_th_sh;          // log2 of TW, TH
+  int cv_tiles_w, cv_tiles_h;      // tiles per image
+  int cv_OH, cv_OW, cv_NB;         // extents of the tiled pixel space and batch
+  int cv_C, cv_cblocks, cv_kw, cv_ph, cv_pw;
   unsigned long long* dbg;   // optional per-CTA phase timestamps (globaltimer ns): start, setup, first full, acc ready, done
   __nv_bfloat16* D16;  // optional bf16 shadow of D (same ld), or nullptr
 };
@@ -202,7 +215,7 @@ struct TcCfg {
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int KIND, bool A_MN, bool B_MN, int BN>
+template <int KIND, bool A_MN, bool B_MN, int BN, int MODE = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmParams p) {
   using Cfg = TcCfg<KIND, BN>;
@@ -261,6 +274,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const int k0 = kb * Cfg::BK;
+          if (MODE == 1) {
+            // implicit-GEMM fprop / dgrad: k-block = (filter tap, 32-channel chunk); the A tile is the TW x TH x TN pixel rectangle of
+            // this M tile shifted by the tap - TMA zero-fills what falls outside the image, which IS the zero padding.
+            const int tap = kb / p.cv_cblocks, cb = kb - tap * p.cv_cblocks;
+            const int u = tap / p.cv_kw, v = tap - u * p.cv_kw;
+            const int wt = tm % p.cv_tiles_w, r2 = tm / p.cv_tiles_w;
+            const int ht = r2 % p.cv_tiles_h, ng = r2 / p.cv_tiles_h;
+            tma_load_4d(&tmA, &full_bar[stage], sa, cb * Cfg::BK, wt * p.cv_TW + v - p.cv_pw, ht * p.cv_TH + u - p.cv_ph, ng * p.cv_TN);
+            tma_load_2d(&tmB, &full_bar[stage], sb, tap * p.cv_C + cb * Cfg::BK, n0);
+          } else if (MODE == 2) {
+            // implicit-GEMM wgrad: M = O, N = (tap, c), k-block = 32 output pixels; A = g^T and B = shifted x, both MN-major
+            const int wt = kb % p.cv_tiles_w, r2 = kb / p.cv_tiles_w;
+            const int ht = r2 % p.cv_tiles_h, ng = r2 / p.cv_tiles_h;
+            const int tap = n0 / p.cv_C, c0 = n0 - tap * p.cv_C;
+            const int u = tap / p.cv_kw, v = tap - u * p.cv_kw;
+#pragma unroll
+            for (int c = 0; c < TC_BM / Cfg::EPC; c++)
+              tma_load_4d(&tmA, &full_bar[stage], sa + c * (Cfg::BK * 128), m0 + c * Cfg::EPC, wt * p.cv_TW, ht * p.cv_TH, ng * p.cv_TN);
+#pragma unroll
+            for (int c = 0; c < BN / Cfg::EPC; c++)
+              tma_load_4d(&tmB, &full_bar[stage], sb + c * (Cfg::BK * 128), c0 + c * Cfg::EPC, wt * p.cv_TW + v - p.cv_pw,
+                          ht * p.cv_TH + u - p.cv_ph, ng * p.cv_TN);
+          } else {
           if (!A_MN) {
             tma_load_2d(&tmA, &full_bar[stage], sa, k0, m0);                       // box {BK, 128}: rows = m
           } else {
@@ -274,6 +310,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int c = 0; c < BN / Cfg::EPC; c++)
               tma_load_2d(&tmB, &full_bar[stage], sb + c * (Cfg::BK * 128), n0 + c * Cfg::EPC, k0);
+          }
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -356,8 +393,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           const int r = 4 * i + rsub;
-          const int mm = m_base + r;
+          int mm = m_base + r;
           float4 o = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
+          if (MODE == 1) {
+            // tile row -> (image, h, w) of the channels-last output; rows outside the image are dropped
+            const int tr = q * 32 + r;
+            const int wt = tm % p.cv_tiles_w, r2 = tm / p.cv_tiles_w;
+            const int ht = r2 % p.cv_tiles_h, ng = r2 / p.cv_tiles_h;
+            const int ww = wt * p.cv_TW + (tr & (p.cv_TW - 1));
+            const int hh = ht * p.cv_TH + ((tr >> p.cv_tw_sh) & (p.cv_TH - 1));
+            const int ni = ng * p.cv_TN + (tr >> (p.cv_tw_sh + p.cv_th_sh));
+            mm = (ww < p.cv_OW && hh < p.cv_OH && ni < p.cv_NB) ? (ni * p.cv_OH + hh) * p.cv_OW + ww : p.M;
+          }
           if (mm < p.M && nn < p.N) {
             if (p.splits > 1) {
               float* dst = p.ws + ((size_t)split * p.M + mm) * (size_t)p.N + nn;
@@ -530,10 +577,10 @@ int make_map_2d(CUtensorMap* map, int kind, const void* base, uint64_t inner, ui
   return OKL_OK;
 }
 
-template <int KIND, bool A_MN, bool B_MN, int BN>
+template <int KIND, bool A_MN, bool B_MN, int BN, int MODE = 0>
 int launch_cfg(okl_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const TcGemmParams& p) {
   using Cfg = TcCfg<KIND, BN>;
-  auto kern = tc_gemm_kernel<KIND, A_MN, B_MN, BN>;
+  auto kern = tc_gemm_kernel<KIND, A_MN, B_MN, BN, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     OKL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -684,6 +731,207 @@ int okl_f32_to_bf16(okl_ctx* ctx, const float* src, void* dst, size_t n) {
   f32_to_bf16_kernel<<<okl_grid_1d(ctx, (n + 1) / 2, 256), 256, 0, ctx->stream>>>(src, (__nv_bfloat16*)dst, n);
   OKL_LAUNCHED(ctx, "f32_to_bf16");
   return OKL_OK;
+}
+
+
+// ================================================================================================ implicit-GEMM convolution
+namespace {
+
+typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 4-D fp32 tensor map over a channels-last activation tensor (N, H, W, C): dims {C, W, H, N}
+int make_map_nhwc(CUtensorMap* map, const void* base, int C, int W, int H, int N, int box_c, int box_w, int box_h, int box_n, bool atom32) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    okl_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return OKL_ERR_CUDA;
+  }
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstride[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    okl_set_error("cuTensorMapEncodeTiled(4d) failed with CUresult %d (C=%d W=%d H=%d N=%d box=%d,%d,%d,%d)", (int)r, C, W, H, N, box_c,
+                  box_w, box_h, box_n);
+    return OKL_ERR_CUDA;
+  }
+  return OKL_OK;
+}
+
+int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+
+// pixels-per-tile rectangle TW x TH x TN (all powers of two, product = `pixels`) for an OH x OW image
+void pick_tile(int OH, int OW, int pixels, int& TW, int& TH, int& TN) {
+  TW = pow2_ceil(OW); if (TW > pixels) TW = pixels;
+  TH = pow2_ceil(OH); if (TH > pixels / TW) TH = pixels / TW;
+  TN = pixels / (TW * TH);
+}
+
+// W2[o][tap][c] = W[o][c][tap]  (K-major filter bank for the channels-last implicit GEMM)
+// Wf[c][tap][o] = W[o][c][T-1-tap]  (flipped + transposed bank: dgrad as a convolution of g)
+__global__ void flip_filters_kernel(const float* __restrict__ W, float* __restrict__ Wf, int O, int C, int T) {
+  const size_t total = (size_t)O * C * T;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i % O);
+    const size_t r = i / O;
+    const int t = (int)(r % T), c = (int)(r / T);
+    Wf[i] = W[((size_t)o * C + c) * T + (T - 1 - t)];
+  }
+}
+
+struct ConvShape { int N, C, O, H, W, KH, KW, PH, PW, OH, OW; };
+
+int conv_shape(const okl_conv_desc* d, ConvShape& s) {
+  s.N = d->N; s.C = d->C; s.O = d->O;
+  if (d->nd == 1) { s.H = 1; s.W = d->in[0]; s.KH = 1; s.KW = d->k[0]; s.PH = 0; s.PW = d->p[0]; }
+  else { s.H = d->in[0]; s.W = d->in[1]; s.KH = d->k[0]; s.KW = d->k[1]; s.PH = d->p[0]; s.PW = d->p[1]; }
+  s.OH = s.H + 2 * s.PH - s.KH + 1;
+  s.OW = s.W + 2 * s.PW - s.KW + 1;
+  return OKL_OK;
+}
+
+int pick_bn(int n) { return n >= 256 && n % 256 == 0 ? 256 : (n >= 128 && n % 128 == 0 ? 128 : (n >= 64 && n % 64 == 0 ? 64 : 32)); }
+
+// y[N,OH,OW,Oc] = act(conv(x[N,H,W,Cc], W2[Oc][T*Cc]) + bias)  with padding (ph, pw), stride 1, everything channels-last
+int conv_igemm_fprop(okl_ctx* ctx, const float* x, int N, int H, int W, int Cc, const float* W2, int Oc, int KH, int KW, int ph, int pw,
+                     int OH, int OW, const float* bias, int act, float* y) {
+  const int T = KH * KW;
+  int TW, TH, TN;
+  pick_tile(OH, OW, TC_BM, TW, TH, TN);
+  int bn = Oc >= 256 ? 256 : (Oc > 64 ? 128 : (Oc > 32 ? 64 : 32));
+  const int tiles_w = (OW + TW - 1) / TW, tiles_h = (OH + TH - 1) / TH, tiles_ng = (N + TN - 1) / TN;
+  long long tiles_m = (long long)tiles_w * tiles_h * tiles_ng;
+  while (bn > 64 && tiles_m * ((Oc + bn - 1) / bn) < ctx->sm_count) bn >>= 1;     // more, smaller tiles when the grid would not fill the chip
+  CUtensorMap ta, tb;
+  int s = make_map_nhwc(&ta, x, Cc, W, H, N, 32, TW, TH, TN, false);
+  if (s != OKL_OK) return s;
+  s = make_map_2d(&tb, 0, W2, (uint64_t)T * Cc, (uint64_t)Oc, (uint64_t)T * Cc, 32, bn);
+  if (s != OKL_OK) return s;
+  TcGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = N * OH * OW; p.N = Oc; p.K = T * Cc;
+  p.tiles_m = (int)tiles_m; p.tiles_n = (Oc + bn - 1) / bn; p.splits = 1;
+  p.kb_total = T * (Cc / 32); p.kb_per_split = p.kb_total;
+  p.D = y; p.ldd = Oc; p.bias = bias; p.act = act;
+  p.cv_TW = TW; p.cv_TH = TH; p.cv_TN = TN; p.cv_tw_sh = ilog2(TW); p.cv_th_sh = ilog2(TH);
+  p.cv_tiles_w = tiles_w; p.cv_tiles_h = tiles_h; p.cv_OH = OH; p.cv_OW = OW; p.cv_NB = N;
+  p.cv_C = Cc; p.cv_cblocks = Cc / 32; p.cv_kw = KW; p.cv_ph = ph; p.cv_pw = pw;
+  p.dbg = nullptr;
+  switch (bn) {
+    case 32: return launch_cfg<0, false, false, 32, 1>(ctx, ta, tb, p);
+    case 64: return launch_cfg<0, false, false, 64, 1>(ctx, ta, tb, p);
+    case 128: return launch_cfg<0, false, false, 128, 1>(ctx, ta, tb, p);
+    default: return launch_cfg<0, false, false, 256, 1>(ctx, ta, tb, p);
+  }
+}
+
+struct Scratch {            // pool block released back when the enqueueing call returns (stream-ordered reuse)
+  okl_ctx* ctx; void* p = nullptr;
+  Scratch(okl_ctx* c) : ctx(c) {}
+  int alloc(size_t bytes) { return okl_malloc(ctx, bytes, &p); }
+  ~Scratch() { if (p) okl_free(ctx, p); }
+};
+
+}  // namespace
+
+bool okl_tc_conv_supported(okl_ctx* ctx, const okl_conv_desc* d) {
+  if (ctx->cc < 100 || env_int("OKL_TC_DISABLE", 0) || env_int("OKL_TC_CONV_DISABLE", 0)) return false;
+  if (d->nd > 2 || d->x_layout != OKL_NXC || d->y_layout != OKL_NXC) return false;
+  for (int i = 0; i < d->nd; i++)
+    if (d->s[i] != 1) return false;
+  if (d->C % 32 || d->O % 32) return false;             // 32 fp32 channels = one 128-byte swizzle row, for x (fprop) and g (dgrad)
+  ConvShape s;
+  conv_shape(d, s);
+  if (s.OH < 1 || s.OW < 1 || s.KH > 16 || s.KW > 16) return false;
+  if (s.PH > s.KH - 1 || s.PW > s.KW - 1) return false;  // dgrad runs as a convolution with padding k-1-p >= 0
+  return true;
+}
+
+int okl_tc_conv_fprop(okl_ctx* ctx, const okl_conv_desc* d, const float* x, const float* W, const float* b, float* y) {
+  ConvShape s;
+  conv_shape(d, s);
+  const int T = s.KH * s.KW;
+  Scratch w2(ctx);
+  int st = w2.alloc((size_t)s.O * T * s.C * sizeof(float));
+  if (st != OKL_OK) return st;
+  st = okl_permute(ctx, w2.p, W, s.O, s.C, T, OKL_NCX);               // (O, C, T) -> (O, T, C)
+  if (st != OKL_OK) return st;
+  return conv_igemm_fprop(ctx, x, s.N, s.H, s.W, s.C, (const float*)w2.p, s.O, s.KH, s.KW, s.PH, s.PW, s.OH, s.OW, b, d->act, y);
+}
+
+int okl_tc_conv_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const float* g, const float* W, float* dx) {
+  // dx = conv(g, flip(W)^T) with padding k-1-p: the same implicit GEMM with the roles of C and O exchanged
+  ConvShape s;
+  conv_shape(d, s);
+  const int T = s.KH * s.KW;
+  Scratch wf(ctx);
+  int st = wf.alloc((size_t)s.O * T * s.C * sizeof(float));
+  if (st != OKL_OK) return st;
+  flip_filters_kernel<<<okl_grid_1d(ctx, (size_t)s.O * T * s.C, 256), 256, 0, ctx->stream>>>(W, (float*)wf.p, s.O, s.C, T);
+  OKL_LAUNCHED(ctx, "flip_filters");
+  return conv_igemm_fprop(ctx, g, s.N, s.OH, s.OW, s.O, (const float*)wf.p, s.C, s.KH, s.KW, s.KH - 1 - s.PH, s.KW - 1 - s.PW, s.H, s.W,
+                          nullptr, OKL_ACT_NONE, dx);
+}
+
+int okl_tc_conv_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const float* x, const float* g, float* dW) {
+  ConvShape s;
+  conv_shape(d, s);
+  const int T = s.KH * s.KW;
+  const int M = s.O, N = T * s.C;
+  int TW, TH, TN;
+  pick_tile(s.OH, s.OW, 32, TW, TH, TN);
+  const int tiles_w = (s.OW + TW - 1) / TW, tiles_h = (s.OH + TH - 1) / TH, tiles_ng = (s.N + TN - 1) / TN;
+  const int kb_total = tiles_w * tiles_h * tiles_ng;
+  const int bn = pick_bn(s.C);                                          // an N tile never straddles two taps
+  const int tiles_m = (M + TC_BM - 1) / TC_BM, tiles_n = N / bn;
+  Scratch dw2(ctx);
+  int st = dw2.alloc((size_t)M * N * sizeof(float));
+  if (st != OKL_OK) return st;
+  CUtensorMap ta, tb;
+  st = make_map_nhwc(&ta, g, s.O, s.OW, s.OH, s.N, 32, TW, TH, TN, true);
+  if (st != OKL_OK) return st;
+  st = make_map_nhwc(&tb, x, s.C, s.W, s.H, s.N, 32, TW, TH, TN, true);
+  if (st != OKL_OK) return st;
+  TcGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = kb_total * 32;
+  p.tiles_m = tiles_m; p.tiles_n = tiles_n;
+  long long tiles = (long long)tiles_m * tiles_n;
+  int splits = (int)(ctx->sm_count / tiles);
+  if (splits > kb_total / 4) splits = kb_total / 4;
+  if (splits > 32) splits = 32;
+  if (splits < 1) splits = 1;
+  p.kb_total = kb_total; p.kb_per_split = (kb_total + splits - 1) / splits;
+  p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.D = (float*)dw2.p; p.ldd = N; p.bias = nullptr; p.act = OKL_ACT_NONE;
+  if (p.splits > 1) {
+    st = okl_ensure_workspace(ctx, (size_t)p.splits * M * N * sizeof(float));
+    if (st != OKL_OK) return st;
+    p.ws = (float*)ctx->workspace;
+    if (!ctx->tile_counters) {
+      OKL_CHECK_CUDA(cudaMalloc(&ctx->tile_counters, 4096 * sizeof(int)));
+      OKL_CHECK_CUDA(cudaMemsetAsync(ctx->tile_counters, 0, 4096 * sizeof(int), ctx->stream));
+    }
+    OKL_REQUIRE(tiles <= 2048, "conv wgrad: too many tiles for split-K");
+    p.counters = ctx->tile_counters;
+  }
+  p.cv_TW = TW; p.cv_TH = TH; p.cv_TN = TN; p.cv_tw_sh = ilog2(TW); p.cv_th_sh = ilog2(TH);
+  p.cv_tiles_w = tiles_w; p.cv_tiles_h = tiles_h; p.cv_OH = s.OH; p.cv_OW = s.OW; p.cv_NB = s.N;
+  p.cv_C = s.C; p.cv_cblocks = s.C / 32; p.cv_kw = s.KW; p.cv_ph = s.PH; p.cv_pw = s.PW;
+  switch (bn) {
+    case 32: st = launch_cfg<0, true, true, 32, 2>(ctx, ta, tb, p); break;
+    case 64: st = launch_cfg<0, true, true, 64, 2>(ctx, ta, tb, p); break;
+    case 128: st = launch_cfg<0, true, true, 128, 2>(ctx, ta, tb, p); break;
+    default: st = launch_cfg<0, true, true, 256, 2>(ctx, ta, tb, p); break;
+  }
+  if (st != OKL_OK) return st;
+  return okl_permute(ctx, dW, dw2.p, s.O, s.C, T, OKL_NXC);             // (O, T, C) -> (O, C, T)
 }
 
 // ------------------------------------------------------------------------------------------------ dense entry points

@@ -242,13 +242,24 @@ class _ConvBase(_ParamLayer):
         check(lib.okl_conv_out_extent(C.byref(d), out))
         return d, tuple(out[i] for i in range(nd))
 
+    def _tc_eligible(self):
+        """Shapes the tcgen05 implicit-GEMM convolution takes (okl_tc_conv_supported): 1-D/2-D, unit stride, channel counts
+        that are multiples of 32, padding <= k-1.  Those layers run channels-last in TF32/BF16 mode."""
+        return (self._nd <= 2 and all(s == 1 for s in self._s) and self.in_channels % 32 == 0 and self.out_channels % 32 == 0 and
+                all(p <= k - 1 for p, k in zip(self._p, self._k)))
+
     def _forward(self, inputs):
         inputs = _as_tensor(inputs)
         ctx = get_ctx()
         self._bucket.materialize()
         self.inputs = inputs
-        xl = inputs._layout if inputs.ndim >= 3 and inputs._dev_valid else NCX
-        yl = getattr(self, "_out_layout", NCX)
+        if ctx.precision != _lib.FP32 and self._tc_eligible():
+            xl = yl = NXC
+        else:
+            xl = inputs._layout if inputs.ndim >= 3 and inputs._dev_valid else NCX
+            if xl == NXC and self.in_channels > 1 and self._nd == 3:
+                xl = NCX
+            yl = getattr(self, "_out_layout", NCX)
         d, oe = self._desc(inputs.shape, xl, yl, self._fused_act)
         out = Tensor._empty((inputs.shape[0], self.out_channels) + oe, self._np_dtype, layout=yl)
         check(lib.okl_conv_fprop(ctx.h, C.byref(d), inputs._dptr(xl), self._bucket.ptr(0), self._bucket.ptr(1), out._ptr_raw()))

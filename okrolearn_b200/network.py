@@ -189,7 +189,8 @@ class NeuralNetwork:
                     ('pre_forward', 'post_forward', 'pre_backward', 'post_backward')))
 
     def _plan(self, fast: bool):
-        key = (fast, self.fuse_activations, self.skip_input_grad, tuple(id(l) for l in self.layers), get_ctx().nranks)
+        key = (fast, self.fuse_activations, self.skip_input_grad, tuple(id(l) for l in self.layers), get_ctx().nranks,
+               get_ctx().precision)
         if key == self._plan_key:
             return
         self._plan_key = key
@@ -203,6 +204,19 @@ class NeuralNetwork:
                 l._bwd_fused_into_next = False
             if isinstance(l, _Pool):
                 l._fused_relu_bwd = False
+        # layout planning: a convolution that feeds (through activations / pooling) a tensor-core-eligible convolution writes
+        # its output channels-last, so no permutation is needed between them
+        tc_mode = get_ctx().precision != _lib.FP32
+        for i, l in enumerate(ls):
+            if isinstance(l, _ConvBase):
+                l._out_layout = NCX
+                if tc_mode:
+                    for nxt in ls[i + 1:]:
+                        if isinstance(nxt, (_Activation, _Pool)):
+                            continue
+                        if isinstance(nxt, _ConvBase) and nxt._tc_eligible():
+                            l._out_layout = _lib.NXC
+                        break
         if not fast:
             return
         if self.fuse_activations:

@@ -80,3 +80,81 @@ def test_tc_gemm_is_deterministic(okl):
     r1 = tc_gemm(okl, 0, 0, 1, A, B)
     r2 = tc_gemm(okl, 0, 0, 1, A, B)
     assert np.array_equal(r1, r2)            # split-K partials are reduced in a fixed order
+
+
+CONV_TC = [
+    # nd, N, C, spatial, O, k, p
+    (2, 4, 32, (16, 16), 32, 3, 1),
+    (2, 8, 64, (32, 32), 64, 3, 1),            # CIFAR layer 2
+    (2, 4, 64, (16, 16), 128, 3, 1),           # CIFAR layer 3
+    (2, 6, 128, (8, 8), 256, 3, 1),            # CIFAR layer 5 (several images per 128-pixel tile)
+    (2, 3, 32, (13, 11), 64, 3, 0),            # odd extents, no padding
+    (2, 2, 64, (9, 20), 32, (3, 5), (1, 2)),   # rectangular filter / padding
+    (2, 2, 32, (8, 8), 32, 1, 0),              # 1x1
+    (1, 4, 64, (256,), 64, 3, 1),              # Conv1D sequence shape
+    (1, 2, 32, (100,), 96, 5, 2),
+]
+
+
+@pytest.mark.parametrize("nd,N,C,sp,Oc,k,p", CONV_TC)
+def test_conv_implicit_gemm_tf32(okl, nd, N, C, sp, Oc, k, p):
+    """tcgen05 implicit-GEMM convolution (fprop, dgrad, wgrad) in TF32 mode vs the fp64 oracle, through the layer API."""
+    okl.set_precision("tf32")
+    try:
+        rng = np.random.default_rng(N * 100 + C + Oc)
+        kt = O._tup(k, nd)
+        x = rng.standard_normal((N, C) + sp).astype(np.float32)
+        W = rng.standard_normal((Oc, C) + kt) * 0.1
+        b = rng.standard_normal((Oc, 1)) * 0.1
+        lay = okl.Conv1DLayer(C, Oc, kt[0], 1, p) if nd == 1 else okl.Conv2DLayer(C, Oc, kt, 1, p)
+        assert lay._tc_eligible()
+        (lay.weights if nd == 1 else lay.filters).data = W.copy()
+        lay.biases.data = b.copy()
+        y = lay.forward(okl.Tensor(x))
+        from okrolearn_b200 import _lib
+        assert y._layout == _lib.NXC                      # ran channels-last on the tensor cores
+        x64 = x.astype(np.float64)
+        yo = O.conv_forward_fast(x64, W, b, 1, p, dtype=np.float64)
+        assert rel_err(y.data, yo) < 3e-3
+        g = rng.standard_normal(yo.shape).astype(np.float32)
+        dX = lay.backward(okl.Tensor(g), 0.05)
+        dW, db, dXo = O.conv_backward_fast(x64, W, g.astype(np.float64), 1, p)
+        Wt = lay.weights if nd == 1 else lay.filters
+        assert rel_err(dX.data, dXo) < 3e-3
+        assert rel_err(Wt.grad, dW) < 3e-3 and rel_err(lay.biases.grad, db) < 1e-5
+        assert rel_err(Wt.data, W - 0.05 * dW) < 3e-3
+    finally:
+        okl.set_precision("fp32")
+
+
+def test_cifar_block_channels_last_pipeline(okl):
+    """Conv(3->32, small-K kernel writing channels-last) -> ReLU -> Conv(32->64, tcgen05) -> ReLU -> MaxPool -> Flatten -> Dense,
+    two train steps in TF32 mode vs the oracle network: exercises layout planning, NXC pooling and the NXC -> NCX flatten."""
+    okl.set_precision("tf32")
+    try:
+        rng = np.random.default_rng(3)
+        N = 8
+        X = rng.standard_normal((N, 3, 16, 16)).astype(np.float32)
+        T = rng.integers(0, 10, N)
+        W1, W2, W3 = rng.standard_normal((32, 3, 3, 3)) * 0.2, rng.standard_normal((64, 32, 3, 3)) * 0.05, rng.standard_normal((64 * 8 * 8, 10)) * 0.02
+        net = okl.NeuralNetwork()
+        c1, c2, d = okl.Conv2DLayer(3, 32, 3, 1, 1), okl.Conv2DLayer(32, 64, 3, 1, 1), okl.DenseLayer(64 * 8 * 8, 10)
+        c1.filters.data, c2.filters.data, d.weights.data = W1.copy(), W2.copy(), W3.copy()
+        for l in (c1, okl.ReLUActivationLayer(), c2, okl.ReLUActivationLayer(), okl.MaxPoolingLayer(2, 2), okl.FlattenLayer(), d,
+                  okl.SoftmaxActivationLayer()):
+            net.add(l)
+        on = O.OracleNetwork([O.OracleConv(W1, np.zeros((32, 1)), 1, 1, fast=True), O.OracleReLU(), O.OracleConv(W2, np.zeros((64, 1)), 1, 1, fast=True),
+                              O.OracleReLU(), O.OracleMaxPool(2, 2), O.OracleFlatten(), O.OracleDense(W3, np.zeros((1, 10))), O.OracleSoftmax()])
+        ce = okl.CrossEntropyLoss()
+        for fast in (False, True):
+            out = net._forward(okl.Tensor(X), _fast=fast)
+            loss = float(ce.forward(out, okl.Tensor(T)))
+            net._backward(ce.backward(out, None), 0.02)
+            ref = on.train_step(X.astype(np.float64), T, O.OracleCrossEntropy(), 0.02)
+            assert abs(loss - ref) < 5e-3 * abs(ref)
+        from okrolearn_b200 import _lib
+        assert c1.outputs._layout == _lib.NXC and c2.outputs._layout == _lib.NXC
+        assert rel_err(c2.filters.data, on.layers[2].W) < 5e-3 and rel_err(c1.filters.data, on.layers[0].W) < 5e-3
+        assert rel_err(d.weights.data, on.layers[6].W) < 5e-3
+    finally:
+        okl.set_precision("fp32")
