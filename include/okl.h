@@ -91,7 +91,9 @@ int okl_gather_rows(okl_ctx* ctx, void* dst, const void* src, const void* idx_i3
  * bwd: dW[K,N] = X^T . G ; db[N] = sum_rows G ; dX[M,K] = G . W^T  okl.py:35-37   (dX may be NULL)            */
 int okl_dense_fwd(okl_ctx* ctx, const void* X, const void* W, const void* b, void* Y, int M, int K, int N, int act);
 int okl_dense_bwd(okl_ctx* ctx, const void* X, const void* W, const void* G, void* dX, void* dW, void* db,
-                  int M, int K, int N);
+                  int M, int K, int N, const void* dx_relu_mask);
+/* dx_relu_mask (optional, shape of dX): dX is zeroed where mask <= 0 - the fused backward `g * (x > 0)` (okl.py:107) of a ReLU
+ * that sits between the previous layer and this one, evaluated in the GEMM epilogue instead of a separate pass. */
 
 /* The tcgen05 GEMM the Dense products run on in TF32/BF16 mode, exposed for tests and benchmarks (reference: np.dot in
  * Tensor.dot, tensor.py:58).  D[M,N] (row-major, ldd) = act(A . B + bias[N]); A, B, D, bias are fp32 device tensors.
@@ -119,7 +121,7 @@ int okl_conv_out_extent(const okl_conv_desc* d, int out[3]);
 /* y = act(conv(x, W) + b)                      okl.py:691-715 / 790-813 / 948-985 */
 int okl_conv_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* W, const void* b, void* y);
 /* dx = conv_transpose(g, W)                    okl.py:736-739 / 867-868 / 1017-1020 (+ repairs R1,R3) */
-int okl_conv_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* g, const void* W, void* dx);
+int okl_conv_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* g, const void* W, void* dx, const void* dx_relu_mask);
 /* dW = x (*) g ; db = sum_{n,pos} g            okl.py:729-735 / 865-866,870 / 1013-1016,991 (+ repairs R1,R2); db may be NULL */
 int okl_conv_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* g, void* dW, void* db);
 

@@ -63,11 +63,11 @@ SIGNATURES = {
     "okl_permute": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i]),
     "okl_gather_rows": (_i, [_vp, _vp, _vp, _vp, _ll, _ll]),
     "okl_dense_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
-    "okl_dense_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i]),
+    "okl_dense_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "okl_tc_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _i]),
     "okl_conv_out_extent": (_i, [_P(ConvDesc), _P(_i)]),
     "okl_conv_fprop": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp]),
-    "okl_conv_dgrad": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp]),
+    "okl_conv_dgrad": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp]),
     "okl_conv_wgrad": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp]),
     "okl_act_fwd": (_i, [_vp, _i, _vp, _vp, _sz]),
     "okl_act_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _sz]),

@@ -102,9 +102,9 @@ static inline int okl_grid_1d(const okl_ctx* ctx, size_t work_items, int block, 
 // FFMA (exact fp32) GEMM-shaped kernels: okl_ffma.cu
 int okl_ffma_dense_fwd(okl_ctx*, const float* X, const float* W, const float* b, float* Y, int M, int K, int N, int act);
 int okl_ffma_dense_dw(okl_ctx*, const float* X, const float* G, float* dW, int M, int K, int N);
-int okl_ffma_dense_dx(okl_ctx*, const float* G, const float* W, float* dX, int M, int K, int N);
+int okl_ffma_dense_dx(okl_ctx*, const float* G, const float* W, float* dX, int M, int K, int N, const float* relu_mask);
 int okl_ffma_conv_fprop(okl_ctx*, const okl_conv_desc*, const float* x, const float* W, const float* b, float* y);
-int okl_ffma_conv_dgrad(okl_ctx*, const okl_conv_desc*, const float* g, const float* W, float* dx);
+int okl_ffma_conv_dgrad(okl_ctx*, const okl_conv_desc*, const float* g, const float* W, float* dx, const float* relu_mask);
 int okl_ffma_conv_wgrad(okl_ctx*, const okl_conv_desc*, const float* x, const float* g, float* dW);
 // reductions: okl_elementwise.cu
 int okl_colsum(okl_ctx*, const float* G, float* out, long long rows, int cols);                       // out[c] = sum_r G[r,c]
@@ -113,10 +113,10 @@ int okl_channel_sum(okl_ctx*, const float* g, float* out, int N, int C, long lon
 bool okl_tc_dense_supported(okl_ctx*, int M, int K, int N);
 int okl_tc_dense_fwd(okl_ctx*, const float* X, const float* W, const float* b, float* Y, int M, int K, int N, int act);
 int okl_tc_dense_dw(okl_ctx*, const float* X, const float* G, float* dW, int M, int K, int N);
-int okl_tc_dense_dx(okl_ctx*, const float* G, const float* W, float* dX, int M, int K, int N);
+int okl_tc_dense_dx(okl_ctx*, const float* G, const float* W, float* dX, int M, int K, int N, const float* relu_mask);
 bool okl_tc_conv_supported(okl_ctx*, const okl_conv_desc*);
 int okl_tc_conv_fprop(okl_ctx*, const okl_conv_desc*, const float* x, const float* W, const float* b, float* y);
-int okl_tc_conv_dgrad(okl_ctx*, const okl_conv_desc*, const float* g, const float* W, float* dx);
+int okl_tc_conv_dgrad(okl_ctx*, const okl_conv_desc*, const float* g, const float* W, float* dx, const float* relu_mask);
 int okl_tc_conv_wgrad(okl_ctx*, const okl_conv_desc*, const float* x, const float* g, float* dW);
 // direct fp32 kernels for tiny reduction dims (first layers): okl_conv_small.cu
 bool okl_conv_small_fprop_ok(const okl_conv_desc*);

@@ -14,7 +14,7 @@ extern "C" int okl_dense_fwd(okl_ctx* ctx, const void* X, const void* W, const v
 }
 
 extern "C" int okl_dense_bwd(okl_ctx* ctx, const void* X, const void* W, const void* G, void* dX, void* dW, void* db,
-                             int M, int K, int N) {
+                             int M, int K, int N, const void* dx_relu_mask) {
   OKL_REQUIRE(ctx, "ctx is NULL");
   OKL_REQUIRE(M >= 0 && K >= 1 && N >= 1, "okl_dense_bwd: bad shape M=%d K=%d N=%d", M, K, N);
   OKL_REQUIRE(X && W && G, "okl_dense_bwd: NULL tensor");
@@ -31,8 +31,8 @@ extern "C" int okl_dense_bwd(okl_ctx* ctx, const void* X, const void* W, const v
     if (s != OKL_OK) return s;
   }
   if (dX && M > 0) {
-    if (tc) s = okl_tc_dense_dx(ctx, (const float*)G, (const float*)W, (float*)dX, M, K, N);
-    else s = okl_ffma_dense_dx(ctx, (const float*)G, (const float*)W, (float*)dX, M, K, N);
+    if (tc) s = okl_tc_dense_dx(ctx, (const float*)G, (const float*)W, (float*)dX, M, K, N, (const float*)dx_relu_mask);
+    else s = okl_ffma_dense_dx(ctx, (const float*)G, (const float*)W, (float*)dX, M, K, N, (const float*)dx_relu_mask);
     if (s != OKL_OK) return s;
   }
   return OKL_OK;
@@ -62,7 +62,7 @@ extern "C" int okl_conv_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void* 
   return okl_ffma_conv_fprop(ctx, d, (const float*)x, (const float*)W, (const float*)b, (float*)y);
 }
 
-extern "C" int okl_conv_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* g, const void* W, void* dx) {
+extern "C" int okl_conv_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* g, const void* W, void* dx, const void* dx_relu_mask) {
   OKL_REQUIRE(ctx && d, "NULL argument");
   long long si, so;
   int s = conv_sizes(d, &si, &so);
@@ -70,8 +70,8 @@ extern "C" int okl_conv_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* 
   if (d->N == 0) return OKL_OK;
   OKL_REQUIRE(g && W && dx, "okl_conv_dgrad: NULL tensor");
   if (ctx->precision != OKL_FP32 && okl_tc_conv_supported(ctx, d))
-    return okl_tc_conv_dgrad(ctx, d, (const float*)g, (const float*)W, (float*)dx);
-  return okl_ffma_conv_dgrad(ctx, d, (const float*)g, (const float*)W, (float*)dx);
+    return okl_tc_conv_dgrad(ctx, d, (const float*)g, (const float*)W, (float*)dx, (const float*)dx_relu_mask);
+  return okl_ffma_conv_dgrad(ctx, d, (const float*)g, (const float*)W, (float*)dx, (const float*)dx_relu_mask);
 }
 
 extern "C" int okl_conv_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* g, void* dW, void* db) {

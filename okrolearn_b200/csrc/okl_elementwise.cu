@@ -117,6 +117,15 @@ __global__ void gather_rows_kernel(float* __restrict__ dst, const float* __restr
   }
 }
 
+__global__ void gather_rows4_kernel(float4* __restrict__ dst, const float4* __restrict__ src, const int* __restrict__ idx, long long rows,
+                                    long long row4) {
+  size_t total = (size_t)rows * row4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i / row4, c = i - r * row4;
+    dst[i] = src[(size_t)idx[r] * row4 + c];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ pooling
 struct PoolGeom { int N, C, H, W, OH, OW, ps, st; long long xs[4], ys[4]; bool cl; };   // strides for (n,c,h,w)
 
@@ -600,6 +609,12 @@ extern "C" int okl_permute(okl_ctx* ctx, void* dst, const void* src, int N, int 
 extern "C" int okl_gather_rows(okl_ctx* ctx, void* dst, const void* src, const void* idx, long long rows, long long row_elems) {
   OKL_REQUIRE(ctx && (rows == 0 || (dst && src && idx)), "NULL argument");
   if (rows <= 0 || row_elems <= 0) return OKL_OK;
+  if ((row_elems & 3) == 0 && aligned16(dst) && aligned16(src)) {
+    gather_rows4_kernel<<<okl_grid_1d(ctx, (size_t)rows * (row_elems / 4), 256, 16), 256, 0, ctx->stream>>>(
+        (float4*)dst, (const float4*)src, (const int*)idx, rows, row_elems / 4);
+    OKL_LAUNCHED(ctx, "gather_rows4");
+    return OKL_OK;
+  }
   gather_rows_kernel<<<okl_grid_1d(ctx, (size_t)rows * row_elems, 256), 256, 0, ctx->stream>>>((float*)dst, (const float*)src,
                                                                                            (const int*)idx, rows, row_elems);
   OKL_LAUNCHED(ctx, "gather_rows");

@@ -116,22 +116,27 @@ struct DgradB {                       // B(k = (o,taps), c) = W[(o*C + c)*T + ta
 // ------------------------------------------------------------------------------------------------ epilogues
 struct DenseEpi {                     // Y[m*N + n] = act(v + b[n])
   static constexpr bool mContig = false;
-  float* Y; const float* b; int N; int act;
+  float* Y; const float* b; int N; int act; const float* mask;
   __device__ __forceinline__ void operator()(int m, int n, float v) const {
     if (b) v += __ldg(b + n);
-    Y[(long long)m * N + n] = apply_act(v, act);
+    v = apply_act(v, act);
+    if (mask && !(__ldg(mask + (long long)m * N + n) > 0.f)) v = 0.f;
+    Y[(long long)m * N + n] = v;
   }
 };
 struct ConvOutEpi {                   // y[n, o, opos] = act(v + b[o]) through the y strides
   static constexpr bool mContig = true;
-  float* y; const float* b; ConvGeom g; int act; bool out_is_input_space;
+  float* y; const float* b; ConvGeom g; int act; bool out_is_input_space; const float* mask;
   __device__ __forceinline__ void operator()(int m, int n, float v) const {
     unsigned t, w, h, d;
     if (out_is_input_space) { g.dIW.divmod((unsigned)m, t, w); g.dIH.divmod(t, t, h); g.dID.divmod(t, t, d); }
     else { g.dOW.divmod((unsigned)m, t, w); g.dOH.divmod(t, t, h); g.dOD.divmod(t, t, d); }
     const long long* st = out_is_input_space ? g.xs : g.ys;
     if (b) v += __ldg(b + n);
-    y[t * st[0] + (long long)n * st[1] + d * st[2] + h * st[3] + w * st[4]] = apply_act(v, act);
+    v = apply_act(v, act);
+    const long long off = t * st[0] + (long long)n * st[1] + d * st[2] + h * st[3] + w * st[4];
+    if (mask && !(__ldg(mask + off) > 0.f)) v = 0.f;
+    y[off] = v;
   }
 };
 
@@ -282,21 +287,21 @@ int launch_igemm(okl_ctx* ctx, const AL& al, const BL& bl, const EP& ep, int M, 
 int okl_ffma_dense_fwd(okl_ctx* ctx, const float* X, const float* W, const float* b, float* Y, int M, int K, int N, int act) {
   MatA<true> a{X, K, 1, M, K};
   MatB<true> bb{W, N, 1, K, N};
-  DenseEpi ep{Y, b, N, act};
+  DenseEpi ep{Y, b, N, act, nullptr};
   return launch_igemm(ctx, a, bb, ep, M, N, K, "ffma_dense_fwd");
 }
 int okl_ffma_dense_dw(okl_ctx* ctx, const float* X, const float* G, float* dW, int M, int K, int N) {
   // dW[K,N] = X^T G : A'(m'=kin, k'=batch) = X[batch*K + kin]
   MatA<false> a{X, 1, K, K, M};
   MatB<true> bb{G, N, 1, M, N};
-  DenseEpi ep{dW, nullptr, N, OKL_ACT_NONE};
+  DenseEpi ep{dW, nullptr, N, OKL_ACT_NONE, nullptr};
   return launch_igemm(ctx, a, bb, ep, K, N, M, "ffma_dense_dw");
 }
-int okl_ffma_dense_dx(okl_ctx* ctx, const float* G, const float* W, float* dX, int M, int K, int N) {
+int okl_ffma_dense_dx(okl_ctx* ctx, const float* G, const float* W, float* dX, int M, int K, int N, const float* mask) {
   // dX[M,K] = G W^T : B'(k'=nout, n'=kin) = W[kin*N + nout]
   MatA<true> a{G, N, 1, M, N};
   MatB<false> bb{W, 1, N, N, K};
-  DenseEpi ep{dX, nullptr, K, OKL_ACT_NONE};
+  DenseEpi ep{dX, nullptr, K, OKL_ACT_NONE, mask};
   return launch_igemm(ctx, a, bb, ep, M, K, N, "ffma_dense_dx");
 }
 
@@ -316,18 +321,18 @@ int okl_ffma_conv_fprop(okl_ctx* ctx, const okl_conv_desc* d, const float* x, co
   int Mpix = g.N * g.Oe[0] * g.Oe[1] * g.Oe[2], K = g.C * g.T;
   FpropA a{ConvPatch{x, g, Mpix, K}};
   FpropB bb{W, K, g.O};
-  ConvOutEpi ep{y, b, g, d->act, false};
+  ConvOutEpi ep{y, b, g, d->act, false, nullptr};
   return launch_igemm(ctx, a, bb, ep, Mpix, g.O, K, "ffma_conv_fprop");
 }
 
-int okl_ffma_conv_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const float* gp, const float* W, float* dx) {
+int okl_ffma_conv_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const float* gp, const float* W, float* dx, const float* mask) {
   ConvGeom g;
   int s = make_geom(d, g);
   if (s != OKL_OK) return s;
   int Mpix = g.N * g.I[0] * g.I[1] * g.I[2], K = g.O * g.T;
   DgradA a{gp, g, Mpix, K};
   DgradB bb{W, g, K};
-  ConvOutEpi ep{dx, nullptr, g, OKL_ACT_NONE, true};
+  ConvOutEpi ep{dx, nullptr, g, OKL_ACT_NONE, true, mask};
   return launch_igemm(ctx, a, bb, ep, Mpix, g.C, K, "ffma_conv_dgrad");
 }
 
@@ -338,6 +343,6 @@ int okl_ffma_conv_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const float* x, co
   int Mpix = g.N * g.Oe[0] * g.Oe[1] * g.Oe[2], KK = g.C * g.T;
   WgradA a{gp, g, Mpix};
   WgradB bb{ConvPatch{x, g, Mpix, KK}};
-  DenseEpi ep{dW, nullptr, KK, OKL_ACT_NONE};
+  DenseEpi ep{dW, nullptr, KK, OKL_ACT_NONE, nullptr};
   return launch_igemm(ctx, a, bb, ep, g.O, KK, Mpix, "ffma_conv_wgrad");
 }

@@ -187,6 +187,7 @@ struct TcGemmParams {
   float* D;            // output (ldd) when splits == 1
   long long ldd;
   const float* bias;   // per-column bias or nullptr
+  const float* mask;   // optional, same indexing as D: D = 0 where mask <= 0 (fused backward of a preceding ReLU)
   int act;
   float* ws;           // [splits][M][N] partials when splits > 1
   int* counters;       // [tiles] arrival counters (zero on entry, reset by the last arriver) when splits > 1
@@ -419,6 +420,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float f[4] = {o.x + bz[0], o.y + bz[1], o.z + bz[2], o.w + bz[3]};
 #pragma unroll
               for (int e = 0; e < 4; e++) f[e] = act_apply(f[e], p.act);
+              if (p.mask) {
+                const float* mk = p.mask + (size_t)mm * (size_t)p.ldd + nn;
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                  if (nn + e < p.N && !(__ldg(mk + e) > 0.f)) f[e] = 0.f;
+              }
               float* dst = p.D + (size_t)mm * (size_t)p.ldd + nn;
               if (vec_ok && nn + 4 <= p.N) *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
               else {
@@ -494,6 +501,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 4; j++) {
               if (p.bias) f[j] += __ldg(p.bias + nn + j);
               f[j] = act_apply(f[j], p.act);
+              if (p.mask && !(__ldg(p.mask + (size_t)mm * p.ldd + nn + j) > 0.f)) f[j] = 0.f;
             }
             *reinterpret_cast<float4*>(p.D + (size_t)mm * p.ldd + nn) = make_float4(f[0], f[1], f[2], f[3]);
             if (p.D16) {
@@ -626,7 +634,7 @@ int okl_f32_to_bf16(okl_ctx* ctx, const float* src, void* dst, size_t n);
 //   b_mn == 0: B stored [N][K] (ldb, K contiguous);  b_mn == 1: B stored [K][N] (ldb, N contiguous)
 // kind 0 = TF32 (A,B are fp32), kind 1 = BF16 (A,B are bf16).
 int okl_tc_gemm_raw(okl_ctx* ctx, int kind, int a_mn, int b_mn, int M, int N, int K, const void* A, long long lda, const void* B,
-                    long long ldb, float* D, long long ldd, const float* bias, int act, void* D16) {
+                    long long ldb, float* D, long long ldd, const float* bias, int act, void* D16, const float* mask = nullptr) {
   const int es = kind == 0 ? 4 : 2;
   const int bk = 128 / es, epc = 128 / es;
   OKL_REQUIRE(M >= 1 && N >= 1 && K >= 1, "tc_gemm: bad shape");
@@ -678,7 +686,10 @@ int okl_tc_gemm_raw(okl_ctx* ctx, int kind, int a_mn, int b_mn, int M, int N, in
   TcGemmParams p;
   p.M = M; p.N = N; p.K = K;
   p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.splits = splits; p.kb_per_split = kb_per_split; p.kb_total = kb_total;
-  p.D = D; p.ldd = ldd; p.bias = bias; p.act = act; p.ws = nullptr; p.D16 = (__nv_bfloat16*)D16;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.splits = splits; p.kb_per_split = kb_per_split; p.kb_total = kb_total;
+  p.D = D; p.ldd = ldd; p.bias = bias; p.act = act; p.ws = nullptr; p.D16 = (__nv_bfloat16*)D16; p.mask = mask;
   p.counters = nullptr;
   p.dbg = (unsigned long long*)ctx->tc_dbg;
   if (splits > 1) {
@@ -800,7 +811,7 @@ int pick_bn(int n) { return n >= 256 && n % 256 == 0 ? 256 : (n >= 128 && n % 12
 
 // y[N,OH,OW,Oc] = act(conv(x[N,H,W,Cc], W2[Oc][T*Cc]) + bias)  with padding (ph, pw), stride 1, everything channels-last
 int conv_igemm_fprop(okl_ctx* ctx, const float* x, int N, int H, int W, int Cc, const float* W2, int Oc, int KH, int KW, int ph, int pw,
-                     int OH, int OW, const float* bias, int act, float* y) {
+                     int OH, int OW, const float* bias, int act, float* y, const float* mask = nullptr) {
   const int T = KH * KW;
   int TW, TH, TN;
   pick_tile(OH, OW, TC_BM, TW, TH, TN);
@@ -818,7 +829,7 @@ int conv_igemm_fprop(okl_ctx* ctx, const float* x, int N, int H, int W, int Cc, 
   p.M = N * OH * OW; p.N = Oc; p.K = T * Cc;
   p.tiles_m = (int)tiles_m; p.tiles_n = (Oc + bn - 1) / bn; p.splits = 1;
   p.kb_total = T * (Cc / 32); p.kb_per_split = p.kb_total;
-  p.D = y; p.ldd = Oc; p.bias = bias; p.act = act;
+  p.D = y; p.ldd = Oc; p.bias = bias; p.act = act; p.mask = mask;
   p.cv_TW = TW; p.cv_TH = TH; p.cv_TN = TN; p.cv_tw_sh = ilog2(TW); p.cv_th_sh = ilog2(TH);
   p.cv_tiles_w = tiles_w; p.cv_tiles_h = tiles_h; p.cv_OH = OH; p.cv_OW = OW; p.cv_NB = N;
   p.cv_C = Cc; p.cv_cblocks = Cc / 32; p.cv_kw = KW; p.cv_ph = ph; p.cv_pw = pw;
@@ -865,7 +876,7 @@ int okl_tc_conv_fprop(okl_ctx* ctx, const okl_conv_desc* d, const float* x, cons
   return conv_igemm_fprop(ctx, x, s.N, s.H, s.W, s.C, (const float*)w2.p, s.O, s.KH, s.KW, s.PH, s.PW, s.OH, s.OW, b, d->act, y);
 }
 
-int okl_tc_conv_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const float* g, const float* W, float* dx) {
+int okl_tc_conv_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const float* g, const float* W, float* dx, const float* mask) {
   // dx = conv(g, flip(W)^T) with padding k-1-p: the same implicit GEMM with the roles of C and O exchanged
   ConvShape s;
   conv_shape(d, s);
@@ -876,7 +887,7 @@ int okl_tc_conv_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const float* g, cons
   flip_filters_kernel<<<okl_grid_1d(ctx, (size_t)s.O * T * s.C, 256), 256, 0, ctx->stream>>>(W, (float*)wf.p, s.O, s.C, T);
   OKL_LAUNCHED(ctx, "flip_filters");
   return conv_igemm_fprop(ctx, g, s.N, s.OH, s.OW, s.O, (const float*)wf.p, s.C, s.KH, s.KW, s.KH - 1 - s.PH, s.KW - 1 - s.PW, s.H, s.W,
-                          nullptr, OKL_ACT_NONE, dx);
+                          nullptr, OKL_ACT_NONE, dx, mask);
 }
 
 int okl_tc_conv_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const float* x, const float* g, float* dW) {
@@ -979,15 +990,15 @@ int okl_tc_dense_fwd(okl_ctx* ctx, const float* X, const float* W, const float* 
   return okl_tc_gemm_raw(ctx, 0, 0, 1, M, N, K, X, K, W, N, Y, N, b, act, nullptr);
 }
 
-int okl_tc_dense_dx(okl_ctx* ctx, const float* G, const float* W, float* dX, int M, int K, int N) {
+int okl_tc_dense_dx(okl_ctx* ctx, const float* G, const float* W, float* dX, int M, int K, int N, const float* mask) {
   // dX[M,K] = G[M,N] . W^T : reduction over N; B'(n'=kin, k'=nout) = W[kin][nout] is K-major as stored
   if (ctx->precision == OKL_BF16) {
     Bf16Scratch sc;
     int s = bf16_operands(ctx, G, (size_t)M * N, W, (size_t)K * N, sc);
     if (s != OKL_OK) return s;
-    return okl_tc_gemm_raw(ctx, 1, 0, 0, M, K, N, sc.a, N, sc.b, N, dX, K, nullptr, OKL_ACT_NONE, nullptr);
+    return okl_tc_gemm_raw(ctx, 1, 0, 0, M, K, N, sc.a, N, sc.b, N, dX, K, nullptr, OKL_ACT_NONE, nullptr, mask);
   }
-  return okl_tc_gemm_raw(ctx, 0, 0, 0, M, K, N, G, N, W, N, dX, K, nullptr, OKL_ACT_NONE, nullptr);
+  return okl_tc_gemm_raw(ctx, 0, 0, 0, M, K, N, G, N, W, N, dX, K, nullptr, OKL_ACT_NONE, nullptr, mask);
 }
 
 int okl_tc_dense_dw(okl_ctx* ctx, const float* X, const float* G, float* dW, int M, int K, int N) {

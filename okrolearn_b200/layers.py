@@ -126,6 +126,7 @@ class _ParamBucket:
 
 
 class _ParamLayer:
+    _dx_relu_mask = False          # NeuralNetwork planner: a fused ReLU precedes this layer; its backward is applied in our dX epilogue
     _defer_update = False          # set by NeuralNetwork when updates are applied after the whole backward (DP overlap)
     _fused_act = ACT_NONE          # set by NeuralNetwork's planner: activation fused into this layer's epilogue
 
@@ -200,8 +201,9 @@ class DenseLayer(_ParamLayer):
         need_dx = getattr(self, "_need_dx", True)
         dX = Tensor._empty((M, K), np.float64) if need_dx else None
         b = self._bucket
-        check(lib.okl_dense_bwd(ctx.h, self.inputs._dptr(NCX), b.ptr(0), dL_dout._dptr(NCX), dX._ptr_raw() if need_dx else None,
-                                b.grad_ptr(0), b.grad_ptr(1), M, K, N))
+        xp = self.inputs._dptr(NCX)
+        check(lib.okl_dense_bwd(ctx.h, xp, b.ptr(0), dL_dout._dptr(NCX), dX._ptr_raw() if need_dx else None,
+                                b.grad_ptr(0), b.grad_ptr(1), M, K, N, xp if (need_dx and self._dx_relu_mask) else None))
         b.step(lr, self._defer_update)
         return dX
 
@@ -280,7 +282,8 @@ class _ConvBase(_ParamLayer):
         dX = None
         if getattr(self, "_need_dx", True):
             dX = Tensor._empty(x.shape, self._dx_dtype(x), layout=xl)
-            check(lib.okl_conv_dgrad(ctx.h, C.byref(d), g, b.ptr(0), dX._ptr_raw()))      # uses the pre-update filters
+            check(lib.okl_conv_dgrad(ctx.h, C.byref(d), g, b.ptr(0), dX._ptr_raw(),        # uses the pre-update filters
+                                     x._dptr(xl) if self._dx_relu_mask else None))
         b.step(lr, self._defer_update)
         return dX
 

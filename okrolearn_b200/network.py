@@ -197,7 +197,7 @@ class NeuralNetwork:
         ls = self.layers
         for l in ls:
             if isinstance(l, _ParamLayer):
-                l._fused_act, l._need_dx = ACT_NONE, True
+                l._fused_act, l._need_dx, l._dx_relu_mask = ACT_NONE, True, False
                 l._defer_update = fast or get_ctx().nranks > 1
             if isinstance(l, _Activation):
                 l._fused_into_prev = False
@@ -223,6 +223,10 @@ class NeuralNetwork:
             for a, b in zip(ls, ls[1:]):
                 if isinstance(a, _ParamLayer) and isinstance(b, (ReLUActivationLayer, SigmoidActivationLayer)):
                     a._fused_act, b._fused_into_prev = b._act, True
+            for a, r, b in zip(ls, ls[1:], ls[2:]):      # Param(+ReLU fused) -> Param: relu' applied in the second layer's dX epilogue
+                if (isinstance(a, _ParamLayer) and isinstance(r, ReLUActivationLayer) and r._fused_into_prev and
+                        isinstance(b, _ParamLayer)):
+                    r._bwd_fused_into_next, b._dx_relu_mask = True, True
             for a, b in zip(ls, ls[1:]):                 # ReLU -> MaxPool: relu' applied inside the pooling backward
                 if isinstance(a, ReLUActivationLayer) and isinstance(b, MaxPoolingLayer):
                     a._bwd_fused_into_next, b._fused_relu_bwd = True, True
@@ -326,37 +330,45 @@ class NeuralNetwork:
         t_row = _numel(t_shape)
         stream = bool(self.stream_inputs)
 
-        # ---- dataset placement
+        # ---- dataset placement.  The dataset is never physically shuffled: every step gathers the rows of its batch through
+        # the epoch's permutation (device index vector) into the step's static input buffer - from HBM, or, with
+        # `stream_inputs`, straight from page-locked host memory over PCIe (the host->device copy is then inside the step).
+        # The reordering of the caller's tensors (okl.py:2959-2960) is applied lazily when `.data` is next read.
+        pend_x, pend_t = getattr(inputs, "_lazy_perm", None), getattr(targets, "_lazy_perm", None)
+        if pend_x is not None and pend_t is not None and np.array_equal(pend_x, pend_t):
+            perm_total = pend_x.copy()                                   # storage order still predates an earlier train()
+            inputs._lazy_perm = targets._lazy_perm = None
+        else:
+            if pend_x is not None:
+                _ = inputs.data
+            if pend_t is not None:
+                _ = targets.data
+            perm_total = np.arange(num_samples)
+        keep = []
         if stream:
-            # the dataset stays in page-locked host memory; every step gathers its (shuffled) rows straight from there over
-            # PCIe/NVLink-C2C into the step's static input buffer (the host->device copy is inside the step)
-            if getattr(inputs, "_lazy_perm", None) is not None:
-                _ = inputs.data                                          # apply a reordering left pending by an earlier train()
-            hx = inputs._host if (inputs._host is not None and not inputs._dev_valid) else inputs.data
-            hx = np.asarray(hx)
+            hx = np.asarray(inputs._host if (inputs._host is not None and not inputs._dev_valid) else inputs.data)
             if hx.dtype == np.float32 and pinned_base(hx) is not None:
                 pin_x = hx.reshape(num_samples, row_elems)               # zero-copy: already pinned
             else:
                 pin_x = pinned_empty((num_samples, row_elems), np.float32)
                 np.copyto(pin_x, np.asarray(hx, dtype=np.float32).reshape(num_samples, row_elems))
-            ht = np.asarray(targets.data).reshape(num_samples, t_row)
+            ht = np.asarray(targets._host if (targets._host is not None and not targets._dev_valid) else targets.data)
             pin_t = pinned_empty((num_samples, t_row), np.int32 if is_ce else np.float32)
-            np.copyto(pin_t, ht.astype(pin_t.dtype))
-            idx_dev = _DevBuf(ctx, max(num_samples, 1) * 4)
-            perm_total = np.arange(num_samples)
+            np.copyto(pin_t, ht.reshape(num_samples, t_row).astype(pin_t.dtype))
+            x_src, t_src = pin_x.ctypes.data, pin_t.ctypes.data
+            keep += [pin_x, pin_t]
         else:
-            x_dev = _DevBuf(ctx, max(inputs.size, 1) * 4)
-            check(lib.okl_d2d(ctx.h, x_dev.ptr, inputs._dptr(NCX), inputs.size * 4))
-            x_alt = _DevBuf(ctx, max(inputs.size, 1) * 4)
-            t_dev = _DevBuf(ctx, max(targets.size, 1) * 4)
-            t_alt = _DevBuf(ctx, max(targets.size, 1) * 4)
+            x_src = inputs._dptr(NCX)
             if is_ce:
-                th = np.ascontiguousarray(np.asarray(targets.data).reshape(-1).astype(np.int64))
-                check(lib.okl_h2d_i32(ctx.h, t_dev.ptr, th.ctypes.data, th.size, _lib.I64))
+                t_buf = _DevBuf(ctx, max(num_samples, 1) * 4)
+                th = np.ascontiguousarray(np.asarray(targets._host if targets._host is not None else targets.data).reshape(-1)
+                                          .astype(np.int64))
+                check(lib.okl_h2d_i32(ctx.h, t_buf.ptr, th.ctypes.data, th.size, _lib.I64))
+                t_src = t_buf.ptr
+                keep.append(t_buf)
             else:
-                check(lib.okl_d2d(ctx.h, t_dev.ptr, targets._dptr(NCX), targets.size * 4))
-            idx_dev = _DevBuf(ctx, max(num_samples, 1) * 4)
-            perm_total = np.arange(num_samples)
+                t_src = targets._dptr(NCX)
+        idx_dev = _DevBuf(ctx, max(num_samples, 1) * 4)
 
         # ---- per-(batch shape, loss) step state: static input buffers + the captured graph
         skey = (batch_size, sample_shape, t_shape, id(loss_function), tuple(id(l) for l in self.layers), fast,
@@ -402,30 +414,17 @@ class NeuralNetwork:
             # shuffle (same host RNG call as okl.py:2957-2958)
             indices = np.arange(num_samples)
             np.random.shuffle(indices)
-            if stream:
-                perm_total = perm_total[indices]
-                i32 = np.ascontiguousarray(perm_total.astype(np.int32))
-                check(lib.okl_h2d_i32(ctx.h, idx_dev.ptr, i32.ctypes.data, i32.size, _lib.I32))
-            else:
-                i32 = np.ascontiguousarray(indices.astype(np.int32))
-                check(lib.okl_h2d_i32(ctx.h, idx_dev.ptr, i32.ctypes.data, i32.size, _lib.I32))
-                check(lib.okl_gather_rows(ctx.h, x_alt.ptr, x_dev.ptr, idx_dev.ptr, num_samples, row_elems))
-                check(lib.okl_gather_rows(ctx.h, t_alt.ptr, t_dev.ptr, idx_dev.ptr, num_samples, t_row))
-                x_dev, x_alt = x_alt, x_dev
-                t_dev, t_alt = t_alt, t_dev
-                perm_total = perm_total[indices]
+            perm_total = perm_total[indices]
+            i32 = np.ascontiguousarray(perm_total.astype(np.int32))
+            check(lib.okl_h2d_i32(ctx.h, idx_dev.ptr, i32.ctypes.data, i32.size, _lib.I32))
 
             for batch in range(num_batches):
                 b0 = batch * batch_size
                 b1 = min(b0 + batch_size, num_samples)
                 rows = b1 - b0
                 full = rows == batch_size
-                if stream:
-                    check(lib.okl_gather_rows(ctx.h, st.xin._ptr_raw(), pin_x.ctypes.data, idx_dev.ptr + b0 * 4, rows, row_elems))
-                    check(lib.okl_gather_rows(ctx.h, st.tin.ptr, pin_t.ctypes.data, idx_dev.ptr + b0 * 4, rows, t_row))
-                else:
-                    check(lib.okl_d2d(ctx.h, st.xin._ptr_raw(), x_dev.ptr + b0 * row_elems * 4, rows * row_elems * 4))
-                    check(lib.okl_d2d(ctx.h, st.tin.ptr, t_dev.ptr + b0 * t_row * 4, rows * t_row * 4))
+                check(lib.okl_gather_rows(ctx.h, st.xin._ptr_raw(), x_src, idx_dev.ptr + b0 * 4, rows, row_elems))
+                check(lib.okl_gather_rows(ctx.h, st.tin.ptr, t_src, idx_dev.ptr + b0 * 4, rows, t_row))
                 if graph_ok and full and st.graph is not None:
                     ctx.graph_launch(st.graph.handle)
                     loss = st.graph.loss
@@ -471,18 +470,11 @@ class NeuralNetwork:
             self._run_hooks('post_epoch', epoch, epochs, avg_loss)
 
         # the reference reorders the caller's tensors in place every epoch (okl.py:2959-2960)
-        if epochs and stream:
+        if epochs:
             ctx.sync()
-            inputs._lazy_perm = perm_total if getattr(inputs, "_lazy_perm", None) is None else inputs._lazy_perm[perm_total]
-            targets._lazy_perm = perm_total if getattr(targets, "_lazy_perm", None) is None else targets._lazy_perm[perm_total]
-        elif epochs:
-            ctx.sync()
-            if inputs._bound:
-                check(lib.okl_d2d(ctx.h, inputs._ptr_raw(), x_dev.ptr, inputs.size * 4))
-            else:
-                inputs._buf, inputs._off, inputs._layout = x_dev, 0, NCX
-            inputs._touch()
-            targets.data = np.asarray(targets.data)[perm_total]
+            inputs._lazy_perm = perm_total
+            targets._lazy_perm = perm_total.copy()
+        del keep
         if not custom_loss:
             loss_function._loss_accum = None
         return losses
