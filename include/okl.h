@@ -125,6 +125,15 @@ int okl_conv_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* g, const vo
 /* dW = x (*) g ; db = sum_{n,pos} g            okl.py:729-735 / 865-866,870 / 1013-1016,991 (+ repairs R1,R2); db may be NULL */
 int okl_conv_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* g, void* dW, void* db);
 
+/* Fused first block Conv2D(3x3, stride 1) -> ReLU -> MaxPool(2,2) for tiny input channel counts (C = 1 or 3): the un-pooled
+ * activation is never written.  fwd writes the pooled maxima (N,O,PH,PW) and a 4-bit mask per pooled element (which of the four
+ * window positions attain the maximum and are > 0 = the combined backward of okl.py:107 and okl.py:1757-1766 with the reference's
+ * tie rule); wgrad consumes the POOLED gradient and that mask and yields dW (O,C,3,3) and db (O) (okl.py:865-866, 870). */
+int okl_conv_relu_pool_supported(const okl_conv_desc* d);
+int okl_conv_relu_pool_fwd(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* W, const void* b, void* pooled, void* mask_u8);
+int okl_conv_relu_pool_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* pooled_g, const void* mask_u8, void* dW,
+                             void* db);
+
 /* ------------------------------------------------------------------ activations (okl.py:94-120, 500-522, 2070-2108) */
 int okl_act_fwd(okl_ctx* ctx, int act, const void* x, void* y, size_t n);
 /* relu: ref = x (g * (x>0), okl.py:107) [y works too]; sigmoid: ref = y (okl.py:514); tanh: ref = x (okl.py:2092) */

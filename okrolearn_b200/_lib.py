@@ -69,6 +69,9 @@ SIGNATURES = {
     "okl_conv_fprop": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp]),
     "okl_conv_dgrad": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp]),
     "okl_conv_wgrad": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp]),
+    "okl_conv_relu_pool_supported": (_i, [_P(ConvDesc)]),
+    "okl_conv_relu_pool_fwd": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
+    "okl_conv_relu_pool_wgrad": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "okl_act_fwd": (_i, [_vp, _i, _vp, _vp, _sz]),
     "okl_act_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _sz]),
     "okl_binary": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _sz]),

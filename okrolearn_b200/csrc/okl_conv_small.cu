@@ -394,3 +394,243 @@ int okl_conv_small_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const float* x, c
   OKL_LAUNCHED(ctx, "conv_smallk_wgrad_reduce");
   return OKL_OK;
 }
+
+// ================================================================================================ Conv -> ReLU -> MaxPool(2,2) block
+// The first block of an MNIST/CIFAR-style CNN is bound by the traffic of the un-pooled activation tensor (22 MB per step at
+// batch 256 for the MNIST CNN: written by the conv, read by the pool, read + written by the pool backward, read by wgrad).
+// Fused, that tensor never exists:
+//   forward : each thread computes the 2x2 group of conv outputs that feed ONE pooled position (bias + ReLU applied), writes the
+//             pooled maximum and a 4-bit mask of which of the four positions attain it (and are > 0).  The mask IS the combined
+//             backward of ReLU and max-pool, with the reference's tie rule (every maximum receives the gradient, okl.py:1757-1766).
+//   backward: dW / db accumulate only over the positions the mask selects (a quarter of the conv outputs), reading the pooled
+//             gradient, the mask and the (4 x 4) input windows - never the un-pooled gradient.
+namespace {
+
+template <int KH, int KW, bool PAD>
+__global__ void __launch_bounds__(256, 2) conv_relu_pool2_fwd(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
+                                                             float* __restrict__ yp, unsigned char* __restrict__ mask, const ConvGeom g,
+                                                             const int K, const int Opad, const int PH, const int PW, const FastDiv dPW,
+                                                             const FastDiv dPH, const int total) {
+  constexpr int OT = 16, WH = KH + 1, WW = KW + 1;
+  extern __shared__ __align__(16) float sm[];
+  float* Ws = sm;                 // [K][Opad]
+  float* bs = sm + K * Opad;      // [Opad]
+  for (int i = threadIdx.x; i < K * Opad; i += blockDim.x) {
+    int k = i / Opad, o = i - k * Opad;
+    Ws[i] = o < g.O ? __ldg(W + (size_t)o * K + k) : 0.f;
+  }
+  for (int i = threadIdx.x; i < Opad; i += blockDim.x) bs[i] = (b && i < g.O) ? __ldg(b + i) : 0.f;
+  __syncthreads();
+  const long long plane = (long long)PH * PW;
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
+    unsigned t, pw, ph;
+    dPW.divmod((unsigned)it, t, pw); dPH.divmod(t, t, ph);
+    const int n = (int)t;
+    const int ih0 = 2 * (int)ph - g.P[1], iw0 = 2 * (int)pw - g.P[2];
+    const float* xn = x + n * g.xs[0];
+    const long long obase = (long long)n * g.O * plane + ph * PW + pw;
+    for (int oc = 0; oc < Opad; oc += OT) {
+      float a[4][OT];
+#pragma unroll
+      for (int j = 0; j < OT; j++) { const float bv = bs[oc + j]; a[0][j] = bv; a[1][j] = bv; a[2][j] = bv; a[3][j] = bv; }
+      for (int c = 0; c < g.C; c++) {
+        const float* xc = xn + c * g.xs[1];
+        float win[WH][WW];
+#pragma unroll
+        for (int r = 0; r < WH; r++)
+#pragma unroll
+          for (int q = 0; q < WW; q++) {
+            const int ih = ih0 + r, iw = iw0 + q;
+            const bool ok = !PAD || ((unsigned)ih < (unsigned)g.I[1] && (unsigned)iw < (unsigned)g.I[2]);
+            win[r][q] = ok ? __ldg(xc + ih * g.xs[3] + iw) : 0.f;
+          }
+#pragma unroll
+        for (int th = 0; th < KH; th++)
+#pragma unroll
+          for (int tw = 0; tw < KW; tw++) {
+            const float4* wr = reinterpret_cast<const float4*>(Ws + ((c * KH + th) * KW + tw) * Opad + oc);
+            const float x00 = win[th][tw], x01 = win[th][tw + 1], x10 = win[th + 1][tw], x11 = win[th + 1][tw + 1];
+#pragma unroll
+            for (int q = 0; q < OT / 4; q++) {
+              const float4 w4 = wr[q];
+              const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                a[0][4 * q + e] = fmaf(x00, wv[e], a[0][4 * q + e]);
+                a[1][4 * q + e] = fmaf(x01, wv[e], a[1][4 * q + e]);
+                a[2][4 * q + e] = fmaf(x10, wv[e], a[2][4 * q + e]);
+                a[3][4 * q + e] = fmaf(x11, wv[e], a[3][4 * q + e]);
+              }
+            }
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < OT; j++) {
+        if (oc + j < g.O) {
+          const float v0 = fmaxf(a[0][j], 0.f), v1 = fmaxf(a[1][j], 0.f), v2 = fmaxf(a[2][j], 0.f), v3 = fmaxf(a[3][j], 0.f);
+          const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+          unsigned mk = 0;
+          if (m > 0.f) mk = (v0 == m ? 1u : 0u) | (v1 == m ? 2u : 0u) | (v2 == m ? 4u : 0u) | (v3 == m ? 8u : 0u);
+          const long long off = obase + (long long)(oc + j) * plane;
+          yp[off] = m;
+          mask[off] = (unsigned char)mk;
+        }
+      }
+    }
+  }
+}
+
+// NW = C * (KH+1) * (KW+1) window rows staged per pooled position; KT >= C*KH*KW + 1
+template <int KH, int KW, int CMAX, int KT, bool PAD>
+__global__ void __launch_bounds__(256, 2)
+conv_relu_pool2_wgrad(const float* __restrict__ x, const float* __restrict__ gp, const unsigned char* __restrict__ mask,
+                      float* __restrict__ partial, const ConvGeom g, const int K, const int PH, const int PW, const FastDiv dPW,
+                      const FastDiv dPH, const int Mpool, const int ntiles) {
+  constexpr int WH = KH + 1, WW = KW + 1, NW = CMAX * WH * WW;
+  __shared__ __align__(16) float gs[WG_OB][WG_PT];
+  __shared__ __align__(16) float xw[NW][WG_PT];
+  __shared__ unsigned char ms[WG_OB][WG_PT];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int o_base = blockIdx.y * WG_OB;
+  const int p = tid & (WG_PT - 1), half = tid >> 7;
+  const long long plane = (long long)PH * PW;
+  float acc[4][KT];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int k = 0; k < KT; k++) acc[i][k] = 0.f;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int m = tile * WG_PT + p;
+    const bool ok = m < Mpool;
+    unsigned t, pw, ph;
+    dPW.divmod((unsigned)m, t, pw); dPH.divmod(t, t, ph);
+    __syncthreads();
+    {
+      const long long gb = (long long)t * g.O * plane + ph * PW + pw;
+#pragma unroll 4
+      for (int o = half; o < WG_OB; o += 2) {
+        const bool v = ok && o_base + o < g.O;
+        gs[o][p] = v ? __ldg(gp + gb + (long long)(o_base + o) * plane) : 0.f;
+        ms[o][p] = v ? __ldg(mask + gb + (long long)(o_base + o) * plane) : (unsigned char)0;
+      }
+      const int ih0 = 2 * (int)ph - g.P[1], iw0 = 2 * (int)pw - g.P[2];
+      const float* xn = x + t * g.xs[0];
+      for (int r = half; r < g.C * WH * WW; r += 2) {
+        const int c = r / (WH * WW), rr = r - c * (WH * WW);
+        const int ih = ih0 + rr / WW, iw = iw0 + rr % WW;
+        const bool in = ok && (!PAD || ((unsigned)ih < (unsigned)g.I[1] && (unsigned)iw < (unsigned)g.I[2]));
+        xw[r][p] = in ? __ldg(xn + c * g.xs[1] + ih * g.xs[3] + iw) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int o = warp * 4 + i;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int pp = lane * 4 + j;
+        const float gv = gs[o][pp];
+        unsigned mk = ms[o][pp];
+        while (mk) {                                   // one iteration per maximum of the window (almost always exactly one)
+          const int bit = __ffs(mk) - 1;
+          mk &= mk - 1;
+          const float* wbase = &xw[(bit >> 1) * WW + (bit & 1)][pp];
+#pragma unroll
+          for (int c = 0; c < CMAX; c++) {
+#pragma unroll
+            for (int th = 0; th < KH; th++)
+#pragma unroll
+              for (int tw = 0; tw < KW; tw++) {
+                const int k = (c * KH + th) * KW + tw;
+                if (k < KT) acc[i][k] = fmaf(gv, wbase[(c * WH * WW + th * WW + tw) * WG_PT], acc[i][k]);
+              }
+          }
+          // bias gradient: the all-ones tap lives in column K (= C*KH*KW, a compile-time constant per instantiation)
+          acc[i][CMAX * KH * KW] += gv;
+        }
+      }
+    }
+  }
+  float* out = partial + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * WG_OB + warp * 4) * KT;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int k = 0; k < KT; k++) {
+      float v = acc[i][k];
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+      if (lane == 0) out[i * KT + k] = v;
+    }
+}
+
+}  // namespace
+
+extern "C" int okl_conv_relu_pool_supported(const okl_conv_desc* d) {
+  if (!d || d->nd != 2 || d->x_layout != OKL_NCX || d->y_layout != OKL_NCX) return 0;
+  if (d->k[0] != 3 || d->k[1] != 3 || d->s[0] != 1 || d->s[1] != 1) return 0;
+  if (d->C != 1 && d->C != 3) return 0;
+  const int oh = d->in[0] + 2 * d->p[0] - 2, ow = d->in[1] + 2 * d->p[1] - 2;
+  if (oh < 2 || ow < 2) return 0;
+  const int Opad = (d->O + 15) / 16 * 16;
+  return (long long)d->C * 9 * Opad + Opad <= 11000 ? 1 : 0;
+}
+
+extern "C" int okl_conv_relu_pool_fwd(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* W, const void* b, void* pooled,
+                                      void* mask) {
+  OKL_REQUIRE(ctx && d && x && W && pooled && mask, "NULL argument");
+  OKL_REQUIRE(okl_conv_relu_pool_supported(d), "okl_conv_relu_pool_fwd: unsupported shape");
+  ConvGeom g;
+  int s = make_geom(d, g);
+  if (s != OKL_OK) return s;
+  const int K = g.C * 9, Opad = (g.O + 15) / 16 * 16;
+  const int PH = g.Oe[1] / 2, PW = g.Oe[2] / 2;
+  const int total = g.N * PH * PW;
+  if (total == 0) return OKL_OK;
+  const size_t smem = (size_t)(K * Opad + Opad) * sizeof(float);
+  int grid = (total + 255) / 256;
+  const int cap = ctx->sm_count * 16;
+  if (grid > cap) grid = cap;
+  const bool pad = g.P[1] || g.P[2];
+  if (pad) conv_relu_pool2_fwd<3, 3, true><<<grid, 256, smem, ctx->stream>>>((const float*)x, (const float*)W, (const float*)b, (float*)pooled,
+                                                                           (unsigned char*)mask, g, K, Opad, PH, PW, FastDiv(PW), FastDiv(PH), total);
+  else conv_relu_pool2_fwd<3, 3, false><<<grid, 256, smem, ctx->stream>>>((const float*)x, (const float*)W, (const float*)b, (float*)pooled,
+                                                                          (unsigned char*)mask, g, K, Opad, PH, PW, FastDiv(PW), FastDiv(PH), total);
+  OKL_LAUNCHED(ctx, "conv_relu_pool2_fwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_conv_relu_pool_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* pooled_g, const void* mask,
+                                        void* dW, void* db) {
+  OKL_REQUIRE(ctx && d && x && pooled_g && mask, "NULL argument");
+  OKL_REQUIRE(okl_conv_relu_pool_supported(d), "okl_conv_relu_pool_wgrad: unsupported shape");
+  ConvGeom g;
+  int s = make_geom(d, g);
+  if (s != OKL_OK) return s;
+  const int K = g.C * 9;
+  const int KT = K + 1 <= 12 ? 12 : 28;
+  const int PH = g.Oe[1] / 2, PW = g.Oe[2] / 2;
+  const int Mpool = g.N * PH * PW;
+  const int ntiles = (Mpool + WG_PT - 1) / WG_PT;
+  const int gy_ = (g.O + WG_OB - 1) / WG_OB;
+  int gx = (2 * ctx->sm_count + gy_ - 1) / gy_;
+  if (gx > ntiles) gx = ntiles;
+  if (gx < 1) gx = 1;
+  s = okl_ensure_workspace(ctx, (size_t)gx * gy_ * WG_OB * KT * sizeof(float));
+  if (s != OKL_OK) return s;
+  float* partial = (float*)ctx->workspace;
+  dim3 grid(gx, gy_);
+  const bool pad = g.P[1] || g.P[2];
+#define OKL_LAUNCH_CRPW(C_, KT_, PAD_)                                                                                               \
+  conv_relu_pool2_wgrad<3, 3, C_, KT_, PAD_><<<grid, 256, 0, ctx->stream>>>((const float*)x, (const float*)pooled_g,                \
+                                                                            (const unsigned char*)mask, partial, g, K, PH, PW,      \
+                                                                            FastDiv(PW), FastDiv(PH), Mpool, ntiles)
+  if (g.C == 1) { if (pad) OKL_LAUNCH_CRPW(1, 12, true); else OKL_LAUNCH_CRPW(1, 12, false); }
+  else { if (pad) OKL_LAUNCH_CRPW(3, 28, true); else OKL_LAUNCH_CRPW(3, 28, false); }
+#undef OKL_LAUNCH_CRPW
+  OKL_LAUNCHED(ctx, "conv_relu_pool2_wgrad");
+  const int total = g.O * (K + 1);
+  conv_smallk_wgrad_reduce<<<(total * 32 + 255) / 256, 256, 0, ctx->stream>>>(partial, (float*)dW, (float*)db, g.O, K, KT, gx);
+  OKL_LAUNCHED(ctx, "conv_smallk_wgrad_reduce");
+  return OKL_OK;
+}

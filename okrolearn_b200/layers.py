@@ -250,11 +250,55 @@ class _ConvBase(_ParamLayer):
         return (self._nd <= 2 and all(s == 1 for s in self._s) and self.in_channels % 32 == 0 and self.out_channels % 32 == 0 and
                 all(p <= k - 1 for p, k in zip(self._p, self._k)))
 
+    _fused_pool = None             # NeuralNetwork planner: (relu, pool) layers fused into this conv (first block, no dX needed)
+
+    def _forward_fused_pool(self, inputs):
+        """Conv -> ReLU -> MaxPool(2,2) in one kernel: returns the POOLED tensor; the un-pooled activation is a lazy placeholder."""
+        ctx = get_ctx()
+        d, oe = self._desc(inputs.shape, NCX, NCX, ACT_RELU)
+        N, O = inputs.shape[0], self.out_channels
+        PH, PW = oe[0] // 2, oe[1] // 2
+        pooled = Tensor._empty((N, O, PH, PW), np.float64)
+        mask = _DevBuf(ctx, max(N * O * PH * PW, 1))
+        check(lib.okl_conv_relu_pool_fwd(ctx.h, C.byref(d), inputs._dptr(NCX), self._bucket.ptr(0), self._bucket.ptr(1),
+                                         pooled._ptr_raw(), mask.ptr))
+        self._pool_mask, self._fwd_layouts = mask, (NCX, NCX)
+        full = Tensor._view(None, 0, (N, O) + oe, self._np_dtype, bound=False)      # never written by the fused kernel
+        full._dev_valid = False
+        layer = self
+
+        def recompute(t):
+            dd, _ = layer._desc(layer.inputs.shape, NCX, NCX, ACT_RELU)
+            t._buf, t._off = _DevBuf(get_ctx(), t.size * 4), 0
+            check(lib.okl_conv_fprop(get_ctx().h, C.byref(dd), layer.inputs._dptr(NCX), layer._bucket.ptr(0), layer._bucket.ptr(1),
+                                     t._ptr_raw()))
+            t._touch()
+        full._lazy_fn = recompute
+        relu, pool = self._fused_pool
+        relu.inputs = relu.outputs = full
+        pool.inputs, pool.output = full, pooled
+        pooled._fused_from = self
+        return pooled, full
+
+    def _backward_fused_pool(self, pooled_grad, lr):
+        ctx = get_ctx()
+        x = self.inputs
+        d, oe = self._desc(x.shape, NCX, NCX)
+        b = self._bucket
+        check(lib.okl_conv_relu_pool_wgrad(ctx.h, C.byref(d), x._dptr(NCX), _as_tensor(pooled_grad)._dptr(NCX), self._pool_mask.ptr,
+                                           b.grad_ptr(0), b.grad_ptr(1)))
+        b.step(lr, self._defer_update)
+        return None
+
     def _forward(self, inputs):
         inputs = _as_tensor(inputs)
         ctx = get_ctx()
         self._bucket.materialize()
         self.inputs = inputs
+        if self._fused_pool is not None:
+            pooled, full = self._forward_fused_pool(inputs)
+            self._fused_out = pooled
+            return full
         if ctx.precision != _lib.FP32 and self._tc_eligible():
             xl = yl = NXC
         else:
@@ -269,6 +313,8 @@ class _ConvBase(_ParamLayer):
         return out
 
     def _backward(self, dL_dout, lr):
+        if self._fused_pool is not None:
+            return self._backward_fused_pool(dL_dout, lr)
         dL_dout = _as_tensor(dL_dout)
         ctx = get_ctx()
         x = self.inputs
@@ -337,7 +383,8 @@ class Conv2DLayer(_ConvBase):
 
     def forward(self, inputs: Tensor):
         self.outputs = self._forward(inputs)
-        return self.outputs
+        # fused first block: what flows on to the (pass-through) ReLU and MaxPool layers is already the pooled tensor
+        return self._fused_out if self._fused_pool is not None else self.outputs
 
     def forward_normal(self, inputs: Tensor):
         return self.forward(inputs)
@@ -396,8 +443,12 @@ class _Activation:
     _fused_into_prev = False     # NeuralNetwork planner: the producing layer's epilogue already applied this activation
     _bwd_fused_into_next = False # NeuralNetwork planner: the following pooling layer's backward already applied relu'
 
+    _in_fused_block = False       # NeuralNetwork planner: part of a fused Conv->ReLU->MaxPool block (pure pass-through)
+
     def _fwd(self, inputs):
         inputs = _as_tensor(inputs)
+        if self._in_fused_block:
+            return inputs                      # .inputs / .outputs were set by the conv layer (lazy un-pooled activation)
         self.inputs = inputs
         if self._fused_into_prev:
             return inputs                      # the tensor already holds act(x); relu backward uses y > 0 <=> x > 0
@@ -438,6 +489,8 @@ class ReLUActivationLayer(_Activation):
         return self.outputs
 
     def backward(self, dL_dout: Tensor, lr: float):
+        if self._in_fused_block:
+            return dL_dout
         dx = _as_tensor(dL_dout) if self._bwd_fused_into_next else self._bwd(dL_dout, self.inputs)
         if not self._fused_into_prev:            # fused: `inputs` IS the post-activation tensor, no separate pre-activation
             _set_input_grad(self.inputs, dx)
@@ -518,7 +571,11 @@ class _Pool:
         self.pool_size = pool_size
         self.stride = stride
 
+    _in_fused_block = False      # NeuralNetwork planner: computed inside the preceding conv's fused kernel (pure pass-through)
+
     def forward(self, inputs):
+        if self._in_fused_block:
+            return inputs                      # already pooled; .inputs / .output were set by the conv layer
         inputs = _as_tensor(inputs)
         ctx = get_ctx()
         if inputs.ndim != 4:
@@ -537,6 +594,8 @@ class _Pool:
         return out
 
     def backward(self, dL_dout: Tensor, lr: float = None):
+        if self._in_fused_block:
+            return dL_dout                     # the conv layer consumes the pooled gradient directly
         dL_dout = _as_tensor(dL_dout)
         ctx = get_ctx()
         x = self.inputs

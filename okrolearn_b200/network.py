@@ -33,7 +33,7 @@ from . import _lib
 from ._lib import lib, check, get_ctx, NCX, ACT_NONE
 from .tensor import Tensor, _DevBuf, _numel, pinned_empty, pinned_base
 from .layers import (apply_pending_updates, _ParamLayer, _Activation, _Pool, ReLUActivationLayer, SigmoidActivationLayer, SoftmaxActivationLayer,
-                     MaxPoolingLayer, DenseLayer,
+                     MaxPoolingLayer, DenseLayer, Conv2DLayer,
                      _ConvBase)
 from .losses import CrossEntropyLoss, MSELoss, LossValue
 
@@ -80,6 +80,7 @@ class NeuralNetwork:
         self.use_graph = os.environ.get("OKL_GRAPH", "1") != "0"
         self.fuse_activations = os.environ.get("OKL_FUSE", "1") != "0"
         self.skip_input_grad = os.environ.get("OKL_SKIP_INPUT_GRAD", "1") != "0"
+        self.fuse_conv_pool = os.environ.get("OKL_FUSE_CONV_POOL", "1") != "0"
         self.stream_inputs = False          # keep the dataset on the host, copy each batch inside the step
         self.sync_loss_every_step = False   # read the loss back to the host after every step (end-to-end mode)
         self.last_step_losses = []
@@ -189,7 +190,7 @@ class NeuralNetwork:
                     ('pre_forward', 'post_forward', 'pre_backward', 'post_backward')))
 
     def _plan(self, fast: bool):
-        key = (fast, self.fuse_activations, self.skip_input_grad, tuple(id(l) for l in self.layers), get_ctx().nranks,
+        key = (fast, self.fuse_activations, self.skip_input_grad, self.fuse_conv_pool, tuple(id(l) for l in self.layers), get_ctx().nranks,
                get_ctx().precision)
         if key == self._plan_key:
             return
@@ -199,11 +200,15 @@ class NeuralNetwork:
             if isinstance(l, _ParamLayer):
                 l._fused_act, l._need_dx, l._dx_relu_mask = ACT_NONE, True, False
                 l._defer_update = fast or get_ctx().nranks > 1
+            if isinstance(l, _ConvBase):
+                l._fused_pool = None
             if isinstance(l, _Activation):
                 l._fused_into_prev = False
                 l._bwd_fused_into_next = False
+                l._in_fused_block = False
             if isinstance(l, _Pool):
                 l._fused_relu_bwd = False
+                l._in_fused_block = False
         # layout planning: a convolution that feeds (through activations / pooling) a tensor-core-eligible convolution writes
         # its output channels-last, so no permutation is needed between them
         tc_mode = get_ctx().precision != _lib.FP32
@@ -232,6 +237,16 @@ class NeuralNetwork:
                     a._bwd_fused_into_next, b._fused_relu_bwd = True, True
         if self.skip_input_grad and ls and isinstance(ls[0], _ParamLayer):
             ls[0]._need_dx = False
+        # first block Conv2D(3x3, s1) -> ReLU -> MaxPool(2,2) with no dX needed: one fused kernel each way, the un-pooled
+        # activation and its gradient are never materialised
+        if (self.fuse_activations and self.fuse_conv_pool and len(ls) >= 3 and isinstance(ls[0], Conv2DLayer) and
+                not ls[0]._need_dx and isinstance(ls[1], ReLUActivationLayer) and isinstance(ls[2], MaxPoolingLayer) and
+                int(ls[2].pool_size) == 2 and int(ls[2].stride) == 2 and ls[0]._k == (3, 3) and ls[0]._s == (1, 1) and
+                ls[0].in_channels in (1, 3) and ls[0].out_channels * ls[0].in_channels * 9 <= 10000):
+            ls[0]._fused_pool = (ls[1], ls[2])
+            ls[0]._fused_act = ACT_NONE
+            ls[1]._in_fused_block = ls[2]._in_fused_block = True
+            ls[1]._fused_into_prev = ls[1]._bwd_fused_into_next = ls[2]._fused_relu_bwd = False
 
     # ------------------------------------------------------------------ forward / backward (okl.py:2871-2914)
     def forward(self, inputs: 'Tensor'):

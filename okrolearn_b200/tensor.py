@@ -202,8 +202,17 @@ class Tensor:
         t.data = array
         return t
 
+    def _materialize(self):
+        """A tensor a fused kernel did not write (e.g. the un-pooled activation of a fused Conv->ReLU->MaxPool block) is
+        recomputed on first access."""
+        fn = getattr(self, "_lazy_fn", None)
+        if fn is not None:
+            self._lazy_fn = None
+            fn(self)
+
     @property
     def data(self):
+        self._materialize()
         perm = getattr(self, "_lazy_perm", None)
         if perm is not None:                 # train() reordered the caller's dataset (okl.py:2959-2960); applied on first read
             self._lazy_perm = None
@@ -274,6 +283,7 @@ class Tensor:
 
     def _dptr(self, layout=None):
         """Device pointer of an up-to-date fp32 copy, in ``layout`` (NCX/NXC) when given."""
+        self._materialize()
         if self._dev_valid and self._exposed_sig is not None and self._host is not None:
             if self._sig(self._host) != self._exposed_sig:      # the snapshot handed out by .data was mutated in place
                 self._dev_valid = False
