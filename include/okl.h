@@ -46,7 +46,8 @@ typedef enum {
 
 /* arithmetic mode of the GEMM-shaped kernels (north_star: 1e-5 rel in FP32, 2e-2 in TF32/BF16) */
 typedef enum { OKL_FP32 = 0, OKL_TF32 = 1, OKL_BF16 = 2 } okl_precision;
-typedef enum { OKL_ACT_NONE = 0, OKL_ACT_RELU = 1, OKL_ACT_SIGMOID = 2, OKL_ACT_TANH = 3 } okl_act;
+/* OKL_ACT_SOFTMAX: row softmax (okl.py:364-373) as the epilogue of okl_dense_fwd, for output widths <= 16 only */
+typedef enum { OKL_ACT_NONE = 0, OKL_ACT_RELU = 1, OKL_ACT_SIGMOID = 2, OKL_ACT_TANH = 3, OKL_ACT_SOFTMAX = 4 } okl_act;
 typedef enum { OKL_F32 = 0, OKL_F64 = 1, OKL_I64 = 2, OKL_I32 = 3, OKL_U8 = 4 } okl_dtype;
 typedef enum { OKL_NCX = 0, OKL_NXC = 1 } okl_layout;
 typedef enum { OKL_POOL_MAX = 0, OKL_POOL_AVG = 1 } okl_pool_kind;
@@ -182,6 +183,15 @@ int okl_graph_begin(okl_ctx* ctx);
 int okl_graph_end(okl_ctx* ctx, okl_graph** out);
 int okl_graph_launch(okl_ctx* ctx, okl_graph* g);
 int okl_graph_destroy(okl_graph* g);
+
+/* ------------------------------------------------------------------ auxiliary lanes (concurrent branches of one step)
+ * Weight / bias gradients are leaves of the backward chain: okl_aux_begin(lane) routes the following launches to an auxiliary
+ * stream (with its own scratch), ordered after what is already enqueued; okl_aux_end returns to the main lane while that work
+ * keeps running; okl_aux_join makes the main lane wait for all auxiliary work (done before the parameter update). */
+int okl_aux_mark(okl_ctx* ctx);      /* optional: the next okl_aux_begin forks from this point instead of from "now" */
+int okl_aux_begin(okl_ctx* ctx, int lane);
+int okl_aux_end(okl_ctx* ctx);
+int okl_aux_join(okl_ctx* ctx);
 
 /* ------------------------------------------------------------------ timing on the compute stream */
 int okl_timer_start(okl_ctx* ctx);

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libokl_b200.so")
 
 OKL_OK, OKL_ERR_INVALID, OKL_ERR_CUDA, OKL_ERR_NCCL, OKL_ERR_OOM, OKL_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 FP32, TF32, BF16 = 0, 1, 2
-ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_SOFTMAX = 0, 1, 2, 3, 4
 F32, F64, I64, I32, U8 = 0, 1, 2, 3, 4
 NCX, NXC = 0, 1
 POOL_MAX, POOL_AVG = 0, 1
@@ -91,6 +91,10 @@ SIGNATURES = {
     "okl_graph_end": (_i, [_vp, _P(_vp)]),
     "okl_graph_launch": (_i, [_vp, _vp]),
     "okl_graph_destroy": (_i, [_vp]),
+    "okl_aux_mark": (_i, [_vp]),
+    "okl_aux_begin": (_i, [_vp, _i]),
+    "okl_aux_end": (_i, [_vp]),
+    "okl_aux_join": (_i, [_vp]),
     "okl_timer_start": (_i, [_vp]),
     "okl_timer_stop": (_i, [_vp, _P(_f)]),
     "okl_flush_l2": (_i, [_vp]),

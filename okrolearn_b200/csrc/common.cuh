@@ -45,6 +45,22 @@ struct okl_ctx {
   int* tile_counters = nullptr;         // split-K arrival counters of the tcgen05 GEMM (all zero between launches)
   void* bf16_scratch = nullptr;         // bf16 copies of GEMM operands (OKL_BF16 mode)
   size_t bf16_scratch_bytes = 0;
+  // auxiliary lanes: independent branches of a step (weight / bias gradients are leaves of the backward chain) run on their own
+  // streams with their own scratch; the fields above (stream, workspace, tile_counters, bf16_scratch) always describe the CURRENT lane
+  struct Lane {
+    cudaStream_t stream = nullptr;
+    void* workspace = nullptr; size_t workspace_bytes = 0;
+    int* tile_counters = nullptr;
+    void* bf16_scratch = nullptr; size_t bf16_scratch_bytes = 0;
+    cudaEvent_t ev = nullptr;
+    bool dirty = false;
+  };
+  Lane lanes[3];
+  int cur_lane = 0;
+  cudaEvent_t ev_mark = nullptr;
+  bool fork_marked = false;
+  bool aux_dirty = false;
+  std::vector<void*> deferred_free;     // pool blocks released while an aux lane may still read them
   // comm
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
@@ -123,3 +139,8 @@ bool okl_conv_small_fprop_ok(const okl_conv_desc*);
 bool okl_conv_small_wgrad_ok(const okl_conv_desc*);
 int okl_conv_small_fprop(okl_ctx*, const okl_conv_desc*, const float* x, const float* W, const float* b, float* y);
 int okl_conv_small_wgrad(okl_ctx*, const okl_conv_desc*, const float* x, const float* g, float* dW, float* db);
+// one-kernel forward (+softmax) and one-kernel backward for tiny output widths (classifier heads): okl_dense_small.cu
+bool okl_dense_small_ok(int M, int K, int N);
+int okl_dense_small_fwd(okl_ctx*, const float* X, const float* W, const float* b, float* Y, int M, int K, int N, int act);
+int okl_dense_small_bwd(okl_ctx*, const float* X, const float* W, const float* G, float* dX, float* dW, float* db, const float* relu_mask,
+                        int M, int K, int N);

@@ -286,14 +286,14 @@ conv_smallk_wgrad(const float* __restrict__ x, const float* __restrict__ gy, flo
 // dW[o, k] = sum_b partial[y][b][o_local][k] (k < K) ; db[o] = sum_b partial[...][K].  One warp per output element: the
 // lanes stride over the blocks' partials (independent loads), then a fixed-order butterfly.
 __global__ void conv_smallk_wgrad_reduce(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ db, int O, int K,
-                                         int KT, int gx) {
+                                         int KT, int gx, int OB) {
   const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (idx >= O * (K + 1)) return;
   const int o = idx / (K + 1), k = idx - o * (K + 1);
-  const int oy = o / WG_OB, ol = o - oy * WG_OB;
-  const float* p = partial + ((size_t)oy * gx * WG_OB + ol) * KT + k;
+  const int oy = o / OB, ol = o - oy * OB;
+  const float* p = partial + ((size_t)oy * gx * OB + ol) * KT + k;
   float s = 0.f;
-  for (int b = lane; b < gx; b += 32) s += p[(size_t)b * WG_OB * KT];
+  for (int b = lane; b < gx; b += 32) s += p[(size_t)b * OB * KT];
 #pragma unroll
   for (int sft = 16; sft > 0; sft >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sft);
   if (lane == 0) {
@@ -390,7 +390,7 @@ int okl_conv_small_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const float* x, c
   }
   OKL_LAUNCHED(ctx, "conv_smallk_wgrad");
   const int total = g.O * (K + 1);
-  conv_smallk_wgrad_reduce<<<(total * 32 + 255) / 256, 256, 0, ctx->stream>>>(partial, dW, db, g.O, K, KT, gx);
+  conv_smallk_wgrad_reduce<<<(total * 32 + 255) / 256, 256, 0, ctx->stream>>>(partial, dW, db, g.O, K, KT, gx, WG_OB);
   OKL_LAUNCHED(ctx, "conv_smallk_wgrad_reduce");
   return OKL_OK;
 }
@@ -406,12 +406,14 @@ int okl_conv_small_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const float* x, c
 //             gradient, the mask and the (4 x 4) input windows - never the un-pooled gradient.
 namespace {
 
+// One thread per (pooled position, group of OT = 8 output channels): enough threads to fill the chip at MNIST sizes, consecutive
+// threads = consecutive pooled positions of one channel group, so the pooled / mask stores are coalesced per channel.
 template <int KH, int KW, bool PAD>
-__global__ void __launch_bounds__(256, 2) conv_relu_pool2_fwd(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
+__global__ void __launch_bounds__(256, 3) conv_relu_pool2_fwd(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
                                                              float* __restrict__ yp, unsigned char* __restrict__ mask, const ConvGeom g,
                                                              const int K, const int Opad, const int PH, const int PW, const FastDiv dPW,
-                                                             const FastDiv dPH, const int total) {
-  constexpr int OT = 16, WH = KH + 1, WW = KW + 1;
+                                                             const FastDiv dPH, const FastDiv dPix, const int npix, const int total) {
+  constexpr int OT = 8, WH = KH + 1, WW = KW + 1;
   extern __shared__ __align__(16) float sm[];
   float* Ws = sm;                 // [K][Opad]
   float* bs = sm + K * Opad;      // [Opad]
@@ -423,76 +425,78 @@ __global__ void __launch_bounds__(256, 2) conv_relu_pool2_fwd(const float* __res
   __syncthreads();
   const long long plane = (long long)PH * PW;
   for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
-    unsigned t, pw, ph;
-    dPW.divmod((unsigned)it, t, pw); dPH.divmod(t, t, ph);
-    const int n = (int)t;
+    unsigned chunk, pix, t, pw, ph;
+    dPix.divmod((unsigned)it, chunk, pix);
+    dPW.divmod(pix, t, pw); dPH.divmod(t, t, ph);
+    const int n = (int)t, oc = (int)chunk * OT;
     const int ih0 = 2 * (int)ph - g.P[1], iw0 = 2 * (int)pw - g.P[2];
     const float* xn = x + n * g.xs[0];
-    const long long obase = (long long)n * g.O * plane + ph * PW + pw;
-    for (int oc = 0; oc < Opad; oc += OT) {
-      float a[4][OT];
+    float a[4][OT];
 #pragma unroll
-      for (int j = 0; j < OT; j++) { const float bv = bs[oc + j]; a[0][j] = bv; a[1][j] = bv; a[2][j] = bv; a[3][j] = bv; }
-      for (int c = 0; c < g.C; c++) {
-        const float* xc = xn + c * g.xs[1];
-        float win[WH][WW];
+    for (int j = 0; j < OT; j++) { const float bv = bs[oc + j]; a[0][j] = bv; a[1][j] = bv; a[2][j] = bv; a[3][j] = bv; }
+    for (int c = 0; c < g.C; c++) {
+      const float* xc = xn + c * g.xs[1];
+      float win[WH][WW];
 #pragma unroll
-        for (int r = 0; r < WH; r++)
+      for (int r = 0; r < WH; r++)
 #pragma unroll
-          for (int q = 0; q < WW; q++) {
-            const int ih = ih0 + r, iw = iw0 + q;
-            const bool ok = !PAD || ((unsigned)ih < (unsigned)g.I[1] && (unsigned)iw < (unsigned)g.I[2]);
-            win[r][q] = ok ? __ldg(xc + ih * g.xs[3] + iw) : 0.f;
-          }
+        for (int q = 0; q < WW; q++) {
+          const int ih = ih0 + r, iw = iw0 + q;
+          const bool ok = !PAD || ((unsigned)ih < (unsigned)g.I[1] && (unsigned)iw < (unsigned)g.I[2]);
+          win[r][q] = ok ? __ldg(xc + ih * g.xs[3] + iw) : 0.f;
+        }
 #pragma unroll
-        for (int th = 0; th < KH; th++)
+      for (int th = 0; th < KH; th++)
 #pragma unroll
-          for (int tw = 0; tw < KW; tw++) {
-            const float4* wr = reinterpret_cast<const float4*>(Ws + ((c * KH + th) * KW + tw) * Opad + oc);
-            const float x00 = win[th][tw], x01 = win[th][tw + 1], x10 = win[th + 1][tw], x11 = win[th + 1][tw + 1];
+        for (int tw = 0; tw < KW; tw++) {
+          const float4* wr = reinterpret_cast<const float4*>(Ws + ((c * KH + th) * KW + tw) * Opad + oc);
+          const float x00 = win[th][tw], x01 = win[th][tw + 1], x10 = win[th + 1][tw], x11 = win[th + 1][tw + 1];
 #pragma unroll
-            for (int q = 0; q < OT / 4; q++) {
-              const float4 w4 = wr[q];
-              const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+          for (int q = 0; q < OT / 4; q++) {
+            const float4 w4 = wr[q];
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-              for (int e = 0; e < 4; e++) {
-                a[0][4 * q + e] = fmaf(x00, wv[e], a[0][4 * q + e]);
-                a[1][4 * q + e] = fmaf(x01, wv[e], a[1][4 * q + e]);
-                a[2][4 * q + e] = fmaf(x10, wv[e], a[2][4 * q + e]);
-                a[3][4 * q + e] = fmaf(x11, wv[e], a[3][4 * q + e]);
-              }
+            for (int e = 0; e < 4; e++) {
+              a[0][4 * q + e] = fmaf(x00, wv[e], a[0][4 * q + e]);
+              a[1][4 * q + e] = fmaf(x01, wv[e], a[1][4 * q + e]);
+              a[2][4 * q + e] = fmaf(x10, wv[e], a[2][4 * q + e]);
+              a[3][4 * q + e] = fmaf(x11, wv[e], a[3][4 * q + e]);
             }
           }
-      }
-#pragma unroll
-      for (int j = 0; j < OT; j++) {
-        if (oc + j < g.O) {
-          const float v0 = fmaxf(a[0][j], 0.f), v1 = fmaxf(a[1][j], 0.f), v2 = fmaxf(a[2][j], 0.f), v3 = fmaxf(a[3][j], 0.f);
-          const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
-          unsigned mk = 0;
-          if (m > 0.f) mk = (v0 == m ? 1u : 0u) | (v1 == m ? 2u : 0u) | (v2 == m ? 4u : 0u) | (v3 == m ? 8u : 0u);
-          const long long off = obase + (long long)(oc + j) * plane;
-          yp[off] = m;
-          mask[off] = (unsigned char)mk;
         }
+    }
+    const long long obase = (long long)n * g.O * plane + ph * PW + pw;
+#pragma unroll
+    for (int j = 0; j < OT; j++) {
+      if (oc + j < g.O) {
+        const float v0 = fmaxf(a[0][j], 0.f), v1 = fmaxf(a[1][j], 0.f), v2 = fmaxf(a[2][j], 0.f), v3 = fmaxf(a[3][j], 0.f);
+        const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+        unsigned mk = 0;
+        if (m > 0.f) mk = (v0 == m ? 1u : 0u) | (v1 == m ? 2u : 0u) | (v2 == m ? 4u : 0u) | (v3 == m ? 8u : 0u);
+        const long long off = obase + (long long)(oc + j) * plane;
+        yp[off] = m;
+        mask[off] = (unsigned char)mk;
       }
     }
   }
 }
 
-// NW = C * (KH+1) * (KW+1) window rows staged per pooled position; KT >= C*KH*KW + 1
+// dW / db from the POOLED gradient.  One 128-thread block per tile of 128 pooled positions and 16 output channels: thread p first
+// issues every global load of its position (16 gradients, 16 masks, the C*(KH+1)*(KW+1) input window) back to back, then warp w
+// accumulates channels 4w..4w+3 with lane l owning positions 4l..4l+3.
+constexpr int CP_OB = 16;
 template <int KH, int KW, int CMAX, int KT, bool PAD>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(128, 4)
 conv_relu_pool2_wgrad(const float* __restrict__ x, const float* __restrict__ gp, const unsigned char* __restrict__ mask,
                       float* __restrict__ partial, const ConvGeom g, const int K, const int PH, const int PW, const FastDiv dPW,
                       const FastDiv dPH, const int Mpool, const int ntiles) {
   constexpr int WH = KH + 1, WW = KW + 1, NW = CMAX * WH * WW;
-  __shared__ __align__(16) float gs[WG_OB][WG_PT];
+  __shared__ __align__(16) float gs[CP_OB][WG_PT];
   __shared__ __align__(16) float xw[NW][WG_PT];
-  __shared__ unsigned char ms[WG_OB][WG_PT];
+  __shared__ unsigned char ms[CP_OB][WG_PT];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int o_base = blockIdx.y * WG_OB;
-  const int p = tid & (WG_PT - 1), half = tid >> 7;
+  const int o_base = blockIdx.y * CP_OB;
+  const int p = tid;
   const long long plane = (long long)PH * PW;
   float acc[4][KT];
 #pragma unroll
@@ -505,24 +509,31 @@ conv_relu_pool2_wgrad(const float* __restrict__ x, const float* __restrict__ gp,
     const bool ok = m < Mpool;
     unsigned t, pw, ph;
     dPW.divmod((unsigned)m, t, pw); dPH.divmod(t, t, ph);
-    __syncthreads();
+    float gr[CP_OB], wr[NW];
+    unsigned char mr[CP_OB];
     {
       const long long gb = (long long)t * g.O * plane + ph * PW + pw;
-#pragma unroll 4
-      for (int o = half; o < WG_OB; o += 2) {
+#pragma unroll
+      for (int o = 0; o < CP_OB; o++) {
         const bool v = ok && o_base + o < g.O;
-        gs[o][p] = v ? __ldg(gp + gb + (long long)(o_base + o) * plane) : 0.f;
-        ms[o][p] = v ? __ldg(mask + gb + (long long)(o_base + o) * plane) : (unsigned char)0;
+        gr[o] = v ? __ldg(gp + gb + (long long)(o_base + o) * plane) : 0.f;
+        mr[o] = v ? __ldg(mask + gb + (long long)(o_base + o) * plane) : (unsigned char)0;
       }
       const int ih0 = 2 * (int)ph - g.P[1], iw0 = 2 * (int)pw - g.P[2];
       const float* xn = x + t * g.xs[0];
-      for (int r = half; r < g.C * WH * WW; r += 2) {
-        const int c = r / (WH * WW), rr = r - c * (WH * WW);
+#pragma unroll
+      for (int r = 0; r < NW; r++) {
+        const int c = r / (WH * WW), rr = r % (WH * WW);
         const int ih = ih0 + rr / WW, iw = iw0 + rr % WW;
         const bool in = ok && (!PAD || ((unsigned)ih < (unsigned)g.I[1] && (unsigned)iw < (unsigned)g.I[2]));
-        xw[r][p] = in ? __ldg(xn + c * g.xs[1] + ih * g.xs[3] + iw) : 0.f;
+        wr[r] = in ? __ldg(xn + c * g.xs[1] + ih * g.xs[3] + iw) : 0.f;
       }
     }
+    __syncthreads();                                   // previous tile fully consumed
+#pragma unroll
+    for (int o = 0; o < CP_OB; o++) { gs[o][p] = gr[o]; ms[o][p] = mr[o]; }
+#pragma unroll
+    for (int r = 0; r < NW; r++) xw[r][p] = wr[r];
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -546,13 +557,12 @@ conv_relu_pool2_wgrad(const float* __restrict__ x, const float* __restrict__ gp,
                 if (k < KT) acc[i][k] = fmaf(gv, wbase[(c * WH * WW + th * WW + tw) * WG_PT], acc[i][k]);
               }
           }
-          // bias gradient: the all-ones tap lives in column K (= C*KH*KW, a compile-time constant per instantiation)
-          acc[i][CMAX * KH * KW] += gv;
+          acc[i][CMAX * KH * KW] += gv;                // bias gradient: the all-ones tap lives in column K
         }
       }
     }
   }
-  float* out = partial + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * WG_OB + warp * 4) * KT;
+  float* out = partial + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * CP_OB + warp * 4) * KT;
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -585,7 +595,8 @@ extern "C" int okl_conv_relu_pool_fwd(okl_ctx* ctx, const okl_conv_desc* d, cons
   if (s != OKL_OK) return s;
   const int K = g.C * 9, Opad = (g.O + 15) / 16 * 16;
   const int PH = g.Oe[1] / 2, PW = g.Oe[2] / 2;
-  const int total = g.N * PH * PW;
+  const int npix = g.N * PH * PW;
+  const int total = npix * (Opad / 8);
   if (total == 0) return OKL_OK;
   const size_t smem = (size_t)(K * Opad + Opad) * sizeof(float);
   int grid = (total + 255) / 256;
@@ -593,9 +604,9 @@ extern "C" int okl_conv_relu_pool_fwd(okl_ctx* ctx, const okl_conv_desc* d, cons
   if (grid > cap) grid = cap;
   const bool pad = g.P[1] || g.P[2];
   if (pad) conv_relu_pool2_fwd<3, 3, true><<<grid, 256, smem, ctx->stream>>>((const float*)x, (const float*)W, (const float*)b, (float*)pooled,
-                                                                           (unsigned char*)mask, g, K, Opad, PH, PW, FastDiv(PW), FastDiv(PH), total);
+                                                                           (unsigned char*)mask, g, K, Opad, PH, PW, FastDiv(PW), FastDiv(PH), FastDiv(npix), npix, total);
   else conv_relu_pool2_fwd<3, 3, false><<<grid, 256, smem, ctx->stream>>>((const float*)x, (const float*)W, (const float*)b, (float*)pooled,
-                                                                          (unsigned char*)mask, g, K, Opad, PH, PW, FastDiv(PW), FastDiv(PH), total);
+                                                                          (unsigned char*)mask, g, K, Opad, PH, PW, FastDiv(PW), FastDiv(PH), FastDiv(npix), npix, total);
   OKL_LAUNCHED(ctx, "conv_relu_pool2_fwd");
   return OKL_OK;
 }
@@ -612,17 +623,17 @@ extern "C" int okl_conv_relu_pool_wgrad(okl_ctx* ctx, const okl_conv_desc* d, co
   const int PH = g.Oe[1] / 2, PW = g.Oe[2] / 2;
   const int Mpool = g.N * PH * PW;
   const int ntiles = (Mpool + WG_PT - 1) / WG_PT;
-  const int gy_ = (g.O + WG_OB - 1) / WG_OB;
-  int gx = (2 * ctx->sm_count + gy_ - 1) / gy_;
+  const int gy_ = (g.O + CP_OB - 1) / CP_OB;
+  int gx = (8 * ctx->sm_count + gy_ - 1) / gy_;          // every tile gets its own resident block at MNIST sizes
   if (gx > ntiles) gx = ntiles;
   if (gx < 1) gx = 1;
-  s = okl_ensure_workspace(ctx, (size_t)gx * gy_ * WG_OB * KT * sizeof(float));
+  s = okl_ensure_workspace(ctx, (size_t)gx * gy_ * CP_OB * KT * sizeof(float));
   if (s != OKL_OK) return s;
   float* partial = (float*)ctx->workspace;
   dim3 grid(gx, gy_);
   const bool pad = g.P[1] || g.P[2];
 #define OKL_LAUNCH_CRPW(C_, KT_, PAD_)                                                                                               \
-  conv_relu_pool2_wgrad<3, 3, C_, KT_, PAD_><<<grid, 256, 0, ctx->stream>>>((const float*)x, (const float*)pooled_g,                \
+  conv_relu_pool2_wgrad<3, 3, C_, KT_, PAD_><<<grid, 128, 0, ctx->stream>>>((const float*)x, (const float*)pooled_g,                \
                                                                             (const unsigned char*)mask, partial, g, K, PH, PW,      \
                                                                             FastDiv(PW), FastDiv(PH), Mpool, ntiles)
   if (g.C == 1) { if (pad) OKL_LAUNCH_CRPW(1, 12, true); else OKL_LAUNCH_CRPW(1, 12, false); }
@@ -630,7 +641,7 @@ extern "C" int okl_conv_relu_pool_wgrad(okl_ctx* ctx, const okl_conv_desc* d, co
 #undef OKL_LAUNCH_CRPW
   OKL_LAUNCHED(ctx, "conv_relu_pool2_wgrad");
   const int total = g.O * (K + 1);
-  conv_smallk_wgrad_reduce<<<(total * 32 + 255) / 256, 256, 0, ctx->stream>>>(partial, (float*)dW, (float*)db, g.O, K, KT, gx);
+  conv_smallk_wgrad_reduce<<<(total * 32 + 255) / 256, 256, 0, ctx->stream>>>(partial, (float*)dW, (float*)db, g.O, K, KT, gx, CP_OB);
   OKL_LAUNCHED(ctx, "conv_smallk_wgrad_reduce");
   return OKL_OK;
 }

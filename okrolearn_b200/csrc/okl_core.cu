@@ -46,8 +46,12 @@ extern "C" int okl_ctx_create(int device, int precision, okl_ctx** out) {
   c->total_mem = prop.totalGlobalMem;
   OKL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   OKL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  c->lanes[0].stream = c->stream;
+  for (int i = 1; i < 3; i++) OKL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->lanes[i].stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 3; i++) OKL_CHECK_CUDA(cudaEventCreateWithFlags(&c->lanes[i].ev, cudaEventDisableTiming));
   OKL_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   OKL_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  OKL_CHECK_CUDA(cudaEventCreateWithFlags(&c->ev_mark, cudaEventDisableTiming));
   OKL_CHECK_CUDA(cudaEventCreate(&c->ev_t0));
   OKL_CHECK_CUDA(cudaEventCreate(&c->ev_t1));
   *out = c;
@@ -56,9 +60,87 @@ extern "C" int okl_ctx_create(int device, int precision, okl_ctx** out) {
 
 extern "C" int okl_comm_destroy(okl_ctx* ctx);
 
+static void lane_save(okl_ctx* c) {
+  okl_ctx::Lane& l = c->lanes[c->cur_lane];
+  l.stream = c->stream; l.workspace = c->workspace; l.workspace_bytes = c->workspace_bytes; l.tile_counters = c->tile_counters;
+  l.bf16_scratch = c->bf16_scratch; l.bf16_scratch_bytes = c->bf16_scratch_bytes;
+}
+static void lane_load(okl_ctx* c, int lane) {
+  okl_ctx::Lane& l = c->lanes[lane];
+  c->stream = l.stream; c->workspace = l.workspace; c->workspace_bytes = l.workspace_bytes; c->tile_counters = l.tile_counters;
+  c->bf16_scratch = l.bf16_scratch; c->bf16_scratch_bytes = l.bf16_scratch_bytes;
+  c->cur_lane = lane;
+}
+
+// Subsequent launches go to auxiliary lane `lane` (1 or 2), ordered after everything enqueued so far on the main lane.
+extern "C" int okl_aux_begin(okl_ctx* ctx, int lane) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  OKL_REQUIRE(lane >= 1 && lane <= 2, "aux lane must be 1 or 2");
+  OKL_REQUIRE(ctx->cur_lane == 0, "okl_aux_begin: already on an auxiliary lane");
+  if (!ctx->fork_marked) OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_mark, ctx->stream));
+  ctx->fork_marked = false;
+  OKL_CHECK_CUDA(cudaStreamWaitEvent(ctx->lanes[lane].stream, ctx->ev_mark, 0));
+  lane_save(ctx);
+  lane_load(ctx, lane);
+  ctx->lanes[lane].dirty = true;
+  ctx->aux_dirty = true;
+  return OKL_OK;
+}
+
+// Remember "now" on the main lane as the point the next okl_aux_begin forks from: lets the caller enqueue the critical-path kernel
+// on the main lane FIRST (so it is scheduled first) and the leaf kernels afterwards, while both only depend on the marked point.
+extern "C" int okl_aux_mark(okl_ctx* ctx) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  OKL_REQUIRE(ctx->cur_lane == 0, "okl_aux_mark: not on the main lane");
+  OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_mark, ctx->stream));
+  ctx->fork_marked = true;
+  return OKL_OK;
+}
+
+// Back to the main lane (the auxiliary work keeps running concurrently).
+extern "C" int okl_aux_end(okl_ctx* ctx) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  if (ctx->cur_lane == 0) return OKL_OK;
+  lane_save(ctx);
+  lane_load(ctx, 0);
+  return OKL_OK;
+}
+
+// The main lane waits for everything issued on the auxiliary lanes.
+extern "C" int okl_aux_join(okl_ctx* ctx) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  if (ctx->cur_lane != 0) { lane_save(ctx); lane_load(ctx, 0); }
+  if (!ctx->aux_dirty) return OKL_OK;
+  for (int i = 1; i < 3; i++) {
+    if (!ctx->lanes[i].dirty) continue;
+    OKL_CHECK_CUDA(cudaEventRecord(ctx->lanes[i].ev, ctx->lanes[i].stream));
+    OKL_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->lanes[i].ev, 0));
+    ctx->lanes[i].dirty = false;
+  }
+  ctx->aux_dirty = false;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (void* p : ctx->deferred_free) {
+      auto it = ctx->live.find(p);
+      if (it != ctx->live.end()) ctx->free_blocks.emplace(it->second, p);
+    }
+    ctx->deferred_free.clear();
+  }
+  return OKL_OK;
+}
+
 extern "C" int okl_ctx_destroy(okl_ctx* ctx) {
   if (!ctx) return OKL_OK;
   cudaSetDevice(ctx->device);
+  okl_aux_join(ctx);
+  for (int i = 1; i < 3; i++) {
+    cudaStreamSynchronize(ctx->lanes[i].stream);
+    if (ctx->lanes[i].workspace) cudaFree(ctx->lanes[i].workspace);
+    if (ctx->lanes[i].tile_counters) cudaFree(ctx->lanes[i].tile_counters);
+    if (ctx->lanes[i].bf16_scratch) cudaFree(ctx->lanes[i].bf16_scratch);
+    cudaStreamDestroy(ctx->lanes[i].stream);
+  }
+  for (int i = 0; i < 3; i++) cudaEventDestroy(ctx->lanes[i].ev);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->comm_stream);
   okl_comm_destroy(ctx);
@@ -80,6 +162,10 @@ extern "C" int okl_ctx_destroy(okl_ctx* ctx) {
 
 extern "C" int okl_ctx_sync(okl_ctx* ctx) {
   OKL_REQUIRE(ctx, "ctx is NULL");
+  if (!ctx->capturing) {
+    int s = okl_aux_join(ctx);
+    if (s != OKL_OK) return s;
+  }
   OKL_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   OKL_CHECK_CUDA(cudaStreamSynchronize(ctx->comm_stream));
   return OKL_OK;
@@ -164,6 +250,10 @@ extern "C" int okl_free(okl_ctx* ctx, void* p) {
   // stream-ordered reuse: every consumer runs on ctx->stream (the comm stream is joined before reuse).  A block released while
   // a CUDA graph is being captured stays out of the pool: the graph's kernels keep writing to it on every replay.
   if (ctx->capturing) return OKL_OK;
+  if (ctx->aux_dirty) {                   // an auxiliary lane may still be reading this block: recycle it at the next join
+    ctx->deferred_free.push_back(p);
+    return OKL_OK;
+  }
   ctx->free_blocks.emplace(it->second, p);
   return OKL_OK;
 }
@@ -291,6 +381,10 @@ extern "C" int okl_d2h(okl_ctx* ctx, void* host, const void* src_f32, size_t n, 
   OKL_REQUIRE(ctx && (n == 0 || (src_f32 && host)), "NULL argument");
   OKL_REQUIRE(dst_dtype == OKL_F32 || dst_dtype == OKL_F64, "okl_d2h: dst dtype must be F32 or F64");
   if (n == 0) return OKL_OK;
+  if (ctx->aux_dirty && !ctx->capturing) {
+    int sj = okl_aux_join(ctx);
+    if (sj != OKL_OK) return sj;
+  }
   if (ctx->comm_pending) {
     int s = okl_comm_wait(ctx);
     if (s != OKL_OK) return s;
@@ -317,6 +411,10 @@ extern "C" int okl_d2d(okl_ctx* ctx, void* dst, const void* src, size_t bytes) {
 
 extern "C" int okl_read_scalar(okl_ctx* ctx, const void* dev_f32, float* out) {
   OKL_REQUIRE(ctx && dev_f32 && out, "NULL argument");
+  if (ctx->aux_dirty && !ctx->capturing) {
+    int sj = okl_aux_join(ctx);
+    if (sj != OKL_OK) return sj;
+  }
   OKL_CHECK_CUDA(cudaMemcpyAsync(out, dev_f32, 4, cudaMemcpyDeviceToHost, ctx->stream));
   OKL_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
   return OKL_OK;
@@ -337,6 +435,10 @@ extern "C" int okl_graph_begin(okl_ctx* ctx) {
 extern "C" int okl_graph_end(okl_ctx* ctx, okl_graph** out) {
   OKL_REQUIRE(ctx && out, "NULL argument");
   OKL_REQUIRE(ctx->capturing, "okl_graph_end: not capturing");
+  {
+    int sj = okl_aux_join(ctx);          // auxiliary lanes must rejoin the origin stream before the capture ends
+    if (sj != OKL_OK) return sj;
+  }
   if (ctx->comm_pending) {                         // join the comm stream back before ending the capture
     int s = okl_comm_wait(ctx);
     if (s != OKL_OK) return s;
@@ -389,6 +491,10 @@ extern "C" int okl_timer_start(okl_ctx* ctx) {
 
 extern "C" int okl_timer_stop(okl_ctx* ctx, float* ms) {
   OKL_REQUIRE(ctx && ms, "NULL argument");
+  {
+    int sj = okl_aux_join(ctx);
+    if (sj != OKL_OK) return sj;
+  }
   if (ctx->comm_pending) {
     int s = okl_comm_wait(ctx);
     if (s != OKL_OK) return s;

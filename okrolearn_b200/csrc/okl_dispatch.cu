@@ -5,9 +5,12 @@
 extern "C" int okl_dense_fwd(okl_ctx* ctx, const void* X, const void* W, const void* b, void* Y, int M, int K, int N, int act) {
   OKL_REQUIRE(ctx, "ctx is NULL");
   OKL_REQUIRE(M >= 0 && K >= 1 && N >= 1, "okl_dense_fwd: bad shape M=%d K=%d N=%d", M, K, N);
-  OKL_REQUIRE(act >= OKL_ACT_NONE && act <= OKL_ACT_TANH, "bad activation %d", act);
+  OKL_REQUIRE(act >= OKL_ACT_NONE && act <= OKL_ACT_SOFTMAX, "bad activation %d", act);
   if (M == 0) return OKL_OK;
   OKL_REQUIRE(X && W && Y, "okl_dense_fwd: NULL tensor");
+  if (okl_dense_small_ok(M, K, N))
+    return okl_dense_small_fwd(ctx, (const float*)X, (const float*)W, (const float*)b, (float*)Y, M, K, N, act);
+  OKL_REQUIRE(act != OKL_ACT_SOFTMAX, "okl_dense_fwd: the fused softmax epilogue needs an output width <= 16");
   if (ctx->precision != OKL_FP32 && okl_tc_dense_supported(ctx, M, K, N))
     return okl_tc_dense_fwd(ctx, (const float*)X, (const float*)W, (const float*)b, (float*)Y, M, K, N, act);
   return okl_ffma_dense_fwd(ctx, (const float*)X, (const float*)W, (const float*)b, (float*)Y, M, K, N, act);
@@ -18,6 +21,9 @@ extern "C" int okl_dense_bwd(okl_ctx* ctx, const void* X, const void* W, const v
   OKL_REQUIRE(ctx, "ctx is NULL");
   OKL_REQUIRE(M >= 0 && K >= 1 && N >= 1, "okl_dense_bwd: bad shape M=%d K=%d N=%d", M, K, N);
   OKL_REQUIRE(X && W && G, "okl_dense_bwd: NULL tensor");
+  if (M > 0 && okl_dense_small_ok(M, K, N))
+    return okl_dense_small_bwd(ctx, (const float*)X, (const float*)W, (const float*)G, (float*)dX, (float*)dW, (float*)db,
+                               (const float*)dx_relu_mask, M, K, N);
   int s;
   const bool tc = ctx->precision != OKL_FP32 && M > 0 && okl_tc_dense_supported(ctx, M, K, N);
   if (dW) {

@@ -190,6 +190,7 @@ struct TcGemmParams {
   const float* mask;   // optional, same indexing as D: D = 0 where mask <= 0 (fused backward of a preceding ReLU)
   int act;
   float* ws;           // [splits][M][N] partials when splits > 1
+  int stages;          // smem ring depth actually used (<= TcCfg::STAGES): short K loops take less smem so CTAs of concurrent kernels co-reside
   int* counters;       // [tiles] arrival counters (zero on entry, reset by the last arriver) when splits > 1
   // implicit-GEMM convolution (MODE 1 = fprop/dgrad, MODE 2 = wgrad); activations are channels-last (N, H, W, C)
   int cv_TW, cv_TH, cv_TN;         // spatial tile: TW x TH pixels of TN images (128 pixels = an M tile in MODE 1, 32 = a k-block in MODE 2)
@@ -222,13 +223,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using Cfg = TcCfg<KIND, BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * Cfg::STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::STAGES;
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
   uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
-  float* stage_base = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);   // 4 warps x 32 rows x 36 floats
+  float* stage_base = reinterpret_cast<float*>(smem + p.stages * Cfg::STAGE_BYTES + 256);   // 4 warps x 32 rows x 36 floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -239,7 +240,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && elect_one()) {
-    for (int s = 0; s < Cfg::STAGES; s++) {
+    for (int s = 0; s < p.stages; s++) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -313,7 +314,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_2d(&tmB, &full_bar[stage], sb + c * (Cfg::BK * 128), n0 + c * Cfg::EPC, k0);
           }
           }
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -349,7 +350,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < Cfg::BK / Cfg::UMMA_K; k++)
             umma<KIND>(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);                 // smem stage reusable once these MMAs have read it
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);                      // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -596,7 +597,11 @@ int launch_cfg(okl_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const
   }
   int total = p.tiles_m * p.tiles_n * p.splits;
   int grid = total < ctx->sm_count ? total : ctx->sm_count;
-  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(ta, tb, p);
+  TcGemmParams q = p;
+  const int kb = p.kb_per_split > 0 ? p.kb_per_split : p.kb_total;
+  q.stages = total <= grid ? (kb < 2 ? 2 : (kb < Cfg::STAGES ? kb : Cfg::STAGES)) : Cfg::STAGES;   // one tile per CTA: no deeper than its K loop
+  const int smem_bytes = Cfg::SMEM_BYTES - (Cfg::STAGES - q.stages) * Cfg::STAGE_BYTES;
+  kern<<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(ta, tb, q);
   OKL_LAUNCHED(ctx, "tc_gemm_kernel");
   return OKL_OK;
 }

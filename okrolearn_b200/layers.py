@@ -126,6 +126,7 @@ class _ParamBucket:
 
 
 class _ParamLayer:
+    _aux_lane = 0                  # NeuralNetwork planner: >0 = compute dW/db (leaves of the backward chain) on that auxiliary lane
     _dx_relu_mask = False          # NeuralNetwork planner: a fused ReLU precedes this layer; its backward is applied in our dX epilogue
     _defer_update = False          # set by NeuralNetwork when updates are applied after the whole backward (DP overlap)
     _fused_act = ACT_NONE          # set by NeuralNetwork's planner: activation fused into this layer's epilogue
@@ -139,6 +140,7 @@ class _ParamLayer:
 def apply_pending_updates(layers):
     """All deferred bucket updates of a network in ONE kernel launch (after the data-parallel exchange has been joined)."""
     ctx = get_ctx()
+    check(lib.okl_aux_join(ctx.h))
     bs = [l._bucket for l in layers if isinstance(l, _ParamLayer) and getattr(l._bucket, "_pending_lr", None) is not None]
     if not bs:
         return
@@ -201,10 +203,20 @@ class DenseLayer(_ParamLayer):
         need_dx = getattr(self, "_need_dx", True)
         dX = Tensor._empty((M, K), np.float64) if need_dx else None
         b = self._bucket
-        xp = self.inputs._dptr(NCX)
-        check(lib.okl_dense_bwd(ctx.h, xp, b.ptr(0), dL_dout._dptr(NCX), dX._ptr_raw() if need_dx else None,
-                                b.grad_ptr(0), b.grad_ptr(1), M, K, N, xp if (need_dx and self._dx_relu_mask) else None))
-        b.step(lr, self._defer_update)
+        xp, gp, wp = self.inputs._dptr(NCX), dL_dout._dptr(NCX), b.ptr(0)
+        mask = xp if (need_dx and self._dx_relu_mask) else None
+        if self._aux_lane and self._defer_update and need_dx:
+            check(lib.okl_aux_mark(ctx.h))
+            check(lib.okl_dense_bwd(ctx.h, xp, wp, gp, dX._ptr_raw(), None, None, M, K, N, mask))     # critical path first
+            check(lib.okl_aux_begin(ctx.h, self._aux_lane))          # dW, db (+ their all-reduce) are leaves: own lane
+            try:
+                check(lib.okl_dense_bwd(ctx.h, xp, wp, gp, None, b.grad_ptr(0), b.grad_ptr(1), M, K, N, None))
+                b.step(lr, True)
+            finally:
+                check(lib.okl_aux_end(ctx.h))
+        else:
+            check(lib.okl_dense_bwd(ctx.h, xp, wp, gp, dX._ptr_raw() if need_dx else None, b.grad_ptr(0), b.grad_ptr(1), M, K, N, mask))
+            b.step(lr, self._defer_update)
         return dX
 
     def get_params(self):
@@ -323,14 +335,24 @@ class _ConvBase(_ParamLayer):
         if dL_dout.shape != (x.shape[0], self.out_channels) + oe:
             raise ValueError(f"dL_dout shape {dL_dout.shape} does not match the layer output {(x.shape[0], self.out_channels) + oe}")
         b = self._bucket
-        g = dL_dout._dptr(yl)
-        check(lib.okl_conv_wgrad(ctx.h, C.byref(d), x._dptr(xl), g, b.grad_ptr(0), b.grad_ptr(1)))
+        g, xp, wp = dL_dout._dptr(yl), x._dptr(xl), b.ptr(0)
+        need_dx = getattr(self, "_need_dx", True)
+        aux = self._aux_lane and self._defer_update and need_dx
         dX = None
-        if getattr(self, "_need_dx", True):
+        if need_dx:
+            if aux:
+                check(lib.okl_aux_mark(ctx.h))
             dX = Tensor._empty(x.shape, self._dx_dtype(x), layout=xl)
-            check(lib.okl_conv_dgrad(ctx.h, C.byref(d), g, b.ptr(0), dX._ptr_raw(),        # uses the pre-update filters
-                                     x._dptr(xl) if self._dx_relu_mask else None))
-        b.step(lr, self._defer_update)
+            check(lib.okl_conv_dgrad(ctx.h, C.byref(d), g, wp, dX._ptr_raw(),              # critical path first; pre-update filters
+                                     xp if self._dx_relu_mask else None))
+        if aux:
+            check(lib.okl_aux_begin(ctx.h, self._aux_lane))          # dW, db (+ their all-reduce) are leaves: own lane
+        try:
+            check(lib.okl_conv_wgrad(ctx.h, C.byref(d), xp, g, b.grad_ptr(0), b.grad_ptr(1)))
+            b.step(lr, True if aux else self._defer_update)
+        finally:
+            if aux:
+                check(lib.okl_aux_end(ctx.h))
         return dX
 
     def _dx_dtype(self, x):
@@ -529,12 +551,17 @@ class SoftmaxActivationLayer:
     """okl.py:355-399: stable softmax over axis 1 (+ nan_to_num); backward = Jacobian product, computed in closed form
     p * (g - sum_k g_k p_k) instead of the reference's B x C x C Python triple loop."""
 
+    _fused_into_prev = False   # NeuralNetwork planner: the preceding (small) DenseLayer's kernel already applied the softmax
+
     def forward(self, inputs: Tensor):
         inputs = _as_tensor(inputs)
         ctx = get_ctx()
         if inputs.ndim != 2:
             raise ValueError(f"softmax expects a 2-D (batch, classes) input, got shape {inputs.shape}")
         self.inputs = inputs
+        if self._fused_into_prev:
+            self.outputs = inputs
+            return inputs
         out = Tensor._empty(inputs.shape, _float_dtype(inputs))
         check(lib.okl_softmax_fwd(ctx.h, inputs._dptr(NCX), out._ptr_raw(), inputs.shape[0], inputs.shape[1]))
         self.outputs = out

@@ -81,6 +81,7 @@ class NeuralNetwork:
         self.fuse_activations = os.environ.get("OKL_FUSE", "1") != "0"
         self.skip_input_grad = os.environ.get("OKL_SKIP_INPUT_GRAD", "1") != "0"
         self.fuse_conv_pool = os.environ.get("OKL_FUSE_CONV_POOL", "1") != "0"
+        self.use_aux_lanes = os.environ.get("OKL_AUX_LANES", "1") != "0"
         self.stream_inputs = False          # keep the dataset on the host, copy each batch inside the step
         self.sync_loss_every_step = False   # read the loss back to the host after every step (end-to-end mode)
         self.last_step_losses = []
@@ -190,7 +191,7 @@ class NeuralNetwork:
                     ('pre_forward', 'post_forward', 'pre_backward', 'post_backward')))
 
     def _plan(self, fast: bool):
-        key = (fast, self.fuse_activations, self.skip_input_grad, self.fuse_conv_pool, tuple(id(l) for l in self.layers), get_ctx().nranks,
+        key = (fast, self.fuse_activations, self.skip_input_grad, self.fuse_conv_pool, self.use_aux_lanes, tuple(id(l) for l in self.layers), get_ctx().nranks,
                get_ctx().precision)
         if key == self._plan_key:
             return
@@ -198,7 +199,7 @@ class NeuralNetwork:
         ls = self.layers
         for l in ls:
             if isinstance(l, _ParamLayer):
-                l._fused_act, l._need_dx, l._dx_relu_mask = ACT_NONE, True, False
+                l._fused_act, l._need_dx, l._dx_relu_mask, l._aux_lane = ACT_NONE, True, False, 0
                 l._defer_update = fast or get_ctx().nranks > 1
             if isinstance(l, _ConvBase):
                 l._fused_pool = None
@@ -209,6 +210,8 @@ class NeuralNetwork:
             if isinstance(l, _Pool):
                 l._fused_relu_bwd = False
                 l._in_fused_block = False
+            if isinstance(l, SoftmaxActivationLayer):
+                l._fused_into_prev = False
         # layout planning: a convolution that feeds (through activations / pooling) a tensor-core-eligible convolution writes
         # its output channels-last, so no permutation is needed between them
         tc_mode = get_ctx().precision != _lib.FP32
@@ -224,10 +227,20 @@ class NeuralNetwork:
                         break
         if not fast:
             return
+        if self.use_aux_lanes:                            # weight-gradient leaves on alternating auxiliary streams
+            lane = 0
+            for l in ls:
+                if isinstance(l, _ParamLayer):
+                    l._aux_lane = 1 + lane % 2
+                    lane += 1
         if self.fuse_activations:
             for a, b in zip(ls, ls[1:]):
                 if isinstance(a, _ParamLayer) and isinstance(b, (ReLUActivationLayer, SigmoidActivationLayer)):
                     a._fused_act, b._fused_into_prev = b._act, True
+            for a, b in zip(ls, ls[1:]):                 # small Dense -> Softmax: softmax in the dense kernel's epilogue
+                if (isinstance(a, DenseLayer) and isinstance(b, SoftmaxActivationLayer) and a.weights.shape[1] <= 16 and
+                        a.weights.shape[0] * a.weights.shape[1] <= 12000):
+                    a._fused_act, b._fused_into_prev = _lib.ACT_SOFTMAX, True
             for a, r, b in zip(ls, ls[1:], ls[2:]):      # Param(+ReLU fused) -> Param: relu' applied in the second layer's dX epilogue
                 if (isinstance(a, _ParamLayer) and isinstance(r, ReLUActivationLayer) and r._fused_into_prev and
                         isinstance(b, _ParamLayer)):
