@@ -39,6 +39,30 @@ def _set_input_grad(inputs, dx):
         inputs._grad = prev + dx
 
 
+class _SubBuf:
+    """A slice of a larger device block (kept alive through ``owner``)."""
+    __slots__ = ("ptr", "nbytes", "owner")
+
+    def __init__(self, owner, off_bytes, nbytes):
+        self.ptr, self.nbytes, self.owner = owner.ptr + off_bytes, nbytes, owner
+
+
+class ParamArena:
+    """All parameter buckets of a small network in ONE device block each for params / accumulated gradients / step gradients:
+    the data-parallel exchange is a single all-reduce and the update a single kernel, whatever the number of layers."""
+
+    def __init__(self, buckets):
+        ctx = get_ctx()
+        self.buckets = list(buckets)
+        self.total = sum(b.total for b in self.buckets)
+        self.param, self.gacc, self.grad = (_DevBuf(ctx, self.total * 4) for _ in range(3))
+        check(lib.okl_memset(ctx.h, self.grad.ptr, 0, self.total * 4))
+        off = 0
+        for b in self.buckets:
+            b.rehome(self, off)
+            off += b.total
+
+
 class _ParamBucket:
     """All parameters of one layer in ONE device block (params | gacc | grads share the same offsets), so the layer's
     gradient exchange is one NCCL allreduce and its update is one kernel.
@@ -75,6 +99,22 @@ class _ParamBucket:
             self.gviews.append(Tensor._view(self.gacc, off * 4, t._shape, t._np_dtype))
         self.ready = True
 
+    arena = None
+
+    def rehome(self, arena, elem_off):
+        """Move this bucket's storage into ``arena`` at element offset ``elem_off`` (contents preserved)."""
+        ctx = get_ctx()
+        for t in self.tensors:
+            t._dptr(NCX)                                   # flush pending host-side assignments into the old location first
+        nb = self.total * 4
+        newp, newa, newg = (_SubBuf(buf, elem_off * 4, nb) for buf in (arena.param, arena.gacc, arena.grad))
+        check(lib.okl_d2d(ctx.h, newp.ptr, self.param.ptr, nb))
+        check(lib.okl_d2d(ctx.h, newa.ptr, self.gacc.ptr, nb))
+        self.param, self.gacc, self.grad, self.arena = newp, newa, newg, arena
+        for t, gv, off in zip(self.tensors, self.gviews, self.offs):
+            t._buf, t._off = self.param, off * 4
+            gv._buf, gv._off = self.gacc, off * 4
+
     def ptr(self, i):
         """Device pointer of parameter i (re-uploading if the user assigned ``.data``)."""
         return self.tensors[i]._dptr(NCX)
@@ -102,7 +142,7 @@ class _ParamBucket:
         """Exchange (data parallel) and apply the accumulated-gradient update for the whole bucket."""
         ctx = get_ctx()
         self._sync_user_grads()
-        if ctx.nranks > 1:
+        if ctx.nranks > 1 and not (deferred and self.arena is not None):     # an arena exchanges all its buckets at once
             check(lib.okl_allreduce_async(ctx.h, self.grad.ptr, self.total))
         if deferred:
             self._pending_lr = lr
@@ -138,27 +178,35 @@ class _ParamLayer:
 
 
 def apply_pending_updates(layers):
-    """All deferred bucket updates of a network in ONE kernel launch (after the data-parallel exchange has been joined)."""
+    """All deferred bucket updates of a network (after joining the auxiliary lanes and the data-parallel exchange): ONE all-reduce
+    and ONE kernel when the buckets live in a ParamArena, else one multi-tensor launch."""
     ctx = get_ctx()
     check(lib.okl_aux_join(ctx.h))
     bs = [l._bucket for l in layers if isinstance(l, _ParamLayer) and getattr(l._bucket, "_pending_lr", None) is not None]
     if not bs:
         return
-    if len(bs) == 1:
-        bs[0].apply(bs[0]._pending_lr)
-        return
-    if ctx.nranks > 1:
-        check(lib.okl_comm_wait(ctx.h))
     lrf, lrp = _lr_args(bs[0]._pending_lr)
-    n = len(bs)
     for b in bs:
         for t in b.tensors:
             t._dptr(NCX)
-    w = (C.c_void_p * n)(*[b.param.ptr for b in bs])
-    ga = (C.c_void_p * n)(*[b.gacc.ptr for b in bs])
-    g = (C.c_void_p * n)(*[b.grad.ptr for b in bs])
-    cnt = (C.c_size_t * n)(*[b.total for b in bs])
-    check(lib.okl_accum_update_multi(ctx.h, n, w, ga, g, cnt, lrf, lrp))
+    arena = bs[0].arena
+    if arena is not None and len(bs) == len(arena.buckets) and all(b.arena is arena for b in bs):
+        if ctx.nranks > 1:
+            check(lib.okl_allreduce_async(ctx.h, arena.grad.ptr, arena.total))
+            check(lib.okl_comm_wait(ctx.h))
+        check(lib.okl_accum_update(ctx.h, arena.param.ptr, arena.gacc.ptr, arena.grad.ptr, arena.total, lrf, lrp))
+    else:
+        if ctx.nranks > 1:
+            for b in bs:
+                if b.arena is not None:                    # partial arena: exchange bucket by bucket
+                    check(lib.okl_allreduce_async(ctx.h, b.grad.ptr, b.total))
+            check(lib.okl_comm_wait(ctx.h))
+        n = len(bs)
+        w = (C.c_void_p * n)(*[b.param.ptr for b in bs])
+        ga = (C.c_void_p * n)(*[b.gacc.ptr for b in bs])
+        g = (C.c_void_p * n)(*[b.grad.ptr for b in bs])
+        cnt = (C.c_size_t * n)(*[b.total for b in bs])
+        check(lib.okl_accum_update_multi(ctx.h, n, w, ga, g, cnt, lrf, lrp))
     for b in bs:
         b._stepped = True
         for t, gv in zip(b.tensors, b.gviews):

@@ -32,7 +32,7 @@ import numpy as np
 from . import _lib
 from ._lib import lib, check, get_ctx, NCX, ACT_NONE
 from .tensor import Tensor, _DevBuf, _numel, pinned_empty, pinned_base
-from .layers import (apply_pending_updates, _ParamLayer, _Activation, _Pool, ReLUActivationLayer, SigmoidActivationLayer, SoftmaxActivationLayer,
+from .layers import (apply_pending_updates, ParamArena, _ParamLayer, _Activation, _Pool, ReLUActivationLayer, SigmoidActivationLayer, SoftmaxActivationLayer,
                      MaxPoolingLayer, DenseLayer, Conv2DLayer,
                      _ConvBase)
 from .losses import CrossEntropyLoss, MSELoss, LossValue
@@ -82,6 +82,7 @@ class NeuralNetwork:
         self.skip_input_grad = os.environ.get("OKL_SKIP_INPUT_GRAD", "1") != "0"
         self.fuse_conv_pool = os.environ.get("OKL_FUSE_CONV_POOL", "1") != "0"
         self.use_aux_lanes = os.environ.get("OKL_AUX_LANES", "1") != "0"
+        self.arena_bytes = int(os.environ.get("OKL_ARENA_BYTES", str(64 << 20)))   # networks up to this size share one arena
         self.stream_inputs = False          # keep the dataset on the host, copy each batch inside the step
         self.sync_loss_every_step = False   # read the loss back to the host after every step (end-to-end mode)
         self.last_step_losses = []
@@ -197,6 +198,13 @@ class NeuralNetwork:
             return
         self._plan_key = key
         ls = self.layers
+        # small networks: one arena for every parameter bucket (single all-reduce, single update kernel)
+        pbs = [l._bucket for l in ls if isinstance(l, _ParamLayer)]
+        if len(pbs) > 1:
+            for b in pbs:
+                b.materialize()
+            if sum(b.total for b in pbs) * 4 <= self.arena_bytes and not (pbs[0].arena is not None and pbs[0].arena.buckets == pbs):
+                self._arena = ParamArena(pbs)
         for l in ls:
             if isinstance(l, _ParamLayer):
                 l._fused_act, l._need_dx, l._dx_relu_mask, l._aux_lane = ACT_NONE, True, False, 0
