@@ -388,10 +388,9 @@ def main():
     os.environ["OKL_PRECISION"] = args.precision
     import okrolearn_b200.okrolearn as okl
     from okrolearn_b200 import _lib
+    from okrolearn_b200 import dist
+    dist.init_data_parallel()
     ctx = okl.get_ctx()
-    if world > 1:
-        uid = rendezvous_unique_id(_lib, rank, world)
-        ctx.comm_init(uid, rank, world)
     np.random.seed(1234)                       # identical initial weights on every rank
     net = build_net(okl, name)
     logging.getLogger("NeuralNetwork").setLevel(logging.CRITICAL)      # NeuralNetwork() re-arms the logger at DEBUG

@@ -203,6 +203,13 @@ int okl_flush_l2(okl_ctx* ctx);
 int okl_comm_unique_id(void* out128);
 int okl_comm_init(okl_ctx* ctx, const void* id128, int rank, int nranks);
 int okl_comm_destroy(okl_ctx* ctx);
+/* Peer-memory path for small buckets: every rank allocates a symmetric buffer (okl_p2p_alloc), the 64-byte cudaIpc handles are
+ * exchanged (okl_p2p_export / okl_p2p_import for every peer), gradient storage is carved out of it (okl_p2p_suballoc, same call
+ * sequence on every rank); okl_allreduce_async on such memory is then ONE two-shot kernel over NVLink instead of an NCCL call. */
+int okl_p2p_alloc(okl_ctx* ctx, size_t bytes);
+int okl_p2p_export(okl_ctx* ctx, void* out64);
+int okl_p2p_import(okl_ctx* ctx, int rank, const void* handle64);
+int okl_p2p_suballoc(okl_ctx* ctx, size_t bytes, void** out);
 /* sum-allreduce `count` fp32 at p on the comm stream, ordered after everything enqueued so far on the compute stream */
 int okl_allreduce_async(okl_ctx* ctx, void* p, size_t count);
 /* make the compute stream wait for every allreduce issued so far */

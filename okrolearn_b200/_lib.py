@@ -101,6 +101,10 @@ SIGNATURES = {
     "okl_comm_unique_id": (_i, [_vp]),
     "okl_comm_init": (_i, [_vp, _vp, _i, _i]),
     "okl_comm_destroy": (_i, [_vp]),
+    "okl_p2p_alloc": (_i, [_vp, _sz]),
+    "okl_p2p_export": (_i, [_vp, _vp]),
+    "okl_p2p_import": (_i, [_vp, _i, _vp]),
+    "okl_p2p_suballoc": (_i, [_vp, _sz, _P(_vp)]),
     "okl_allreduce_async": (_i, [_vp, _vp, _sz]),
     "okl_comm_wait": (_i, [_vp]),
     "okl_allreduce_max_host": (_i, [_vp, _P(C.c_double)]),
@@ -147,6 +151,7 @@ class Context:
         self.epoch = 0            # bumped whenever device memory may have changed behind host mirrors (graph replay)
         self.capturing = False
         self.rank, self.nranks = 0, 1
+        self.p2p_ready = False
         sm, mem, cc = _i(), _sz(), _i()
         check(lib.okl_device_info(self.h, C.byref(sm), C.byref(mem), C.byref(cc)))
         self.sm_count, self.total_mem, self.cc = sm.value, mem.value, cc.value

@@ -144,3 +144,6 @@ bool okl_dense_small_ok(int M, int K, int N);
 int okl_dense_small_fwd(okl_ctx*, const float* X, const float* W, const float* b, float* Y, int M, int K, int N, int act);
 int okl_dense_small_bwd(okl_ctx*, const float* X, const float* W, const float* G, float* dX, float* dW, float* db, const float* relu_mask,
                         int M, int K, int N);
+// peer-memory (NVLink) all-reduce for small buckets: okl_p2p.cu
+bool okl_p2p_applicable(okl_ctx*, const void* p, size_t count);
+int okl_p2p_allreduce(okl_ctx*, void* p, size_t count);

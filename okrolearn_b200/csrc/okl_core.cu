@@ -615,6 +615,8 @@ extern "C" int okl_comm_destroy(okl_ctx* ctx) {
 extern "C" int okl_allreduce_async(okl_ctx* ctx, void* p, size_t count) {
   OKL_REQUIRE(ctx && p, "NULL argument");
   if (ctx->nranks == 1 || count == 0) return OKL_OK;
+  if (okl_p2p_applicable(ctx, p, count))            // small bucket inside the symmetric buffer: one peer-memory kernel, no NCCL
+    return okl_p2p_allreduce(ctx, p, count);
   OKL_REQUIRE(ctx->nccl_comm, "okl_allreduce_async: communicator not initialised");
   // fork: comm stream waits for everything enqueued so far on the compute stream (works under capture too)
   OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));

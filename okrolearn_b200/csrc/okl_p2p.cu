@@ -1,0 +1,189 @@
+// Latency-optimised gradient all-reduce over NVLink peer memory (one process per GPU, one node).
+//
+// For the small gradient buckets of a CNN (a few MB) an NCCL all-reduce is dominated by launch / protocol latency, not by the
+// 900 GB/s links.  Here every rank owns a *symmetric* buffer (plain cudaMalloc, exported with cudaIpcGetMemHandle and mapped by all
+// peers through NVSwitch), the network's gradient arena lives inside it, and ONE kernel per step does a two-shot all-reduce
+// directly on peer memory:
+//     ready barrier  : each rank raises its flag in every peer's buffer (release.sys) and polls its OWN copy of the flags
+//     reduce-scatter : rank r sums slice r over all ranks' buffers in fixed rank order (bit-identical result on every rank) ...
+//     all-gather     : ... and stores the sum straight into slice r of every rank's buffer (128-bit remote stores)
+//     done barrier   : the last CTA of each rank raises the done flag everywhere; the kernel ends once all peers have done so
+// Sequence numbers live on the device (the kernel bumps them), so the kernel is replayable from a CUDA graph.  All spins are
+// bounded (trap after ~10 s) so a missing peer cannot wedge a GPU.
+#include "common.cuh"
+
+namespace {
+
+constexpr int P2P_MAX_RANKS = 8;
+constexpr size_t P2P_HDR_BYTES = 4096;      // flags + counters at the start of the symmetric buffer
+
+struct P2PHeader {                          // lives at the start of every rank's symmetric buffer
+  unsigned ready[P2P_MAX_RANKS];            // ready[p] = last sequence number for which rank p's gradients are complete
+  unsigned done[P2P_MAX_RANKS];             // done[p]  = last sequence number for which rank p has written its slice everywhere
+  unsigned seq;                             // sequence number of the last completed all-reduce on this rank
+  unsigned cta_count;                       // CTAs of the running kernel that have finished their writes
+};
+
+struct P2PPeers {
+  float* data[P2P_MAX_RANKS];               // data region of every rank (own rank included), same layout everywhere
+  P2PHeader* hdr[P2P_MAX_RANKS];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void spin_until(const unsigned* flag, unsigned target) {
+  const long long t0 = clock64();
+  while ((int)(ld_acquire_sys(flag) - target) < 0) {
+    if (clock64() - t0 > 20000000000LL) {
+      printf("okl p2p all-reduce: timed out waiting for a peer (flag %p target %u)\n", flag, target);
+      __trap();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PPeers peers, const int rank, const int nranks, const size_t off4,
+                                                           const size_t n4) {
+  P2PHeader* me = peers.hdr[rank];
+  const unsigned s = me->seq + 1;           // every CTA reads it before the last CTA bumps it at the very end
+  // ---- ready barrier: my gradients are complete (stream order); tell everyone, then wait for everyone
+  if (blockIdx.x == 0 && threadIdx.x < nranks) st_release_sys(&peers.hdr[threadIdx.x]->ready[rank], s);
+  if (threadIdx.x < nranks) spin_until(&me->ready[threadIdx.x], s);
+  __syncthreads();
+  // ---- reduce-scatter + all-gather on my slice, 128-bit accesses, fixed summation order
+  const size_t chunk = (n4 + nranks - 1) / nranks;
+  const size_t beg = (size_t)rank * chunk, end = min(n4, beg + chunk);
+  for (size_t i = beg + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < end; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v[P2P_MAX_RANKS];
+#pragma unroll
+    for (int p = 0; p < P2P_MAX_RANKS; p++)
+      if (p < nranks) v[p] = reinterpret_cast<const float4*>(peers.data[p])[off4 + i];
+    float4 a = v[0];
+#pragma unroll
+    for (int p = 1; p < P2P_MAX_RANKS; p++)
+      if (p < nranks) { a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w; }
+#pragma unroll
+    for (int p = 0; p < P2P_MAX_RANKS; p++)
+      if (p < nranks) reinterpret_cast<float4*>(peers.data[p])[off4 + i] = a;
+  }
+  // ---- done barrier
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int is_last;
+  if (threadIdx.x == 0) is_last = (atomicAdd(&me->cta_count, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) {
+    if (threadIdx.x < nranks) st_release_sys(&peers.hdr[threadIdx.x]->done[rank], s);
+    if (threadIdx.x < nranks) spin_until(&me->done[threadIdx.x], s);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      me->cta_count = 0;
+      me->seq = s;
+      __threadfence();
+    }
+  }
+}
+
+struct P2PState {
+  void* base = nullptr;                     // local symmetric buffer (header + data)
+  size_t bytes = 0, bump = 0;
+  void* peer_base[P2P_MAX_RANKS] = {};
+  bool imported[P2P_MAX_RANKS] = {};
+  int nimported = 0;
+};
+
+std::map<okl_ctx*, P2PState> g_p2p;
+
+}  // namespace
+
+// Allocate this rank's symmetric buffer (`bytes` of data) - call once, before okl_p2p_export.
+extern "C" int okl_p2p_alloc(okl_ctx* ctx, size_t bytes) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  P2PState& st = g_p2p[ctx];
+  OKL_REQUIRE(st.base == nullptr, "okl_p2p_alloc: already allocated");
+  OKL_REQUIRE(ctx->nranks <= P2P_MAX_RANKS, "okl_p2p: at most %d ranks", P2P_MAX_RANKS);
+  OKL_CHECK_CUDA(cudaSetDevice(ctx->device));
+  st.bytes = P2P_HDR_BYTES + ((bytes + 255) & ~size_t(255));
+  OKL_CHECK_CUDA(cudaMalloc(&st.base, st.bytes));
+  OKL_CHECK_CUDA(cudaMemset(st.base, 0, st.bytes));
+  OKL_CHECK_CUDA(cudaDeviceSynchronize());
+  st.peer_base[ctx->rank] = st.base;
+  st.imported[ctx->rank] = true;
+  st.nimported = 1;
+  return OKL_OK;
+}
+
+extern "C" int okl_p2p_export(okl_ctx* ctx, void* out64) {
+  OKL_REQUIRE(ctx && out64, "NULL argument");
+  P2PState& st = g_p2p[ctx];
+  OKL_REQUIRE(st.base, "okl_p2p_export: call okl_p2p_alloc first");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  OKL_CHECK_CUDA(cudaIpcGetMemHandle(&h, st.base));
+  memcpy(out64, &h, 64);
+  return OKL_OK;
+}
+
+extern "C" int okl_p2p_import(okl_ctx* ctx, int rank, const void* handle64) {
+  OKL_REQUIRE(ctx && handle64, "NULL argument");
+  P2PState& st = g_p2p[ctx];
+  OKL_REQUIRE(st.base, "okl_p2p_import: call okl_p2p_alloc first");
+  OKL_REQUIRE(rank >= 0 && rank < ctx->nranks && rank != ctx->rank, "okl_p2p_import: bad rank %d", rank);
+  if (st.imported[rank]) return OKL_OK;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  OKL_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  st.peer_base[rank] = p;
+  st.imported[rank] = true;
+  st.nimported++;
+  return OKL_OK;
+}
+
+// Sub-allocate from the local symmetric data region (same call sequence on every rank => same offsets everywhere).
+extern "C" int okl_p2p_suballoc(okl_ctx* ctx, size_t bytes, void** out) {
+  OKL_REQUIRE(ctx && out, "NULL argument");
+  P2PState& st = g_p2p[ctx];
+  OKL_REQUIRE(st.base, "okl_p2p_suballoc: no symmetric buffer");
+  size_t b = (bytes + 255) & ~size_t(255);
+  if (P2P_HDR_BYTES + st.bump + b > st.bytes) {
+    okl_set_error("okl_p2p_suballoc: symmetric buffer exhausted (%zu + %zu > %zu)", st.bump, b, st.bytes - P2P_HDR_BYTES);
+    return OKL_ERR_OOM;
+  }
+  *out = (char*)st.base + P2P_HDR_BYTES + st.bump;
+  st.bump += b;
+  return OKL_OK;
+}
+
+// 1 if [p, p + count floats) lies in the symmetric region, every peer is mapped and the peer-memory kernel applies.
+bool okl_p2p_applicable(okl_ctx* ctx, const void* p, size_t count) {
+  auto it = g_p2p.find(ctx);
+  if (it == g_p2p.end() || !it->second.base || it->second.nimported != ctx->nranks) return false;
+  const P2PState& st = it->second;
+  const char* lo = (const char*)st.base + P2P_HDR_BYTES;
+  const char* q = (const char*)p;
+  return q >= lo && q + count * 4 <= (const char*)st.base + st.bytes && ((q - lo) & 15) == 0 && (count & 3) == 0;
+}
+
+int okl_p2p_allreduce(okl_ctx* ctx, void* p, size_t count) {
+  P2PState& st = g_p2p[ctx];
+  P2PPeers peers;
+  memset(&peers, 0, sizeof(peers));
+  for (int r = 0; r < ctx->nranks; r++) {
+    peers.hdr[r] = (P2PHeader*)st.peer_base[r];
+    peers.data[r] = (float*)((char*)st.peer_base[r] + P2P_HDR_BYTES);
+  }
+  const size_t off4 = ((char*)p - ((char*)st.base + P2P_HDR_BYTES)) / 16, n4 = count / 4;
+  const size_t chunk = (n4 + ctx->nranks - 1) / ctx->nranks;
+  int grid = (int)((chunk + 511) / 512);
+  if (grid > 64) grid = 64;
+  if (grid < 1) grid = 1;
+  p2p_allreduce_kernel<<<grid, 512, 0, ctx->stream>>>(peers, ctx->rank, ctx->nranks, off4, n4);
+  OKL_LAUNCHED(ctx, "p2p_allreduce");
+  return OKL_OK;
+}

@@ -47,6 +47,13 @@ class _SubBuf:
         self.ptr, self.nbytes, self.owner = owner.ptr + off_bytes, nbytes, owner
 
 
+class _BorrowedPtr:
+    __slots__ = ("ptr", "nbytes")
+
+    def __init__(self, ptr, nbytes):
+        self.ptr, self.nbytes = ptr, nbytes
+
+
 class ParamArena:
     """All parameter buckets of a small network in ONE device block each for params / accumulated gradients / step gradients:
     the data-parallel exchange is a single all-reduce and the update a single kernel, whatever the number of layers."""
@@ -55,7 +62,15 @@ class ParamArena:
         ctx = get_ctx()
         self.buckets = list(buckets)
         self.total = sum(b.total for b in self.buckets)
-        self.param, self.gacc, self.grad = (_DevBuf(ctx, self.total * 4) for _ in range(3))
+        self.param, self.gacc = _DevBuf(ctx, self.total * 4), _DevBuf(ctx, self.total * 4)
+        self.grad = None
+        if ctx.nranks > 1 and getattr(ctx, "p2p_ready", False):
+            # gradients live in the rank's symmetric (peer-mapped) buffer: their all-reduce is one NVLink kernel
+            p = C.c_void_p()
+            if lib.okl_p2p_suballoc(ctx.h, self.total * 4, C.byref(p)) == 0:
+                self.grad = _BorrowedPtr(p.value, self.total * 4)
+        if self.grad is None:
+            self.grad = _DevBuf(ctx, self.total * 4)
         check(lib.okl_memset(ctx.h, self.grad.ptr, 0, self.total * 4))
         off = 0
         for b in self.buckets:

@@ -72,10 +72,9 @@ else:
     import logging
     import okrolearn_b200.okrolearn as okl
     from okrolearn_b200 import _lib
-    sys.path.insert(0, ROOT)
-    from bench import rendezvous_unique_id
+    from okrolearn_b200 import dist
+    dist.init_data_parallel()
     ctx = okl.get_ctx()
-    ctx.comm_init(rendezvous_unique_id(_lib, rank, world), rank, world)
     net = okl.NeuralNetwork()
     logging.getLogger("NeuralNetwork").setLevel(logging.CRITICAL)
     conv, d1, d2 = okl.Conv2DLayer(1, 4, 3), okl.DenseLayer(100, 16), okl.DenseLayer(16, 10)
@@ -92,7 +91,8 @@ else:
                                                                            (d1.weights.data, full.layers[4].W),
                                                                            (d2.weights.data, full.layers[6].W),
                                                                            (d1.biases.data, full.layers[4].b))]
-    res = {"w_err": max(errs), "local_mean_loss": float(losses[0]), "ref_mean_loss": float(np.mean(ref_losses))}
+    res = {"w_err": max(errs), "local_mean_loss": float(losses[0]), "ref_mean_loss": float(np.mean(ref_losses)),
+           "p2p": bool(ctx.p2p_ready)}
     ctx.sync()
 
 if rank == 0:

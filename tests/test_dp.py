@@ -39,8 +39,10 @@ def test_rendezvous_file_roundtrip(tmp_path, monkeypatch):
         Context = FakeCtx
     monkeypatch.setenv("MASTER_PORT", "45999")
     monkeypatch.setenv("TORCHELASTIC_RUN_ID", f"t{os.getpid()}")
-    a = bench.rendezvous_unique_id(FakeLib, 0, 2)
-    b = bench.rendezvous_unique_id(FakeLib, 1, 2)
+    from okrolearn_b200 import dist
+    monkeypatch.setattr(dist._lib, "Context", FakeCtx)
+    a = dist.exchange_unique_id(0, 2)
+    b = dist.exchange_unique_id(1, 2)
     assert a == b == bytes(range(128))
 
 
@@ -57,3 +59,9 @@ def test_dp_nccl_world2_matches_single_process_oracle():
         pytest.skip("needs 2 GPUs")
     res = run_workers("nccl", 2, 29543)
     assert res["w_err"] < 2e-5
+    os.environ["OKL_P2P"] = "0"                      # and once more with the NCCL exchange instead of the peer-memory kernel
+    try:
+        res2 = run_workers("nccl", 2, 29545)
+    finally:
+        del os.environ["OKL_P2P"]
+    assert res2["w_err"] < 2e-5 and not res2["p2p"]
