@@ -96,6 +96,13 @@ int okl_dense_bwd(okl_ctx* ctx, const void* X, const void* W, const void* G, voi
 /* dx_relu_mask (optional, shape of dX): dX is zeroed where mask <= 0 - the fused backward `g * (x > 0)` (okl.py:107) of a ReLU
  * that sits between the previous layer and this one, evaluated in the GEMM epilogue instead of a separate pass. */
 
+/* BF16 mode with caller-kept shadows: X16 / W16 / G16 are bf16 copies of the fp32 tensors (okl_to_bf16, or written by a producing
+ * kernel as Y16 / dX16), so the GEMMs read 2-byte operands without a per-call conversion; outputs stay fp32 (+ optional bf16). */
+int okl_to_bf16(okl_ctx* ctx, const void* src_f32, void* dst_bf16, size_t n);
+int okl_dense_fwd_bf16(okl_ctx* ctx, const void* X16, const void* W16, const void* b, void* Y, void* Y16, int M, int K, int N, int act);
+int okl_dense_bwd_bf16(okl_ctx* ctx, const void* X16, const void* W16, const void* G16, const void* G, void* dX, void* dX16, void* dW,
+                       void* db, int M, int K, int N, const void* dx_relu_mask);
+
 /* The tcgen05 GEMM the Dense products run on in TF32/BF16 mode, exposed for tests and benchmarks (reference: np.dot in
  * Tensor.dot, tensor.py:58).  D[M,N] (row-major, ldd) = act(A . B + bias[N]); A, B, D, bias are fp32 device tensors.
  *   a_mn = 0: A stored [M][K] (lda);  a_mn = 1: A stored [K][M] (lda)   -  b_mn = 0: B stored [N][K];  b_mn = 1: B stored [K][N]

@@ -64,6 +64,9 @@ SIGNATURES = {
     "okl_gather_rows": (_i, [_vp, _vp, _vp, _vp, _ll, _ll]),
     "okl_dense_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "okl_dense_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "okl_to_bf16": (_i, [_vp, _vp, _vp, _sz]),
+    "okl_dense_fwd_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    "okl_dense_bwd_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "okl_tc_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _i]),
     "okl_conv_out_extent": (_i, [_P(ConvDesc), _P(_i)]),
     "okl_conv_fprop": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp]),

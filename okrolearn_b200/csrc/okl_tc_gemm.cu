@@ -1016,3 +1016,42 @@ int okl_tc_dense_dw(okl_ctx* ctx, const float* X, const float* G, float* dW, int
   }
   return okl_tc_gemm_raw(ctx, 0, 1, 1, K, N, M, X, K, G, N, dW, N, nullptr, OKL_ACT_NONE, nullptr);
 }
+
+// ------------------------------------------------------------------------------------------------ BF16 operands kept by the caller
+// The Python layers keep a bf16 shadow next to every fp32 activation / weight tensor that feeds a GEMM (written by the producing
+// kernel's epilogue), so no operand is converted per call.
+extern "C" int okl_to_bf16(okl_ctx* ctx, const void* src_f32, void* dst_bf16, size_t n) {
+  OKL_REQUIRE(ctx && (n == 0 || (src_f32 && dst_bf16)), "NULL argument");
+  return okl_f32_to_bf16(ctx, (const float*)src_f32, dst_bf16, n);
+}
+
+extern "C" int okl_dense_fwd_bf16(okl_ctx* ctx, const void* X16, const void* W16, const void* b, void* Y, void* Y16, int M, int K, int N,
+                                  int act) {
+  OKL_REQUIRE(ctx && X16 && W16 && Y, "NULL argument");
+  OKL_REQUIRE(M >= 1 && K >= 64 && N >= 64 && K % 8 == 0 && N % 8 == 0, "okl_dense_fwd_bf16: unsupported shape M=%d K=%d N=%d", M, K, N);
+  OKL_REQUIRE(act >= OKL_ACT_NONE && act <= OKL_ACT_TANH, "bad activation %d", act);
+  return okl_tc_gemm_raw(ctx, 1, 0, 1, M, N, K, X16, K, W16, N, (float*)Y, N, (const float*)b, act, Y16);
+}
+
+// dW = X^T G, db = sum_rows G (from the fp32 G), dX = (G W^T) (* relu mask), dX16 = bf16 shadow of dX.  Any output may be NULL.
+extern "C" int okl_dense_bwd_bf16(okl_ctx* ctx, const void* X16, const void* W16, const void* G16, const void* G, void* dX, void* dX16,
+                                  void* dW, void* db, int M, int K, int N, const void* dx_relu_mask) {
+  OKL_REQUIRE(ctx && X16 && W16 && G16, "NULL argument");
+  OKL_REQUIRE(M >= 64 && K >= 64 && N >= 64 && K % 8 == 0 && N % 8 == 0 && M % 8 == 0, "okl_dense_bwd_bf16: unsupported shape M=%d K=%d N=%d", M,
+              K, N);
+  int s;
+  if (dW) {
+    s = okl_tc_gemm_raw(ctx, 1, 1, 1, K, N, M, X16, K, G16, N, (float*)dW, N, nullptr, OKL_ACT_NONE, nullptr);
+    if (s != OKL_OK) return s;
+  }
+  if (db) {
+    OKL_REQUIRE(G, "okl_dense_bwd_bf16: the fp32 gradient is needed for db");
+    s = okl_colsum(ctx, (const float*)G, (float*)db, M, N);
+    if (s != OKL_OK) return s;
+  }
+  if (dX) {
+    s = okl_tc_gemm_raw(ctx, 1, 0, 0, M, K, N, G16, N, W16, N, (float*)dX, K, nullptr, OKL_ACT_NONE, dX16, (const float*)dx_relu_mask);
+    if (s != OKL_OK) return s;
+  }
+  return OKL_OK;
+}

@@ -137,6 +137,10 @@ class _ParamBucket:
     def grad_ptr(self, i):
         return self.grad.ptr + self.offs[i] * 4
 
+    def ptr16(self, i):
+        """bf16 shadow of parameter i, refreshed when the fp32 master changed (after every update)."""
+        return self.tensors[i]._b16()
+
     def _sync_user_grads(self):
         """``layer.weights.grad = None`` / ``= ndarray`` by the user replaces the accumulator."""
         ctx = get_ctx()
@@ -251,8 +255,14 @@ class DenseLayer(_ParamLayer):
         self.inputs = inputs
         M = inputs.shape[0]
         out = Tensor._empty((M, N), np.float64)
-        check(lib.okl_dense_fwd(ctx.h, inputs._dptr(NCX), self._bucket.ptr(0), self._bucket.ptr(1), out._ptr_raw(), M, K, N,
-                                self._fused_act))
+        self._bf16_path = (ctx.precision == _lib.BF16 and M >= 64 and M % 8 == 0 and K >= 64 and N >= 64 and K % 8 == 0 and N % 8 == 0
+                           and self._fused_act <= ACT_TANH)
+        if self._bf16_path:                      # operands and result carry bf16 shadows: no per-call conversion
+            check(lib.okl_dense_fwd_bf16(ctx.h, inputs._b16(), self._bucket.ptr16(0), self._bucket.ptr(1), out._ptr_raw(),
+                                         out._new_b16(), M, K, N, self._fused_act))
+        else:
+            check(lib.okl_dense_fwd(ctx.h, inputs._dptr(NCX), self._bucket.ptr(0), self._bucket.ptr(1), out._ptr_raw(), M, K, N,
+                                    self._fused_act))
         self.outputs = out
         return out
 
@@ -268,6 +278,23 @@ class DenseLayer(_ParamLayer):
         b = self._bucket
         xp, gp, wp = self.inputs._dptr(NCX), dL_dout._dptr(NCX), b.ptr(0)
         mask = xp if (need_dx and self._dx_relu_mask) else None
+        if getattr(self, "_bf16_path", False) and ctx.precision == _lib.BF16:
+            x16, g16, w16 = self.inputs._b16(), dL_dout._b16(), b.ptr16(0)
+            dxp, dx16 = (dX._ptr_raw(), dX._new_b16()) if need_dx else (None, None)
+            aux = self._aux_lane and self._defer_update and need_dx
+            if aux:
+                check(lib.okl_aux_mark(ctx.h))
+            if need_dx:
+                check(lib.okl_dense_bwd_bf16(ctx.h, x16, w16, g16, gp, dxp, dx16, None, None, M, K, N, mask))
+            if aux:
+                check(lib.okl_aux_begin(ctx.h, self._aux_lane))
+            try:
+                check(lib.okl_dense_bwd_bf16(ctx.h, x16, w16, g16, gp, None, None, b.grad_ptr(0), b.grad_ptr(1), M, K, N, None))
+                b.step(lr, True if aux else self._defer_update)
+            finally:
+                if aux:
+                    check(lib.okl_aux_end(ctx.h))
+            return dX
         if self._aux_lane and self._defer_update and need_dx:
             check(lib.okl_aux_mark(ctx.h))
             check(lib.okl_dense_bwd(ctx.h, xp, wp, gp, dX._ptr_raw(), None, None, M, K, N, mask))     # critical path first
