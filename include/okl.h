@@ -133,6 +133,13 @@ int okl_conv_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* g, const vo
 /* dW = x (*) g ; db = sum_{n,pos} g            okl.py:729-735 / 865-866,870 / 1013-1016,991 (+ repairs R1,R2); db may be NULL */
 int okl_conv_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* g, void* dW, void* db);
 
+/* BF16 shadows for the implicit-GEMM convolution (channels-last, unit stride, C and O multiples of 64): activations / gradients are read
+ * through their bf16 shadows, results are written as fp32 + bf16 */
+int okl_conv_bf16_supported(okl_ctx* ctx, const okl_conv_desc* d);
+int okl_conv_fprop_bf16(okl_ctx* ctx, const okl_conv_desc* d, const void* x16, const void* W, const void* b, void* y, void* y16);
+int okl_conv_dgrad_bf16(okl_ctx* ctx, const okl_conv_desc* d, const void* g16, const void* W, void* dx, void* dx16, const void* dx_relu_mask);
+int okl_conv_wgrad_bf16(okl_ctx* ctx, const okl_conv_desc* d, const void* x16, const void* g16, const void* g, void* dW, void* db);
+
 /* Fused first block Conv2D(3x3, stride 1) -> ReLU -> MaxPool(2,2) for tiny input channel counts (C = 1 or 3): the un-pooled
  * activation is never written.  fwd writes the pooled maxima (N,O,PH,PW) and a 4-bit mask per pooled element (which of the four
  * window positions attain the maximum and are > 0 = the combined backward of okl.py:107 and okl.py:1757-1766 with the reference's

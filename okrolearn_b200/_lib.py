@@ -67,6 +67,10 @@ SIGNATURES = {
     "okl_to_bf16": (_i, [_vp, _vp, _vp, _sz]),
     "okl_dense_fwd_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "okl_dense_bwd_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "okl_conv_bf16_supported": (_i, [_vp, _P(ConvDesc)]),
+    "okl_conv_fprop_bf16": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
+    "okl_conv_dgrad_bf16": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
+    "okl_conv_wgrad_bf16": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "okl_tc_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _i]),
     "okl_conv_out_extent": (_i, [_P(ConvDesc), _P(_i)]),
     "okl_conv_fprop": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp]),

@@ -758,17 +758,20 @@ typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 4-D fp32 tensor map over a channels-last activation tensor (N, H, W, C): dims {C, W, H, N}
-int make_map_nhwc(CUtensorMap* map, const void* base, int C, int W, int H, int N, int box_c, int box_w, int box_h, int box_n, bool atom32) {
+int make_map_nhwc(CUtensorMap* map, const void* base, int C, int W, int H, int N, int box_c, int box_w, int box_h, int box_n, bool atom32,
+                  int kind = 0) {
+  const cuuint64_t es = kind == 0 ? 4 : 2;
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     okl_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
     return OKL_ERR_CUDA;
   }
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t gstride[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint64_t gstride[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
   cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(map, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim,
+                  gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -815,9 +818,10 @@ int conv_shape(const okl_conv_desc* d, ConvShape& s) {
 int pick_bn(int n) { return n >= 256 && n % 256 == 0 ? 256 : (n >= 128 && n % 128 == 0 ? 128 : (n >= 64 && n % 64 == 0 ? 64 : 32)); }
 
 // y[N,OH,OW,Oc] = act(conv(x[N,H,W,Cc], W2[Oc][T*Cc]) + bias)  with padding (ph, pw), stride 1, everything channels-last
-int conv_igemm_fprop(okl_ctx* ctx, const float* x, int N, int H, int W, int Cc, const float* W2, int Oc, int KH, int KW, int ph, int pw,
-                     int OH, int OW, const float* bias, int act, float* y, const float* mask = nullptr) {
+int conv_igemm_fprop(okl_ctx* ctx, const void* x, int N, int H, int W, int Cc, const void* W2, int Oc, int KH, int KW, int ph, int pw,
+                     int OH, int OW, const float* bias, int act, float* y, const float* mask = nullptr, int kind = 0, void* y16 = nullptr) {
   const int T = KH * KW;
+  const int bkc = kind == 0 ? 32 : 64;                  // channels per k-block (one 128-byte swizzle row)
   int TW, TH, TN;
   pick_tile(OH, OW, TC_BM, TW, TH, TN);
   int bn = Oc >= 256 ? 256 : (Oc > 64 ? 128 : (Oc > 32 ? 64 : 32));
@@ -825,20 +829,28 @@ int conv_igemm_fprop(okl_ctx* ctx, const float* x, int N, int H, int W, int Cc, 
   long long tiles_m = (long long)tiles_w * tiles_h * tiles_ng;
   while (bn > 64 && tiles_m * ((Oc + bn - 1) / bn) < ctx->sm_count) bn >>= 1;     // more, smaller tiles when the grid would not fill the chip
   CUtensorMap ta, tb;
-  int s = make_map_nhwc(&ta, x, Cc, W, H, N, 32, TW, TH, TN, false);
+  int s = make_map_nhwc(&ta, x, Cc, W, H, N, bkc, TW, TH, TN, false, kind);
   if (s != OKL_OK) return s;
-  s = make_map_2d(&tb, 0, W2, (uint64_t)T * Cc, (uint64_t)Oc, (uint64_t)T * Cc, 32, bn);
+  s = make_map_2d(&tb, kind, W2, (uint64_t)T * Cc, (uint64_t)Oc, (uint64_t)T * Cc, bkc, bn);
   if (s != OKL_OK) return s;
   TcGemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = N * OH * OW; p.N = Oc; p.K = T * Cc;
   p.tiles_m = (int)tiles_m; p.tiles_n = (Oc + bn - 1) / bn; p.splits = 1;
-  p.kb_total = T * (Cc / 32); p.kb_per_split = p.kb_total;
-  p.D = y; p.ldd = Oc; p.bias = bias; p.act = act; p.mask = mask;
+  p.kb_total = T * (Cc / bkc); p.kb_per_split = p.kb_total;
+  p.D = y; p.ldd = Oc; p.bias = bias; p.act = act; p.mask = mask; p.D16 = (__nv_bfloat16*)y16;
   p.cv_TW = TW; p.cv_TH = TH; p.cv_TN = TN; p.cv_tw_sh = ilog2(TW); p.cv_th_sh = ilog2(TH);
   p.cv_tiles_w = tiles_w; p.cv_tiles_h = tiles_h; p.cv_OH = OH; p.cv_OW = OW; p.cv_NB = N;
-  p.cv_C = Cc; p.cv_cblocks = Cc / 32; p.cv_kw = KW; p.cv_ph = ph; p.cv_pw = pw;
+  p.cv_C = Cc; p.cv_cblocks = Cc / bkc; p.cv_kw = KW; p.cv_ph = ph; p.cv_pw = pw;
   p.dbg = nullptr;
+  if (kind == 1) {
+    switch (bn) {
+      case 32: return launch_cfg<1, false, false, 32, 1>(ctx, ta, tb, p);
+      case 64: return launch_cfg<1, false, false, 64, 1>(ctx, ta, tb, p);
+      case 128: return launch_cfg<1, false, false, 128, 1>(ctx, ta, tb, p);
+      default: return launch_cfg<1, false, false, 256, 1>(ctx, ta, tb, p);
+    }
+  }
   switch (bn) {
     case 32: return launch_cfg<0, false, false, 32, 1>(ctx, ta, tb, p);
     case 64: return launch_cfg<0, false, false, 64, 1>(ctx, ta, tb, p);
@@ -1052,6 +1064,130 @@ extern "C" int okl_dense_bwd_bf16(okl_ctx* ctx, const void* X16, const void* W16
   if (dX) {
     s = okl_tc_gemm_raw(ctx, 1, 0, 0, M, K, N, G16, N, W16, N, (float*)dX, K, nullptr, OKL_ACT_NONE, dX16, (const float*)dx_relu_mask);
     if (s != OKL_OK) return s;
+  }
+  return OKL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ BF16 implicit-GEMM convolution
+namespace {
+// W2_16[o][tap][c] = bf16(W[o][c][tap])  and  Wf_16[c][tap][o] = bf16(W[o][c][T-1-tap])
+__global__ void filters_to_bf16_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int O, int C, int T, int flip) {
+  const size_t total = (size_t)O * C * T;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    if (!flip) {
+      const int c = (int)(i % C);
+      const size_t r = i / C;
+      const int t = (int)(r % T), o = (int)(r / T);
+      out[i] = __float2bfloat16(W[((size_t)o * C + c) * T + t]);
+    } else {
+      const int o = (int)(i % O);
+      const size_t r = i / O;
+      const int t = (int)(r % T), c = (int)(r / T);
+      out[i] = __float2bfloat16(W[((size_t)o * C + c) * T + (T - 1 - t)]);
+    }
+  }
+}
+}  // namespace
+
+extern "C" int okl_conv_bf16_supported(okl_ctx* ctx, const okl_conv_desc* d) {
+  if (!ctx || !d || !okl_tc_conv_supported(ctx, d)) return 0;
+  return (d->C % 64 == 0 && d->O % 64 == 0) ? 1 : 0;
+}
+
+// x16 / y16 / g16 / dx16 are channels-last bf16 shadows of the fp32 tensors; filters stay fp32 masters (converted per call: tiny)
+extern "C" int okl_conv_fprop_bf16(okl_ctx* ctx, const okl_conv_desc* d, const void* x16, const void* W, const void* b, void* y, void* y16) {
+  OKL_REQUIRE(ctx && d && x16 && W && y, "NULL argument");
+  OKL_REQUIRE(okl_conv_bf16_supported(ctx, d), "okl_conv_fprop_bf16: unsupported shape / layout");
+  ConvShape s;
+  conv_shape(d, s);
+  const int T = s.KH * s.KW;
+  Scratch w2(ctx);
+  int st = w2.alloc((size_t)s.O * T * s.C * 2);
+  if (st != OKL_OK) return st;
+  filters_to_bf16_kernel<<<okl_grid_1d(ctx, (size_t)s.O * T * s.C, 256), 256, 0, ctx->stream>>>((const float*)W, (__nv_bfloat16*)w2.p, s.O, s.C, T, 0);
+  OKL_LAUNCHED(ctx, "filters_to_bf16");
+  return conv_igemm_fprop(ctx, x16, s.N, s.H, s.W, s.C, w2.p, s.O, s.KH, s.KW, s.PH, s.PW, s.OH, s.OW, (const float*)b, d->act, (float*)y,
+                          nullptr, 1, y16);
+}
+
+extern "C" int okl_conv_dgrad_bf16(okl_ctx* ctx, const okl_conv_desc* d, const void* g16, const void* W, void* dx, void* dx16,
+                                   const void* dx_relu_mask) {
+  OKL_REQUIRE(ctx && d && g16 && W && dx, "NULL argument");
+  OKL_REQUIRE(okl_conv_bf16_supported(ctx, d), "okl_conv_dgrad_bf16: unsupported shape / layout");
+  ConvShape s;
+  conv_shape(d, s);
+  const int T = s.KH * s.KW;
+  Scratch wf(ctx);
+  int st = wf.alloc((size_t)s.O * T * s.C * 2);
+  if (st != OKL_OK) return st;
+  filters_to_bf16_kernel<<<okl_grid_1d(ctx, (size_t)s.O * T * s.C, 256), 256, 0, ctx->stream>>>((const float*)W, (__nv_bfloat16*)wf.p, s.O, s.C, T, 1);
+  OKL_LAUNCHED(ctx, "filters_to_bf16");
+  return conv_igemm_fprop(ctx, g16, s.N, s.OH, s.OW, s.O, wf.p, s.C, s.KH, s.KW, s.KH - 1 - s.PH, s.KW - 1 - s.PW, s.H, s.W, nullptr,
+                          OKL_ACT_NONE, (float*)dx, (const float*)dx_relu_mask, 1, dx16);
+}
+
+extern "C" int okl_conv_wgrad_bf16(okl_ctx* ctx, const okl_conv_desc* d, const void* x16, const void* g16, const void* g, void* dW, void* db) {
+  OKL_REQUIRE(ctx && d && x16 && g16, "NULL argument");
+  OKL_REQUIRE(okl_conv_bf16_supported(ctx, d), "okl_conv_wgrad_bf16: unsupported shape / layout");
+  ConvShape s;
+  conv_shape(d, s);
+  const int T = s.KH * s.KW;
+  int st;
+  if (dW) {
+    const int M = s.O, N = T * s.C;
+    int TW, TH, TN;
+    pick_tile(s.OH, s.OW, 64, TW, TH, TN);                              // 64 pixels = one bf16 k-block
+    const int tiles_w = (s.OW + TW - 1) / TW, tiles_h = (s.OH + TH - 1) / TH, tiles_ng = (s.N + TN - 1) / TN;
+    const int kb_total = tiles_w * tiles_h * tiles_ng;
+    const int bn = pick_bn(s.C) < 64 ? 64 : pick_bn(s.C);
+    const int tiles_m = (M + TC_BM - 1) / TC_BM, tiles_n = N / bn;
+    Scratch dw2(ctx);
+    st = dw2.alloc((size_t)M * N * sizeof(float));
+    if (st != OKL_OK) return st;
+    CUtensorMap ta, tb;
+    st = make_map_nhwc(&ta, g16, s.O, s.OW, s.OH, s.N, 64, TW, TH, TN, false, 1);
+    if (st != OKL_OK) return st;
+    st = make_map_nhwc(&tb, x16, s.C, s.W, s.H, s.N, 64, TW, TH, TN, false, 1);
+    if (st != OKL_OK) return st;
+    TcGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.N = N; p.K = kb_total * 64;
+    p.tiles_m = tiles_m; p.tiles_n = tiles_n;
+    long long tiles = (long long)tiles_m * tiles_n;
+    int splits = (int)(ctx->sm_count / tiles);
+    if (splits > kb_total / 4) splits = kb_total / 4;
+    if (splits > 32) splits = 32;
+    if (splits < 1) splits = 1;
+    p.kb_total = kb_total; p.kb_per_split = (kb_total + splits - 1) / splits;
+    p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.D = (float*)dw2.p; p.ldd = N;
+    if (p.splits > 1) {
+      st = okl_ensure_workspace(ctx, (size_t)p.splits * M * N * sizeof(float));
+      if (st != OKL_OK) return st;
+      p.ws = (float*)ctx->workspace;
+      if (!ctx->tile_counters) {
+        OKL_CHECK_CUDA(cudaMalloc(&ctx->tile_counters, 4096 * sizeof(int)));
+        OKL_CHECK_CUDA(cudaMemsetAsync(ctx->tile_counters, 0, 4096 * sizeof(int), ctx->stream));
+      }
+      OKL_REQUIRE(tiles <= 2048, "conv wgrad: too many tiles for split-K");
+      p.counters = ctx->tile_counters;
+    }
+    p.cv_TW = TW; p.cv_TH = TH; p.cv_TN = TN; p.cv_tw_sh = ilog2(TW); p.cv_th_sh = ilog2(TH);
+    p.cv_tiles_w = tiles_w; p.cv_tiles_h = tiles_h; p.cv_OH = s.OH; p.cv_OW = s.OW; p.cv_NB = s.N;
+    p.cv_C = s.C; p.cv_cblocks = s.C / 64; p.cv_kw = s.KW; p.cv_ph = s.PH; p.cv_pw = s.PW;
+    switch (bn) {
+      case 64: st = launch_cfg<1, true, true, 64, 2>(ctx, ta, tb, p); break;
+      case 128: st = launch_cfg<1, true, true, 128, 2>(ctx, ta, tb, p); break;
+      default: st = launch_cfg<1, true, true, 256, 2>(ctx, ta, tb, p); break;
+    }
+    if (st != OKL_OK) return st;
+    st = okl_permute(ctx, dW, dw2.p, s.O, s.C, T, OKL_NXC);             // (O, T, C) -> (O, C, T)
+    if (st != OKL_OK) return st;
+  }
+  if (db) {
+    OKL_REQUIRE(g, "okl_conv_wgrad_bf16: the fp32 gradient is needed for db");
+    st = okl_channel_sum(ctx, (const float*)g, (float*)db, s.N, s.O, (long long)s.OH * s.OW, OKL_NXC);
+    if (st != OKL_OK) return st;
   }
   return OKL_OK;
 }

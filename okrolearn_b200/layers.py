@@ -410,7 +410,13 @@ class _ConvBase(_ParamLayer):
             yl = getattr(self, "_out_layout", NCX)
         d, oe = self._desc(inputs.shape, xl, yl, self._fused_act)
         out = Tensor._empty((inputs.shape[0], self.out_channels) + oe, self._np_dtype, layout=yl)
-        check(lib.okl_conv_fprop(ctx.h, C.byref(d), inputs._dptr(xl), self._bucket.ptr(0), self._bucket.ptr(1), out._ptr_raw()))
+        self._bf16_path = bool(ctx.precision == _lib.BF16 and xl == NXC and yl == NXC and inputs.shape[0] > 0 and
+                               lib.okl_conv_bf16_supported(ctx.h, C.byref(d)))
+        if self._bf16_path:                      # activations carry channels-last bf16 shadows: 2-byte operands, no conversions
+            check(lib.okl_conv_fprop_bf16(ctx.h, C.byref(d), inputs._b16(NXC), self._bucket.ptr(0), self._bucket.ptr(1), out._ptr_raw(),
+                                          out._new_b16()))
+        else:
+            check(lib.okl_conv_fprop(ctx.h, C.byref(d), inputs._dptr(xl), self._bucket.ptr(0), self._bucket.ptr(1), out._ptr_raw()))
         self._fwd_layouts = (xl, yl)
         return out
 
@@ -428,17 +434,26 @@ class _ConvBase(_ParamLayer):
         g, xp, wp = dL_dout._dptr(yl), x._dptr(xl), b.ptr(0)
         need_dx = getattr(self, "_need_dx", True)
         aux = self._aux_lane and self._defer_update and need_dx
+        b16 = getattr(self, "_bf16_path", False) and ctx.precision == _lib.BF16
+        if b16:
+            x16, g16 = x._b16(NXC), dL_dout._b16(NXC)
         dX = None
         if need_dx:
             if aux:
                 check(lib.okl_aux_mark(ctx.h))
             dX = Tensor._empty(x.shape, self._dx_dtype(x), layout=xl)
-            check(lib.okl_conv_dgrad(ctx.h, C.byref(d), g, wp, dX._ptr_raw(),              # critical path first; pre-update filters
-                                     xp if self._dx_relu_mask else None))
+            mask = xp if self._dx_relu_mask else None
+            if b16:
+                check(lib.okl_conv_dgrad_bf16(ctx.h, C.byref(d), g16, wp, dX._ptr_raw(), dX._new_b16(), mask))
+            else:
+                check(lib.okl_conv_dgrad(ctx.h, C.byref(d), g, wp, dX._ptr_raw(), mask))   # critical path first; pre-update filters
         if aux:
             check(lib.okl_aux_begin(ctx.h, self._aux_lane))          # dW, db (+ their all-reduce) are leaves: own lane
         try:
-            check(lib.okl_conv_wgrad(ctx.h, C.byref(d), xp, g, b.grad_ptr(0), b.grad_ptr(1)))
+            if b16:
+                check(lib.okl_conv_wgrad_bf16(ctx.h, C.byref(d), x16, g16, g, b.grad_ptr(0), b.grad_ptr(1)))
+            else:
+                check(lib.okl_conv_wgrad(ctx.h, C.byref(d), xp, g, b.grad_ptr(0), b.grad_ptr(1)))
             b.step(lr, True if aux else self._defer_update)
         finally:
             if aux:

@@ -293,22 +293,23 @@ class Tensor:
             self._relayout(layout)
         return self._ptr_raw()
 
-    def _b16(self):
-        """Device pointer of an up-to-date bf16 copy of this tensor (reference element order); converted on demand, or supplied
-        by the kernel that produced the tensor (``_set_b16``)."""
+    def _b16(self, layout=NCX):
+        """Device pointer of an up-to-date bf16 copy of this tensor in ``layout``; converted on demand, or supplied by the kernel
+        that produced the tensor (``_new_b16``)."""
         ctx = get_ctx()
-        src = self._dptr(NCX)
-        if getattr(self, "_bf16", None) is None or self._bf16_ver != self._dev_ver or self._bf16.nbytes < self.size * 2:
+        src = self._dptr(layout)
+        if (getattr(self, "_bf16", None) is None or self._bf16_ver != (self._dev_ver, self._layout) or
+                self._bf16.nbytes < self.size * 2):
             if getattr(self, "_bf16", None) is None or self._bf16.nbytes < self.size * 2:
                 self._bf16 = _DevBuf(ctx, max(self.size, 1) * 2)
             check(lib.okl_to_bf16(ctx.h, src, self._bf16.ptr, self.size))
-            self._bf16_ver = self._dev_ver
+            self._bf16_ver = (self._dev_ver, self._layout)
         return self._bf16.ptr
 
     def _new_b16(self):
         """Fresh bf16 shadow buffer that the producing kernel fills together with the fp32 data."""
         self._bf16 = _DevBuf(get_ctx(), max(self.size, 1) * 2)
-        self._bf16_ver = self._dev_ver
+        self._bf16_ver = (self._dev_ver, self._layout)
         return self._bf16.ptr
 
     def _relayout(self, layout):

@@ -158,3 +158,32 @@ def test_cifar_block_channels_last_pipeline(okl):
         assert rel_err(d.weights.data, on.layers[6].W) < 5e-3
     finally:
         okl.set_precision("fp32")
+
+
+@pytest.mark.parametrize("nd,N,C,sp,Oc,k,p", [(2, 8, 64, (32, 32), 64, 3, 1), (2, 4, 64, (16, 16), 128, 3, 1), (2, 6, 128, (8, 8), 256, 3, 1),
+                                              (2, 3, 64, (13, 11), 64, 3, 0), (1, 4, 64, (256,), 64, 3, 1)])
+def test_conv_implicit_gemm_bf16(okl, nd, N, C, sp, Oc, k, p):
+    """BF16 implicit-GEMM convolution with channels-last bf16 shadows vs the fp64 oracle (north_star tolerance 2e-2)."""
+    okl.set_precision("bf16")
+    try:
+        rng = np.random.default_rng(N * 100 + C + Oc)
+        kt = O._tup(k, nd)
+        x = rng.standard_normal((N, C) + sp).astype(np.float32)
+        W = rng.standard_normal((Oc, C) + kt) * 0.1
+        b = rng.standard_normal((Oc, 1)) * 0.1
+        lay = okl.Conv1DLayer(C, Oc, kt[0], 1, p) if nd == 1 else okl.Conv2DLayer(C, Oc, kt, 1, p)
+        (lay.weights if nd == 1 else lay.filters).data = W.copy()
+        lay.biases.data = b.copy()
+        y = lay.forward(okl.Tensor(x))
+        assert lay._bf16_path
+        x64 = x.astype(np.float64)
+        yo = O.conv_forward_fast(x64, W, b, 1, p, dtype=np.float64)
+        assert rel_err(y.data, yo) < 1.5e-2
+        g = rng.standard_normal(yo.shape).astype(np.float32)
+        dX = lay.backward(okl.Tensor(g), 0.05)
+        dW, db, dXo = O.conv_backward_fast(x64, W, g.astype(np.float64), 1, p)
+        Wt = lay.weights if nd == 1 else lay.filters
+        assert rel_err(dX.data, dXo) < 1.5e-2
+        assert rel_err(Wt.grad, dW) < 1.5e-2 and rel_err(lay.biases.grad, db) < 1e-5
+    finally:
+        okl.set_precision("fp32")
