@@ -22,7 +22,7 @@
 namespace {
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;        // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -213,7 +213,7 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue staging*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 16 * 36 * 4 /*epilogue staging*/;
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -246,7 +246,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);      // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], 8);      // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -357,56 +357,92 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===================================================================== epilogue (warps 4..7 <-> TMEM lanes 0..127)
-    const int q = warp & 3;
+    // ===================================================================== epilogue: 8 warps (4..11).  Warp w serves TMEM lanes
+    // 32*(w&3)..+31 (hardware lane partition) and every second 32-column chunk (half = (w-4)>>2), so two warps per lane quarter keep
+    // twice as many TMEM loads / global stores in flight; everything that does not depend on the accumulator (bias, row -> pixel
+    // mapping) is fetched BEFORE waiting for it.
+    const int q = warp & 3, half = (warp - 4) >> 2;
     int acc = 0;
+    int dbg_tile = 0;
     uint32_t acc_phase = 0;
     const bool vec_ok = (p.splits > 1) ? ((p.N & 3) == 0) : ((p.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
+    const bool vec16_ok = p.D16 && (p.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(p.D16) & 7) == 0;
+    float* stg = stage_base + (warp - 4) * (16 * 36);
+    const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+    constexpr int NCH = BN / 32;                     // 32-column chunks per tile
+    constexpr int MYCH = (NCH + 1) / 2;              // chunks this warp may own
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int split = w / (p.tiles_m * p.tiles_n);
       const int t = w - split * (p.tiles_m * p.tiles_n);
       const int tm = t % p.tiles_m, tn = t / p.tiles_m;
       const int n0 = tn * BN;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      if (p.dbg && threadIdx.x == 128) p.dbg[blockIdx.x * 8 + 3] = gtime();
-      // TMEM -> registers -> per-warp smem staging (padded rows, conflict-free 128-bit accesses) -> global, so that every
-      // store instruction writes four full 128-byte row segments instead of 32 scattered 16-byte pieces.
-      float* stg = stage_base + (warp - 4) * (32 * 36);
       const int m_base = tm * TC_BM + q * 32;
-      const int c4 = (lane & 7) * 4, rsub = lane >> 3;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
-        tmem_ld_wait();
+      // ---- accumulator-independent prefetch: bias values of my columns, output row of each of my 8 row slots
+      float bz[MYCH][4];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(stg + lane * 36 + j) =
-              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        __syncwarp();
-        const int nn = n0 + c + c4;
-        float bz[4] = {0.f, 0.f, 0.f, 0.f};
-        if (p.splits == 1 && p.bias) {
+      for (int ci = 0; ci < MYCH; ci++) {
+        const int nn = n0 + (half + 2 * ci) * 32 + c4;
 #pragma unroll
-          for (int e = 0; e < 4; e++)
-            if (nn + e < p.N) bz[e] = __ldg(p.bias + nn + e);
-        }
+        for (int e = 0; e < 4; e++) bz[ci][e] = (p.splits == 1 && p.bias && half + 2 * ci < NCH && nn + e < p.N) ? __ldg(p.bias + nn + e) : 0.f;
+      }
+      int rowm[8];
+      if (MODE == 1) {
+        const int wt = tm % p.cv_tiles_w, r2 = tm / p.cv_tiles_w;
+        const int ht = r2 % p.cv_tiles_h, ng = r2 / p.cv_tiles_h;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-          const int r = 4 * i + rsub;
-          int mm = m_base + r;
-          float4 o = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
-          if (MODE == 1) {
-            // tile row -> (image, h, w) of the channels-last output; rows outside the image are dropped
-            const int tr = q * 32 + r;
-            const int wt = tm % p.cv_tiles_w, r2 = tm / p.cv_tiles_w;
-            const int ht = r2 % p.cv_tiles_h, ng = r2 / p.cv_tiles_h;
-            const int ww = wt * p.cv_TW + (tr & (p.cv_TW - 1));
-            const int hh = ht * p.cv_TH + ((tr >> p.cv_tw_sh) & (p.cv_TH - 1));
-            const int ni = ng * p.cv_TN + (tr >> (p.cv_tw_sh + p.cv_th_sh));
-            mm = (ww < p.cv_OW && hh < p.cv_OH && ni < p.cv_NB) ? (ni * p.cv_OH + hh) * p.cv_OW + ww : p.M;
+          const int tr = q * 32 + 4 * i + rsub;      // tile row -> (image, h, w) of the channels-last output
+          const int ww = wt * p.cv_TW + (tr & (p.cv_TW - 1));
+          const int hh = ht * p.cv_TH + ((tr >> p.cv_tw_sh) & (p.cv_TH - 1));
+          const int ni = ng * p.cv_TN + (tr >> (p.cv_tw_sh + p.cv_th_sh));
+          rowm[i] = (ww < p.cv_OW && hh < p.cv_OH && ni < p.cv_NB) ? (ni * p.cv_OH + hh) * p.cv_OW + ww : p.M;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) rowm[i] = m_base + 4 * i + rsub;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      if (p.dbg && threadIdx.x == 128) {
+        p.dbg[blockIdx.x * 8 + 3] = gtime();
+        if (blockIdx.x == 0 && dbg_tile < 24) p.dbg[148 * 8 + 2 * dbg_tile] = gtime();
+      }
+      // TMEM -> registers -> per-warp smem staging (padded rows, conflict-free 128-bit accesses) -> global: every store instruction
+      // writes four full 128-byte row segments.
+#pragma unroll
+      for (int ci = 0; ci < MYCH; ci++) {
+        const int ch = half + 2 * ci;
+        if (ch >= NCH) break;
+        const int c = ch * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c), v);
+        const int nn = n0 + c + c4;
+        float4 mk[8];
+        if (p.mask && p.splits == 1) {               // relu mask of the 8 row slots: all loads in flight while TMEM drains
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            mk[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (rowm[i] < p.M && nn + 4 <= p.N && vec_ok)
+              mk[i] = __ldg(reinterpret_cast<const float4*>(p.mask + (size_t)rowm[i] * (size_t)p.ldd + nn));
           }
+        }
+        tmem_ld_wait();
+        // two passes of 16 rows through an 16 x 36-float staging tile per warp (keeps the 8 staging tiles within the smem budget)
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          if ((i & 3) == 0) {
+            __syncwarp();
+            if ((lane >> 4) == (i >> 2)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(stg + (lane & 15) * 36 + j) =
+                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            }
+            __syncwarp();
+          }
+          const int r = 4 * (i & 3) + rsub;
+          const int mm = rowm[i];
+          float4 o = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
           if (mm < p.M && nn < p.N) {
             if (p.splits > 1) {
               float* dst = p.ws + ((size_t)split * p.M + mm) * (size_t)p.N + nn;
@@ -418,14 +454,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   if (nn + e < p.N) dst[e] = f[e];
               }
             } else {
-              float f[4] = {o.x + bz[0], o.y + bz[1], o.z + bz[2], o.w + bz[3]};
+              float f[4] = {o.x + bz[ci][0], o.y + bz[ci][1], o.z + bz[ci][2], o.w + bz[ci][3]};
 #pragma unroll
               for (int e = 0; e < 4; e++) f[e] = act_apply(f[e], p.act);
               if (p.mask) {
-                const float* mk = p.mask + (size_t)mm * (size_t)p.ldd + nn;
+                if (vec_ok && nn + 4 <= p.N) {
+                  if (!(mk[i].x > 0.f)) f[0] = 0.f;
+                  if (!(mk[i].y > 0.f)) f[1] = 0.f;
+                  if (!(mk[i].z > 0.f)) f[2] = 0.f;
+                  if (!(mk[i].w > 0.f)) f[3] = 0.f;
+                } else {
+                  const float* mp = p.mask + (size_t)mm * (size_t)p.ldd + nn;
 #pragma unroll
-                for (int e = 0; e < 4; e++)
-                  if (nn + e < p.N && !(__ldg(mk + e) > 0.f)) f[e] = 0.f;
+                  for (int e = 0; e < 4; e++)
+                    if (nn + e < p.N && !(__ldg(mp + e) > 0.f)) f[e] = 0.f;
+                }
               }
               float* dst = p.D + (size_t)mm * (size_t)p.ldd + nn;
               if (vec_ok && nn + 4 <= p.N) *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
@@ -436,15 +479,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
               if (p.D16) {
                 __nv_bfloat16* d16 = p.D16 + (size_t)mm * (size_t)p.ldd + nn;
+                if (vec16_ok && nn + 4 <= p.N) {
+                  __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);
+                  uint2 pk;
+                  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                  *reinterpret_cast<uint2*>(d16) = pk;
+                } else {
 #pragma unroll
-                for (int e = 0; e < 4; e++)
-                  if (nn + e < p.N) d16[e] = __float2bfloat16(f[e]);
+                  for (int e = 0; e < 4; e++)
+                    if (nn + e < p.N) d16[e] = __float2bfloat16(f[e]);
+                }
               }
             }
           }
         }
         __syncwarp();
       }
+      if (p.dbg && threadIdx.x == 128 && blockIdx.x == 0 && dbg_tile < 24) p.dbg[148 * 8 + 2 * dbg_tile + 1] = gtime();
+      dbg_tile++;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -454,7 +507,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // when splits > 1), so the `splits` CTAs of a tile meet at a counter, then EACH reduces 1/splits of the tile over
         // all partials in fixed split order (deterministic) and applies bias + activation.
         __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (threadIdx.x == 128) {
           atomicAdd(p.counters + 2 * t, 1);
           const long long t0 = clock64();
@@ -466,17 +519,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         __threadfence();
         {
-          const int te = threadIdx.x - 128;
+          const int te = threadIdx.x - 128;           // 0..255
           const int m0 = tm * TC_BM;
           const size_t plane = (size_t)p.M * p.N;
           constexpr int C4 = BN / 4;
           constexpr int TOTAL4 = TC_BM * C4;
           const int chunk = (TOTAL4 + p.splits - 1) / p.splits;
           const int beg = split * chunk, end = min(TOTAL4, beg + chunk);
-          for (int idx = beg + te; idx < end; idx += 128) {
+          for (int idx = beg + te; idx < end; idx += 256) {
             const int r = idx / C4, c = (idx - r * C4) * 4;
             const int mm = m0 + r, nn = n0 + c;
             if (mm >= p.M || nn >= p.N) continue;
@@ -511,7 +564,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (threadIdx.x == 128) {
           const int old = atomicAdd(p.counters + 2 * t + 1, 1);
           if (old == p.splits - 1) {          // last CTA to leave: every reader is done, re-arm both counters
@@ -842,7 +895,7 @@ int conv_igemm_fprop(okl_ctx* ctx, const void* x, int N, int H, int W, int Cc, c
   p.cv_TW = TW; p.cv_TH = TH; p.cv_TN = TN; p.cv_tw_sh = ilog2(TW); p.cv_th_sh = ilog2(TH);
   p.cv_tiles_w = tiles_w; p.cv_tiles_h = tiles_h; p.cv_OH = OH; p.cv_OW = OW; p.cv_NB = N;
   p.cv_C = Cc; p.cv_cblocks = Cc / bkc; p.cv_kw = KW; p.cv_ph = ph; p.cv_pw = pw;
-  p.dbg = nullptr;
+  p.dbg = (unsigned long long*)ctx->tc_dbg;
   if (kind == 1) {
     switch (bn) {
       case 32: return launch_cfg<1, false, false, 32, 1>(ctx, ta, tb, p);
