@@ -129,6 +129,11 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def wait_first(self, timeout_s):
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout_s:
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
@@ -223,23 +228,23 @@ def time_cpu(name, budget_s, steps=None, warmup=1):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def rendezvous_unique_id(okl_lib, rank, world):
-    """Share the 128-byte ncclUniqueId between the ranks of one node through a file (no torch needed)."""
-    tag = f"{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', 'x')}_{os.getppid()}"
-    path = f"/tmp/okl_nccl_id_{tag}"
-    if rank == 0:
-        uid = okl_lib.Context.comm_unique_id()
-        with open(path + ".tmp", "wb") as f:
-            f.write(uid)
-        os.replace(path + ".tmp", path)
-        return uid
-    t0 = time.time()
-    while not os.path.exists(path):
-        if time.time() - t0 > 120:
-            raise RuntimeError("timed out waiting for the NCCL unique id from rank 0")
-        time.sleep(0.01)
-    with open(path, "rb") as f:
-        return f.read()
+def ncu_traffic(profile, needle):
+    """DRAM bytes (read + write) per launch of the kernel whose name contains `needle`, from the committed `ncu --set full`
+    capture of this bench command (profiles/<profile>); None when that kernel is not in the capture."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", profile)
+    try:
+        with open(path) as f:
+            doc = json.load(f)
+    except (OSError, ValueError):
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for k in doc.get("kernels", []):
+        if needle in k.get("Kernel Name", ""):
+            tot = 0.0
+            for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(k[m]) * scale.get(doc["units"].get(m, "byte"), 1.0)
+            return tot
+    return None
 
 
 def kernel_rooflines(okl, ctx, name, batch, peaks):
@@ -274,11 +279,11 @@ def kernel_rooflines(okl, ctx, name, batch, peaks):
         xp, wp, gp = X._dptr(), W._dptr(), G._dptr()
         cases = [
             ("dense1_wgrad (dW = X^T G, 5408x128, K=256)", lambda: check(lib.okl_dense_bwd(ctx.h, xp, wp, gp, None, dW._ptr_raw(), None, M, K, N, None)),
-             2.0 * M * K * N, 4.0 * (M * K + M * N + K * N)),
+             2.0 * M * K * N, 4.0 * (M * K + M * N + K * N), "tc_gemm_kernel<0, 1, 1, 64, 0>"),
             ("dense1_fwd (Y = X W, 256x5408x128)", lambda: check(lib.okl_dense_fwd(ctx.h, xp, wp, None, Y._ptr_raw(), M, K, N, 1)),
-             2.0 * M * K * N, 4.0 * (M * K + K * N + M * N)),
+             2.0 * M * K * N, 4.0 * (M * K + K * N + M * N), "tc_gemm_kernel<0, 0, 1, 64, 0>"),
             ("dense1_dgrad (dX = G W^T)", lambda: check(lib.okl_dense_bwd(ctx.h, xp, wp, gp, dX._ptr_raw(), None, None, M, K, N, None)),
-             2.0 * M * K * N, 4.0 * (M * N + K * N + M * K)),
+             2.0 * M * K * N, 4.0 * (M * N + K * N + M * K), "tc_gemm_kernel<0, 0, 0,"),
         ]
         d = _lib.ConvDesc()
         d.nd, d.N, d.C, d.O = 2, batch, 1, 32
@@ -301,11 +306,11 @@ def kernel_rooflines(okl, ctx, name, batch, peaks):
             # fused Conv2D(1,32,3)+bias+ReLU+MaxPool(2,2): reads x, writes pooled (fp32) + mask (u8); the 22 MB un-pooled tensor never exists
             ("conv1_relu_pool_fwd (256x1x28x28 -> 32@3x3 -> pool 13x13)",
              lambda: check(lib.okl_conv_relu_pool_fwd(ctx.h, C.byref(d), cxp, cwp, cbp, pooled._ptr_raw(), mask._ptr_raw())),
-             convf, 4.0 * batch * 784 + 5.0 * npool),
+             convf, 4.0 * batch * 784 + 5.0 * npool, "conv_relu_pool2_fwd"),
             # its backward: dW, db from the POOLED gradient + mask + x
             ("conv1_relu_pool_wgrad (dW 32x9, db 32 from pooled gradient + mask)",
              lambda: check(lib.okl_conv_relu_pool_wgrad(ctx.h, C.byref(d), cxp, pgp, mask._ptr_raw(), cdw._ptr_raw(), cdb._ptr_raw())),
-             2.0 * npool * 10, 4.0 * batch * 784 + 5.0 * npool),
+             2.0 * npool * 10, 4.0 * batch * 784 + 5.0 * npool, "conv_relu_pool2_wgrad"),
         ] + cases
     elif name == "mlp8192":
         M = K = N = 8192
@@ -315,10 +320,10 @@ def kernel_rooflines(okl, ctx, name, batch, peaks):
         check(lib.okl_memset(ctx.h, X._ptr_raw(), 0, M * K * 4))
         check(lib.okl_memset(ctx.h, W._ptr_raw(), 0, M * K * 4))
         cases = [("dense_fwd 8192^3", lambda: check(lib.okl_dense_fwd(ctx.h, X._ptr_raw(), W._ptr_raw(), None, Y._ptr_raw(), M, K, N, 1)),
-                  2.0 * M * K * N, 4.0 * 3 * M * N)]
+                  2.0 * M * K * N, 4.0 * 3 * M * N, None)]
     else:
         return res
-    for label, fn, flops, byts in cases:
+    for label, fn, flops, byts, needle in cases:
         fn()
         ctx.sync()
         best, mean = timed(fn)
@@ -329,7 +334,10 @@ def kernel_rooflines(okl, ctx, name, batch, peaks):
         else:
             ach, peak, unit, bound = byts / mean / 1e9, peaks["hbm_gbs"], "GB/s", "hbm"
         res.append({"kernel": label, "bound": bound, "achieved": round(ach, 3), "peak": peak, "unit": unit,
-                    "frac": round(ach / peak, 4), "traffic": None, "us": round(mean * 1e6, 2), "us_best": round(best * 1e6, 2),
+                    "frac": round(ach / peak, 4),
+                    # dram read+write per launch from the committed ncu --set full capture of this command (tf32 default only)
+                    "traffic": ncu_traffic("r1_ncu_full_top_kernels_mnist_cnn.json", needle) if (needle and prec == "tf32") else None,
+                    "us": round(mean * 1e6, 2), "us_best": round(best * 1e6, 2),
                     "algo_flops": flops, "algo_bytes": byts, "mode": prec})
     return res
 
@@ -405,11 +413,14 @@ def main():
     for t in (tXw, tXk) + (() if w["loss"] == "ce" else (tTw, tTk)):
         t._dptr()
     np.random.seed(99)
-    net.train(tXw, tTw, 1, sched, opt, B, loss_fn)          # warm-up: eager step, capture, replays
-    ctx.sync()
-    _lib.check(_lib.lib.okl_barrier(ctx.h))
+    # nvidia-smi is started BEFORE the warm-up and must have delivered its first sample before the timed region begins: its
+    # start-up (NVML initialisation) stalls kernel launches for tens of ms, which is as long as the whole timed region here
     sampler = ClockSampler(ctx.device)
     sampler.start()
+    net.train(tXw, tTw, 1, sched, opt, B, loss_fn)          # warm-up: eager step, capture, replays
+    ctx.sync()
+    sampler.wait_first(3.0)
+    _lib.check(_lib.lib.okl_barrier(ctx.h))
     l0 = ctx.launch_count()
     ctx.timer_start()
     losses = net.train(tXk, tTk, 1, sched, opt, B, loss_fn)  # exactly K steps

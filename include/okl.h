@@ -86,6 +86,23 @@ int okl_h2d_i32(okl_ctx* ctx, void* dst_i32, const void* host, size_t n, int src
 int okl_permute(okl_ctx* ctx, void* dst, const void* src, int N, int C, long long S, int src_layout);
 /* dst[r,:] = src[idx[r],:]  (epoch shuffle okl.py:2957-2960 as a device gather); idx int32 on device */
 int okl_gather_rows(okl_ctx* ctx, void* dst, const void* src, const void* idx_i32, long long rows, long long row_elems);
+/* the same for one training batch: rows idx[0..rows) of the inputs (fp32) and of the targets (32-bit words) in ONE launch
+ * (batch slicing okl.py:2966-2967); either source may be device memory or page-locked host memory */
+int okl_gather_batch(okl_ctx* ctx, void* x_dst, const void* x_src, long long x_row_elems, void* t_dst, const void* t_src,
+                     long long t_row_elems, const void* idx_i32, long long rows);
+
+/* Batch pipeline of the train loop (okl.py:2963-2967 slices the next batch on the host between steps; here the gather of step
+ * s+1's rows - from HBM, or over PCIe from page-locked host memory - runs on a copy stream WHILE step s computes).
+ * okl_batch_prefetch: okl_gather_batch into input slot 0/1 on the copy stream, ordered after everything enqueued so far on the
+ * compute stream (so the slot's previous consumer is finished); okl_batch_wait: the compute stream waits for that slot. */
+int okl_batch_prefetch(okl_ctx* ctx, int slot, void* x_dst, const void* x_src, long long x_row_elems, void* t_dst, const void* t_src,
+                       long long t_row_elems, const void* idx_i32, long long rows);
+int okl_batch_wait(okl_ctx* ctx, int slot);
+/* Per-step loss read-back (okl.py:2973 reads loss.data every batch) without stalling the device: _async copies the device scalar
+ * to page-locked host memory in stream order (slot 0/1), _wait blocks the host until that copy has landed and returns it - called
+ * for step s-1 after step s has been enqueued, so the device never idles. */
+int okl_loss_fetch_async(okl_ctx* ctx, int slot, const void* dev_f32);
+int okl_loss_fetch_wait(okl_ctx* ctx, int slot, float* out);
 
 /* ------------------------------------------------------------------ Dense (okl.py:18-54; tensor.py:57-67)
  * fwd: Y[M,N] = act(X[M,K] . W[K,N] + b[N])                       okl.py:31 (+ fused activation epilogue)
@@ -175,6 +192,13 @@ int okl_softmax_bwd(okl_ctx* ctx, const void* p, const void* g, void* dx, int ro
  * (okl.py:376-393), so a Softmax + CrossEntropy head costs one kernel for loss, loss gradient and softmax gradient. */
 int okl_ce_fwd_bwd(okl_ctx* ctx, const void* p, const void* targets_i32, void* loss, void* grad, int rows, int cols, float denom,
                    void* loss_accum, void* softmax_dx);
+/* Classifier head DenseLayer(K <= 256, N <= 16) -> SoftmaxActivationLayer -> CrossEntropyLoss in one launch (okl.py:26-29, 364-373,
+ * 1388-1403, 376-393, 35-37): P = softmax(X W + b); loss / loss_accum / grad as okl_ce_fwd_bwd; dZ = softmax backward of grad
+ * (the gradient w.r.t. the logits, from which okl_dense_bwd later forms dW, db); dX (optional) = dZ W^T, zeroed where
+ * dx_relu_mask <= 0 when that pointer is given.  Same summation orders as the separate entry points. */
+int okl_dense_softmax_ce(okl_ctx* ctx, const void* X, const void* W, const void* b, const void* targets_i32, void* P, void* loss,
+                         void* grad, void* dZ, void* dX, const void* dx_relu_mask, int M, int K, int N, float denom,
+                         void* loss_accum);
 /* loss[0] = sum((o-t)^2) / n ; grad = 2 (o - t) / denom   (denom = global element count) */
 int okl_mse_fwd_bwd(okl_ctx* ctx, const void* o, const void* t, void* loss, void* grad, size_t n, float denom, void* loss_accum);
 int okl_read_scalar(okl_ctx* ctx, const void* dev_f32, float* out);
@@ -226,6 +250,10 @@ int okl_p2p_import(okl_ctx* ctx, int rank, const void* handle64);
 int okl_p2p_suballoc(okl_ctx* ctx, size_t bytes, void** out);
 /* sum-allreduce `count` fp32 at p on the comm stream, ordered after everything enqueued so far on the compute stream */
 int okl_allreduce_async(okl_ctx* ctx, void* p, size_t count);
+/* the same, but also ordered after the auxiliary lanes (where weight gradients are produced) and ALWAYS on the comm stream -
+ * peer-memory kernel included - so that it overlaps what the caller enqueues next on the compute stream (early exchange of the
+ * gradients that are already complete while the first layers' backward still runs) */
+int okl_allreduce_fork(okl_ctx* ctx, void* p, size_t count);
 /* make the compute stream wait for every allreduce issued so far */
 int okl_comm_wait(okl_ctx* ctx);
 int okl_allreduce_max_host(okl_ctx* ctx, double* value);   /* small host-value reduction for max-over-ranks timing */

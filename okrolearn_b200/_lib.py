@@ -62,6 +62,11 @@ SIGNATURES = {
     "okl_h2d_i32": (_i, [_vp, _vp, _vp, _sz, _i]),
     "okl_permute": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i]),
     "okl_gather_rows": (_i, [_vp, _vp, _vp, _vp, _ll, _ll]),
+    "okl_gather_batch": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll]),
+    "okl_batch_prefetch": (_i, [_vp, _i, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll]),
+    "okl_batch_wait": (_i, [_vp, _i]),
+    "okl_loss_fetch_async": (_i, [_vp, _i, _vp]),
+    "okl_loss_fetch_wait": (_i, [_vp, _i, C.POINTER(C.c_float)]),
     "okl_dense_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "okl_dense_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "okl_to_bf16": (_i, [_vp, _vp, _vp, _sz]),
@@ -88,6 +93,7 @@ SIGNATURES = {
     "okl_softmax_fwd": (_i, [_vp, _vp, _vp, _i, _i]),
     "okl_softmax_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i]),
     "okl_ce_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp]),
+    "okl_dense_softmax_ce": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "okl_mse_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _f, _vp]),
     "okl_read_scalar": (_i, [_vp, _vp, _P(_f)]),
     "okl_accum_update": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _vp]),
@@ -113,6 +119,7 @@ SIGNATURES = {
     "okl_p2p_import": (_i, [_vp, _i, _vp]),
     "okl_p2p_suballoc": (_i, [_vp, _sz, _P(_vp)]),
     "okl_allreduce_async": (_i, [_vp, _vp, _sz]),
+    "okl_allreduce_fork": (_i, [_vp, _vp, _sz]),
     "okl_comm_wait": (_i, [_vp]),
     "okl_allreduce_max_host": (_i, [_vp, _P(C.c_double)]),
     "okl_barrier": (_i, [_vp]),

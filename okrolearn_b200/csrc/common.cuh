@@ -44,6 +44,7 @@ struct okl_ctx {
   void* tc_dbg = nullptr;               // debug: timestamp buffer for the tcgen05 GEMM
   int* tile_counters = nullptr;         // split-K arrival counters of the tcgen05 GEMM (all zero between launches)
   void* bf16_scratch = nullptr;         // bf16 copies of GEMM operands (OKL_BF16 mode)
+  void* head_scratch = nullptr;         // arrival counter + per-block loss partials of the fused classifier head
   size_t bf16_scratch_bytes = 0;
   // auxiliary lanes: independent branches of a step (weight / bias gradients are leaves of the backward chain) run on their own
   // streams with their own scratch; the fields above (stream, workspace, tile_counters, bf16_scratch) always describe the CURRENT lane
@@ -65,6 +66,15 @@ struct okl_ctx {
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
   bool comm_pending = false;
+  unsigned long long* tl_buf = nullptr; // debug timeline: one globaltimer stamp after every kernel (okl_debug_timeline_*)
+  int tl_n = 0;
+  std::vector<std::string> tl_names;
+  // double-buffered batch prefetch + lagged loss read-back (okl_batch_prefetch / okl_batch_wait / okl_loss_fetch_*)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy_fork = nullptr, ev_slot[2] = {nullptr, nullptr}, ev_loss[2] = {nullptr, nullptr};
+  float* loss_pinned = nullptr;         // 2 slots x {value, sequence number}
+  unsigned loss_seq[2] = {0, 0};
+  int pdl = 0;                          // programmatic dependent launch: 0 off (default: measured no gain), 1 on except while an aux lane is forked, 2 always
 };
 
 void okl_set_error(const char* fmt, ...);
@@ -87,8 +97,10 @@ void okl_set_error(const char* fmt, ...);
   } while (0)
 
 // account one kernel launch and surface launch-configuration errors immediately
+void okl_timeline_stamp(okl_ctx* ctx, const char* what);
 static inline int okl_post_launch(okl_ctx* ctx, const char* what) {
   if (ctx->capturing) ctx->capture_launches++; else ctx->launches++;
+  if (ctx->tl_buf) okl_timeline_stamp(ctx, what);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -103,8 +115,38 @@ static inline int okl_post_launch(okl_ctx* ctx, const char* what) {
     if (_s != OKL_OK) return _s;                         \
   } while (0)
 
+// ---- programmatic dependent launch (PDL).  A step is a chain of ~10 short kernels; with a plain stream / graph edge each
+// boundary costs the full drain -> launch -> ramp latency.  Kernels on the chain call okl_pdl_sync() before touching global
+// memory: it waits until the predecessor grid has completed and flushed (a no-op when the launch did not carry the attribute),
+// then lets the successor grid start launching, so the successor's CTAs are already resident when this grid drains.  The wait
+// comes first on purpose: a successor can then only start once its predecessor has passed its own wait, so completion is
+// transitive along the chain and everything before the wait needs no data produced by earlier kernels.
+#ifdef __CUDACC__
+__device__ __forceinline__ void okl_pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline void okl_launch(okl_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+  cudaLaunchAttribute at;
+  memset(&at, 0, sizeof(at));
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  // while weight-gradient kernels run on an auxiliary lane, early-resident CTAs of the next main-lane kernel would squat on the
+  // SMs those kernels need - keep plain edges there
+  const bool pdl = ctx->pdl == 2 || (ctx->pdl == 1 && (ctx->cur_lane != 0 || !ctx->aux_dirty));
+  cfg.attrs = &at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);      // errors surface through OKL_LAUNCHED
+}
+#endif
+
 int okl_ensure_workspace(okl_ctx* ctx, size_t bytes);   // grows ctx->workspace (not during capture)
 int okl_ensure_staging(okl_ctx* ctx, size_t bytes);
+int okl_loss_post(okl_ctx* ctx, float* host_slot, const void* dev_loss, unsigned seq);
 
 static inline int okl_grid_1d(const okl_ctx* ctx, size_t work_items, int block, int max_waves = 8) {
   size_t blocks = (work_items + block - 1) / block;

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256) conv_smallk_fprop(const float* __restrict
   extern __shared__ __align__(16) float sm[];
   float* Ws = sm;                 // [K][Opad]
   float* bs = sm + K * Opad;      // [Opad]
+  okl_pdl_sync();
   for (int i = threadIdx.x; i < K * Opad; i += blockDim.x) {
     int k = i / Opad, o = i - k * Opad;
     Ws[i] = o < g.O ? __ldg(W + (size_t)o * K + k) : 0.f;
@@ -287,6 +288,7 @@ conv_smallk_wgrad(const float* __restrict__ x, const float* __restrict__ gy, flo
 // lanes stride over the blocks' partials (independent loads), then a fixed-order butterfly.
 __global__ void conv_smallk_wgrad_reduce(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ db, int O, int K,
                                          int KT, int gx, int OB) {
+  okl_pdl_sync();
   const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (idx >= O * (K + 1)) return;
   const int o = idx / (K + 1), k = idx - o * (K + 1);
@@ -390,7 +392,7 @@ int okl_conv_small_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const float* x, c
   }
   OKL_LAUNCHED(ctx, "conv_smallk_wgrad");
   const int total = g.O * (K + 1);
-  conv_smallk_wgrad_reduce<<<(total * 32 + 255) / 256, 256, 0, ctx->stream>>>(partial, dW, db, g.O, K, KT, gx, WG_OB);
+  okl_launch(ctx, conv_smallk_wgrad_reduce, dim3((total * 32 + 255) / 256), dim3(256), 0, (const float*)partial, dW, db, g.O, K, KT, gx, WG_OB);
   OKL_LAUNCHED(ctx, "conv_smallk_wgrad_reduce");
   return OKL_OK;
 }
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(256, 3) conv_relu_pool2_fwd(const float* __res
 // accumulates channels 4w..4w+3 with lane l owning positions 4l..4l+3.
 constexpr int CP_OB = 16;
 template <int KH, int KW, int CMAX, int KT, bool PAD>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, CMAX == 1 ? 5 : 3)
 conv_relu_pool2_wgrad(const float* __restrict__ x, const float* __restrict__ gp, const unsigned char* __restrict__ mask,
                       float* __restrict__ partial, const ConvGeom g, const int K, const int PH, const int PW, const FastDiv dPW,
                       const FastDiv dPH, const int Mpool, const int ntiles) {
@@ -497,6 +499,7 @@ conv_relu_pool2_wgrad(const float* __restrict__ x, const float* __restrict__ gp,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int o_base = blockIdx.y * CP_OB;
   const int p = tid;
+  okl_pdl_sync();
   const long long plane = (long long)PH * PW;
   float acc[4][KT];
 #pragma unroll
@@ -603,10 +606,10 @@ extern "C" int okl_conv_relu_pool_fwd(okl_ctx* ctx, const okl_conv_desc* d, cons
   const int cap = ctx->sm_count * 16;
   if (grid > cap) grid = cap;
   const bool pad = g.P[1] || g.P[2];
-  if (pad) conv_relu_pool2_fwd<3, 3, true><<<grid, 256, smem, ctx->stream>>>((const float*)x, (const float*)W, (const float*)b, (float*)pooled,
-                                                                           (unsigned char*)mask, g, K, Opad, PH, PW, FastDiv(PW), FastDiv(PH), FastDiv(npix), npix, total);
-  else conv_relu_pool2_fwd<3, 3, false><<<grid, 256, smem, ctx->stream>>>((const float*)x, (const float*)W, (const float*)b, (float*)pooled,
-                                                                          (unsigned char*)mask, g, K, Opad, PH, PW, FastDiv(PW), FastDiv(PH), FastDiv(npix), npix, total);
+  if (pad) okl_launch(ctx, conv_relu_pool2_fwd<3, 3, true>, dim3(grid), dim3(256), smem, (const float*)x, (const float*)W, (const float*)b,
+                      (float*)pooled, (unsigned char*)mask, g, K, Opad, PH, PW, FastDiv(PW), FastDiv(PH), FastDiv(npix), npix, total);
+  else okl_launch(ctx, conv_relu_pool2_fwd<3, 3, false>, dim3(grid), dim3(256), smem, (const float*)x, (const float*)W, (const float*)b,
+                  (float*)pooled, (unsigned char*)mask, g, K, Opad, PH, PW, FastDiv(PW), FastDiv(PH), FastDiv(npix), npix, total);
   OKL_LAUNCHED(ctx, "conv_relu_pool2_fwd");
   return OKL_OK;
 }
@@ -624,7 +627,8 @@ extern "C" int okl_conv_relu_pool_wgrad(okl_ctx* ctx, const okl_conv_desc* d, co
   const int Mpool = g.N * PH * PW;
   const int ntiles = (Mpool + WG_PT - 1) / WG_PT;
   const int gy_ = (g.O + CP_OB - 1) / CP_OB;
-  int gx = (8 * ctx->sm_count + gy_ - 1) / gy_;          // every tile gets its own resident block at MNIST sizes
+  const int resident = g.C == 1 ? 5 : 3;                  // CTAs per SM the register budget allows (__launch_bounds__)
+  int gx = (resident * ctx->sm_count) / gy_;              // one wave: every tile gets its own resident block at MNIST sizes
   if (gx > ntiles) gx = ntiles;
   if (gx < 1) gx = 1;
   s = okl_ensure_workspace(ctx, (size_t)gx * gy_ * CP_OB * KT * sizeof(float));
@@ -633,15 +637,15 @@ extern "C" int okl_conv_relu_pool_wgrad(okl_ctx* ctx, const okl_conv_desc* d, co
   dim3 grid(gx, gy_);
   const bool pad = g.P[1] || g.P[2];
 #define OKL_LAUNCH_CRPW(C_, KT_, PAD_)                                                                                               \
-  conv_relu_pool2_wgrad<3, 3, C_, KT_, PAD_><<<grid, 128, 0, ctx->stream>>>((const float*)x, (const float*)pooled_g,                \
-                                                                            (const unsigned char*)mask, partial, g, K, PH, PW,      \
-                                                                            FastDiv(PW), FastDiv(PH), Mpool, ntiles)
+  okl_launch(ctx, conv_relu_pool2_wgrad<3, 3, C_, KT_, PAD_>, grid, dim3(128), 0, (const float*)x, (const float*)pooled_g,            \
+             (const unsigned char*)mask, partial, g, K, PH, PW, FastDiv(PW), FastDiv(PH), Mpool, ntiles)
   if (g.C == 1) { if (pad) OKL_LAUNCH_CRPW(1, 12, true); else OKL_LAUNCH_CRPW(1, 12, false); }
   else { if (pad) OKL_LAUNCH_CRPW(3, 28, true); else OKL_LAUNCH_CRPW(3, 28, false); }
 #undef OKL_LAUNCH_CRPW
   OKL_LAUNCHED(ctx, "conv_relu_pool2_wgrad");
   const int total = g.O * (K + 1);
-  conv_smallk_wgrad_reduce<<<(total * 32 + 255) / 256, 256, 0, ctx->stream>>>(partial, (float*)dW, (float*)db, g.O, K, KT, gx, CP_OB);
+  okl_launch(ctx, conv_smallk_wgrad_reduce, dim3((total * 32 + 255) / 256), dim3(256), 0, (const float*)partial, (float*)dW, (float*)db, g.O, K, KT,
+             gx, CP_OB);
   OKL_LAUNCHED(ctx, "conv_smallk_wgrad_reduce");
   return OKL_OK;
 }

@@ -44,6 +44,7 @@ extern "C" int okl_ctx_create(int device, int precision, okl_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   c->cc = prop.major * 10 + prop.minor;
   c->total_mem = prop.totalGlobalMem;
+  if (const char* e = getenv("OKL_PDL")) c->pdl = atoi(e);
   OKL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   OKL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
   c->lanes[0].stream = c->stream;
@@ -129,9 +130,100 @@ extern "C" int okl_aux_join(okl_ctx* ctx) {
   return OKL_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ batch pipeline
+// Step s+1's batch is gathered (from HBM, or over PCIe from page-locked host memory) into the other input slot on a copy stream
+// while step s computes.  The copy forks from the compute stream's current position - the previous user of that slot has been
+// enqueued by then - and the step that consumes the slot waits for the slot's event.
+static int ensure_pipeline(okl_ctx* ctx) {
+  if (ctx->copy_stream) return OKL_OK;
+  OKL_CHECK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  OKL_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 2; i++) {
+    OKL_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->ev_slot[i], cudaEventDisableTiming));
+    OKL_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->ev_loss[i], cudaEventDisableTiming));
+  }
+  OKL_CHECK_CUDA(cudaMallocHost(&ctx->loss_pinned, 4 * sizeof(float)));
+  memset(ctx->loss_pinned, 0, 4 * sizeof(float));
+  return OKL_OK;
+}
+
+extern "C" int okl_batch_prefetch(okl_ctx* ctx, int slot, void* x_dst, const void* x_src, long long x_row_elems, void* t_dst,
+                                  const void* t_src, long long t_row_elems, const void* idx, long long rows) {
+  OKL_REQUIRE(ctx && (slot == 0 || slot == 1), "okl_batch_prefetch: slot must be 0 or 1");
+  OKL_REQUIRE(!ctx->capturing && ctx->cur_lane == 0, "okl_batch_prefetch: not inside a capture / auxiliary lane");
+  int s = ensure_pipeline(ctx);
+  if (s != OKL_OK) return s;
+  OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_copy_fork, ctx->stream));
+  OKL_CHECK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_fork, 0));
+  cudaStream_t main_stream = ctx->stream;
+  ctx->stream = ctx->copy_stream;
+  s = okl_gather_batch(ctx, x_dst, x_src, x_row_elems, t_dst, t_src, t_row_elems, idx, rows);
+  ctx->stream = main_stream;
+  if (s != OKL_OK) return s;
+  OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_slot[slot], ctx->copy_stream));
+  return OKL_OK;
+}
+
+extern "C" int okl_batch_wait(okl_ctx* ctx, int slot) {
+  OKL_REQUIRE(ctx && (slot == 0 || slot == 1) && ctx->copy_stream, "okl_batch_wait: no prefetch issued for this slot");
+  OKL_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_slot[slot], 0));
+  return OKL_OK;
+}
+
+// Loss read-back without draining the pipeline: the scalar is copied to page-locked host memory in stream order right after its
+// step; the host collects it (okl_loss_fetch_wait) once the NEXT step has been enqueued.
+extern "C" int okl_loss_fetch_async(okl_ctx* ctx, int slot, const void* dev_f32) {
+  OKL_REQUIRE(ctx && dev_f32 && (slot == 0 || slot == 1), "okl_loss_fetch_async: bad argument");
+  OKL_REQUIRE(!ctx->capturing, "okl_loss_fetch_async: not inside a capture");
+  int s = ensure_pipeline(ctx);
+  if (s != OKL_OK) return s;
+  if (ctx->aux_dirty) {
+    s = okl_aux_join(ctx);
+    if (s != OKL_OK) return s;
+  }
+  // a one-thread kernel posts {value, sequence number} into page-locked host memory and the host polls the sequence number.
+  // It runs on the COPY stream, behind an event recorded on the compute stream: anything enqueued between two step graphs on the
+  // compute stream itself (DMA copy or kernel with a system-scope fence) costs ~10 us of step time, measured.
+  OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_copy_fork, ctx->stream));
+  OKL_CHECK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_fork, 0));
+  cudaStream_t main_stream = ctx->stream;
+  ctx->stream = ctx->copy_stream;
+  s = okl_loss_post(ctx, ctx->loss_pinned + 2 * slot, dev_f32, ++ctx->loss_seq[slot]);
+  ctx->stream = main_stream;
+  return s;
+}
+
+extern "C" int okl_loss_fetch_wait(okl_ctx* ctx, int slot, float* out) {
+  OKL_REQUIRE(ctx && out && (slot == 0 || slot == 1) && ctx->loss_pinned, "okl_loss_fetch_wait: nothing to wait for");
+  volatile unsigned* seq = reinterpret_cast<volatile unsigned*>(ctx->loss_pinned + 2 * slot + 1);
+  const unsigned want = ctx->loss_seq[slot];
+  for (unsigned long long spins = 0; *seq != want; spins++) {
+    if ((spins & 0xfffff) == 0xfffff) {                     // every ~1M polls: has the stream died?
+      cudaError_t e = cudaStreamQuery(ctx->copy_stream);
+      if (e != cudaSuccess && e != cudaErrorNotReady) {
+        okl_set_error("okl_loss_fetch_wait: stream failed: %s", cudaGetErrorString(e));
+        return OKL_ERR_CUDA;
+      }
+      if (e == cudaSuccess && *seq != want) {                // stream drained but the post never arrived
+        okl_set_error("okl_loss_fetch_wait: no loss was posted for slot %d", slot);
+        return OKL_ERR_INVALID;
+      }
+    }
+  }
+  *out = *reinterpret_cast<volatile float*>(ctx->loss_pinned + 2 * slot);
+  return OKL_OK;
+}
+
 extern "C" int okl_ctx_destroy(okl_ctx* ctx) {
   if (!ctx) return OKL_OK;
   cudaSetDevice(ctx->device);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    cudaEventDestroy(ctx->ev_copy_fork);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_slot[i]); cudaEventDestroy(ctx->ev_loss[i]); }
+    cudaFreeHost(ctx->loss_pinned);
+  }
   okl_aux_join(ctx);
   for (int i = 1; i < 3; i++) {
     cudaStreamSynchronize(ctx->lanes[i].stream);
@@ -150,6 +242,7 @@ extern "C" int okl_ctx_destroy(okl_ctx* ctx) {
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   if (ctx->bf16_scratch) cudaFree(ctx->bf16_scratch);
   if (ctx->tile_counters) cudaFree(ctx->tile_counters);
+  if (ctx->head_scratch) cudaFree(ctx->head_scratch);
   cudaEventDestroy(ctx->ev_fork);
   cudaEventDestroy(ctx->ev_join);
   cudaEventDestroy(ctx->ev_t0);
@@ -626,6 +719,33 @@ extern "C" int okl_allreduce_async(okl_ctx* ctx, void* p, size_t count) {
   return OKL_OK;
 }
 
+// Early exchange: the all-reduce runs on the comm stream as soon as everything enqueued so far on the main lane AND on the
+// auxiliary lanes (where the weight gradients are produced) has finished, concurrently with whatever the caller enqueues next
+// (the remaining backward); okl_comm_wait joins it.
+extern "C" int okl_allreduce_fork(okl_ctx* ctx, void* p, size_t count) {
+  OKL_REQUIRE(ctx && p, "NULL argument");
+  if (ctx->nranks == 1 || count == 0) return OKL_OK;
+  OKL_REQUIRE(ctx->cur_lane == 0, "okl_allreduce_fork: call from the main lane");
+  OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  OKL_CHECK_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_fork, 0));
+  for (int i = 1; i < 3; i++) {
+    if (!ctx->lanes[i].dirty) continue;
+    OKL_CHECK_CUDA(cudaEventRecord(ctx->lanes[i].ev, ctx->lanes[i].stream));
+    OKL_CHECK_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->lanes[i].ev, 0));
+  }
+  ctx->comm_pending = true;
+  if (okl_p2p_applicable(ctx, p, count)) {
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = ctx->comm_stream;
+    int s = okl_p2p_allreduce(ctx, p, count);
+    ctx->stream = main_stream;
+    return s;
+  }
+  OKL_REQUIRE(ctx->nccl_comm, "okl_allreduce_fork: communicator not initialised");
+  OKL_CHECK_NCCL(g_nccl.AllReduce(p, p, count, ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->comm_stream));
+  return OKL_OK;
+}
+
 extern "C" int okl_comm_wait(okl_ctx* ctx) {
   OKL_REQUIRE(ctx, "ctx is NULL");
   if (!ctx->comm_pending) return OKL_OK;
@@ -654,4 +774,52 @@ extern "C" int okl_barrier(okl_ctx* ctx) {
   int s = okl_ctx_sync(ctx);
   if (s != OKL_OK) return s;
   return okl_allreduce_max_host(ctx, &v);
+}
+
+// ------------------------------------------------------------------------------------------------ debug timeline (not in okl.h)
+// A one-thread kernel after every launch records %globaltimer, in stream order and inside captured graphs alike, so the
+// effective cost of every link of a step's kernel chain (launch gap + execution) can be read back.  Perturbs timing by the
+// stamp kernels' own latency (calibrated by the two back-to-back stamps at the start).
+namespace {
+__global__ void timeline_stamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+}  // namespace
+
+void okl_timeline_stamp(okl_ctx* ctx, const char* what) {
+  if (ctx->tl_n >= 4096) return;
+  char nm[96];
+  snprintf(nm, sizeof(nm), "%s@%d%s", what, ctx->cur_lane, ctx->capturing ? "g" : "");
+  ctx->tl_names.push_back(nm);
+  timeline_stamp_kernel<<<1, 1, 0, ctx->stream>>>(ctx->tl_buf + ctx->tl_n++);
+}
+
+extern "C" int okl_debug_timeline_begin(okl_ctx* ctx) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  if (!ctx->tl_buf) {
+    OKL_CHECK_CUDA(cudaMalloc(&ctx->tl_buf, 4096 * sizeof(unsigned long long)));
+    OKL_CHECK_CUDA(cudaMemset(ctx->tl_buf, 0, 4096 * sizeof(unsigned long long)));
+  }
+  ctx->tl_n = 0;
+  ctx->tl_names.clear();
+  okl_timeline_stamp(ctx, "start0");
+  okl_timeline_stamp(ctx, "start1");
+  return OKL_OK;
+}
+
+// copies the stamps (ns) to out[0..n) and the '\n'-separated labels to names; stops recording
+extern "C" int okl_debug_timeline_read(okl_ctx* ctx, unsigned long long* out, int cap, char* names, int names_cap, int* n) {
+  OKL_REQUIRE(ctx && out && names && n && ctx->tl_buf, "okl_debug_timeline_read: no timeline");
+  OKL_CHECK_CUDA(cudaDeviceSynchronize());
+  const int cnt = ctx->tl_n < cap ? ctx->tl_n : cap;
+  OKL_CHECK_CUDA(cudaMemcpy(out, ctx->tl_buf, cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  std::string all;
+  for (int i = 0; i < cnt; i++) { all += ctx->tl_names[i]; all += '\n'; }
+  snprintf(names, names_cap, "%s", all.c_str());
+  *n = cnt;
+  cudaFree(ctx->tl_buf);
+  ctx->tl_buf = nullptr;
+  return OKL_OK;
 }

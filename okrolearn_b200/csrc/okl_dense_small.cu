@@ -22,6 +22,7 @@ __device__ __forceinline__ float sn_act(float v, int act) {
 __global__ void __launch_bounds__(256) dense_smalln_fwd(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ b,
                                                        float* __restrict__ Y, int M, int K, int N, int act) {
   extern __shared__ float Ws[];            // [K][N]
+  okl_pdl_sync();
   for (int i = threadIdx.x; i < K * N; i += blockDim.x) Ws[i] = __ldg(W + i);
   __syncthreads();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(256) dense_smalln_bwd(const float* __restrict_
                                                        const float* __restrict__ mask, int M, int K, int N, int nbx, int nbw) {
   extern __shared__ float Ws[];            // [K][N] (dX blocks only)
   const int bid = blockIdx.x;
+  okl_pdl_sync();
   if (bid < nbx) {
     for (int i = threadIdx.x; i < K * N; i += blockDim.x) Ws[i] = __ldg(W + i);
     __syncthreads();
@@ -132,16 +134,139 @@ __global__ void __launch_bounds__(256) dense_smalln_bwd(const float* __restrict_
   }
 }
 
+
+// Classifier head in ONE kernel (rows are independent): logits = X W + b, stable softmax, cross-entropy value, the loss gradient
+// (clip(p) - onehot) / denom, its pass through the softmax Jacobian (okl.py:376-393) and dX = dZ W^T (optionally with the ReLU
+// mask of the layer that produced X).  One warp per row; lane l owns k = l, l + 32, ... for BOTH products, so its KJ x N slice of
+// W is loaded once into registers (all loads of a row - x, W, target - are in flight together: one memory round trip before the
+// arithmetic).  Summation orders are those of dense_smalln_fwd / ce_fused_rowthread / dense_smalln_bwd, so the results match the
+// unfused chain bit for bit except the loss sum, which is reduced per block and then over blocks in fixed order by the last
+// block to arrive (deterministic for a given grid).
+template <int KJ>
+__global__ void __launch_bounds__(256) dense_softmax_ce_kernel(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ b,
+                                                              const int* __restrict__ t, float* __restrict__ P, float* __restrict__ grad,
+                                                              float* __restrict__ dZ, float* __restrict__ dX, const float* __restrict__ mask,
+                                                              float* __restrict__ loss, float* __restrict__ loss_acc, float* __restrict__ partial,
+                                                              unsigned* __restrict__ counter, int M, int K, int N, float inv_denom) {
+  __shared__ float wl[8];
+  __shared__ bool is_last;
+  okl_pdl_sync();
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * 8 + wib, nwarps = gridDim.x * 8;
+  float wreg[KJ][SN_MAXN], bias[SN_MAXN];
+#pragma unroll
+  for (int j = 0; j < KJ; j++) {
+    const int k = lane + 32 * j;
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; n++) wreg[j][n] = (k < K && n < N) ? __ldg(W + (size_t)k * N + n) : 0.f;
+  }
+#pragma unroll
+  for (int n = 0; n < SN_MAXN; n++) bias[n] = (b && n < N) ? __ldg(b + n) : 0.f;
+  float lsum = 0.f;
+  for (int m = warp; m < M; m += nwarps) {
+    const float* xr = X + (size_t)m * K;
+    float xv[KJ];
+#pragma unroll
+    for (int j = 0; j < KJ; j++) xv[j] = (lane + 32 * j < K) ? __ldg(xr + lane + 32 * j) : 0.f;
+    const int tc = __ldg(t + m);
+    float acc[SN_MAXN];
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; n++) acc[n] = 0.f;
+#pragma unroll
+    for (int j = 0; j < KJ; j++)
+#pragma unroll
+      for (int n = 0; n < SN_MAXN; n++) acc[n] = fmaf(xv[j], wreg[j][n], acc[n]);
+    float mx = -INFINITY, sum = 0.f;
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; n++) {
+      if (n < N) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], s);
+        if (b) acc[n] += bias[n];
+        mx = fmaxf(mx, acc[n]);
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; n++)
+      if (n < N) { acc[n] = expf(acc[n] - mx); sum += acc[n]; }
+    float dot = 0.f, pt = 1.f, gv[SN_MAXN];
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; n++) {
+      gv[n] = 0.f;
+      if (n < N) {
+        float v = acc[n] / sum;
+        v = isnan(v) ? 0.f : v;            // nan_to_num, okl.py:370
+        acc[n] = v;
+        float g = fminf(fmaxf(v, 1e-12f), 1.0f);      // np.clip(p, 1e-12, 1 - 1e-12), okl.py:1391 (upper bound rounds to 1.0f)
+        if (n == tc) { pt = g; g -= 1.f; }
+        g *= inv_denom;
+        gv[n] = g;
+        dot += g * v;
+      }
+    }
+    lsum += -logf(pt);
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; n++)
+      if (n < N) {
+        const float dz = acc[n] * (gv[n] - dot);
+        if (lane == n) {
+          P[(size_t)m * N + n] = acc[n];
+          grad[(size_t)m * N + n] = gv[n];
+          dZ[(size_t)m * N + n] = dz;
+        }
+        gv[n] = dz;
+      }
+    if (dX) {
+#pragma unroll
+      for (int j = 0; j < KJ; j++) {
+        const int k = lane + 32 * j;
+        float s = 0.f;
+#pragma unroll
+        for (int n = 0; n < SN_MAXN; n++)
+          if (n < N) s = fmaf(gv[n], wreg[j][n], s);
+        // the mask is the post-ReLU input itself when given (X == mask in the train loop), but honour a distinct pointer
+        if (mask && !((mask == X ? xv[j] : __ldg(mask + (size_t)m * K + k)) > 0.f)) s = 0.f;
+        if (k < K) dX[(size_t)m * K + k] = s;
+      }
+    }
+  }
+  if (lane == 0) wl[wib] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) s += wl[w];
+    partial[blockIdx.x] = s;
+    __threadfence();
+    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last && wib == 0) {                  // last block to arrive: fixed-order sum of the per-block partials
+    __threadfence();
+    float tot = 0.f;
+    for (unsigned i = lane; i < gridDim.x; i += 32) tot += __ldcg(partial + i);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, s);
+    if (lane == 0) {
+      const float l = tot / (float)M;
+      loss[0] = l;
+      if (loss_acc) loss_acc[0] += l;
+      *counter = 0u;
+    }
+  }
+}
+
 }  // namespace
 
 bool okl_dense_small_ok(int M, int K, int N) { return N >= 1 && N <= SN_MAXN && (long long)K * N <= 12000 && M >= 1; }
+bool okl_dense_head_ok(int M, int K, int N) { return N >= 1 && N <= SN_MAXN && K >= 1 && K <= 256 && M >= 1; }
 
 int okl_dense_small_fwd(okl_ctx* ctx, const float* X, const float* W, const float* b, float* Y, int M, int K, int N, int act) {
   int warps = M;
   int grid = (warps * 32 + 255) / 256;
   const int cap = ctx->sm_count * 4;
   if (grid > cap) grid = cap;
-  dense_smalln_fwd<<<grid, 256, (size_t)K * N * sizeof(float), ctx->stream>>>(X, W, b, Y, M, K, N, act);
+  okl_launch(ctx, dense_smalln_fwd, dim3(grid), dim3(256), (size_t)K * N * sizeof(float), X, W, b, Y, M, K, N, act);
   OKL_LAUNCHED(ctx, "dense_smalln_fwd");
   return OKL_OK;
 }
@@ -159,7 +284,34 @@ int okl_dense_small_bwd(okl_ctx* ctx, const float* X, const float* W, const floa
   if (total == 0) return OKL_OK;
   size_t smem = (size_t)K * N * sizeof(float), smem_w = (size_t)SN_MC * (32 + N) * sizeof(float);
   if (smem_w > smem) smem = smem_w;
-  dense_smalln_bwd<<<total, 256, smem, ctx->stream>>>(X, W, G, dX, dW, db, mask, M, K, N, nbx, nbw);
+  okl_launch(ctx, dense_smalln_bwd, dim3(total), dim3(256), smem, X, W, G, dX, dW, db, mask, M, K, N, nbx, nbw);
   OKL_LAUNCHED(ctx, "dense_smalln_bwd");
+  return OKL_OK;
+}
+
+// DenseLayer(K, N <= 16) -> SoftmaxActivationLayer -> CrossEntropyLoss, forward and backward down to dX (see the kernel).
+extern "C" int okl_dense_softmax_ce(okl_ctx* ctx, const void* X, const void* W, const void* b, const void* targets_i32, void* P, void* loss,
+                                    void* grad, void* dZ, void* dX, const void* dx_relu_mask, int M, int K, int N, float denom,
+                                    void* loss_accum) {
+  OKL_REQUIRE(ctx && X && W && targets_i32 && P && loss && grad && dZ, "NULL argument");
+  OKL_REQUIRE(okl_dense_head_ok(M, K, N) && denom > 0.f, "okl_dense_softmax_ce: needs 1 <= N <= %d and 1 <= K <= 256", SN_MAXN);
+  if (!ctx->head_scratch) {
+    OKL_CHECK_CUDA(cudaMalloc(&ctx->head_scratch, 8192));
+    OKL_CHECK_CUDA(cudaMemset(ctx->head_scratch, 0, 8192));
+  }
+  int grid = (M + 7) / 8;
+  const int cap = ctx->sm_count * 4 < 2000 ? ctx->sm_count * 4 : 2000;
+  if (grid > cap) grid = cap;
+  unsigned* counter = (unsigned*)ctx->head_scratch;
+  float* partial = (float*)ctx->head_scratch + 16;
+  if (K <= 128)
+    okl_launch(ctx, dense_softmax_ce_kernel<4>, dim3(grid), dim3(256), 0, (const float*)X, (const float*)W, (const float*)b,
+               (const int*)targets_i32, (float*)P, (float*)grad, (float*)dZ, (float*)dX, (const float*)dx_relu_mask, (float*)loss,
+               (float*)loss_accum, partial, counter, M, K, N, 1.f / denom);
+  else
+    okl_launch(ctx, dense_softmax_ce_kernel<8>, dim3(grid), dim3(256), 0, (const float*)X, (const float*)W, (const float*)b,
+               (const int*)targets_i32, (float*)P, (float*)grad, (float*)dZ, (float*)dX, (const float*)dx_relu_mask, (float*)loss,
+               (float*)loss_accum, partial, counter, M, K, N, 1.f / denom);
+  OKL_LAUNCHED(ctx, "dense_softmax_ce");
   return OKL_OK;
 }

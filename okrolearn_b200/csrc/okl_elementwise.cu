@@ -110,6 +110,7 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
 }
 __global__ void gather_rows_kernel(float* __restrict__ dst, const float* __restrict__ src, const int* __restrict__ idx,
                                    long long rows, long long row_elems) {
+  okl_pdl_sync();
   size_t total = (size_t)rows * row_elems;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t r = i / row_elems, c = i - r * row_elems;
@@ -119,11 +120,52 @@ __global__ void gather_rows_kernel(float* __restrict__ dst, const float* __restr
 
 __global__ void gather_rows4_kernel(float4* __restrict__ dst, const float4* __restrict__ src, const int* __restrict__ idx, long long rows,
                                     long long row4) {
+  okl_pdl_sync();
   size_t total = (size_t)rows * row4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t r = i / row4, c = i - r * row4;
     dst[i] = src[(size_t)idx[r] * row4 + c];
   }
+}
+
+// one batch = the rows idx[0..rows) of the inputs (float4 granules) AND of the targets (32-bit words), in one launch.  The
+// source may be page-locked HOST memory (zero-copy over PCIe, ~2 us per round trip): every thread keeps GB_U independent loads in
+// flight and the grid covers the batch in a single pass, so the transfer is bound by the link, not by latency.
+constexpr int GB_U = 4;
+__global__ void __launch_bounds__(256) gather_batch_kernel(float4* __restrict__ xd, const float4* __restrict__ xs, long long xrow4,
+                                                           unsigned* __restrict__ td, const unsigned* __restrict__ ts, long long trow,
+                                                           const int* __restrict__ idx, long long rows) {
+  okl_pdl_sync();
+  const size_t nx = (size_t)rows * xrow4, total = nx + (size_t)rows * trow;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t base = blockIdx.x * (size_t)blockDim.x + threadIdx.x; base < total; base += stride * GB_U) {
+    float4 v[GB_U];
+    unsigned u[GB_U];
+#pragma unroll
+    for (int j = 0; j < GB_U; j++) {
+      const size_t i = base + j * stride;
+      if (i < nx) {
+        const size_t r = i / xrow4, c = i - r * xrow4;
+        v[j] = xs[(size_t)idx[r] * xrow4 + c];
+      } else if (i < total) {
+        const size_t q = i - nx, r = q / trow, c = q - r * trow;
+        u[j] = ts[(size_t)idx[r] * trow + c];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < GB_U; j++) {
+      const size_t i = base + j * stride;
+      if (i < nx) xd[i] = v[j];
+      else if (i < total) td[i - nx] = u[j];
+    }
+  }
+}
+
+// loss read-back without a DMA copy: {value, sequence number} posted into page-locked host memory; the host polls the number
+__global__ void loss_post_kernel(volatile float* __restrict__ host_slot, const float* __restrict__ dev_loss, unsigned seq) {
+  host_slot[0] = dev_loss[0];
+  __threadfence_system();
+  reinterpret_cast<volatile unsigned*>(host_slot)[1] = seq;
 }
 
 // ------------------------------------------------------------------------------------------------ pooling
@@ -447,6 +489,7 @@ __global__ void colsum_stage1(const float* __restrict__ G, float* __restrict__ p
 // single pass (rows small, or enough column blocks to fill the chip): out[c] = sum_r G[r, c]; 32 cols x 32 row-lanes per block
 __global__ void colsum_single(const float* __restrict__ G, float* __restrict__ out, long long rows, int cols) {
   __shared__ float sh[32][33];
+  okl_pdl_sync();
   int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
   if (c < cols)
@@ -485,6 +528,7 @@ __global__ void colsum_stage2(const float* __restrict__ partial, float* __restri
 template <bool VEC>
 __global__ void accum_update_kernel(float* __restrict__ w, float* __restrict__ gacc, const float* __restrict__ g, size_t n, float lr,
                                     const float* __restrict__ lr_dev) {
+  okl_pdl_sync();
   if (lr_dev) lr = __ldg(lr_dev);
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
   if (VEC) {
@@ -618,6 +662,30 @@ extern "C" int okl_gather_rows(okl_ctx* ctx, void* dst, const void* src, const v
   gather_rows_kernel<<<okl_grid_1d(ctx, (size_t)rows * row_elems, 256), 256, 0, ctx->stream>>>((float*)dst, (const float*)src,
                                                                                            (const int*)idx, rows, row_elems);
   OKL_LAUNCHED(ctx, "gather_rows");
+  return OKL_OK;
+}
+
+extern "C" int okl_gather_batch(okl_ctx* ctx, void* x_dst, const void* x_src, long long x_row_elems, void* t_dst, const void* t_src,
+                                long long t_row_elems, const void* idx, long long rows) {
+  OKL_REQUIRE(ctx && (rows == 0 || (x_dst && x_src && t_dst && t_src && idx)), "NULL argument");
+  if (rows <= 0) return OKL_OK;
+  if (x_row_elems > 0 && t_row_elems > 0 && (x_row_elems & 3) == 0 && aligned16(x_dst) && aligned16(x_src)) {
+    const size_t total = (size_t)rows * (x_row_elems / 4 + t_row_elems);
+    size_t blocks = (total + 256 * GB_U - 1) / (256 * GB_U);
+    if (blocks > (size_t)ctx->sm_count * 8) blocks = (size_t)ctx->sm_count * 8;
+    okl_launch(ctx, gather_batch_kernel, dim3((unsigned)blocks), dim3(256), 0, (float4*)x_dst, (const float4*)x_src,
+               x_row_elems / 4, (unsigned*)t_dst, (const unsigned*)t_src, t_row_elems, (const int*)idx, rows);
+    OKL_LAUNCHED(ctx, "gather_batch");
+    return OKL_OK;
+  }
+  int s = okl_gather_rows(ctx, x_dst, x_src, idx, rows, x_row_elems);
+  if (s != OKL_OK) return s;
+  return okl_gather_rows(ctx, t_dst, t_src, idx, rows, t_row_elems);
+}
+
+int okl_loss_post(okl_ctx* ctx, float* host_slot, const void* dev_loss, unsigned seq) {
+  loss_post_kernel<<<1, 1, 0, ctx->stream>>>(host_slot, (const float*)dev_loss, seq);
+  OKL_LAUNCHED(ctx, "loss_post");
   return OKL_OK;
 }
 
@@ -759,7 +827,7 @@ int okl_colsum(okl_ctx* ctx, const float* G, float* out, long long rows, int col
   if (cols <= 0) return OKL_OK;
   int col_blocks = (cols + 31) / 32;
   if (rows <= 4096 || col_blocks >= ctx->sm_count) {
-    colsum_single<<<col_blocks, dim3(32, 32), 0, ctx->stream>>>(G, out, rows, cols);
+    okl_launch(ctx, colsum_single, dim3(col_blocks), dim3(32, 32), 0, G, out, rows, cols);
     OKL_LAUNCHED(ctx, "colsum_single");
     return OKL_OK;
   }
@@ -802,8 +870,8 @@ extern "C" int okl_accum_update(okl_ctx* ctx, void* w, void* gacc, const void* g
   if (n == 0) return OKL_OK;
   bool vec = aligned16(w) && aligned16(gacc) && aligned16(g);
   int grid = okl_grid_1d(ctx, vec ? (n + 3) / 4 : n, 256);
-  if (vec) accum_update_kernel<true><<<grid, 256, 0, ctx->stream>>>((float*)w, (float*)gacc, (const float*)g, n, lr, (const float*)lr_dev);
-  else accum_update_kernel<false><<<grid, 256, 0, ctx->stream>>>((float*)w, (float*)gacc, (const float*)g, n, lr, (const float*)lr_dev);
+  if (vec) okl_launch(ctx, accum_update_kernel<true>, dim3(grid), dim3(256), 0, (float*)w, (float*)gacc, (const float*)g, n, lr, (const float*)lr_dev);
+  else okl_launch(ctx, accum_update_kernel<false>, dim3(grid), dim3(256), 0, (float*)w, (float*)gacc, (const float*)g, n, lr, (const float*)lr_dev);
   OKL_LAUNCHED(ctx, "accum_update");
   return OKL_OK;
 }

@@ -255,6 +255,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  okl_pdl_sync();                          // barriers, TMEM and descriptor prefetch above overlap the predecessor's tail
   if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 1] = gtime();
 
   const int total_work = p.tiles_m * p.tiles_n * p.splits;
@@ -654,7 +655,7 @@ int launch_cfg(okl_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const
   const int kb = p.kb_per_split > 0 ? p.kb_per_split : p.kb_total;
   q.stages = total <= grid ? (kb < 2 ? 2 : (kb < Cfg::STAGES ? kb : Cfg::STAGES)) : Cfg::STAGES;   // one tile per CTA: no deeper than its K loop
   const int smem_bytes = Cfg::SMEM_BYTES - (Cfg::STAGES - q.stages) * Cfg::STAGE_BYTES;
-  kern<<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(ta, tb, q);
+  okl_launch(ctx, kern, dim3(grid), dim3(TC_THREADS), smem_bytes, ta, tb, q);
   OKL_LAUNCHED(ctx, "tc_gemm_kernel");
   return OKL_OK;
 }

@@ -76,6 +76,16 @@ class ParamArena:
         for b in self.buckets:
             b.rehome(self, off)
             off += b.total
+        self._tail_exchanged = False
+
+    def exchange_tail(self):
+        """Data parallel: start the all-reduce of every bucket but the first (their gradients are complete once the backward pass
+        reaches the first parametric layer) on the comm stream, overlapping that layer's backward."""
+        ctx = get_ctx()
+        head = self.buckets[0].total
+        if ctx.nranks > 1 and len(self.buckets) > 1 and not self._tail_exchanged:
+            check(lib.okl_allreduce_fork(ctx.h, self.grad.ptr + head * 4, self.total - head))
+            self._tail_exchanged = True
 
 
 class _ParamBucket:
@@ -189,6 +199,7 @@ class _ParamLayer:
     _dx_relu_mask = False          # NeuralNetwork planner: a fused ReLU precedes this layer; its backward is applied in our dX epilogue
     _defer_update = False          # set by NeuralNetwork when updates are applied after the whole backward (DP overlap)
     _fused_act = ACT_NONE          # set by NeuralNetwork's planner: activation fused into this layer's epilogue
+    _fused_head = False            # NeuralNetwork planner: last Dense(N<=16) -> Softmax; the loss's kernel computes the head
 
     def _finish_update(self):
         b = self._bucket
@@ -211,7 +222,12 @@ def apply_pending_updates(layers):
     arena = bs[0].arena
     if arena is not None and len(bs) == len(arena.buckets) and all(b.arena is arena for b in bs):
         if ctx.nranks > 1:
-            check(lib.okl_allreduce_async(ctx.h, arena.grad.ptr, arena.total))
+            if arena._tail_exchanged:                      # the rest is already in flight: only the first bucket is left
+                check(lib.okl_comm_wait(ctx.h))
+                check(lib.okl_allreduce_async(ctx.h, arena.grad.ptr, arena.buckets[0].total))
+                arena._tail_exchanged = False
+            else:
+                check(lib.okl_allreduce_async(ctx.h, arena.grad.ptr, arena.total))
             check(lib.okl_comm_wait(ctx.h))
         check(lib.okl_accum_update(ctx.h, arena.param.ptr, arena.gacc.ptr, arena.grad.ptr, arena.total, lrf, lrp))
     else:
@@ -255,6 +271,22 @@ class DenseLayer(_ParamLayer):
         self.inputs = inputs
         M = inputs.shape[0]
         out = Tensor._empty((M, N), np.float64)
+        self._head_pre = None
+        if self._fused_head:
+            # classifier head: the probabilities are produced by the loss's fused kernel (okl_dense_softmax_ce) when a
+            # CrossEntropyLoss consumes them next; any other reader triggers the ordinary dense + softmax kernel
+            self._bf16_path = False
+            layer = self
+
+            def compute(t):
+                c = get_ctx()
+                check(lib.okl_dense_fwd(c.h, layer.inputs._dptr(NCX), layer._bucket.ptr(0), layer._bucket.ptr(1), t._ptr_raw(),
+                                        M, K, N, layer._fused_act))
+                t._touch()
+            out._lazy_fn = compute
+            out._head_of = self
+            self.outputs = out
+            return out
         self._bf16_path = (ctx.precision == _lib.BF16 and M >= 64 and M % 8 == 0 and K >= 64 and N >= 64 and K % 8 == 0 and N % 8 == 0
                            and self._fused_act <= ACT_TANH)
         if self._bf16_path:                      # operands and result carry bf16 shadows: no per-call conversion
@@ -274,8 +306,23 @@ class DenseLayer(_ParamLayer):
         if dL_dout.shape != (M, N):
             raise ValueError(f"dL_dout shape {dL_dout.shape} does not match the layer output {(M, N)}")
         need_dx = getattr(self, "_need_dx", True)
-        dX = Tensor._empty((M, K), np.float64) if need_dx else None
         b = self._bucket
+        pre, self._head_pre = getattr(self, "_head_pre", None), None
+        if pre is not None and pre[0] is dL_dout:            # fused classifier head: dX already produced with the loss
+            dX = pre[1]
+            aux = bool(self._aux_lane and self._defer_update)
+            if aux:
+                check(lib.okl_aux_mark(ctx.h))
+                check(lib.okl_aux_begin(ctx.h, self._aux_lane))
+            try:
+                check(lib.okl_dense_bwd(ctx.h, self.inputs._dptr(NCX), b.ptr(0), dL_dout._dptr(NCX), None, b.grad_ptr(0),
+                                        b.grad_ptr(1), M, K, N, None))
+                b.step(lr, self._defer_update)
+            finally:
+                if aux:
+                    check(lib.okl_aux_end(ctx.h))
+            return dX
+        dX = Tensor._empty((M, K), np.float64) if need_dx else None
         xp, gp, wp = self.inputs._dptr(NCX), dL_dout._dptr(NCX), b.ptr(0)
         mask = xp if (need_dx and self._dx_relu_mask) else None
         if getattr(self, "_bf16_path", False) and ctx.precision == _lib.BF16:

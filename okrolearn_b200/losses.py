@@ -122,6 +122,26 @@ class CrossEntropyLoss:
         tptr = tbuf if isinstance(tbuf, int) else tbuf.ptr
         sm = self._fuse_softmax          # NeuralNetwork fast path: the softmax layer whose backward is computed right here
         dz = Tensor._empty((rows, cols), np.float64) if (sm is not None and sm.outputs is outputs) else None
+        head = getattr(outputs, "_head_of", None)
+        if dz is not None and head is not None and getattr(outputs, "_lazy_fn", None) is not None and head.outputs is outputs:
+            # the probabilities have not been computed yet: Dense -> Softmax -> CE forward and backward down to the dense
+            # layer's dX in one kernel
+            outputs._lazy_fn = None
+            x = head.inputs
+            K = x.shape[1]
+            dx = Tensor._empty((rows, K), np.float64) if getattr(head, "_need_dx", True) else None
+            xp = x._dptr(NCX)
+            check(lib.okl_dense_softmax_ce(ctx.h, xp, head._bucket.ptr(0), head._bucket.ptr(1), tptr, outputs._ptr_raw(), loss.ptr,
+                                           grad._ptr_raw(), dz._ptr_raw(), dx._ptr_raw() if dx is not None else None,
+                                           xp if (dx is not None and head._dx_relu_mask) else None, rows, K, cols,
+                                           float(rows * ctx.nranks), self._loss_accum))
+            outputs._touch()
+            head._head_pre = (dz, dx)
+            sm._precomputed = (grad, dz)
+            self.outputs, self.targets = outputs, targets
+            self._grad = grad
+            self._loss = LossValue(loss)
+            return self._loss
         check(lib.okl_ce_fwd_bwd(ctx.h, outputs._dptr(NCX), tptr, loss.ptr, grad._ptr_raw(), rows, cols, float(rows * ctx.nranks),
                                  self._loss_accum, dz._ptr_raw() if dz is not None else None))
         if dz is not None:

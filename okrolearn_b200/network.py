@@ -38,14 +38,22 @@ from .layers import (apply_pending_updates, ParamArena, _ParamLayer, _Activation
 from .losses import CrossEntropyLoss, MSELoss, LossValue
 
 
-class _StepState:
-    """Static device buffers a captured train step reads its batch from, plus the graph itself."""
+class _Slot:
+    """One of the two input slots of the train loop: static device buffers a captured step reads its batch from + that graph."""
 
     def __init__(self, ctx, batch_size, sample_shape, t_row):
         self.xin = Tensor._empty((batch_size,) + tuple(sample_shape), np.float32)
         self.tin = _DevBuf(ctx, max(batch_size * t_row, 1) * 4)
-        self.eloss = _DevBuf(ctx, 4)
         self.graph = None
+
+
+class _StepState:
+    """Per (batch shape, loss, layer list) state of train(): two input slots (step s+1's batch is gathered into the other slot
+    while step s computes), the epoch-loss accumulator both graphs add to, and whether an eager warm-up step has run."""
+
+    def __init__(self, ctx, batch_size, sample_shape, t_row):
+        self.slots = [_Slot(ctx, batch_size, sample_shape, t_row), _Slot(ctx, batch_size, sample_shape, t_row)]
+        self.eloss = _DevBuf(ctx, 4)
         self.warm = False
 
 
@@ -81,6 +89,9 @@ class NeuralNetwork:
         self.fuse_activations = os.environ.get("OKL_FUSE", "1") != "0"
         self.skip_input_grad = os.environ.get("OKL_SKIP_INPUT_GRAD", "1") != "0"
         self.fuse_conv_pool = os.environ.get("OKL_FUSE_CONV_POOL", "1") != "0"
+        self.fuse_head = os.environ.get("OKL_FUSE_HEAD", "1") != "0"
+        self.prefetch_batches = os.environ.get("OKL_PREFETCH", "1") != "0"
+        self.early_exchange = os.environ.get("OKL_EARLY_EXCHANGE", "1") != "0"
         self.use_aux_lanes = os.environ.get("OKL_AUX_LANES", "1") != "0"
         self.arena_bytes = int(os.environ.get("OKL_ARENA_BYTES", str(64 << 20)))   # networks up to this size share one arena
         self.stream_inputs = False          # keep the dataset on the host, copy each batch inside the step
@@ -192,7 +203,7 @@ class NeuralNetwork:
                     ('pre_forward', 'post_forward', 'pre_backward', 'post_backward')))
 
     def _plan(self, fast: bool):
-        key = (fast, self.fuse_activations, self.skip_input_grad, self.fuse_conv_pool, self.use_aux_lanes, tuple(id(l) for l in self.layers), get_ctx().nranks,
+        key = (fast, self.fuse_activations, self.skip_input_grad, self.fuse_conv_pool, self.fuse_head, self.use_aux_lanes, tuple(id(l) for l in self.layers), get_ctx().nranks,
                get_ctx().precision)
         if key == self._plan_key:
             return
@@ -208,6 +219,7 @@ class NeuralNetwork:
         for l in ls:
             if isinstance(l, _ParamLayer):
                 l._fused_act, l._need_dx, l._dx_relu_mask, l._aux_lane = ACT_NONE, True, False, 0
+                l._fused_head = False
                 l._defer_update = fast or get_ctx().nranks > 1
             if isinstance(l, _ConvBase):
                 l._fused_pool = None
@@ -249,6 +261,8 @@ class NeuralNetwork:
                 if (isinstance(a, DenseLayer) and isinstance(b, SoftmaxActivationLayer) and a.weights.shape[1] <= 16 and
                         a.weights.shape[0] * a.weights.shape[1] <= 12000):
                     a._fused_act, b._fused_into_prev = _lib.ACT_SOFTMAX, True
+                    # ... and when that pair ends the network, a CrossEntropyLoss computes the whole head in its own kernel
+                    a._fused_head = bool(self.fuse_head and b is ls[-1] and a.weights.shape[0] <= 256)
             for a, r, b in zip(ls, ls[1:], ls[2:]):      # Param(+ReLU fused) -> Param: relu' applied in the second layer's dX epilogue
                 if (isinstance(a, _ParamLayer) and isinstance(r, ReLUActivationLayer) and r._fused_into_prev and
                         isinstance(b, _ParamLayer)):
@@ -312,7 +326,18 @@ class NeuralNetwork:
     def _backward(self, loss_gradient: 'Tensor', lr: float):
         self._run_hooks('pre_backward', loss_gradient, lr)
         self.gradients = []
+        # data parallel + arena: once the backward pass reaches the first parametric layer every other layer's gradients are
+        # complete - their all-reduce starts now and overlaps that layer's backward
+        arena = getattr(self, "_arena", None) if (self.early_exchange and get_ctx().nranks > 1) else None
+        first = None
+        if arena is not None:
+            first = next((l for l in self.layers if isinstance(l, _ParamLayer)), None)
+            if first is None or first._bucket is not arena.buckets[0] or not all(
+                    l._defer_update and l._bucket.arena is arena for l in self.layers if isinstance(l, _ParamLayer)):
+                first = None
         for i, layer in reversed(list(enumerate(self.layers))):
+            if layer is first:
+                arena.exchange_tail()
             loss_gradient = layer.backward(loss_gradient, lr)
             self._log_gradient(i, loss_gradient)
         apply_pending_updates(self.layers)                 # deferred updates (fast path / data parallel): one launch
@@ -421,13 +446,27 @@ class NeuralNetwork:
         if not custom_loss:
             loss_function._loss_accum = st.eloss.ptr
 
-        def make_targets(rows):
+        def make_targets(rows, slot):
             if is_ce:
                 t = Tensor(np.zeros((0,)), requires_grad=False)
                 t._shape = (rows,) + t_shape
-                t._i32_dev = st.tin.ptr
+                t._i32_dev = slot.tin.ptr
                 return t
-            return Tensor._view(st.tin, 0, (rows,) + t_shape, np.float32, bound=False)
+            return Tensor._view(slot.tin, 0, (rows,) + t_shape, np.float32, bound=False)
+
+        def prefetch(batch):
+            """gather batch `batch` of the current permutation into slot batch % 2 on the copy stream"""
+            b0 = batch * batch_size
+            rows = min(b0 + batch_size, num_samples) - b0
+            sl = st.slots[batch & 1]
+            check(lib.okl_batch_prefetch(ctx.h, batch & 1, sl.xin._ptr_raw(), x_src, row_elems, sl.tin.ptr, t_src, t_row,
+                                         idx_dev.ptr + b0 * 4, rows))
+
+        lossf = C.c_float()
+
+        def collect(slot_idx):
+            check(lib.okl_loss_fetch_wait(ctx.h, slot_idx, C.byref(lossf)))
+            self.last_step_losses.append(float(lossf.value))
 
         for epoch in range(epochs):
             self._run_hooks('pre_epoch', epoch, epochs)
@@ -454,20 +493,30 @@ class NeuralNetwork:
             i32 = np.ascontiguousarray(perm_total.astype(np.int32))
             check(lib.okl_h2d_i32(ctx.h, idx_dev.ptr, i32.ctypes.data, i32.size, _lib.I32))
 
+            pipelined = bool(self.prefetch_batches)
+            if num_batches and pipelined:
+                prefetch(0)
+            pending_loss = None                      # slot whose loss copy is in flight (sync_loss_every_step, lag 1)
             for batch in range(num_batches):
                 b0 = batch * batch_size
                 b1 = min(b0 + batch_size, num_samples)
                 rows = b1 - b0
                 full = rows == batch_size
-                check(lib.okl_gather_rows(ctx.h, st.xin._ptr_raw(), x_src, idx_dev.ptr + b0 * 4, rows, row_elems))
-                check(lib.okl_gather_rows(ctx.h, st.tin.ptr, t_src, idx_dev.ptr + b0 * 4, rows, t_row))
-                if graph_ok and full and st.graph is not None:
-                    ctx.graph_launch(st.graph.handle)
-                    loss = st.graph.loss
+                sl = st.slots[batch & 1] if pipelined else st.slots[0]
+                if pipelined:
+                    if batch + 1 < num_batches:
+                        prefetch(batch + 1)          # overlaps this step; ordered after the previous user of that slot
+                    check(lib.okl_batch_wait(ctx.h, batch & 1))
                 else:
-                    st.xin._touch()
-                    bx = st.xin if full else Tensor._view(st.xin._buf, 0, (rows,) + sample_shape, np.float32, bound=False)
-                    bt = make_targets(rows)
+                    check(lib.okl_gather_batch(ctx.h, sl.xin._ptr_raw(), x_src, row_elems, sl.tin.ptr, t_src, t_row,
+                                               idx_dev.ptr + b0 * 4, rows))
+                if graph_ok and full and sl.graph is not None:
+                    ctx.graph_launch(sl.graph.handle)
+                    loss = sl.graph.loss
+                else:
+                    sl.xin._touch()
+                    bx = sl.xin if full else Tensor._view(sl.xin._buf, 0, (rows,) + sample_shape, np.float32, bound=False)
+                    bt = make_targets(rows, sl)
                     if graph_ok and full and st.warm:
                         keep = []
                         ctx._capture_keep = keep
@@ -478,9 +527,9 @@ class NeuralNetwork:
                             handle = ctx.graph_end()
                             ctx._capture_keep = None
                         keep.extend([outputs, loss, bx, bt])
-                        st.graph = _StepGraph(handle, keep, 0)
-                        st.graph.loss = loss
-                        ctx.graph_launch(st.graph.handle)
+                        sl.graph = _StepGraph(handle, keep, 0)
+                        sl.graph.loss = loss
+                        ctx.graph_launch(sl.graph.handle)
                     else:
                         outputs, loss = self._one_step(bx, bt, loss_function, current_lr, optimizer, fast)
                         if full:
@@ -490,7 +539,17 @@ class NeuralNetwork:
                 if custom_loss:                      # duck-typed user loss: its value lives on the host (okl.py:2973)
                     host_losses.append(float(np.sum(getattr(loss, "data", loss))))
                 if self.sync_loss_every_step:
-                    self.last_step_losses.append(float(loss))
+                    if isinstance(loss, LossValue) and pipelined:
+                        # the loss of every step reaches the host, one step late: its copy is enqueued behind the step and
+                        # collected after the NEXT step has been enqueued, so the device never waits for the host
+                        check(lib.okl_loss_fetch_async(ctx.h, batch & 1, loss._buf.ptr))
+                        if pending_loss is not None:
+                            collect(pending_loss)
+                        pending_loss = batch & 1
+                    else:
+                        self.last_step_losses.append(float(loss))
+            if pending_loss is not None:
+                collect(pending_loss)
 
             if custom_loss:
                 avg_loss = float(np.sum(host_losses)) / num_batches

@@ -198,3 +198,55 @@ def test_full_size_mnist_cnn_step_properties(okl):
                           O.OracleFlatten(), O.OracleDense(d1.weights.data, d1.biases.data), O.OracleReLU(),
                           O.OracleDense(d2.weights.data, d2.biases.data), O.OracleSoftmax()])
     assert rel_err(p[:8], on.forward(X[:8].astype(np.float64))) < 1e-4
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_fused_classifier_head_equals_unfused_and_oracle(okl, graph):
+    """Dense(N<=16) -> Softmax -> CrossEntropy as ONE kernel (okl_dense_softmax_ce) must give the same parameters as the separate
+    dense / CE / dense-backward kernels (same summation orders => bit-identical) and match the oracle; short last batch included."""
+    rng = np.random.default_rng(33)
+    N, B = 56, 16                                   # 3 full batches + one of 8 rows
+    X = rng.standard_normal((N, 20)).astype(np.float32)
+    T = rng.integers(0, 10, N)
+    W1, W2 = rng.standard_normal((20, 16)) * 0.3, rng.standard_normal((16, 10)) * 0.3
+    res = {}
+    for fuse in (True, False):
+        net = okl.NeuralNetwork()
+        d1, d2 = okl.DenseLayer(20, 16), okl.DenseLayer(16, 10)
+        d1.weights.data, d2.weights.data = W1.copy(), W2.copy()
+        for l in (d1, okl.ReLUActivationLayer(), d2, okl.SoftmaxActivationLayer()):
+            net.add(l)
+        net.fuse_head, net.use_graph = fuse, graph
+        np.random.seed(3)
+        ls = net.train(okl.Tensor(X.copy()), okl.Tensor(T.copy()), epochs=2, lr_scheduler=okl.LearningRateScheduler(0.1),
+                       optimizer=okl.SGDOptimizer(), batch_size=B, loss_function=okl.CrossEntropyLoss())
+        assert d2._fused_head == fuse
+        res[fuse] = (np.array(ls), d1.weights.data.copy(), d1.biases.data.copy(), d2.weights.data.copy(), d2.biases.data.copy())
+    for a, b in zip(res[True][1:], res[False][1:]):
+        assert np.array_equal(a, b)
+    assert rel_err(res[True][0], res[False][0]) < 1e-6
+    on = O.OracleNetwork([O.OracleDense(W1, np.zeros((1, 16))), O.OracleReLU(), O.OracleDense(W2, np.zeros((1, 10))), O.OracleSoftmax()])
+    np.random.seed(3)
+    Xo, To, ol = X.astype(np.float64), T.copy(), []
+    for ep in range(2):
+        idx = np.arange(N)
+        np.random.shuffle(idx)
+        Xo, To = Xo[idx], To[idx]
+        ol.append(sum(on.train_step(Xo[s:s + B], To[s:s + B], O.OracleCrossEntropy(), 0.1) for s in range(0, N, B)) / 4)
+    assert rel_err(res[True][0], ol) < 2e-5
+    assert rel_err(res[True][1], on.layers[0].W) < TOL32 and rel_err(res[True][3], on.layers[2].W) < TOL32
+    assert rel_err(res[True][2], on.layers[0].b) < 2e-5 and rel_err(res[True][4], on.layers[2].b) < 2e-5
+
+
+def test_fused_head_output_still_readable(okl):
+    """The head's probabilities are materialised on demand when something other than CrossEntropyLoss reads them first."""
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((8, 12))
+    net = okl.NeuralNetwork()
+    d = okl.DenseLayer(12, 5)
+    net.add(d)
+    net.add(okl.SoftmaxActivationLayer())
+    out = net._forward(okl.Tensor(X), _fast=True)
+    assert d._fused_head
+    z = X @ d.weights.data + d.biases.data
+    assert rel_err(out.data, O.softmax_forward(z)) < TOL32
