@@ -18,6 +18,7 @@ struct okl_graph {
   unsigned long long launches = 0;
 };
 
+#define OKL_FLOW_DEPTH 8
 struct okl_ctx {
   int device = 0;
   int precision = OKL_FP32;
@@ -66,6 +67,7 @@ struct okl_ctx {
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
   bool comm_pending = false;
+  int comm_p2p_kind = 0;                // peer-memory exchange in flight on the comm stream: 0 none, 1 two-shot, 2 packet (LL)
   unsigned long long* tl_buf = nullptr; // debug timeline: one globaltimer stamp after every kernel (okl_debug_timeline_*)
   int tl_n = 0;
   std::vector<std::string> tl_names;
@@ -74,6 +76,8 @@ struct okl_ctx {
   cudaEvent_t ev_copy_fork = nullptr, ev_slot[2] = {nullptr, nullptr}, ev_loss[2] = {nullptr, nullptr};
   float* loss_pinned = nullptr;         // 2 slots x {value, sequence number}
   unsigned loss_seq[2] = {0, 0};
+  cudaEvent_t ev_flow[8] = {};
+  unsigned long long flow_next = 0;
   int pdl = 0;                          // programmatic dependent launch: 0 off (default: measured no gain), 1 on except while an aux lane is forked, 2 always
 };
 
@@ -189,3 +193,4 @@ int okl_dense_small_bwd(okl_ctx*, const float* X, const float* W, const float* G
 // peer-memory (NVLink) all-reduce for small buckets: okl_p2p.cu
 bool okl_p2p_applicable(okl_ctx*, const void* p, size_t count);
 int okl_p2p_allreduce(okl_ctx*, void* p, size_t count);
+bool okl_p2p_is_ll(size_t count);

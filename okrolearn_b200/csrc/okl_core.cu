@@ -142,6 +142,7 @@ static int ensure_pipeline(okl_ctx* ctx) {
     OKL_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->ev_slot[i], cudaEventDisableTiming));
     OKL_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->ev_loss[i], cudaEventDisableTiming));
   }
+  for (int i = 0; i < OKL_FLOW_DEPTH; i++) OKL_CHECK_CUDA(cudaEventCreateWithFlags(&ctx->ev_flow[i], cudaEventDisableTiming));
   OKL_CHECK_CUDA(cudaMallocHost(&ctx->loss_pinned, 4 * sizeof(float)));
   memset(ctx->loss_pinned, 0, 4 * sizeof(float));
   return OKL_OK;
@@ -153,6 +154,10 @@ extern "C" int okl_batch_prefetch(okl_ctx* ctx, int slot, void* x_dst, const voi
   OKL_REQUIRE(!ctx->capturing && ctx->cur_lane == 0, "okl_batch_prefetch: not inside a capture / auxiliary lane");
   int s = ensure_pipeline(ctx);
   if (s != OKL_OK) return s;
+  // flow control: the host may run at most OKL_FLOW_DEPTH batches ahead of the device (an unbounded launch backlog occasionally
+  // made step times bimodal; a depth of 1-2 makes the device wait for host wake-ups)
+  const int fi = ctx->flow_next % OKL_FLOW_DEPTH;
+  if (ctx->flow_next >= OKL_FLOW_DEPTH) OKL_CHECK_CUDA(cudaEventSynchronize(ctx->ev_flow[fi]));
   OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_copy_fork, ctx->stream));
   OKL_CHECK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_fork, 0));
   cudaStream_t main_stream = ctx->stream;
@@ -161,6 +166,8 @@ extern "C" int okl_batch_prefetch(okl_ctx* ctx, int slot, void* x_dst, const voi
   ctx->stream = main_stream;
   if (s != OKL_OK) return s;
   OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_slot[slot], ctx->copy_stream));
+  OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_flow[fi], ctx->copy_stream));
+  ctx->flow_next++;
   return OKL_OK;
 }
 
@@ -222,6 +229,7 @@ extern "C" int okl_ctx_destroy(okl_ctx* ctx) {
     cudaStreamDestroy(ctx->copy_stream);
     cudaEventDestroy(ctx->ev_copy_fork);
     for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_slot[i]); cudaEventDestroy(ctx->ev_loss[i]); }
+    for (int i = 0; i < OKL_FLOW_DEPTH; i++) cudaEventDestroy(ctx->ev_flow[i]);
     cudaFreeHost(ctx->loss_pinned);
   }
   okl_aux_join(ctx);
@@ -705,11 +713,17 @@ extern "C" int okl_comm_destroy(okl_ctx* ctx) {
   return OKL_OK;
 }
 
+extern "C" int okl_comm_wait(okl_ctx* ctx);
 extern "C" int okl_allreduce_async(okl_ctx* ctx, void* p, size_t count) {
   OKL_REQUIRE(ctx && p, "NULL argument");
   if (ctx->nranks == 1 || count == 0) return OKL_OK;
-  if (okl_p2p_applicable(ctx, p, count))            // small bucket inside the symmetric buffer: one peer-memory kernel, no NCCL
+  if (okl_p2p_applicable(ctx, p, count)) {          // small bucket inside the symmetric buffer: one peer-memory kernel, no NCCL
+    if (ctx->comm_pending && ctx->comm_p2p_kind == (okl_p2p_is_ll(count) ? 2 : 1)) {   // same flags / staging in flight: serialise
+      int s = okl_comm_wait(ctx);
+      if (s != OKL_OK) return s;
+    }
     return okl_p2p_allreduce(ctx, p, count);
+  }
   OKL_REQUIRE(ctx->nccl_comm, "okl_allreduce_async: communicator not initialised");
   // fork: comm stream waits for everything enqueued so far on the compute stream (works under capture too)
   OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
@@ -735,6 +749,7 @@ extern "C" int okl_allreduce_fork(okl_ctx* ctx, void* p, size_t count) {
   }
   ctx->comm_pending = true;
   if (okl_p2p_applicable(ctx, p, count)) {
+    ctx->comm_p2p_kind = okl_p2p_is_ll(count) ? 2 : 1;
     cudaStream_t main_stream = ctx->stream;
     ctx->stream = ctx->comm_stream;
     int s = okl_p2p_allreduce(ctx, p, count);
@@ -752,6 +767,7 @@ extern "C" int okl_comm_wait(okl_ctx* ctx) {
   OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_join, ctx->comm_stream));
   OKL_CHECK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
   ctx->comm_pending = false;
+  ctx->comm_p2p_kind = 0;
   return OKL_OK;
 }
 

@@ -15,13 +15,21 @@
 namespace {
 
 constexpr int P2P_MAX_RANKS = 8;
-constexpr size_t P2P_HDR_BYTES = 4096;      // flags + counters at the start of the symmetric buffer
+constexpr size_t P2P_FLAGS_BYTES = 4096;    // flags + counters at the start of the symmetric buffer
+// one-shot "LL" exchange for tiny buckets (NCCL's low-latency protocol): a 16-byte packet carries two floats and two copies of the
+// sequence number and is written with ONE store, so the receiver needs no separate flag, fence or barrier - it polls the packet
+// itself.  Latency = one one-way NVLink trip instead of the four of the two-shot kernel (ready, pull, push-ack, done).
+constexpr int LL_MAX_FLOATS = 4096;
+constexpr int LL_PKTS = LL_MAX_FLOATS / 2;
+constexpr size_t LL_BYTES = (size_t)2 * P2P_MAX_RANKS * LL_PKTS * 16;   // [parity][source rank][packet]
+constexpr size_t P2P_HDR_BYTES = P2P_FLAGS_BYTES + LL_BYTES;
 
 struct P2PHeader {                          // lives at the start of every rank's symmetric buffer
   unsigned ready[P2P_MAX_RANKS];            // ready[p] = last sequence number for which rank p's gradients are complete
   unsigned done[P2P_MAX_RANKS];             // done[p]  = last sequence number for which rank p has written its slice everywhere
   unsigned seq;                             // sequence number of the last completed all-reduce on this rank
   unsigned cta_count;                       // CTAs of the running kernel that have finished their writes
+  unsigned ll_seq;                          // sequence number of the last completed LL all-reduce on this rank
 };
 
 struct P2PPeers {
@@ -87,6 +95,59 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PPeers peers
       __threadfence();
     }
   }
+}
+
+__device__ __forceinline__ uint4* ll_slot(P2PHeader* h, unsigned par, int src, int i) {
+  return reinterpret_cast<uint4*>(reinterpret_cast<char*>(h) + P2P_FLAGS_BYTES) + ((size_t)(par * P2P_MAX_RANKS + src) * LL_PKTS + i);
+}
+
+// One CTA.  Every rank pushes its whole vector, as packets, into slot [parity][rank] of every peer, then sums the R contributions
+// in rank order (its own from the gradient buffer, the others polled out of its own staging area) - the same order on every
+// rank, so all ranks end with identical bits.  Staging alternates between two halves by sequence parity: a rank can only start
+// all-reduce s+2 after s+1 completed, which needed every peer's s+1 packets, which they sent after finishing s - so nobody still
+// reads the half that s+2 overwrites.
+__global__ void __launch_bounds__(1024) p2p_ll_allreduce_kernel(const P2PPeers peers, const int rank, const int nranks, const size_t off,
+                                                                const int n) {
+  P2PHeader* me = peers.hdr[rank];
+  const unsigned s = me->ll_seq + 1, par = s & 1u;
+  float* mine = peers.data[rank] + off;
+  const int npk = n >> 1;
+  for (int i = threadIdx.x; i < npk; i += blockDim.x) {
+    const float2 v = *reinterpret_cast<const float2*>(mine + 2 * i);
+    const uint4 pk = make_uint4(__float_as_uint(v.x), s, __float_as_uint(v.y), s);
+#pragma unroll
+    for (int p = 0; p < P2P_MAX_RANKS; p++)
+      if (p < nranks && p != rank) {
+        uint4* dst = ll_slot(peers.hdr[p], par, rank, i);
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+      }
+  }
+  for (int i = threadIdx.x; i < npk; i += blockDim.x) {
+    const float2 v = *reinterpret_cast<const float2*>(mine + 2 * i);
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < P2P_MAX_RANKS; r++)
+      if (r < nranks) {
+        float2 c = v;
+        if (r != rank) {
+          const uint4* src = ll_slot(me, par, r, i);
+          uint4 q;
+          const long long t0 = clock64();
+          do {
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(src) : "memory");
+            if (clock64() - t0 > 20000000000LL) {
+              printf("okl p2p LL all-reduce: timed out waiting for rank %d (seq %u)\n", r, s);
+              __trap();
+            }
+          } while (q.y != s || q.w != s);
+          c = make_float2(__uint_as_float(q.x), __uint_as_float(q.z));
+        }
+        if (r == 0) acc = c; else { acc.x += c.x; acc.y += c.y; }
+      }
+    *reinterpret_cast<float2*>(mine + 2 * i) = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) me->ll_seq = s;
 }
 
 struct P2PState {
@@ -170,6 +231,9 @@ bool okl_p2p_applicable(okl_ctx* ctx, const void* p, size_t count) {
   return q >= lo && q + count * 4 <= (const char*)st.base + st.bytes && ((q - lo) & 15) == 0 && (count & 3) == 0;
 }
 
+// tiny buckets use the packet kernel, which has its own sequence counter and may run concurrently with a two-shot exchange
+bool okl_p2p_is_ll(size_t count) { return count <= (size_t)LL_MAX_FLOATS; }
+
 int okl_p2p_allreduce(okl_ctx* ctx, void* p, size_t count) {
   P2PState& st = g_p2p[ctx];
   P2PPeers peers;
@@ -178,10 +242,20 @@ int okl_p2p_allreduce(okl_ctx* ctx, void* p, size_t count) {
     peers.hdr[r] = (P2PHeader*)st.peer_base[r];
     peers.data[r] = (float*)((char*)st.peer_base[r] + P2P_HDR_BYTES);
   }
+  if (count <= (size_t)LL_MAX_FLOATS) {                  // tiny bucket: one-shot packet exchange, one CTA
+    const size_t off = ((char*)p - ((char*)st.base + P2P_HDR_BYTES)) / 4;
+    const int npk = (int)(count / 2);
+    int threads = (npk + 31) / 32 * 32;
+    if (threads > 1024) threads = 1024;
+    if (threads < 32) threads = 32;
+    p2p_ll_allreduce_kernel<<<1, threads, 0, ctx->stream>>>(peers, ctx->rank, ctx->nranks, off, (int)count);
+    OKL_LAUNCHED(ctx, "p2p_ll_allreduce");
+    return OKL_OK;
+  }
   const size_t off4 = ((char*)p - ((char*)st.base + P2P_HDR_BYTES)) / 16, n4 = count / 4;
   const size_t chunk = (n4 + ctx->nranks - 1) / ctx->nranks;
-  int grid = (int)((chunk + 511) / 512);
-  if (grid > 64) grid = 64;
+  int grid = (int)((chunk + 511) / 512);                 // one float4 per thread: the exchange is latency-, not bandwidth-bound
+  if (grid > 2 * ctx->sm_count) grid = 2 * ctx->sm_count;
   if (grid < 1) grid = 1;
   p2p_allreduce_kernel<<<grid, 512, 0, ctx->stream>>>(peers, ctx->rank, ctx->nranks, off4, n4);
   OKL_LAUNCHED(ctx, "p2p_allreduce");

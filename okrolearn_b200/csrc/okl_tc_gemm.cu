@@ -703,6 +703,14 @@ int okl_tc_gemm_raw(okl_ctx* ctx, int kind, int a_mn, int b_mn, int M, int N, in
   int bn = env_int("OKL_TC_BN", 0);
   const int tiles_m = (M + TC_BM - 1) / TC_BM;
   const int kb_total = (K + bk - 1) / bk;
+  // a GEMM on an auxiliary lane (a weight gradient) runs NEXT TO the main lane's kernel (the matching dX GEMM): it gets a CTA
+  // budget that lets both be resident at once instead of queueing for SMs behind it
+  const int sm_budget = (ctx->cur_lane != 0 && env_int("OKL_TC_AUX_BUDGET", 1)) ? ctx->sm_count * 42 / 100 : ctx->sm_count;
+  if (bn == 0 && sm_budget < ctx->sm_count) {
+    auto tiles = [&](int b) { return (long long)tiles_m * ((N + b - 1) / b); };
+    for (int b = 64; b <= 256 && bn == 0; b *= 2)             // smallest tile (most CTAs) that stays within the budget
+      if (tiles(b) <= sm_budget && (b == 64 || N > b / 2)) bn = b;
+  }
   if (bn == 0) {
     auto tiles = [&](int b) { return (long long)tiles_m * ((N + b - 1) / b); };
     if (N > 128 && tiles(256) >= ctx->sm_count) bn = 256;
@@ -723,7 +731,7 @@ int okl_tc_gemm_raw(okl_ctx* ctx, int kind, int a_mn, int b_mn, int M, int N, in
     // 128-bit accesses
     const long long tiles = (long long)tiles_m * tiles_n;
     const bool can_split = (N & 3) == 0 && (ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0 && tiles <= 2048;
-    int max_splits = (int)(ctx->sm_count / tiles);
+    int max_splits = (int)(sm_budget / tiles);
     if (max_splits > kb_total / 4) max_splits = kb_total / 4;
     if (max_splits > 32) max_splits = 32;
     if (max_splits < 1 || !can_split) max_splits = 1;

@@ -223,7 +223,6 @@ def apply_pending_updates(layers):
     if arena is not None and len(bs) == len(arena.buckets) and all(b.arena is arena for b in bs):
         if ctx.nranks > 1:
             if arena._tail_exchanged:                      # the rest is already in flight: only the first bucket is left
-                check(lib.okl_comm_wait(ctx.h))
                 check(lib.okl_allreduce_async(ctx.h, arena.grad.ptr, arena.buckets[0].total))
                 arena._tail_exchanged = False
             else:

@@ -14,6 +14,8 @@ from okrolearn_b200 import _lib  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "mnist_cnn"
 okl.set_precision(sys.argv[2] if len(sys.argv) > 2 else "tf32")
+from okrolearn_b200 import dist  # noqa: E402
+rank, world = dist.init_data_parallel()
 ctx = okl.get_ctx()
 raw = C.CDLL(_lib.lib._name)
 w = bench.WORKLOADS[name]
@@ -24,7 +26,7 @@ logging.getLogger("NeuralNetwork").setLevel(logging.CRITICAL)
 loss_fn = okl.CrossEntropyLoss() if w["loss"] == "ce" else okl.MSELoss()
 lr = 1e-9 if name == "mlp8192" else 0.01
 sched, opt = okl.LearningRateScheduler(lr), okl.SGDOptimizer(lr=lr)
-X, T = bench.synth(name, B * 6, 0)
+X, T = bench.synth(name, B * 6, rank)
 tX, tT = okl.Tensor(X), okl.Tensor(T)
 tX._dptr()
 net.train(tX, tT, 1, sched, opt, B, loss_fn)            # allocations, workspace growth
@@ -38,6 +40,8 @@ out = (C.c_ulonglong * 4096)()
 names = C.create_string_buffer(1 << 18)
 n = C.c_int()
 assert raw.okl_debug_timeline_read(ctx.h, out, 4096, names, 1 << 18, C.byref(n)) == 0
+if rank != 0:
+    sys.exit(0)
 labels = names.value.decode().split("\n")[:n.value]
 ts = [out[i] for i in range(n.value)]
 cal = ts[1] - ts[0]

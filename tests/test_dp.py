@@ -65,3 +65,9 @@ def test_dp_nccl_world2_matches_single_process_oracle():
     finally:
         del os.environ["OKL_P2P"]
     assert res2["w_err"] < 2e-5 and not res2["p2p"]
+    os.environ["OKL_EARLY_EXCHANGE"] = "0"           # one all-reduce after the whole backward instead of the overlapped tail
+    try:
+        res3 = run_workers("nccl", 2, 29547)
+    finally:
+        del os.environ["OKL_EARLY_EXCHANGE"]
+    assert res3["w_err"] < 2e-5
