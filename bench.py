@@ -455,10 +455,12 @@ def main():
         net.stream_inputs, net.sync_loss_every_step = False, False
         t_bytes = B * 4 if w["loss"] == "ce" else int(np.prod(out_shape(name, B))) * 4
         e2e = {"value": round(world * B * K / dt, 1), "unit": "samples/s", "h2d_bytes_per_step": int(B * np.prod(w["sample"]) * 4 + t_bytes),
-               "d2h_bytes_per_step": 4, "ms_per_step": round(dt / K * 1e3, 4),
-               "api": "NeuralNetwork.train(Tensor.wrap(pinned host ndarray), ...) with stream_inputs (every step gathers its shuffled "
-                      "batch rows host->device from the pinned dataset inside the step) and sync_loss_every_step (loss read back to "
-                      "the host after every step)"}
+               "d2h_bytes_per_step": 8, "ms_per_step": round(dt / K * 1e3, 4),
+               "api": "NeuralNetwork.train(Tensor.wrap(pinned host ndarray), ...) with stream_inputs (every step's shuffled batch "
+                      "rows are gathered host->device over PCIe from the pinned dataset, on a copy stream while the previous step "
+                      "computes - double-buffered input slots) and sync_loss_every_step (every step's loss {value, sequence "
+                      "number} is posted to pinned host memory behind its step and collected by the host one step later); "
+                      "wall clock around the whole call incl. the final sync"}
 
     if rank != 0:
         return 0

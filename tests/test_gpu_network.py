@@ -250,3 +250,35 @@ def test_fused_head_output_still_readable(okl):
     assert d._fused_head
     z = X @ d.weights.data + d.biases.data
     assert rel_err(out.data, O.softmax_forward(z)) < TOL32
+
+
+def test_pipelined_train_loop_equals_inline_loop(okl):
+    """Double-buffered batch prefetch (copy stream) + lagged per-step loss read-back must give exactly what the inline loop
+    (gather on the compute stream, blocking loss read) gives: same parameters bit for bit, same per-step losses, including a short
+    last batch and two epochs (slot parity crosses the epoch boundary); host-resident (pinned) and device-resident datasets."""
+    rng = np.random.default_rng(17)
+    N, B = 88, 16                                   # 5 full batches + one of 8 rows
+    X = rng.standard_normal((N, 1, 12, 12)).astype(np.float32)
+    T = rng.integers(0, 10, N)
+    g = {"Wc1": rng.standard_normal((4, 1, 3, 3)) * 0.3, "Wd1": rng.standard_normal((100, 16)) * 0.1, "Wd2": rng.standard_normal((16, 10)) * 0.1}
+    res = {}
+    for mode in ("inline", "prefetch", "prefetch_stream"):
+        net, conv, d1, d2 = cnn_small(okl, g)
+        net.prefetch_batches = mode != "inline"
+        net.stream_inputs = mode == "prefetch_stream"
+        net.sync_loss_every_step = True
+        np.random.seed(11)
+        if mode == "prefetch_stream":
+            pX = okl.pinned_empty(X.shape, np.float32)
+            pX[...] = X
+            tx = okl.Tensor.wrap(pX)
+        else:
+            tx = okl.Tensor(X.copy())
+        ls = net.train(tx, okl.Tensor(T.copy()), epochs=2, lr_scheduler=okl.LearningRateScheduler(0.05), optimizer=okl.SGDOptimizer(),
+                       batch_size=B, loss_function=okl.CrossEntropyLoss())
+        assert len(net.last_step_losses) == 12      # every step of both epochs
+        res[mode] = (np.array(ls), np.array(net.last_step_losses), conv.filters.data.copy(), d1.weights.data.copy(), d2.weights.data.copy())
+    for mode in ("prefetch", "prefetch_stream"):
+        for a, b in zip(res[mode], res["inline"]):
+            assert np.array_equal(a, b), mode
+    assert abs(res["inline"][1][6:].mean() - res["inline"][0][-1]) < 1e-6  # epoch loss = mean of its step losses
