@@ -131,8 +131,8 @@ __global__ void gather_rows4_kernel(float4* __restrict__ dst, const float4* __re
 // one batch = the rows idx[0..rows) of the inputs (float4 granules) AND of the targets (32-bit words), in one launch.  The
 // source may be page-locked HOST memory (zero-copy over PCIe, ~2 us per round trip): every thread keeps GB_U independent loads in
 // flight and the grid covers the batch in a single pass, so the transfer is bound by the link, not by latency.
-constexpr int GB_U = 4;
-__global__ void __launch_bounds__(256) gather_batch_kernel(float4* __restrict__ xd, const float4* __restrict__ xs, long long xrow4,
+constexpr int GB_U = 8, GB_THREADS = 128;
+__global__ void __launch_bounds__(GB_THREADS) gather_batch_kernel(float4* __restrict__ xd, const float4* __restrict__ xs, long long xrow4,
                                                            unsigned* __restrict__ td, const unsigned* __restrict__ ts, long long trow,
                                                            const int* __restrict__ idx, long long rows) {
   okl_pdl_sync();
@@ -671,9 +671,13 @@ extern "C" int okl_gather_batch(okl_ctx* ctx, void* x_dst, const void* x_src, lo
   if (rows <= 0) return OKL_OK;
   if (x_row_elems > 0 && t_row_elems > 0 && (x_row_elems & 3) == 0 && aligned16(x_dst) && aligned16(x_src)) {
     const size_t total = (size_t)rows * (x_row_elems / 4 + t_row_elems);
-    size_t blocks = (total + 256 * GB_U - 1) / (256 * GB_U);
-    if (blocks > (size_t)ctx->sm_count * 8) blocks = (size_t)ctx->sm_count * 8;
-    okl_launch(ctx, gather_batch_kernel, dim3((unsigned)blocks), dim3(256), 0, (float4*)x_dst, (const float4*)x_src,
+    // the gather runs NEXT TO the compute kernels of the previous step (copy stream): few, small blocks with many loads in flight
+    // per thread, so it does not take a register-file slot away from a whole wave of a compute kernel on every SM
+    size_t blocks = (total + (size_t)GB_THREADS * GB_U * 4 - 1) / ((size_t)GB_THREADS * GB_U * 4);     // ~4 rounds per thread
+    if (blocks < 16) blocks = 16;
+    if (blocks > (size_t)ctx->sm_count * 4) blocks = (size_t)ctx->sm_count * 4;
+    if (blocks * GB_THREADS * GB_U > total + GB_THREADS * GB_U) blocks = (total + GB_THREADS * GB_U - 1) / (GB_THREADS * GB_U);
+    okl_launch(ctx, gather_batch_kernel, dim3((unsigned)blocks), dim3(GB_THREADS), 0, (float4*)x_dst, (const float4*)x_src,
                x_row_elems / 4, (unsigned*)t_dst, (const unsigned*)t_src, t_row_elems, (const int*)idx, rows);
     OKL_LAUNCHED(ctx, "gather_batch");
     return OKL_OK;
