@@ -279,7 +279,7 @@ def kernel_rooflines(okl, ctx, name, batch, peaks):
         xp, wp, gp = X._dptr(), W._dptr(), G._dptr()
         cases = [
             ("dense1_wgrad (dW = X^T G, 5408x128, K=256)", lambda: check(lib.okl_dense_bwd(ctx.h, xp, wp, gp, None, dW._ptr_raw(), None, M, K, N, None)),
-             2.0 * M * K * N, 4.0 * (M * K + M * N + K * N), "tc_gemm_kernel<0, 1, 1, 64, 0>"),
+             2.0 * M * K * N, 4.0 * (M * K + M * N + K * N), "tc_gemm_kernel<0, 1, 1,"),
             ("dense1_fwd (Y = X W, 256x5408x128)", lambda: check(lib.okl_dense_fwd(ctx.h, xp, wp, None, Y._ptr_raw(), M, K, N, 1)),
              2.0 * M * K * N, 4.0 * (M * K + K * N + M * N), "tc_gemm_kernel<0, 0, 1, 64, 0>"),
             ("dense1_dgrad (dX = G W^T)", lambda: check(lib.okl_dense_bwd(ctx.h, xp, wp, gp, dX._ptr_raw(), None, None, M, K, N, None)),
