@@ -199,8 +199,11 @@ int okl_ce_fwd_bwd(okl_ctx* ctx, const void* p, const void* targets_i32, void* l
 int okl_dense_softmax_ce(okl_ctx* ctx, const void* X, const void* W, const void* b, const void* targets_i32, void* P, void* loss,
                          void* grad, void* dZ, void* dX, const void* dx_relu_mask, int M, int K, int N, float denom,
                          void* loss_accum);
-/* loss[0] = sum((o-t)^2) / n ; grad = 2 (o - t) / denom   (denom = global element count) */
-int okl_mse_fwd_bwd(okl_ctx* ctx, const void* o, const void* t, void* loss, void* grad, size_t n, float denom, void* loss_accum);
+/* loss[0] = sum((o-t)^2) / n ; grad = 2 (o - t) / denom   (denom = global element count).
+ * relu_outputs != 0: o is the output of a ReLU whose backward (g * (x > 0), okl.py:107; y > 0 <=> x > 0) is applied here, i.e.
+ * grad is already the gradient w.r.t. the ReLU's input - one pass over the outputs instead of two. */
+int okl_mse_fwd_bwd(okl_ctx* ctx, const void* o, const void* t, void* loss, void* grad, size_t n, float denom, void* loss_accum,
+                    int relu_outputs);
 int okl_read_scalar(okl_ctx* ctx, const void* dev_f32, float* out);
 
 /* ------------------------------------------------------------------ parameter updates

@@ -94,7 +94,7 @@ SIGNATURES = {
     "okl_softmax_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i]),
     "okl_ce_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp]),
     "okl_dense_softmax_ce": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
-    "okl_mse_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _f, _vp]),
+    "okl_mse_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _f, _vp, _i]),
     "okl_read_scalar": (_i, [_vp, _vp, _P(_f)]),
     "okl_accum_update": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _vp]),
     "okl_accum_update_multi": (_i, [_vp, _i, _P(_vp), _P(_vp), _P(_vp), _P(_sz), _f, _vp]),

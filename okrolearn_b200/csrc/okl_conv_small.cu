@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(256) conv_smallk_fprop(const float* __restrict
 // Fast path: unit stride along the innermost dimension, KH x KW window known at compile time.  Each thread produces TWO
 // adjacent outputs of a row for OT = 32 channels at a time: one (KW+1)-wide input window per filter row feeds both outputs,
 // one broadcast LDS.128 of four filter taps feeds eight FMAs, and every channel's pair is written with one 64-bit store.
-template <int KH, int KW, bool PAD>
-__global__ void __launch_bounds__(256, 2) conv_smallk_fprop2(const float* __restrict__ x, const float* __restrict__ W,
+template <int KH, int KW, bool PAD, int THREADS = 256, int MINB = 2>
+__global__ void __launch_bounds__(THREADS, MINB) conv_smallk_fprop2(const float* __restrict__ x, const float* __restrict__ W,
                                                             const float* __restrict__ b, float* __restrict__ y, const ConvGeom g,
                                                             const int K, const int Opad, const int act, const FastDiv dPairs,
                                                             const int total) {
@@ -196,13 +196,14 @@ conv_smallk_wgrad(const float* __restrict__ x, const float* __restrict__ gy, flo
   __shared__ int ktap[KT];          // packed (td, th, tw) of tap k for the padding bounds checks
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int o_base = blockIdx.y * WG_OB;
+  const int k0 = blockIdx.z * KT;                             // this block's slice of the K + 1 taps (large K: several slices)
   const int p = tid & (WG_PT - 1), half = tid >> 7;          // this thread stages position p, rows half, half+2, ...
   static_assert(WG_OB % 2 == 0, "two staging threads per position");
   if (tid < KT) {
     int off = 0, pk = 0;
-    if (tid < K) {
+    if (k0 + tid < K) {
       unsigned u, tw, th, td;
-      g.dKW.divmod((unsigned)tid, u, tw); g.dKH.divmod(u, u, th); g.dKD.divmod(u, u, td);
+      g.dKW.divmod((unsigned)(k0 + tid), u, tw); g.dKH.divmod(u, u, th); g.dKD.divmod(u, u, td);
       off = (int)(u * g.xs[1] + td * g.xs[2] + th * g.xs[3] + tw * g.xs[4]);
       pk = (int)((td << 20) | (th << 10) | tw);
     }
@@ -236,7 +237,7 @@ conv_smallk_wgrad(const float* __restrict__ x, const float* __restrict__ gy, flo
     for (int i = 0; i < NX; i++) {
       const int k = half + 2 * i;
       float v = 0.f;
-      if (k < K && ok) {
+      if (k0 + k < K && ok) {
         bool in = true;
         if (PAD) {
           const int pk = ktap[k];
@@ -244,7 +245,7 @@ conv_smallk_wgrad(const float* __restrict__ x, const float* __restrict__ gy, flo
                (unsigned)(iw0 + (pk & 1023)) < (unsigned)g.I[2];
         }
         if (in) v = __ldg(xb + koff[k]);
-      } else if (k == K && ok) {
+      } else if (k0 + k == K && ok) {
         v = 1.f;                                              // the all-ones tap: column K accumulates the bias gradient
       }
       xnext[i] = v;
@@ -268,11 +269,12 @@ conv_smallk_wgrad(const float* __restrict__ x, const float* __restrict__ gy, flo
     for (int k = 0; k < KT; k++) {
       const float4 xv = *reinterpret_cast<const float4*>(&xs[k][lane * 4]);
 #pragma unroll
-      for (int i = 0; i < 4; i++) acc[i][k] += gv[i].x * xv.x + gv[i].y * xv.y + gv[i].z * xv.z + gv[i].w * xv.w;
+      for (int i = 0; i < 4; i++)
+        acc[i][k] = fmaf(gv[i].w, xv.w, fmaf(gv[i].z, xv.z, fmaf(gv[i].y, xv.y, fmaf(gv[i].x, xv.x, acc[i][k]))));
     }
   }
   // combine the 32 lanes (fixed butterfly order), lane 0 writes partial[block][o][k]
-  float* out = partial + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * WG_OB + warp * 4) * KT;
+  float* out = partial + ((size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * WG_OB + warp * 4) * KT;
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -287,13 +289,14 @@ conv_smallk_wgrad(const float* __restrict__ x, const float* __restrict__ gy, flo
 // dW[o, k] = sum_b partial[y][b][o_local][k] (k < K) ; db[o] = sum_b partial[...][K].  One warp per output element: the
 // lanes stride over the blocks' partials (independent loads), then a fixed-order butterfly.
 __global__ void conv_smallk_wgrad_reduce(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ db, int O, int K,
-                                         int KT, int gx, int OB) {
+                                         int KT, int gx, int OB, int gy) {
   okl_pdl_sync();
   const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (idx >= O * (K + 1)) return;
   const int o = idx / (K + 1), k = idx - o * (K + 1);
   const int oy = o / OB, ol = o - oy * OB;
-  const float* p = partial + ((size_t)oy * gx * OB + ol) * KT + k;
+  const int kz = k / KT, kl = k - kz * KT;                    // tap slice (blockIdx.z of the producer) and column inside it
+  const float* p = partial + ((size_t)(kz * gy + oy) * gx * OB + ol) * KT + kl;
   float s = 0.f;
   for (int b = lane; b < gx; b += 32) s += p[(size_t)b * OB * KT];
 #pragma unroll
@@ -318,7 +321,13 @@ bool okl_conv_small_wgrad_ok(const okl_conv_desc* d) {
   if (d->x_layout != OKL_NCX && d->C != 1) return false;
   long long K = d->C;
   for (int i = 0; i < d->nd; i++) K *= d->k[i];
-  return K + 1 <= 28;
+  return K <= 96 && K + 1 <= 28 * 4;                                     // up to four 28-tap slices (video 3x3x3x3: K + 1 = 82 -> 3 slices)
+}
+
+static bool env_flag_fprop3() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("OKL_FPROP2_SMALLBLOCK"); v = e ? atoi(e) : 1; }
+  return v != 0;
 }
 
 template <int KH, int KW>
@@ -328,10 +337,26 @@ static int launch_fprop2(okl_ctx* ctx, const ConvGeom& g, const float* x, const 
   const int npairs = (g.Oe[2] + 1) / 2;
   const long long total_ll = (long long)g.N * g.Oe[0] * g.Oe[1] * npairs;
   const int total = (int)total_ll;
+  const bool pad = g.P[0] || g.P[1] || g.P[2];
+  if (env_flag_fprop3()) {
+    // the fully unrolled KH x KW body with 64 accumulators needs ~160 registers; at the 128 the two-blocks-of-256
+    // variant allows, the accumulators spill inside the FMA loop (1 local load per 3 FMAs, measured 15x off the FMA peak).
+    // Three blocks of 128 threads with up to 170 registers keep everything in registers.
+    int grid3 = (total + 127) / 128;
+    if (grid3 > ctx->sm_count * 24) grid3 = ctx->sm_count * 24;
+    if (pad) {
+      if (smem > 48 * 1024) cudaFuncSetAttribute(conv_smallk_fprop2<KH, KW, true, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      conv_smallk_fprop2<KH, KW, true, 128, 3><<<grid3, 128, smem, ctx->stream>>>(x, W, b, y, g, K, Opad, act, FastDiv((unsigned)npairs), total);
+    } else {
+      if (smem > 48 * 1024) cudaFuncSetAttribute(conv_smallk_fprop2<KH, KW, false, 128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      conv_smallk_fprop2<KH, KW, false, 128, 3><<<grid3, 128, smem, ctx->stream>>>(x, W, b, y, g, K, Opad, act, FastDiv((unsigned)npairs), total);
+    }
+    OKL_LAUNCHED(ctx, "conv_smallk_fprop2_3d");
+    return OKL_OK;
+  }
   int grid = (total + 255) / 256;
   const int cap = ctx->sm_count * 16;
   if (grid > cap) grid = cap;
-  const bool pad = g.P[0] || g.P[1] || g.P[2];
   if (pad) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(conv_smallk_fprop2<KH, KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     conv_smallk_fprop2<KH, KW, true><<<grid, 256, smem, ctx->stream>>>(x, W, b, y, g, K, Opad, act, FastDiv((unsigned)npairs), total);
@@ -372,15 +397,16 @@ int okl_conv_small_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const float* x, c
   if (s != OKL_OK) return s;
   const int Mpix = g.N * g.Oe[0] * g.Oe[1] * g.Oe[2], K = g.C * g.T;
   const int KT = K + 1 <= 12 ? 12 : 28;
+  const int gz = (K + 1 + KT - 1) / KT;                       // tap slices
   const int ntiles = (Mpix + WG_PT - 1) / WG_PT;
   const int gy_ = (g.O + WG_OB - 1) / WG_OB;
-  int gx = ((KT <= 12 ? 4 : 2) * ctx->sm_count + gy_ - 1) / gy_;
+  int gx = ((KT <= 12 ? 4 : 2) * ctx->sm_count) / (gy_ * gz);  // floor: whole waves of resident blocks (2 / 1 per SM), no straggler wave
   if (gx > ntiles) gx = ntiles;
   if (gx < 1) gx = 1;
-  s = okl_ensure_workspace(ctx, (size_t)gx * gy_ * WG_OB * KT * sizeof(float));
+  s = okl_ensure_workspace(ctx, (size_t)gx * gy_ * gz * WG_OB * KT * sizeof(float));
   if (s != OKL_OK) return s;
   float* partial = (float*)ctx->workspace;
-  dim3 grid(gx, gy_);
+  dim3 grid(gx, gy_, gz);
   const bool pad = g.P[0] || g.P[1] || g.P[2];
   OKL_REQUIRE(g.Kk[0] < 1024 && g.Kk[1] < 1024 && g.Kk[2] < 1024, "filter extent too large");
   if (KT == 12) {
@@ -392,7 +418,7 @@ int okl_conv_small_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const float* x, c
   }
   OKL_LAUNCHED(ctx, "conv_smallk_wgrad");
   const int total = g.O * (K + 1);
-  okl_launch(ctx, conv_smallk_wgrad_reduce, dim3((total * 32 + 255) / 256), dim3(256), 0, (const float*)partial, dW, db, g.O, K, KT, gx, WG_OB);
+  okl_launch(ctx, conv_smallk_wgrad_reduce, dim3((total * 32 + 255) / 256), dim3(256), 0, (const float*)partial, dW, db, g.O, K, KT, gx, WG_OB, gy_);
   OKL_LAUNCHED(ctx, "conv_smallk_wgrad_reduce");
   return OKL_OK;
 }
@@ -645,7 +671,7 @@ extern "C" int okl_conv_relu_pool_wgrad(okl_ctx* ctx, const okl_conv_desc* d, co
   OKL_LAUNCHED(ctx, "conv_relu_pool2_wgrad");
   const int total = g.O * (K + 1);
   okl_launch(ctx, conv_smallk_wgrad_reduce, dim3((total * 32 + 255) / 256), dim3(256), 0, (const float*)partial, (float*)dW, (float*)db, g.O, K, KT,
-             gx, CP_OB);
+             gx, CP_OB, gy_);
   OKL_LAUNCHED(ctx, "conv_smallk_wgrad_reduce");
   return OKL_OK;
 }

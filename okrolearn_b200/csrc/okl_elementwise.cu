@@ -444,15 +444,40 @@ __global__ void ce_fused_rowthread_kernel(const float* __restrict__ p, const int
   }
 }
 
+// RELU: the outputs come from a ReLU whose backward is applied right here (g * (o > 0), okl.py:107): one pass over o instead of two
+template <bool RELU>
 __global__ void mse_kernel(const float* __restrict__ o, const float* __restrict__ t, float* __restrict__ partial, float* __restrict__ grad,
                            size_t n, float scale) {
   __shared__ float sh[32];
   float s = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    float d = o[i] - t[i];
+    const float ov = o[i], d = ov - t[i];
     s += d * d;
-    grad[i] = d * scale;                                               // 2 (o - t) / denom, okl.py:1838
+    grad[i] = (RELU && !(ov > 0.f)) ? 0.f : d * scale;                 // 2 (o - t) / denom, okl.py:1838
   }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+// 128-bit variant (n % 4 == 0, 16-byte aligned pointers): two independent float4 pairs in flight per thread
+template <bool RELU>
+__global__ void __launch_bounds__(256) mse_kernel4(const float4* __restrict__ o, const float4* __restrict__ t, float* __restrict__ partial,
+                                                   float4* __restrict__ grad, size_t n4, float scale) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  auto one = [&](const float4 a, const float4 b) {
+    const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;
+    s += dx * dx + dy * dy + dz * dz + dw * dw;
+    return make_float4((RELU && !(a.x > 0.f)) ? 0.f : dx * scale, (RELU && !(a.y > 0.f)) ? 0.f : dy * scale,
+                       (RELU && !(a.z > 0.f)) ? 0.f : dz * scale, (RELU && !(a.w > 0.f)) ? 0.f : dw * scale);
+  };
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  for (; i + stride < n4; i += 2 * stride) {
+    const float4 a0 = o[i], b0 = t[i], a1 = o[i + stride], b1 = t[i + stride];
+    grad[i] = one(a0, b0);
+    grad[i + stride] = one(a1, b1);
+  }
+  if (i < n4) grad[i] = one(o[i], t[i]);
   s = block_sum(s, sh);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
@@ -814,15 +839,24 @@ extern "C" int okl_ce_fwd_bwd(okl_ctx* ctx, const void* p, const void* t, void* 
 }
 
 extern "C" int okl_mse_fwd_bwd(okl_ctx* ctx, const void* o, const void* t, void* loss, void* grad, size_t n, float denom,
-                               void* loss_accum) {
+                               void* loss_accum, int relu_outputs) {
   OKL_REQUIRE(ctx && o && t && loss && grad, "NULL argument");
   OKL_REQUIRE(n >= 1 && denom > 0.f, "bad mse shape");
-  int grid = okl_grid_1d(ctx, n, 256, 4);
+  const bool vec = (n & 3) == 0 && aligned16(o) && aligned16(t) && aligned16(grad);
+  int grid = vec ? okl_grid_1d(ctx, n / 4, 256, 2) : okl_grid_1d(ctx, n, 256, 4);
+  if (vec && grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
   int s = okl_ensure_workspace(ctx, (size_t)grid * sizeof(float));
   if (s != OKL_OK) return s;
-  mse_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)o, (const float*)t, (float*)ctx->workspace, (float*)grad, n, 2.f / denom);
+  float* partial = (float*)ctx->workspace;
+  if (vec) {
+    if (relu_outputs) mse_kernel4<true><<<grid, 256, 0, ctx->stream>>>((const float4*)o, (const float4*)t, partial, (float4*)grad, n / 4, 2.f / denom);
+    else mse_kernel4<false><<<grid, 256, 0, ctx->stream>>>((const float4*)o, (const float4*)t, partial, (float4*)grad, n / 4, 2.f / denom);
+  } else {
+    if (relu_outputs) mse_kernel<true><<<grid, 256, 0, ctx->stream>>>((const float*)o, (const float*)t, partial, (float*)grad, n, 2.f / denom);
+    else mse_kernel<false><<<grid, 256, 0, ctx->stream>>>((const float*)o, (const float*)t, partial, (float*)grad, n, 2.f / denom);
+  }
   OKL_LAUNCHED(ctx, "mse_fwd_bwd");
-  final_sum_kernel<<<1, 256, 0, ctx->stream>>>((const float*)ctx->workspace, grid, (float*)loss, 1.f / (float)n, (float*)loss_accum);
+  final_sum_kernel<<<1, 256, 0, ctx->stream>>>((const float*)partial, grid, (float*)loss, 1.f / (float)n, (float*)loss_accum);
   OKL_LAUNCHED(ctx, "final_sum");
   return OKL_OK;
 }

@@ -661,10 +661,13 @@ class ReLUActivationLayer(_Activation):
         self.outputs = self._fwd(inputs)
         return self.outputs
 
+    _precomputed = None          # gradient tensor an MSELoss already multiplied by relu' (NeuralNetwork fast path)
+
     def backward(self, dL_dout: Tensor, lr: float):
         if self._in_fused_block:
             return dL_dout
-        dx = _as_tensor(dL_dout) if self._bwd_fused_into_next else self._bwd(dL_dout, self.inputs)
+        pre, self._precomputed = self._precomputed, None
+        dx = _as_tensor(dL_dout) if (self._bwd_fused_into_next or (pre is not None and pre is dL_dout)) else self._bwd(dL_dout, self.inputs)
         if not self._fused_into_prev:            # fused: `inputs` IS the post-activation tensor, no separate pre-activation
             _set_input_grad(self.inputs, dx)
         return dx

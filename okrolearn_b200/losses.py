@@ -162,6 +162,7 @@ class CrossEntropyLoss:
 class MSELoss:
     """okl.py:1833-1839: mean((o - t)^2); gradient 2 (o - t) / t.size."""
     _loss_accum = None
+    _fuse_relu = None          # NeuralNetwork fast path: trailing ReLU layer whose backward is applied in the loss kernel
 
     def forward(self, outputs: Tensor, targets: Tensor):
         ctx = get_ctx()
@@ -170,8 +171,12 @@ class MSELoss:
         loss = _DevBuf(ctx, 4)
         grad = Tensor._empty(outputs.shape, np.float64)
         n = outputs.size
+        relu = self._fuse_relu
+        fuse = relu is not None and getattr(relu, "outputs", None) is outputs
         check(lib.okl_mse_fwd_bwd(ctx.h, outputs._dptr(NCX), targets._dptr(NCX), loss.ptr, grad._ptr_raw(), n, float(n * ctx.nranks),
-                                  self._loss_accum))
+                                  self._loss_accum, 1 if fuse else 0))
+        if fuse:
+            relu._precomputed = grad             # already g * (y > 0): the layer's backward passes it through
         self._grad = grad
         self._key = (id(outputs), id(targets))
         self._loss = LossValue(loss)

@@ -360,9 +360,12 @@ class NeuralNetwork:
     def _one_step(self, batch_inputs, batch_targets, loss_function, lr, optimizer, fast):
         """forward + loss + backward (+ optimizer for layers exposing parameters/gradients): okl.py:2969-2988."""
         outputs = self._forward(batch_inputs, _fast=fast) if fast else self.forward(batch_inputs)
+        last = self.layers[-1] if self.layers else None
         if isinstance(loss_function, CrossEntropyLoss):
-            last = self.layers[-1] if self.layers else None
             loss_function._fuse_softmax = last if (fast and isinstance(last, SoftmaxActivationLayer)) else None
+        elif type(loss_function) is MSELoss:      # trailing ReLU: its backward is applied inside the loss kernel
+            loss_function._fuse_relu = last if (fast and self.fuse_activations and isinstance(last, ReLUActivationLayer) and
+                                                self.temperature == 1.0 and not last._in_fused_block) else None
         loss = loss_function.forward(outputs, batch_targets)
         loss_gradient = loss_function.backward(outputs, batch_targets)
         if fast:

@@ -282,3 +282,38 @@ def test_pipelined_train_loop_equals_inline_loop(okl):
         for a, b in zip(res[mode], res["inline"]):
             assert np.array_equal(a, b), mode
     assert abs(res["inline"][1][6:].mean() - res["inline"][0][-1]) < 1e-6  # epoch loss = mean of its step losses
+
+
+@pytest.mark.parametrize("nd,fuse", [(3, True), (3, False), (1, True)])
+def test_conv_relu_mse_regression_train(okl, nd, fuse):
+    """Conv3D(3, 8, 3, 1, 1) / Conv1D(3, 8, 3, 1, 1) + ReLU trained against a random target with MSELoss (BASELINE configs[3] shape
+    family).  Fast path: ReLU in the conv epilogue, its backward inside the MSE kernel, tap-sliced small-K weight gradient (K + 1 =
+    82 > one 28-tap slice for the 3-D layer); must match the oracle network and the unfused path."""
+    okl.set_precision("fp32")
+    rng = np.random.default_rng(50 + nd)
+    sp = (5, 6, 7) if nd == 3 else (40,)
+    N, B = 6, 3
+    X = rng.standard_normal((N, 3) + sp).astype(np.float32)
+    X.reshape(-1)[0] = abs(X.reshape(-1)[0]) + 0.1
+    T = rng.standard_normal((N, 8) + sp).astype(np.float32)
+    W = (rng.standard_normal((8, 3) + (3,) * nd) * 0.2).astype(np.float32)
+    net = okl.NeuralNetwork()
+    conv = okl.Conv3DLayer(3, 8, 3, 1, 1) if nd == 3 else okl.Conv1DLayer(3, 8, 3, 1, 1)
+    (conv.filters if nd == 3 else conv.weights).data = W.copy()
+    net.add(conv)
+    net.add(okl.ReLUActivationLayer())
+    net.fuse_activations = fuse
+    np.random.seed(2)
+    ls = net.train(okl.Tensor(X.copy()), okl.Tensor(T.copy()), epochs=2, lr_scheduler=okl.LearningRateScheduler(0.05),
+                   optimizer=okl.SGDOptimizer(), batch_size=B, loss_function=okl.MSELoss())
+    on = O.OracleNetwork([O.OracleConv(W, np.zeros((8, 1)), 1, 1, fast=True), O.OracleReLU()])
+    np.random.seed(2)
+    Xo, To, ol = X.copy(), T.copy(), []
+    for ep in range(2):
+        idx = np.arange(N)
+        np.random.shuffle(idx)
+        Xo, To = Xo[idx], To[idx]
+        ol.append(sum(on.train_step(Xo[s:s + B], To[s:s + B], O.OracleMSE(), 0.05) for s in range(0, N, B)) / 2)
+    assert rel_err(ls, ol) < 2e-5
+    assert rel_err((conv.filters if nd == 3 else conv.weights).data, on.layers[0].W) < 5e-5
+    assert rel_err(conv.biases.data, on.layers[0].b) < 5e-5
