@@ -439,7 +439,11 @@ def main():
         def host_dataset(X, T):                      # the dataset as a user would hold it for streaming: page-locked host arrays
             pX = okl.pinned_empty(X.shape, np.float32)
             pX[...] = X
-            return okl.Tensor.wrap(pX), okl.Tensor(T)
+            if w["loss"] == "ce":
+                return okl.Tensor.wrap(pX), okl.Tensor(T)
+            pT = okl.pinned_empty(T.shape, np.float32)             # regression targets are as large as the outputs: pinned too
+            pT[...] = T
+            return okl.Tensor.wrap(pX), okl.Tensor.wrap(pT)
         hXw, hTw = host_dataset(Xw, Tw)
         net.train(hXw, hTw, 1, sched, opt, B, loss_fn)
         hX, hT = host_dataset(Xk, Tk)

@@ -177,6 +177,9 @@ int okl_tc_dense_fwd(okl_ctx*, const float* X, const float* W, const float* b, f
 int okl_tc_dense_dw(okl_ctx*, const float* X, const float* G, float* dW, int M, int K, int N);
 int okl_tc_dense_dx(okl_ctx*, const float* G, const float* W, float* dX, int M, int K, int N, const float* relu_mask);
 bool okl_tc_conv_supported(okl_ctx*, const okl_conv_desc*);
+bool okl_tc_conv_smallc_supported(okl_ctx*, const okl_conv_desc*);
+int okl_tc_conv_smallc_fprop(okl_ctx*, const okl_conv_desc*, const float* x, const float* W, const float* b, float* y);
+int okl_tc_conv_smallc_wgrad(okl_ctx*, const okl_conv_desc*, const float* x, const float* g, float* dW, float* db);
 int okl_tc_conv_fprop(okl_ctx*, const okl_conv_desc*, const float* x, const float* W, const float* b, float* y);
 int okl_tc_conv_dgrad(okl_ctx*, const okl_conv_desc*, const float* g, const float* W, float* dx, const float* relu_mask);
 int okl_tc_conv_wgrad(okl_ctx*, const okl_conv_desc*, const float* x, const float* g, float* dW);

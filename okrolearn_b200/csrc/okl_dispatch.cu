@@ -62,6 +62,8 @@ extern "C" int okl_conv_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void* 
   OKL_REQUIRE(d->act >= OKL_ACT_NONE && d->act <= OKL_ACT_TANH, "bad activation %d", d->act);
   if (d->N == 0) return OKL_OK;
   OKL_REQUIRE(x && W && y, "okl_conv_fprop: NULL tensor");
+  if (ctx->precision != OKL_FP32 && okl_tc_conv_smallc_supported(ctx, d))       // small C, many taps: im2col built in smem, tcgen05
+    return okl_tc_conv_smallc_fprop(ctx, d, (const float*)x, (const float*)W, (const float*)b, (float*)y);
   if (okl_conv_small_fprop_ok(d)) return okl_conv_small_fprop(ctx, d, (const float*)x, (const float*)W, (const float*)b, (float*)y);
   if (ctx->precision != OKL_FP32 && okl_tc_conv_supported(ctx, d))
     return okl_tc_conv_fprop(ctx, d, (const float*)x, (const float*)W, (const float*)b, (float*)y);
@@ -93,6 +95,8 @@ extern "C" int okl_conv_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* 
     return OKL_OK;
   }
   OKL_REQUIRE(x && g, "okl_conv_wgrad: NULL tensor");
+  if (ctx->precision != OKL_FP32 && okl_tc_conv_smallc_supported(ctx, d))
+    return okl_tc_conv_smallc_wgrad(ctx, d, (const float*)x, (const float*)g, (float*)dW, (float*)db);
   if (okl_conv_small_wgrad_ok(d)) return okl_conv_small_wgrad(ctx, d, (const float*)x, (const float*)g, (float*)dW, (float*)db);
   if (dW) {
     if (ctx->precision != OKL_FP32 && okl_tc_conv_supported(ctx, d))

@@ -16,6 +16,7 @@
 // Small problems are split along K over CTAs (fp32 partials in a workspace, reduced in fixed order by a second kernel
 // that applies the epilogue) so that e.g. the 256x5408x128 DenseLayer of the MNIST CNN still fills the 148 SMs.
 #include "common.cuh"
+#include "conv_geom.cuh"
 
 #include <cuda_bf16.h>
 
@@ -1251,5 +1252,386 @@ extern "C" int okl_conv_wgrad_bf16(okl_ctx* ctx, const okl_conv_desc* d, const v
     st = okl_channel_sum(ctx, (const float*)g, (float*)db, s.N, s.O, (long long)s.OH * s.OW, OKL_NXC);
     if (st != OKL_OK) return st;
   }
+  return OKL_OK;
+}
+
+// ================================================================================================ small-C convolution on tcgen05
+// First layers (video 3 x 3x3x3 -> K = 81, ...): C * taps + 1 <= 96 is far too small for the TMA implicit GEMM above (its k-blocks
+// are 32-channel slices of ONE tap) and the FFMA small-K kernels top out at ~25 % of the fp32 peak.  Here the im2col operand is
+// BUILT IN SHARED MEMORY by the CTA's own threads, directly in the canonical UMMA layout (K-major rows of 32 tf32 = 128 bytes,
+// 128-byte swizzle: 16-byte chunk index XOR (row & 7), 8-row groups 1024 bytes apart), and consumed by tcgen05.mma:
+//   fprop : D[128 pixels, O] = A[128 pixels, 96 taps] . W^T ; A built per tile (each thread: one pixel row, 12 x 16-byte chunks),
+//           W (96 x O, zero padded) built once per CTA; two TMEM accumulators, so the epilogue of tile i (TMEM lane = pixel ->
+//           every channel's store is a coalesced 128-byte line of the NC(D)HW output, bias + activation fused) overlaps the MMAs
+//           of tile i+1.
+//   wgrad : D[O, 96] = g^T[O, 32 pixels] . patch[96, 32 pixels]^T accumulated in TMEM over the CTA's share of all 32-pixel
+//           k-blocks (split-K over CTAs, fixed-order second-stage reduce); the g rows are 128-byte copies, patch row k is the
+//           input shifted by tap k (row K is all ones: its column of D is the bias gradient).
+// The padded rows / taps are zero, so they cost tensor-core time (irrelevant) but no memory traffic.
+namespace {
+
+constexpr int SC_K = 96;               // padded reduction extent (3 k-blocks of 32 tf32)
+constexpr int SC_THREADS = 256;
+
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {   // byte offset of element (row r, col c < 32) in a swizzled K-major tile
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 2) ^ (r & 7))) << 4) + ((c & 3) << 2));
+}
+
+struct ScParams {
+  const float* x; const float* W; const float* b; float* y;       // fprop
+  const float* gy; float* partial;                                 // wgrad
+  okl_conv::ConvGeom g;
+  okl_conv::FastDiv dSo;
+  int K, Mpix, So, act, ntiles, kb_per_img, kb_total, kb_per_cta;
+};
+
+struct ScTaps { int off[SC_K]; int pk[SC_K]; };                    // tap k -> offset from the window origin, packed (td, th, tw)
+
+__device__ __forceinline__ void sc_build_taps(ScTaps* t, const ScParams& p) {
+  for (int k = threadIdx.x; k < SC_K; k += blockDim.x) {
+    int off = 0, pk = 0;
+    if (k < p.K) {
+      unsigned u, tw, th, td;
+      p.g.dKW.divmod((unsigned)k, u, tw); p.g.dKH.divmod(u, u, th); p.g.dKD.divmod(u, u, td);
+      off = (int)(u * p.g.xs[1] + td * p.g.xs[2] + th * p.g.xs[3] + tw * p.g.xs[4]);
+      pk = (int)((td << 20) | (th << 10) | tw);
+    }
+    t->off[k] = off;
+    t->pk[k] = pk;
+  }
+}
+
+// value of tap k for the window whose origin is (id0, ih0, iw0) at xw
+__device__ __forceinline__ float sc_tap(const ScTaps* t, const ScParams& p, const float* xw, int id0, int ih0, int iw0, int k) {
+  const int pk = t->pk[k];
+  const bool in = (unsigned)(id0 + (pk >> 20)) < (unsigned)p.g.I[0] && (unsigned)(ih0 + ((pk >> 10) & 1023)) < (unsigned)p.g.I[1] &&
+                  (unsigned)(iw0 + (pk & 1023)) < (unsigned)p.g.I[2];
+  return in ? __ldg(xw + t->off[k]) : 0.f;
+}
+
+template <int NB>     // NB = padded output channels (UMMA N): 64 or 128
+__global__ void __launch_bounds__(SC_THREADS, 2) sc_fprop_kernel(const ScParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int A_KB = 128 * 128;                 // one k-block of A: 128 pixel rows x 128 bytes
+  constexpr int B_KB = NB * 128;
+  uint8_t* sA = smem;                             // [3 k-blocks][128 rows]
+  uint8_t* sB = smem + 3 * A_KB;                  // [3 k-blocks][NB rows]
+  uint64_t* mma_done = reinterpret_cast<uint64_t*>(sB + 3 * B_KB);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);             // [NB]
+  ScTaps* taps = reinterpret_cast<ScTaps*>(bias_s + NB);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(&mma_done[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<NB>(tmem_slot);
+  sc_build_taps(taps, p);
+  for (int i = tid; i < NB; i += SC_THREADS) bias_s[i] = (p.b && i < p.g.O) ? __ldg(p.b + i) : 0.f;
+  for (int i = tid; i < NB * SC_K; i += SC_THREADS) {          // weights, zero padded to NB x 96
+    const int o = i / SC_K, k = i - o * SC_K;
+    const float v = (o < p.g.O && k < p.K) ? __ldg(p.W + (size_t)o * p.K + k) : 0.f;
+    *reinterpret_cast<float*>(sB + (k >> 5) * B_KB + sw128_off(o, k & 31)) = v;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t idesc = make_idesc(0, false, false, 128, NB);
+
+  // This thread builds pixel row r of the 128 x 96 patch tile: chunks half*4 .. half*4+3 of each of the 3 k-blocks = 48 taps.
+  // The taps of the NEXT tile are loaded into registers one iteration ahead (latency overlaps the MMA and the epilogue stores).
+  const int r = tid & 127, half = tid >> 7;
+  float pv[48];
+  auto fetch = [&](int tile) {
+    const int m = tile * 128 + r;
+    const bool ok = m < p.Mpix;
+    unsigned t = 0, ow = 0, oh = 0, od = 0;
+    if (ok) { p.g.dOW.divmod((unsigned)m, t, ow); p.g.dOH.divmod(t, t, oh); p.g.dOD.divmod(t, t, od); }
+    const int id0 = (int)od * p.g.S[0] - p.g.P[0], ih0 = (int)oh * p.g.S[1] - p.g.P[1], iw0 = (int)ow * p.g.S[2] - p.g.P[2];
+    const float* xw = p.x + (size_t)t * p.g.xs[0] + (long long)id0 * p.g.xs[2] + (long long)ih0 * p.g.xs[3] + (long long)iw0 * p.g.xs[4];
+    // whole window inside the input (the common case): no per-tap bounds checks
+    const bool inner = ok && id0 >= 0 && id0 + p.g.Kk[0] <= p.g.I[0] && ih0 >= 0 && ih0 + p.g.Kk[1] <= p.g.I[1] && iw0 >= 0 &&
+                       iw0 + p.g.Kk[2] <= p.g.I[2];
+#pragma unroll
+    for (int kb = 0; kb < 3; kb++)
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int k = kb * 32 + (half * 4 + cc) * 4 + e;
+          float v = 0.f;
+          if (k < p.K) {
+            if (inner) v = __ldg(xw + taps->off[k]);
+            else if (ok) v = sc_tap(taps, p, xw, id0, ih0, iw0, k);
+          }
+          pv[(kb * 4 + cc) * 4 + e] = v;
+        }
+  };
+
+  uint32_t parity = 0;
+  if ((int)blockIdx.x < p.ntiles) fetch(blockIdx.x);
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+#pragma unroll
+    for (int kb = 0; kb < 3; kb++)
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) {
+        const int q = (kb * 4 + cc) * 4;
+        *reinterpret_cast<float4*>(sA + kb * A_KB + sw128_off(r, (half * 4 + cc) * 4)) = make_float4(pv[q], pv[q + 1], pv[q + 2], pv[q + 3]);
+      }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kb = 0; kb < 3; kb++) {
+        const uint64_t adesc = make_smem_desc(smem_u32(sA + kb * A_KB), 16, 1024, 2);
+        const uint64_t bdesc = make_smem_desc(smem_u32(sB + kb * B_KB), 16, 1024, 2);
+#pragma unroll
+        for (int k = 0; k < 4; k++) umma<0>(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+      }
+      umma_commit(&mma_done[0]);
+    }
+    if (tile + (int)gridDim.x < p.ntiles) fetch(tile + gridDim.x);
+    // ---- epilogue: TMEM lane = pixel, so every channel's store is one coalesced 128-byte line of the NC(D)HW output
+    mbar_wait(&mma_done[0], parity);
+    parity ^= 1;
+    tc_fence_after();
+    {
+      const int q = warp & 3;
+      const int m = tile * 128 + q * 32 + lane;
+      unsigned n = 0, sp = 0;
+      if (m < p.Mpix) p.dSo.divmod((unsigned)m, n, sp);
+      float* yb = p.y + (size_t)n * p.g.ys[0] + sp;
+#pragma unroll
+      for (int ch = (warp >> 2); ch < NB / 32; ch += 2) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+        tmem_ld_wait();
+        if (m < p.Mpix) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const int o = ch * 32 + j;
+            if (o < p.g.O) yb[(size_t)o * p.g.ys[1]] = act_apply(__uint_as_float(v[j]) + bias_s[o], p.act);
+          }
+        }
+      }
+    }
+    tc_fence_before();                            // the next tile's MMAs overwrite the accumulator only after the sync below
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<NB>(tmem_base);
+}
+
+constexpr int SCW_NST = 2;             // smem stages of the wgrad kernel (58 KB -> three CTAs per SM hide each other's load latency)
+constexpr int SCW_MAXA = 4;            // 16-byte chunks of g per thread and k-block (O <= 128: 128 * 8 / 256)
+constexpr int SCW_MAXB = SC_K / (SC_THREADS / 32);   // patch values per thread and k-block
+
+__global__ void __launch_bounds__(SC_THREADS, 3) sc_wgrad_kernel(const ScParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int A_BYTES = 128 * 128, B_BYTES = SC_K * 128, STAGE = A_BYTES + B_BYTES, NST = SCW_NST;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NST * STAGE);    // stage_free[NST], done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NST + 1);
+  ScTaps* taps = reinterpret_cast<ScTaps*>(tmem_slot + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i <= NST; i++) mbar_init(&bars[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<128>(tmem_slot);
+  sc_build_taps(taps, p);
+  for (int i = tid; i < NST * STAGE / 16; i += SC_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t idesc = make_idesc(0, false, false, 128, SC_K);
+
+  const int kb_begin = blockIdx.x * p.kb_per_cta, kb_end = min(p.kb_total, kb_begin + p.kb_per_cta);
+  const int na = (p.g.O * 8 + SC_THREADS - 1) / SC_THREADS;          // g chunks this thread copies per k-block
+  // registers holding the NEXT k-block's global data: the loads are issued one iteration ahead, so their latency overlaps the
+  // shared-memory stores, the barrier and the MMA issue of the current one (and the other resident CTAs' work)
+  float4 av[SCW_MAXA];
+  float bv[SCW_MAXB];
+  auto fetch = [&](int kb) {
+    const int n = kb / p.kb_per_img, p0 = (kb - n * p.kb_per_img) * 32;
+#pragma unroll
+    for (int q = 0; q < SCW_MAXA; q++) {
+      const int idx = tid + q * SC_THREADS, o = idx >> 3, c = idx & 7;
+      av[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < na && o < p.g.O && p0 + c * 4 < p.So)
+        av[q] = __ldg(reinterpret_cast<const float4*>(p.gy + (size_t)n * p.g.ys[0] + (size_t)o * p.g.ys[1] + p0 + c * 4));
+    }
+    const int sp = p0 + lane;
+    const bool ok = sp < p.So;
+    unsigned t = 0, ow = 0, oh = 0, od = 0;
+    if (ok) { p.g.dOW.divmod((unsigned)sp, t, ow); p.g.dOH.divmod(t, od, oh); }
+    const int id0 = (int)od * p.g.S[0] - p.g.P[0], ih0 = (int)oh * p.g.S[1] - p.g.P[1], iw0 = (int)ow * p.g.S[2] - p.g.P[2];
+    const float* xw = p.x + (size_t)n * p.g.xs[0] + (long long)id0 * p.g.xs[2] + (long long)ih0 * p.g.xs[3] + (long long)iw0 * p.g.xs[4];
+    const bool inner = ok && id0 >= 0 && id0 + p.g.Kk[0] <= p.g.I[0] && ih0 >= 0 && ih0 + p.g.Kk[1] <= p.g.I[1] && iw0 >= 0 &&
+                       iw0 + p.g.Kk[2] <= p.g.I[2];          // whole window inside the input: no per-tap bounds checks
+#pragma unroll
+    for (int q = 0; q < SCW_MAXB; q++) {
+      const int r = warp + q * (SC_THREADS / 32);
+      float v = 0.f;
+      if (ok && r <= p.K) v = r == p.K ? 1.f : (inner ? __ldg(xw + taps->off[r]) : sc_tap(taps, p, xw, id0, ih0, iw0, r));
+      bv[q] = v;
+    }
+  };
+  if (kb_begin < kb_end) fetch(kb_begin);
+  int i = 0;
+  for (int kb = kb_begin; kb < kb_end; kb++, i++) {
+    const int s = i % NST;
+    if (i >= NST) mbar_wait(&bars[s], (uint32_t)((i / NST - 1) & 1));      // the MMAs that read this stage NST k-blocks ago are done
+    uint8_t* a = smem + s * STAGE;
+    uint8_t* b = a + A_BYTES;
+    // A: row o = 32 consecutive pixels of channel o of the output gradient (one 128-byte line), as 16-byte chunks
+#pragma unroll
+    for (int q = 0; q < SCW_MAXA; q++) {
+      const int idx = tid + q * SC_THREADS, o = idx >> 3, c = idx & 7;
+      if (q < na && o < p.g.O) *reinterpret_cast<float4*>(a + sw128_off(o, c * 4)) = av[q];
+    }
+    // B: row k = the input shifted by tap k at the same 32 pixels; row K = ones (bias gradient); rows > K stay zero
+#pragma unroll
+    for (int q = 0; q < SCW_MAXB; q++) {
+      const int r = warp + q * (SC_THREADS / 32);
+      if (r <= p.K) *reinterpret_cast<float*>(b + sw128_off(r, lane)) = bv[q];
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (kb + 1 < kb_end) fetch(kb + 1);
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t adesc = make_smem_desc(smem_u32(a), 16, 1024, 2);
+      const uint64_t bdesc = make_smem_desc(smem_u32(b), 16, 1024, 2);
+#pragma unroll
+      for (int k = 0; k < 4; k++) umma<0>(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) ? 1u : 0u);
+      umma_commit(&bars[s]);
+    }
+  }
+  if (tid == 0) umma_commit(&bars[NST]);          // everything issued so far has completed when this barrier flips
+  mbar_wait(&bars[NST], 0);
+  tc_fence_after();
+  // D[o, k] -> partial[block][o][k]  (TMEM lane = o; three 32-column chunks)
+  {
+    const int q = warp & 3, o = q * 32 + lane;
+    for (int ch = (warp >> 2); ch < SC_K / 32; ch += 2) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+      tmem_ld_wait();
+      if (o < p.g.O && kb_begin < kb_end) {
+        float* dst = p.partial + ((size_t)blockIdx.x * p.g.O + o) * SC_K + ch * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<128>(tmem_base);
+}
+
+// dW[o, k] = sum_blocks partial[b][o][k], db[o] = sum_blocks partial[b][o][K]: one warp per output, fixed order
+__global__ void sc_wgrad_reduce(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ db, int O, int K, int nblk) {
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (idx >= O * (K + 1)) return;
+  const int o = idx / (K + 1), k = idx - o * (K + 1);
+  float s = 0.f;
+  for (int b = lane; b < nblk; b += 32) s += partial[((size_t)b * O + o) * SC_K + k];
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sft);
+  if (lane == 0) {
+    if (k < K) { if (dW) dW[(size_t)o * K + k] = s; }
+    else if (db) db[o] = s;
+  }
+}
+
+int sc_make_params(const okl_conv_desc* d, ScParams& p) {
+  int s = okl_conv::make_geom(d, p.g);
+  if (s != OKL_OK) return s;
+  p.K = p.g.C * p.g.T;
+  p.So = p.g.Oe[0] * p.g.Oe[1] * p.g.Oe[2];
+  p.Mpix = p.g.N * p.So;
+  p.dSo = okl_conv::FastDiv((unsigned)(p.So > 0 ? p.So : 1));
+  p.act = d->act;
+  return OKL_OK;
+}
+
+}  // namespace
+
+// K = C * taps in [48, 95] (smaller K: the direct kernels are already bound by the activation traffic), O <= 128, plain NC(D)HW
+// tensors, enough pixels to fill the chip; the 16-byte loads of the gradient need So % 4 == 0.
+bool okl_tc_conv_smallc_supported(okl_ctx* ctx, const okl_conv_desc* d) {
+  if (!d || ctx->cc < 100 || d->x_layout != OKL_NCX || d->y_layout != OKL_NCX) return false;
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("OKL_TC_SMALLC"); enabled = e ? atoi(e) : 1; }
+  if (!enabled) return false;
+  long long K = d->C, So = 1, taps_ok = 1;
+  for (int i = 0; i < d->nd; i++) {
+    K *= d->k[i];
+    if (d->k[i] >= 1024) taps_ok = 0;
+    const long long e = (d->in[i] + 2LL * d->p[i] - d->k[i]) / d->s[i] + 1;
+    So *= e;
+  }
+  return taps_ok && K >= 48 && K + 1 <= SC_K && d->O <= 128 && So % 4 == 0 && (long long)d->N * So >= 128LL * ctx->sm_count &&
+         (long long)d->N * So < (1LL << 30);
+}
+
+int okl_tc_conv_smallc_fprop(okl_ctx* ctx, const okl_conv_desc* d, const float* x, const float* W, const float* b, float* y) {
+  ScParams p;
+  memset(&p, 0, sizeof(p));
+  int s = sc_make_params(d, p);
+  if (s != OKL_OK) return s;
+  if (p.Mpix == 0) return OKL_OK;
+  p.x = x; p.W = W; p.b = b; p.y = y;
+  p.ntiles = (p.Mpix + 127) / 128;
+  const int grid = p.ntiles < 2 * ctx->sm_count ? p.ntiles : 2 * ctx->sm_count;      // two resident CTAs per SM
+  if (p.g.O <= 64) {
+    const int smem = 3 * 128 * 128 + 3 * 64 * 128 + 64 + 64 * 4 + (int)sizeof(ScTaps) + 1024;
+    static bool set = false;
+    if (!set) { OKL_CHECK_CUDA(cudaFuncSetAttribute(sc_fprop_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+    sc_fprop_kernel<64><<<grid, SC_THREADS, smem, ctx->stream>>>(p);
+  } else {
+    const int smem = 3 * 128 * 128 + 3 * 128 * 128 + 64 + 128 * 4 + (int)sizeof(ScTaps) + 1024;
+    static bool set = false;
+    if (!set) { OKL_CHECK_CUDA(cudaFuncSetAttribute(sc_fprop_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+    sc_fprop_kernel<128><<<grid, SC_THREADS, smem, ctx->stream>>>(p);
+  }
+  OKL_LAUNCHED(ctx, "tc_conv_smallc_fprop");
+  return OKL_OK;
+}
+
+int okl_tc_conv_smallc_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const float* x, const float* g, float* dW, float* db) {
+  ScParams p;
+  memset(&p, 0, sizeof(p));
+  int s = sc_make_params(d, p);
+  if (s != OKL_OK) return s;
+  p.x = x; p.gy = g;
+  p.kb_per_img = (p.So + 31) / 32;
+  p.kb_total = p.g.N * p.kb_per_img;
+  int grid = 3 * ctx->sm_count;                       // three resident CTAs per SM
+  if (grid > p.kb_total) grid = p.kb_total;
+  p.kb_per_cta = (p.kb_total + grid - 1) / grid;
+  grid = (p.kb_total + p.kb_per_cta - 1) / p.kb_per_cta;
+  s = okl_ensure_workspace(ctx, (size_t)grid * p.g.O * SC_K * sizeof(float));
+  if (s != OKL_OK) return s;
+  p.partial = (float*)ctx->workspace;
+  const int smem = SCW_NST * (128 * 128 + SC_K * 128) + 64 + (int)sizeof(ScTaps) + 1024;
+  static bool set = false;
+  if (!set) { OKL_CHECK_CUDA(cudaFuncSetAttribute(sc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+  sc_wgrad_kernel<<<grid, SC_THREADS, smem, ctx->stream>>>(p);
+  OKL_LAUNCHED(ctx, "tc_conv_smallc_wgrad");
+  const int total = p.g.O * (p.K + 1);
+  sc_wgrad_reduce<<<(total * 32 + 255) / 256, 256, 0, ctx->stream>>>(p.partial, dW, db, p.g.O, p.K, grid);
+  OKL_LAUNCHED(ctx, "tc_conv_smallc_wgrad_reduce");
   return OKL_OK;
 }

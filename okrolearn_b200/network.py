@@ -43,6 +43,7 @@ class _Slot:
 
     def __init__(self, ctx, batch_size, sample_shape, t_row):
         self.xin = Tensor._empty((batch_size,) + tuple(sample_shape), np.float32)
+        self.xbuf = self.xin._buf                  # the slot's own storage (layers only ever see views of it)
         self.tin = _DevBuf(ctx, max(batch_size * t_row, 1) * 4)
         self.graph = None
 
@@ -417,8 +418,12 @@ class NeuralNetwork:
                 pin_x = pinned_empty((num_samples, row_elems), np.float32)
                 np.copyto(pin_x, np.asarray(hx, dtype=np.float32).reshape(num_samples, row_elems))
             ht = np.asarray(targets._host if (targets._host is not None and not targets._dev_valid) else targets.data)
-            pin_t = pinned_empty((num_samples, t_row), np.int32 if is_ce else np.float32)
-            np.copyto(pin_t, ht.reshape(num_samples, t_row).astype(pin_t.dtype))
+            t_dtype = np.int32 if is_ce else np.float32
+            if ht.dtype == t_dtype and pinned_base(ht) is not None:
+                pin_t = ht.reshape(num_samples, t_row)                   # zero-copy: already pinned, already the device dtype
+            else:
+                pin_t = pinned_empty((num_samples, t_row), t_dtype)
+                np.copyto(pin_t, ht.reshape(num_samples, t_row).astype(t_dtype))
             x_src, t_src = pin_x.ctypes.data, pin_t.ctypes.data
             keep += [pin_x, pin_t]
         else:
@@ -462,7 +467,7 @@ class NeuralNetwork:
             b0 = batch * batch_size
             rows = min(b0 + batch_size, num_samples) - b0
             sl = st.slots[batch & 1]
-            check(lib.okl_batch_prefetch(ctx.h, batch & 1, sl.xin._ptr_raw(), x_src, row_elems, sl.tin.ptr, t_src, t_row,
+            check(lib.okl_batch_prefetch(ctx.h, batch & 1, sl.xbuf.ptr, x_src, row_elems, sl.tin.ptr, t_src, t_row,
                                          idx_dev.ptr + b0 * 4, rows))
 
         lossf = C.c_float()
@@ -511,14 +516,15 @@ class NeuralNetwork:
                         prefetch(batch + 1)          # overlaps this step; ordered after the previous user of that slot
                     check(lib.okl_batch_wait(ctx.h, batch & 1))
                 else:
-                    check(lib.okl_gather_batch(ctx.h, sl.xin._ptr_raw(), x_src, row_elems, sl.tin.ptr, t_src, t_row,
+                    check(lib.okl_gather_batch(ctx.h, sl.xbuf.ptr, x_src, row_elems, sl.tin.ptr, t_src, t_row,
                                                idx_dev.ptr + b0 * 4, rows))
                 if graph_ok and full and sl.graph is not None:
                     ctx.graph_launch(sl.graph.handle)
                     loss = sl.graph.loss
                 else:
-                    sl.xin._touch()
-                    bx = sl.xin if full else Tensor._view(sl.xin._buf, 0, (rows,) + sample_shape, np.float32, bound=False)
+                    # a fresh view per step: a layer may re-lay-out ITS input tensor (channels-last for the tensor-core convs),
+                    # which must never redirect or relabel the slot's own buffer - the gather keeps writing NC.. rows there
+                    bx = Tensor._view(sl.xbuf, 0, (rows,) + sample_shape, np.float32, bound=False)
                     bt = make_targets(rows, sl)
                     if graph_ok and full and st.warm:
                         keep = []

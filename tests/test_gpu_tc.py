@@ -187,3 +187,79 @@ def test_conv_implicit_gemm_bf16(okl, nd, N, C, sp, Oc, k, p):
         assert rel_err(Wt.grad, dW) < 1.5e-2 and rel_err(lay.biases.grad, db) < 1e-5
     finally:
         okl.set_precision("fp32")
+
+
+SMALLC_TC = [
+    # (nd, N, C, spatial, O, k, s, p): C * taps in [48, 95], enough pixels to fill the chip
+    (3, 2, 3, (8, 28, 44), 8, 3, 1, 1),        # video first layer shape family (K = 81), padding
+    (3, 2, 3, (10, 30, 46), 64, 3, 1, 0),      # no padding, all 64 accumulator columns used
+    (2, 4, 2, (72, 76), 20, 5, 1, 2),          # 2-D 5x5 (K = 50), O not a multiple of 16
+    (2, 6, 3, (160, 84), 70, 5, 2, 2),         # stride 2, O > 64 (128-column variant), K = 75
+]
+
+
+@pytest.mark.parametrize("nd,N,C,sp,Oc,k,s,p", SMALLC_TC)
+def test_conv_small_c_tcgen05(okl, nd, N, C, sp, Oc, k, s, p):
+    """Small-C convolution with the im2col operand built in shared memory in the UMMA layout (tcgen05 fprop + wgrad incl. the bias
+    gradient as the all-ones tap), TF32 mode vs the fp64 oracle through the layer API."""
+    okl.set_precision("tf32")
+    try:
+        rng = np.random.default_rng(N * 10 + C + Oc)
+        kt = O._tup(k, nd)
+        x = rng.standard_normal((N, C) + sp).astype(np.float32)
+        W = rng.standard_normal((Oc, C) + kt) * 0.1
+        b = rng.standard_normal((Oc, 1)) * 0.1
+        lay = okl.Conv3DLayer(C, Oc, kt, s, p) if nd == 3 else okl.Conv2DLayer(C, Oc, kt, s, p)
+        lay.filters.data = W.copy()
+        lay.biases.data = b.copy()
+        from okrolearn_b200 import _lib
+        ctx = _lib.get_ctx()
+        n0 = ctx.launch_count()
+        y = lay.forward(okl.Tensor(x))
+        x64 = x.astype(np.float64)
+        yo = O.conv_forward_fast(x64, W, b, s, p, dtype=np.float64)
+        assert rel_err(y.data, yo) < 3e-3
+        g = rng.standard_normal(yo.shape).astype(np.float32)
+        lay._need_dx = False
+        lay.backward(okl.Tensor(g), 0.05)
+        dW, db, _ = O.conv_backward_fast(x64, W, g.astype(np.float64), s, p)
+        assert rel_err(lay.filters.grad, dW) < 3e-3 and rel_err(lay.biases.grad, db) < 3e-3
+    finally:
+        okl.set_precision("fp32")
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_train_with_tensor_core_first_layer_sees_every_batch(okl, graph):
+    """A tensor-core-eligible FIRST layer re-lays-out its input (channels-last).  That must act on a per-step view: the train
+    loop's input slots keep receiving NC.. batches.  Regression test: several different batches, graph replay and eager, TF32 mode,
+    against the oracle network (a stale or mis-labelled slot buffer changes the losses by O(1))."""
+    okl.set_precision("tf32")
+    try:
+        rng = np.random.default_rng(77)
+        N, B, L = 64, 8, 160
+        X = rng.standard_normal((N, 32, L)).astype(np.float32)
+        X.reshape(-1)[0] = abs(X.reshape(-1)[0]) + 0.1
+        T = rng.standard_normal((N, 32, L)).astype(np.float32)
+        W = (rng.standard_normal((32, 32, 3)) * 0.1).astype(np.float32)
+        net = okl.NeuralNetwork()
+        conv = okl.Conv1DLayer(32, 32, 3, 1, 1)
+        assert conv._tc_eligible()
+        conv.weights.data = W.copy()
+        net.add(conv)
+        net.add(okl.ReLUActivationLayer())
+        net.use_graph = graph
+        np.random.seed(9)
+        ls = net.train(okl.Tensor(X.copy()), okl.Tensor(T.copy()), epochs=2, lr_scheduler=okl.LearningRateScheduler(0.1),
+                       optimizer=okl.SGDOptimizer(), batch_size=B, loss_function=okl.MSELoss())
+        on = O.OracleNetwork([O.OracleConv(W, np.zeros((32, 1)), 1, 1, fast=True), O.OracleReLU()])
+        np.random.seed(9)
+        Xo, To, ol = X.copy(), T.copy(), []
+        for ep in range(2):
+            idx = np.arange(N)
+            np.random.shuffle(idx)
+            Xo, To = Xo[idx], To[idx]
+            ol.append(sum(on.train_step(Xo[s:s + B], To[s:s + B], O.OracleMSE(), 0.1) for s in range(0, N, B)) / (N // B))
+        assert rel_err(ls, ol) < 2e-3
+        assert rel_err(conv.weights.data, on.layers[0].W) < 2e-2
+    finally:
+        okl.set_precision("fp32")
