@@ -1289,7 +1289,7 @@ struct ScTaps { int off[SC_K]; int pk[SC_K]; };                    // tap k -> o
 
 __device__ __forceinline__ void sc_build_taps(ScTaps* t, const ScParams& p) {
   for (int k = threadIdx.x; k < SC_K; k += blockDim.x) {
-    int off = 0, pk = 0;
+    int off = 0, pk = 31 << 20;                   // padding taps: bit 31 is never set in a window mask -> value 0, no load
     if (k < p.K) {
       unsigned u, tw, th, td;
       p.g.dKW.divmod((unsigned)k, u, tw); p.g.dKH.divmod(u, u, th); p.g.dKD.divmod(u, u, td);
@@ -1299,6 +1299,18 @@ __device__ __forceinline__ void sc_build_taps(ScTaps* t, const ScParams& p) {
     t->off[k] = off;
     t->pk[k] = pk;
   }
+}
+
+// bit t of the result = tap offset t of a window starting at i0 lies inside [0, I)   (k <= 16 taps per dimension)
+__device__ __forceinline__ unsigned sc_mask(int i0, int k, int I) {
+  const int lo = max(0, -i0), hi = min(k, I - i0);
+  return hi > lo ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+}
+// value of tap k given the window's three validity masks: ONE code path for interior and border pixels (no divergence)
+__device__ __forceinline__ float sc_tap_m(const ScTaps* t, const float* xw, unsigned dm, unsigned hm, unsigned wm, int k) {
+  const int pk = t->pk[k];
+  const unsigned in = (dm >> (pk >> 20)) & (hm >> ((pk >> 10) & 1023)) & (wm >> (pk & 1023)) & 1u;
+  return in ? __ldg(xw + t->off[k]) : 0.f;
 }
 
 // value of tap k for the window whose origin is (id0, ih0, iw0) at xw
@@ -1353,23 +1365,14 @@ __global__ void __launch_bounds__(SC_THREADS, 2) sc_fprop_kernel(const ScParams 
     if (ok) { p.g.dOW.divmod((unsigned)m, t, ow); p.g.dOH.divmod(t, t, oh); p.g.dOD.divmod(t, t, od); }
     const int id0 = (int)od * p.g.S[0] - p.g.P[0], ih0 = (int)oh * p.g.S[1] - p.g.P[1], iw0 = (int)ow * p.g.S[2] - p.g.P[2];
     const float* xw = p.x + (size_t)t * p.g.xs[0] + (long long)id0 * p.g.xs[2] + (long long)ih0 * p.g.xs[3] + (long long)iw0 * p.g.xs[4];
-    // whole window inside the input (the common case): no per-tap bounds checks
-    const bool inner = ok && id0 >= 0 && id0 + p.g.Kk[0] <= p.g.I[0] && ih0 >= 0 && ih0 + p.g.Kk[1] <= p.g.I[1] && iw0 >= 0 &&
-                       iw0 + p.g.Kk[2] <= p.g.I[2];
+    const unsigned dm = ok ? sc_mask(id0, p.g.Kk[0], p.g.I[0]) : 0u, hm = sc_mask(ih0, p.g.Kk[1], p.g.I[1]), wm = sc_mask(iw0, p.g.Kk[2], p.g.I[2]);
 #pragma unroll
     for (int kb = 0; kb < 3; kb++)
 #pragma unroll
       for (int cc = 0; cc < 4; cc++)
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const int k = kb * 32 + (half * 4 + cc) * 4 + e;
-          float v = 0.f;
-          if (k < p.K) {
-            if (inner) v = __ldg(xw + taps->off[k]);
-            else if (ok) v = sc_tap(taps, p, xw, id0, ih0, iw0, k);
-          }
-          pv[(kb * 4 + cc) * 4 + e] = v;
-        }
+        for (int e = 0; e < 4; e++)
+          pv[(kb * 4 + cc) * 4 + e] = sc_tap_m(taps, xw, dm, hm, wm, kb * 32 + (half * 4 + cc) * 4 + e);
   };
 
   uint32_t parity = 0;
@@ -1475,14 +1478,11 @@ __global__ void __launch_bounds__(SC_THREADS, 3) sc_wgrad_kernel(const ScParams 
     if (ok) { p.g.dOW.divmod((unsigned)sp, t, ow); p.g.dOH.divmod(t, od, oh); }
     const int id0 = (int)od * p.g.S[0] - p.g.P[0], ih0 = (int)oh * p.g.S[1] - p.g.P[1], iw0 = (int)ow * p.g.S[2] - p.g.P[2];
     const float* xw = p.x + (size_t)n * p.g.xs[0] + (long long)id0 * p.g.xs[2] + (long long)ih0 * p.g.xs[3] + (long long)iw0 * p.g.xs[4];
-    const bool inner = ok && id0 >= 0 && id0 + p.g.Kk[0] <= p.g.I[0] && ih0 >= 0 && ih0 + p.g.Kk[1] <= p.g.I[1] && iw0 >= 0 &&
-                       iw0 + p.g.Kk[2] <= p.g.I[2];          // whole window inside the input: no per-tap bounds checks
+    const unsigned dm = ok ? sc_mask(id0, p.g.Kk[0], p.g.I[0]) : 0u, hm = sc_mask(ih0, p.g.Kk[1], p.g.I[1]), wm = sc_mask(iw0, p.g.Kk[2], p.g.I[2]);
 #pragma unroll
     for (int q = 0; q < SCW_MAXB; q++) {
-      const int r = warp + q * (SC_THREADS / 32);
-      float v = 0.f;
-      if (ok && r <= p.K) v = r == p.K ? 1.f : (inner ? __ldg(xw + taps->off[r]) : sc_tap(taps, p, xw, id0, ih0, iw0, r));
-      bv[q] = v;
+      const int r = warp + q * (SC_THREADS / 32);                 // < 96: padding taps read as 0, row K is the ones row
+      bv[q] = (r == p.K) ? (ok ? 1.f : 0.f) : sc_tap_m(taps, xw, dm, hm, wm, r);
     }
   };
   if (kb_begin < kb_end) fetch(kb_begin);
@@ -1578,7 +1578,7 @@ bool okl_tc_conv_smallc_supported(okl_ctx* ctx, const okl_conv_desc* d) {
   long long K = d->C, So = 1, taps_ok = 1;
   for (int i = 0; i < d->nd; i++) {
     K *= d->k[i];
-    if (d->k[i] >= 1024) taps_ok = 0;
+    if (d->k[i] > 16) taps_ok = 0;
     const long long e = (d->in[i] + 2LL * d->p[i] - d->k[i]) / d->s[i] + 1;
     So *= e;
   }
