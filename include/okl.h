@@ -94,9 +94,11 @@ int okl_gather_batch(okl_ctx* ctx, void* x_dst, const void* x_src, long long x_r
 /* Batch pipeline of the train loop (okl.py:2963-2967 slices the next batch on the host between steps; here the gather of step
  * s+1's rows - from HBM, or over PCIe from page-locked host memory - runs on a copy stream WHILE step s computes).
  * okl_batch_prefetch: okl_gather_batch into input slot 0/1 on the copy stream, ordered after everything enqueued so far on the
- * compute stream (so the slot's previous consumer is finished); okl_batch_wait: the compute stream waits for that slot. */
+ * compute stream (so the slot's previous consumer is finished); okl_batch_wait: the compute stream waits for that slot.
+ * x_nxc_dst (optional): additionally a channels-last (N, S, C) copy of the gathered inputs, for a first layer that runs
+ * channels-last on the tensor cores - its layout permutation then overlaps the previous step too. */
 int okl_batch_prefetch(okl_ctx* ctx, int slot, void* x_dst, const void* x_src, long long x_row_elems, void* t_dst, const void* t_src,
-                       long long t_row_elems, const void* idx_i32, long long rows);
+                       long long t_row_elems, const void* idx_i32, long long rows, void* x_nxc_dst, int x_channels);
 int okl_batch_wait(okl_ctx* ctx, int slot);
 /* Per-step loss read-back (okl.py:2973 reads loss.data every batch) without stalling the device: _async copies the device scalar
  * to page-locked host memory in stream order (slot 0/1), _wait blocks the host until that copy has landed and returns it - called
@@ -204,6 +206,10 @@ int okl_dense_softmax_ce(okl_ctx* ctx, const void* X, const void* W, const void*
  * grad is already the gradient w.r.t. the ReLU's input - one pass over the outputs instead of two. */
 int okl_mse_fwd_bwd(okl_ctx* ctx, const void* o, const void* t, void* loss, void* grad, size_t n, float denom, void* loss_accum,
                     int relu_outputs);
+/* the same for outputs (and gradient) in channels-last layout (N, S, C) - what the tensor-core convolutions produce - against
+ * targets in the caller's (N, C, S) layout: the target tile is transposed on the fly, nothing is permuted in memory */
+int okl_mse_fwd_bwd_nxc(okl_ctx* ctx, const void* o_nxc, const void* t_ncx, void* loss, void* grad_nxc, int N, int C, long long S,
+                        float denom, void* loss_accum, int relu_outputs);
 int okl_read_scalar(okl_ctx* ctx, const void* dev_f32, float* out);
 
 /* ------------------------------------------------------------------ parameter updates

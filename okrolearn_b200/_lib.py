@@ -63,7 +63,7 @@ SIGNATURES = {
     "okl_permute": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i]),
     "okl_gather_rows": (_i, [_vp, _vp, _vp, _vp, _ll, _ll]),
     "okl_gather_batch": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll]),
-    "okl_batch_prefetch": (_i, [_vp, _i, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll]),
+    "okl_batch_prefetch": (_i, [_vp, _i, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _i]),
     "okl_batch_wait": (_i, [_vp, _i]),
     "okl_loss_fetch_async": (_i, [_vp, _i, _vp]),
     "okl_loss_fetch_wait": (_i, [_vp, _i, C.POINTER(C.c_float)]),
@@ -95,6 +95,7 @@ SIGNATURES = {
     "okl_ce_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp]),
     "okl_dense_softmax_ce": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "okl_mse_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _f, _vp, _i]),
+    "okl_mse_fwd_bwd_nxc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _f, _vp, _i]),
     "okl_read_scalar": (_i, [_vp, _vp, _P(_f)]),
     "okl_accum_update": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _vp]),
     "okl_accum_update_multi": (_i, [_vp, _i, _P(_vp), _P(_vp), _P(_vp), _P(_sz), _f, _vp]),

@@ -481,6 +481,45 @@ __global__ void __launch_bounds__(256) mse_kernel4(const float4* __restrict__ o,
   s = block_sum(s, sh);
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
+// Outputs channels-last (n, s, c) - as the tensor-core convolutions produce them - against targets in the caller's (n, c, s)
+// layout: the target tile is transposed through shared memory, so neither the outputs nor the gradient are ever permuted.
+constexpr int MSE_NXC_TILES = 8;
+template <bool RELU>
+__global__ void mse_nxc_kernel(const float* __restrict__ o, const float* __restrict__ t, float* __restrict__ partial, float* __restrict__ grad,
+                               int Cc, long long S, float scale) {
+  __shared__ float tile[32][33];
+  __shared__ float sh[32];
+  const size_t img = (size_t)blockIdx.z * Cc * S;
+  const int c0 = blockIdx.x * 32;
+  float acc = 0.f;
+  for (int st = 0; st < MSE_NXC_TILES; st++) {             // several 32-position tiles per block: fewer partials, less ramp
+    const long long s0 = ((long long)blockIdx.y * MSE_NXC_TILES + st) * 32;
+    if (s0 >= S) break;
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const int c = c0 + j; const long long sp = s0 + threadIdx.x;
+      tile[j][threadIdx.x] = (c < Cc && sp < S) ? t[img + (size_t)c * S + sp] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const long long sp = s0 + j; const int c = c0 + threadIdx.x;
+      if (sp < S && c < Cc) {
+        const size_t i = img + (size_t)sp * Cc + c;
+        const float ov = o[i], d = ov - tile[threadIdx.x][j];
+        acc += d * d;
+        grad[i] = (RELU && !(ov > 0.f)) ? 0.f : d * scale;
+      }
+    }
+  }
+  acc = warp_sum(acc);                                   // a warp = one threadIdx.y row of the 32 x 8 block
+  if (threadIdx.x == 0) sh[threadIdx.y] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)blockDim.y; w++) tot += sh[w];
+    partial[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+  }
+}
 __global__ void final_sum_kernel(const float* __restrict__ partial, int count, float* __restrict__ out, float scale, float* __restrict__ acc) {
   __shared__ float sh[32];
   float s = 0.f;
@@ -857,6 +896,25 @@ extern "C" int okl_mse_fwd_bwd(okl_ctx* ctx, const void* o, const void* t, void*
   }
   OKL_LAUNCHED(ctx, "mse_fwd_bwd");
   final_sum_kernel<<<1, 256, 0, ctx->stream>>>((const float*)partial, grid, (float*)loss, 1.f / (float)n, (float*)loss_accum);
+  OKL_LAUNCHED(ctx, "final_sum");
+  return OKL_OK;
+}
+
+extern "C" int okl_mse_fwd_bwd_nxc(okl_ctx* ctx, const void* o_nxc, const void* t_ncx, void* loss, void* grad_nxc, int N, int Cc, long long S,
+                                   float denom, void* loss_accum, int relu_outputs) {
+  OKL_REQUIRE(ctx && o_nxc && t_ncx && loss && grad_nxc, "NULL argument");
+  OKL_REQUIRE(N >= 1 && Cc >= 1 && S >= 1 && denom > 0.f, "bad mse shape");
+  dim3 grid((unsigned)((Cc + 31) / 32), (unsigned)((S + 32 * MSE_NXC_TILES - 1) / (32 * MSE_NXC_TILES)), (unsigned)N);
+  OKL_REQUIRE(grid.y <= 65535 && N <= 65535, "okl_mse_fwd_bwd_nxc: extent too large");
+  const size_t nblk = (size_t)grid.x * grid.y * grid.z;
+  OKL_REQUIRE(nblk < (1u << 30), "okl_mse_fwd_bwd_nxc: too many tiles");
+  int s = okl_ensure_workspace(ctx, nblk * sizeof(float));
+  if (s != OKL_OK) return s;
+  float* partial = (float*)ctx->workspace;
+  if (relu_outputs) mse_nxc_kernel<true><<<grid, dim3(32, 8), 0, ctx->stream>>>((const float*)o_nxc, (const float*)t_ncx, partial, (float*)grad_nxc, Cc, S, 2.f / denom);
+  else mse_nxc_kernel<false><<<grid, dim3(32, 8), 0, ctx->stream>>>((const float*)o_nxc, (const float*)t_ncx, partial, (float*)grad_nxc, Cc, S, 2.f / denom);
+  OKL_LAUNCHED(ctx, "mse_fwd_bwd_nxc");
+  final_sum_kernel<<<1, 1024, 0, ctx->stream>>>((const float*)partial, (int)nblk, (float*)loss, 1.f / ((float)N * (float)Cc * (float)S), (float*)loss_accum);
   OKL_LAUNCHED(ctx, "final_sum");
   return OKL_OK;
 }

@@ -173,8 +173,18 @@ class MSELoss:
         n = outputs.size
         relu = self._fuse_relu
         fuse = relu is not None and getattr(relu, "outputs", None) is outputs
-        check(lib.okl_mse_fwd_bwd(ctx.h, outputs._dptr(NCX), targets._dptr(NCX), loss.ptr, grad._ptr_raw(), n, float(n * ctx.nranks),
-                                  self._loss_accum, 1 if fuse else 0))
+        if (outputs.ndim >= 3 and outputs._dev_valid and outputs._layout == _lib.NXC and outputs.shape[1] > 1 and
+                outputs.shape[0] <= 65535 and getattr(outputs, "_lazy_fn", None) is None):
+            # channels-last outputs of a tensor-core convolution: loss and gradient are computed in that layout against the
+            # caller's (N, C, ...) targets - neither tensor is permuted in memory
+            N_, C_ = outputs.shape[0], outputs.shape[1]
+            S_ = n // (N_ * C_)
+            grad._layout = _lib.NXC
+            check(lib.okl_mse_fwd_bwd_nxc(ctx.h, outputs._dptr(), targets._dptr(NCX), loss.ptr, grad._ptr_raw(), N_, C_, S_,
+                                          float(n * ctx.nranks), self._loss_accum, 1 if fuse else 0))
+        else:
+            check(lib.okl_mse_fwd_bwd(ctx.h, outputs._dptr(NCX), targets._dptr(NCX), loss.ptr, grad._ptr_raw(), n, float(n * ctx.nranks),
+                                      self._loss_accum, 1 if fuse else 0))
         if fuse:
             relu._precomputed = grad             # already g * (y > 0): the layer's backward passes it through
         self._grad = grad

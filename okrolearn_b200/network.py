@@ -441,7 +441,7 @@ class NeuralNetwork:
 
         # ---- per-(batch shape, loss) step state: static input buffers + the captured graph
         skey = (batch_size, sample_shape, t_shape, id(loss_function), tuple(id(l) for l in self.layers), fast,
-                self.fuse_activations, self.skip_input_grad)
+                self.fuse_activations, self.skip_input_grad, ctx.precision, bool(self.prefetch_batches))
         st = self._graphs.get(skey)
         if st is None:
             st = _StepState(ctx, batch_size, sample_shape, t_row)
@@ -462,13 +462,22 @@ class NeuralNetwork:
                 return t
             return Tensor._view(slot.tin, 0, (rows,) + t_shape, np.float32, bound=False)
 
+        # a first layer that runs channels-last on the tensor cores gets its batch in that layout straight from the prefetch
+        first = self.layers[0] if self.layers else None
+        x_nxc = bool(self.prefetch_batches and ctx.precision != _lib.FP32 and isinstance(first, _ConvBase) and first._tc_eligible() and
+                     getattr(first, "_fused_pool", None) is None and len(sample_shape) >= 2 and sample_shape[0] > 1 and _numel(sample_shape[1:]) > 1)
+        if x_nxc:
+            for sl_ in st.slots:
+                if getattr(sl_, "xnxc", None) is None:
+                    sl_.xnxc = _DevBuf(ctx, max(batch_size * row_elems, 1) * 4)
+
         def prefetch(batch):
             """gather batch `batch` of the current permutation into slot batch % 2 on the copy stream"""
             b0 = batch * batch_size
             rows = min(b0 + batch_size, num_samples) - b0
             sl = st.slots[batch & 1]
             check(lib.okl_batch_prefetch(ctx.h, batch & 1, sl.xbuf.ptr, x_src, row_elems, sl.tin.ptr, t_src, t_row,
-                                         idx_dev.ptr + b0 * 4, rows))
+                                         idx_dev.ptr + b0 * 4, rows, sl.xnxc.ptr if x_nxc else None, sample_shape[0] if x_nxc else 0))
 
         lossf = C.c_float()
 
@@ -524,7 +533,11 @@ class NeuralNetwork:
                 else:
                     # a fresh view per step: a layer may re-lay-out ITS input tensor (channels-last for the tensor-core convs),
                     # which must never redirect or relabel the slot's own buffer - the gather keeps writing NC.. rows there
-                    bx = Tensor._view(sl.xbuf, 0, (rows,) + sample_shape, np.float32, bound=False)
+                    if x_nxc and pipelined:
+                        bx = Tensor._view(sl.xnxc, 0, (rows,) + sample_shape, np.float32, bound=False)
+                        bx._layout = _lib.NXC
+                    else:
+                        bx = Tensor._view(sl.xbuf, 0, (rows,) + sample_shape, np.float32, bound=False)
                     bt = make_targets(rows, sl)
                     if graph_ok and full and st.warm:
                         keep = []
