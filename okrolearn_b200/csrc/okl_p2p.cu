@@ -55,26 +55,39 @@ __device__ __forceinline__ void spin_until(const unsigned* flag, unsigned target
   }
 }
 
-__global__ void __launch_bounds__(512) p2p_allreduce_kernel(const P2PPeers peers, const int rank, const int nranks, const size_t off4,
-                                                           const size_t n4) {
+// THREADS = 512: the exchange has the GPU to itself.  THREADS = 128 with <= 32 registers per thread: the overlapped variant
+// (okl_allreduce_fork) - one such CTA fits into the register-file space a resident wave of the weight-gradient kernels leaves
+// free on every SM, so the exchange really runs next to them instead of queueing behind them.
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) p2p_allreduce_kernel(const P2PPeers peers, const int rank, const int nranks, const size_t off4,
+                                                                     const size_t n4) {
   P2PHeader* me = peers.hdr[rank];
   const unsigned s = me->seq + 1;           // every CTA reads it before the last CTA bumps it at the very end
   // ---- ready barrier: my gradients are complete (stream order); tell everyone, then wait for everyone
   if (blockIdx.x == 0 && threadIdx.x < nranks) st_release_sys(&peers.hdr[threadIdx.x]->ready[rank], s);
   if (threadIdx.x < nranks) spin_until(&me->ready[threadIdx.x], s);
   __syncthreads();
-  // ---- reduce-scatter + all-gather on my slice, 128-bit accesses, fixed summation order
+  // ---- reduce-scatter + all-gather on my slice, 128-bit accesses, fixed summation order (rank 0, 1, 2, ...), at most four
+  // peer loads in flight per thread (16 registers)
   const size_t chunk = (n4 + nranks - 1) / nranks;
   const size_t beg = (size_t)rank * chunk, end = min(n4, beg + chunk);
   for (size_t i = beg + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < end; i += (size_t)gridDim.x * blockDim.x) {
-    float4 v[P2P_MAX_RANKS];
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int p = 0; p < P2P_MAX_RANKS; p++)
-      if (p < nranks) v[p] = reinterpret_cast<const float4*>(peers.data[p])[off4 + i];
-    float4 a = v[0];
+    for (int p0 = 0; p0 < P2P_MAX_RANKS; p0 += 4) {
+      if (p0 < nranks) {
+        float4 v[4];
 #pragma unroll
-    for (int p = 1; p < P2P_MAX_RANKS; p++)
-      if (p < nranks) { a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w; }
+        for (int q = 0; q < 4; q++)
+          if (p0 + q < nranks) v[q] = reinterpret_cast<const float4*>(peers.data[p0 + q])[off4 + i];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (p0 + q < nranks) {
+            if (p0 + q == 0) a = v[q];
+            else { a.x += v[q].x; a.y += v[q].y; a.z += v[q].z; a.w += v[q].w; }
+          }
+      }
+    }
 #pragma unroll
     for (int p = 0; p < P2P_MAX_RANKS; p++)
       if (p < nranks) reinterpret_cast<float4*>(peers.data[p])[off4 + i] = a;
@@ -254,10 +267,21 @@ int okl_p2p_allreduce(okl_ctx* ctx, void* p, size_t count) {
   }
   const size_t off4 = ((char*)p - ((char*)st.base + P2P_HDR_BYTES)) / 16, n4 = count / 4;
   const size_t chunk = (n4 + ctx->nranks - 1) / ctx->nranks;
+  static int small_ok = -1;
+  if (small_ok < 0) { const char* e = getenv("OKL_P2P_SMALL"); small_ok = e ? atoi(e) : 1; }
+  // overlapped with the remaining backward and at most ~4 float4 per thread: the small-footprint variant
+  if (small_ok && ctx->comm_p2p_kind == 1 && ctx->stream == ctx->comm_stream && chunk <= (size_t)4 * 128 * ctx->sm_count) {
+    int grid = (int)((chunk + 127) / 128);
+    if (grid > ctx->sm_count) grid = ctx->sm_count;
+    if (grid < 1) grid = 1;
+    p2p_allreduce_kernel<128, 16><<<grid, 128, 0, ctx->stream>>>(peers, ctx->rank, ctx->nranks, off4, n4);
+    OKL_LAUNCHED(ctx, "p2p_allreduce");
+    return OKL_OK;
+  }
   int grid = (int)((chunk + 511) / 512);                 // one float4 per thread: the exchange is latency-, not bandwidth-bound
   if (grid > 2 * ctx->sm_count) grid = 2 * ctx->sm_count;
   if (grid < 1) grid = 1;
-  p2p_allreduce_kernel<<<grid, 512, 0, ctx->stream>>>(peers, ctx->rank, ctx->nranks, off4, n4);
+  p2p_allreduce_kernel<512, 1><<<grid, 512, 0, ctx->stream>>>(peers, ctx->rank, ctx->nranks, off4, n4);
   OKL_LAUNCHED(ctx, "p2p_allreduce");
   return OKL_OK;
 }
