@@ -569,7 +569,7 @@ conv_relu_pool2_wgrad(const float* __restrict__ x, const float* __restrict__ gp,
       const int o = warp * 4 + i;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const int pp = lane * 4 + j;
+        const int pp = lane + 32 * j;                     // consecutive lanes -> consecutive words: conflict-free (lane * 4 + j was 4-way)
         const float gv = gs[o][pp];
         unsigned mk = ms[o][pp];
         while (mk) {                                   // one iteration per maximum of the window (almost always exactly one)
