@@ -358,6 +358,14 @@ class NeuralNetwork:
         self.profiler.disable()
         return result
 
+    def _epoch_pinned(self, num_samples):
+        """(scalar slot, int32 index buffer) in page-locked host memory, cached on the network and grown on demand."""
+        cur = getattr(self, "_pin_epoch", None)
+        if cur is None or cur[1].size < num_samples:
+            cap = max(1024, int(num_samples * 1.5))
+            self._pin_epoch = cur = (pinned_empty((1,), np.int32), pinned_empty((cap,), np.int32))
+        return cur
+
     def _one_step(self, batch_inputs, batch_targets, loss_function, lr, optimizer, fast):
         """forward + loss + backward (+ optimizer for layers exposing parameters/gradients): okl.py:2969-2988."""
         outputs = self._forward(batch_inputs, _fast=fast) if fast else self.forward(batch_inputs)
@@ -498,8 +506,12 @@ class NeuralNetwork:
                 optimizer.set_lr(current_lr)
             else:
                 self.logger.warning("Unable to update optimizer's learning rate. Scheduler may not have an effect.")
-            lr32 = np.array([current_lr], dtype=np.float32)
-            check(lib.okl_h2d(ctx.h, ctx.lr_dev, lr32.ctypes.data, 1, _lib.F32))
+            # per-epoch scalars and the permutation go through cached page-locked buffers with asynchronous copies: no host sync
+            # in the epoch prologue (the read of the epoch loss at the end of every epoch is the one synchronisation point,
+            # so the buffers are never rewritten while a copy is in flight)
+            pin = self._epoch_pinned(num_samples)
+            pin[0].view(np.float32)[0] = current_lr
+            check(lib.okl_h2d_async_raw(ctx.h, ctx.lr_dev, pin[0].ctypes.data, 4))
             check(lib.okl_memset(ctx.h, st.eloss.ptr, 0, 4))
             host_losses = []
 
@@ -507,8 +519,9 @@ class NeuralNetwork:
             indices = np.arange(num_samples)
             np.random.shuffle(indices)
             perm_total = perm_total[indices]
-            i32 = np.ascontiguousarray(perm_total.astype(np.int32))
-            check(lib.okl_h2d_i32(ctx.h, idx_dev.ptr, i32.ctypes.data, i32.size, _lib.I32))
+            np.copyto(pin[1][:num_samples], perm_total, casting="unsafe")
+            if num_samples:
+                check(lib.okl_h2d_async_raw(ctx.h, idx_dev.ptr, pin[1].ctypes.data, num_samples * 4))
 
             pipelined = bool(self.prefetch_batches)
             if num_batches and pipelined:
