@@ -178,6 +178,15 @@ int okl_binary(okl_ctx* ctx, int op, const void* a, const void* b, void* out, si
 /* x *= alpha   (final `inputs.data / temperature`, okl.py:2890) */
 int okl_scale(okl_ctx* ctx, void* x, size_t n, float alpha);
 
+/* ------------------------------------------------------------------ Unfold / Fold (okl.py:525-636; im2col / fold as standalone layers)
+ * unfold_fwd: out (N, C*k*k, OH*OW), row c*k*k + u*k + v, column i*OW + j (okl.py:584-605, including the reference's handling of
+ * padding > 0: the clipped window goes to the top-left of a zero patch); unfold_bwd: col2im scatter-add for padding == 0
+ * (okl.py:625-634); fold_permute: Fold.forward's reshape/transpose (N*C, k, k, OH, OW) -> (N*C, OH, k, OW, k) (543-547), inverse = 1
+ * for Fold.backward (559-563). */
+int okl_unfold_fwd(okl_ctx* ctx, const void* x, void* out, int N, int C, int H, int W, int k, int stride, int pad);
+int okl_unfold_bwd(okl_ctx* ctx, const void* g, void* dx, int N, int C, int H, int W, int k, int stride);
+int okl_fold_permute(okl_ctx* ctx, const void* in, void* out, long long NC, int k, int OH, int OW, int inverse);
+
 /* ------------------------------------------------------------------ pooling (okl.py:1715-1831 + repairs R4,R5) */
 int okl_pool_fwd(okl_ctx* ctx, int kind, const void* x, void* y, int N, int C, int H, int W, int pool, int stride, int layout);
 /* relu_mask != 0 additionally zeroes dx where x <= 0: the fused backward of a ReLU placed right before the pooling layer

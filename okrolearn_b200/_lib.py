@@ -62,6 +62,9 @@ SIGNATURES = {
     "okl_h2d_i32": (_i, [_vp, _vp, _vp, _sz, _i]),
     "okl_permute": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i]),
     "okl_gather_rows": (_i, [_vp, _vp, _vp, _vp, _ll, _ll]),
+    "okl_unfold_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i]),
+    "okl_unfold_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i]),
+    "okl_fold_permute": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _i]),
     "okl_gather_batch": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll]),
     "okl_batch_prefetch": (_i, [_vp, _i, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _i]),
     "okl_batch_wait": (_i, [_vp, _i]),

@@ -168,6 +168,66 @@ __global__ void loss_post_kernel(volatile float* __restrict__ host_slot, const f
   reinterpret_cast<volatile unsigned*>(host_slot)[1] = seq;
 }
 
+// ------------------------------------------------------------------------------------------------ Unfold / Fold (okl.py:525-636)
+// Unfold.forward: out[n, c*k*k + u*k + v, i*OW + j]; a window that sticks out of the image is CLIPPED and copied into the top-left
+// corner of a zero k x k patch (what okl.py:588-603 does for padding > 0 - not true zero padding).
+__global__ void unfold_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int C, int H, int W, int k, int st, int pad, int OH, int OW,
+                                  size_t total) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int L = OH * OW, kk = k * k;
+    const int col = (int)(idx % L);
+    size_t t = idx / L;
+    const int row = (int)(t % ((size_t)C * kk));
+    const int n = (int)(t / ((size_t)C * kk));
+    const int c = row / kk, u = (row - c * kk) / k, v = row - c * kk - u * k;
+    const int i = col / OW, j = col - i * OW;
+    const int hs = i * st - pad, ws = j * st - pad;
+    const int h0 = max(0, hs), h1 = min(H, hs + k), w0 = max(0, ws), w1 = min(W, ws + k);
+    const int ih = h0 + u, iw = w0 + v;
+    out[idx] = (ih < h1 && iw < w1) ? x[(((size_t)n * C + c) * H + ih) * W + iw] : 0.f;
+  }
+}
+// Unfold.backward for padding == 0 (col2im): dx[n,c,h,w] = sum over the windows (i, j) and taps (u, v) that cover (h, w)
+__global__ void unfold_bwd_kernel(const float* __restrict__ g, float* __restrict__ dx, int C, int H, int W, int k, int st, int OH, int OW,
+                                  size_t total) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(idx % W);
+    size_t t = idx / W;
+    const int h = (int)(t % H); t /= H;
+    const int c = (int)(t % C);
+    const int n = (int)(t / C);
+    const int L = OH * OW, kk = k * k;
+    const float* gn = g + ((size_t)n * C + c) * kk * L;
+    float s = 0.f;
+    for (int u = 0; u < k; u++) {
+      const int hh = h - u;
+      if (hh < 0 || hh % st) continue;
+      const int i = hh / st;
+      if (i >= OH) continue;
+      for (int v = 0; v < k; v++) {
+        const int ww = w - v;
+        if (ww < 0 || ww % st) continue;
+        const int j = ww / st;
+        if (j < OW) s += gn[(size_t)(u * k + v) * L + i * OW + j];
+      }
+    }
+    dx[idx] = s;
+  }
+}
+// Fold.forward (inverse == 0): (n, c, u, v, oh, ow) -> (n, c, oh, u, ow, v); Fold.backward (inverse == 1): the other way round
+__global__ void fold_permute_kernel(const float* __restrict__ in, float* __restrict__ out, int k, int OH, int OW, int inverse, size_t total) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    // idx enumerates the (n, c, oh, u, ow, v) order
+    size_t t = idx;
+    const int v = (int)(t % k); t /= k;
+    const int ow = (int)(t % OW); t /= OW;
+    const int u = (int)(t % k); t /= k;
+    const int oh = (int)(t % OH); t /= OH;                  // t = n * C + c
+    const size_t src = (((t * k + u) * k + v) * OH + oh) * (size_t)OW + ow;
+    if (inverse) out[src] = in[idx]; else out[idx] = in[src];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ pooling
 struct PoolGeom { int N, C, H, W, OH, OW, ps, st; long long xs[4], ys[4]; bool cl; };   // strides for (n,c,h,w)
 
@@ -754,6 +814,39 @@ extern "C" int okl_gather_batch(okl_ctx* ctx, void* x_dst, const void* x_src, lo
 int okl_loss_post(okl_ctx* ctx, float* host_slot, const void* dev_loss, unsigned seq) {
   loss_post_kernel<<<1, 1, 0, ctx->stream>>>(host_slot, (const float*)dev_loss, seq);
   OKL_LAUNCHED(ctx, "loss_post");
+  return OKL_OK;
+}
+
+extern "C" int okl_unfold_fwd(okl_ctx* ctx, const void* x, void* out, int N, int C, int H, int W, int k, int stride, int pad) {
+  OKL_REQUIRE(ctx && N >= 0 && C >= 1 && H >= 1 && W >= 1 && k >= 1 && stride >= 1 && pad >= 0, "bad unfold shape");
+  const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
+  OKL_REQUIRE(H + 2 * pad >= k && W + 2 * pad >= k, "unfold: kernel larger than the padded input");
+  const size_t total = (size_t)N * C * k * k * OH * OW;
+  if (total == 0) return OKL_OK;
+  OKL_REQUIRE(x && out, "NULL argument");
+  unfold_fwd_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)x, (float*)out, C, H, W, k, stride, pad, OH, OW, total);
+  OKL_LAUNCHED(ctx, "unfold_fwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_unfold_bwd(okl_ctx* ctx, const void* g, void* dx, int N, int C, int H, int W, int k, int stride) {
+  OKL_REQUIRE(ctx && N >= 0 && C >= 1 && H >= k && W >= k && k >= 1 && stride >= 1, "bad unfold shape");
+  const int OH = (H - k) / stride + 1, OW = (W - k) / stride + 1;
+  const size_t total = (size_t)N * C * H * W;
+  if (total == 0) return OKL_OK;
+  OKL_REQUIRE(g && dx, "NULL argument");
+  unfold_bwd_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)g, (float*)dx, C, H, W, k, stride, OH, OW, total);
+  OKL_LAUNCHED(ctx, "unfold_bwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_fold_permute(okl_ctx* ctx, const void* in, void* out, long long NC, int k, int OH, int OW, int inverse) {
+  OKL_REQUIRE(ctx && NC >= 0 && k >= 1 && OH >= 1 && OW >= 1, "bad fold shape");
+  const size_t total = (size_t)NC * k * k * OH * OW;
+  if (total == 0) return OKL_OK;
+  OKL_REQUIRE(in && out, "NULL argument");
+  fold_permute_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)in, (float*)out, k, OH, OW, inverse, total);
+  OKL_LAUNCHED(ctx, "fold_permute");
   return OKL_OK;
 }
 

@@ -830,6 +830,99 @@ class FlattenLayer:
         pass
 
 
+class Unfold:
+    """okl.py:568-636: im2col as a standalone layer.  forward: (N, C, H, W) -> (N, C*k*k, OH*OW) float64, row c*k*k + u*k + v,
+    column i*OW + j; with padding > 0 a border window is clipped and copied to the top-left of a zero patch (as shipped, not true
+    zero padding).  backward: col2im scatter-add; with padding > 0 the reference's clipped slice cannot take the k x k block and
+    NumPy raises ValueError - so does this."""
+
+    def __init__(self, kernel_size, stride=1, padding=0):
+        self.kernel_size, self.stride, self.padding = kernel_size, stride, padding
+        self.input_shape = None
+
+    def _extent(self, H, W):
+        k, s, p = int(self.kernel_size), int(self.stride), int(self.padding)
+        return k, s, p, (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+
+    def forward(self, inputs: Tensor):
+        inputs = _as_tensor(inputs)
+        if inputs.ndim != 4:
+            raise ValueError(f"not enough values to unpack (expected 4, got {inputs.ndim})")          # okl.py:577
+        self.input_shape = inputs.shape
+        N, Cc, H, W = inputs.shape
+        k, s, p, OH, OW = self._extent(H, W)
+        if OH < 0 or OW < 0:
+            raise ValueError("negative dimensions are not allowed")
+        ctx = get_ctx()
+        out = Tensor._empty((N, Cc * k * k, max(OH, 0) * max(OW, 0)), np.float64)
+        if out.size:
+            check(lib.okl_unfold_fwd(ctx.h, inputs._dptr(NCX), out._ptr_raw(), N, Cc, H, W, k, s, p))
+        return out
+
+    def backward(self, dL_dout: Tensor):
+        dL_dout = _as_tensor(dL_dout)
+        N, Cc, H, W = self.input_shape
+        k, s, p, OH, OW = self._extent(H, W)
+        if dL_dout.ndim != 3:
+            raise ValueError(f"not enough values to unpack (expected 3, got {dL_dout.ndim})")         # okl.py:615
+        if dL_dout.size != N * Cc * k * k * OH * OW:
+            raise ValueError(f"cannot reshape array of size {dL_dout.size} into shape {(N, Cc, k, k, OH, OW)}")
+        if p > 0 and OH * OW > 0:
+            # okl.py:633: the clipped border slice is smaller than the (N, C, k, k) block added to it
+            raise ValueError("operands could not be broadcast together: Unfold.backward with padding > 0 adds a k x k block to a "
+                             "clipped border slice (okl.py:633 raises the same way)")
+        ctx = get_ctx()
+        dx = Tensor._empty(self.input_shape, np.float64)
+        if dx.size:
+            check(lib.okl_unfold_bwd(ctx.h, dL_dout._dptr(NCX), dx._ptr_raw(), N, Cc, H, W, k, s))
+        return dx
+
+
+class Fold:
+    """okl.py:525-565: NOT col2im - a pure reshape / transposition (N, C*k*k, OH*OW) -> (N, C, k, k, OH, OW) -> transpose
+    (0, 1, 4, 2, 5, 3) -> (N, -1, H, W), which equals col2im only for stride == kernel, padding == 0; backward is its inverse."""
+
+    def __init__(self, output_size, kernel_size, stride=1, padding=0):
+        self.output_size, self.kernel_size, self.stride, self.padding = output_size, kernel_size, stride, padding
+        self.input_shape = None
+
+    def forward(self, inputs: Tensor):
+        inputs = _as_tensor(inputs)
+        if inputs.ndim != 3:
+            raise ValueError(f"not enough values to unpack (expected 3, got {inputs.ndim})")
+        self.input_shape = inputs.shape
+        N, nch, L = inputs.shape
+        H, W = self.output_size
+        k, s, p = int(self.kernel_size), int(self.stride), int(self.padding)
+        OH, OW = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        Cc = nch // (k * k)
+        if Cc * k * k * OH * OW != nch * L or OH < 0 or OW < 0:
+            raise ValueError(f"cannot reshape array of size {inputs.size} into shape {(N, Cc, k, k, OH, OW)}")
+        if H * W == 0 or (Cc * k * k * OH * OW) % (H * W) != 0:
+            raise ValueError(f"cannot reshape array of size {inputs.size} into shape ({N},-1,{H},{W})")
+        ctx = get_ctx()
+        out = Tensor._empty((N, Cc * k * k * OH * OW // (H * W), H, W), _float_dtype(inputs))
+        if out.size:
+            check(lib.okl_fold_permute(ctx.h, inputs._dptr(NCX), out._ptr_raw(), N * Cc, k, OH, OW, 0))
+        return out
+
+    def backward(self, dL_dout: Tensor):
+        dL_dout = _as_tensor(dL_dout)
+        if dL_dout.ndim != 4:
+            raise ValueError(f"not enough values to unpack (expected 4, got {dL_dout.ndim})")
+        N, _, H, W = dL_dout.shape
+        k, s, p = int(self.kernel_size), int(self.stride), int(self.padding)
+        OH, OW = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        blk = OH * k * OW * k
+        if blk <= 0 or (dL_dout.size // max(N, 1)) % blk != 0 or dL_dout.size != _numel(self.input_shape):
+            raise ValueError(f"cannot reshape array of size {dL_dout.size} into shape {self.input_shape}")
+        ctx = get_ctx()
+        out = Tensor._empty(self.input_shape, _float_dtype(dL_dout))
+        if out.size:
+            check(lib.okl_fold_permute(ctx.h, dL_dout._dptr(NCX), out._ptr_raw(), dL_dout.size // blk, k, OH, OW, 1))
+        return out
+
+
 class UnflattenLayer:
     """okl.py:654-666."""
 

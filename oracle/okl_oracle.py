@@ -205,6 +205,62 @@ def unfold_forward(x, kernel_size, stride=1):
     return win.transpose(0, 1, 4, 5, 2, 3).reshape(N, C * k * k, OH * OW)
 
 
+def unfold_forward_loops(x, kernel_size, stride=1, padding=0):
+    """okl.py:575-612 as written, including the padding > 0 behaviour: a border patch is the CLIPPED window copied into the
+    top-left corner of a zero k x k patch (not true zero padding, SURVEY 8(a) IM).  Output float64 (np.zeros default)."""
+    N, C, H, Wd = x.shape
+    k = kernel_size
+    OH = (H + 2 * padding - k) // stride + 1
+    OW = (Wd + 2 * padding - k) // stride + 1
+    out = np.zeros((N, C * k * k, OH * OW))
+    for i in range(OH):
+        for j in range(OW):
+            hs, ws = i * stride - padding, j * stride - padding
+            patch = x[:, :, max(0, hs):min(H, hs + k), max(0, ws):min(Wd, ws + k)]
+            if patch.shape[2] < k or patch.shape[3] < k:
+                pp = np.zeros((N, C, k, k))
+                pp[:, :, :patch.shape[2], :patch.shape[3]] = patch
+                patch = pp
+            out[:, :, i * OW + j] = patch.reshape(N, -1)
+    return out
+
+
+def unfold_backward(g, input_shape, kernel_size, stride=1, padding=0):
+    """okl.py:614-636: col2im scatter-add.  With padding > 0 the clipped border slice cannot take the (N, C, k, k) block and
+    NumPy raises ValueError - exactly what the reference does."""
+    N, C, H, Wd = input_shape
+    k = kernel_size
+    OH = (H + 2 * padding - k) // stride + 1
+    OW = (Wd + 2 * padding - k) // stride + 1
+    dx = np.zeros(input_shape)
+    g6 = np.asarray(g).reshape(N, C, k, k, OH, OW)
+    for i in range(OH):
+        for j in range(OW):
+            hs, ws = i * stride - padding, j * stride - padding
+            dx[:, :, max(0, hs):min(H, hs + k), max(0, ws):min(Wd, ws + k)] += g6[:, :, :, :, i, j]
+    return dx
+
+
+def fold_backward(g, input_shape, output_size, kernel_size, stride=1, padding=0):
+    """okl.py:552-565: the inverse reshape / transposition of Fold.forward."""
+    N = g.shape[0]
+    k = kernel_size
+    H, Wd = g.shape[2], g.shape[3]
+    OH = (H + 2 * padding - k) // stride + 1
+    OW = (Wd + 2 * padding - k) // stride + 1
+    return g.reshape(N, -1, OH, k, OW, k).transpose(0, 1, 3, 5, 2, 4).reshape(input_shape)
+
+
+def fold_forward_ref(cols, output_size, kernel_size, stride=1, padding=0):
+    """okl.py:533-550 as written (output extents from stride / padding as the reference computes them)."""
+    N, nch, L = cols.shape
+    k = kernel_size
+    H, Wd = output_size
+    OH = (H + 2 * padding - k) // stride + 1
+    OW = (Wd + 2 * padding - k) // stride + 1
+    return cols.reshape(N, nch // (k * k), k, k, OH, OW).transpose(0, 1, 4, 2, 5, 3).reshape(N, -1, H, Wd)
+
+
 def fold_forward(cols, output_size, kernel_size):
     """okl.py:533-550: pure reshape/transposition, equals col2im only when stride == kernel, p == 0."""
     N = cols.shape[0]

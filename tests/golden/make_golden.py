@@ -286,6 +286,34 @@ yc = ref.Conv2DLayer(3, 5, 3)
 yc.filters.data = Wc
 close((Wc.reshape(5, -1) @ u3).reshape(2, 5, 4, 4), yc.forward(T(xu)).data, 1e-12, what="W.reshape @ unfold == conv")
 save("unfold_fold", x=xu, unfold_k2s2=u, unfold_k3s1=u3, src="reference")
+# Unfold with padding (the reference's top-left-aligned border patches), Unfold.backward (p = 0), Fold forward / backward
+uf = ref.Unfold(3, 2, 1)
+u_p = uf.forward(T(xu)).data
+close(O.unfold_forward_loops(xu, 3, 2, 1), u_p, 0, what="unfold padding quirk")
+uf0 = ref.Unfold(3, 1, 0)
+u0 = uf0.forward(T(xu)).data
+gu = rng.standard_normal(u0.shape)
+dxu = uf0.backward(T(gu)).data
+close(O.unfold_backward(gu, xu.shape, 3, 1, 0), dxu, 1e-13, what="unfold backward")
+uf2 = ref.Unfold(2, 2, 0)
+u2 = uf2.forward(T(xu)).data
+gu2 = rng.standard_normal(u2.shape)
+dxu2 = uf2.backward(T(gu2)).data
+close(O.unfold_backward(gu2, xu.shape, 2, 2, 0), dxu2, 1e-13, what="unfold backward s2")
+try:
+    uf.backward(T(rng.standard_normal(u_p.shape)))
+    unfold_pad_bwd_raises = False
+except ValueError:
+    unfold_pad_bwd_raises = True
+assert unfold_pad_bwd_raises
+fo = ref.Fold((6, 6), 2, 2, 0)
+f_out = fo.forward(T(u2)).data
+close(O.fold_forward_ref(u2, (6, 6), 2, 2, 0), f_out, 0, what="fold forward")
+gf = rng.standard_normal(f_out.shape)
+f_bwd = fo.backward(T(gf)).data
+close(O.fold_backward(gf, u2.shape, (6, 6), 2, 2, 0), f_bwd, 0, what="fold backward")
+save("unfold_fold2", x=xu, unfold_k3s2p1=u_p, g_k3s1=gu, dx_k3s1=dxu, g_k2s2=gu2, dx_k2s2=dxu2, fold_in=u2, fold_out=f_out, fold_g=gf,
+     fold_bwd=f_bwd, src="reference")
 
 # ----------------------------------------------------------------------------- optimizers / schedulers
 w0 = rng.standard_normal((5, 4))

@@ -294,3 +294,43 @@ def test_layouts_channels_last_roundtrip(okl):
     dX = lay.backward(okl.Tensor(gr), 0.0)
     dW, db, dXo = O.conv_backward_fast(x, W, gr, 1, 1)
     assert rel_err(dX.data, dXo) < TOL32 and rel_err(lay.filters.grad, dW) < TOL32
+
+
+def test_unfold_fold_layers(okl):
+    """Unfold / Fold (okl.py:525-636) on the device against the reference's own vectors and the oracle on larger random shapes."""
+    g = golden("unfold_fold")
+    g2 = golden("unfold_fold2")
+    x = g["x"]
+    assert rel_err(okl.Unfold(2, 2).forward(okl.Tensor(x)).data, g["unfold_k2s2"]) < TOL32
+    assert rel_err(okl.Unfold(3, 1).forward(okl.Tensor(x)).data, g["unfold_k3s1"]) < TOL32
+    up = okl.Unfold(3, 2, 1)
+    yp = up.forward(okl.Tensor(x))
+    assert yp.data.dtype == np.float64 and rel_err(yp.data, g2["unfold_k3s2p1"]) < TOL32
+    with pytest.raises(ValueError):
+        up.backward(okl.Tensor(np.zeros(yp.shape)))                 # okl.py:633 raises for padding > 0
+    u3 = okl.Unfold(3, 1, 0)
+    u3.forward(okl.Tensor(x))
+    assert rel_err(u3.backward(okl.Tensor(g2["g_k3s1"])).data, g2["dx_k3s1"]) < TOL32
+    u2 = okl.Unfold(2, 2, 0)
+    u2.forward(okl.Tensor(x))
+    assert rel_err(u2.backward(okl.Tensor(g2["g_k2s2"])).data, g2["dx_k2s2"]) < TOL32
+    fo = okl.Fold((6, 6), 2, 2, 0)
+    assert rel_err(fo.forward(okl.Tensor(g2["fold_in"])).data, g2["fold_out"]) < TOL32
+    assert rel_err(fo.backward(okl.Tensor(g2["fold_g"])).data, g2["fold_bwd"]) < TOL32
+    with pytest.raises(ValueError):
+        okl.Fold((6, 6), 4, 2, 0).forward(okl.Tensor(g2["fold_in"]))
+    # larger random shapes vs the oracle; W.reshape(O, -1) @ unfold(x) == conv(x) ties the K ordering to the conv layers
+    rng = np.random.default_rng(12)
+    xb = rng.standard_normal((3, 5, 19, 23))
+    for k, s, p in ((3, 1, 0), (4, 2, 0), (3, 2, 2), (5, 3, 1)):
+        assert rel_err(okl.Unfold(k, s, p).forward(okl.Tensor(xb)).data, O.unfold_forward_loops(xb, k, s, p)) < TOL32
+    ub = okl.Unfold(4, 2, 0)
+    cols = ub.forward(okl.Tensor(xb))
+    gb = rng.standard_normal(cols.shape)
+    assert rel_err(ub.backward(okl.Tensor(gb)).data, O.unfold_backward(gb, xb.shape, 4, 2, 0)) < TOL32
+    Wc = rng.standard_normal((7, 5, 3, 3))
+    conv = okl.Conv2DLayer(5, 7, 3)
+    conv.filters.data = Wc.copy()
+    cols3 = okl.Unfold(3, 1, 0).forward(okl.Tensor(xb)).data
+    yc = conv.forward(okl.Tensor(xb)).data
+    assert rel_err((Wc.reshape(7, -1) @ cols3).reshape(yc.shape), yc) < 2e-5
