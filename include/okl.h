@@ -47,7 +47,10 @@ typedef enum {
 /* arithmetic mode of the GEMM-shaped kernels (north_star: 1e-5 rel in FP32, 2e-2 in TF32/BF16) */
 typedef enum { OKL_FP32 = 0, OKL_TF32 = 1, OKL_BF16 = 2 } okl_precision;
 /* OKL_ACT_SOFTMAX: row softmax (okl.py:364-373) as the epilogue of okl_dense_fwd, for output widths <= 16 only */
-typedef enum { OKL_ACT_NONE = 0, OKL_ACT_RELU = 1, OKL_ACT_SIGMOID = 2, OKL_ACT_TANH = 3, OKL_ACT_SOFTMAX = 4 } okl_act;
+typedef enum { OKL_ACT_NONE = 0, OKL_ACT_RELU = 1, OKL_ACT_SIGMOID = 2, OKL_ACT_TANH = 3, OKL_ACT_SOFTMAX = 4,
+               /* okl_act2_fwd / okl_act2_bwd only: */
+               OKL_ACT_ELU = 10, OKL_ACT_SELU = 11, OKL_ACT_LEAKY = 12, OKL_ACT_SWISH = 13, OKL_ACT_GELU = 14, OKL_ACT_SOFTSIGN = 15,
+               OKL_ACT_HARDTANH = 16 } okl_act;
 typedef enum { OKL_F32 = 0, OKL_F64 = 1, OKL_I64 = 2, OKL_I32 = 3, OKL_U8 = 4 } okl_dtype;
 typedef enum { OKL_NCX = 0, OKL_NXC = 1 } okl_layout;
 typedef enum { OKL_POOL_MAX = 0, OKL_POOL_AVG = 1 } okl_pool_kind;
@@ -172,6 +175,17 @@ int okl_conv_relu_pool_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x
 int okl_act_fwd(okl_ctx* ctx, int act, const void* x, void* y, size_t n);
 /* relu: ref = x (g * (x>0), okl.py:107) [y works too]; sigmoid: ref = y (okl.py:514); tanh: ref = x (okl.py:2092) */
 int okl_act_bwd(okl_ctx* ctx, int act, const void* ref, const void* g, void* dx, size_t n);
+/* the reference's other elementwise activations (okl.py:57-352, 2111-2153): y = f(x), dx = g * f'(x) evaluated from the INPUT x.
+ * alpha: ELU / SELU / LeakyReLU / PReLU slope; scale: SELU.  Swish, GELU (tanh form, derivative as written in okl.py:300) and the
+ * clips the reference applies are reproduced literally. */
+int okl_act2_fwd(okl_ctx* ctx, int act, const void* x, void* y, size_t n, float alpha, float scale);
+int okl_act2_bwd(okl_ctx* ctx, int act, const void* x, const void* g, void* dx, size_t n, float alpha, float scale);
+/* PReLU (okl.py:250-251): out_scalar[0] = sum(g * x * [x <= 0]), fixed summation order */
+int okl_prelu_alpha_grad(okl_ctx* ctx, const void* x, const void* g, size_t n, void* out_scalar);
+/* row-wise classifiers next to softmax: kind 0 = Softmin forward (okl.py:410-416: exp(-(x + max)) normalised, nan_to_num),
+ * 1 = LogSoftmax forward (455-468), 2 = LogSoftmax backward a = log-softmax output, b = g: g_j - sum_k exp(a_k) g_k (470-488).
+ * Softmin's backward has the softmax form and uses okl_softmax_bwd. */
+int okl_rowwise(okl_ctx* ctx, int kind, const void* a, const void* b, void* out, int rows, int cols);
 /* out[i] = a[i] (op) b[i % nb]; op 0 = add (Tensor.__add__, tensor.py:12-22), 1 = mul (Tensor.__mul__, tensor.py:24-39).
  * nb = n for same-shape operands, the row length for a (1,N) row broadcast, 1 for a scalar held on the device. */
 int okl_binary(okl_ctx* ctx, int op, const void* a, const void* b, void* out, size_t n, size_t nb);

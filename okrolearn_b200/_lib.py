@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libokl_b200.so")
 OKL_OK, OKL_ERR_INVALID, OKL_ERR_CUDA, OKL_ERR_NCCL, OKL_ERR_OOM, OKL_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 FP32, TF32, BF16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_SOFTMAX = 0, 1, 2, 3, 4
+ACT_ELU, ACT_SELU, ACT_LEAKY, ACT_SWISH, ACT_GELU, ACT_SOFTSIGN, ACT_HARDTANH = 10, 11, 12, 13, 14, 15, 16
 F32, F64, I64, I32, U8 = 0, 1, 2, 3, 4
 NCX, NXC = 0, 1
 POOL_MAX, POOL_AVG = 0, 1
@@ -89,6 +90,10 @@ SIGNATURES = {
     "okl_conv_relu_pool_wgrad": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "okl_act_fwd": (_i, [_vp, _i, _vp, _vp, _sz]),
     "okl_act_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _sz]),
+    "okl_act2_fwd": (_i, [_vp, _i, _vp, _vp, _sz, _f, _f]),
+    "okl_act2_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _f, _f]),
+    "okl_prelu_alpha_grad": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "okl_rowwise": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i]),
     "okl_binary": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _sz]),
     "okl_scale": (_i, [_vp, _vp, _sz, _f]),
     "okl_pool_fwd": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i]),

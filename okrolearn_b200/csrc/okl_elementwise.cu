@@ -713,6 +713,139 @@ __global__ void adam_kernel(float* __restrict__ w, float* __restrict__ m, float*
 }  // namespace
 
 // ================================================================================================ entry points
+// ------------------------------------------------------------------------------------------------ parametric activations
+// (okl.py:57-352, 2111-2153).  Formulas follow the reference line by line, including the clips it applies and the
+// GELU derivative exactly as written there (0.5 tanh + ..., okl.py:300-301).
+namespace {
+__device__ __forceinline__ float act2_f(int kind, float x, float alpha, float scale) {
+  switch (kind) {
+    case OKL_ACT_ELU: return x > 0.f ? x : alpha * (expf(x) - 1.f);                                   // okl.py:70
+    case OKL_ACT_SELU: return scale * (x > 0.f ? x : alpha * (expf(x) - 1.f));                        // okl.py:179
+    case OKL_ACT_LEAKY: return x > 0.f ? x : alpha * x;                                               // okl.py:212 / 245
+    case OKL_ACT_SWISH: return x / (1.f + expf(-fminf(fmaxf(x, -88.f), 88.f)));                       // okl.py:131-137
+    case OKL_ACT_GELU: {                                                                              // okl.py:277-285
+      const float a = fminf(fmaxf(0.7978845608028654f * (x + 0.044715f * x * x * x), -15.f), 15.f);
+      return 0.5f * x * (1.f + tanhf(a));
+    }
+    case OKL_ACT_SOFTSIGN: return x / (1.f + fabsf(x));                                               // okl.py:322
+    case OKL_ACT_HARDTANH: return fminf(fmaxf(x, -1.f), 1.f);                                         // okl.py:2135
+    default: return x;
+  }
+}
+__device__ __forceinline__ float act2_d(int kind, float x, float alpha, float scale) {
+  switch (kind) {
+    case OKL_ACT_ELU: return x > 0.f ? 1.f : alpha * expf(x);                                         // okl.py:74-78
+    case OKL_ACT_SELU: return x > 0.f ? scale : scale * alpha * expf(x);                              // okl.py:183-184
+    case OKL_ACT_LEAKY: return x > 0.f ? 1.f : alpha;                                                 // okl.py:216 / 249
+    case OKL_ACT_SWISH: {                                                                             // okl.py:141-149
+      const float sg = 1.f / (1.f + expf(-fminf(fmaxf(x, -88.f), 88.f))), sw = x * sg;
+      return fminf(fmaxf(sw + sg * (1.f - sw), -1e9f), 1e9f);
+    }
+    case OKL_ACT_GELU: {                                                                              // okl.py:291-301 as written
+      const float a = fminf(fmaxf(0.7978845608028654f * (x + 0.044715f * x * x * x), -15.f), 15.f);
+      const float th = tanhf(a);
+      return 0.5f * th + 0.5f * x * (1.f - th * th) * 0.7978845608028654f * (1.f + 3.f * 0.044715f * x * x);
+    }
+    case OKL_ACT_SOFTSIGN: { const float d = 1.f + fabsf(x); return 1.f / (d * d); }                 // okl.py:330
+    case OKL_ACT_HARDTANH: return (x >= -1.f && x <= 1.f) ? 1.f : 0.f;                                // okl.py:2139
+    default: return 1.f;
+  }
+}
+__global__ void act2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, int kind, float alpha, float scale) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = act2_f(kind, x[i], alpha, scale);
+}
+__global__ void act2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ dx, size_t n, int kind, float alpha,
+                                float scale) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dx[i] = g[i] * act2_d(kind, x[i], alpha, scale);
+}
+// PReLU: per-block partial of sum g * x * [x <= 0] (okl.py:250-251); combined in fixed order by final_sum_kernel
+__global__ void prelu_alpha_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ partial, size_t n) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float xv = x[i];
+    if (!(xv > 0.f)) s += g[i] * xv;
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+// one warp per row: softmin forward (as written: exp(-(x + max)), okl.py:410-416), log-softmax forward / backward (okl.py:455-488)
+__global__ void rowwise_kernel(int kind, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int rows, int cols) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* ar = a + (size_t)row * cols;
+  float* orow = out + (size_t)row * cols;
+  if (kind == 2) {                                         // log-softmax backward: g_j - sum_k exp(ls_k) g_k
+    const float* gr = b + (size_t)row * cols;
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s += expf(ar[c]) * gr[c];
+    s = warp_sum(s);
+    for (int c = lane; c < cols; c += 32) orow[c] = gr[c] - s;
+    return;
+  }
+  float mx = -INFINITY;
+  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, ar[c]);
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sft));
+  float s = 0.f;
+  if (kind == 0) {                                         // softmin
+    for (int c = lane; c < cols; c += 32) s += expf(-(ar[c] + mx));
+    s = warp_sum(s);
+    for (int c = lane; c < cols; c += 32) {
+      float v = expf(-(ar[c] + mx)) / s;
+      if (isnan(v)) v = 0.f; else if (isinf(v)) v = v > 0.f ? 1.f : 0.f;      // nan_to_num(nan=0, posinf=1, neginf=0)
+      orow[c] = v;
+    }
+  } else {                                                 // log-softmax
+    for (int c = lane; c < cols; c += 32) s += expf(fminf(fmaxf(ar[c] - mx, -500.f), 500.f));
+    s = warp_sum(s);
+    const float ls = logf(s);
+    for (int c = lane; c < cols; c += 32) orow[c] = (ar[c] - mx) - ls;
+  }
+}
+}  // namespace
+
+extern "C" int okl_act2_fwd(okl_ctx* ctx, int act, const void* x, void* y, size_t n, float alpha, float scale) {
+  OKL_REQUIRE(ctx && (n == 0 || (x && y)), "NULL argument");
+  OKL_REQUIRE(act >= OKL_ACT_ELU && act <= OKL_ACT_HARDTANH, "bad activation %d", act);
+  if (n == 0) return OKL_OK;
+  act2_fwd_kernel<<<okl_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>((const float*)x, (float*)y, n, act, alpha, scale);
+  OKL_LAUNCHED(ctx, "act2_fwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_act2_bwd(okl_ctx* ctx, int act, const void* x, const void* g, void* dx, size_t n, float alpha, float scale) {
+  OKL_REQUIRE(ctx && (n == 0 || (x && g && dx)), "NULL argument");
+  OKL_REQUIRE(act >= OKL_ACT_ELU && act <= OKL_ACT_HARDTANH, "bad activation %d", act);
+  if (n == 0) return OKL_OK;
+  act2_bwd_kernel<<<okl_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>((const float*)x, (const float*)g, (float*)dx, n, act, alpha, scale);
+  OKL_LAUNCHED(ctx, "act2_bwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_prelu_alpha_grad(okl_ctx* ctx, const void* x, const void* g, size_t n, void* out_scalar) {
+  OKL_REQUIRE(ctx && out_scalar && (n == 0 || (x && g)), "NULL argument");
+  int grid = n ? okl_grid_1d(ctx, n, 256, 4) : 1;
+  if (grid > 1024) grid = 1024;
+  int s = okl_ensure_workspace(ctx, (size_t)grid * sizeof(float));
+  if (s != OKL_OK) return s;
+  prelu_alpha_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)x, (const float*)g, (float*)ctx->workspace, n);
+  OKL_LAUNCHED(ctx, "prelu_alpha");
+  final_sum_kernel<<<1, 256, 0, ctx->stream>>>((const float*)ctx->workspace, grid, (float*)out_scalar, 1.f, nullptr);
+  OKL_LAUNCHED(ctx, "final_sum");
+  return OKL_OK;
+}
+
+extern "C" int okl_rowwise(okl_ctx* ctx, int kind, const void* a, const void* b, void* out, int rows, int cols) {
+  OKL_REQUIRE(ctx && kind >= 0 && kind <= 2 && rows >= 0 && cols >= 1, "bad rowwise arguments");
+  if (rows == 0) return OKL_OK;
+  OKL_REQUIRE(a && out && (kind != 2 || b), "NULL argument");
+  rowwise_kernel<<<(rows * 32 + 255) / 256, 256, 0, ctx->stream>>>(kind, (const float*)a, (const float*)b, (float*)out, rows, cols);
+  OKL_LAUNCHED(ctx, "rowwise");
+  return OKL_OK;
+}
+
 extern "C" int okl_act_fwd(okl_ctx* ctx, int act, const void* x, void* y, size_t n) {
   OKL_REQUIRE(ctx && (n == 0 || (x && y)), "NULL argument");
   OKL_REQUIRE(act >= OKL_ACT_NONE && act <= OKL_ACT_TANH, "bad activation %d", act);

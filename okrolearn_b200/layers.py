@@ -701,6 +701,234 @@ class TanhActivationLayer(_Activation):
         return dx
 
 
+# ---- the reference's other elementwise activations: one device kernel pair, per-layer formulas in the kernel
+class _Act2:
+    """y = f(x); backward g * f'(x) evaluated from the stored INPUT.  Sub-classes fix the kernel id and which side effects the
+    reference has on ``inputs.grad``."""
+    _act = 0
+    _sets_input_grad = "accumulate"       # "accumulate" (okl.py:81, 151, 187, 219), "assign" (GELU, okl.py:304), None (Softsign)
+
+    def _params(self):
+        return 0.0, 1.0
+
+    def forward(self, inputs: Tensor):
+        inputs = _as_tensor(inputs)
+        self.inputs = inputs
+        ctx = get_ctx()
+        out = Tensor._empty(inputs.shape, _float_dtype(inputs), layout=inputs._layout if inputs._dev_valid else NCX)
+        src = inputs._dptr()
+        out._layout = inputs._layout
+        a, sc = self._params()
+        check(lib.okl_act2_fwd(ctx.h, self._act, src, out._ptr_raw(), inputs.size, float(a), float(sc)))
+        self.outputs = out
+        return out
+
+    def _dx(self, dL_dout):
+        dL_dout = _as_tensor(dL_dout)
+        ref = self.inputs
+        if dL_dout.shape != ref.shape:
+            raise ValueError(f"operands could not be broadcast together with shapes {dL_dout.shape} {ref.shape}")
+        ctx = get_ctx()
+        rp = ref._dptr()
+        dx = Tensor._empty(ref.shape, np.result_type(_float_dtype(dL_dout), _float_dtype(ref)), layout=ref._layout)
+        a, sc = self._params()
+        check(lib.okl_act2_bwd(ctx.h, self._act, rp, dL_dout._dptr(ref._layout), dx._ptr_raw(), ref.size, float(a), float(sc)))
+        return dx, dL_dout
+
+    def backward(self, dL_dout: Tensor, lr: float = None):
+        dx, _ = self._dx(dL_dout)
+        if self._sets_input_grad == "accumulate":
+            _set_input_grad(self.inputs, dx)
+        elif self._sets_input_grad == "assign" and self.inputs.requires_grad:
+            self.inputs._grad = dx
+        return dx
+
+    def get_params(self):
+        return None
+
+    def set_params(self, params):
+        pass
+
+
+class ELUActivationLayer(_Act2):
+    """okl.py:57-91: x if x > 0 else alpha (exp(x) - 1)."""
+    _act = _lib.ACT_ELU
+
+    def __init__(self, alpha=1.0):
+        self.alpha = alpha
+
+    def _params(self):
+        return self.alpha, 1.0
+
+
+class SELUActivationLayer(_Act2):
+    """okl.py:168-196: scale * ELU_alpha(x)."""
+    _act = _lib.ACT_SELU
+
+    def __init__(self, alpha=1.6732632423543772848170429916717, scale=1.0507009873554804934193349852946):
+        self.alpha, self.scale = alpha, scale
+
+    def _params(self):
+        return self.alpha, self.scale
+
+
+class LeakyReLUActivationLayer(_Act2):
+    """okl.py:199-227: x if x > 0 else alpha x.  (The shipped backward goes through np.vectorize, which truncates the derivative to
+    integers when x.flat[0] > 0 - the same dtype-inference quirk as ReLU's forward; this implements the float derivative.)"""
+    _act = _lib.ACT_LEAKY
+
+    def __init__(self, alpha: float = 0.01):
+        self.alpha = alpha
+
+    def _params(self):
+        return self.alpha, 1.0
+
+
+class PReLUActivationLayer(LeakyReLUActivationLayer):
+    """okl.py:230-268: LeakyReLU whose slope is learned: d_alpha = sum(g * x * [x <= 0]); alpha -= lr * d_alpha inside backward."""
+
+    def __init__(self, alpha: float = 0.01):
+        self.alpha = alpha
+        self.d_alpha = 0
+
+    def backward(self, dL_dout: Tensor, lr: float):
+        dx, g = self._dx(dL_dout)                      # uses the PRE-update alpha (okl.py:249 before 253)
+        ctx = get_ctx()
+        buf = _DevBuf(ctx, 4)
+        check(lib.okl_prelu_alpha_grad(ctx.h, self.inputs._dptr(), g._dptr(self.inputs._layout), self.inputs.size, buf.ptr))
+        v = C.c_float()
+        check(lib.okl_read_scalar(ctx.h, buf.ptr, C.byref(v)))
+        self.d_alpha = np.float64(v.value)
+        self.alpha -= lr * self.d_alpha
+        _set_input_grad(self.inputs, dx)
+        return dx
+
+    def get_params(self):
+        return {'alpha': self.alpha}
+
+    def set_params(self, params):
+        if params and 'alpha' in params:
+            self.alpha = params['alpha']
+
+
+class SwishActivationLayer(_Act2):
+    """okl.py:123-165: x * sigmoid(clip(x, -88, 88)); derivative swish + sigmoid (1 - swish), clipped to +-1e9."""
+    _act = _lib.ACT_SWISH
+
+    def forward(self, inputs: Tensor):
+        out = super().forward(inputs)
+        self.sigmoid_values = None                     # the reference keeps sigmoid(x) here; recomputed in the backward kernel
+        return out
+
+
+class GELUActivationLayer(_Act2):
+    """okl.py:271-312: tanh form with the argument clipped to +-15; the derivative is the reference's expression as written."""
+    _act = _lib.ACT_GELU
+    _sets_input_grad = "assign"
+
+    def __init__(self):
+        self.sqrt_2_over_pi = np.sqrt(2 / np.pi)
+        self.tanh_clip_value = 15
+
+
+class SoftsignActivationLayer(_Act2):
+    """okl.py:315-338: x / (1 + |x|)."""
+    _act = _lib.ACT_SOFTSIGN
+    _sets_input_grad = None
+
+
+class HardTanhActivationLayer(_Act2):
+    """okl.py:2111-2153: clip(x, -1, 1); gradient passes where -1 <= x <= 1."""
+    _act = _lib.ACT_HARDTANH
+
+    def __init__(self):
+        self.inputs = self.output = self.dl_dinputs = self.dl_doutputs = None
+
+    def forward(self, inputs: Tensor):
+        self.output = super().forward(inputs)
+        return self.output
+
+
+class LinearActivationLayer:
+    """okl.py:1989-2008: identity; backward passes the gradient through and accumulates it into inputs.grad."""
+
+    def forward(self, inputs: Tensor):
+        self.inputs = _as_tensor(inputs)
+        return inputs
+
+    def backward(self, dL_dout: Tensor, lr: float):
+        dx = _as_tensor(dL_dout)
+        _set_input_grad(self.inputs, dx)
+        return dx
+
+    def get_params(self):
+        return None
+
+    def set_params(self, params):
+        pass
+
+
+class SoftminActivationLayer:
+    """okl.py:402-442: exp(-(x + rowmax)) normalised (+ nan_to_num) exactly as written; the Jacobian has the softmax form."""
+
+    def forward(self, inputs: Tensor):
+        inputs = _as_tensor(inputs)
+        if inputs.ndim != 2:
+            raise ValueError(f"softmin expects a 2-D (batch, classes) input, got shape {inputs.shape}")
+        ctx = get_ctx()
+        out = Tensor._empty(inputs.shape, _float_dtype(inputs))
+        check(lib.okl_rowwise(ctx.h, 0, inputs._dptr(NCX), None, out._ptr_raw(), inputs.shape[0], inputs.shape[1]))
+        self.outputs = out
+        return out
+
+    def backward(self, dL_dout: Tensor, lr: float = None):
+        dL_dout = _as_tensor(dL_dout)
+        p = self.outputs
+        if dL_dout.shape != p.shape:
+            raise ValueError(f"operands could not be broadcast together with shapes {dL_dout.shape} {p.shape}")
+        ctx = get_ctx()
+        dx = Tensor._empty(p.shape, np.float64)
+        check(lib.okl_softmax_bwd(ctx.h, p._dptr(NCX), dL_dout._dptr(NCX), dx._ptr_raw(), p.shape[0], p.shape[1]))
+        return dx
+
+    def get_params(self):
+        return None
+
+    def set_params(self, params: dict):
+        pass
+
+
+class LogSoftmaxActivationLayer:
+    """okl.py:445-497: (x - max) - log(sum(exp(clip(x - max, -500, 500)))) in float64; backward = the reference's Jacobian product
+    g_j - sum_k exp(ls_k) g_k."""
+
+    def forward(self, inputs: Tensor):
+        inputs = _as_tensor(inputs)
+        if inputs.ndim != 2:
+            raise ValueError(f"log-softmax expects a 2-D (batch, classes) input, got shape {inputs.shape}")
+        ctx = get_ctx()
+        out = Tensor._empty(inputs.shape, np.float64)
+        check(lib.okl_rowwise(ctx.h, 1, inputs._dptr(NCX), None, out._ptr_raw(), inputs.shape[0], inputs.shape[1]))
+        self.outputs = out
+        return out
+
+    def backward(self, dL_dout: Tensor, lr: float = None):
+        dL_dout = _as_tensor(dL_dout)
+        ls = self.outputs
+        if dL_dout.shape != ls.shape:
+            raise ValueError(f"operands could not be broadcast together with shapes {dL_dout.shape} {ls.shape}")
+        ctx = get_ctx()
+        dx = Tensor._empty(ls.shape, np.float64)
+        check(lib.okl_rowwise(ctx.h, 2, ls._dptr(NCX), dL_dout._dptr(NCX), dx._ptr_raw(), ls.shape[0], ls.shape[1]))
+        return dx
+
+    def get_params(self):
+        return None
+
+    def set_params(self, params: dict):
+        pass
+
+
 class SoftmaxActivationLayer:
     """okl.py:355-399: stable softmax over axis 1 (+ nan_to_num); backward = Jacobian product, computed in closed form
     p * (g - sum_k g_k p_k) instead of the reference's B x C x C Python triple loop."""

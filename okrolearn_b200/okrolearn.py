@@ -6,7 +6,9 @@ from ._lib import get_ctx, set_precision, FP32, TF32, BF16  # noqa: F401
 from .tensor import Tensor, pinned_empty  # noqa: F401
 from .layers import (DenseLayer, Conv1DLayer, Conv2DLayer, Conv3DLayer, ReLUActivationLayer, SigmoidActivationLayer,  # noqa: F401
                      TanhActivationLayer, SoftmaxActivationLayer, MaxPoolingLayer, AveragePoolingLayer, FlattenLayer,
-                     UnflattenLayer, Unfold, Fold)
+                     UnflattenLayer, Unfold, Fold, ELUActivationLayer, SELUActivationLayer, LeakyReLUActivationLayer,
+                     PReLUActivationLayer, SwishActivationLayer, GELUActivationLayer, SoftsignActivationLayer,
+                     HardTanhActivationLayer, LinearActivationLayer, SoftminActivationLayer, LogSoftmaxActivationLayer)
 from .losses import CrossEntropyLoss, MSELoss, LossValue  # noqa: F401
 from .schedulers import (LearningRateScheduler, StepLRScheduler, TimeBasedDecayScheduler, ExponentialDecayScheduler,  # noqa: F401
                          LinearDecayScheduler)

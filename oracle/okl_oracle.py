@@ -291,6 +291,88 @@ def relu_backward(x, g):
     return g * (x > 0)
 
 
+# ---- the other elementwise activations, each as the reference computes it
+_S2PI = np.sqrt(2 / np.pi)
+
+
+def elu(x, alpha=1.0):                      # okl.py:70
+    return np.where(x > 0, x, alpha * (np.exp(x) - 1))
+
+
+def elu_d(x, alpha=1.0):                    # okl.py:74-78
+    return np.where(x > 0, 1.0, alpha * np.exp(x))
+
+
+def selu(x, alpha=1.6732632423543772848170429916717, scale=1.0507009873554804934193349852946):        # okl.py:179
+    return scale * np.where(x > 0, x, alpha * (np.exp(x) - 1))
+
+
+def selu_d(x, alpha=1.6732632423543772848170429916717, scale=1.0507009873554804934193349852946):      # okl.py:183-184
+    return np.where(x > 0, scale, scale * alpha * np.exp(x))
+
+
+def leaky(x, alpha=0.01):                   # okl.py:212, 245
+    return np.where(x > 0, x, alpha * x)
+
+
+def leaky_d(x, alpha=0.01):                 # okl.py:216, 249 (intended float semantics; np.vectorize truncates when x.flat[0] > 0)
+    return np.where(x > 0, 1.0, alpha)
+
+
+def prelu_alpha_grad(x, g):                 # okl.py:250-251
+    return float(np.sum(g * np.where(x <= 0, x, 0.0)))
+
+
+def swish(x):                               # okl.py:131-137
+    return x * (1 / (1 + np.exp(-np.clip(x, -88, 88))))
+
+
+def swish_d(x):                             # okl.py:141-149
+    sg = 1 / (1 + np.exp(-np.clip(x, -88, 88)))
+    sw = x * sg
+    return np.clip(sw + sg * (1 - sw), -1e9, 1e9)
+
+
+def gelu(x):                                # okl.py:277-285
+    return 0.5 * x * (1 + np.tanh(np.clip(_S2PI * (x + 0.044715 * np.power(x, 3)), -15, 15)))
+
+
+def gelu_d(x):                              # okl.py:291-301 AS WRITTEN (0.5 * tanh, not 0.5 * (1 + tanh))
+    th = np.tanh(np.clip(_S2PI * (x + 0.044715 * np.power(x, 3)), -15, 15))
+    return 0.5 * th + 0.5 * x * (1 - th ** 2) * _S2PI * (1 + 3 * 0.044715 * np.power(x, 2))
+
+
+def softsign(x):                            # okl.py:322
+    return x / (1 + np.abs(x))
+
+
+def softsign_d(x):                          # okl.py:330
+    return 1 / ((1 + np.abs(x)) ** 2)
+
+
+def hardtanh(x):                            # okl.py:2135
+    return np.clip(x, -1, 1)
+
+
+def hardtanh_d(x):                          # okl.py:2139
+    return np.logical_and(x >= -1, x <= 1).astype(float)
+
+
+def softmin_forward(x):                     # okl.py:410-416 as written: exp(-(x + max))
+    inv = np.exp(-(x + np.max(x, axis=1, keepdims=True)))
+    return np.nan_to_num(inv / np.sum(inv, axis=1, keepdims=True), nan=0.0, posinf=1.0, neginf=0.0)
+
+
+def logsoftmax_forward(x):                  # okl.py:455-468
+    x = x.astype(np.float64)
+    mx = np.max(x, axis=1, keepdims=True)
+    return (x - mx) - np.log(np.sum(np.exp(np.clip(x - mx, -500, 500)), axis=1, keepdims=True))
+
+
+def logsoftmax_backward(ls, g):             # okl.py:470-488: J[j,k] = 1 - exp(ls_j) if j == k else -exp(ls_k);  out = J . g
+    return g - np.sum(np.exp(ls) * g, axis=1, keepdims=True)
+
+
 def sigmoid_forward(x):
     """okl.py:509: 1 / (1 + exp(-x))."""
     return 1 / (1 + np.exp(-x))

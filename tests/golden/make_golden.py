@@ -315,6 +315,44 @@ close(O.fold_backward(gf, u2.shape, (6, 6), 2, 2, 0), f_bwd, 0, what="fold backw
 save("unfold_fold2", x=xu, unfold_k3s2p1=u_p, g_k3s1=gu, dx_k3s1=dxu, g_k2s2=gu2, dx_k2s2=dxu2, fold_in=u2, fold_out=f_out, fold_g=gf,
      fold_bwd=f_bwd, src="reference")
 
+# ----------------------------------------------------------------------------- the other activations
+xa = rng.standard_normal((6, 7)) * 2.0
+xa.flat[0] = -0.3        # np.vectorize infers the dtype of `lambda x: 1 if x > 0 else alpha` from element 0: keep it float
+ga = rng.standard_normal((6, 7))
+acts = {}
+for nm, lay, f, d in (("elu", ref.ELUActivationLayer(0.7), lambda v: O.elu(v, 0.7), lambda v: O.elu_d(v, 0.7)),
+                      ("selu", ref.SELUActivationLayer(), O.selu, O.selu_d),
+                      ("leaky", ref.LeakyReLUActivationLayer(0.05), lambda v: O.leaky(v, 0.05), lambda v: O.leaky_d(v, 0.05)),
+                      ("swish", ref.SwishActivationLayer(), O.swish, O.swish_d),
+                      ("gelu", ref.GELUActivationLayer(), O.gelu, O.gelu_d),
+                      ("softsign", ref.SoftsignActivationLayer(), O.softsign, O.softsign_d),
+                      ("hardtanh", ref.HardTanhActivationLayer(), O.hardtanh, O.hardtanh_d)):
+    y = lay.forward(T(xa.copy())).data
+    dx = lay.backward(T(ga.copy()), 0.1)
+    dx = dx.data if hasattr(dx, "data") else dx
+    close(f(xa), y, 1e-13, what=nm + " forward")
+    close(ga * d(xa), dx, 1e-13, what=nm + " backward")
+    acts[nm + "_y"], acts[nm + "_dx"] = np.asarray(y, dtype=np.float64), np.asarray(dx, dtype=np.float64)
+pl = ref.PReLUActivationLayer(0.05)
+ypl = pl.forward(T(xa.copy())).data
+dpl = pl.backward(T(ga.copy()), 0.1).data
+close(O.leaky(xa, 0.05), ypl, 1e-13, what="prelu forward")
+close(ga * O.leaky_d(xa, 0.05), dpl, 1e-13, what="prelu backward")
+close(np.array(O.prelu_alpha_grad(xa, ga)), np.array(pl.d_alpha), 1e-12, what="prelu d_alpha")
+close(np.array(0.05 - 0.1 * O.prelu_alpha_grad(xa, ga)), np.array(pl.alpha), 1e-12, what="prelu alpha update")
+sm_l = ref.SoftminActivationLayer()
+ysm = sm_l.forward(T(xa.copy())).data
+dsm = sm_l.backward(T(ga.copy())).data
+close(O.softmin_forward(xa), ysm, 1e-13, what="softmin forward")
+close(O.softmax_backward(ysm, ga), dsm, 1e-12, what="softmin backward")
+ls_l = ref.LogSoftmaxActivationLayer()
+yls = ls_l.forward(T(xa.copy())).data
+dls = ls_l.backward(T(ga.copy())).data
+close(O.logsoftmax_forward(xa), yls, 1e-13, what="logsoftmax forward")
+close(O.logsoftmax_backward(yls, ga), dls, 1e-12, what="logsoftmax backward")
+save("activations2", x=xa, g=ga, prelu_y=ypl, prelu_dx=dpl, prelu_d_alpha=np.array(pl.d_alpha), prelu_alpha_after=np.array(pl.alpha),
+     softmin_y=ysm, softmin_dx=dsm, logsoftmax_y=yls, logsoftmax_dx=dls, src="reference", **acts)
+
 # ----------------------------------------------------------------------------- optimizers / schedulers
 w0 = rng.standard_normal((5, 4))
 gs = [rng.standard_normal((5, 4)) for _ in range(3)]

@@ -334,3 +334,53 @@ def test_unfold_fold_layers(okl):
     cols3 = okl.Unfold(3, 1, 0).forward(okl.Tensor(xb)).data
     yc = conv.forward(okl.Tensor(xb)).data
     assert rel_err((Wc.reshape(7, -1) @ cols3).reshape(yc.shape), yc) < 2e-5
+
+
+def test_other_activation_layers(okl):
+    """the remaining elementwise / row-wise activation layers on the device vs the reference's vectors."""
+    g = golden("activations2")
+    x, gg = g["x"], g["g"]
+    for nm, lay in (("elu", okl.ELUActivationLayer(0.7)), ("selu", okl.SELUActivationLayer()), ("leaky", okl.LeakyReLUActivationLayer(0.05)),
+                    ("swish", okl.SwishActivationLayer()), ("gelu", okl.GELUActivationLayer()), ("softsign", okl.SoftsignActivationLayer()),
+                    ("hardtanh", okl.HardTanhActivationLayer())):
+        xt = okl.Tensor(x.copy())
+        y = lay.forward(xt)
+        assert rel_err(y.data, g[nm + "_y"]) < 2e-6, nm
+        dx = lay.backward(okl.Tensor(gg.copy()), 0.1)
+        assert rel_err(dx.data, g[nm + "_dx"]) < 2e-6, nm
+        if nm not in ("softsign",):
+            assert rel_err(np.asarray(xt.grad), g[nm + "_dx"]) < 2e-6, nm      # inputs.grad side effect (okl.py:81, 151, 187, 219, 304)
+        else:
+            assert xt.grad is None
+    pl = okl.PReLUActivationLayer(0.05)
+    xt = okl.Tensor(x.copy())
+    assert rel_err(pl.forward(xt).data, g["prelu_y"]) < 2e-6
+    assert rel_err(pl.backward(okl.Tensor(gg.copy()), 0.1).data, g["prelu_dx"]) < 2e-6
+    assert abs(pl.d_alpha - float(g["prelu_d_alpha"])) < 1e-4 and abs(pl.alpha - float(g["prelu_alpha_after"])) < 1e-5
+    assert pl.get_params() == {"alpha": pl.alpha}
+    sm = okl.SoftminActivationLayer()
+    assert rel_err(sm.forward(okl.Tensor(x.copy())).data, g["softmin_y"]) < 2e-6
+    assert rel_err(sm.backward(okl.Tensor(gg.copy())).data, g["softmin_dx"]) < 2e-5
+    ls = okl.LogSoftmaxActivationLayer()
+    yl = ls.forward(okl.Tensor(x.copy()))
+    assert yl.data.dtype == np.float64 and rel_err(yl.data, g["logsoftmax_y"]) < 2e-6
+    assert rel_err(ls.backward(okl.Tensor(gg.copy())).data, g["logsoftmax_dx"]) < 2e-5
+    li = okl.LinearActivationLayer()
+    xt = okl.Tensor(x.copy())
+    assert li.forward(xt) is xt
+    assert rel_err(li.backward(okl.Tensor(gg.copy()), 0.1).data, gg) < 1e-7 and rel_err(np.asarray(xt.grad), gg) < 1e-7
+    # a Dense -> GELU -> Dense -> LogSoftmax stack trains through NeuralNetwork.forward / backward with these layers
+    rng = np.random.default_rng(5)
+    net = okl.NeuralNetwork()
+    d1, d2 = okl.DenseLayer(7, 9), okl.DenseLayer(9, 4)
+    W1, W2 = d1.weights.data.copy(), d2.weights.data.copy()
+    for l in (d1, okl.GELUActivationLayer(), d2, okl.LogSoftmaxActivationLayer()):
+        net.add(l)
+    out = net.forward(okl.Tensor(x))
+    h = O.gelu(x @ W1)
+    assert rel_err(out.data, O.logsoftmax_forward(h @ W2)) < 2e-5
+    net.backward(okl.Tensor(gg[:, :4].copy()), 0.01)
+    dz2 = O.logsoftmax_backward(O.logsoftmax_forward(h @ W2), gg[:, :4])
+    assert rel_err(d2.weights.data, W2 - 0.01 * (h.T @ dz2)) < 2e-5
+    dz1 = (dz2 @ W2.T) * O.gelu_d(x @ W1)
+    assert rel_err(d1.weights.data, W1 - 0.01 * (x.T @ dz1)) < 2e-5
