@@ -192,6 +192,15 @@ int okl_binary(okl_ctx* ctx, int op, const void* a, const void* b, void* out, si
 /* x *= alpha   (final `inputs.data / temperature`, okl.py:2890) */
 int okl_scale(okl_ctx* ctx, void* x, size_t n, float alpha);
 
+/* ------------------------------------------------------------------ BatchNormLayer (okl.py:1145-1222), (B, F) inputs
+ * fwd: batch mean / population variance over axis 0 (training) or the running statistics; running = momentum * batch +
+ * (1 - momentum) * running; y = gamma (x - mean) / sqrt(max(var, eps) + eps) + beta, nan_to_num.  *_mean_var are 2F floats
+ * [mean | var].  bwd reproduces okl.py:1193-1204 literally - the chain rule uses the RUNNING variance, x_norm the batch one. */
+int okl_bn_fwd(okl_ctx* ctx, const void* x, const void* gamma, const void* beta, void* running_mean_var, void* batch_mean_var, void* y,
+               int B, int F, float eps, float momentum, int training);
+int okl_bn_bwd(okl_ctx* ctx, const void* x, const void* g, const void* gamma, const void* running_mean_var, const void* batch_mean_var,
+               void* dx, void* dgamma, void* dbeta, int B, int F, float eps);
+
 /* ------------------------------------------------------------------ Unfold / Fold (okl.py:525-636; im2col / fold as standalone layers)
  * unfold_fwd: out (N, C*k*k, OH*OW), row c*k*k + u*k + v, column i*OW + j (okl.py:584-605, including the reference's handling of
  * padding > 0: the clipped window goes to the top-left of a zero patch); unfold_bwd: col2im scatter-add for padding == 0

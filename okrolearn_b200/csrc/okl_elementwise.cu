@@ -806,6 +806,120 @@ __global__ void rowwise_kernel(int kind, const float* __restrict__ a, const floa
 }
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------ BatchNorm (okl.py:1145-1222)
+// (B, F) inputs, statistics over the batch axis.  One block per 32 features, 32 row lanes: column sums are formed in a fixed order.
+namespace {
+// stats[0:F] = mean, stats[F:2F] = population variance (np.mean / np.var, okl.py:1171-1172)
+__global__ void bn_stats_kernel(const float* __restrict__ x, float* __restrict__ stats, int B, int F) {
+  __shared__ float sh[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (c < F) for (int r = threadIdx.y; r < B; r += 32) s += x[(size_t)r * F + c];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  float mean = 0.f;
+  for (int q = 0; q < 32; q++) mean += sh[q][threadIdx.x];
+  mean /= (float)B;
+  __syncthreads();
+  float v = 0.f;
+  if (c < F) for (int r = threadIdx.y; r < B; r += 32) { const float d = x[(size_t)r * F + c] - mean; v += d * d; }
+  sh[threadIdx.y][threadIdx.x] = v;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < F) {
+    float var = 0.f;
+    for (int q = 0; q < 32; q++) var += sh[q][threadIdx.x];
+    stats[c] = mean;
+    stats[F + c] = var / (float)B;
+  }
+}
+// running = momentum * batch + (1 - momentum) * running for mean and var (okl.py:1175-1176); n = 2F
+__global__ void bn_running_kernel(float* __restrict__ running, const float* __restrict__ stats, int n, float momentum) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) running[i] = momentum * stats[i] + (1.f - momentum) * running[i];
+}
+// y = gamma * (x - mean) / sqrt(max(var, eps) + eps) + beta, nan_to_num(nan = 0, +inf = 1, -inf = 0)  (okl.py:1182-1190)
+__global__ void bn_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mv, const float* __restrict__ gamma, const float* __restrict__ beta,
+                              float* __restrict__ y, int F, size_t n, float eps) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % F);
+    float v = gamma[c] * ((x[i] - mv[c]) / sqrtf(fmaxf(mv[F + c], eps) + eps)) + beta[c];
+    if (isnan(v)) v = 0.f; else if (isinf(v)) v = v > 0.f ? 1.f : 0.f;
+    y[i] = v;
+  }
+}
+// column sums the backward needs: red[0:F] = sum g, [F:2F] = sum g * xnorm, [2F:3F] = sum g * xc, [3F:4F] = sum xc
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mv, float* __restrict__ red,
+                                     int B, int F, float eps) {
+  __shared__ float sh[4][32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < F) {
+    const float mean = mv[c], rstd = 1.f / sqrtf(fmaxf(mv[F + c], eps) + eps);
+    for (int r = threadIdx.y; r < B; r += 32) {
+      const float gv = g[(size_t)r * F + c], xc = x[(size_t)r * F + c] - mean;
+      a0 += gv; a1 += gv * (xc * rstd); a2 += gv * xc; a3 += xc;
+    }
+  }
+  sh[0][threadIdx.y][threadIdx.x] = a0; sh[1][threadIdx.y][threadIdx.x] = a1;
+  sh[2][threadIdx.y][threadIdx.x] = a2; sh[3][threadIdx.y][threadIdx.x] = a3;
+  __syncthreads();
+  if (threadIdx.y < 4 && c < F) {
+    float t = 0.f;
+    for (int q = 0; q < 32; q++) t += sh[threadIdx.y][q][threadIdx.x];
+    red[threadIdx.y * F + c] = t;
+  }
+}
+// dx exactly as okl.py:1197-1204 writes it, with the RUNNING variance in the chain rule (reference behaviour)
+__global__ void bn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mv, const float* __restrict__ running,
+                              const float* __restrict__ gamma, const float* __restrict__ red, float* __restrict__ dx, int B, int F, size_t n, float eps) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % F);
+    const float rv = running[F + c] + eps, ga = gamma[c];
+    const float inv = 1.f / sqrtf(rv);
+    const float dvar = ga * red[2 * F + c] * -0.5f * powf(rv, -1.5f);
+    const float dmean = ga * red[c] * -inv + dvar * (-2.f * red[3 * F + c] / (float)B);
+    const float xc = x[i] - mv[c];
+    dx[i] = g[i] * ga * inv + dvar * 2.f * xc / (float)B + dmean / (float)B;
+  }
+}
+}  // namespace
+
+extern "C" int okl_bn_fwd(okl_ctx* ctx, const void* x, const void* gamma, const void* beta, void* running_mean_var, void* batch_mean_var,
+                          void* y, int B, int F, float eps, float momentum, int training) {
+  OKL_REQUIRE(ctx && x && gamma && beta && running_mean_var && batch_mean_var && y && B >= 1 && F >= 1, "bad batch-norm arguments");
+  const size_t n = (size_t)B * F;
+  if (training) {
+    bn_stats_kernel<<<(F + 31) / 32, dim3(32, 32), 0, ctx->stream>>>((const float*)x, (float*)batch_mean_var, B, F);
+    OKL_LAUNCHED(ctx, "bn_stats");
+    bn_running_kernel<<<(2 * F + 255) / 256, 256, 0, ctx->stream>>>((float*)running_mean_var, (const float*)batch_mean_var, 2 * F, momentum);
+    OKL_LAUNCHED(ctx, "bn_running");
+  } else {
+    int s = okl_d2d(ctx, batch_mean_var, running_mean_var, (size_t)2 * F * sizeof(float));
+    if (s != OKL_OK) return s;
+  }
+  bn_fwd_kernel<<<okl_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>((const float*)x, (const float*)batch_mean_var, (const float*)gamma,
+                                                                  (const float*)beta, (float*)y, F, n, eps);
+  OKL_LAUNCHED(ctx, "bn_fwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_bn_bwd(okl_ctx* ctx, const void* x, const void* g, const void* gamma, const void* running_mean_var, const void* batch_mean_var,
+                          void* dx, void* dgamma, void* dbeta, int B, int F, float eps) {
+  OKL_REQUIRE(ctx && x && g && gamma && running_mean_var && batch_mean_var && dx && dgamma && dbeta && B >= 1 && F >= 1, "bad batch-norm arguments");
+  int s = okl_ensure_workspace(ctx, (size_t)4 * F * sizeof(float));
+  if (s != OKL_OK) return s;
+  float* red = (float*)ctx->workspace;
+  bn_bwd_reduce_kernel<<<(F + 31) / 32, dim3(32, 32), 0, ctx->stream>>>((const float*)x, (const float*)g, (const float*)batch_mean_var, red, B, F, eps);
+  OKL_LAUNCHED(ctx, "bn_bwd_reduce");
+  const size_t n = (size_t)B * F;
+  bn_bwd_kernel<<<okl_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>((const float*)x, (const float*)g, (const float*)batch_mean_var,
+                                                                  (const float*)running_mean_var, (const float*)gamma, red, (float*)dx, B, F, n, eps);
+  OKL_LAUNCHED(ctx, "bn_bwd");
+  s = okl_d2d(ctx, dbeta, red, (size_t)F * sizeof(float));
+  if (s != OKL_OK) return s;
+  return okl_d2d(ctx, dgamma, red + F, (size_t)F * sizeof(float));
+}
+
 extern "C" int okl_act2_fwd(okl_ctx* ctx, int act, const void* x, void* y, size_t n, float alpha, float scale) {
   OKL_REQUIRE(ctx && (n == 0 || (x && y)), "NULL argument");
   OKL_REQUIRE(act >= OKL_ACT_ELU && act <= OKL_ACT_HARDTANH, "bad activation %d", act);

@@ -971,6 +971,104 @@ class SoftmaxActivationLayer:
         pass
 
 
+# ====================================================================================================== batch normalisation
+class BatchNormLayer:
+    """okl.py:1145-1222: (B, F) inputs; training mode normalises with the batch mean / population variance and
+    updates the running statistics, eval mode uses them.  As shipped: ``var = max(var, eps)`` before ``+ eps``; the backward's
+    chain rule uses the RUNNING variance while x_norm uses the batch one; gamma / beta gradients accumulate forever and the update
+    ``p -= lr * p.grad`` happens inside backward (same rule as the other layers, so the same bucket machinery - one all-reduce per
+    step under data parallelism; statistics stay per replica like the reference's)."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1):
+        self.num_features, self.eps, self.momentum = num_features, eps, momentum
+        self.gamma = Tensor(np.ones((1, num_features)))
+        self.beta = Tensor(np.zeros((1, num_features)))
+        self._bucket = _ParamBucket([self.gamma, self.beta])
+        self._running = None                          # device [mean | var], created on first use
+        self._running_host = (np.zeros((1, num_features)), np.ones((1, num_features)))
+        self.training = True
+
+    # running statistics live on the device; the attributes mirror the reference's ndarrays
+    def _running_buf(self):
+        if self._running is None:
+            ctx = get_ctx()
+            F = self.num_features
+            self._running = _DevBuf(ctx, 2 * F * 4)
+            h = np.ascontiguousarray(np.concatenate([np.asarray(self._running_host[0], dtype=np.float64).reshape(-1),
+                                                     np.asarray(self._running_host[1], dtype=np.float64).reshape(-1)]))
+            if h.size != 2 * F:
+                raise ValueError("running statistics have the wrong number of features")
+            check(lib.okl_h2d(ctx.h, self._running.ptr, h.ctypes.data, h.size, _lib.F64))
+        return self._running
+
+    def _read_running(self):
+        if self._running is None:
+            return self._running_host
+        ctx = get_ctx()
+        F = self.num_features
+        out = np.empty(2 * F, dtype=np.float64)
+        check(lib.okl_d2h(ctx.h, out.ctypes.data, self._running.ptr, out.size, _lib.F64))
+        return out[:F].reshape(1, F), out[F:].reshape(1, F)
+
+    @property
+    def running_mean(self):
+        return self._read_running()[0]
+
+    @running_mean.setter
+    def running_mean(self, v):
+        self._running_host = (np.asarray(v, dtype=np.float64), self._read_running()[1])
+        self._running = None
+
+    @property
+    def running_var(self):
+        return self._read_running()[1]
+
+    @running_var.setter
+    def running_var(self, v):
+        self._running_host = (self._read_running()[0], np.asarray(v, dtype=np.float64))
+        self._running = None
+
+    def forward(self, inputs: Tensor):
+        inputs = _as_tensor(inputs)
+        if inputs.ndim != 2:
+            raise ValueError(f"too many values to unpack (expected 2)" if inputs.ndim > 2 else "not enough values to unpack (expected 2, got 1)")
+        B, F = inputs.shape
+        if F != self.num_features:
+            raise ValueError(f"operands could not be broadcast together with shapes {inputs.shape} (1,{self.num_features})")
+        ctx = get_ctx()
+        self._bucket.materialize()
+        self.inputs, self.batch_size = inputs, B
+        self._mv = _DevBuf(ctx, 2 * F * 4)
+        out = Tensor._empty((B, F), np.float64)
+        if B:
+            check(lib.okl_bn_fwd(ctx.h, inputs._dptr(NCX), self._bucket.ptr(0), self._bucket.ptr(1), self._running_buf().ptr, self._mv.ptr,
+                                 out._ptr_raw(), B, F, float(self.eps), float(self.momentum), 1 if self.training else 0))
+        self.outputs = out
+        return out
+
+    def backward(self, dL_dout: Tensor, lr: float):
+        dL_dout = _as_tensor(dL_dout)
+        B, F = self.inputs.shape
+        if dL_dout.shape != (B, F):
+            raise ValueError(f"operands could not be broadcast together with shapes {dL_dout.shape} {(B, F)}")
+        ctx = get_ctx()
+        b = self._bucket
+        dx = Tensor._empty((B, F), np.float64)
+        check(lib.okl_bn_bwd(ctx.h, self.inputs._dptr(NCX), dL_dout._dptr(NCX), b.ptr(0), self._running_buf().ptr, self._mv.ptr,
+                             dx._ptr_raw(), b.grad_ptr(0), b.grad_ptr(1), B, F, float(self.eps)))
+        b.step(lr, False)
+        return dx
+
+    def get_params(self):
+        return {'gamma': self.gamma.data, 'beta': self.beta.data, 'running_mean': self.running_mean, 'running_var': self.running_var}
+
+    def set_params(self, params):
+        self.gamma.data = params['gamma']
+        self.beta.data = params['beta']
+        self.running_mean = params['running_mean']
+        self.running_var = params['running_var']
+
+
 # ====================================================================================================== pooling / flatten
 class _Pool:
     _kind = POOL_MAX

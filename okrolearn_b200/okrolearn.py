@@ -8,7 +8,8 @@ from .layers import (DenseLayer, Conv1DLayer, Conv2DLayer, Conv3DLayer, ReLUActi
                      TanhActivationLayer, SoftmaxActivationLayer, MaxPoolingLayer, AveragePoolingLayer, FlattenLayer,
                      UnflattenLayer, Unfold, Fold, ELUActivationLayer, SELUActivationLayer, LeakyReLUActivationLayer,
                      PReLUActivationLayer, SwishActivationLayer, GELUActivationLayer, SoftsignActivationLayer,
-                     HardTanhActivationLayer, LinearActivationLayer, SoftminActivationLayer, LogSoftmaxActivationLayer)
+                     HardTanhActivationLayer, LinearActivationLayer, SoftminActivationLayer, LogSoftmaxActivationLayer,
+                     BatchNormLayer)
 from .losses import CrossEntropyLoss, MSELoss, LossValue  # noqa: F401
 from .schedulers import (LearningRateScheduler, StepLRScheduler, TimeBasedDecayScheduler, ExponentialDecayScheduler,  # noqa: F401
                          LinearDecayScheduler)

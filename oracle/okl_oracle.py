@@ -291,6 +291,44 @@ def relu_backward(x, g):
     return g * (x > 0)
 
 
+class OracleBatchNorm:
+    """okl.py:1145-1222 restated line by line (2-D inputs; backward uses the running variance in the chain rule as shipped;
+    gamma / beta gradients accumulate forever and the update is applied inside backward)."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1):
+        self.eps, self.momentum = eps, momentum
+        self.gamma, self.beta = np.ones((1, num_features)), np.zeros((1, num_features))
+        self.running_mean, self.running_var = np.zeros((1, num_features)), np.ones((1, num_features))
+        self.ggrad = self.bgrad = None
+        self.training = True
+
+    def forward(self, x):
+        self.B = x.shape[0]
+        if self.training:
+            mean, var = np.mean(x, axis=0), np.var(x, axis=0)
+            self.running_mean = self.momentum * mean + (1 - self.momentum) * self.running_mean
+            self.running_var = self.momentum * var + (1 - self.momentum) * self.running_var
+        else:
+            mean, var = self.running_mean, self.running_var
+        var = np.maximum(var, self.eps)
+        self.xc = x - mean
+        self.xn = self.xc / np.sqrt(var + self.eps)
+        return np.nan_to_num(self.gamma * self.xn + self.beta, nan=0.0, posinf=1.0, neginf=0.0)
+
+    def backward(self, g, lr):
+        dgamma, dbeta = np.sum(g * self.xn, axis=0), np.sum(g, axis=0)
+        dxn = g * self.gamma
+        rv = self.running_var + self.eps
+        dvar = np.sum(dxn * self.xc * -0.5 * np.power(rv, -1.5), axis=0)
+        dmean = np.sum(dxn * -1 / np.sqrt(rv), axis=0) + dvar * np.mean(-2 * self.xc, axis=0)
+        dx = dxn / np.sqrt(rv) + dvar * 2 * self.xc / self.B + dmean / self.B
+        self.ggrad = dgamma if self.ggrad is None else self.ggrad + dgamma
+        self.bgrad = dbeta if self.bgrad is None else self.bgrad + dbeta
+        self.gamma = self.gamma - lr * self.ggrad
+        self.beta = self.beta - lr * self.bgrad
+        return dx
+
+
 # ---- the other elementwise activations (SURVEY 8(f) N1), each as the reference computes it
 _S2PI = np.sqrt(2 / np.pi)
 

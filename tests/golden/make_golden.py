@@ -353,6 +353,25 @@ close(O.logsoftmax_backward(yls, ga), dls, 1e-12, what="logsoftmax backward")
 save("activations2", x=xa, g=ga, prelu_y=ypl, prelu_dx=dpl, prelu_d_alpha=np.array(pl.d_alpha), prelu_alpha_after=np.array(pl.alpha),
      softmin_y=ysm, softmin_dx=dsm, logsoftmax_y=yls, logsoftmax_dx=dls, src="reference", **acts)
 
+# ----------------------------------------------------------------------------- BatchNormLayer
+xb1, xb2 = rng.standard_normal((12, 5)) * 1.5 + 0.3, rng.standard_normal((12, 5)) * 0.7 - 0.2
+gb1, gb2 = rng.standard_normal((12, 5)), rng.standard_normal((12, 5))
+rb, ob = ref.BatchNormLayer(5), O.OracleBatchNorm(5)
+bn = {}
+for step, (xv, gv) in enumerate(((xb1, gb1), (xb2, gb2))):
+    yr, yo = rb.forward(T(xv.copy())).data, ob.forward(xv)
+    close(yo, yr, 1e-13, what=f"batchnorm forward {step}")
+    dr, do = rb.backward(T(gv.copy()), 0.05).data, ob.backward(gv, 0.05)
+    close(do, dr, 1e-12, what=f"batchnorm backward {step}")
+    close(ob.gamma, rb.gamma.data, 1e-13, what="batchnorm gamma")
+    close(ob.beta, rb.beta.data, 1e-13, what="batchnorm beta")
+    bn.update({f"y{step}": yr, f"dx{step}": dr, f"gamma{step}": rb.gamma.data.copy(), f"beta{step}": rb.beta.data.copy(),
+               f"rm{step}": rb.running_mean.copy(), f"rv{step}": rb.running_var.copy()})
+rb.training = ob.training = False
+close(ob.forward(xb1), rb.forward(T(xb1.copy())).data, 1e-13, what="batchnorm eval forward")
+bn["y_eval"] = rb.forward(T(xb1.copy())).data
+save("batchnorm", x0=xb1, x1=xb2, g0=gb1, g1=gb2, src="reference", **bn)
+
 # ----------------------------------------------------------------------------- optimizers / schedulers
 w0 = rng.standard_normal((5, 4))
 gs = [rng.standard_normal((5, 4)) for _ in range(3)]

@@ -384,3 +384,41 @@ def test_other_activation_layers(okl):
     assert rel_err(d2.weights.data, W2 - 0.01 * (h.T @ dz2)) < 2e-5
     dz1 = (dz2 @ W2.T) * O.gelu_d(x @ W1)
     assert rel_err(d1.weights.data, W1 - 0.01 * (x.T @ dz1)) < 2e-5
+
+
+def test_batchnorm_layer(okl):
+    """BatchNormLayer on the device vs the reference's vectors: two training steps (outputs, input gradients, the
+    accumulated-gradient update of gamma / beta, running statistics), eval mode, and the params round trip."""
+    g = golden("batchnorm")
+    bn = okl.BatchNormLayer(5)
+    for step in (0, 1):
+        y = bn.forward(okl.Tensor(g[f"x{step}"]))
+        assert y.data.dtype == np.float64 and rel_err(y.data, g[f"y{step}"]) < 2e-6
+        dx = bn.backward(okl.Tensor(g[f"g{step}"]), 0.05)
+        assert rel_err(dx.data, g[f"dx{step}"]) < 2e-5
+        assert rel_err(bn.gamma.data, g[f"gamma{step}"]) < 2e-6 and rel_err(bn.beta.data, g[f"beta{step}"]) < 2e-6
+        assert rel_err(bn.running_mean, g[f"rm{step}"]) < 2e-6 and rel_err(bn.running_var, g[f"rv{step}"]) < 2e-6
+    bn.training = False
+    assert rel_err(bn.forward(okl.Tensor(g["x0"])).data, g["y_eval"]) < 2e-6
+    p = bn.get_params()
+    bn2 = okl.BatchNormLayer(5)
+    bn2.set_params(p)
+    bn2.training = False
+    assert rel_err(bn2.forward(okl.Tensor(g["x0"])).data, g["y_eval"]) < 2e-6
+    # inside a network, between two Dense layers, on larger random data vs the oracle
+    rng = np.random.default_rng(31)
+    X, G = rng.standard_normal((64, 40)), rng.standard_normal((64, 24))
+    net = okl.NeuralNetwork()
+    d1, b1, d2 = okl.DenseLayer(40, 33), okl.BatchNormLayer(33), okl.DenseLayer(33, 24)
+    W1, W2 = d1.weights.data.copy(), d2.weights.data.copy()
+    for l in (d1, b1, okl.ReLUActivationLayer(), d2):
+        net.add(l)
+    on = O.OracleNetwork([O.OracleDense(W1, np.zeros((1, 33))), O.OracleBatchNorm(33), O.OracleReLU(), O.OracleDense(W2, np.zeros((1, 24)))])
+    for _ in range(2):
+        out = net.forward(okl.Tensor(X))
+        oo = on.forward(X)
+        assert rel_err(out.data, oo) < 5e-5
+        net.backward(okl.Tensor(G), 0.01)
+        on.backward(G, 0.01)
+    assert rel_err(d1.weights.data, on.layers[0].W) < 5e-5 and rel_err(b1.gamma.data, on.layers[1].gamma) < 5e-5
+    assert rel_err(b1.running_var, on.layers[1].running_var) < 5e-5
