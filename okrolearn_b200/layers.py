@@ -1069,6 +1069,80 @@ class BatchNormLayer:
         self.running_var = params['running_var']
 
 
+class _RegularizationLayer:
+    """okl.py:1052-1142: wraps a layer that has ``gamma`` / ``beta`` (BatchNormLayer).  After the wrapped layer's backward the
+    penalty gradient is added to the accumulated gradients AND applied to the parameters once more (as shipped).  The vectors are
+    a few hundred floats: the arithmetic runs on the lazy host mirrors, exactly the reference's NumPy expressions."""
+
+    def __init__(self, layer, lambda_):
+        self.layer, self.lambda_ = layer, lambda_
+
+    def forward(self, inputs):
+        return self.layer.forward(inputs)
+
+    def _penalty_grad(self, p):
+        raise NotImplementedError
+
+    def backward(self, dL_dout, lr):
+        dL_dx = self.layer.backward(dL_dout, lr)
+        for t in (self.layer.gamma, self.layer.beta):
+            pg = self._penalty_grad(np.asarray(t.data))
+            t.grad = np.asarray(t.grad) + pg.reshape(np.asarray(t.grad).shape)
+            t.data = np.asarray(t.data) - lr * pg.reshape(np.asarray(t.data).shape)
+        return dL_dx
+
+    def get_params(self):
+        return self.layer.get_params()
+
+    def set_params(self, params):
+        self.layer.set_params(params)
+
+
+class L1RegularizationLayer(_RegularizationLayer):
+    def _penalty_grad(self, p):
+        return self.lambda_ * np.sign(p)                    # okl.py:1070-1071
+
+
+class L2RegularizationLayer(_RegularizationLayer):
+    def _penalty_grad(self, p):
+        return 2 * self.lambda_ * p                         # okl.py:1099-1100
+
+
+class L3RegularizationLayer(_RegularizationLayer):
+    def _penalty_grad(self, p):
+        return 3 * self.lambda_ * p ** 2                    # okl.py:1126-1127
+
+
+class DropoutLayer:
+    """okl.py:1336-1377.  The mask is drawn on the HOST with the reference's own call (np.random.binomial on the global NumPy
+    stream, scaled by 1 / (1 - rate)), so a seeded run drops exactly the units the reference drops; it is uploaded once and the
+    products run on the device."""
+
+    def __init__(self, rate=0.5):
+        self.rate = rate
+
+    def forward(self, inputs: Tensor, training=True):
+        inputs = _as_tensor(inputs)
+        self.inputs = inputs
+        if not training:
+            return inputs
+        self.mask = np.random.binomial(1, 1 - self.rate, size=inputs.shape) / (1 - self.rate)
+        self._mask_dev = Tensor(self.mask, requires_grad=False)
+        self.outputs = inputs * self._mask_dev
+        return self.outputs
+
+    def backward(self, dL_dout: Tensor, lr: float):
+        dx = _as_tensor(dL_dout) * self._mask_dev
+        _set_input_grad(self.inputs, dx)
+        return dx
+
+    def get_params(self):
+        return None
+
+    def set_params(self, params):
+        pass
+
+
 # ====================================================================================================== pooling / flatten
 class _Pool:
     _kind = POOL_MAX

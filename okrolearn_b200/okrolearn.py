@@ -9,7 +9,7 @@ from .layers import (DenseLayer, Conv1DLayer, Conv2DLayer, Conv3DLayer, ReLUActi
                      UnflattenLayer, Unfold, Fold, ELUActivationLayer, SELUActivationLayer, LeakyReLUActivationLayer,
                      PReLUActivationLayer, SwishActivationLayer, GELUActivationLayer, SoftsignActivationLayer,
                      HardTanhActivationLayer, LinearActivationLayer, SoftminActivationLayer, LogSoftmaxActivationLayer,
-                     BatchNormLayer)
+                     BatchNormLayer, L1RegularizationLayer, L2RegularizationLayer, L3RegularizationLayer, DropoutLayer)
 from .losses import CrossEntropyLoss, MSELoss, LossValue  # noqa: F401
 from .schedulers import (LearningRateScheduler, StepLRScheduler, TimeBasedDecayScheduler, ExponentialDecayScheduler,  # noqa: F401
                          LinearDecayScheduler)

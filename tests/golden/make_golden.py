@@ -371,6 +371,20 @@ rb.training = ob.training = False
 close(ob.forward(xb1), rb.forward(T(xb1.copy())).data, 1e-13, what="batchnorm eval forward")
 bn["y_eval"] = rb.forward(T(xb1.copy())).data
 save("batchnorm", x0=xb1, x1=xb2, g0=gb1, g1=gb2, src="reference", **bn)
+# regularisation wrappers around BatchNorm (two steps each) and Dropout with a seeded mask
+reg = {}
+for nm, cls in (("l1", ref.L1RegularizationLayer), ("l2", ref.L2RegularizationLayer), ("l3", ref.L3RegularizationLayer)):
+    lay = cls(ref.BatchNormLayer(5), 0.01)
+    for step, (xv, gv) in enumerate(((xb1, gb1), (xb2, gb2))):
+        lay.forward(T(xv.copy()))
+        reg[f"{nm}_dx{step}"] = lay.backward(T(gv.copy()), 0.05).data
+    reg[f"{nm}_gamma"], reg[f"{nm}_beta"] = lay.layer.gamma.data.copy(), lay.layer.beta.data.copy()
+    reg[f"{nm}_ggrad"], reg[f"{nm}_bgrad"] = np.asarray(lay.layer.gamma.grad).copy(), np.asarray(lay.layer.beta.grad).copy()
+np.random.seed(123)
+dl = ref.DropoutLayer(0.3)
+yd = dl.forward(T(xb1.copy())).data
+dd = dl.backward(T(gb1.copy()), 0.05).data
+save("reg_dropout", x0=xb1, x1=xb2, g0=gb1, g1=gb2, drop_y=yd, drop_dx=dd, drop_mask=dl.mask, src="reference", **reg)
 
 # ----------------------------------------------------------------------------- optimizers / schedulers
 w0 = rng.standard_normal((5, 4))

@@ -422,3 +422,26 @@ def test_batchnorm_layer(okl):
         on.backward(G, 0.01)
     assert rel_err(d1.weights.data, on.layers[0].W) < 5e-5 and rel_err(b1.gamma.data, on.layers[1].gamma) < 5e-5
     assert rel_err(b1.running_var, on.layers[1].running_var) < 5e-5
+
+
+def test_regularization_wrappers_and_dropout(okl):
+    """L1 / L2 / L3RegularizationLayer around BatchNormLayer (two steps: the penalty is added to the accumulated gradients and applied
+    once more, okl.py:1070-1078) and DropoutLayer with the reference's seeded host mask, vs vectors from the running reference."""
+    g = golden("reg_dropout")
+    for nm, cls in (("l1", okl.L1RegularizationLayer), ("l2", okl.L2RegularizationLayer), ("l3", okl.L3RegularizationLayer)):
+        lay = cls(okl.BatchNormLayer(5), 0.01)
+        for step in (0, 1):
+            lay.forward(okl.Tensor(g[f"x{step}"]))
+            dx = lay.backward(okl.Tensor(g[f"g{step}"]), 0.05)
+            assert rel_err(dx.data, g[f"{nm}_dx{step}"]) < 3e-5, nm
+        assert rel_err(lay.layer.gamma.data, g[f"{nm}_gamma"]) < 3e-6 and rel_err(lay.layer.beta.data, g[f"{nm}_beta"]) < 3e-6, nm
+        assert rel_err(np.asarray(lay.layer.gamma.grad).reshape(-1), g[f"{nm}_ggrad"].reshape(-1)) < 3e-6, nm
+        assert rel_err(np.asarray(lay.layer.beta.grad).reshape(-1), g[f"{nm}_bgrad"].reshape(-1)) < 3e-6, nm
+    np.random.seed(123)
+    dl = okl.DropoutLayer(0.3)
+    y = dl.forward(okl.Tensor(g["x0"]))
+    assert np.array_equal(dl.mask, g["drop_mask"])            # same host RNG call -> the same units are dropped
+    assert rel_err(y.data, g["drop_y"]) < 1e-6
+    assert rel_err(dl.backward(okl.Tensor(g["g0"]), 0.05).data, g["drop_dx"]) < 1e-6
+    xt = okl.Tensor(g["x0"])
+    assert dl.forward(xt, training=False) is xt
