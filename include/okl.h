@@ -192,6 +192,13 @@ int okl_binary(okl_ctx* ctx, int op, const void* a, const void* b, void* out, si
 /* x *= alpha   (final `inputs.data / temperature`, okl.py:2890) */
 int okl_scale(okl_ctx* ctx, void* x, size_t n, float alpha);
 
+/* Conv2DLayer(transposed=True) (okl.py:815-840, 891-926) needs no kernel of its own: its forward IS
+ * okl_conv_dgrad of the mirrored ordinary convolution (C = out_channels, O = in_channels, input extent = the transposed layer's
+ * OUTPUT extent), its input gradient IS okl_conv_fprop of the output gradient, its filter gradient IS okl_conv_wgrad with the two
+ * activations swapped.  Only the bias needs these two: y[n, c, s] += b[c] and db[c] = sum_{n, s} g[n, c, s]. */
+int okl_bias_add(okl_ctx* ctx, void* y, const void* b, int N, int C, long long S);
+int okl_bias_grad(okl_ctx* ctx, const void* g, void* db, int N, int C, long long S);
+
 /* ------------------------------------------------------------------ BatchNormLayer (okl.py:1145-1222), (B, F) inputs
  * fwd: batch mean / population variance over axis 0 (training) or the running statistics; running = momentum * batch +
  * (1 - momentum) * running; y = gamma (x - mean) / sqrt(max(var, eps) + eps) + beta, nan_to_num.  *_mean_var are 2F floats

@@ -63,6 +63,8 @@ SIGNATURES = {
     "okl_h2d_i32": (_i, [_vp, _vp, _vp, _sz, _i]),
     "okl_permute": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i]),
     "okl_gather_rows": (_i, [_vp, _vp, _vp, _vp, _ll, _ll]),
+    "okl_bias_add": (_i, [_vp, _vp, _vp, _i, _i, _ll]),
+    "okl_bias_grad": (_i, [_vp, _vp, _vp, _i, _i, _ll]),
     "okl_bn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i]),
     "okl_bn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f]),
     "okl_unfold_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i]),

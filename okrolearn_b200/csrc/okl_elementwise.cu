@@ -1064,6 +1064,29 @@ int okl_loss_post(okl_ctx* ctx, float* host_slot, const void* dev_loss, unsigned
   return OKL_OK;
 }
 
+namespace {
+__global__ void bias_add_kernel(float* __restrict__ y, const float* __restrict__ b, int C, long long S, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] += b[(i / S) % C];
+}
+}  // namespace
+
+// y[n, c, s] += b[c] in place (transposed convolution's bias, okl.py:838)
+extern "C" int okl_bias_add(okl_ctx* ctx, void* y, const void* b, int N, int C, long long S) {
+  OKL_REQUIRE(ctx && N >= 0 && C >= 1 && S >= 1, "bad bias_add shape");
+  const size_t n = (size_t)N * C * S;
+  if (n == 0) return OKL_OK;
+  OKL_REQUIRE(y && b, "NULL argument");
+  bias_add_kernel<<<okl_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>((float*)y, (const float*)b, C, S, n);
+  OKL_LAUNCHED(ctx, "bias_add");
+  return OKL_OK;
+}
+
+// db[c] = sum over n and s of g[n, c, s] (okl.py:917)
+extern "C" int okl_bias_grad(okl_ctx* ctx, const void* g, void* db, int N, int C, long long S) {
+  OKL_REQUIRE(ctx && g && db && N >= 1 && C >= 1 && S >= 1, "bad bias_grad arguments");
+  return okl_channel_sum(ctx, (const float*)g, (float*)db, N, C, S, OKL_NCX);
+}
+
 extern "C" int okl_unfold_fwd(okl_ctx* ctx, const void* x, void* out, int N, int C, int H, int W, int k, int stride, int pad) {
   OKL_REQUIRE(ctx && N >= 0 && C >= 1 && H >= 1 && W >= 1 && k >= 1 && stride >= 1 && pad >= 0, "bad unfold shape");
   const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;

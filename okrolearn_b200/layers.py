@@ -540,8 +540,12 @@ class Conv1DLayer(_ConvBase):
 
 
 class Conv2DLayer(_ConvBase):
-    """okl.py:767-933 (normal mode).  filters (O,C,kh,kw) float64 * 0.1, biases (O,1); int-or-tuple kernel/stride/padding;
-    output float64.  ``transposed=True`` (okl.py:815-840) is outside the hot path."""
+    """okl.py:767-933.  filters (O,C,kh,kw) float64 * 0.1, biases (O,1); int-or-tuple kernel/stride/padding; output float64.
+    ``transposed=True`` (okl.py:815-840, 891-926): filters (C_in, C_out, kh, kw); the forward is the data-gradient
+    kernel of the mirrored ordinary convolution, the input gradient its forward kernel and the filter gradient its weight-gradient
+    kernel with the activations swapped - no kernel of its own.  As shipped, padding > 0 raises (the output is allocated at the
+    cropped size and then scattered into, okl.py:821-832); the shipped backward raises for every shape (okl.py:904-912 broadcast,
+    924 bias shape) - implemented with the intended sums, cross-checked with torch.autograd like the other conv backward paths."""
     _nd, _np_dtype = 2, np.float64
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, transposed=False):
@@ -549,12 +553,75 @@ class Conv2DLayer(_ConvBase):
         self.kernel_size, self.stride, self.padding = self._k, self._s, self._p
         self.transposed = transposed
         if transposed:
-            raise NotImplementedError("Conv2DLayer(transposed=True) is not part of the B200 hot path (SURVEY.md 8(f) N3)")
-        self.filters = Tensor(np.random.randn(out_channels, in_channels, *self._k) * 0.1)
+            self.filters = Tensor(np.random.randn(in_channels, out_channels, *self._k) * 0.1)
+        else:
+            self.filters = Tensor(np.random.randn(out_channels, in_channels, *self._k) * 0.1)
         self.biases = Tensor(np.zeros((out_channels, 1)))
         self._bucket = _ParamBucket([self.filters, self.biases])
 
+    def _tc_eligible(self):
+        return (not self.transposed) and super()._tc_eligible()
+
+    def _mirror_desc(self, N, out_hw):
+        """descriptor of the ordinary convolution (C = out_channels -> O = in_channels) whose dgrad / fprop / wgrad are this
+        transposed layer's forward / input gradient / filter gradient; its input extent is our OUTPUT extent"""
+        d = ConvDesc()
+        d.nd, d.N, d.C, d.O = 2, N, self.out_channels, self.in_channels
+        for i in range(2):
+            d.inp[i], d.k[i], d.s[i], d.p[i] = out_hw[i], self._k[i], self._s[i], 0
+        d.act, d.x_layout, d.y_layout = ACT_NONE, NCX, NCX
+        return d
+
+    def forward_transposed(self, inputs: Tensor):
+        inputs = _as_tensor(inputs)
+        if inputs.ndim != 4:
+            raise ValueError(f"expected a 4-D input (N, C, H, W), got shape {inputs.shape}")
+        if inputs.shape[1] != self.in_channels:
+            raise ValueError(f"input has {inputs.shape[1]} channels, layer expects {self.in_channels}")
+        if self._p[0] > 0 or self._p[1] > 0:
+            raise ValueError("operands could not be broadcast together: forward_transposed with padding > 0 scatters into an output "
+                             "allocated at the cropped size (okl.py:821-832 raises the same way)")
+        ctx = get_ctx()
+        self._bucket.materialize()
+        self.inputs = inputs
+        N, _, H, W = inputs.shape
+        oh, ow = (H - 1) * self._s[0] + self._k[0], (W - 1) * self._s[1] + self._k[1]
+        d = self._mirror_desc(N, (oh, ow))
+        out = Tensor._empty((N, self.out_channels, oh, ow), np.float64)
+        if out.size:
+            check(lib.okl_conv_dgrad(ctx.h, C.byref(d), inputs._dptr(NCX), self._bucket.ptr(0), out._ptr_raw(), None))
+            check(lib.okl_bias_add(ctx.h, out._ptr_raw(), self._bucket.ptr(1), N, self.out_channels, oh * ow))
+            if self._fused_act != ACT_NONE:            # planner fused a following ReLU / sigmoid into "this layer's epilogue"
+                check(lib.okl_act_fwd(ctx.h, self._fused_act, out._ptr_raw(), out._ptr_raw(), out.size))
+        self.outputs = out
+        return out
+
+    def backward_transposed(self, dL_dout: Tensor, lr: float):
+        dL_dout = _as_tensor(dL_dout)
+        ctx = get_ctx()
+        x = self.inputs
+        N, _, H, W = x.shape
+        oh, ow = (H - 1) * self._s[0] + self._k[0], (W - 1) * self._s[1] + self._k[1]
+        if dL_dout.shape != (N, self.out_channels, oh, ow):
+            raise ValueError(f"dL_dout shape {dL_dout.shape} does not match the layer output {(N, self.out_channels, oh, ow)}")
+        d = self._mirror_desc(N, (oh, ow))
+        b = self._bucket
+        gp = dL_dout._dptr(NCX)
+        need_dx = getattr(self, "_need_dx", True)
+        dX = Tensor._empty(x.shape, np.float64) if need_dx else None
+        if need_dx and dX.size:
+            check(lib.okl_conv_fprop(ctx.h, C.byref(d), gp, b.ptr(0), None, dX._ptr_raw()))
+            if self._dx_relu_mask:                      # a ReLU fused into the previous layer: its backward applied here
+                check(lib.okl_act_bwd(ctx.h, ACT_RELU, x._dptr(NCX), dX._ptr_raw(), dX._ptr_raw(), dX.size))
+        if N:
+            check(lib.okl_conv_wgrad(ctx.h, C.byref(d), gp, x._dptr(NCX), b.grad_ptr(0), None))
+            check(lib.okl_bias_grad(ctx.h, gp, b.grad_ptr(1), N, self.out_channels, oh * ow))
+        b.step(lr, self._defer_update)
+        return dX
+
     def forward(self, inputs: Tensor):
+        if self.transposed:
+            return self.forward_transposed(inputs)
         self.outputs = self._forward(inputs)
         # fused first block: what flows on to the (pass-through) ReLU and MaxPool layers is already the pooled tensor
         return self._fused_out if self._fused_pool is not None else self.outputs
@@ -563,6 +630,8 @@ class Conv2DLayer(_ConvBase):
         return self.forward(inputs)
 
     def backward(self, dL_dout: Tensor, lr: float):
+        if self.transposed:
+            return self.backward_transposed(dL_dout, lr)
         return self._backward(dL_dout, lr)
 
     def backward_normal(self, dL_dout: Tensor, lr: float):

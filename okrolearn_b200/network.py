@@ -275,7 +275,7 @@ class NeuralNetwork:
             ls[0]._need_dx = False
         # first block Conv2D(3x3, s1) -> ReLU -> MaxPool(2,2) with no dX needed: one fused kernel each way, the un-pooled
         # activation and its gradient are never materialised
-        if (self.fuse_activations and self.fuse_conv_pool and len(ls) >= 3 and isinstance(ls[0], Conv2DLayer) and
+        if (self.fuse_activations and self.fuse_conv_pool and len(ls) >= 3 and isinstance(ls[0], Conv2DLayer) and not ls[0].transposed and
                 not ls[0]._need_dx and isinstance(ls[1], ReLUActivationLayer) and isinstance(ls[2], MaxPoolingLayer) and
                 int(ls[2].pool_size) == 2 and int(ls[2].stride) == 2 and ls[0]._k == (3, 3) and ls[0]._s == (1, 1) and
                 ls[0].in_channels in (1, 3) and ls[0].out_channels * ls[0].in_channels * 9 <= 10000):

@@ -291,6 +291,38 @@ def relu_backward(x, g):
     return g * (x > 0)
 
 
+def conv2d_transposed_forward(x, F, b, stride, padding):
+    """okl.py:815-840 as written: F is (in_channels, out_channels, kh, kw); every input pixel scatters its k x k stamp, the
+    result is cropped by the padding, then the bias is added."""
+    s, p = _tup(stride, 2), _tup(padding, 2)
+    N, Ci, H, Wd = x.shape
+    Co, kh, kw = F.shape[1], F.shape[2], F.shape[3]
+    OH, OW = (H - 1) * s[0] - 2 * p[0] + kh, (Wd - 1) * s[1] - 2 * p[1] + kw
+    out = np.zeros((N, Co, OH + 2 * p[0], OW + 2 * p[1]))
+    for i in range(H):
+        for j in range(Wd):
+            out[:, :, i * s[0]:i * s[0] + kh, j * s[1]:j * s[1] + kw] += np.sum(x[:, :, i, j][:, :, None, None, None] * F, axis=1)
+    if p[0] > 0 or p[1] > 0:
+        out = out[:, :, p[0]:out.shape[2] - p[0], p[1]:out.shape[3] - p[1]]
+    return out + np.asarray(b).reshape(1, -1, 1, 1)
+
+
+def conv2d_transposed_backward(x, F, g, stride, padding):
+    """okl.py:891-917 (the loops as written; the bias gradient is returned as (O, 1) - the shipped update at okl.py:924 raises on
+    its (1, O, 1, 1) shape exactly like the ordinary layer's, repair R2).  Returns dF, db, dX."""
+    s, p = _tup(stride, 2), _tup(padding, 2)
+    N, Ci, H, Wd = x.shape
+    kh, kw = F.shape[2], F.shape[3]
+    gp = np.pad(g, ((0, 0), (0, 0), (p[0], p[0]), (p[1], p[1])), mode="constant")
+    dF, dX = np.zeros_like(F, dtype=np.float64), np.zeros((N, Ci, H, Wd))
+    for i in range(H):
+        for j in range(Wd):
+            win = gp[:, None, :, i * s[0]:i * s[0] + kh, j * s[1]:j * s[1] + kw]
+            dF += np.sum(x[:, :, i:i + 1, j:j + 1][:, :, None, :, :] * win, axis=0)
+            dX[:, :, i, j] = np.sum(F * win, axis=(2, 3, 4))
+    return dF, np.sum(g, axis=(0, 2, 3)).reshape(-1, 1), dX
+
+
 class OracleBatchNorm:
     """okl.py:1145-1222 restated line by line (2-D inputs; backward uses the running variance in the chain rule as shipped;
     gamma / beta gradients accumulate forever and the update is applied inside backward)."""

@@ -353,6 +353,45 @@ close(O.logsoftmax_backward(yls, ga), dls, 1e-12, what="logsoftmax backward")
 save("activations2", x=xa, g=ga, prelu_y=ypl, prelu_dx=dpl, prelu_d_alpha=np.array(pl.d_alpha), prelu_alpha_after=np.array(pl.alpha),
      softmin_y=ysm, softmin_dx=dsm, logsoftmax_y=yls, logsoftmax_dx=dls, src="reference", **acts)
 
+# ----------------------------------------------------------------------------- Conv2DLayer(transposed=True)
+import torch
+import torch.nn.functional as TF
+tconv = {}
+for ci, (Ci, Co, k, st, pd, hw) in enumerate(((3, 4, 3, 1, 0, (5, 6)), (2, 5, (3, 2), 2, 0, (6, 5)), (4, 3, 4, (2, 3), 0, (4, 4)))):
+    lay = ref.Conv2DLayer(Ci, Co, k, st, pd, transposed=True)
+    Ft = rng.standard_normal(lay.filters.data.shape) * 0.3
+    bt = rng.standard_normal((Co, 1)) * 0.2
+    lay.filters.data, lay.biases.data = Ft.copy(), bt.copy()
+    xt_ = rng.standard_normal((2, Ci) + hw)
+    yr = lay.forward(T(xt_.copy())).data
+    close(O.conv2d_transposed_forward(xt_, Ft, bt, st, pd), yr, 1e-13, what=f"transposed conv forward {ci}")
+    gt_ = rng.standard_normal(yr.shape)
+    try:
+        lay.backward(T(gt_.copy()), 0.1)
+        raised = False
+    except ValueError:
+        raised = True
+    assert raised, "shipped backward_transposed was expected to raise (okl.py:904-912 broadcast)"
+    xt64 = torch.tensor(xt_, requires_grad=True)
+    Ft64 = torch.tensor(Ft, requires_grad=True)
+    bt64 = torch.tensor(bt.reshape(-1), requires_grad=True)
+    yt = TF.conv_transpose2d(xt64, Ft64, bt64, stride=st, padding=pd)
+    close(yt.detach().numpy(), yr, 1e-12, what=f"transposed conv forward vs torch {ci}")
+    yt.backward(torch.tensor(gt_))
+    dF, db_, dX_ = O.conv2d_transposed_backward(xt_, Ft, gt_, st, pd)
+    close(dF, Ft64.grad.numpy(), 1e-12, what=f"transposed dF vs torch {ci}")
+    close(db_.reshape(-1), bt64.grad.numpy(), 1e-12, what=f"transposed db vs torch {ci}")
+    close(dX_, xt64.grad.numpy(), 1e-12, what=f"transposed dX vs torch {ci}")
+    tconv.update({f"x{ci}": xt_, f"F{ci}": Ft, f"b{ci}": bt, f"y{ci}": yr, f"g{ci}": gt_, f"dF{ci}": dF, f"db{ci}": db_, f"dX{ci}": dX_,
+                  f"cfg{ci}": np.array([Ci, Co] + list(O._tup(k, 2)) + list(O._tup(st, 2)) + list(O._tup(pd, 2)))})
+try:                                              # padding > 0: the shipped forward allocates the CROPPED output and then scatters into it
+    ref.Conv2DLayer(2, 3, 3, 1, 1, transposed=True).forward(T(rng.standard_normal((1, 2, 4, 4))))
+    raised = False
+except ValueError:
+    raised = True
+assert raised, "forward_transposed with padding > 0 was expected to raise"
+save("conv2d_transposed", src="reference forward; backward = repaired loops cross-checked with torch.autograd", **tconv)
+
 # ----------------------------------------------------------------------------- BatchNormLayer
 xb1, xb2 = rng.standard_normal((12, 5)) * 1.5 + 0.3, rng.standard_normal((12, 5)) * 0.7 - 0.2
 gb1, gb2 = rng.standard_normal((12, 5)), rng.standard_normal((12, 5))

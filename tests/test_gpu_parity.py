@@ -445,3 +445,42 @@ def test_regularization_wrappers_and_dropout(okl):
     assert rel_err(dl.backward(okl.Tensor(g["g0"]), 0.05).data, g["drop_dx"]) < 1e-6
     xt = okl.Tensor(g["x0"])
     assert dl.forward(xt, training=False) is xt
+
+
+def test_conv2d_transposed_layer(okl):
+    """Conv2DLayer(transposed=True) = dgrad / fprop / wgrad of the mirrored convolution; forward vs the reference's
+    outputs, backward vs the torch-checked sums, the in-layer accumulated update, and the padding > 0 error behaviour."""
+    g = golden("conv2d_transposed")
+    for ci in range(3):
+        Ci, Co, kh, kw, sh, sw, ph, pw = [int(v) for v in g[f"cfg{ci}"]]
+        lay = okl.Conv2DLayer(Ci, Co, (kh, kw), (sh, sw), (ph, pw), transposed=True)
+        assert lay.filters.shape == (Ci, Co, kh, kw)
+        lay.filters.data, lay.biases.data = g[f"F{ci}"].copy(), g[f"b{ci}"].copy()
+        y = lay.forward(okl.Tensor(g[f"x{ci}"]))
+        assert y.data.dtype == np.float64 and rel_err(y.data, g[f"y{ci}"]) < TOL32
+        dX = lay.backward(okl.Tensor(g[f"g{ci}"]), 0.1)
+        assert rel_err(dX.data, g[f"dX{ci}"]) < TOL32
+        assert rel_err(lay.filters.grad, g[f"dF{ci}"]) < TOL32 and rel_err(np.asarray(lay.biases.grad).reshape(-1), g[f"db{ci}"].reshape(-1)) < TOL32
+        assert rel_err(lay.filters.data, g[f"F{ci}"] - 0.1 * g[f"dF{ci}"]) < TOL32
+        assert rel_err(lay.biases.data, g[f"b{ci}"] - 0.1 * g[f"db{ci}"]) < TOL32
+    with pytest.raises(ValueError):
+        okl.Conv2DLayer(2, 3, 3, 1, 1, transposed=True).forward(okl.Tensor(np.zeros((1, 2, 4, 4))))
+    # encoder / decoder stack through NeuralNetwork: Conv2D(s2) -> ReLU -> transposed Conv2D(s2) restores the extent
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((4, 3, 9, 9))
+    X.reshape(-1)[0] = abs(X.reshape(-1)[0]) + 0.1
+    enc, dec = okl.Conv2DLayer(3, 6, 3, 2, 0), okl.Conv2DLayer(6, 3, 3, 2, 0, transposed=True)
+    We, Wd = enc.filters.data.copy(), dec.filters.data.copy()
+    net = okl.NeuralNetwork()
+    for l in (enc, okl.ReLUActivationLayer(), dec):
+        net.add(l)
+    out = net.forward(okl.Tensor(X))
+    h = O.relu_forward(O.conv_forward_fast(X, We, np.zeros((6, 1)), 2, 0, dtype=np.float64))
+    yo = O.conv2d_transposed_forward(h, Wd, np.zeros((3, 1)), 2, 0)
+    assert out.shape == X.shape and rel_err(out.data, yo) < 2e-5
+    G = rng.standard_normal(X.shape)
+    net.backward(okl.Tensor(G), 0.05)
+    dF, db, dh = O.conv2d_transposed_backward(h, Wd, G, 2, 0)
+    assert rel_err(dec.filters.data, Wd - 0.05 * dF) < 2e-5
+    dWe, dbe, _ = O.conv_backward_fast(X, We, dh * (h > 0), 2, 0)
+    assert rel_err(enc.filters.data, We - 0.05 * dWe) < 2e-5
