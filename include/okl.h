@@ -199,6 +199,13 @@ int okl_scale(okl_ctx* ctx, void* x, size_t n, float alpha);
 int okl_bias_add(okl_ctx* ctx, void* y, const void* b, int N, int C, long long S);
 int okl_bias_grad(okl_ctx* ctx, const void* g, void* db, int N, int C, long long S);
 
+/* Max / AverageUnpoolingLayer (okl.py:2619-2705; kind 0 = max: the value, 1 = average: value / pool^2) and Zero / Reflection
+ * PaddingLayer (okl.py:1920-1986; reflect = np.pad mode 'reflect'; backward of both = the crop) - SURVEY 8(f) N3 */
+int okl_unpool_fwd(okl_ctx* ctx, int kind, const void* x, void* y, long long NC, int H, int W, int pool, int stride);
+int okl_unpool_bwd(okl_ctx* ctx, int kind, const void* g, void* dx, long long NC, int H, int W, int pool, int stride);
+int okl_pad2d(okl_ctx* ctx, const void* x, void* y, long long NC, int H, int W, int top, int bottom, int left, int right, int reflect);
+int okl_crop2d(okl_ctx* ctx, const void* g, void* dx, long long NC, int GH, int GW, int top, int left, int h, int w);
+
 /* ------------------------------------------------------------------ BatchNormLayer (okl.py:1145-1222), (B, F) inputs
  * fwd: batch mean / population variance over axis 0 (training) or the running statistics; running = momentum * batch +
  * (1 - momentum) * running; y = gamma (x - mean) / sqrt(max(var, eps) + eps) + beta, nan_to_num.  *_mean_var are 2F floats

@@ -65,6 +65,10 @@ SIGNATURES = {
     "okl_gather_rows": (_i, [_vp, _vp, _vp, _vp, _ll, _ll]),
     "okl_bias_add": (_i, [_vp, _vp, _vp, _i, _i, _ll]),
     "okl_bias_grad": (_i, [_vp, _vp, _vp, _i, _i, _ll]),
+    "okl_unpool_fwd": (_i, [_vp, _i, _vp, _vp, _ll, _i, _i, _i, _i]),
+    "okl_unpool_bwd": (_i, [_vp, _i, _vp, _vp, _ll, _i, _i, _i, _i]),
+    "okl_pad2d": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i]),
+    "okl_crop2d": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i]),
     "okl_bn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i]),
     "okl_bn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f]),
     "okl_unfold_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i]),

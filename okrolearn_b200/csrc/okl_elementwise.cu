@@ -1087,6 +1087,115 @@ extern "C" int okl_bias_grad(okl_ctx* ctx, const void* g, void* db, int N, int C
   return okl_channel_sum(ctx, (const float*)g, (float*)db, N, C, S, OKL_NCX);
 }
 
+// ------------------------------------------------------------------------------------------------ un-pooling / padding
+namespace {
+// Max / AverageUnpoolingLayer.forward (okl.py:2624-2637 / 2666-2679): every input pixel stamps a ps x ps block (value, or value /
+// ps^2) at (i * stride, j * stride) with plain assignment in (i, j) loop order - where stamps overlap the LAST one wins, where
+// none reaches the output stays 0.
+__global__ void unpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int OH, int OW, int ps, int st, float scale,
+                                  size_t total) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(idx % OW);
+    size_t t = idx / OW;
+    const int h = (int)(t % OH);
+    const size_t nc = t / OH;
+    const int i = min(H - 1, h / st), j = min(W - 1, w / st);
+    y[idx] = (h < i * st + ps && w < j * st + ps) ? x[(nc * H + i) * W + j] * scale : 0.f;
+  }
+}
+// backward (okl.py:2640-2649): dx[i, j] = scale * sum of the ps x ps block of g at (i * stride, j * stride)
+__global__ void unpool_bwd_kernel(const float* __restrict__ g, float* __restrict__ dx, int H, int W, int OH, int OW, int ps, int st, float scale,
+                                  size_t total) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % W);
+    size_t t = idx / W;
+    const int i = (int)(t % H);
+    const size_t nc = t / H;
+    float s = 0.f;
+    for (int u = 0; u < ps; u++)
+      for (int v = 0; v < ps; v++) s += g[(nc * OH + i * st + u) * OW + j * st + v];
+    dx[idx] = s * scale;
+  }
+}
+// Zero / ReflectionPaddingLayer.forward (okl.py:1946-1950, 1966-1969): np.pad over the two spatial axes, mode constant 0 / reflect
+__global__ void pad2d_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int pt, int pl, int OH, int OW, int reflect,
+                             size_t total) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(idx % OW);
+    size_t t = idx / OW;
+    const int h = (int)(t % OH);
+    const size_t nc = t / OH;
+    int ih = h - pt, iw = w - pl;
+    float v = 0.f;
+    if (reflect) {                                            // np.pad 'reflect': mirror without repeating the edge, periodically
+      const int ph = 2 * (H - 1), pw = 2 * (W - 1);
+      if (ph > 0) { ih %= ph; if (ih < 0) ih += ph; if (ih >= H) ih = ph - ih; } else ih = 0;
+      if (pw > 0) { iw %= pw; if (iw < 0) iw += pw; if (iw >= W) iw = pw - iw; } else iw = 0;
+      v = x[(nc * H + ih) * W + iw];
+    } else if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) {
+      v = x[(nc * H + ih) * W + iw];
+    }
+    y[idx] = v;
+  }
+}
+// backward of both padding layers (okl.py:1953-1955): the crop g[:, :, top : top + h, left : left + w]
+__global__ void crop2d_kernel(const float* __restrict__ g, float* __restrict__ dx, int GH, int GW, int top, int left, int h, int w, size_t total) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % w);
+    size_t t = idx / w;
+    const int r = (int)(t % h);
+    const size_t nc = t / h;
+    dx[idx] = g[(nc * GH + top + r) * GW + left + c];
+  }
+}
+}  // namespace
+
+extern "C" int okl_unpool_fwd(okl_ctx* ctx, int kind, const void* x, void* y, long long NC, int H, int W, int pool, int stride) {
+  OKL_REQUIRE(ctx && NC >= 0 && H >= 1 && W >= 1 && pool >= 1 && stride >= 1 && (kind == 0 || kind == 1), "bad unpool arguments");
+  const int OH = (H - 1) * stride + pool, OW = (W - 1) * stride + pool;
+  const size_t total = (size_t)NC * OH * OW;
+  if (total == 0) return OKL_OK;
+  OKL_REQUIRE(x && y, "NULL argument");
+  unpool_fwd_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)x, (float*)y, H, W, OH, OW, pool, stride,
+                                                                         kind == 0 ? 1.f : 1.f / (float)(pool * pool), total);
+  OKL_LAUNCHED(ctx, "unpool_fwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_unpool_bwd(okl_ctx* ctx, int kind, const void* g, void* dx, long long NC, int H, int W, int pool, int stride) {
+  OKL_REQUIRE(ctx && NC >= 0 && H >= 1 && W >= 1 && pool >= 1 && stride >= 1 && (kind == 0 || kind == 1), "bad unpool arguments");
+  const int OH = (H - 1) * stride + pool, OW = (W - 1) * stride + pool;
+  const size_t total = (size_t)NC * H * W;
+  if (total == 0) return OKL_OK;
+  OKL_REQUIRE(g && dx, "NULL argument");
+  unpool_bwd_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)g, (float*)dx, H, W, OH, OW, pool, stride,
+                                                                         kind == 0 ? 1.f : 1.f / (float)(pool * pool), total);
+  OKL_LAUNCHED(ctx, "unpool_bwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_pad2d(okl_ctx* ctx, const void* x, void* y, long long NC, int H, int W, int top, int bottom, int left, int right, int reflect) {
+  OKL_REQUIRE(ctx && NC >= 0 && H >= 1 && W >= 1 && top >= 0 && bottom >= 0 && left >= 0 && right >= 0, "bad pad2d arguments");
+  OKL_REQUIRE(!reflect || ((top < H && bottom < H && left < W && right < W) || (H > 1 && W > 1)), "reflect padding needs extent > 1");
+  const int OH = H + top + bottom, OW = W + left + right;
+  const size_t total = (size_t)NC * OH * OW;
+  if (total == 0) return OKL_OK;
+  OKL_REQUIRE(x && y, "NULL argument");
+  pad2d_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)x, (float*)y, H, W, top, left, OH, OW, reflect, total);
+  OKL_LAUNCHED(ctx, "pad2d");
+  return OKL_OK;
+}
+
+extern "C" int okl_crop2d(okl_ctx* ctx, const void* g, void* dx, long long NC, int GH, int GW, int top, int left, int h, int w) {
+  OKL_REQUIRE(ctx && NC >= 0 && top >= 0 && left >= 0 && h >= 0 && w >= 0 && top + h <= GH && left + w <= GW, "bad crop2d arguments");
+  const size_t total = (size_t)NC * h * w;
+  if (total == 0) return OKL_OK;
+  OKL_REQUIRE(g && dx, "NULL argument");
+  crop2d_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)g, (float*)dx, GH, GW, top, left, h, w, total);
+  OKL_LAUNCHED(ctx, "crop2d");
+  return OKL_OK;
+}
+
 extern "C" int okl_unfold_fwd(okl_ctx* ctx, const void* x, void* out, int N, int C, int H, int W, int k, int stride, int pad) {
   OKL_REQUIRE(ctx && N >= 0 && C >= 1 && H >= 1 && W >= 1 && k >= 1 && stride >= 1 && pad >= 0, "bad unfold shape");
   const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;

@@ -1278,6 +1278,138 @@ class AveragePoolingLayer(_Pool):
     _kind = POOL_AVG
 
 
+class _Unpool:
+    """okl.py:2619-2705: every input pixel stamps a pool x pool block at (i * stride, j * stride) by plain assignment (overlaps:
+    the last stamp in (i, j) order wins; gaps stay 0); backward sums the block.  Output float64."""
+    _kind = 0
+
+    def __init__(self, pool_size=2, stride=2):
+        self.pool_size, self.stride = pool_size, stride
+
+    def forward(self, inputs):
+        inputs = _as_tensor(inputs)
+        if inputs.ndim != 4:
+            raise ValueError(f"not enough values to unpack (expected 4, got {inputs.ndim})")
+        N, Cc, H, W = inputs.shape
+        ps, st = int(self.pool_size), int(self.stride)
+        ctx = get_ctx()
+        out = Tensor._empty((N, Cc, (H - 1) * st + ps, (W - 1) * st + ps), np.float64)
+        if out.size:
+            check(lib.okl_unpool_fwd(ctx.h, self._kind, inputs._dptr(NCX), out._ptr_raw(), N * Cc, H, W, ps, st))
+        self.inputs, self.output = inputs, out
+        return out
+
+    def backward(self, dL_dout: Tensor, lr: float = None):
+        dL_dout = _as_tensor(dL_dout)
+        N, Cc, H, W = self.inputs.shape
+        ps, st = int(self.pool_size), int(self.stride)
+        if dL_dout.shape != (N, Cc, (H - 1) * st + ps, (W - 1) * st + ps):
+            raise ValueError(f"could not broadcast input array from shape {dL_dout.shape} into the unpooled extent")
+        ctx = get_ctx()
+        dx = Tensor._empty(self.inputs.shape, _float_dtype(self.inputs))
+        if dx.size:
+            check(lib.okl_unpool_bwd(ctx.h, self._kind, dL_dout._dptr(NCX), dx._ptr_raw(), N * Cc, H, W, ps, st))
+        _set_input_grad(self.inputs, dx)
+        return dx
+
+    def get_params(self):
+        return None
+
+    def set_params(self, params):
+        pass
+
+
+class MaxUnpoolingLayer(_Unpool):
+    _kind = 0
+
+
+class AverageUnpoolingLayer(_Unpool):
+    _kind = 1
+
+
+class PaddingLayer:
+    """okl.py:1920-1943: int, (pad_h, pad_w) or (top, bottom, left, right)."""
+
+    def __init__(self, padding):
+        if isinstance(padding, int):
+            self.padding = ((padding, padding), (padding, padding))
+        elif len(padding) == 2:
+            self.padding = ((padding[0], padding[0]), (padding[1], padding[1]))
+        elif len(padding) == 4:
+            self.padding = ((padding[0], padding[1]), (padding[2], padding[3]))
+        else:
+            raise ValueError("Invalid padding format. Use int, (pad_h, pad_w) or (pad_top, pad_bottom, pad_left, pad_right)")
+
+    def forward(self, inputs: Tensor) -> Tensor:
+        raise NotImplementedError
+
+    def backward(self, dL_dout: Tensor, lr: float = None) -> Tensor:
+        raise NotImplementedError
+
+    def get_params(self):
+        return None
+
+    def set_params(self, params):
+        pass
+
+    _reflect = 0
+
+    def _pad(self, inputs):
+        inputs = _as_tensor(inputs)
+        if inputs.ndim != 4:
+            raise ValueError("operands could not be broadcast together with remapped shapes [original->remapped]")   # np.pad pad_width
+        (pt, pb), (pl, pr) = self.padding
+        N, Cc, H, W = inputs.shape
+        if self._reflect and ((max(pt, pb) > 0 and H < 2) or (max(pl, pr) > 0 and W < 2)):
+            raise ValueError("can't extend empty axis / single element using modes other than 'constant'")
+        ctx = get_ctx()
+        out = Tensor._empty((N, Cc, H + pt + pb, W + pl + pr), _float_dtype(inputs))
+        if out.size:
+            check(lib.okl_pad2d(ctx.h, inputs._dptr(NCX), out._ptr_raw(), N * Cc, H, W, pt, pb, pl, pr, self._reflect))
+        self.inputs = inputs
+        return out
+
+    def _crop(self, dL_dout):
+        dL_dout = _as_tensor(dL_dout)
+        (pt, pb), (pl, pr) = self.padding
+        N, Cc, GH, GW = dL_dout.shape
+        # okl.py:1955 slices pad_top:-pad_bottom - an empty slice when the bottom / right pad is 0 (as shipped)
+        h = max(GH - pb - pt, 0) if pb > 0 else 0
+        w = max(GW - pr - pl, 0) if pr > 0 else 0
+        ctx = get_ctx()
+        dx = Tensor._empty((N, Cc, h, w), _float_dtype(dL_dout))
+        if dx.size:
+            check(lib.okl_crop2d(ctx.h, dL_dout._dptr(NCX), dx._ptr_raw(), N * Cc, GH, GW, pt, pl, h, w))
+        if dx.shape == self.inputs.shape:
+            _set_input_grad(self.inputs, dx)
+        elif self.inputs.requires_grad and self.inputs._grad is not None:
+            raise ValueError(f"operands could not be broadcast together with shapes {self.inputs.shape} {dx.shape}")
+        elif self.inputs.requires_grad:
+            self.inputs._grad = dx
+        return dx
+
+
+class ZeroPaddingLayer(PaddingLayer):
+    """okl.py:1946-1962."""
+
+    def forward(self, inputs: Tensor) -> Tensor:
+        return self._pad(inputs)
+
+    def backward(self, dL_dout: Tensor, lr: float = None) -> Tensor:
+        return self._crop(dL_dout)
+
+
+class ReflectionPaddingLayer(PaddingLayer):
+    """okl.py:1965-1981: np.pad mode 'reflect'; the backward is the plain crop (as shipped, not the adjoint of the reflection)."""
+    _reflect = 1
+
+    def forward(self, inputs: Tensor) -> Tensor:
+        return self._pad(inputs)
+
+    def backward(self, dL_dout: Tensor, lr: float = None) -> Tensor:
+        return self._crop(dL_dout)
+
+
 class FlattenLayer:
     """okl.py:639-651: (N, ...) -> (N, -1) and back; a zero-copy view of the device block."""
 

@@ -9,7 +9,8 @@ from .layers import (DenseLayer, Conv1DLayer, Conv2DLayer, Conv3DLayer, ReLUActi
                      UnflattenLayer, Unfold, Fold, ELUActivationLayer, SELUActivationLayer, LeakyReLUActivationLayer,
                      PReLUActivationLayer, SwishActivationLayer, GELUActivationLayer, SoftsignActivationLayer,
                      HardTanhActivationLayer, LinearActivationLayer, SoftminActivationLayer, LogSoftmaxActivationLayer,
-                     BatchNormLayer, L1RegularizationLayer, L2RegularizationLayer, L3RegularizationLayer, DropoutLayer)
+                     BatchNormLayer, L1RegularizationLayer, L2RegularizationLayer, L3RegularizationLayer, DropoutLayer,
+                     MaxUnpoolingLayer, AverageUnpoolingLayer, PaddingLayer, ZeroPaddingLayer, ReflectionPaddingLayer)
 from .losses import CrossEntropyLoss, MSELoss, LossValue  # noqa: F401
 from .schedulers import (LearningRateScheduler, StepLRScheduler, TimeBasedDecayScheduler, ExponentialDecayScheduler,  # noqa: F401
                          LinearDecayScheduler)

@@ -291,6 +291,39 @@ def relu_backward(x, g):
     return g * (x > 0)
 
 
+def unpool_forward(x, pool_size=2, stride=2, average=False):
+    """okl.py:2624-2637 / 2666-2679 as written (assignment: later stamps overwrite earlier ones)."""
+    N, C, H, Wd = x.shape
+    out = np.zeros((N, C, (H - 1) * stride + pool_size, (Wd - 1) * stride + pool_size))
+    dv = pool_size * pool_size if average else 1
+    for i in range(H):
+        for j in range(Wd):
+            out[:, :, i * stride:i * stride + pool_size, j * stride:j * stride + pool_size] = np.expand_dims(x[:, :, i, j], axis=(2, 3)) / dv
+    return out
+
+
+def unpool_backward(g, in_shape, pool_size=2, stride=2, average=False):
+    """okl.py:2640-2649 / 2682-2691."""
+    N, C, H, Wd = in_shape
+    dx = np.zeros(in_shape)
+    dv = pool_size * pool_size if average else 1
+    for i in range(H):
+        for j in range(Wd):
+            dx[:, :, i, j] = np.sum(g[:, :, i * stride:i * stride + pool_size, j * stride:j * stride + pool_size], axis=(2, 3)) / dv
+    return dx
+
+
+def pad_forward(x, padding, reflect=False):
+    """okl.py:1948-1949 / 1968: np.pad over the spatial axes; padding = ((top, bottom), (left, right))."""
+    return np.pad(x, ((0, 0), (0, 0)) + tuple(padding), mode="reflect") if reflect else np.pad(x, ((0, 0), (0, 0)) + tuple(padding), mode="constant", constant_values=0)
+
+
+def pad_backward(g, padding):
+    """okl.py:1953-1955 as written (a zero bottom / right pad makes the slice empty)."""
+    (pt, pb), (pl, pr) = padding
+    return g[:, :, pt:-pb, pl:-pr]
+
+
 def conv2d_transposed_forward(x, F, b, stride, padding):
     """okl.py:815-840 as written: F is (in_channels, out_channels, kh, kw); every input pixel scatters its k x k stamp, the
     result is cropped by the padding, then the bias is added."""

@@ -392,6 +392,29 @@ except ValueError:
 assert raised, "forward_transposed with padding > 0 was expected to raise"
 save("conv2d_transposed", src="reference forward; backward = repaired loops cross-checked with torch.autograd", **tconv)
 
+# ----------------------------------------------------------------------------- un-pooling / padding layers
+xu_ = rng.standard_normal((2, 3, 4, 5))
+up = {}
+for nm, cls, avg in (("max", ref.MaxUnpoolingLayer, False), ("avg", ref.AverageUnpoolingLayer, True)):
+    for tag, ps, st in (("a", 2, 2), ("b", 3, 2), ("c", 2, 3)):
+        lay = cls(ps, st)
+        y = lay.forward(T(xu_.copy())).data
+        close(O.unpool_forward(xu_, ps, st, avg), y, 0, what=f"{nm} unpool forward {tag}")
+        gg_ = rng.standard_normal(y.shape)
+        d = lay.backward(T(gg_.copy())).data
+        close(O.unpool_backward(gg_, xu_.shape, ps, st, avg), d, 1e-13, what=f"{nm} unpool backward {tag}")
+        up.update({f"{nm}_{tag}_y": y, f"{nm}_{tag}_g": gg_, f"{nm}_{tag}_dx": d})
+for nm, cls, refl in (("zero", ref.ZeroPaddingLayer, False), ("reflect", ref.ReflectionPaddingLayer, True)):
+    for tag, pd in (("a", 1), ("b", (2, 1)), ("c", (1, 2, 3, 1))):
+        lay = cls(pd)
+        y = lay.forward(T(xu_.copy())).data
+        close(O.pad_forward(xu_, lay.padding, refl), y, 0, what=f"{nm} pad forward {tag}")
+        gg_ = rng.standard_normal(y.shape)
+        d = lay.backward(T(gg_.copy())).data
+        close(O.pad_backward(gg_, lay.padding), d, 0, what=f"{nm} pad backward {tag}")
+        up.update({f"{nm}_{tag}_y": y, f"{nm}_{tag}_g": gg_, f"{nm}_{tag}_dx": d})
+save("unpool_pad", x=xu_, src="reference", **up)
+
 # ----------------------------------------------------------------------------- BatchNormLayer
 xb1, xb2 = rng.standard_normal((12, 5)) * 1.5 + 0.3, rng.standard_normal((12, 5)) * 0.7 - 0.2
 gb1, gb2 = rng.standard_normal((12, 5)), rng.standard_normal((12, 5))

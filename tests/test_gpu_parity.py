@@ -484,3 +484,29 @@ def test_conv2d_transposed_layer(okl):
     assert rel_err(dec.filters.data, Wd - 0.05 * dF) < 2e-5
     dWe, dbe, _ = O.conv_backward_fast(X, We, dh * (h > 0), 2, 0)
     assert rel_err(enc.filters.data, We - 0.05 * dWe) < 2e-5
+
+
+def test_unpooling_and_padding_layers(okl):
+    """Max / AverageUnpoolingLayer (overlapping stamps: last wins; gaps stay 0) and Zero / ReflectionPaddingLayer vs the
+    running reference's vectors."""
+    g = golden("unpool_pad")
+    x = g["x"]
+    for nm, cls in (("max", okl.MaxUnpoolingLayer), ("avg", okl.AverageUnpoolingLayer)):
+        for tag, ps, st in (("a", 2, 2), ("b", 3, 2), ("c", 2, 3)):
+            lay = cls(ps, st)
+            xt = okl.Tensor(x.copy())
+            assert rel_err(lay.forward(xt).data, g[f"{nm}_{tag}_y"]) < TOL32, (nm, tag)
+            dx = lay.backward(okl.Tensor(g[f"{nm}_{tag}_g"]))
+            assert rel_err(dx.data, g[f"{nm}_{tag}_dx"]) < TOL32, (nm, tag)
+            assert rel_err(np.asarray(xt.grad), g[f"{nm}_{tag}_dx"]) < TOL32
+    for nm, cls in (("zero", okl.ZeroPaddingLayer), ("reflect", okl.ReflectionPaddingLayer)):
+        for tag, pd in (("a", 1), ("b", (2, 1)), ("c", (1, 2, 3, 1))):
+            lay = cls(pd)
+            y = lay.forward(okl.Tensor(x.copy()))
+            assert y.shape == g[f"{nm}_{tag}_y"].shape and rel_err(y.data, g[f"{nm}_{tag}_y"]) < 1e-7, (nm, tag)
+            dx = lay.backward(okl.Tensor(g[f"{nm}_{tag}_g"]))
+            assert dx.shape == g[f"{nm}_{tag}_dx"].shape and rel_err(dx.data, g[f"{nm}_{tag}_dx"]) < 1e-7, (nm, tag)
+    with pytest.raises(ValueError):
+        okl.ZeroPaddingLayer((1, 2, 3))
+    with pytest.raises(NotImplementedError):
+        okl.PaddingLayer(1).forward(okl.Tensor(x))
