@@ -645,6 +645,44 @@ class NeuralNetwork:
         for layer, param in zip(self.layers, params):
             layer.set_params(param)
 
+    # ------------------------------------------------------------------ exact checkpoints (not in the reference)
+    def save_checkpoint(self, file_path: str):
+        """``save`` plus the state the reference's file format loses: every layer's ACCUMULATED gradients (the in-layer update
+        rule never resets them, okl.py:39-45, so a run resumed from ``save`` / ``load`` diverges from the uninterrupted one).
+        Values are the device's fp32 numbers widened to float64 - exact - so training resumed from this file continues bit for
+        bit.  The ``params`` entry is what ``save`` writes, so ``load_weights``-style readers can still use the file."""
+        state = []
+        for layer in self.layers:
+            b = getattr(layer, "_bucket", None)
+            if b is None:
+                state.append(None)
+                continue
+            b.materialize()
+            stepped = bool(getattr(b, "_stepped", False))
+            state.append([np.asarray(t.grad).copy() if (stepped or t._grad is not None) else None for t in b.tensors])
+        with open(file_path, 'wb') as f:
+            pickle.dump({"format": "okrolearn-b200-checkpoint-1", "params": [layer.get_params() for layer in self.layers],
+                         "accumulated_gradients": state, "temperature": self.temperature}, f)
+
+    def load_checkpoint(self, file_path: str):
+        with open(file_path, 'rb') as f:
+            ck = pickle.load(f)
+        if not isinstance(ck, dict) or ck.get("format") != "okrolearn-b200-checkpoint-1":
+            raise ValueError("not a checkpoint written by save_checkpoint")
+        if len(ck["params"]) != len(self.layers):
+            raise ValueError(f"checkpoint has {len(ck['params'])} layers, the network {len(self.layers)}")
+        self.temperature = ck["temperature"]
+        for layer, param, acc in zip(self.layers, ck["params"], ck["accumulated_gradients"]):
+            layer.set_params(param)
+            b = getattr(layer, "_bucket", None)
+            if b is None or acc is None:
+                continue
+            b.materialize()
+            for t, g in zip(b.tensors, acc):
+                t.grad = None if g is None else np.asarray(g)
+            if any(g is not None for g in acc):
+                b._stepped = True               # a later `.grad = None` by the user then really clears the accumulator
+
     def set_temperature(self, temperature: float):
         self.temperature = temperature
 

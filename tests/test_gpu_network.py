@@ -317,3 +317,44 @@ def test_conv_relu_mse_regression_train(okl, nd, fuse):
     assert rel_err(ls, ol) < 2e-5
     assert rel_err((conv.filters if nd == 3 else conv.weights).data, on.layers[0].W) < 5e-5
     assert rel_err(conv.biases.data, on.layers[0].b) < 5e-5
+
+
+def test_checkpoint_resume_is_bit_exact(okl):
+    """save_checkpoint / load_checkpoint keep the accumulated gradients, so (1 epoch, checkpoint, fresh network,
+    1 epoch) ends with exactly the parameters of 2 uninterrupted epochs - which ``save`` / ``load`` (the reference's format) cannot."""
+    import os
+    import tempfile
+    rng = np.random.default_rng(44)
+    N, B = 48, 16
+    X = rng.standard_normal((N, 1, 12, 12)).astype(np.float32)
+    T = rng.integers(0, 10, N)
+    g = {"Wc1": rng.standard_normal((4, 1, 3, 3)) * 0.3, "Wd1": rng.standard_normal((100, 16)) * 0.1, "Wd2": rng.standard_normal((16, 10)) * 0.1}
+
+    def run(net, x, t, epochs):
+        return net.train(x, t, epochs=epochs, lr_scheduler=okl.LearningRateScheduler(0.05), optimizer=okl.SGDOptimizer(), batch_size=B,
+                         loss_function=okl.CrossEntropyLoss())
+
+    netA, convA, d1A, d2A = cnn_small(okl, g)
+    np.random.seed(6)
+    run(netA, okl.Tensor(X.copy()), okl.Tensor(T.copy()), 2)
+    ref_w = [convA.filters.data.copy(), convA.biases.data.copy(), d1A.weights.data.copy(), d2A.weights.data.copy(), d2A.biases.data.copy()]
+
+    with tempfile.TemporaryDirectory() as d:
+        for mode in ("checkpoint", "save"):
+            netB, *_ = cnn_small(okl, g)
+            netC, convC, d1C, d2C = cnn_small(okl, g)         # built BEFORE seeding: layer constructors draw from np.random
+            xs, ts = okl.Tensor(X.copy()), okl.Tensor(T.copy())
+            np.random.seed(6)
+            run(netB, xs, ts, 1)
+            path = os.path.join(d, mode + ".pkl")
+            (netB.save_checkpoint if mode == "checkpoint" else netB.save)(path)
+            (netC.load_checkpoint if mode == "checkpoint" else netC.load)(path)
+            run(netC, xs, ts, 1)                      # same (reordered) dataset tensors, NumPy RNG stream continues
+            got = [convC.filters.data, convC.biases.data, d1C.weights.data, d2C.weights.data, d2C.biases.data]
+            if mode == "checkpoint":
+                for a, b in zip(got, ref_w):
+                    assert np.array_equal(a, b)
+            else:                                     # the reference's format drops the accumulators: the resumed run differs
+                assert not np.array_equal(got[2], ref_w[2])
+        with pytest.raises(ValueError):
+            netC.load_checkpoint(os.path.join(d, "save.pkl"))
