@@ -45,8 +45,14 @@ extern "C" int okl_ctx_create(int device, int precision, okl_ctx** out) {
   c->cc = prop.major * 10 + prop.minor;
   c->total_mem = prop.totalGlobalMem;
   if (const char* e = getenv("OKL_PDL")) c->pdl = atoi(e);
-  OKL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  OKL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  // the compute stream carries the critical path: highest priority, so its CTAs are placed before those of the gradient exchange
+  // (comm stream, lowest priority) that runs next to it; graph kernel nodes inherit the priority of the stream they were captured on
+  int prio_lo = 0, prio_hi = 0;
+  OKL_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  const char* pe = getenv("OKL_STREAM_PRIORITY");
+  const bool use_prio = !pe || atoi(pe) != 0;
+  OKL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, use_prio ? prio_hi : 0));
+  OKL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, use_prio ? prio_lo : 0));
   c->lanes[0].stream = c->stream;
   for (int i = 1; i < 3; i++) OKL_CHECK_CUDA(cudaStreamCreateWithFlags(&c->lanes[i].stream, cudaStreamNonBlocking));
   for (int i = 0; i < 3; i++) OKL_CHECK_CUDA(cudaEventCreateWithFlags(&c->lanes[i].ev, cudaEventDisableTiming));
@@ -156,8 +162,10 @@ extern "C" int okl_batch_prefetch(okl_ctx* ctx, int slot, void* x_dst, const voi
   if (s != OKL_OK) return s;
   // flow control: the host may run at most OKL_FLOW_DEPTH batches ahead of the device (an unbounded launch backlog occasionally
   // made step times bimodal; a depth of 1-2 makes the device wait for host wake-ups)
-  const int fi = ctx->flow_next % OKL_FLOW_DEPTH;
-  if (ctx->flow_next >= OKL_FLOW_DEPTH) OKL_CHECK_CUDA(cudaEventSynchronize(ctx->ev_flow[fi]));
+  static int depth = 0;
+  if (depth == 0) { const char* e = getenv("OKL_FLOW_DEPTH"); depth = e ? atoi(e) : OKL_FLOW_DEPTH; if (depth < 1 || depth > OKL_FLOW_DEPTH) depth = OKL_FLOW_DEPTH; }
+  const int fi = ctx->flow_next % depth;
+  if (ctx->flow_next >= (unsigned long long)depth) OKL_CHECK_CUDA(cudaEventSynchronize(ctx->ev_flow[fi]));
   OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_copy_fork, ctx->stream));
   OKL_CHECK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_fork, 0));
   cudaStream_t main_stream = ctx->stream;

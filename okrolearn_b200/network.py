@@ -358,6 +358,41 @@ class NeuralNetwork:
         self.profiler.disable()
         return result
 
+    @staticmethod
+    def _class_indices(targets, num_samples):
+        """int32 device copy of the class targets in their current storage order (okl.py:1392 does ``.astype(int)``), cached on
+        the tensor until its host data is replaced."""
+        ctx = get_ctx()
+        host = targets._host if targets._host is not None else targets.data
+        key = (id(host), targets._dev_ver)
+        cached = getattr(targets, "_cls_dev", None)
+        if cached is not None and cached[0] == key and cached[1].nbytes >= max(num_samples, 1) * 4:
+            return cached[1]
+        buf = _DevBuf(ctx, max(num_samples, 1) * 4)
+        th = np.ascontiguousarray(np.asarray(host).reshape(-1).astype(np.int64))
+        check(lib.okl_h2d_i32(ctx.h, buf.ptr, th.ctypes.data, th.size, _lib.I64))
+        targets._cls_dev = (key, buf)
+        return buf
+
+    def prepare(self, inputs: 'Tensor', targets: 'Tensor', loss_function=None):
+        """Dataset placement ahead of ``train`` (optional; ``train`` does the same lazily on first use): uploads the inputs and
+        the targets (class indices for CrossEntropyLoss) to the device and sizes the per-epoch index buffers, so that a following
+        ``train`` call starts stepping immediately.  With ``stream_inputs`` the dataset stays in page-locked host memory and only
+        the buffers are sized."""
+        ctx = get_ctx()
+        num_samples = inputs.shape[0]
+        self._epoch_pinned(num_samples)
+        idx_dev = getattr(self, "_idx_dev", None)
+        if idx_dev is None or idx_dev.nbytes < max(num_samples, 1) * 4:
+            self._idx_dev = _DevBuf(ctx, max(int(num_samples * 1.5), 1024) * 4)
+        if not self.stream_inputs and getattr(inputs, "_lazy_perm", None) is None:
+            inputs._dptr(NCX)
+            if isinstance(loss_function, CrossEntropyLoss):
+                self._class_indices(targets, num_samples)
+            elif getattr(targets, "_lazy_perm", None) is None:
+                targets._dptr(NCX)
+        ctx.sync()
+
     def _epoch_pinned(self, num_samples):
         """(scalar slot, int32 index buffer) in page-locked host memory, cached on the network and grown on demand."""
         cur = getattr(self, "_pin_epoch", None)
@@ -437,15 +472,16 @@ class NeuralNetwork:
         else:
             x_src = inputs._dptr(NCX)
             if is_ce:
-                t_buf = _DevBuf(ctx, max(num_samples, 1) * 4)
-                th = np.ascontiguousarray(np.asarray(targets._host if targets._host is not None else targets.data).reshape(-1)
-                                          .astype(np.int64))
-                check(lib.okl_h2d_i32(ctx.h, t_buf.ptr, th.ctypes.data, th.size, _lib.I64))
+                t_buf = self._class_indices(targets, num_samples)      # cached on the targets tensor (prepare() fills it ahead)
                 t_src = t_buf.ptr
                 keep.append(t_buf)
             else:
                 t_src = targets._dptr(NCX)
-        idx_dev = _DevBuf(ctx, max(num_samples, 1) * 4)
+        # device index vector of the epoch's permutation: cached on the network and grown on demand (no allocation inside the loop
+        # of repeated train() calls)
+        idx_dev = getattr(self, "_idx_dev", None)
+        if idx_dev is None or idx_dev.nbytes < max(num_samples, 1) * 4:
+            idx_dev = self._idx_dev = _DevBuf(ctx, max(int(num_samples * 1.5), 1024) * 4)
 
         # ---- per-(batch shape, loss) step state: static input buffers + the captured graph
         skey = (batch_size, sample_shape, t_shape, id(loss_function), tuple(id(l) for l in self.layers), fast,
