@@ -50,7 +50,7 @@ extern "C" int okl_ctx_create(int device, int precision, okl_ctx** out) {
   int prio_lo = 0, prio_hi = 0;
   OKL_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   const char* pe = getenv("OKL_STREAM_PRIORITY");
-  const bool use_prio = !pe || atoi(pe) != 0;
+  const bool use_prio = pe && atoi(pe) != 0;          // opt-in: the 2-GPU A/B was within run-to-run noise
   OKL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, use_prio ? prio_hi : 0));
   OKL_CHECK_CUDA(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, use_prio ? prio_lo : 0));
   c->lanes[0].stream = c->stream;
