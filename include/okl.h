@@ -50,7 +50,9 @@ typedef enum { OKL_FP32 = 0, OKL_TF32 = 1, OKL_BF16 = 2 } okl_precision;
 typedef enum { OKL_ACT_NONE = 0, OKL_ACT_RELU = 1, OKL_ACT_SIGMOID = 2, OKL_ACT_TANH = 3, OKL_ACT_SOFTMAX = 4,
                /* okl_act2_fwd / okl_act2_bwd only: */
                OKL_ACT_ELU = 10, OKL_ACT_SELU = 11, OKL_ACT_LEAKY = 12, OKL_ACT_SWISH = 13, OKL_ACT_GELU = 14, OKL_ACT_SOFTSIGN = 15,
-               OKL_ACT_HARDTANH = 16 } okl_act;
+               OKL_ACT_HARDTANH = 16,
+               /* okl_act2_bwd only: dx = g * (1 - y^2) with the tanh OUTPUT y passed as x (RNNLayer, okl.py:1667) */
+               OKL_ACT_TANH_OUT = 17 } okl_act;
 typedef enum { OKL_F32 = 0, OKL_F64 = 1, OKL_I64 = 2, OKL_I32 = 3, OKL_U8 = 4 } okl_dtype;
 typedef enum { OKL_NCX = 0, OKL_NXC = 1 } okl_layout;
 typedef enum { OKL_POOL_MAX = 0, OKL_POOL_AVG = 1 } okl_pool_kind;

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libokl_b200.so")
 OKL_OK, OKL_ERR_INVALID, OKL_ERR_CUDA, OKL_ERR_NCCL, OKL_ERR_OOM, OKL_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 FP32, TF32, BF16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_SOFTMAX = 0, 1, 2, 3, 4
-ACT_ELU, ACT_SELU, ACT_LEAKY, ACT_SWISH, ACT_GELU, ACT_SOFTSIGN, ACT_HARDTANH = 10, 11, 12, 13, 14, 15, 16
+ACT_ELU, ACT_SELU, ACT_LEAKY, ACT_SWISH, ACT_GELU, ACT_SOFTSIGN, ACT_HARDTANH, ACT_TANH_OUT = 10, 11, 12, 13, 14, 15, 16, 17
 F32, F64, I64, I32, U8 = 0, 1, 2, 3, 4
 NCX, NXC = 0, 1
 POOL_MAX, POOL_AVG = 0, 1

@@ -748,6 +748,7 @@ __device__ __forceinline__ float act2_d(int kind, float x, float alpha, float sc
     }
     case OKL_ACT_SOFTSIGN: { const float d = 1.f + fabsf(x); return 1.f / (d * d); }                 // okl.py:330
     case OKL_ACT_HARDTANH: return (x >= -1.f && x <= 1.f) ? 1.f : 0.f;                                // okl.py:2139
+    case OKL_ACT_TANH_OUT: return 1.f - x * x;                // x is the tanh OUTPUT here (RNNLayer, okl.py:1667: 1 - hidden^2)
     default: return 1.f;
   }
 }
@@ -931,7 +932,7 @@ extern "C" int okl_act2_fwd(okl_ctx* ctx, int act, const void* x, void* y, size_
 
 extern "C" int okl_act2_bwd(okl_ctx* ctx, int act, const void* x, const void* g, void* dx, size_t n, float alpha, float scale) {
   OKL_REQUIRE(ctx && (n == 0 || (x && g && dx)), "NULL argument");
-  OKL_REQUIRE(act >= OKL_ACT_ELU && act <= OKL_ACT_HARDTANH, "bad activation %d", act);
+  OKL_REQUIRE(act >= OKL_ACT_ELU && act <= OKL_ACT_TANH_OUT, "bad activation %d", act);
   if (n == 0) return OKL_OK;
   act2_bwd_kernel<<<okl_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>((const float*)x, (const float*)g, (float*)dx, n, act, alpha, scale);
   OKL_LAUNCHED(ctx, "act2_bwd");

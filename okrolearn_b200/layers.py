@@ -1040,6 +1040,75 @@ class SoftmaxActivationLayer:
         pass
 
 
+# ====================================================================================================== recurrent cell
+class RNNLayer:
+    """okl.py:1646-1697: one step of an Elman cell, hidden = tanh(x Wx + h_prev Wh + b).  The whole cell runs on
+    the Dense kernels: two ``okl_dense_fwd`` and two ``okl_dense_bwd`` (each gives a weight gradient AND an input gradient).  As
+    shipped, backward only ACCUMULATES into ``.grad`` - it never updates the weights - which is the bucket update with lr = 0;
+    it returns (dL/dx, dL/dh_prev) and adds them to ``inputs.grad`` / ``prev_hidden.grad``."""
+
+    def __init__(self, input_size, hidden_size):
+        self.input_size, self.hidden_size = input_size, hidden_size
+        self.Wh = Tensor(np.random.randn(hidden_size, hidden_size) * 0.01)
+        self.Wx = Tensor(np.random.randn(input_size, hidden_size) * 0.01)
+        self.b = Tensor(np.zeros((1, hidden_size)))
+        self._bucket = _ParamBucket([self.Wh, self.Wx, self.b])
+
+    def forward(self, inputs: Tensor, prev_hidden=None):
+        inputs = _as_tensor(inputs)
+        if inputs.ndim != 2 or inputs.shape[1] != self.input_size:
+            raise ValueError(f"shapes {inputs.shape} and {(self.input_size, self.hidden_size)} not aligned")
+        B, H = inputs.shape[0], self.hidden_size
+        if prev_hidden is None:
+            prev_hidden = Tensor(np.zeros((B, H)))
+        prev_hidden = _as_tensor(prev_hidden)
+        if prev_hidden.shape != (B, H):
+            raise ValueError(f"shapes {prev_hidden.shape} and {(H, H)} not aligned")
+        ctx = get_ctx()
+        b = self._bucket
+        b.materialize()
+        self.inputs, self.prev_hidden = inputs, prev_hidden
+        zx = Tensor._empty((B, H), np.float64)
+        zh = Tensor._empty((B, H), np.float64)
+        out = Tensor._empty((B, H), np.float64)
+        if B:
+            check(lib.okl_dense_fwd(ctx.h, inputs._dptr(NCX), b.ptr(1), b.ptr(2), zx._ptr_raw(), B, self.input_size, H, ACT_NONE))
+            check(lib.okl_dense_fwd(ctx.h, prev_hidden._dptr(NCX), b.ptr(0), None, zh._ptr_raw(), B, H, H, ACT_NONE))
+            check(lib.okl_binary(ctx.h, 0, zx._ptr_raw(), zh._ptr_raw(), zx._ptr_raw(), zx.size, zh.size))
+            check(lib.okl_act_fwd(ctx.h, ACT_TANH, zx._ptr_raw(), out._ptr_raw(), out.size))
+        self.hidden = out
+        return out
+
+    def backward(self, dL_dh: Tensor, lr: float):
+        dL_dh = _as_tensor(dL_dh)
+        B, H = self.hidden.shape
+        if dL_dh.shape != (B, H):
+            raise ValueError(f"operands could not be broadcast together with shapes {dL_dh.shape} {(B, H)}")
+        ctx = get_ctx()
+        b = self._bucket
+        dz = Tensor._empty((B, H), np.float64)
+        dx = Tensor._empty((B, self.input_size), np.float64)
+        dprev = Tensor._empty((B, H), np.float64)
+        if B:
+            check(lib.okl_act2_bwd(ctx.h, _lib.ACT_TANH_OUT, self.hidden._dptr(NCX), dL_dh._dptr(NCX), dz._ptr_raw(), dz.size, 0.0, 1.0))
+            check(lib.okl_dense_bwd(ctx.h, self.prev_hidden._dptr(NCX), b.ptr(0), dz._ptr_raw(), dprev._ptr_raw(), b.grad_ptr(0), None,
+                                    B, H, H, None))
+            check(lib.okl_dense_bwd(ctx.h, self.inputs._dptr(NCX), b.ptr(1), dz._ptr_raw(), dx._ptr_raw(), b.grad_ptr(1), b.grad_ptr(2),
+                                    B, self.input_size, H, None))
+            b.step(0.0, False)                       # accumulate only (okl.py:1669-1674 never touch the weights)
+        _set_input_grad(self.prev_hidden, dprev)
+        _set_input_grad(self.inputs, dx)
+        return dx, dprev
+
+    def get_params(self):
+        return {'Wh': self.Wh.data, 'Wx': self.Wx.data, 'b': self.b.data}
+
+    def set_params(self, params):
+        self.Wh.data = params['Wh']
+        self.Wx.data = params['Wx']
+        self.b.data = params['b']
+
+
 # ====================================================================================================== batch normalisation
 class BatchNormLayer:
     """okl.py:1145-1222: (B, F) inputs; training mode normalises with the batch mean / population variance and

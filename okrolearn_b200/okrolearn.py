@@ -10,7 +10,8 @@ from .layers import (DenseLayer, Conv1DLayer, Conv2DLayer, Conv3DLayer, ReLUActi
                      PReLUActivationLayer, SwishActivationLayer, GELUActivationLayer, SoftsignActivationLayer,
                      HardTanhActivationLayer, LinearActivationLayer, SoftminActivationLayer, LogSoftmaxActivationLayer,
                      BatchNormLayer, L1RegularizationLayer, L2RegularizationLayer, L3RegularizationLayer, DropoutLayer,
-                     MaxUnpoolingLayer, AverageUnpoolingLayer, PaddingLayer, ZeroPaddingLayer, ReflectionPaddingLayer)
+                     MaxUnpoolingLayer, AverageUnpoolingLayer, PaddingLayer, ZeroPaddingLayer, ReflectionPaddingLayer,
+                     RNNLayer)
 from .losses import CrossEntropyLoss, MSELoss, LossValue  # noqa: F401
 from .schedulers import (LearningRateScheduler, StepLRScheduler, TimeBasedDecayScheduler, ExponentialDecayScheduler,  # noqa: F401
                          LinearDecayScheduler)

@@ -356,6 +356,30 @@ def conv2d_transposed_backward(x, F, g, stride, padding):
     return dF, np.sum(g, axis=(0, 2, 3)).reshape(-1, 1), dX
 
 
+class OracleRNN:
+    """okl.py:1646-1697: hidden = tanh(x Wx + h_prev Wh + b); backward accumulates the three gradients (no update) and returns
+    (dL/dx, dL/dh_prev)."""
+
+    def __init__(self, Wh, Wx, b):
+        self.Wh, self.Wx, self.b = np.array(Wh, dtype=np.float64), np.array(Wx, dtype=np.float64), np.array(b, dtype=np.float64)
+        self.gWh = self.gWx = self.gb = None
+
+    def forward(self, x, h_prev=None):
+        if h_prev is None:
+            h_prev = np.zeros((x.shape[0], self.Wh.shape[0]))
+        self.x, self.h_prev = x, h_prev
+        self.h = np.tanh(x @ self.Wx + h_prev @ self.Wh + self.b)
+        return self.h
+
+    def backward(self, g):
+        dz = g * (1 - self.h ** 2)
+        dWh, dWx, db = self.h_prev.T @ dz, self.x.T @ dz, np.sum(dz, axis=0, keepdims=True)
+        self.gWh = dWh if self.gWh is None else self.gWh + dWh
+        self.gWx = dWx if self.gWx is None else self.gWx + dWx
+        self.gb = db if self.gb is None else self.gb + db
+        return dz @ self.Wx.T, dz @ self.Wh.T
+
+
 class OracleBatchNorm:
     """okl.py:1145-1222 restated line by line (2-D inputs; backward uses the running variance in the chain rule as shipped;
     gamma / beta gradients accumulate forever and the update is applied inside backward)."""

@@ -415,6 +415,31 @@ for nm, cls, refl in (("zero", ref.ZeroPaddingLayer, False), ("reflect", ref.Ref
         up.update({f"{nm}_{tag}_y": y, f"{nm}_{tag}_g": gg_, f"{nm}_{tag}_dx": d})
 save("unpool_pad", x=xu_, src="reference", **up)
 
+# ----------------------------------------------------------------------------- RNNLayer
+rl = ref.RNNLayer(6, 5)
+rWh, rWx, rb = rng.standard_normal((5, 5)) * 0.4, rng.standard_normal((6, 5)) * 0.4, rng.standard_normal((1, 5)) * 0.1
+rl.Wh.data, rl.Wx.data, rl.b.data = rWh.copy(), rWx.copy(), rb.copy()
+orl = O.OracleRNN(rWh, rWx, rb)
+xs_ = [rng.standard_normal((4, 6)) for _ in range(3)]
+gs_ = [rng.standard_normal((4, 5)) for _ in range(3)]
+rn = {}
+hp, hpo = None, None
+for t_, (xv, gv) in enumerate(zip(xs_, gs_)):
+    h_r = rl.forward(T(xv.copy()), None if hp is None else T(hp.copy())).data
+    h_o = orl.forward(xv, hpo)
+    close(h_o, h_r, 1e-13, what=f"rnn forward {t_}")
+    dx_r, dp_r = rl.backward(T(gv.copy()), 0.1)
+    dx_o, dp_o = orl.backward(gv)
+    close(dx_o, dx_r.data, 1e-13, what=f"rnn dx {t_}")
+    close(dp_o, dp_r.data, 1e-13, what=f"rnn dprev {t_}")
+    rn.update({f"x{t_}": xv, f"g{t_}": gv, f"h{t_}": h_r, f"dx{t_}": dx_r.data, f"dprev{t_}": dp_r.data})
+    hp, hpo = h_r, h_o
+close(orl.gWh, rl.Wh.grad, 1e-13, what="rnn Wh.grad")
+close(orl.gWx, rl.Wx.grad, 1e-13, what="rnn Wx.grad")
+close(orl.gb, rl.b.grad, 1e-13, what="rnn b.grad")
+close(rWh, rl.Wh.data, 0, what="rnn weights untouched by backward")
+save("rnn", Wh=rWh, Wx=rWx, b=rb, gWh=np.asarray(rl.Wh.grad), gWx=np.asarray(rl.Wx.grad), gb=np.asarray(rl.b.grad), src="reference", **rn)
+
 # ----------------------------------------------------------------------------- BatchNormLayer
 xb1, xb2 = rng.standard_normal((12, 5)) * 1.5 + 0.3, rng.standard_normal((12, 5)) * 0.7 - 0.2
 gb1, gb2 = rng.standard_normal((12, 5)), rng.standard_normal((12, 5))

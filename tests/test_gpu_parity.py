@@ -510,3 +510,25 @@ def test_unpooling_and_padding_layers(okl):
         okl.ZeroPaddingLayer((1, 2, 3))
     with pytest.raises(NotImplementedError):
         okl.PaddingLayer(1).forward(okl.Tensor(x))
+
+
+def test_rnn_layer(okl):
+    """RNNLayer (one Elman step on the Dense kernels) unrolled over three steps vs the running reference: hidden
+    states, both returned gradients, the accumulated (never applied) weight gradients, and the inputs.grad / prev_hidden.grad side
+    effects."""
+    g = golden("rnn")
+    lay = okl.RNNLayer(6, 5)
+    lay.Wh.data, lay.Wx.data, lay.b.data = g["Wh"].copy(), g["Wx"].copy(), g["b"].copy()
+    hp = None
+    for t in range(3):
+        xt = okl.Tensor(g[f"x{t}"])
+        ht = None if hp is None else okl.Tensor(hp)
+        h = lay.forward(xt, ht)
+        assert h.data.dtype == np.float64 and rel_err(h.data, g[f"h{t}"]) < 2e-6
+        dx, dp = lay.backward(okl.Tensor(g[f"g{t}"]), 0.1)
+        assert rel_err(dx.data, g[f"dx{t}"]) < 2e-5 and rel_err(dp.data, g[f"dprev{t}"]) < 2e-5
+        assert rel_err(np.asarray(xt.grad), g[f"dx{t}"]) < 2e-5
+        hp = g[f"h{t}"]
+    assert rel_err(lay.Wh.grad, g["gWh"]) < 2e-5 and rel_err(lay.Wx.grad, g["gWx"]) < 2e-5 and rel_err(lay.b.grad, g["gb"]) < 2e-5
+    assert rel_err(lay.Wh.data, g["Wh"]) < 1e-7 and rel_err(lay.Wx.data, g["Wx"]) < 1e-7       # backward never updates (okl.py:1669-1674)
+    assert set(lay.get_params()) == {"Wh", "Wx", "b"}
