@@ -208,6 +208,19 @@ int okl_unpool_bwd(okl_ctx* ctx, int kind, const void* g, void* dx, long long NC
 int okl_pad2d(okl_ctx* ctx, const void* x, void* y, long long NC, int H, int W, int top, int bottom, int left, int right, int reflect);
 int okl_crop2d(okl_ctx* ctx, const void* g, void* dx, long long NC, int GH, int GW, int top, int left, int h, int w);
 
+/* LSTMLayer (okl.py:1412-1534): the four gate products are okl_dense_fwd (sigmoid / tanh fused) on
+ * [inputs | prev_hidden] (okl_concat_cols), their gradients four okl_dense_bwd; these entry points are the pointwise parts:
+ * cell = f c_prev + i c~, hidden = o tanh(cell); the gate pre-activation gradients and dL/dc_prev of okl.py:1464-1483, 1510;
+ * dL/dh_prev = the hidden-state columns of the four input gradients summed in the reference's order (okl.py:1506-1509). */
+int okl_concat_cols(okl_ctx* ctx, const void* a, const void* b, void* out, long long rows, int ca, int cb);
+int okl_lstm_pointwise_fwd(okl_ctx* ctx, const void* f, const void* i, const void* c_cand, const void* o, const void* c_prev, void* cell,
+                           void* hidden, size_t n);
+int okl_lstm_pointwise_bwd(okl_ctx* ctx, const void* f, const void* i, const void* c_cand, const void* o, const void* c_prev,
+                           const void* cell, const void* dh, const void* dc, void* dzf, void* dzi, void* dzc, void* dzo, void* dc_prev,
+                           size_t n);
+int okl_sum4_cols(okl_ctx* ctx, const void* a0, const void* a1, const void* a2, const void* a3, void* out, long long rows, int ld, int off,
+                  int cols);
+
 /* ------------------------------------------------------------------ BatchNormLayer (okl.py:1145-1222), (B, F) inputs
  * fwd: batch mean / population variance over axis 0 (training) or the running statistics; running = momentum * batch +
  * (1 - momentum) * running; y = gamma (x - mean) / sqrt(max(var, eps) + eps) + beta, nan_to_num.  *_mean_var are 2F floats

@@ -69,6 +69,10 @@ SIGNATURES = {
     "okl_unpool_bwd": (_i, [_vp, _i, _vp, _vp, _ll, _i, _i, _i, _i]),
     "okl_pad2d": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i]),
     "okl_crop2d": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i]),
+    "okl_concat_cols": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i]),
+    "okl_lstm_pointwise_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),
+    "okl_lstm_pointwise_bwd": (_i, [_vp] + [_vp] * 13 + [_sz]),
+    "okl_sum4_cols": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i]),
     "okl_bn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i]),
     "okl_bn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f]),
     "okl_unfold_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i]),

@@ -807,6 +807,96 @@ __global__ void rowwise_kernel(int kind, const float* __restrict__ a, const floa
 }
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------ LSTM cell pointwise parts (okl.py:1412-1534)
+namespace {
+// out[r, :] = [a[r, :ca] | b[r, :cb]]   (np.concatenate((inputs, prev_hidden), axis=1), okl.py:1452)
+__global__ void concat_cols_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int ca, int cb, size_t total) {
+  const int cw = ca + cb;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / cw; const int c = (int)(i - r * cw);
+    out[i] = c < ca ? a[r * ca + c] : b[r * cb + (c - ca)];
+  }
+}
+// cell = f * c_prev + i * c~ ; hidden = o * tanh(cell)   (okl.py:1456-1458)
+__global__ void lstm_fwd_kernel(const float* __restrict__ f, const float* __restrict__ ig, const float* __restrict__ cc, const float* __restrict__ o,
+                                const float* __restrict__ cprev, float* __restrict__ cell, float* __restrict__ hidden, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float c = f[i] * cprev[i] + ig[i] * cc[i];
+    cell[i] = c;
+    hidden[i] = o[i] * tanhf(c);
+  }
+}
+// gate pre-activation gradients and dL/dc_prev exactly as okl.py:1464-1483, 1510 write them
+__global__ void lstm_bwd_kernel(const float* __restrict__ f, const float* __restrict__ ig, const float* __restrict__ cc, const float* __restrict__ o,
+                                const float* __restrict__ cprev, const float* __restrict__ cell, const float* __restrict__ dh,
+                                const float* __restrict__ dc, float* __restrict__ dzf, float* __restrict__ dzi, float* __restrict__ dzc,
+                                float* __restrict__ dzo, float* __restrict__ dcprev, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float th = tanhf(cell[i]);
+    const float d_o = dh[i] * th;
+    const float dcell = dc[i] + dh[i] * o[i] * (1.f - th * th);
+    dzf[i] = dcell * cprev[i] * f[i] * (1.f - f[i]);
+    dzi[i] = dcell * cc[i] * ig[i] * (1.f - ig[i]);
+    dzc[i] = dcell * ig[i] * (1.f - cc[i] * cc[i]);
+    dzo[i] = d_o * o[i] * (1.f - o[i]);
+    dcprev[i] = dcell * f[i];
+  }
+}
+// out[r, c] = a0[r, off + c] + a1[...] + a2[...] + a3[...] for c < cols  (dL/dh_prev: the hidden-state columns of the four dX, okl.py:1506-1509)
+__global__ void sum4_cols_kernel(const float* __restrict__ a0, const float* __restrict__ a1, const float* __restrict__ a2, const float* __restrict__ a3,
+                                 float* __restrict__ out, int ld, int off, int cols, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / cols; const int c = (int)(i - r * cols);
+    const size_t j = r * ld + off + c;
+    out[i] = ((a0[j] + a1[j]) + a2[j]) + a3[j];
+  }
+}
+}  // namespace
+
+extern "C" int okl_concat_cols(okl_ctx* ctx, const void* a, const void* b, void* out, long long rows, int ca, int cb) {
+  OKL_REQUIRE(ctx && rows >= 0 && ca >= 0 && cb >= 0, "bad concat arguments");
+  const size_t total = (size_t)rows * (ca + cb);
+  if (total == 0) return OKL_OK;
+  OKL_REQUIRE(out && (ca == 0 || a) && (cb == 0 || b), "NULL argument");
+  concat_cols_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)a, (const float*)b, (float*)out, ca, cb, total);
+  OKL_LAUNCHED(ctx, "concat_cols");
+  return OKL_OK;
+}
+
+extern "C" int okl_lstm_pointwise_fwd(okl_ctx* ctx, const void* f, const void* i, const void* c_cand, const void* o, const void* c_prev,
+                                      void* cell, void* hidden, size_t n) {
+  OKL_REQUIRE(ctx && (n == 0 || (f && i && c_cand && o && c_prev && cell && hidden)), "NULL argument");
+  if (n == 0) return OKL_OK;
+  lstm_fwd_kernel<<<okl_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>((const float*)f, (const float*)i, (const float*)c_cand, (const float*)o,
+                                                                    (const float*)c_prev, (float*)cell, (float*)hidden, n);
+  OKL_LAUNCHED(ctx, "lstm_fwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_lstm_pointwise_bwd(okl_ctx* ctx, const void* f, const void* i, const void* c_cand, const void* o, const void* c_prev,
+                                      const void* cell, const void* dh, const void* dc, void* dzf, void* dzi, void* dzc, void* dzo,
+                                      void* dc_prev, size_t n) {
+  OKL_REQUIRE(ctx && (n == 0 || (f && i && c_cand && o && c_prev && cell && dh && dc && dzf && dzi && dzc && dzo && dc_prev)), "NULL argument");
+  if (n == 0) return OKL_OK;
+  lstm_bwd_kernel<<<okl_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>((const float*)f, (const float*)i, (const float*)c_cand, (const float*)o,
+                                                                    (const float*)c_prev, (const float*)cell, (const float*)dh, (const float*)dc,
+                                                                    (float*)dzf, (float*)dzi, (float*)dzc, (float*)dzo, (float*)dc_prev, n);
+  OKL_LAUNCHED(ctx, "lstm_bwd");
+  return OKL_OK;
+}
+
+extern "C" int okl_sum4_cols(okl_ctx* ctx, const void* a0, const void* a1, const void* a2, const void* a3, void* out, long long rows, int ld,
+                             int off, int cols) {
+  OKL_REQUIRE(ctx && rows >= 0 && ld >= 1 && off >= 0 && cols >= 0 && off + cols <= ld, "bad sum4 arguments");
+  const size_t total = (size_t)rows * cols;
+  if (total == 0) return OKL_OK;
+  OKL_REQUIRE(a0 && a1 && a2 && a3 && out, "NULL argument");
+  sum4_cols_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)a0, (const float*)a1, (const float*)a2, (const float*)a3,
+                                                                        (float*)out, ld, off, cols, total);
+  OKL_LAUNCHED(ctx, "sum4_cols");
+  return OKL_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ BatchNorm (okl.py:1145-1222)
 // (B, F) inputs, statistics over the batch axis.  One block per 32 features, 32 row lanes: column sums are formed in a fixed order.
 namespace {

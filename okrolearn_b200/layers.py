@@ -1109,6 +1109,88 @@ class RNNLayer:
         self.b.data = params['b']
 
 
+class LSTMLayer:
+    """okl.py:1412-1534: one LSTM step.  Gates f, i, o = sigmoid, c~ = tanh of [x | h_prev] W_g + b_g - four
+    ``okl_dense_fwd`` with the activation fused; cell / hidden by one pointwise kernel.  backward(dL_dh, dL_dc, lr): the gate
+    gradients by one pointwise kernel, then four ``okl_dense_bwd`` (weight, bias and [x | h] gradients); as shipped it ACCUMULATES
+    the eight parameter gradients without ever applying them (bucket update with lr = 0) and returns (dL/dh_prev, dL/dc_prev)
+    only, adding them to ``prev_hidden.grad`` / ``prev_cell.grad``."""
+
+    def __init__(self, input_size, hidden_size):
+        self.input_size, self.hidden_size = input_size, hidden_size
+        shape = (input_size + hidden_size, hidden_size)
+        self.Wf, self.Wi, self.Wc, self.Wo = (Tensor(np.random.randn(*shape) * 0.01) for _ in range(4))
+        self.bf, self.bi, self.bc, self.bo = (Tensor(np.zeros((1, hidden_size))) for _ in range(4))
+        self._bucket = _ParamBucket([self.Wf, self.Wi, self.Wc, self.Wo, self.bf, self.bi, self.bc, self.bo])
+
+    def sigmoid(self, x: Tensor):
+        x = _as_tensor(x)
+        out = Tensor._empty(x.shape, _float_dtype(x))
+        check(lib.okl_act_fwd(get_ctx().h, ACT_SIGMOID, x._dptr(NCX), out._ptr_raw(), x.size))
+        return out
+
+    def forward(self, inputs: Tensor, prev_hidden=None, prev_cell=None):
+        inputs = _as_tensor(inputs)
+        I, H = self.input_size, self.hidden_size
+        if inputs.ndim != 2 or inputs.shape[1] != I:
+            raise ValueError(f"shapes {(inputs.shape[0], inputs.shape[-1] + H)} and {(I + H, H)} not aligned")
+        B = inputs.shape[0]
+        prev_hidden = Tensor(np.zeros((B, H))) if prev_hidden is None else _as_tensor(prev_hidden)
+        prev_cell = Tensor(np.zeros((B, H))) if prev_cell is None else _as_tensor(prev_cell)
+        if prev_hidden.shape != (B, H) or prev_cell.shape != (B, H):
+            raise ValueError(f"operands could not be broadcast together with shapes {prev_hidden.shape} {prev_cell.shape} {(B, H)}")
+        ctx = get_ctx()
+        b = self._bucket
+        b.materialize()
+        self.inputs, self.prev_hidden, self.prev_cell = inputs, prev_hidden, prev_cell
+        comb = Tensor._empty((B, I + H), np.float64)
+        gates = [Tensor._empty((B, H), np.float64) for _ in range(4)]
+        cell, hidden = Tensor._empty((B, H), np.float64), Tensor._empty((B, H), np.float64)
+        if B:
+            check(lib.okl_concat_cols(ctx.h, inputs._dptr(NCX), prev_hidden._dptr(NCX), comb._ptr_raw(), B, I, H))
+            for gi, act in enumerate((ACT_SIGMOID, ACT_SIGMOID, ACT_TANH, ACT_SIGMOID)):            # f, i, c~, o
+                check(lib.okl_dense_fwd(ctx.h, comb._ptr_raw(), b.ptr(gi), b.ptr(4 + gi), gates[gi]._ptr_raw(), B, I + H, H, act))
+            check(lib.okl_lstm_pointwise_fwd(ctx.h, gates[0]._ptr_raw(), gates[1]._ptr_raw(), gates[2]._ptr_raw(), gates[3]._ptr_raw(),
+                                             prev_cell._dptr(NCX), cell._ptr_raw(), hidden._ptr_raw(), B * H))
+        self._comb = comb
+        self.f, self.i, self.c_candidate, self.o = gates
+        self.cell, self.hidden = cell, hidden
+        return hidden, cell
+
+    def backward(self, dL_dh: Tensor, dL_dc: Tensor, lr: float):
+        dL_dh, dL_dc = _as_tensor(dL_dh), _as_tensor(dL_dc)
+        I, H = self.input_size, self.hidden_size
+        B = self.hidden.shape[0]
+        if dL_dh.shape != (B, H) or dL_dc.shape != (B, H):
+            raise ValueError(f"operands could not be broadcast together with shapes {dL_dh.shape} {dL_dc.shape} {(B, H)}")
+        ctx = get_ctx()
+        b = self._bucket
+        dz = [Tensor._empty((B, H), np.float64) for _ in range(4)]
+        dcomb = [Tensor._empty((B, I + H), np.float64) for _ in range(4)]
+        dprev_c, dprev_h = Tensor._empty((B, H), np.float64), Tensor._empty((B, H), np.float64)
+        if B:
+            check(lib.okl_lstm_pointwise_bwd(ctx.h, self.f._ptr_raw(), self.i._ptr_raw(), self.c_candidate._ptr_raw(), self.o._ptr_raw(),
+                                             self.prev_cell._dptr(NCX), self.cell._ptr_raw(), dL_dh._dptr(NCX), dL_dc._dptr(NCX),
+                                             dz[0]._ptr_raw(), dz[1]._ptr_raw(), dz[2]._ptr_raw(), dz[3]._ptr_raw(), dprev_c._ptr_raw(), B * H))
+            for gi in range(4):
+                check(lib.okl_dense_bwd(ctx.h, self._comb._ptr_raw(), b.ptr(gi), dz[gi]._ptr_raw(), dcomb[gi]._ptr_raw(), b.grad_ptr(gi),
+                                        b.grad_ptr(4 + gi), B, I + H, H, None))
+            check(lib.okl_sum4_cols(ctx.h, dcomb[0]._ptr_raw(), dcomb[1]._ptr_raw(), dcomb[2]._ptr_raw(), dcomb[3]._ptr_raw(),
+                                    dprev_h._ptr_raw(), B, I + H, I, H))
+            b.step(0.0, False)                       # accumulate only: okl.py:1493-1504 never touch the weights
+        _set_input_grad(self.prev_hidden, dprev_h)
+        _set_input_grad(self.prev_cell, dprev_c)
+        return dprev_h, dprev_c
+
+    def get_params(self):
+        return {'Wf': self.Wf.data, 'Wi': self.Wi.data, 'Wc': self.Wc.data, 'Wo': self.Wo.data,
+                'bf': self.bf.data, 'bi': self.bi.data, 'bc': self.bc.data, 'bo': self.bo.data}
+
+    def set_params(self, params):
+        for k in ('Wf', 'Wi', 'Wc', 'Wo', 'bf', 'bi', 'bc', 'bo'):
+            getattr(self, k).data = params[k]
+
+
 # ====================================================================================================== batch normalisation
 class BatchNormLayer:
     """okl.py:1145-1222: (B, F) inputs; training mode normalises with the batch mean / population variance and

@@ -380,6 +380,42 @@ class OracleRNN:
         return dz @ self.Wx.T, dz @ self.Wh.T
 
 
+class OracleLSTM:
+    """okl.py:1412-1534 line by line: gates on [x | h_prev]; backward accumulates the eight gradients (no update) and returns
+    (dL/dh_prev, dL/dc_prev)."""
+
+    def __init__(self, W, b, input_size):
+        self.W = [np.array(w, dtype=np.float64) for w in W]          # Wf, Wi, Wc, Wo
+        self.b = [np.array(v, dtype=np.float64) for v in b]          # bf, bi, bc, bo
+        self.I = input_size
+        self.gW, self.gb = [None] * 4, [None] * 4
+
+    def forward(self, x, h_prev=None, c_prev=None):
+        H = self.W[0].shape[1]
+        h_prev = np.zeros((x.shape[0], H)) if h_prev is None else h_prev
+        c_prev = np.zeros((x.shape[0], H)) if c_prev is None else c_prev
+        sg = lambda z: 1 / (1 + np.exp(-z))                            # noqa: E731
+        self.comb, self.c_prev = np.concatenate((x, h_prev), axis=1), c_prev
+        self.f, self.i = sg(self.comb @ self.W[0] + self.b[0]), sg(self.comb @ self.W[1] + self.b[1])
+        self.cc = np.tanh(self.comb @ self.W[2] + self.b[2])
+        self.cell = self.f * c_prev + self.i * self.cc
+        self.o = sg(self.comb @ self.W[3] + self.b[3])
+        self.h = self.o * np.tanh(self.cell)
+        return self.h, self.cell
+
+    def backward(self, dh, dc):
+        d_o = dh * np.tanh(self.cell)
+        dcell = dc + dh * self.o * (1 - np.tanh(self.cell) ** 2)
+        dz = [dcell * self.c_prev * self.f * (1 - self.f), dcell * self.cc * self.i * (1 - self.i), dcell * self.i * (1 - self.cc ** 2),
+              d_o * self.o * (1 - self.o)]
+        for k in range(4):
+            dW, db = self.comb.T @ dz[k], np.sum(dz[k], axis=0, keepdims=True)
+            self.gW[k] = dW if self.gW[k] is None else self.gW[k] + dW
+            self.gb[k] = db if self.gb[k] is None else self.gb[k] + db
+        dprev_h = sum(dz[k] @ self.W[k][self.I:].T for k in range(4))
+        return dprev_h, dcell * self.f
+
+
 class OracleBatchNorm:
     """okl.py:1145-1222 restated line by line (2-D inputs; backward uses the running variance in the chain rule as shipped;
     gamma / beta gradients accumulate forever and the update is applied inside backward)."""

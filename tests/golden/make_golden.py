@@ -440,6 +440,38 @@ close(orl.gb, rl.b.grad, 1e-13, what="rnn b.grad")
 close(rWh, rl.Wh.data, 0, what="rnn weights untouched by backward")
 save("rnn", Wh=rWh, Wx=rWx, b=rb, gWh=np.asarray(rl.Wh.grad), gWx=np.asarray(rl.Wx.grad), gb=np.asarray(rl.b.grad), src="reference", **rn)
 
+# ----------------------------------------------------------------------------- LSTMLayer
+ll = ref.LSTMLayer(6, 5)
+lW = [rng.standard_normal((11, 5)) * 0.4 for _ in range(4)]
+lb = [rng.standard_normal((1, 5)) * 0.1 for _ in range(4)]
+for nm_, wv in zip(("Wf", "Wi", "Wc", "Wo"), lW):
+    getattr(ll, nm_).data = wv.copy()
+for nm_, bv in zip(("bf", "bi", "bc", "bo"), lb):
+    getattr(ll, nm_).data = bv.copy()
+ol = O.OracleLSTM(lW, lb, 6)
+ls_ = {}
+hp = cp = hpo = cpo = None
+for t_ in range(3):
+    xv, gh, gc = rng.standard_normal((4, 6)), rng.standard_normal((4, 5)), rng.standard_normal((4, 5))
+    h_r, c_r = ll.forward(T(xv.copy()), None if hp is None else T(hp.copy()), None if cp is None else T(cp.copy()))
+    h_o, c_o = ol.forward(xv, hpo, cpo)
+    close(h_o, h_r.data, 1e-13, what=f"lstm hidden {t_}")
+    close(c_o, c_r.data, 1e-13, what=f"lstm cell {t_}")
+    dh_r, dc_r = ll.backward(T(gh.copy()), T(gc.copy()), 0.1)
+    dh_o, dc_o = ol.backward(gh, gc)
+    close(dh_o, dh_r.data, 1e-13, what=f"lstm dprev_h {t_}")
+    close(dc_o, dc_r.data, 1e-13, what=f"lstm dprev_c {t_}")
+    ls_.update({f"x{t_}": xv, f"gh{t_}": gh, f"gc{t_}": gc, f"h{t_}": h_r.data, f"c{t_}": c_r.data, f"dh{t_}": dh_r.data, f"dc{t_}": dc_r.data})
+    hp, cp, hpo, cpo = h_r.data, c_r.data, h_o, c_o
+for k_, nm_ in enumerate(("Wf", "Wi", "Wc", "Wo")):
+    close(ol.gW[k_], getattr(ll, nm_).grad, 1e-13, what="lstm " + nm_ + ".grad")
+    close(lW[k_], getattr(ll, nm_).data, 0, what="lstm weights untouched")
+    ls_["g" + nm_] = np.asarray(getattr(ll, nm_).grad)
+for k_, nm_ in enumerate(("bf", "bi", "bc", "bo")):
+    close(ol.gb[k_], getattr(ll, nm_).grad, 1e-13, what="lstm " + nm_ + ".grad")
+    ls_["g" + nm_] = np.asarray(getattr(ll, nm_).grad)
+save("lstm", Wf=lW[0], Wi=lW[1], Wc=lW[2], Wo=lW[3], bf=lb[0], bi=lb[1], bc=lb[2], bo=lb[3], src="reference", **ls_)
+
 # ----------------------------------------------------------------------------- BatchNormLayer
 xb1, xb2 = rng.standard_normal((12, 5)) * 1.5 + 0.3, rng.standard_normal((12, 5)) * 0.7 - 0.2
 gb1, gb2 = rng.standard_normal((12, 5)), rng.standard_normal((12, 5))

@@ -532,3 +532,23 @@ def test_rnn_layer(okl):
     assert rel_err(lay.Wh.grad, g["gWh"]) < 2e-5 and rel_err(lay.Wx.grad, g["gWx"]) < 2e-5 and rel_err(lay.b.grad, g["gb"]) < 2e-5
     assert rel_err(lay.Wh.data, g["Wh"]) < 1e-7 and rel_err(lay.Wx.data, g["Wx"]) < 1e-7       # backward never updates (okl.py:1669-1674)
     assert set(lay.get_params()) == {"Wh", "Wx", "b"}
+
+
+def test_lstm_layer(okl):
+    """LSTMLayer (gates on the Dense kernels + pointwise cell kernels) unrolled over three steps vs the running
+    reference: hidden / cell states, the two returned gradients, the eight accumulated (never applied) parameter gradients."""
+    g = golden("lstm")
+    lay = okl.LSTMLayer(6, 5)
+    for nm in ("Wf", "Wi", "Wc", "Wo", "bf", "bi", "bc", "bo"):
+        getattr(lay, nm).data = g[nm].copy()
+    hp = cp = None
+    for t in range(3):
+        h, c = lay.forward(okl.Tensor(g[f"x{t}"]), None if hp is None else okl.Tensor(hp), None if cp is None else okl.Tensor(cp))
+        assert rel_err(h.data, g[f"h{t}"]) < 3e-6 and rel_err(c.data, g[f"c{t}"]) < 3e-6
+        dh, dc = lay.backward(okl.Tensor(g[f"gh{t}"]), okl.Tensor(g[f"gc{t}"]), 0.1)
+        assert rel_err(dh.data, g[f"dh{t}"]) < 3e-5 and rel_err(dc.data, g[f"dc{t}"]) < 3e-5
+        hp, cp = g[f"h{t}"], g[f"c{t}"]
+    for nm in ("Wf", "Wi", "Wc", "Wo", "bf", "bi", "bc", "bo"):
+        assert rel_err(np.asarray(getattr(lay, nm).grad).reshape(g["g" + nm].shape), g["g" + nm]) < 3e-5, nm
+        assert rel_err(getattr(lay, nm).data, g[nm]) < 1e-7, nm                 # backward never updates the weights
+    assert set(lay.get_params()) == {"Wf", "Wi", "Wc", "Wo", "bf", "bi", "bc", "bo"}
