@@ -221,6 +221,17 @@ int okl_lstm_pointwise_bwd(okl_ctx* ctx, const void* f, const void* i, const voi
 int okl_sum4_cols(okl_ctx* ctx, const void* a0, const void* a1, const void* a2, const void* a3, void* out, long long rows, int ld, int off,
                   int cols);
 
+/* GRULayer (okl.py:1537-1643): gates z, r on [x | h_prev], candidate on [x | r h_prev] (okl_dense_fwd, activations fused); these
+ * are its pointwise parts.  okl_gru_pointwise mode 0: hidden = (1 - z) h_prev + z h~; mode 1: out0 = dh z (1 - h~^2) (candidate
+ * pre-activation gradient), out1 = dh (h~ - h_prev) z (1 - z) (update-gate one).  okl_gru_dr: the reset-gate pre-activation
+ * gradient from the hidden columns of the candidate's [x | r h] gradient.  okl_gru_dinputs: dL/dx and dL/dh_prev assembled from the
+ * three [x | h] gradients in the reference's order of additions (okl.py:1597-1605). */
+int okl_gru_pointwise(okl_ctx* ctx, int mode, const void* z, const void* h_cand, const void* h_prev, const void* dh, void* out0, void* out1,
+                      size_t n);
+int okl_gru_dr(okl_ctx* ctx, const void* dcomb_h, const void* h_prev, const void* r, void* dzr, long long rows, int I, int H);
+int okl_gru_dinputs(okl_ctx* ctx, const void* dcomb_z, const void* dcomb_r, const void* dcomb_h, const void* r, const void* z, const void* dh,
+                    void* dx, void* dprev, long long rows, int I, int H);
+
 /* ------------------------------------------------------------------ BatchNormLayer (okl.py:1145-1222), (B, F) inputs
  * fwd: batch mean / population variance over axis 0 (training) or the running statistics; running = momentum * batch +
  * (1 - momentum) * running; y = gamma (x - mean) / sqrt(max(var, eps) + eps) + beta, nan_to_num.  *_mean_var are 2F floats

@@ -73,6 +73,9 @@ SIGNATURES = {
     "okl_lstm_pointwise_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),
     "okl_lstm_pointwise_bwd": (_i, [_vp] + [_vp] * 13 + [_sz]),
     "okl_sum4_cols": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i]),
+    "okl_gru_pointwise": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),
+    "okl_gru_dr": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i]),
+    "okl_gru_dinputs": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i]),
     "okl_bn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _i]),
     "okl_bn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f]),
     "okl_unfold_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i]),

@@ -853,6 +853,78 @@ __global__ void sum4_cols_kernel(const float* __restrict__ a0, const float* __re
 }
 }  // namespace
 
+namespace {
+// ---- GRU cell pointwise parts (okl.py:1537-1643)
+// mode 0: hidden = (1 - z) h_prev + z h~                                                     (okl.py:1569)
+// mode 1: dzh = dh z (1 - h~^2) -> out0 ; dzz = dh (h~ - h_prev) z (1 - z) -> out1            (okl.py:1574-1575, 1579, 1583)
+__global__ void gru_pointwise_kernel(int mode, const float* __restrict__ z, const float* __restrict__ hc, const float* __restrict__ hprev,
+                                     const float* __restrict__ dh, float* __restrict__ out0, float* __restrict__ out1, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (mode == 0) out0[i] = (1.f - z[i]) * hprev[i] + z[i] * hc[i];
+    else {
+      out0[i] = dh[i] * z[i] * (1.f - hc[i] * hc[i]);
+      out1[i] = dh[i] * (hc[i] - hprev[i]) * z[i] * (1.f - z[i]);
+    }
+  }
+}
+// dzr = dcomb_h[:, I:] * h_prev * r (1 - r)                                                   (okl.py:1576-1577, 1581)
+__global__ void gru_dr_kernel(const float* __restrict__ dcomb_h, const float* __restrict__ hprev, const float* __restrict__ r, float* __restrict__ dzr,
+                              int I, int H, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / H; const int c = (int)(i - row * H);
+    dzr[i] = dcomb_h[row * (I + H) + I + c] * hprev[i] * r[i] * (1.f - r[i]);
+  }
+}
+// dL/dh_prev and dL/dx from the three [x | h] gradients, in the reference's order of additions (okl.py:1597-1605)
+__global__ void gru_dinputs_kernel(const float* __restrict__ dcz, const float* __restrict__ dcr, const float* __restrict__ dch,
+                                   const float* __restrict__ r, const float* __restrict__ z, const float* __restrict__ dh, float* __restrict__ dx,
+                                   float* __restrict__ dprev, int I, int H, size_t rows) {
+  const int cw = I + H;
+  const size_t total = rows * cw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / cw; const int c = (int)(i - row * cw);
+    if (c < I) dx[row * I + c] = (dcz[i] + dcr[i]) + dch[i];
+    else {
+      const size_t j = row * H + (c - I);
+      dprev[j] = ((dcz[i] + dcr[i]) + dch[i] * r[j]) + dh[j] * (1.f - z[j]);
+    }
+  }
+}
+}  // namespace
+
+extern "C" int okl_gru_pointwise(okl_ctx* ctx, int mode, const void* z, const void* h_cand, const void* h_prev, const void* dh, void* out0,
+                                 void* out1, size_t n) {
+  OKL_REQUIRE(ctx && (mode == 0 || mode == 1), "bad gru_pointwise mode");
+  if (n == 0) return OKL_OK;
+  OKL_REQUIRE(z && h_cand && h_prev && out0 && (mode == 0 || (dh && out1)), "NULL argument");
+  gru_pointwise_kernel<<<okl_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>(mode, (const float*)z, (const float*)h_cand, (const float*)h_prev,
+                                                                         (const float*)dh, (float*)out0, (float*)out1, n);
+  OKL_LAUNCHED(ctx, "gru_pointwise");
+  return OKL_OK;
+}
+
+extern "C" int okl_gru_dr(okl_ctx* ctx, const void* dcomb_h, const void* h_prev, const void* r, void* dzr, long long rows, int I, int H) {
+  OKL_REQUIRE(ctx && rows >= 0 && I >= 0 && H >= 1, "bad gru_dr arguments");
+  const size_t n = (size_t)rows * H;
+  if (n == 0) return OKL_OK;
+  OKL_REQUIRE(dcomb_h && h_prev && r && dzr, "NULL argument");
+  gru_dr_kernel<<<okl_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>((const float*)dcomb_h, (const float*)h_prev, (const float*)r, (float*)dzr, I, H, n);
+  OKL_LAUNCHED(ctx, "gru_dr");
+  return OKL_OK;
+}
+
+extern "C" int okl_gru_dinputs(okl_ctx* ctx, const void* dcomb_z, const void* dcomb_r, const void* dcomb_h, const void* r, const void* z,
+                               const void* dh, void* dx, void* dprev, long long rows, int I, int H) {
+  OKL_REQUIRE(ctx && rows >= 0 && I >= 1 && H >= 1, "bad gru_dinputs arguments");
+  if (rows == 0) return OKL_OK;
+  OKL_REQUIRE(dcomb_z && dcomb_r && dcomb_h && r && z && dh && dx && dprev, "NULL argument");
+  gru_dinputs_kernel<<<okl_grid_1d(ctx, (size_t)rows * (I + H), 256), 256, 0, ctx->stream>>>(
+      (const float*)dcomb_z, (const float*)dcomb_r, (const float*)dcomb_h, (const float*)r, (const float*)z, (const float*)dh, (float*)dx,
+      (float*)dprev, I, H, (size_t)rows);
+  OKL_LAUNCHED(ctx, "gru_dinputs");
+  return OKL_OK;
+}
+
 extern "C" int okl_concat_cols(okl_ctx* ctx, const void* a, const void* b, void* out, long long rows, int ca, int cb) {
   OKL_REQUIRE(ctx && rows >= 0 && ca >= 0 && cb >= 0, "bad concat arguments");
   const size_t total = (size_t)rows * (ca + cb);

@@ -1191,6 +1191,84 @@ class LSTMLayer:
             getattr(self, k).data = params[k]
 
 
+class GRULayer:
+    """okl.py:1537-1643: one GRU step.  z, r = sigmoid([x | h_prev] W + b), h~ = tanh([x | r h_prev] Wh + bh),
+    hidden = (1 - z) h_prev + z h~.  Three ``okl_dense_fwd`` (activations fused) and three ``okl_dense_bwd`` plus pointwise
+    kernels; backward accumulates the six parameter gradients without applying them (as shipped) and returns (dL/dx, dL/dh_prev)."""
+
+    def __init__(self, input_size, hidden_size):
+        self.input_size, self.hidden_size = input_size, hidden_size
+        shape = (input_size + hidden_size, hidden_size)
+        self.Wz, self.Wr, self.Wh = (Tensor(np.random.randn(*shape) * 0.01) for _ in range(3))
+        self.bz, self.br, self.bh = (Tensor(np.zeros((1, hidden_size))) for _ in range(3))
+        self._bucket = _ParamBucket([self.Wz, self.Wr, self.Wh, self.bz, self.br, self.bh])
+
+    sigmoid = LSTMLayer.sigmoid
+
+    def forward(self, inputs: Tensor, prev_hidden=None):
+        inputs = _as_tensor(inputs)
+        I, H = self.input_size, self.hidden_size
+        if inputs.ndim != 2 or inputs.shape[1] != I:
+            raise ValueError(f"shapes {(inputs.shape[0], inputs.shape[-1] + H)} and {(I + H, H)} not aligned")
+        B = inputs.shape[0]
+        prev_hidden = Tensor(np.zeros((B, H))) if prev_hidden is None else _as_tensor(prev_hidden)
+        if prev_hidden.shape != (B, H):
+            raise ValueError(f"operands could not be broadcast together with shapes {prev_hidden.shape} {(B, H)}")
+        ctx = get_ctx()
+        b = self._bucket
+        b.materialize()
+        self.inputs, self.prev_hidden = inputs, prev_hidden
+        comb, comb2 = Tensor._empty((B, I + H), np.float64), Tensor._empty((B, I + H), np.float64)
+        z, r, rh, hc, hidden = (Tensor._empty((B, H), np.float64) for _ in range(5))
+        if B:
+            xp, hp = inputs._dptr(NCX), prev_hidden._dptr(NCX)
+            check(lib.okl_concat_cols(ctx.h, xp, hp, comb._ptr_raw(), B, I, H))
+            check(lib.okl_dense_fwd(ctx.h, comb._ptr_raw(), b.ptr(0), b.ptr(3), z._ptr_raw(), B, I + H, H, ACT_SIGMOID))
+            check(lib.okl_dense_fwd(ctx.h, comb._ptr_raw(), b.ptr(1), b.ptr(4), r._ptr_raw(), B, I + H, H, ACT_SIGMOID))
+            check(lib.okl_binary(ctx.h, 1, r._ptr_raw(), hp, rh._ptr_raw(), B * H, B * H))
+            check(lib.okl_concat_cols(ctx.h, xp, rh._ptr_raw(), comb2._ptr_raw(), B, I, H))
+            check(lib.okl_dense_fwd(ctx.h, comb2._ptr_raw(), b.ptr(2), b.ptr(5), hc._ptr_raw(), B, I + H, H, ACT_TANH))
+            check(lib.okl_gru_pointwise(ctx.h, 0, z._ptr_raw(), hc._ptr_raw(), hp, None, hidden._ptr_raw(), None, B * H))
+        self._comb, self._comb2 = comb, comb2
+        self.z, self.r, self.h_candidate, self.hidden = z, r, hc, hidden
+        return hidden
+
+    def backward(self, dL_dh: Tensor, lr: float):
+        dL_dh = _as_tensor(dL_dh)
+        I, H = self.input_size, self.hidden_size
+        B = self.hidden.shape[0]
+        if dL_dh.shape != (B, H):
+            raise ValueError(f"operands could not be broadcast together with shapes {dL_dh.shape} {(B, H)}")
+        ctx = get_ctx()
+        b = self._bucket
+        dzh, dzz, dzr, dprev = (Tensor._empty((B, H), np.float64) for _ in range(4))
+        dcz, dcr, dch = (Tensor._empty((B, I + H), np.float64) for _ in range(3))
+        dx = Tensor._empty((B, I), np.float64)
+        if B:
+            hp, dhp = self.prev_hidden._dptr(NCX), dL_dh._dptr(NCX)
+            check(lib.okl_gru_pointwise(ctx.h, 1, self.z._ptr_raw(), self.h_candidate._ptr_raw(), hp, dhp, dzh._ptr_raw(), dzz._ptr_raw(), B * H))
+            check(lib.okl_dense_bwd(ctx.h, self._comb2._ptr_raw(), b.ptr(2), dzh._ptr_raw(), dch._ptr_raw(), b.grad_ptr(2), b.grad_ptr(5),
+                                    B, I + H, H, None))
+            check(lib.okl_gru_dr(ctx.h, dch._ptr_raw(), hp, self.r._ptr_raw(), dzr._ptr_raw(), B, I, H))
+            check(lib.okl_dense_bwd(ctx.h, self._comb._ptr_raw(), b.ptr(0), dzz._ptr_raw(), dcz._ptr_raw(), b.grad_ptr(0), b.grad_ptr(3),
+                                    B, I + H, H, None))
+            check(lib.okl_dense_bwd(ctx.h, self._comb._ptr_raw(), b.ptr(1), dzr._ptr_raw(), dcr._ptr_raw(), b.grad_ptr(1), b.grad_ptr(4),
+                                    B, I + H, H, None))
+            check(lib.okl_gru_dinputs(ctx.h, dcz._ptr_raw(), dcr._ptr_raw(), dch._ptr_raw(), self.r._ptr_raw(), self.z._ptr_raw(), dhp,
+                                      dx._ptr_raw(), dprev._ptr_raw(), B, I, H))
+            b.step(0.0, False)                       # accumulate only (okl.py:1590-1595 never touch the weights)
+        _set_input_grad(self.prev_hidden, dprev)
+        _set_input_grad(self.inputs, dx)
+        return dx, dprev
+
+    def get_params(self):
+        return {'Wz': self.Wz.data, 'Wr': self.Wr.data, 'Wh': self.Wh.data, 'bz': self.bz.data, 'br': self.br.data, 'bh': self.bh.data}
+
+    def set_params(self, params):
+        for k in ('Wz', 'Wr', 'Wh', 'bz', 'br', 'bh'):
+            getattr(self, k).data = params[k]
+
+
 # ====================================================================================================== batch normalisation
 class BatchNormLayer:
     """okl.py:1145-1222: (B, F) inputs; training mode normalises with the batch mean / population variance and

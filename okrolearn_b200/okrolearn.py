@@ -11,7 +11,7 @@ from .layers import (DenseLayer, Conv1DLayer, Conv2DLayer, Conv3DLayer, ReLUActi
                      HardTanhActivationLayer, LinearActivationLayer, SoftminActivationLayer, LogSoftmaxActivationLayer,
                      BatchNormLayer, L1RegularizationLayer, L2RegularizationLayer, L3RegularizationLayer, DropoutLayer,
                      MaxUnpoolingLayer, AverageUnpoolingLayer, PaddingLayer, ZeroPaddingLayer, ReflectionPaddingLayer,
-                     RNNLayer, LSTMLayer)
+                     RNNLayer, LSTMLayer, GRULayer)
 from .losses import CrossEntropyLoss, MSELoss, LossValue  # noqa: F401
 from .schedulers import (LearningRateScheduler, StepLRScheduler, TimeBasedDecayScheduler, ExponentialDecayScheduler,  # noqa: F401
                          LinearDecayScheduler)

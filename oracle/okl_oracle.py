@@ -416,6 +416,42 @@ class OracleLSTM:
         return dprev_h, dcell * self.f
 
 
+class OracleGRU:
+    """okl.py:1537-1643 line by line; backward accumulates the six gradients (no update), returns (dL/dx, dL/dh_prev)."""
+
+    def __init__(self, W, b, input_size):
+        self.W = [np.array(w, dtype=np.float64) for w in W]          # Wz, Wr, Wh
+        self.b = [np.array(v, dtype=np.float64) for v in b]          # bz, br, bh
+        self.I = input_size
+        self.gW, self.gb = [None] * 3, [None] * 3
+
+    def forward(self, x, h_prev=None):
+        H = self.W[0].shape[1]
+        h_prev = np.zeros((x.shape[0], H)) if h_prev is None else h_prev
+        sg = lambda v: 1 / (1 + np.exp(-v))                            # noqa: E731
+        self.x, self.h_prev = x, h_prev
+        comb = np.concatenate((x, h_prev), axis=1)
+        self.z, self.r = sg(comb @ self.W[0] + self.b[0]), sg(comb @ self.W[1] + self.b[1])
+        self.hc = np.tanh(np.concatenate((x, self.r * h_prev), axis=1) @ self.W[2] + self.b[2])
+        self.h = (1 - self.z) * h_prev + self.z * self.hc
+        return self.h
+
+    def backward(self, dh):
+        I = self.I
+        dz, dhc = dh * (self.hc - self.h_prev), dh * self.z
+        dzh = dhc * (1 - self.hc ** 2)
+        dr = (dzh @ self.W[2][I:].T) * self.h_prev
+        dzz, dzr = dz * self.z * (1 - self.z), dr * self.r * (1 - self.r)
+        comb, comb2 = np.concatenate((self.x, self.h_prev), axis=1), np.concatenate((self.x, self.r * self.h_prev), axis=1)
+        for k, (c, d) in enumerate(((comb, dzz), (comb, dzr), (comb2, dzh))):
+            dW, db = c.T @ d, np.sum(d, axis=0, keepdims=True)
+            self.gW[k] = dW if self.gW[k] is None else self.gW[k] + dW
+            self.gb[k] = db if self.gb[k] is None else self.gb[k] + db
+        dprev = dzz @ self.W[0][I:].T + dzr @ self.W[1][I:].T + (dzh @ self.W[2][I:].T) * self.r + dh * (1 - self.z)
+        dx = dzz @ self.W[0][:I].T + dzr @ self.W[1][:I].T + dzh @ self.W[2][:I].T
+        return dx, dprev
+
+
 class OracleBatchNorm:
     """okl.py:1145-1222 restated line by line (2-D inputs; backward uses the running variance in the chain rule as shipped;
     gamma / beta gradients accumulate forever and the update is applied inside backward)."""

@@ -472,6 +472,37 @@ for k_, nm_ in enumerate(("bf", "bi", "bc", "bo")):
     ls_["g" + nm_] = np.asarray(getattr(ll, nm_).grad)
 save("lstm", Wf=lW[0], Wi=lW[1], Wc=lW[2], Wo=lW[3], bf=lb[0], bi=lb[1], bc=lb[2], bo=lb[3], src="reference", **ls_)
 
+# ----------------------------------------------------------------------------- GRULayer
+gl = ref.GRULayer(6, 5)
+gW = [rng.standard_normal((11, 5)) * 0.4 for _ in range(3)]
+gb_ = [rng.standard_normal((1, 5)) * 0.1 for _ in range(3)]
+for nm_, wv in zip(("Wz", "Wr", "Wh"), gW):
+    getattr(gl, nm_).data = wv.copy()
+for nm_, bv in zip(("bz", "br", "bh"), gb_):
+    getattr(gl, nm_).data = bv.copy()
+og = O.OracleGRU(gW, gb_, 6)
+gr_ = {}
+hp = hpo = None
+for t_ in range(3):
+    xv, gh = rng.standard_normal((4, 6)), rng.standard_normal((4, 5))
+    h_r = gl.forward(T(xv.copy()), None if hp is None else T(hp.copy())).data
+    h_o = og.forward(xv, hpo)
+    close(h_o, h_r, 1e-13, what=f"gru hidden {t_}")
+    dx_r, dp_r = gl.backward(T(gh.copy()), 0.1)
+    dx_o, dp_o = og.backward(gh)
+    close(dx_o, dx_r.data, 1e-13, what=f"gru dx {t_}")
+    close(dp_o, dp_r.data, 1e-13, what=f"gru dprev {t_}")
+    gr_.update({f"x{t_}": xv, f"gh{t_}": gh, f"h{t_}": h_r, f"dx{t_}": dx_r.data, f"dprev{t_}": dp_r.data})
+    hp, hpo = h_r, h_o
+for k_, nm_ in enumerate(("Wz", "Wr", "Wh")):
+    close(og.gW[k_], getattr(gl, nm_).grad, 1e-13, what="gru " + nm_ + ".grad")
+    close(gW[k_], getattr(gl, nm_).data, 0, what="gru weights untouched")
+    gr_["g" + nm_] = np.asarray(getattr(gl, nm_).grad)
+for k_, nm_ in enumerate(("bz", "br", "bh")):
+    close(og.gb[k_], getattr(gl, nm_).grad, 1e-13, what="gru " + nm_ + ".grad")
+    gr_["g" + nm_] = np.asarray(getattr(gl, nm_).grad)
+save("gru", Wz=gW[0], Wr=gW[1], Wh=gW[2], bz=gb_[0], br=gb_[1], bh=gb_[2], src="reference", **gr_)
+
 # ----------------------------------------------------------------------------- BatchNormLayer
 xb1, xb2 = rng.standard_normal((12, 5)) * 1.5 + 0.3, rng.standard_normal((12, 5)) * 0.7 - 0.2
 gb1, gb2 = rng.standard_normal((12, 5)), rng.standard_normal((12, 5))

@@ -552,3 +552,22 @@ def test_lstm_layer(okl):
         assert rel_err(np.asarray(getattr(lay, nm).grad).reshape(g["g" + nm].shape), g["g" + nm]) < 3e-5, nm
         assert rel_err(getattr(lay, nm).data, g[nm]) < 1e-7, nm                 # backward never updates the weights
     assert set(lay.get_params()) == {"Wf", "Wi", "Wc", "Wo", "bf", "bi", "bc", "bo"}
+
+
+def test_gru_layer(okl):
+    """GRULayer unrolled over three steps vs the running reference (hidden states, dL/dx, dL/dh_prev, the six accumulated
+    parameter gradients; weights untouched by backward)."""
+    g = golden("gru")
+    lay = okl.GRULayer(6, 5)
+    for nm in ("Wz", "Wr", "Wh", "bz", "br", "bh"):
+        getattr(lay, nm).data = g[nm].copy()
+    hp = None
+    for t in range(3):
+        h = lay.forward(okl.Tensor(g[f"x{t}"]), None if hp is None else okl.Tensor(hp))
+        assert rel_err(h.data, g[f"h{t}"]) < 3e-6
+        dx, dp = lay.backward(okl.Tensor(g[f"gh{t}"]), 0.1)
+        assert rel_err(dx.data, g[f"dx{t}"]) < 3e-5 and rel_err(dp.data, g[f"dprev{t}"]) < 3e-5
+        hp = g[f"h{t}"]
+    for nm in ("Wz", "Wr", "Wh", "bz", "br", "bh"):
+        assert rel_err(np.asarray(getattr(lay, nm).grad).reshape(g["g" + nm].shape), g["g" + nm]) < 3e-5, nm
+        assert rel_err(getattr(lay, nm).data, g[nm]) < 1e-7, nm
