@@ -428,6 +428,16 @@ class NeuralNetwork:
         num_samples = inputs.shape[0]
         num_batches = int(np.ceil(num_samples / batch_size))
         losses = []
+        # parameters / accumulated gradients the user assigned on the host since the last step (``layer.weights.data = ...``,
+        # ``.grad = None``, ``load``) must be on the device before a captured step is replayed - replay touches no Python state
+        for layer in self.layers:
+            b = getattr(layer, "_bucket", None)
+            if b is not None and getattr(b, "ready", False):
+                for t in b.tensors:
+                    t._dptr(NCX)
+                    if getattr(t, "_bf16", None) is not None:
+                        t._b16()
+                b._sync_user_grads()
         fast = not self._observed()
         graph_ok = (fast and self.use_graph and not any(hasattr(l, 'parameters') for l in self.layers) and clip_grad is None
                     and hasattr(type(loss_function), "_loss_accum"))
@@ -484,12 +494,19 @@ class NeuralNetwork:
             idx_dev = self._idx_dev = _DevBuf(ctx, max(int(num_samples * 1.5), 1024) * 4)
 
         # ---- per-(batch shape, loss) step state: static input buffers + the captured graph
-        skey = (batch_size, sample_shape, t_shape, id(loss_function), tuple(id(l) for l in self.layers), fast,
-                self.fuse_activations, self.skip_input_grad, ctx.precision, bool(self.prefetch_batches))
-        st = self._graphs.get(skey)
+        # the stock losses are stateless: a fresh CrossEntropyLoss() / MSELoss() per train() call (the usual way to call it) reuses
+        # the captured step instead of capturing - and keeping alive - a new set of graphs and activation buffers every time
+        loss_key = type(loss_function) if type(loss_function) in (CrossEntropyLoss, MSELoss) else id(loss_function)
+        skey = (batch_size, sample_shape, t_shape, loss_key, tuple(id(l) for l in self.layers), fast,
+                self.fuse_activations, self.skip_input_grad, ctx.precision, bool(self.prefetch_batches), self.fuse_head,
+                self.fuse_conv_pool, self.use_aux_lanes, self.early_exchange, ctx.nranks)
+        st = self._graphs.pop(skey, None)
         if st is None:
             st = _StepState(ctx, batch_size, sample_shape, t_row)
-            self._graphs[skey] = st
+            while len(self._graphs) >= 4:                       # bounded: drop the least recently used configuration
+                ctx.sync()
+                self._graphs.pop(next(iter(self._graphs)))
+        self._graphs[skey] = st                                 # (re-)inserted last = most recently used
         if not hasattr(ctx, "lr_buf"):
             ctx.lr_buf = _DevBuf(ctx, 4)
         ctx.lr_dev = ctx.lr_buf.ptr

@@ -358,3 +358,33 @@ def test_checkpoint_resume_is_bit_exact(okl):
                 assert not np.array_equal(got[2], ref_w[2])
         with pytest.raises(ValueError):
             netC.load_checkpoint(os.path.join(d, "save.pkl"))
+
+
+def test_host_side_parameter_edits_reach_replayed_graphs(okl):
+    """train() (graphs captured) -> the user resets the parameters and clears the accumulated gradients on the host -> train() again
+    with a FRESH loss object (reuses the captured step) must equal a fresh network trained once: replay must see the edits."""
+    rng = np.random.default_rng(71)
+    N, B = 64, 16
+    X = rng.standard_normal((N, 1, 12, 12)).astype(np.float32)
+    T = rng.integers(0, 10, N)
+    g = {"Wc1": rng.standard_normal((4, 1, 3, 3)) * 0.3, "Wd1": rng.standard_normal((100, 16)) * 0.1, "Wd2": rng.standard_normal((16, 10)) * 0.1}
+
+    def run(net):
+        np.random.seed(13)
+        return net.train(okl.Tensor(X.copy()), okl.Tensor(T.copy()), epochs=1, lr_scheduler=okl.LearningRateScheduler(0.05),
+                         optimizer=okl.SGDOptimizer(), batch_size=B, loss_function=okl.CrossEntropyLoss())
+
+    netA, convA, d1A, d2A = cnn_small(okl, g)
+    netB, convB, d1B, d2B = cnn_small(okl, g)
+    lossA1 = run(netA)
+    n_graphs = len(netA._graphs)
+    convA.filters.data, d1A.weights.data, d2A.weights.data = g["Wc1"].copy(), g["Wd1"].copy(), g["Wd2"].copy()
+    convA.biases.data, d1A.biases.data, d2A.biases.data = np.zeros((4, 1)), np.zeros((1, 16)), np.zeros((1, 10))
+    for t in (convA.filters, convA.biases, d1A.weights, d1A.biases, d2A.weights, d2A.biases):
+        t.grad = None
+    lossA2 = run(netA)
+    lossB = run(netB)
+    assert len(netA._graphs) == n_graphs                       # the fresh CrossEntropyLoss() reused the captured step
+    assert np.array_equal(np.array(lossA2), np.array(lossB)) and np.array_equal(np.array(lossA1), np.array(lossB))
+    for a, b in ((convA.filters, convB.filters), (d1A.weights, d1B.weights), (d2A.weights, d2B.weights), (d2A.biases, d2B.biases)):
+        assert np.array_equal(a.data, b.data)
