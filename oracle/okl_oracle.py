@@ -16,6 +16,9 @@ reference loops with the five minimal repairs R1-R5 listed there, and is pinned 
 ``torch.autograd`` (CPU, fp64) instead.  The reference's own conv known-answer tests
 (tests/conv2d.py:43-48, tests/conv1d.py:30-31) hold wrong expected arrays (the reference code
 itself disagrees with them and matches torch), so they are recorded, not enforced.
+The SURVEY 8(f) rows added later (Unfold / Fold, the other activations, BatchNorm, the regularisation wrappers, Dropout, un-pooling,
+padding, RNN / LSTM / GRU cells, transposed-conv forward) are pinned the same way on the running reference; the transposed-conv
+backward - which raises as shipped - on ``torch.autograd``.
 
 Every function cites the reference file:line it follows.  "okl.py" = src/okrolearn/okrolearn.py.
 
