@@ -571,3 +571,40 @@ def test_gru_layer(okl):
     for nm in ("Wz", "Wr", "Wh", "bz", "br", "bh"):
         assert rel_err(np.asarray(getattr(lay, nm).grad).reshape(g["g" + nm].shape), g["g" + nm]) < 3e-5, nm
         assert rel_err(getattr(lay, nm).data, g[nm]) < 1e-7, nm
+
+
+def test_conv_random_shapes_fp32(okl):
+    """Randomised parity of Conv1D / Conv2D / Conv3D (forward, dX, dW, db, in-layer update) in FP32 mode against the oracle: strides
+    1-3, paddings 0-2, rectangular kernels, odd channel counts - beyond the enumerated golden cases."""
+    rng = np.random.default_rng(4242)
+    for case in range(18):
+        nd = int(rng.integers(1, 4))
+        N, C, Oc = int(rng.integers(1, 5)), int(rng.integers(1, 7)), int(rng.integers(1, 9))
+        k = tuple(int(v) for v in rng.integers(1, 4, nd))
+        s = tuple(int(v) for v in rng.integers(1, 4, nd))
+        p = tuple(int(v) for v in rng.integers(0, 3, nd))
+        sp = tuple(int(kk + rng.integers(0, 9)) for kk in k)
+        x = rng.standard_normal((N, C) + sp)
+        W = rng.standard_normal((Oc, C) + k) * 0.3
+        b = rng.standard_normal((Oc, 1)) * 0.2
+        if nd == 1:
+            lay = okl.Conv1DLayer(C, Oc, k[0], s[0], p[0])
+            lay.weights.data = W.copy()
+        elif nd == 2:
+            lay = okl.Conv2DLayer(C, Oc, k, s, p)
+            lay.filters.data = W.copy()
+        else:
+            lay = okl.Conv3DLayer(C, Oc, k, s, p)
+            lay.filters.data = W.copy()
+        lay.biases.data = b.copy()
+        Wt = lay.weights if nd == 1 else lay.filters
+        tag = (case, nd, N, C, Oc, k, s, p, sp)
+        y = lay.forward(okl.Tensor(x))
+        yo = O.conv_forward_fast(x, W, b, s, p, dtype=np.float64)
+        assert y.shape == yo.shape and rel_err(y.data, yo) < 2e-5, tag
+        g = rng.standard_normal(yo.shape)
+        dX = lay.backward(okl.Tensor(g), 0.05)
+        dW, db, dXo = O.conv_backward_fast(x, W, g, s, p)
+        assert rel_err(dX.data, dXo) < 2e-5, tag
+        assert rel_err(Wt.grad, dW) < 2e-5 and rel_err(np.asarray(lay.biases.grad).reshape(-1), np.asarray(db).reshape(-1)) < 2e-5, tag
+        assert rel_err(Wt.data, W - 0.05 * dW) < 2e-5, tag
