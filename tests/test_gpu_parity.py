@@ -608,3 +608,32 @@ def test_conv_random_shapes_fp32(okl):
         assert rel_err(dX.data, dXo) < 2e-5, tag
         assert rel_err(Wt.grad, dW) < 2e-5 and rel_err(np.asarray(lay.biases.grad).reshape(-1), np.asarray(db).reshape(-1)) < 2e-5, tag
         assert rel_err(Wt.data, W - 0.05 * dW) < 2e-5, tag
+
+
+def test_dense_random_shapes_and_empty_batches(okl):
+    """Randomised DenseLayer parity in FP32 mode (tiny-N head kernel, FFMA tiles, odd sizes) and the empty-batch edge cases of Dense and
+    Conv2D (zero rows in, zero rows out, zero gradients, parameters unchanged)."""
+    rng = np.random.default_rng(99)
+    for case in range(14):
+        M, K, N = int(rng.integers(1, 70)), int(rng.integers(1, 90)), int(rng.integers(1, 40))
+        x, W, b = rng.standard_normal((M, K)), rng.standard_normal((K, N)) * 0.3, rng.standard_normal((1, N)) * 0.2
+        lay = okl.DenseLayer(K, N)
+        lay.weights.data, lay.biases.data = W.copy(), b.copy()
+        y = lay.forward(okl.Tensor(x))
+        assert rel_err(y.data, x @ W + b) < 2e-5, (case, M, K, N)
+        g = rng.standard_normal((M, N))
+        dX = lay.backward(okl.Tensor(g), 0.05)
+        assert rel_err(dX.data, g @ W.T) < 2e-5, (case, M, K, N)
+        assert rel_err(lay.weights.data, W - 0.05 * (x.T @ g)) < 2e-5 and rel_err(lay.biases.data, b - 0.05 * g.sum(0, keepdims=True)) < 2e-5
+    d = okl.DenseLayer(7, 5)
+    W0 = d.weights.data.copy()
+    y0 = d.forward(okl.Tensor(np.zeros((0, 7))))
+    assert y0.shape == (0, 5) and y0.data.shape == (0, 5)
+    dx0 = d.backward(okl.Tensor(np.zeros((0, 5))), 0.1)
+    assert dx0.shape == (0, 7) and np.array_equal(d.weights.data.astype(np.float32), W0.astype(np.float32))
+    c = okl.Conv2DLayer(2, 3, 3, 1, 1)
+    F0 = c.filters.data.copy()
+    yc = c.forward(okl.Tensor(np.zeros((0, 2, 6, 6))))
+    assert yc.shape == (0, 3, 6, 6)
+    dxc = c.backward(okl.Tensor(np.zeros((0, 3, 6, 6))), 0.1)
+    assert dxc.shape == (0, 2, 6, 6) and np.array_equal(c.filters.data.astype(np.float32), F0.astype(np.float32))
