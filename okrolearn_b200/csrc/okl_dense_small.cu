@@ -237,8 +237,11 @@ __global__ void __launch_bounds__(256) dense_softmax_ce_kernel(const float* __re
 #pragma unroll
     for (int w = 0; w < 8; w++) s += wl[w];
     partial[blockIdx.x] = s;
-    __threadfence();
-    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    is_last = false;
+    if (counter) {                               // no counter: head_loss_finalize_kernel sums the partials (off the critical path)
+      __threadfence();
+      is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
   }
   __syncthreads();
   if (is_last && wib == 0) {                  // last block to arrive: fixed-order sum of the per-block partials
@@ -253,6 +256,20 @@ __global__ void __launch_bounds__(256) dense_softmax_ce_kernel(const float* __re
       if (loss_acc) loss_acc[0] += l;
       *counter = 0u;
     }
+  }
+}
+
+// loss = sum(partials) / M in the same fixed order as the in-kernel tail; one warp
+__global__ void head_loss_finalize_kernel(const float* __restrict__ partial, int nblk, int M, float* __restrict__ loss, float* __restrict__ loss_acc) {
+  const int lane = threadIdx.x;
+  float tot = 0.f;
+  for (int i = lane; i < nblk; i += 32) tot += partial[i];
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, s);
+  if (lane == 0) {
+    const float l = tot / (float)M;
+    loss[0] = l;
+    if (loss_acc) loss_acc[0] += l;
   }
 }
 
@@ -302,7 +319,12 @@ extern "C" int okl_dense_softmax_ce(okl_ctx* ctx, const void* X, const void* W, 
   int grid = (M + 7) / 8;
   const int cap = ctx->sm_count * 4 < 2000 ? ctx->sm_count * 4 : 2000;
   if (grid > cap) grid = cap;
-  unsigned* counter = (unsigned*)ctx->head_scratch;
+  // The loss VALUE is not needed by anything on the step's critical path: its final reduction (fence + ticket + last-block sum
+  // inside the kernel, ~2 us) is done by a one-warp kernel on auxiliary lane 1 instead, joined with the other leaves of the step.
+  static int defer_env = -1;
+  if (defer_env < 0) { const char* e = getenv("OKL_HEAD_DEFER"); defer_env = e ? atoi(e) : 1; }
+  const bool defer = defer_env && ctx->cur_lane == 0;
+  unsigned* counter = defer ? nullptr : (unsigned*)ctx->head_scratch;
   float* partial = (float*)ctx->head_scratch + 16;
   if (K <= 128)
     okl_launch(ctx, dense_softmax_ce_kernel<4>, dim3(grid), dim3(256), 0, (const float*)X, (const float*)W, (const float*)b,
@@ -313,5 +335,14 @@ extern "C" int okl_dense_softmax_ce(okl_ctx* ctx, const void* X, const void* W, 
                (const int*)targets_i32, (float*)P, (float*)grad, (float*)dZ, (float*)dX, (const float*)dx_relu_mask, (float*)loss,
                (float*)loss_accum, partial, counter, M, K, N, 1.f / denom);
   OKL_LAUNCHED(ctx, "dense_softmax_ce");
+  if (defer) {
+    int s = okl_aux_mark(ctx);
+    if (s == OKL_OK) s = okl_aux_begin(ctx, 1);
+    if (s != OKL_OK) return s;
+    head_loss_finalize_kernel<<<1, 32, 0, ctx->stream>>>(partial, grid, M, (float*)loss, (float*)loss_accum);
+    s = okl_post_launch(ctx, "head_loss_finalize");
+    const int e = okl_aux_end(ctx);
+    return s != OKL_OK ? s : e;
+  }
   return OKL_OK;
 }
