@@ -323,7 +323,7 @@ extern "C" int okl_dense_softmax_ce(okl_ctx* ctx, const void* X, const void* W, 
   // inside the kernel, ~2 us) is done by a one-warp kernel on auxiliary lane 1 instead, joined with the other leaves of the step.
   static int defer_env = -1;
   if (defer_env < 0) { const char* e = getenv("OKL_HEAD_DEFER"); defer_env = e ? atoi(e) : 1; }
-  const bool defer = defer_env && ctx->cur_lane == 0;
+  const bool defer = defer_env && ctx->cur_lane == 0 && ctx->nranks == 1;     // data-parallel runs keep the verified in-kernel tail
   unsigned* counter = defer ? nullptr : (unsigned*)ctx->head_scratch;
   float* partial = (float*)ctx->head_scratch + 16;
   if (K <= 128)
