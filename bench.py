@@ -6,7 +6,10 @@
     torchrun --nproc-per-node N ... bench.py --gpus N ...          # one process per GPU, NCCL gradient allreduce
 
 A "step" is one train step (forward + loss + backward + in-layer accumulated-gradient update) on one batch of synthetic
-data.  Default workload = BASELINE.json configs[1]: MNIST-shaped CNN, batch 256 per GPU (weak scaling).
+data.  Default workload = BASELINE.json configs[2]: the CIFAR-shaped 6-conv network at GLOBAL batch 1024, split over the N GPUs
+(strong scaling: N=1 runs all 1024, N=8 runs 128 per GPU), BF16 operands / FP32 accumulate.  The other BASELINE configs are
+measured in the same run and reported under "configs" (N=1: all of them; N>1: the two that name a multi-GPU run), the TF32 and
+FP32-FFMA modes of the headline workload under "modes".
 """
 from __future__ import annotations
 
@@ -33,7 +36,7 @@ WORKLOADS = {
     "conv2d_single": dict(desc="single Conv2D(1,16,3) fwd+bwd on 32x1x28x28 (MSE to a random target)", batch=32,
                           sample=(1, 28, 28), classes=0, loss="mse"),
     "cifar6": dict(desc="CIFAR-shaped 6x Conv2D(3x3,p1) 3-64-64-P-128-128-P-256-256-P-Flatten-Dense(4096,10)-Softmax+CE",
-                   batch=128, sample=(3, 32, 32), classes=10, loss="ce"),
+                   batch=1024, sample=(3, 32, 32), classes=10, loss="ce"),
     "mlp8192": dict(desc="4x DenseLayer(8192,8192)+ReLU, MSE", batch=8192, sample=(8192,), classes=0, loss="mse"),
     "conv1d_seq": dict(desc="Conv1D(64,64,3,1,1)+ReLU on 512x64x1024, MSE", batch=512, sample=(64, 1024), classes=0, loss="mse"),
     "conv3d_video": dict(desc="Conv3D(3,64,3,1,1)+ReLU on 8x3x16x112x112, MSE", batch=8, sample=(3, 16, 112, 112), classes=0,
@@ -228,47 +231,96 @@ def time_cpu(name, budget_s, steps=None, warmup=1):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# per-kernel rooflines (timed live, CUDA events on the library's compute stream = the stream the kernels are launched on)
+# ----------------------------------------------------------------------------------------------------------------------
+PROFILE_FILES = {"cifar6": "r2_ncu_cifar6_kernels.json", "mnist_cnn": "r1_ncu_full_top_kernels_mnist_cnn.json"}
+
+
 def ncu_traffic(profile, needle):
-    """DRAM bytes (read + write) per launch of the kernel whose name contains `needle`, from the committed `ncu --set full`
+    """DRAM bytes (read + write) per launch of the kernel whose label contains `needle`, from the committed `ncu --set full`
     capture of this bench command (profiles/<profile>); None when that kernel is not in the capture."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", profile)
+    path = os.path.join(ROOT, "profiles", profile)
     try:
         with open(path) as f:
             doc = json.load(f)
     except (OSError, ValueError):
-        return None
+        return None, None
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for k in doc.get("kernels", []):
-        if needle in k.get("Kernel Name", ""):
+        if needle in k.get("Kernel Name", "") or needle == k.get("label"):
             tot = 0.0
             for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                tot += float(k[m]) * scale.get(doc["units"].get(m, "byte"), 1.0)
-            return tot
-    return None
+                tot += float(k[m]) * scale.get(doc.get("units", {}).get(m, "byte"), 1.0)
+            return tot, f"profiles/{profile}@{doc.get('commit', '?')}"
+    return None, None
 
 
-def kernel_rooflines(okl, ctx, name, batch, peaks):
-    """Per-kernel roofline of the dominant kernels, timed live with CUDA events on the launching stream, L2 flushed
-    between launches.  Returns a list of dicts (first entry = the dominant kernel of the step)."""
+CIFAR_LAYERS = [(3, 64, 32), (64, 64, 32), (64, 128, 16), (128, 128, 16), (128, 256, 8), (256, 256, 8)]
+
+
+def conv_cases(okl, ctx, nd, N, Cc, Oc, sp, k, pad, relu, label, prec, need_dx=True):
+    """fprop / dgrad / wgrad of one convolution layer through the C ABI (the calls the layer makes), on synthetic tensors."""
+    import ctypes as C
+    from okrolearn_b200 import _lib
+    lib, check = _lib.lib, _lib.check
+    rng = np.random.default_rng(0)
+    lay = {1: okl.Conv1DLayer, 2: okl.Conv2DLayer, 3: okl.Conv3DLayer}[nd](Cc, Oc, k, 1, pad)
+    lay._fused_act = 1 if relu else 0
+    x = okl.Tensor(rng.standard_normal((N, Cc) + sp, dtype=np.float32))
+    y = lay.forward(x)                                   # decides layouts / bf16 path exactly as the training step does
+    g = okl.Tensor(rng.standard_normal(y.shape, dtype=np.float32))
+    xl, yl = lay._fwd_layouts
+    d, oe = lay._desc(x.shape, xl, yl, lay._fused_act)
+    d0, _ = lay._desc(x.shape, xl, yl, 0)
+    b = lay._bucket
+    So = int(np.prod(oe))
+    taps = int(np.prod(lay._k))
+    fl = 2.0 * N * So * Oc * Cc * taps
+    es = 2 if getattr(lay, "_bf16_path", False) else 4
+    xb, yb, wb = N * Cc * int(np.prod(sp)), N * Oc * So, Oc * Cc * taps
+    dx = okl.Tensor._empty(x.shape, np.float32, layout=xl)
+    if getattr(lay, "_bf16_path", False):
+        x16, g16 = x._b16(_lib.NXC), g._b16(_lib.NXC)
+        y16, dx16 = y._new_b16(), dx._new_b16()
+        f_fp = lambda: check(lib.okl_conv_fprop_bf16(ctx.h, C.byref(d), x16, b.ptr(0), b.ptr(1), y._ptr_raw(), y16))        # noqa: E731
+        f_dg = lambda: check(lib.okl_conv_dgrad_bf16(ctx.h, C.byref(d0), g16, b.ptr(0), dx._ptr_raw(), dx16, x._dptr(xl)))   # noqa: E731
+        f_wg = lambda: check(lib.okl_conv_wgrad_bf16(ctx.h, C.byref(d0), x16, g16, g._dptr(yl), b.grad_ptr(0), b.grad_ptr(1)))  # noqa: E731
+        by_fp = es * (xb + wb) + (4 + 2) * yb
+        by_dg = es * (yb + wb) + (4 + 2 + 4) * xb       # g16 + filters read; dX fp32 + bf16 written; fp32 ReLU mask read
+        by_wg = es * (xb + yb) + 4 * yb + 4 * wb         # x16, g16, fp32 g (bias gradient) read; dW written
+    else:
+        xp, gp = x._dptr(xl), g._dptr(yl)
+        f_fp = lambda: check(lib.okl_conv_fprop(ctx.h, C.byref(d), xp, b.ptr(0), b.ptr(1), y._ptr_raw()))                   # noqa: E731
+        f_dg = lambda: check(lib.okl_conv_dgrad(ctx.h, C.byref(d0), gp, b.ptr(0), dx._ptr_raw(), xp))                       # noqa: E731
+        f_wg = lambda: check(lib.okl_conv_wgrad(ctx.h, C.byref(d0), xp, gp, b.grad_ptr(0), b.grad_ptr(1)))                  # noqa: E731
+        by_fp, by_dg, by_wg = 4.0 * (xb + wb + yb), 4.0 * (yb + wb + 2 * xb), 4.0 * (xb + yb + wb)
+    keep = (lay, x, y, g, dx)
+    cases = [(f"{label} fprop", f_fp, fl, by_fp, keep), (f"{label} wgrad", f_wg, fl, by_wg, keep)]
+    if need_dx:                                           # a network's FIRST layer never computes its input gradient (nothing reads it)
+        cases.insert(1, (f"{label} dgrad", f_dg, fl, by_dg, keep))
+    return cases
+
+
+def kernel_rooflines(okl, ctx, name, batch, peaks, prec):
+    """Per-kernel roofline of the dominant kernels of a workload.  Returns a list of dicts."""
     import ctypes as C
     from okrolearn_b200 import _lib
     lib, check = _lib.lib, _lib.check
     res = []
-
-    def timed(fn, reps=10, flush=True):
-        ts = []
-        for _ in range(reps):
-            if flush:
-                check(lib.okl_flush_l2(ctx.h))
-            ctx.timer_start()
-            fn()
-            ts.append(ctx.timer_stop())
-        ts.sort()
-        return float(np.mean(ts[:max(1, len(ts) // 2)])) * 1e-3, float(np.mean(ts)) * 1e-3
-
-    prec = {0: "fp32", 1: "tf32", 2: "bf16"}[ctx.precision]
     tensor_peak = {"fp32": 74.5, "tf32": peaks["bf16_tflops"] / 2, "bf16": peaks["bf16_tflops"]}[prec]
-    if name == "mnist_cnn":
+    cases = []
+    if name == "cifar6":
+        for i, (c, o, s) in enumerate(CIFAR_LAYERS):
+            if i == 0:
+                continue                                  # 3 -> 64 first layer: fused conv+relu(+pool-less) small-K kernels, HBM-bound
+            cases += conv_cases(okl, ctx, 2, batch, c, o, (s, s), 3, 1, True, f"conv{i + 1} {c}->{o}@{s}x{s}", prec)
+    elif name == "conv1d_seq":
+        cases += conv_cases(okl, ctx, 1, batch, 64, 64, (1024,), 3, 1, True, "conv1d 64->64 L1024", prec, need_dx=False)
+    elif name == "conv3d_video":
+        cases += conv_cases(okl, ctx, 3, batch, 3, 64, (16, 112, 112), 3, 1, True, "conv3d 3->64 16x112x112", prec, need_dx=False)
+    elif name == "conv2d_single":
+        cases += conv_cases(okl, ctx, 2, batch, 1, 16, (28, 28), 3, 0, False, "conv2d 1->16 28x28", prec, need_dx=False)
+    elif name == "mnist_cnn":
         rng = np.random.default_rng(0)
         M, K, N = batch, 5408, 128
         X = okl.Tensor(rng.standard_normal((M, K)).astype(np.float32))
@@ -278,13 +330,14 @@ def kernel_rooflines(okl, ctx, name, batch, peaks):
         dW = okl.Tensor._empty((K, N), np.float32)
         dX = okl.Tensor._empty((M, K), np.float32)
         xp, wp, gp = X._dptr(), W._dptr(), G._dptr()
+        keep = (X, W, G, Y, dW, dX)
         cases = [
             ("dense1_wgrad (dW = X^T G, 5408x128, K=256)", lambda: check(lib.okl_dense_bwd(ctx.h, xp, wp, gp, None, dW._ptr_raw(), None, M, K, N, None)),
-             2.0 * M * K * N, 4.0 * (M * K + M * N + K * N), "tc_gemm_kernel<0, 1, 1,"),
+             2.0 * M * K * N, 4.0 * (M * K + M * N + K * N), keep),
             ("dense1_fwd (Y = X W, 256x5408x128)", lambda: check(lib.okl_dense_fwd(ctx.h, xp, wp, None, Y._ptr_raw(), M, K, N, 1)),
-             2.0 * M * K * N, 4.0 * (M * K + K * N + M * N), "tc_gemm_kernel<0, 0, 1, 64, 0>"),
+             2.0 * M * K * N, 4.0 * (M * K + K * N + M * N), keep),
             ("dense1_dgrad (dX = G W^T)", lambda: check(lib.okl_dense_bwd(ctx.h, xp, wp, gp, dX._ptr_raw(), None, None, M, K, N, None)),
-             2.0 * M * K * N, 4.0 * (M * N + K * N + M * K), "tc_gemm_kernel<0, 0, 0,"),
+             2.0 * M * K * N, 4.0 * (M * N + K * N + M * K), keep),
         ]
         d = _lib.ConvDesc()
         d.nd, d.N, d.C, d.O = 2, batch, 1, 32
@@ -303,75 +356,267 @@ def kernel_rooflines(okl, ctx, name, batch, peaks):
         check(lib.okl_conv_relu_pool_fwd(ctx.h, C.byref(d), cxp, cwp, cbp, pooled._ptr_raw(), mask._ptr_raw()))
         npool = batch * 32 * 13 * 13
         convf = 2.0 * batch * 32 * 26 * 26 * 9
+        keep2 = (cx, cw, cb, pooled, pg, mask, cdw, cdb, d)
         cases = [
-            # fused Conv2D(1,32,3)+bias+ReLU+MaxPool(2,2): reads x, writes pooled (fp32) + mask (u8); the 22 MB un-pooled tensor never exists
             ("conv1_relu_pool_fwd (256x1x28x28 -> 32@3x3 -> pool 13x13)",
              lambda: check(lib.okl_conv_relu_pool_fwd(ctx.h, C.byref(d), cxp, cwp, cbp, pooled._ptr_raw(), mask._ptr_raw())),
-             convf, 4.0 * batch * 784 + 5.0 * npool, "conv_relu_pool2_fwd"),
-            # its backward: dW, db from the POOLED gradient + mask + x
+             convf, 4.0 * batch * 784 + 5.0 * npool, keep2),
             ("conv1_relu_pool_wgrad (dW 32x9, db 32 from pooled gradient + mask)",
              lambda: check(lib.okl_conv_relu_pool_wgrad(ctx.h, C.byref(d), cxp, pgp, mask._ptr_raw(), cdw._ptr_raw(), cdb._ptr_raw())),
-             2.0 * npool * 10, 4.0 * batch * 784 + 5.0 * npool, "conv_relu_pool2_wgrad"),
+             2.0 * npool * 10, 4.0 * batch * 784 + 5.0 * npool, keep2),
         ] + cases
     elif name == "mlp8192":
-        M = K = N = 8192
-        X = okl.Tensor._empty((M, K), np.float32)
-        W = okl.Tensor._empty((K, N), np.float32)
-        Y = okl.Tensor._empty((M, N), np.float32)
-        check(lib.okl_memset(ctx.h, X._ptr_raw(), 0, M * K * 4))
-        check(lib.okl_memset(ctx.h, W._ptr_raw(), 0, M * K * 4))
-        cases = [("dense_fwd 8192^3", lambda: check(lib.okl_dense_fwd(ctx.h, X._ptr_raw(), W._ptr_raw(), None, Y._ptr_raw(), M, K, N, 1)),
-                  2.0 * M * K * N, 4.0 * 3 * M * N, None)]
-    else:
-        return res
-    for label, fn, flops, byts, needle in cases:
-        fn()
-        ctx.sync()
-        # the kernel as it runs inside the step: its operands were produced by the preceding kernels of the same step and sit in
-        # the 126 MB L2 (a step touches ~40 MB), so the primary figure is the back-to-back (L2-warm) launch time; the L2-flushed
-        # time - every operand from DRAM - is reported next to it
+        M, K, N = batch, 8192, 8192
+        lay = okl.DenseLayer.__new__(okl.DenseLayer)
+        X, W, G = okl.Tensor._empty((M, K), np.float32), okl.Tensor._empty((K, N), np.float32), okl.Tensor._empty((M, N), np.float32)
+        Y, dW, dX = okl.Tensor._empty((M, N), np.float32), okl.Tensor._empty((K, N), np.float32), okl.Tensor._empty((M, K), np.float32)
+        for t in (X, W, G):
+            check(lib.okl_memset(ctx.h, t._ptr_raw(), 0x3c, t.size * 4))
+        keep = (X, W, G, Y, dW, dX, lay)
+        es = 2 if prec == "bf16" else 4
+        if prec == "bf16":
+            x16, w16, g16 = X._b16(), W._b16(), G._b16()
+            y16, dx16 = Y._new_b16(), dX._new_b16()
+            cases = [
+                ("dense 8192 fwd", lambda: check(lib.okl_dense_fwd_bf16(ctx.h, x16, w16, None, Y._ptr_raw(), y16, M, K, N, 1)),
+                 2.0 * M * K * N, es * (M * K + K * N) + 6.0 * M * N, keep),
+                ("dense 8192 dgrad", lambda: check(lib.okl_dense_bwd_bf16(ctx.h, x16, w16, g16, G._ptr_raw(), dX._ptr_raw(), dx16, None, None, M, K, N, None)),
+                 2.0 * M * K * N, es * (M * N + K * N) + 6.0 * M * K, keep),
+                ("dense 8192 wgrad", lambda: check(lib.okl_dense_bwd_bf16(ctx.h, x16, w16, g16, G._ptr_raw(), None, None, dW._ptr_raw(), None, M, K, N, None)),
+                 2.0 * M * K * N, es * (M * K + M * N) + 4.0 * K * N, keep),
+            ]
+        else:
+            xp, wp, gp = X._ptr_raw(), W._ptr_raw(), G._ptr_raw()
+            cases = [
+                ("dense 8192 fwd", lambda: check(lib.okl_dense_fwd(ctx.h, xp, wp, None, Y._ptr_raw(), M, K, N, 1)), 2.0 * M * K * N, 4.0 * (M * K + K * N + M * N), keep),
+                ("dense 8192 dgrad", lambda: check(lib.okl_dense_bwd(ctx.h, xp, wp, gp, dX._ptr_raw(), None, None, M, K, N, None)), 2.0 * M * K * N, 4.0 * (M * K + K * N + M * N), keep),
+                ("dense 8192 wgrad", lambda: check(lib.okl_dense_bwd(ctx.h, xp, wp, gp, None, dW._ptr_raw(), None, M, K, N, None)), 2.0 * M * K * N, 4.0 * (M * K + K * N + M * N), keep),
+            ]
+    prof = PROFILE_FILES.get(name)
+    for label, fn, flops, byts, keep in cases:
         for _ in range(3):
             fn()
+        ctx.sync()
+        reps = 20
         ctx.timer_start()
-        for _ in range(50):
+        for _ in range(reps):
             fn()
-        mean = ctx.timer_stop() * 1e-3 / 50                # one event pair around 50 pipelined launches: no launch latency in it
-        best_c, mean_c = timed(fn)
+        warm = ctx.timer_stop() * 1e-3 / reps              # one event pair around back-to-back launches: no launch latency in it
+        cold = []
+        for _ in range(5):
+            check(lib.okl_flush_l2(ctx.h))
+            ctx.timer_start()
+            fn()
+            cold.append(ctx.timer_stop() * 1e-3)
+        cold = float(np.median(cold))
+        # working sets of these layers (0.1 - 1 GB at the bench batch) exceed the 126 MB L2, so the back-to-back time is already a
+        # DRAM-fed time; for the small MNIST kernels the L2-flushed time is reported beside it
         ai = flops / byts
         ridge = tensor_peak * 1e12 / (peaks["hbm_gbs"] * 1e9)
         if ai >= ridge:
-            ach, ach_c, peak, unit, bound = flops / mean / 1e12, flops / mean_c / 1e12, tensor_peak, "TFLOP/s", "tensor"
+            ach, ach_c, peak, unit, bound = flops / warm / 1e12, flops / cold / 1e12, tensor_peak, "TFLOP/s", "tensor"
         else:
-            ach, ach_c, peak, unit, bound = byts / mean / 1e9, byts / mean_c / 1e9, peaks["hbm_gbs"], "GB/s", "hbm"
-        res.append({"kernel": label, "bound": bound, "achieved": round(ach, 3), "peak": peak, "unit": unit,
-                    "frac": round(ach / peak, 4),
-                    # dram read+write per launch from the committed ncu --set full capture of this command (tf32 default only)
-                    "traffic": ncu_traffic("r1_ncu_full_top_kernels_mnist_cnn.json", needle) if (needle and prec == "tf32") else None,
-                    "us": round(mean * 1e6, 2), "us_cold_l2": round(mean_c * 1e6, 2), "achieved_cold_l2": round(ach_c, 3),
-                    "frac_cold_l2": round(ach_c / peak, 4), "algo_flops": flops, "algo_bytes": byts, "mode": prec,
-                    "timing": "CUDA events on the launching stream: us = one event pair around 50 back-to-back launches / 50 (L2-warm, as "
-                              "inside the step); *_cold_l2 = mean of 10 single launches, each after an L2 flush (includes launch latency)"})
+            ach, ach_c, peak, unit, bound = byts / warm / 1e9, byts / cold / 1e9, peaks["hbm_gbs"], "GB/s", "hbm"
+        traffic, tsrc = ncu_traffic(prof, label) if (prof and prec in ("bf16", "tf32")) else (None, None)
+        res.append({"kernel": label, "bound": bound, "achieved": round(ach, 3), "peak": peak, "unit": unit, "frac": round(ach / peak, 4),
+                    "traffic": traffic, "traffic_source": tsrc, "us": round(warm * 1e6, 2), "us_cold_l2": round(cold * 1e6, 2),
+                    "frac_cold_l2": round(ach_c / peak, 4), "tflops": round(flops / warm / 1e12, 2), "gbs": round(byts / warm / 1e9, 1),
+                    "algo_flops": flops, "algo_bytes": byts, "arith_intensity": round(ai, 1), "mode": prec})
+        del keep
+    return res
+
+
+ROOFLINE_TIMING = ("CUDA events on the launching stream: us = one event pair around 20 back-to-back launches / 20; us_cold_l2 = median of 5 "
+                   "single launches, each after an L2 flush (includes launch latency)")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# one workload through the public API
+# ----------------------------------------------------------------------------------------------------------------------
+def run_workload(okl, ctx, name, B, K, W_, prec, rank, world, want_e2e=True, min_gpu_s=0.5, max_repeats=40):
+    """W_ warm-up steps, then `repeats` timed regions of EXACTLY K steps of NeuralNetwork.train each (barrier + sync on both
+    sides, CUDA events on the library's stream, max over ranks), repeated until >= min_gpu_s of device time; the reported step
+    time is the MEDIAN region."""
+    from okrolearn_b200 import _lib
+    w = WORKLOADS[name]
+    okl.set_precision(prec)
+    np.random.seed(1234)                       # identical initial weights on every rank
+    net = build_net(okl, name)
+    logging.getLogger("NeuralNetwork").setLevel(logging.CRITICAL)      # NeuralNetwork() re-arms the logger at DEBUG
+    loss_fn = okl.CrossEntropyLoss() if w["loss"] == "ce" else okl.MSELoss()
+    lr = 1e-9 if name == "mlp8192" else (1e-4 if name == "cifar6" else 0.01)   # reference init (randn * 0.1): keep wide nets finite
+    sched, opt = okl.LearningRateScheduler(lr), okl.SGDOptimizer(lr=lr)
+    Xw, Tw = synth(name, B * W_, rank)
+    Xk, Tk = synth(name, B * K, rank)
+    tXw, tTw, tXk, tTk = okl.Tensor(Xw), okl.Tensor(Tw), okl.Tensor(Xk), okl.Tensor(Tk)
+    for t in (tXw, tXk) + (() if w["loss"] == "ce" else (tTw, tTk)):
+        t._dptr()
+    np.random.seed(99 + rank * 0)              # same shuffles on every rank (each rank shuffles its own shard)
+    net.train(tXw, tTw, 1, sched, opt, B, loss_fn)          # warm-up: eager step, capture, replays
+    ctx.sync()
+    net.prepare(tXk, tTk, loss_fn)                            # dataset placement: inputs AND targets resident in HBM before the timed region
+    regions, launches, losses = [], 0, []
+    total = 0.0
+    while True:
+        _lib.check(_lib.lib.okl_barrier(ctx.h))
+        ctx.sync()
+        l0 = ctx.launch_count()
+        ctx.timer_start()
+        losses = net.train(tXk, tTk, 1, sched, opt, B, loss_fn)  # exactly K steps
+        ms = ctx.timer_stop()
+        launches = ctx.launch_count() - l0
+        v = C_double(ms)
+        _lib.check(_lib.lib.okl_allreduce_max_host(ctx.h, v))
+        regions.append(v.value)
+        total += v.value
+        # the decision to stop is taken on the max-over-ranks value, so every rank takes it identically
+        if total >= min_gpu_s * 1e3 or len(regions) >= max_repeats:
+            break
+    ms = float(np.median(regions))
+    out = {"ms_per_step": ms / K, "value": world * B * K / (ms * 1e-3), "repeats": len(regions),
+           "region_ms": [round(r, 4) for r in regions], "gpu_launches": int(launches), "final_loss": float(losses[-1]) if losses else None,
+           "net": net}
+    # ------------------------------------------------------------------ end to end: host (pinned) -> device every step, loss read back every step
+    if want_e2e:
+        net.stream_inputs, net.sync_loss_every_step = True, True
+
+        def host_dataset(X, T):                      # the dataset as a user would hold it for streaming: page-locked host arrays
+            pX = okl.pinned_empty(X.shape, np.float32)
+            pX[...] = X
+            pT = okl.pinned_empty(T.shape, np.int32 if w["loss"] == "ce" else np.float32)
+            pT[...] = T
+            return okl.Tensor.wrap(pX), okl.Tensor.wrap(pT)
+        hXw, hTw = host_dataset(Xw, Tw)
+        net.train(hXw, hTw, 1, sched, opt, B, loss_fn)
+        hX, hT = host_dataset(Xk, Tk)
+        net.prepare(hX, hT, loss_fn)                          # stream mode: only sizes the index buffers; the data stays on the host
+        times, tot = [], 0.0
+        while True:
+            ctx.sync()
+            _lib.check(_lib.lib.okl_barrier(ctx.h))
+            t0 = time.perf_counter()
+            net.train(hX, hT, 1, sched, opt, B, loss_fn)
+            ctx.sync()
+            v = C_double(time.perf_counter() - t0)
+            _lib.check(_lib.lib.okl_allreduce_max_host(ctx.h, v))
+            times.append(v.value)
+            tot += v.value
+            if tot >= min_gpu_s or len(times) >= max_repeats:
+                break
+        dt = float(np.median(times))
+        net.stream_inputs, net.sync_loss_every_step = False, False
+        t_bytes = B * 4 if w["loss"] == "ce" else int(np.prod(out_shape(name, B))) * 4
+        out["e2e"] = {"value": round(world * B * K / dt, 1), "unit": "samples/s",
+                      "h2d_bytes_per_step": int(B * np.prod(w["sample"]) * 4 + t_bytes), "d2h_bytes_per_step": 8,
+                      "ms_per_step": round(dt / K * 1e3, 4), "repeats": len(times),
+                      "api": "NeuralNetwork.train(Tensor.wrap(pinned host ndarray), ...) with stream_inputs (every step's shuffled batch "
+                             "rows are gathered host->device over PCIe from the pinned dataset, on a copy stream while the previous step "
+                             "computes - double-buffered input slots) and sync_loss_every_step (every step's loss {value, sequence "
+                             "number} is posted to pinned host memory behind its step and collected by the host one step later); "
+                             "wall clock around the whole call incl. the final sync, median of the repeats"}
+        del hX, hT, hXw, hTw
+    del tXw, tTw, tXk, tTk
+    return out
+
+
+def dp_check(okl, ctx, net, rank, world):
+    """Data-parallel self-check, printed in the JSON line: (a) after the timed run every rank must hold bit-identical parameters
+    (max over ranks of |param - rank 0's param|); (b) two train steps of a fresh CIFAR-shaped network on a small GLOBAL batch,
+    sharded over the ranks, against the single-process oracle on the whole global batch (okl.py:2930-3001 under sharding)."""
+    from okrolearn_b200 import _lib
+    from okrolearn_b200.layers import _ParamLayer
+    lib, check = _lib.lib, _lib.check
+    worst = 0.0
+    for l in net.layers:
+        if not isinstance(l, _ParamLayer):
+            continue
+        for t in l._bucket.tensors:
+            mine = okl.Tensor._empty((t.size,), np.float32)
+            check(lib.okl_d2d(ctx.h, mine._ptr_raw(), t._dptr(), t.size * 4))
+            ref = okl.Tensor._empty((t.size,), np.float32)
+            if rank == 0:
+                check(lib.okl_d2d(ctx.h, ref._ptr_raw(), mine._ptr_raw(), t.size * 4))
+            else:
+                check(lib.okl_memset(ctx.h, ref._ptr_raw(), 0, t.size * 4))
+            if world > 1:
+                check(lib.okl_allreduce_async(ctx.h, ref._ptr_raw(), t.size))      # sum with zeros elsewhere = rank 0's values
+                check(lib.okl_comm_wait(ctx.h))
+            mine._touch()
+            ref._touch()
+            worst = max(worst, float(np.max(np.abs(mine.data.astype(np.float64) - ref.data.astype(np.float64)))) if t.size else 0.0)
+    v = C_double(worst)
+    check(lib.okl_allreduce_max_host(ctx.h, v))
+    res = {"param_max_abs_diff_across_ranks": v.value}
+    # (b) small sharded run vs the oracle
+    from oracle import okl_oracle as O
+    per, steps, lr = 4, 2, 0.01
+    G = per * world
+    rng = np.random.default_rng(4321)
+    X = rng.standard_normal((steps * G, 3, 32, 32), dtype=np.float32)
+    T = rng.integers(0, 10, steps * G)
+    np.random.seed(777)
+    net2 = build_net(okl, "cifar6")
+    logging.getLogger("NeuralNetwork").setLevel(logging.CRITICAL)
+    W0 = [np.array(t.data, dtype=np.float64) for l in net2.layers if isinstance(l, _ParamLayer) for t in l._bucket.tensors[:1]]
+    # rank r owns rows [r*per, (r+1)*per) of every global batch; no shuffling (batch = shard, one batch per step and rank)
+    ce = okl.CrossEntropyLoss()
+    for s_ in range(steps):
+        xs = X[s_ * G + rank * per: s_ * G + (rank + 1) * per]
+        ts = T[s_ * G + rank * per: s_ * G + (rank + 1) * per]
+        out = net2._forward(okl.Tensor(xs), _fast=True)
+        ce.forward(out, okl.Tensor(ts))
+        net2._backward(ce.backward(out, None), lr)
+    got = [np.array(t.data, dtype=np.float64) for l in net2.layers if isinstance(l, _ParamLayer) for t in l._bucket.tensors[:1]]
+    worst_rel = 0.0
+    if rank == 0:
+        ol = []
+        it = iter(W0)
+        for c in [(3, 64), (64, 64), None, (64, 128), (128, 128), None, (128, 256), (256, 256), None]:
+            ol += [O.OracleMaxPool(2, 2)] if c is None else [O.OracleConv(next(it), np.zeros((c[1], 1)), 1, 1, fast=True), O.OracleReLU()]
+        ol += [O.OracleFlatten(), O.OracleDense(next(it), np.zeros((1, 10))), O.OracleSoftmax()]
+        on = O.OracleNetwork(ol)
+        for s_ in range(steps):
+            on.train_step(X[s_ * G:(s_ + 1) * G].astype(np.float64), T[s_ * G:(s_ + 1) * G], O.OracleCrossEntropy(), lr)
+        refs = [l.W for l in on.layers if hasattr(l, "W")]
+        for a, b_, w0 in zip(got, refs, W0):
+            # relative error of the parameter UPDATE (W - W0): the quantity the sharded gradients determine
+            den = max(float(np.max(np.abs(b_ - w0))), 1e-30)
+            worst_rel = max(worst_rel, float(np.max(np.abs((a - w0) - (b_ - w0)))) / den)
+    res.update({"oracle_2step_update_max_rel": worst_rel, "global_batch": G, "steps": steps, "max_rel": worst_rel,
+                "what": "(a) |param - rank0 param| after the timed run, max over all parameters and ranks; (b) 2 train steps of the "
+                        "CIFAR-shaped net on a global batch sharded over the ranks vs the single-process fp64 oracle on the whole "
+                        "batch: max over layers of max|dW_dev - dW_oracle| / max|dW_oracle| of the parameter update"})
     return res
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="okl", choices=["okl", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("OKL_WORKLOAD", "mnist_cnn"), choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default=os.environ.get("OKL_PRECISION", "tf32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--workload", default=os.environ.get("OKL_WORKLOAD", "cifar6"), choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=os.environ.get("OKL_PRECISION", "bf16"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--scaling", default=os.environ.get("OKL_SCALING", "strong"), choices=["strong", "weak"],
+                    help="strong (default): the workload's batch is the GLOBAL batch, split over the ranks; weak: it is the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary BASELINE configs and the tf32/fp32 modes")
+    ap.add_argument("--no-dp-check", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     name = args.workload
     w = WORKLOADS[name]
-    B = w["batch"]
+    if args.batch:
+        B, scaling = args.batch, "weak"
+    elif args.scaling == "strong" and w["batch"] % max(world, 1) == 0:
+        B, scaling = w["batch"] // max(world, 1), "strong"
+    else:
+        B, scaling = w["batch"], "weak"
     K, W_ = max(1, args.steps), max(3, args.warmup)
     logging.getLogger("NeuralNetwork").setLevel(logging.CRITICAL)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -382,22 +627,25 @@ def main():
         peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
         peaks_src = "fallback (B200_PROFILING.md)"
     cfg = {"workload": name, "desc": w["desc"], "batch_per_gpu": B, "global_batch": B * max(world, 1),
-           "parallelism": f"dp{world}", "l2": "dataset of steps x batch samples streamed from HBM (larger than L2 at the default "
-           "--steps); weights/activations re-touched every step as in steady-state training; per-kernel roofline timings flush L2"}
+           "parallelism": f"dp{world}", "l2": "every step's activations / gradients (> 1 GB at the bench batch) exceed the 126 MB L2 and the "
+           "dataset of steps x batch samples is streamed from HBM; per-kernel roofline timings additionally report an L2-flushed time"}
 
-    # ------------------------------------------------------------------ reference arm (CPU)
+    # ------------------------------------------------------------------ reference arm (CPU): one process on the host cores
     if args.impl == "reference":
         if rank != 0:
             return 0
         cores = os.cpu_count() or 1
         budget = float(os.environ.get("OKL_REF_BUDGET_S", "150"))
-        sps, b, nsteps, dt = time_cpu(name, budget, steps=K, warmup=min(W_, 3))
+        sps, b, nsteps, dt = time_cpu(name, budget, steps=K, warmup=W_)
+        cfg["parallelism"] = f"cpu, 1 process, {cores} host cores (NumPy/OpenBLAS threads); the GPU count does not apply to this arm"
+        cfg["cpu_sample_batch"] = b
         line = {"impl": "reference", "metric": "CNN train samples/sec", "value": round(sps, 3), "unit": "samples/s", "n_gpus": args.gpus,
-                "steps": K, "warmup": min(W_, 3), "ms_per_step": round(dt / nsteps * 1e3, 3), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "steps": K, "warmup": W_, "ms_per_step": round(dt / nsteps * 1e3, 3), "higher_is_better": True,
+                "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
                 "cpu_baseline": {"value": round(sps, 3), "unit": "samples/s", "cores": cores, "kind": "port",
-                                 "sample": f"{nsteps} oracle train steps at batch {b} of {B} (per-position NumPy loops + np.vectorize "
-                                           f"ReLU as shipped; conv/pool backward = repaired loops R1-R5)"},
+                                 "sample": f"{nsteps} oracle train steps (+{W_} warm-up) at batch {b} of the workload's {w['batch']} "
+                                           f"(per-position NumPy loops + np.vectorize ReLU as shipped; conv/pool backward = repaired loops R1-R5); "
+                                           f"samples/s does not depend on the batch (per-sample Python loops)"},
                 "e2e": {"value": round(sps, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -407,102 +655,100 @@ def main():
     os.environ.setdefault("OKL_DEVICE", str(local_rank))
     os.environ["OKL_PRECISION"] = args.precision
     import okrolearn_b200.okrolearn as okl
-    from okrolearn_b200 import _lib
     from okrolearn_b200 import dist
     dist.init_data_parallel()
     ctx = okl.get_ctx()
-    np.random.seed(1234)                       # identical initial weights on every rank
-    net = build_net(okl, name)
-    logging.getLogger("NeuralNetwork").setLevel(logging.CRITICAL)      # NeuralNetwork() re-arms the logger at DEBUG
-    loss_fn = okl.CrossEntropyLoss() if w["loss"] == "ce" else okl.MSELoss()
-    lr = 1e-9 if name == "mlp8192" else 0.01      # reference init (randn * 0.1) at width 8192 needs a tiny step to stay finite
-    sched, opt = okl.LearningRateScheduler(lr), okl.SGDOptimizer(lr=lr)
-
-    # device-resident dataset: K batches (timed) and W batches (warm-up)
-    Xw, Tw = synth(name, B * W_, rank)
-    Xk, Tk = synth(name, B * K, rank)
-    tXw, tTw, tXk, tTk = okl.Tensor(Xw), okl.Tensor(Tw), okl.Tensor(Xk), okl.Tensor(Tk)
-    for t in (tXw, tXk) + (() if w["loss"] == "ce" else (tTw, tTk)):
-        t._dptr()
-    np.random.seed(99)
     # nvidia-smi is started BEFORE the warm-up and must have delivered its first sample before the timed region begins: its
-    # start-up (NVML initialisation) stalls kernel launches for tens of ms, which is as long as the whole timed region here
+    # start-up (NVML initialisation) stalls kernel launches for tens of ms
     sampler = ClockSampler(ctx.device)
     sampler.start()
-    net.train(tXw, tTw, 1, sched, opt, B, loss_fn)          # warm-up: eager step, capture, replays
-    ctx.sync()
     sampler.wait_first(3.0)
-    net.prepare(tXk, tTk, loss_fn)                            # dataset placement: inputs AND targets resident in HBM before the timed region
-    _lib.check(_lib.lib.okl_barrier(ctx.h))
-    l0 = ctx.launch_count()
-    ctx.timer_start()
-    losses = net.train(tXk, tTk, 1, sched, opt, B, loss_fn)  # exactly K steps
-    ms = ctx.timer_stop()
-    launches = ctx.launch_count() - l0
-    v = C_double(ms)
-    _lib.check(_lib.lib.okl_allreduce_max_host(ctx.h, v))
-    ms = v.value
+    main_run = run_workload(okl, ctx, name, B, K, W_, args.precision, rank, world, want_e2e=not args.no_e2e)
     clocks = sampler.stop()
-    value = world * B * K / (ms * 1e-3)
+    dpc = None
+    if world > 1 and not args.no_dp_check and name == "cifar6":
+        dpc = dp_check(okl, ctx, main_run["net"], rank, world)
+        okl.set_precision(args.precision)
+    main_run.pop("net")
 
-    # ------------------------------------------------------------------ end to end: host (pinned) -> device every step, loss read back every step
-    e2e = None
-    if not args.no_e2e:
-        net.stream_inputs, net.sync_loss_every_step = True, True
-        def host_dataset(X, T):                      # the dataset as a user would hold it for streaming: page-locked host arrays
-            pX = okl.pinned_empty(X.shape, np.float32)
-            pX[...] = X
-            if w["loss"] == "ce":
-                pT = okl.pinned_empty(T.shape, np.int32)           # class targets page-locked too, already in the device dtype
-                pT[...] = T
-                return okl.Tensor.wrap(pX), okl.Tensor.wrap(pT)
-            pT = okl.pinned_empty(T.shape, np.float32)             # regression targets are as large as the outputs: pinned too
-            pT[...] = T
-            return okl.Tensor.wrap(pX), okl.Tensor.wrap(pT)
-        hXw, hTw = host_dataset(Xw, Tw)
-        net.train(hXw, hTw, 1, sched, opt, B, loss_fn)
-        hX, hT = host_dataset(Xk, Tk)
-        net.prepare(hX, hT, loss_fn)                          # stream mode: only sizes the index buffers; the data stays on the host
-        ctx.sync()
-        _lib.check(_lib.lib.okl_barrier(ctx.h))
-        t0 = time.perf_counter()
-        net.train(hX, hT, 1, sched, opt, B, loss_fn)
-        ctx.sync()
-        dt = time.perf_counter() - t0
-        v = C_double(dt)
-        _lib.check(_lib.lib.okl_allreduce_max_host(ctx.h, v))
-        dt = v.value
-        net.stream_inputs, net.sync_loss_every_step = False, False
-        t_bytes = B * 4 if w["loss"] == "ce" else int(np.prod(out_shape(name, B))) * 4
-        e2e = {"value": round(world * B * K / dt, 1), "unit": "samples/s", "h2d_bytes_per_step": int(B * np.prod(w["sample"]) * 4 + t_bytes),
-               "d2h_bytes_per_step": 8, "ms_per_step": round(dt / K * 1e3, 4),
-               "api": "NeuralNetwork.train(Tensor.wrap(pinned host ndarray), ...) with stream_inputs (every step's shuffled batch "
-                      "rows are gathered host->device over PCIe from the pinned dataset, on a copy stream while the previous step "
-                      "computes - double-buffered input slots) and sync_loss_every_step (every step's loss {value, sequence "
-                      "number} is posted to pinned host memory behind its step and collected by the host one step later); "
-                      "wall clock around the whole call incl. the final sync"}
+    # ------------------------------------------------------------------ other precision modes of the headline workload
+    modes = {}
+    if not args.no_configs:
+        for prec in ("tf32", "fp32"):
+            if prec == args.precision:
+                continue
+            r = run_workload(okl, ctx, name, B, max(2, min(K, 10 if prec == "tf32" else 4)), 3, prec, rank, world, want_e2e=False,
+                             min_gpu_s=0.25 if prec == "tf32" else 0.1, max_repeats=8)
+            r.pop("net")
+            kk = max(2, min(K, 10 if prec == "tf32" else 4))
+            modes[prec] = {"value": round(r["value"], 1), "ms_per_step": round(r["ms_per_step"], 5), "steps": kk, "repeats": r["repeats"],
+                           "step_tflops": round(flops_per_step(name, B) * world / (r["ms_per_step"] * 1e-3) / 1e12, 2),
+                           "dtype": {"tf32": "tf32 operands, fp32 accumulate", "fp32": "fp32 FFMA (1e-5 parity mode)"}[prec]}
+        okl.set_precision(args.precision)
+
+    # ------------------------------------------------------------------ the other BASELINE configs (same process, same GPUs)
+    configs = {}
+    if not args.no_configs:
+        second = ["mnist_cnn", "conv2d_single", "conv1d_seq", "conv3d_video", "mlp8192"] if world == 1 else ["mnist_cnn", "mlp8192"]
+        for wl in second:
+            if wl == name:
+                continue
+            prec = "bf16" if wl in ("mlp8192",) else "tf32"
+            kk = {"mnist_cnn": 200, "conv2d_single": 200, "conv1d_seq": 10, "conv3d_video": 10, "mlp8192": 4}[wl]
+            try:
+                r = run_workload(okl, ctx, wl, WORKLOADS[wl]["batch"], kk, 3, prec, rank, world, want_e2e=(world == 1 and wl in ("mnist_cnn",)),
+                                 min_gpu_s=0.3, max_repeats=20)
+            except Exception as e:                               # a secondary config must never cost the headline line
+                configs[wl] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                continue
+            r.pop("net")
+            entry = {"desc": WORKLOADS[wl]["desc"], "batch_per_gpu": WORKLOADS[wl]["batch"], "scaling": "weak", "precision": prec,
+                     "value": round(r["value"], 1), "unit": "samples/s", "ms_per_step": round(r["ms_per_step"], 5), "steps": kk,
+                     "repeats": r["repeats"], "gpu_launches": r["gpu_launches"],
+                     "step_tflops": round(flops_per_step(wl, WORKLOADS[wl]["batch"]) * world / (r["ms_per_step"] * 1e-3) / 1e12, 3)}
+            if r.get("e2e"):
+                entry["e2e"] = {k_: r["e2e"][k_] for k_ in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "ms_per_step")}
+            if rank == 0 and not args.no_roofline:
+                try:
+                    rl = kernel_rooflines(okl, ctx, wl, WORKLOADS[wl]["batch"], peaks, prec)
+                    if rl:
+                        top = max(rl, key=lambda q: q["us"])
+                        entry["roofline"] = {k_: top[k_] for k_ in ("kernel", "bound", "achieved", "peak", "unit", "frac", "us", "mode")}
+                        entry["roofline_all"] = [{k_: q[k_] for k_ in ("kernel", "bound", "frac", "us", "tflops", "gbs")} for q in rl]
+                except Exception as e:
+                    entry["roofline"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+            configs[wl] = entry
+        okl.set_precision(args.precision)
 
     if rank != 0:
         return 0
-    roof_all = [] if args.no_roofline else kernel_rooflines(okl, ctx, name, B, peaks)
-    roofline = dict(max(roof_all, key=lambda r: r["us"])) if roof_all else {"bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                                     "frac": None, "traffic": None}
+    roof_all = [] if args.no_roofline else kernel_rooflines(okl, ctx, name, B, peaks, args.precision)
+    roofline = dict(max(roof_all, key=lambda r: r["us"])) if roof_all else {"bound": "tensor", "achieved": None, "peak": peaks["bf16_tflops"],
+                                                                            "unit": "TFLOP/s", "frac": None, "traffic": None}
     roofline["peak_source"] = peaks_src
+    roofline["timing"] = ROOFLINE_TIMING
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         sps, b, nsteps, dt = time_cpu(name, float(os.environ.get("OKL_CPU_BUDGET_S", "20")))
         cpu = {"value": round(sps, 3), "unit": "samples/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"{nsteps} oracle train steps at batch {b} of {B} in {dt:.1f}s (per-position NumPy loops + np.vectorize ReLU "
+               "sample": f"{nsteps} oracle train steps at batch {b} of {w['batch']} in {dt:.1f}s (per-position NumPy loops + np.vectorize ReLU "
                          f"as shipped; conv/pool backward = repaired loops R1-R5)"}
     flops = flops_per_step(name, B)
-    line = {"metric": "CNN train samples/sec", "value": round(value, 1), "unit": "samples/s", "n_gpus": world, "steps": K,
-            "warmup": W_, "ms_per_step": round(ms / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    step_tflops = flops * world / (main_run["ms_per_step"] * 1e-3) / 1e12
+    tensor_peak = {"fp32": 74.5, "tf32": peaks["bf16_tflops"] / 2, "bf16": peaks["bf16_tflops"]}[args.precision]
+    line = {"metric": "CNN train samples/sec", "value": round(main_run["value"], 1), "unit": "samples/s", "n_gpus": world, "steps": K,
+            "warmup": W_, "ms_per_step": round(main_run["ms_per_step"], 5), "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": {"fp32": "f32", "tf32": "tf32 (fp32 storage, fp32 accumulate)", "bf16": "bf16 (fp32 accumulate)"}[args.precision],
-            "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": main_run.get("e2e"), "gpu_launches": main_run["gpu_launches"],
+            "repeats": main_run["repeats"], "region_ms": main_run["region_ms"],
             "roofline": roofline, "roofline_all": roof_all, "cpu_baseline": cpu,
-            "step_tflops": round(flops * world / (ms / K * 1e-3) / 1e12, 3), "final_loss": float(losses[-1]) if losses else None,
+            "step_tflops": round(step_tflops, 3), "step_frac_of_tensor_peak": round(step_tflops / world / tensor_peak, 4),
+            "conv_tflops_vs_tensor_peak": {"whole_step_tflops_per_gpu": round(step_tflops / world, 2), "peak": tensor_peak,
+                                           "frac": round(step_tflops / world / tensor_peak, 4), "peak_source": peaks_src},
+            "modes": modes, "configs": configs, "dp_check": dpc, "final_loss": main_run["final_loss"],
             "timing": "CUDA events on the library's compute stream around K steps of NeuralNetwork.train on an HBM-resident "
-                      "dataset, max over ranks; barrier + sync on both sides"}
+                      "dataset, max over ranks, barrier + sync on both sides; the K-step region is repeated until >= 0.5 s of device "
+                      "time and the median region is reported (repeats, region_ms)"}
     print(json.dumps(line))
     return 0
 

@@ -430,14 +430,17 @@ class NeuralNetwork:
         losses = []
         # parameters / accumulated gradients the user assigned on the host since the last step (``layer.weights.data = ...``,
         # ``.grad = None``, ``load``) must be on the device before a captured step is replayed - replay touches no Python state
-        for layer in self.layers:
-            b = getattr(layer, "_bucket", None)
-            if b is not None and getattr(b, "ready", False):
-                for t in b.tensors:
-                    t._dptr(NCX)
-                    if getattr(t, "_bf16", None) is not None:
-                        t._b16()
-                b._sync_user_grads()
+        def flush_host_params():
+            for layer in self.layers:
+                b = getattr(layer, "_bucket", None)
+                if b is not None and getattr(b, "ready", False):
+                    for t in b.tensors:
+                        t._dptr(NCX)
+                        if getattr(t, "_bf16", None) is not None:
+                            t._b16()
+                    b._sync_user_grads()
+        flush_host_params()
+        epoch_hooks = bool(self.hooks.get('pre_epoch') or self.hooks.get('post_epoch'))
         fast = not self._observed()
         graph_ok = (fast and self.use_graph and not any(hasattr(l, 'parameters') for l in self.layers) and clip_grad is None
                     and hasattr(type(loss_function), "_loss_accum"))
@@ -453,14 +456,13 @@ class NeuralNetwork:
         # `stream_inputs`, straight from page-locked host memory over PCIe (the host->device copy is then inside the step).
         # The reordering of the caller's tensors (okl.py:2959-2960) is applied lazily when `.data` is next read.
         pend_x, pend_t = getattr(inputs, "_lazy_perm", None), getattr(targets, "_lazy_perm", None)
-        if pend_x is not None and pend_t is not None and np.array_equal(pend_x, pend_t):
+        if (pend_x is not None and pend_t is not None and len(pend_x) == num_samples == targets.shape[0] and
+                np.array_equal(pend_x, pend_t)):
             perm_total = pend_x.copy()                                   # storage order still predates an earlier train()
             inputs._lazy_perm = targets._lazy_perm = None
         else:
-            if pend_x is not None:
-                _ = inputs.data
-            if pend_t is not None:
-                _ = targets.data
+            inputs._apply_lazy_perm()                                    # device row gather / host fancy index, whichever holds the data
+            targets._apply_lazy_perm()
             perm_total = np.arange(num_samples)
         keep = []
         if stream:
@@ -499,7 +501,8 @@ class NeuralNetwork:
         loss_key = type(loss_function) if type(loss_function) in (CrossEntropyLoss, MSELoss) else id(loss_function)
         skey = (batch_size, sample_shape, t_shape, loss_key, tuple(id(l) for l in self.layers), fast,
                 self.fuse_activations, self.skip_input_grad, ctx.precision, bool(self.prefetch_batches), self.fuse_head,
-                self.fuse_conv_pool, self.use_aux_lanes, self.early_exchange, ctx.nranks)
+                self.fuse_conv_pool, self.use_aux_lanes, self.early_exchange, ctx.nranks,
+                float(self.temperature))         # 1/temperature is baked into the captured step by value
         st = self._graphs.pop(skey, None)
         if st is None:
             st = _StepState(ctx, batch_size, sample_shape, t_row)
@@ -548,6 +551,8 @@ class NeuralNetwork:
 
         for epoch in range(epochs):
             self._run_hooks('pre_epoch', epoch, epochs)
+            if epoch_hooks:                          # an epoch hook may have assigned layer.weights.data / .grad on the host
+                flush_host_params()
             epoch_start_time = time.time()
             current_lr = lr_scheduler.step(epoch)
             if hasattr(optimizer, 'param_groups'):

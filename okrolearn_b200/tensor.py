@@ -15,6 +15,7 @@ Semantics that differ from a plain ndarray attribute, by construction:
 from __future__ import annotations
 
 import ctypes as C
+import zlib
 
 import numpy as np
 
@@ -168,13 +169,20 @@ class Tensor:
         return _numel(self._shape)
 
     # ------------------------------------------------------------------ host mirror
+    _SIG_FULL_BYTES = 32 << 20
+
     def _sig(self, a):
+        """Signature of a host snapshot handed out by ``.data`` (checked on the next device use to catch in-place edits such as
+        ``layer.weights.data[i, j] = 0``).  Up to 32 MiB: CRC-32 of every byte - any edit is seen.  Larger arrays (datasets): the
+        full float64 sum plus a strided sample - an edit that preserves both goes unnoticed; assign through ``t.data = arr`` there."""
         if a.size == 0:
-            return 0.0
+            return 0
+        if a.nbytes <= self._SIG_FULL_BYTES and a.dtype != object:
+            return zlib.crc32(memoryview(np.ascontiguousarray(a)).cast("B"))
         flat = a.reshape(-1)
-        step = max(1, flat.size // 1024)
+        step = max(1, flat.size // 4096)
         with np.errstate(all="ignore"):
-            return float(np.sum(flat[::step].astype(np.float64)) + float(flat[-1]))
+            return (float(np.sum(flat, dtype=np.float64)), float(np.sum(flat[::step].astype(np.float64)) + float(flat[-1])))
 
     def _fetch(self):
         ctx = get_ctx()
@@ -213,10 +221,7 @@ class Tensor:
     @property
     def data(self):
         self._materialize()
-        perm = getattr(self, "_lazy_perm", None)
-        if perm is not None:                 # train() reordered the caller's dataset (okl.py:2959-2960); applied on first read
-            self._lazy_perm = None
-            self.data = np.asarray(self.data)[perm]
+        self._apply_lazy_perm()
         if self._dev_valid:
             ctx = get_ctx()
             if self._host is None or self._host_stamp != (self._dev_ver, ctx.epoch):
@@ -236,6 +241,34 @@ class Tensor:
         self._np_dtype = arr.dtype
         self._dev_valid = False
         self._exposed_sig = None
+        self._lazy_perm = None               # a pending reorder belonged to the data that was just replaced
+
+    def _apply_lazy_perm(self):
+        """train() reorders the caller's dataset every epoch (okl.py:2959-2960).  Here the reorder is recorded as a pending row
+        permutation and applied on the first use of the tensor by ANY consumer - host (``.data``) or device (``_dptr``: a row
+        gather on the device, no host round trip) - so both always see the same, reference-ordered rows."""
+        perm = getattr(self, "_lazy_perm", None)
+        if perm is None:
+            return
+        self._lazy_perm = None
+        rows = self._shape[0] if self._shape else 0
+        if perm.shape[0] != rows or rows == 0:
+            return
+        if self._dev_valid and self._buf is not None and not self._bound:
+            ctx = get_ctx()
+            idx = _DevBuf(ctx, rows * 4)
+            p64 = np.ascontiguousarray(perm, dtype=np.int64)
+            check(lib.okl_h2d_i32(ctx.h, idx.ptr, p64.ctypes.data, rows, _lib.I64))
+            nb = _DevBuf(ctx, max(self.size, 1) * 4)
+            check(lib.okl_gather_rows(ctx.h, nb.ptr, self._ptr_raw(), idx.ptr, rows, self.size // rows))
+            self._buf, self._off = nb, 0
+            self._touch()                    # host mirror (if any) is stale now; re-fetched on the next .data read
+            del idx
+        else:
+            host = self._host if self._host is not None else self.data
+            self._host = np.asarray(host)[perm]
+            self._dev_valid = False
+            self._exposed_sig = None
 
     def to_numpy(self):
         return self.data
@@ -284,6 +317,7 @@ class Tensor:
     def _dptr(self, layout=None):
         """Device pointer of an up-to-date fp32 copy, in ``layout`` (NCX/NXC) when given."""
         self._materialize()
+        self._apply_lazy_perm()
         if self._dev_valid and self._exposed_sig is not None and self._host is not None:
             if self._sig(self._host) != self._exposed_sig:      # the snapshot handed out by .data was mutated in place
                 self._dev_valid = False

@@ -388,3 +388,107 @@ def test_host_side_parameter_edits_reach_replayed_graphs(okl):
     assert np.array_equal(np.array(lossA2), np.array(lossB)) and np.array_equal(np.array(lossA1), np.array(lossB))
     for a, b in ((convA.filters, convB.filters), (d1A.weights, d1B.weights), (d2A.weights, d2B.weights), (d2A.biases, d2B.biases)):
         assert np.array_equal(a.data, b.data)
+
+
+# ---------------------------------------------------------------------------------------------- round-2 regressions
+def _small_dense(okl, seed=3):
+    rng = np.random.default_rng(seed)
+    g = {"Wa": rng.standard_normal((6, 8)) * 0.3, "Wb": rng.standard_normal((8, 3)) * 0.3}
+    return dense_net(okl, g) + (g,)
+
+
+def test_device_consumers_see_the_reordered_dataset_after_train(okl):
+    """okl.py:2959-2960 permutes inputs.data / targets.data eagerly, so ``net.forward(X)`` after ``train`` lines up with
+    ``T.data``.  Here the reorder is pending until first use - and a DEVICE consumer (forward) must honour it as well as .data."""
+    net, d1, d2, g = _small_dense(okl)
+    rng = np.random.default_rng(0)
+    X0, T0 = rng.standard_normal((25, 6)), rng.integers(0, 3, 25)
+    X, T = okl.Tensor(X0.copy()), okl.Tensor(T0.copy())
+    np.random.seed(4)
+    net.train(X, T, 2, okl.LearningRateScheduler(0.05), okl.SGDOptimizer(lr=0.05), 10, okl.CrossEntropyLoss())
+    out_dev = net.forward(X).data                     # device consumer first: no .data read of X before it
+    np.random.seed(4)
+    perm = np.arange(25)
+    for _ in range(2):
+        idx = np.arange(25)
+        np.random.shuffle(idx)
+        perm = perm[idx]
+    assert rel_err(X.data, X0[perm]) < 1e-6 and np.array_equal(np.asarray(T.data).astype(int), T0[perm])
+    on = O.OracleNetwork([O.OracleDense(d1.weights.data, d1.biases.data), O.OracleTanh(), O.OracleDense(d2.weights.data, d2.biases.data),
+                          O.OracleSoftmax()])
+    assert rel_err(out_dev, on.forward(X0[perm])) < 2e-5
+    # predictions and labels are paired the way the reference pairs them
+    assert out_dev.shape[0] == np.asarray(T.data).shape[0]
+
+
+def test_data_setter_drops_a_pending_reorder(okl):
+    net, d1, d2, g = _small_dense(okl)
+    rng = np.random.default_rng(1)
+    X, T = okl.Tensor(rng.standard_normal((25, 6))), okl.Tensor(rng.integers(0, 3, 25))
+    net.train(X, T, 1, okl.LearningRateScheduler(0.05), okl.SGDOptimizer(lr=0.05), 10, okl.CrossEntropyLoss())
+    new = rng.standard_normal((12, 6))                # smaller dataset on the same Tensor objects
+    X.data = new
+    assert np.array_equal(X.data, new)                # not shuffled by the stale permutation
+    T.data = rng.integers(0, 3, 12)
+    losses = net.train(X, T, 1, okl.LearningRateScheduler(0.05), okl.SGDOptimizer(lr=0.05), 5, okl.CrossEntropyLoss())
+    assert np.isfinite(losses).all()
+    # only ONE of the two replaced: the other's pending order must be applied, not reused for both
+    X2, T2 = okl.Tensor(rng.standard_normal((20, 6))), okl.Tensor(rng.integers(0, 3, 20))
+    net.train(X2, T2, 1, okl.LearningRateScheduler(0.05), okl.SGDOptimizer(lr=0.05), 10, okl.CrossEntropyLoss())
+    t_after = np.asarray(T2.data).copy()
+    X2.data = rng.standard_normal((20, 6))
+    keep = np.asarray(X2.data).copy()
+    np.random.seed(8)
+    net.train(X2, T2, 1, okl.LearningRateScheduler(0.05), okl.SGDOptimizer(lr=0.05), 10, okl.CrossEntropyLoss())
+    np.random.seed(8)
+    idx = np.arange(20)
+    np.random.shuffle(idx)
+    assert rel_err(X2.data, keep[idx]) < 1e-6 and np.array_equal(np.asarray(T2.data), t_after[idx])
+
+
+def test_temperature_change_is_not_served_from_a_stale_graph(okl):
+    rng = np.random.default_rng(2)
+    X0, T0 = rng.standard_normal((20, 6)), rng.integers(0, 3, 20)
+    res = {}
+    for mode in ("graph", "eager"):
+        net, d1, d2, g = _small_dense(okl)
+        net.use_graph = mode == "graph"
+        for temp in (1.0, 2.0):
+            net.set_temperature(temp)
+            np.random.seed(3)
+            net.train(okl.Tensor(X0.copy()), okl.Tensor(T0.copy()), 2, okl.LearningRateScheduler(0.05), okl.SGDOptimizer(lr=0.05), 10,
+                      okl.CrossEntropyLoss())
+        res[mode] = (d1.weights.data.copy(), d2.weights.data.copy())
+    assert rel_err(res["graph"][0], res["eager"][0]) < 1e-6 and rel_err(res["graph"][1], res["eager"][1]) < 1e-6
+
+
+def test_inplace_edit_of_any_element_reaches_the_device(okl):
+    """``layer.weights.data[i, j] = 0`` on the array returned by ``.data`` (the reference's live array) - every element counts."""
+    lay = okl.DenseLayer(300, 200)                    # 60 000 elements: most are not on a 1024-point sample grid
+    x = okl.Tensor(np.ones((1, 300)))
+    lay.forward(x).data
+    w = lay.weights.data
+    w[137, 91] += 5.0                                 # touches neither a strided sample nor the last element
+    y = lay.forward(x).data
+    assert abs(y[0, 91] - (w[:, 91].sum())) < 1e-3
+
+
+def test_epoch_hook_assignment_survives_graph_replay(okl):
+    rng = np.random.default_rng(5)
+    X0, T0 = rng.standard_normal((20, 6)), rng.integers(0, 3, 20)
+    res = {}
+    for mode in ("graph", "eager"):
+        net, d1, d2, g = _small_dense(okl)
+        net.use_graph = mode == "graph"
+        Wnew = rng.standard_normal((8, 3)) * 0.2 if mode == "graph" else res["_W"]
+        res["_W"] = Wnew
+
+        def hook(epoch, epochs, _d2=d2, _W=Wnew):
+            if epoch == 1:
+                _d2.weights.data = _W.copy()
+        net.add_hook("pre_epoch", hook)
+        np.random.seed(6)
+        net.train(okl.Tensor(X0.copy()), okl.Tensor(T0.copy()), 3, okl.LearningRateScheduler(0.05), okl.SGDOptimizer(lr=0.05), 10,
+                  okl.CrossEntropyLoss())
+        res[mode] = (d1.weights.data.copy(), d2.weights.data.copy())
+    assert rel_err(res["graph"][0], res["eager"][0]) < 1e-6 and rel_err(res["graph"][1], res["eager"][1]) < 1e-6
