@@ -279,7 +279,24 @@ def conv_cases(okl, ctx, nd, N, Cc, Oc, sp, k, pad, relu, label, prec, need_dx=T
     es = 2 if getattr(lay, "_bf16_path", False) else 4
     xb, yb, wb = N * Cc * int(np.prod(sp)), N * Oc * So, Oc * Cc * taps
     dx = okl.Tensor._empty(x.shape, np.float32, layout=xl)
-    if getattr(lay, "_bf16_path", False):
+    if getattr(lay, "_conv2", False):
+        # second-generation BF16 path (okl_conv_tc.cu): every operand and result is channels-last bf16, exactly the calls the layer makes
+        w2, wf = lay._filter_banks(d)
+        x16, g16 = x._b16(_lib.NXC), g._b16(_lib.NXC)
+        y16, dx16 = okl.Tensor._empty_b16(y.shape, np.float32), okl.Tensor._empty_b16(x.shape, np.float32)
+        keep_extra = (y16, dx16)
+        f_fp = lambda: check(lib.okl_conv2_fprop(ctx.h, C.byref(d), x16, w2, b.ptr(1), None, y16._bf16.ptr))                 # noqa: E731
+        f_dg = lambda: check(lib.okl_conv2_dgrad(ctx.h, C.byref(d0), g16, wf, None, dx16._bf16.ptr, x16))                     # noqa: E731
+        if _lib.HAVE_CONV2_WGRAD and lib.okl_conv2_wgrad_supported(ctx.h, C.byref(d0)):
+            f_wg = lambda: check(lib.okl_conv2_wgrad(ctx.h, C.byref(d0), x16, g16, b.grad_ptr(0), b.grad_ptr(1)))             # noqa: E731
+        else:
+            def f_wg():
+                check(lib.okl_conv_wgrad_bf16(ctx.h, C.byref(d0), x16, g16, None, b.grad_ptr(0), None))
+                check(lib.okl_channel_sum_bf16(ctx.h, g16, b.grad_ptr(1), N * So, Oc))
+        by_fp = 2.0 * (xb + wb + yb)
+        by_dg = 2.0 * (yb + wb + xb) + 2.0 * xb          # g16 + filters read, dX16 written, bf16 ReLU mask (the layer input) read
+        by_wg = 2.0 * (xb + yb) + 4.0 * wb
+    elif getattr(lay, "_bf16_path", False):
         x16, g16 = x._b16(_lib.NXC), g._b16(_lib.NXC)
         y16, dx16 = y._new_b16(), dx._new_b16()
         f_fp = lambda: check(lib.okl_conv_fprop_bf16(ctx.h, C.byref(d), x16, b.ptr(0), b.ptr(1), y._ptr_raw(), y16))        # noqa: E731
@@ -294,7 +311,7 @@ def conv_cases(okl, ctx, nd, N, Cc, Oc, sp, k, pad, relu, label, prec, need_dx=T
         f_dg = lambda: check(lib.okl_conv_dgrad(ctx.h, C.byref(d0), gp, b.ptr(0), dx._ptr_raw(), xp))                       # noqa: E731
         f_wg = lambda: check(lib.okl_conv_wgrad(ctx.h, C.byref(d0), xp, gp, b.grad_ptr(0), b.grad_ptr(1)))                  # noqa: E731
         by_fp, by_dg, by_wg = 4.0 * (xb + wb + yb), 4.0 * (yb + wb + 2 * xb), 4.0 * (xb + yb + wb)
-    keep = (lay, x, y, g, dx)
+    keep = (lay, x, y, g, dx, locals().get("keep_extra"))
     cases = [(f"{label} fprop", f_fp, fl, by_fp, keep), (f"{label} wgrad", f_wg, fl, by_wg, keep)]
     if need_dx:                                           # a network's FIRST layer never computes its input gradient (nothing reads it)
         cases.insert(1, (f"{label} dgrad", f_dg, fl, by_dg, keep))

@@ -318,6 +318,39 @@ int okl_timer_stop(okl_ctx* ctx, float* ms);     /* records, synchronises, retur
 /* write `bytes` of a scratch buffer larger than L2 (between timed iterations) */
 int okl_flush_l2(okl_ctx* ctx);
 
+/* Memory-bound companions of the BF16 tensor-core pipeline (csrc/okl_bf16_ops.cu): between tcgen05 layers activations and
+ * gradients exist as channels-last bf16 only.  okl_from_bf16: bf16 -> fp32 when a host mirror / fp32 consumer asks.
+ * okl_pool2_bf16_*: MaxPoolingLayer(2, 2) forward / backward on (N, H, W, C) bf16 (okl.py:1731-1772, tie rule R4); the backward
+ * optionally applies the preceding ReLU's backward (okl.py:107-112) and reduces the gradient it writes to db[C] (fp32), the bias
+ * gradient of the convolution in front (okl.py:870, R2).  okl_channel_sum_bf16: out[c] = sum_rows g[row, c] (bias gradients). */
+int okl_from_bf16(okl_ctx* ctx, const void* src_bf16, void* dst_f32, size_t n);
+int okl_pool2_bf16_supported(int C, int H, int W);
+int okl_pool2_bf16_fwd(okl_ctx* ctx, const void* x16, void* y16, int N, int C, int H, int W);
+int okl_pool2_bf16_bwd(okl_ctx* ctx, const void* x16, const void* g16, void* dx16, int N, int C, int H, int W, int relu_mask, void* db);
+int okl_channel_sum_bf16(okl_ctx* ctx, const void* g16, void* out, long long rows, int C);
+
+/* BF16 implicit-GEMM convolution on tcgen05, second generation (csrc/okl_conv_tc.cu): replaces the contraction of
+ * Conv1DLayer/Conv2DLayer.forward (okl.py:700-711, 801-811) and of their input-gradient loops (okl.py:722-740, 854-868 with repairs
+ * R1/R3).  Channels-last bf16 activations (N, *spatial, C), unit stride, C and O multiples of 64.  okl_conv2_filter_banks converts
+ * the fp32 master filters (O, C, *k) into the two K-major bf16 banks once per update: w2 [O][tap][C] (forward) and wf [C][tap][O],
+ * taps flipped (input gradient as a convolution of the output gradient).  y / dx (fp32) and y16 / dx16 (bf16) are both optional
+ * outputs, at least one is required; d->act may be OKL_ACT_NONE or OKL_ACT_RELU; relu_mask16 (bf16, indexed like dx) zeroes dx where
+ * it is <= 0 (backward of the ReLU that produced this layer's input). */
+int okl_conv2_supported(okl_ctx* ctx, const okl_conv_desc* d);
+int okl_conv2_filter_banks(okl_ctx* ctx, const okl_conv_desc* d, const void* W, void* w2_16, void* wf_16);
+int okl_conv2_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void* x16, const void* w2_16, const void* bias, void* y, void* y16);
+int okl_conv2_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* g16, const void* wf_16, void* dx, void* dx16, const void* relu_mask16);
+/* First layer of an image network (tiny C: C * taps < 32, e.g. Conv2DLayer(3, 64, 3, 1, 1); okl.py:790-813, 869-871): x is the fp32
+ * (N, C, H, W) batch, y16 / g16 are channels-last bf16; the im2col operand is built in shared memory in the UMMA layout and consumed
+ * by tcgen05.mma; bias and bias gradient ride in the same product as a constant-one tap. */
+int okl_conv_first_supported(okl_ctx* ctx, const okl_conv_desc* d);
+int okl_conv_first_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* W, const void* bias, void* y16);
+int okl_conv_first_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* g16, void* dW, void* db);
+/* filter gradient (okl.py:739-741, 869-871) and, optionally, the bias gradient (okl.py:721, 870 with repair R2): dW fp32 in the
+ * reference layout (O, C, *k); both operands channels-last bf16; split-K over the SMs with a fixed-order second stage. */
+int okl_conv2_wgrad_supported(okl_ctx* ctx, const okl_conv_desc* d);
+int okl_conv2_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x16, const void* g16, void* dW, void* db);
+
 /* ------------------------------------------------------------------ data-parallel gradient exchange (NCCL over NVLink) */
 int okl_comm_unique_id(void* out128);
 int okl_comm_init(okl_ctx* ctx, const void* id128, int rank, int nranks);

@@ -95,6 +95,20 @@ SIGNATURES = {
     "okl_conv_fprop_bf16": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "okl_conv_dgrad_bf16": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "okl_conv_wgrad_bf16": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
+    "okl_from_bf16": (_i, [_vp, _vp, _vp, _sz]),
+    "okl_pool2_bf16_supported": (_i, [_i, _i, _i]),
+    "okl_pool2_bf16_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
+    "okl_pool2_bf16_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "okl_channel_sum_bf16": (_i, [_vp, _vp, _vp, _ll, _i]),
+    "okl_conv2_supported": (_i, [_vp, _P(ConvDesc)]),
+    "okl_conv2_filter_banks": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp]),
+    "okl_conv2_fprop": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
+    "okl_conv2_dgrad": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
+    "okl_conv_first_supported": (_i, [_vp, _P(ConvDesc)]),
+    "okl_conv_first_fprop": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp]),
+    "okl_conv_first_wgrad": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp]),
+    "okl_conv2_wgrad_supported": (_i, [_vp, _P(ConvDesc)]),
+    "okl_conv2_wgrad": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp]),
     "okl_tc_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _i]),
     "okl_conv_out_extent": (_i, [_P(ConvDesc), _P(_i)]),
     "okl_conv_fprop": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp]),
@@ -270,6 +284,9 @@ def get_ctx() -> Context:
     if _ctx is None:
         _ctx = Context()
     return _ctx
+
+
+HAVE_CONV2_WGRAD = os.environ.get("OKL_CONV_TC2_WGRAD", "1") != "0"
 
 
 def set_precision(p):

@@ -1,0 +1,1209 @@
+// BF16 implicit-GEMM convolution on tcgen05, second generation (fprop + dgrad; okl.py:790-813, 848-883 / 700-711, 722-740).
+//
+// What the first generation (okl_tc_gemm.cu MODE 1) left on the table, measured on the CIFAR-shaped layers at batch 1024 (ncu,
+// profiles/r2_*): tensor pipe 12-29 %, L2 22-33 %, DRAM 6-33 % - nothing saturated.  The per-tile timeline showed a 128 x 64
+// tile taking 3.9 us against 0.6 us of MMA time: (1) the single TMA-producer thread did five integer divisions per k-block,
+// (2) the 11 000-instruction epilogue (run-time activation switch, scalar fall-backs) missed the instruction cache, (3) every
+// filter tap re-loaded its shifted 128-pixel activation tile (9 x 16 KB per 128 x 64 tile) and every 128-pixel tile its own copy
+// of the filter bank.  This kernel:
+//   * M = 256 pixels per CTA (two 128-row accumulators sharing every filter tile) - half the filter traffic per flop;
+//   * SLAB mode (image rows >= 8 pixels wide, tile inside one image): per (channel chunk, horizontal tap v) ONE TMA box of
+//     TH + KH - 1 input rows; the KH vertical taps are the same shared-memory slab at a row offset (a multiple of 1024 bytes, so
+//     the 128-byte-swizzle phase is unchanged) - 2.4-2.7 x less activation traffic; TMA's out-of-bounds zero fill IS the padding;
+//   * independent A (slab / tap tile) and B (filter tile) rings with their own producer warps; no division inside the k loop;
+//   * epilogue specialised at compile time (bias + optional ReLU + optional ReLU-backward mask), bf16 packed in registers, staged
+//     per warp in the swizzled layout and written with TMA STORES (cp.async.bulk.tensor ... global.shared::cta) that clip partial
+//     tiles; the fp32 copy of the output is optional (BF16-only activations between tensor-core layers);
+//   * double-buffered TMEM accumulators (2 tiles x 2 sub-tiles x BN columns) so the epilogue overlaps the next tile's MMAs.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int CT_THREADS = 384;        // warp 0: A producer, 1: MMA issuer, 2: TMEM allocator, 3: B producer, 4-11: epilogue
+constexpr int CT_A_STAGE = 40960;      // one (TH + KH - 1)-row slab (<= 320 rows of 128 B) or one 256-pixel tap tile (32 KB)
+constexpr int CT_NA = 3;
+constexpr int CT_STG = 4096;           // per epilogue warp: 32 rows x 128 B, swizzled like the TMA box it is stored from
+constexpr int CT_MAX_OC = 512;
+
+template <int BN>
+struct CtCfg {
+  static constexpr int B_STAGE = BN * 128;
+  static constexpr int NB = BN == 64 ? 6 : (BN == 128 ? 4 : 2);
+  static constexpr int ACC = (4 * BN <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS = ACC * 2 * BN;            // 256 / 512 / 512
+  static constexpr int SMEM = CT_NA * CT_A_STAGE + NB * B_STAGE + 8 * CT_STG + 512 /*barriers*/ + CT_MAX_OC * 4 /*bias*/ + 1024 /*align*/;
+};
+
+struct ConvTcParams {
+  int tiles_m, tiles_n, tiles_w, tiles_h;
+  int TW, TH, TN, tw_sh, th_sh;        // CTA tile: TW x TH pixels of TN images = 256 output pixels (all powers of two)
+  int KH, KW, cblocks, C;              // taps; 64-channel chunks of the reduction; channels of the input tensor
+  int ph, pw;
+  int slab;                            // 1: A = one slab per (chunk, v), vertical taps are row offsets into it; 0: one tile per tap
+  int sub_bytes, row_bytes, a_bytes;   // second sub-tile / one tap row inside an A stage; bytes of one A transaction
+  int OH, OW, NB, Oc;
+  int RH, RN;                          // TMA store box of one epilogue warp (32 pixels): TW x RH x RN
+  const float* bias;
+  int relu;
+  const __nv_bfloat16* mask;           // optional, indexed like the output: out = 0 where mask <= 0 (backward of a preceding ReLU)
+  int want_f32, want_b16;
+  unsigned long long* dbg;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(CT_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY16,
+               const __grid_constant__ CUtensorMap tmY32, const ConvTcParams p) {
+  using Cfg = CtCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + CT_NA * CT_A_STAGE;
+  uint8_t* sStg = sB + Cfg::NB * Cfg::B_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + 8 * CT_STG);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + CT_NA;
+  uint64_t* b_full = a_empty + CT_NA;
+  uint64_t* b_empty = b_full + Cfg::NB;
+  uint64_t* t_full = b_empty + Cfg::NB;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 0] = gtime();
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmY16);
+    tma_prefetch_desc(&tmY32);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < CT_NA; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < Cfg::NB; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  for (int i = threadIdx.x; i < CT_MAX_OC; i += CT_THREADS) bias_s[i] = (p.bias && i < p.Oc) ? __ldg(p.bias + i) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  okl_pdl_sync();
+
+  const int total = p.tiles_m * p.tiles_n;
+
+  if (warp == 0) {
+    // ===================================================================== A producer: activation slabs / tap tiles
+    if (elect_one()) {
+      int st = 0;
+      uint32_t ph_ = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int tm = w / p.tiles_n;
+        const int wt = tm % p.tiles_w, r2 = tm / p.tiles_w;
+        const int ht = r2 % p.tiles_h, ng = r2 / p.tiles_h;
+        const int w0 = wt * p.TW - p.pw, h0 = ht * p.TH - p.ph, n0 = ng * p.TN;
+        for (int cb = 0; cb < p.cblocks; cb++) {
+          for (int v = 0; v < p.KW; v++) {
+            if (p.slab) {
+              mbar_wait(&a_empty[st], ph_ ^ 1);
+              mbar_expect_tx(&a_full[st], p.a_bytes);
+              tma_load_4d(&tmA, &a_full[st], sA + st * CT_A_STAGE, cb * 64, w0 + v, h0, n0);
+              if (++st == CT_NA) { st = 0; ph_ ^= 1; }
+            } else {
+              for (int u = 0; u < p.KH; u++) {
+                mbar_wait(&a_empty[st], ph_ ^ 1);
+                mbar_expect_tx(&a_full[st], p.a_bytes);
+                tma_load_4d(&tmA, &a_full[st], sA + st * CT_A_STAGE, cb * 64, w0 + v, h0 + u, n0);
+                if (++st == CT_NA) { st = 0; ph_ ^= 1; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================================================================== B producer: one filter tile per (chunk, tap)
+    if (elect_one()) {
+      int st = 0;
+      uint32_t ph_ = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int tn = w % p.tiles_n;
+        const int n_off = tn * BN;
+        for (int cb = 0; cb < p.cblocks; cb++) {
+          for (int v = 0; v < p.KW; v++) {
+            int kcol = v * p.C + cb * 64;                 // tap (u, v) -> column (u * KW + v) * C + cb * 64 of the K-major bank
+            for (int u = 0; u < p.KH; u++, kcol += p.KW * p.C) {
+              mbar_wait(&b_empty[st], ph_ ^ 1);
+              mbar_expect_tx(&b_full[st], Cfg::B_STAGE);
+              tma_load_2d(&tmB, &b_full[st], sB + st * Cfg::B_STAGE, kcol, n_off);
+              if (++st == Cfg::NB) { st = 0; ph_ ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(1, false, false, 128, BN);
+      int sa = 0, sb = 0, acc = 0;
+      uint32_t pa = 0, pb = 0, pacc = 0;
+      bool first_tile = true;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        mbar_wait(&t_empty[acc], pacc ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * BN);
+        uint32_t accum = 0;
+        for (int cb = 0; cb < p.cblocks; cb++) {
+          for (int v = 0; v < p.KW; v++) {
+            if (p.slab) {
+              mbar_wait(&a_full[sa], pa);
+              tc_fence_after();
+              if (p.dbg && first_tile && cb == 0 && v == 0) p.dbg[blockIdx.x * 8 + 1] = gtime();
+            }
+            for (int u = 0; u < p.KH; u++) {
+              if (!p.slab) {
+                mbar_wait(&a_full[sa], pa);
+                tc_fence_after();
+              }
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+              const uint32_t a_addr = smem_u32(sA + sa * CT_A_STAGE) + (p.slab ? (uint32_t)(u * p.row_bytes) : 0u);
+              const uint64_t adesc0 = make_smem_desc(a_addr, 16, 1024, 2);
+              const uint64_t adesc1 = make_smem_desc(a_addr + (uint32_t)p.sub_bytes, 16, 1024, 2);
+              const uint64_t bdesc = make_smem_desc(smem_u32(sB + sb * Cfg::B_STAGE), 16, 1024, 2);
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                umma<1>(d0, adesc0 + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum | (uint32_t)k);
+                umma<1>(d0 + BN, adesc1 + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum | (uint32_t)k);
+              }
+              accum = 1;
+              umma_commit(&b_empty[sb]);
+              if (++sb == Cfg::NB) { sb = 0; pb ^= 1; }
+              if (!p.slab) {
+                umma_commit(&a_empty[sa]);
+                if (++sa == CT_NA) { sa = 0; pa ^= 1; }
+              }
+            }
+            if (p.slab) {
+              umma_commit(&a_empty[sa]);
+              if (++sa == CT_NA) { sa = 0; pa ^= 1; }
+            }
+          }
+        }
+        umma_commit(&t_full[acc]);
+        first_tile = false;
+        if (Cfg::ACC == 2) { if (++acc == 2) { acc = 0; pacc ^= 1; } }
+        else pacc ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue: warp ew serves sub-tile ew / 4, TMEM lanes 32 * (ew % 4) ..
+    const int ew = warp - 4, s = ew >> 2, q = ew & 3;
+    uint8_t* stg = sStg + ew * CT_STG;
+    const int pbase = s * 128 + q * 32;                   // first pixel (row of the CTA tile) of this warp
+    const int r = pbase + lane;
+    int acc = 0, dbg_tile = 0;
+    uint32_t pacc = 0;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int tm = w / p.tiles_n, tn = w - tm * p.tiles_n;
+      const int wt = tm % p.tiles_w, r2 = tm / p.tiles_w;
+      const int ht = r2 % p.tiles_h, ng = r2 / p.tiles_h;
+      const int w0 = wt * p.TW, h0 = ht * p.TH, n0 = ng * p.TN;
+      const int ch0 = tn * BN;
+      const int bh = h0 + ((pbase >> p.tw_sh) & (p.TH - 1)), bn = n0 + (pbase >> (p.tw_sh + p.th_sh));
+      const __nv_bfloat16* mrow = nullptr;
+      if (p.mask) {
+        const int rw = w0 + (r & (p.TW - 1)), rh = h0 + ((r >> p.tw_sh) & (p.TH - 1)), rn = n0 + (r >> (p.tw_sh + p.th_sh));
+        if (rw < p.OW && rh < p.OH && rn < p.NB) mrow = p.mask + (((size_t)rn * p.OH + rh) * p.OW + rw) * (size_t)p.Oc + ch0;
+      }
+      mbar_wait(&t_full[acc], pacc);
+      tc_fence_after();
+      if (p.dbg && threadIdx.x == 128 && blockIdx.x == 0 && dbg_tile < 24) p.dbg[148 * 8 + 2 * dbg_tile] = gtime();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN + s * BN);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 64; ch++) {
+        uint4 mk[8];
+        if (p.mask) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) mk[j] = mrow ? __ldg(reinterpret_cast<const uint4*>(mrow + ch * 64) + j) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        uint32_t v0[32], v1[32];
+        tmem_ld32(taddr + (uint32_t)(ch * 64), v0);
+        tmem_ld32(taddr + (uint32_t)(ch * 64 + 32), v1);
+        tmem_ld_wait();
+        const float* bz = bias_s + ch0 + ch * 64;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          float a = __uint_as_float(v0[j]) + bz[j], b = __uint_as_float(v1[j]) + bz[32 + j];
+          if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+          v0[j] = __float_as_uint(a);
+          v1[j] = __float_as_uint(b);
+        }
+        if (p.mask) {
+          // bf16 sign/zero test on the raw 16-bit patterns: value > 0  <=>  sign bit clear and not +0
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const uint32_t wds[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const uint32_t lo = wds[e] & 0xFFFFu, hi = wds[e] >> 16;
+              const int c = j * 8 + e * 2;                                   // channel inside the 64-channel chunk
+              const bool klo = (lo & 0x8000u) == 0 && (lo & 0x7FFFu) != 0, khi = (hi & 0x8000u) == 0 && (hi & 0x7FFFu) != 0;
+              if (c < 32) { if (!klo) v0[c] = 0u; if (!khi) v0[c + 1] = 0u; }
+              else { if (!klo) v1[c - 32] = 0u; if (!khi) v1[c - 31] = 0u; }
+            }
+          }
+        }
+        if (p.want_f32) {
+#pragma unroll
+          for (int half = 0; half < 2; half++) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            const uint32_t* vv = half ? v1 : v0;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ sw) << 4)) = make_uint4(vv[4 * j], vv[4 * j + 1], vv[4 * j + 2], vv[4 * j + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tmY32, stg, ch0 + ch * 64 + half * 32, w0, bh, bn);
+              tma_store_commit();
+            }
+          }
+        }
+        if (p.want_b16) {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const uint32_t* vv = j < 4 ? v0 : v1;
+            const int b = (j & 3) * 8;
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(vv[b + 2 * e]), __uint_as_float(vv[b + 2 * e + 1]));
+              pk[e] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmY16, stg, ch0 + ch * 64, w0, bh, bn);
+            tma_store_commit();
+          }
+        }
+      }
+      if (p.dbg && threadIdx.x == 128 && blockIdx.x == 0 && dbg_tile < 24) p.dbg[148 * 8 + 2 * dbg_tile + 1] = gtime();
+      dbg_tile++;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[acc]);
+      if (Cfg::ACC == 2) { if (++acc == 2) { acc = 0; pacc ^= 1; } }
+      else pacc ^= 1;
+    }
+    if (lane == 0) tma_store_wait<0>();                    // every store of this warp has been written before the CTA exits
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 3] = gtime();
+}
+
+// ------------------------------------------------------------------------------------------------ filter banks
+// w2[o][tap][c] = bf16(W[o][c][tap])           K-major bank of the forward convolution
+// wf[c][tap][o] = bf16(W[o][c][T - 1 - tap])   flipped + transposed bank: dgrad as a convolution of the output gradient
+__global__ void conv_filter_banks_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ w2, __nv_bfloat16* __restrict__ wf, int O, int C,
+                                         int T) {
+  const size_t total = (size_t)O * C * T;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    {
+      const int c = (int)(i % C);
+      const size_t r = i / C;
+      const int t = (int)(r % T), o = (int)(r / T);
+      if (w2) w2[i] = __float2bfloat16(W[((size_t)o * C + c) * T + t]);
+    }
+    {
+      const int o = (int)(i % O);
+      const size_t r = i / O;
+      const int t = (int)(r % T), c = (int)(r / T);
+      if (wf) wf[i] = __float2bfloat16(W[((size_t)o * C + c) * T + (T - 1 - t)]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*CtEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+CtEncodeFn ct_encode_fn() {
+  static CtEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<CtEncodeFn>(q);
+  }
+  return fn;
+}
+
+// 4-D map over a channels-last tensor (N, H, W, C) of `es`-byte elements: dims {C, W, H, N}, 128-byte swizzle
+int ct_map_nhwc(CUtensorMap* map, const void* base, int es, int C, int W, int H, int N, int box_c, int box_w, int box_h, int box_n) {
+  CtEncodeFn fn = ct_encode_fn();
+  if (!fn) {
+    okl_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return OKL_ERR_CUDA;
+  }
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gstride[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    okl_set_error("cuTensorMapEncodeTiled(nhwc) failed with CUresult %d (C=%d W=%d H=%d N=%d box=%d,%d,%d,%d es=%d)", (int)r, C, W, H, N, box_c,
+                  box_w, box_h, box_n, es);
+    return OKL_ERR_CUDA;
+  }
+  return OKL_OK;
+}
+
+// 2-D map over a row-major bf16 matrix [outer][inner]
+int ct_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
+  CtEncodeFn fn = ct_encode_fn();
+  if (!fn) {
+    okl_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return OKL_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {inner * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    okl_set_error("cuTensorMapEncodeTiled(2d) failed with CUresult %d (inner=%llu outer=%llu box=%ux%u)", (int)r, (unsigned long long)inner,
+                  (unsigned long long)outer, box_inner, box_outer);
+    return OKL_ERR_CUDA;
+  }
+  return OKL_OK;
+}
+
+int ct_pow2_ceil(int v) { int q = 1; while (q < v) q <<= 1; return q; }
+int ct_ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+int ct_env(const char* name, int dflt) { const char* s = getenv(name); return s && *s ? atoi(s) : dflt; }
+
+template <int BN>
+int ct_launch(okl_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty16, const CUtensorMap& ty32, const ConvTcParams& p) {
+  using Cfg = CtCfg<BN>;
+  auto kern = conv_tc_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OKL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  const int total = p.tiles_m * p.tiles_n;
+  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  okl_launch(ctx, kern, dim3(grid), dim3(CT_THREADS), Cfg::SMEM, ta, tb, ty16, ty32, p);
+  OKL_LAUNCHED(ctx, "conv_tc_kernel");
+  return OKL_OK;
+}
+
+struct CtShape { int N, C, O, H, W, KH, KW, PH, PW, OH, OW; };
+
+void ct_shape(const okl_conv_desc* d, CtShape& s) {
+  s.N = d->N; s.C = d->C; s.O = d->O;
+  if (d->nd == 1) { s.H = 1; s.W = d->in[0]; s.KH = 1; s.KW = d->k[0]; s.PH = 0; s.PW = d->p[0]; }
+  else { s.H = d->in[0]; s.W = d->in[1]; s.KH = d->k[0]; s.KW = d->k[1]; s.PH = d->p[0]; s.PW = d->p[1]; }
+  s.OH = s.H + 2 * s.PH - s.KH + 1;
+  s.OW = s.W + 2 * s.PW - s.KW + 1;
+}
+
+// y[N, OH, OW, Oc] = act(conv(x16[N, H, W, Cc], bank[Oc][T * Cc]) + bias) (* mask > 0), stride 1, padding (ph, pw), channels-last
+int conv_tc_run(okl_ctx* ctx, const void* x16, int N, int H, int W, int Cc, const void* bank, int Oc, int KH, int KW, int ph, int pw, int OH, int OW,
+                const float* bias, int relu, float* y, void* y16, const void* mask16) {
+  OKL_REQUIRE(Cc % 64 == 0 && Oc % 64 == 0 && Oc <= CT_MAX_OC, "conv_tc: channel counts must be multiples of 64 (C=%d O=%d)", Cc, Oc);
+  OKL_REQUIRE(y || y16, "conv_tc: no output requested");
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  int bn = ct_env("OKL_CT_BN", 0);
+  if (bn != 64 && bn != 128 && bn != 256) bn = Oc % 128 == 0 ? 128 : 64;
+  if (Oc % bn) bn = 64;
+  p.TW = ct_pow2_ceil(OW); if (p.TW > 32) p.TW = 32;
+  p.TH = ct_pow2_ceil(OH); if (p.TH > 256 / p.TW) p.TH = 256 / p.TW;
+  p.TN = 256 / (p.TW * p.TH);
+  p.tw_sh = ct_ilog2(p.TW); p.th_sh = ct_ilog2(p.TH);
+  p.tiles_w = (OW + p.TW - 1) / p.TW; p.tiles_h = (OH + p.TH - 1) / p.TH;
+  const int tiles_ng = (N + p.TN - 1) / p.TN;
+  p.tiles_m = p.tiles_w * p.tiles_h * tiles_ng;
+  p.tiles_n = Oc / bn;
+  p.KH = KH; p.KW = KW; p.cblocks = Cc / 64; p.C = Cc; p.ph = ph; p.pw = pw;
+  p.row_bytes = p.TW * 128;
+  p.slab = (p.TN == 1 && KH > 1 && p.TW >= 8 && (p.TH + KH - 1) * p.TW * 128 <= CT_A_STAGE && ct_env("OKL_CT_SLAB", 1)) ? 1 : 0;
+  p.sub_bytes = p.slab ? (p.TH / 2) * p.row_bytes : 128 * 128;
+  p.a_bytes = p.slab ? (p.TH + KH - 1) * p.row_bytes : 256 * 128;
+  p.OH = OH; p.OW = OW; p.NB = N; p.Oc = Oc;
+  p.RH = p.TH < 32 / p.TW ? p.TH : 32 / p.TW; if (p.RH < 1) p.RH = 1;
+  p.RN = 32 / (p.TW * p.RH);
+  p.bias = bias; p.relu = relu; p.mask = (const __nv_bfloat16*)mask16;
+  p.want_f32 = y ? 1 : 0; p.want_b16 = y16 ? 1 : 0;
+  p.dbg = (unsigned long long*)ctx->tc_dbg;
+  CUtensorMap ta, tb, ty16, ty32;
+  int s = ct_map_nhwc(&ta, x16, 2, Cc, W, H, N, 64, p.TW, p.slab ? p.TH + KH - 1 : p.TH, p.TN);
+  if (s != OKL_OK) return s;
+  s = ct_map_2d(&tb, bank, (uint64_t)KH * KW * Cc, (uint64_t)Oc, 64, (uint32_t)bn);
+  if (s != OKL_OK) return s;
+  // an absent output still needs a valid descriptor object (never dereferenced by the kernel): alias the other one
+  s = ct_map_nhwc(&ty16, y16 ? y16 : (const void*)y, y16 ? 2 : 4, Oc, OW, OH, N, y16 ? 64 : 32, p.TW, p.RH, p.RN);
+  if (s != OKL_OK) return s;
+  s = ct_map_nhwc(&ty32, y ? (const void*)y : y16, y ? 4 : 2, Oc, OW, OH, N, y ? 32 : 64, p.TW, p.RH, p.RN);
+  if (s != OKL_OK) return s;
+  switch (bn) {
+    case 64: return ct_launch<64>(ctx, ta, tb, ty16, ty32, p);
+    case 128: return ct_launch<128>(ctx, ta, tb, ty16, ty32, p);
+    default: return ct_launch<256>(ctx, ta, tb, ty16, ty32, p);
+  }
+}
+
+bool ct_supported(okl_ctx* ctx, const okl_conv_desc* d) {
+  if (ctx->cc < 100 || ct_env("OKL_CONV_TC2", 1) == 0) return false;
+  if (d->nd > 2 || d->x_layout != OKL_NXC || d->y_layout != OKL_NXC) return false;
+  for (int i = 0; i < d->nd; i++)
+    if (d->s[i] != 1) return false;
+  if (d->C % 64 || d->O % 64 || d->C > CT_MAX_OC || d->O > CT_MAX_OC || d->N < 1) return false;
+  CtShape s;
+  ct_shape(d, s);
+  if (s.OH < 1 || s.OW < 1 || s.KH > 7 || s.KW > 7) return false;
+  if (s.PH > s.KH - 1 || s.PW > s.KW - 1) return false;
+  return true;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ C ABI (include/okl.h)
+extern "C" int okl_conv2_supported(okl_ctx* ctx, const okl_conv_desc* d) {
+  if (!ctx || !d) return 0;
+  return ct_supported(ctx, d) ? 1 : 0;
+}
+
+extern "C" int okl_conv2_filter_banks(okl_ctx* ctx, const okl_conv_desc* d, const void* W, void* w2_16, void* wf_16) {
+  OKL_REQUIRE(ctx && d && W && (w2_16 || wf_16), "NULL argument");
+  long long T = 1;
+  for (int i = 0; i < d->nd; i++) T *= d->k[i];
+  const size_t total = (size_t)d->O * d->C * T;
+  conv_filter_banks_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>((const float*)W, (__nv_bfloat16*)w2_16, (__nv_bfloat16*)wf_16, d->O,
+                                                                                 d->C, (int)T);
+  OKL_LAUNCHED(ctx, "conv_filter_banks");
+  return OKL_OK;
+}
+
+extern "C" int okl_conv2_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void* x16, const void* w2_16, const void* bias, void* y, void* y16) {
+  OKL_REQUIRE(ctx && d && x16 && w2_16 && (y || y16), "NULL argument");
+  OKL_REQUIRE(ct_supported(ctx, d), "okl_conv2_fprop: unsupported shape / layout");
+  OKL_REQUIRE(d->act == OKL_ACT_NONE || d->act == OKL_ACT_RELU, "okl_conv2_fprop: only ReLU can be fused (act=%d)", d->act);
+  CtShape s;
+  ct_shape(d, s);
+  return conv_tc_run(ctx, x16, s.N, s.H, s.W, s.C, w2_16, s.O, s.KH, s.KW, s.PH, s.PW, s.OH, s.OW, (const float*)bias, d->act == OKL_ACT_RELU ? 1 : 0,
+                     (float*)y, y16, nullptr);
+}
+
+extern "C" int okl_conv2_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* g16, const void* wf_16, void* dx, void* dx16,
+                               const void* relu_mask16) {
+  OKL_REQUIRE(ctx && d && g16 && wf_16 && (dx || dx16), "NULL argument");
+  OKL_REQUIRE(ct_supported(ctx, d), "okl_conv2_dgrad: unsupported shape / layout");
+  CtShape s;
+  ct_shape(d, s);
+  // dx = conv(g, flip(W)^T) with padding k - 1 - p: the same kernel with the roles of C and O exchanged
+  return conv_tc_run(ctx, g16, s.N, s.OH, s.OW, s.O, wf_16, s.C, s.KH, s.KW, s.KH - 1 - s.PH, s.KW - 1 - s.PW, s.H, s.W, nullptr, 0, (float*)dx, dx16,
+                     relu_mask16);
+}
+
+// ================================================================================================ weight gradient
+// dW[o][c][u][v] = sum_{n,h,w} g[n,h,w,o] * x[n, h+u-ph, w+v-pw, c]   (okl.py:739-741, 869-871: filter gradient of Conv1D / Conv2D)
+//
+// GEMM per CTA: D_u[(v, c) (M = 128), o (N = BN)] += x_slab_u^T . g over the CTA's share of 128-pixel tiles (split-K over CTAs, fixed-
+// order second-stage reduce).  Both operands are MN-major straight from the channels-last bf16 tensors: one TMA box of
+// (TH + KH - 1) input rows per (v, 64-channel chunk) - the KH vertical taps are the same slab at a row offset, each with its own
+// TMEM accumulator - and one box of the gradient tile per 64 output channels, shared by every tap of the CTA.  An M tile is two
+// 64-channel chunks; a chunk slot without data (C = 64 layers: 3 taps = 3 chunks) reads a constant all-ones region, which makes
+// row 64 of that accumulator the bias gradient for free.  The first generation re-read the gradient once per tap and N tile
+// (3.6 GB of L2 -> SM traffic on the 64 -> 64 layer at batch 1024, ncu) and was bound by exactly that.
+namespace {
+
+constexpr int WG_THREADS = 256;        // warp 0: TMA producer, 1: MMA issuer, 2: TMEM allocator, 4-7: epilogue
+constexpr int WG_SLOT = 24576;         // one activation slab: (TH + KH - 1) rows of a 128-pixel tile, 64 channels
+constexpr int WG_GCH = 16384;          // one gradient chunk: 128 pixels x 64 channels
+constexpr int WG_ONES = 32768;         // constant region of bf16 1.0 (covers the largest shifted 128-pixel view)
+constexpr int WG_PT = 128;             // pixels per k-block
+
+struct WgParams {
+  int tiles_mt, tiles_n;               // work tiles: M-tile groups x N tiles; splits CTAs each
+  int splits, ktiles;                  // pixel tiles in total
+  int tiles_w, tiles_h;
+  int TW, TH, TN, tw_sh, pimg_sh;      // pixel tile TW x TH x TN = 128; pimg_sh = log2(TW * TH)
+  int KH, KW, cpc, nchunks;            // cpc = C / 64; nchunks = KW * cpc real (v, channel-chunk) slots
+  int MT;                              // M tiles (of two chunk slots) per CTA: 1 or 2
+  int ph, pw;
+  int slab_bytes, row_bytes, img_bytes;
+  int stages, stage_bytes, nreal_max;
+  int BN, has_db;
+  float* ws;                           // [split][tile][MT * KH][128][BN]
+};
+
+template <int BN>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sSt = smem;
+  uint8_t* sOnes = sSt + p.stages * p.stage_bytes;          // after the stages: "ones - slab" is a positive leading-dimension offset
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + WG_ONES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 4;
+  uint64_t* done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmG);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  for (int i = threadIdx.x; i < WG_ONES / 16; i += WG_THREADS) reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  okl_pdl_sync();
+
+  // work decomposition: blockIdx.x = (tile, split)
+  const int tile = blockIdx.x / p.splits, split = blockIdx.x - tile * p.splits;
+  const int tmt = tile / p.tiles_n, tn = tile - tmt * p.tiles_n;
+  const int q0 = tmt * p.MT * 2;                           // first chunk slot (flattened (v, channel chunk)) of this CTA
+  int nreal = p.nchunks - q0;
+  if (nreal > p.MT * 2) nreal = p.MT * 2;
+  const int gbytes = (BN / 64) * WG_GCH;
+  const uint32_t tx_bytes = (uint32_t)(nreal * p.slab_bytes + gbytes);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int st = 0;
+      uint32_t ph_ = 0;
+      for (int kt = split; kt < p.ktiles; kt += p.splits) {
+        const int wt = kt % p.tiles_w, r2 = kt / p.tiles_w;
+        const int ht = r2 % p.tiles_h, ng = r2 / p.tiles_h;
+        const int w0 = wt * p.TW, h0 = ht * p.TH, n0 = ng * p.TN;
+        mbar_wait(&empty[st], ph_ ^ 1);
+        mbar_expect_tx(&full[st], tx_bytes);
+        uint8_t* base = sSt + st * p.stage_bytes;
+        for (int j = 0; j < nreal; j++) {
+          const int q = q0 + j, v = q / p.cpc, cc = q - v * p.cpc;
+          tma_load_4d(&tmX, &full[st], base + j * WG_SLOT, cc * 64, w0 + v - p.pw, h0 - p.ph, n0);
+        }
+        uint8_t* gb = base + p.nreal_max * WG_SLOT;
+#pragma unroll
+        for (int j = 0; j < BN / 64; j++) tma_load_4d(&tmG, &full[st], gb + j * WG_GCH, tn * BN + j * 64, w0, h0, n0);
+        if (++st == p.stages) { st = 0; ph_ ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(1, true, true, 128, BN);
+      int st = 0;
+      uint32_t ph_ = 0;
+      uint32_t accum = 0;
+      for (int kt = split; kt < p.ktiles; kt += p.splits) {
+        mbar_wait(&full[st], ph_);
+        tc_fence_after();
+        const uint32_t base = smem_u32(sSt + st * p.stage_bytes);
+        const uint32_t gb = base + (uint32_t)(p.nreal_max * WG_SLOT);
+        const uint32_t ones = smem_u32(sOnes);
+        for (int kk = 0; kk < WG_PT / 16; kk++) {
+          const int pix = kk * 16;
+          const int img = pix >> p.pimg_sh, pin = pix & ((1 << p.pimg_sh) - 1);
+          const uint32_t off0 = (uint32_t)(img * p.img_bytes + (pin >> p.tw_sh) * p.row_bytes + (pin & (p.TW - 1)) * 128);
+          const uint64_t bdesc = make_smem_desc(gb + (uint32_t)(kk * 2048), WG_GCH, 1024, 2);
+          for (int t = 0; t < p.MT; t++) {
+            if (2 * t >= nreal + p.has_db) break;          // nothing (not even the bias-gradient slot) lives in this M tile
+            // chunk slots 2t and 2t+1 of this CTA: real slabs or the ones region
+            const bool r0 = 2 * t < nreal, r1 = 2 * t + 1 < nreal;
+            const uint32_t a0 = r0 ? base + (uint32_t)(2 * t * WG_SLOT) : ones;
+            const uint32_t a1 = r1 ? base + (uint32_t)((2 * t + 1) * WG_SLOT) : (r0 ? ones : ones + 1024u);
+            const uint32_t lbo = a1 - a0;                  // same for every tap and k group (offsets are added to the start address)
+            for (int u = 0; u < p.KH; u++) {
+              const uint32_t off = off0 + (uint32_t)(u * p.row_bytes);
+              const uint64_t adesc = make_smem_desc(a0 + off, lbo, 1024, 2);
+              umma<1>(tmem_base + (uint32_t)((t * p.KH + u) * BN), adesc, bdesc, idesc, accum);
+            }
+          }
+          accum = 1;
+        }
+        umma_commit(&empty[st]);
+        if (++st == p.stages) { st = 0; ph_ ^= 1; }
+      }
+      umma_commit(done);
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue: accumulators -> fp32 partials of this (tile, split)
+    const int q = warp & 3;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const bool any = split < p.ktiles;
+    const int nacc = p.MT * p.KH;
+    float* dst0 = p.ws + (((size_t)split * (p.tiles_mt * p.tiles_n) + tile) * nacc) * (size_t)(128 * BN);
+    for (int a = 0; a < nacc; a++) {
+      if (2 * (a / p.KH) >= nreal + p.has_db) break;       // M tiles the MMA loop skipped
+      float* row = dst0 + ((size_t)a * 128 + q * 32 + lane) * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        if (any) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c), v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(row + c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// dW[o][c][u][v] = sum_split ws[split][tile][t * KH + u][m][o'] ; db[o] from the ones slot.  One thread per (q, m64, u, o): consecutive
+// threads walk o (the contiguous dimension of the partials).
+__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dW, float* __restrict__ db, int O, int C, int KH, int KW,
+                                         int cpc, int nchunks, int MT, int BN, int tiles_mt, int tiles_n, int splits) {
+  const int nq = nchunks + (db ? 1 : 0);
+  const size_t total = (size_t)nq * 64 * KH * O;
+  const int nacc = MT * KH;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i % O);
+    size_t r = i / O;
+    const int u = (int)(r % KH); r /= KH;
+    const int m64 = (int)(r % 64);
+    const int q = (int)(r / 64);
+    const bool is_db = q == nchunks;
+    if (is_db && (m64 != 0 || u != 0)) continue;
+    const int tmt = q / (2 * MT), slot = q - tmt * 2 * MT, t = slot >> 1, j = slot & 1;
+    const int tn = o / BN, on = o - tn * BN;
+    const int tile = tmt * tiles_n + tn;
+    const size_t stride = (size_t)(tiles_mt * tiles_n) * nacc * 128 * BN;
+    const float* src = ws + (((size_t)tile * nacc + (t * KH + u)) * 128 + (j * 64 + m64)) * (size_t)BN + on;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) acc[e] = 0.f;
+    int k = 0;
+    for (; k + 7 < splits; k += 8) {                         // eight independent loads in flight per thread (the loop is pure latency)
+      float t[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) t[e] = __ldcs(src + (size_t)(k + e) * stride);
+#pragma unroll
+      for (int e = 0; e < 8; e++) acc[e] += t[e];
+    }
+    for (; k < splits; k++) acc[0] += __ldcs(src + (size_t)k * stride);
+    const float s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    if (is_db) db[o] = s;
+    else {
+      const int v = q / cpc, c = (q - v * cpc) * 64 + m64;
+      dW[(((size_t)o * C + c) * KH + u) * KW + v] = s;
+    }
+  }
+}
+
+struct WgPlan { WgParams p; int smem; bool db_fused; };
+
+bool wg_plan(okl_ctx* ctx, const okl_conv_desc* d, bool want_db, WgPlan& pl) {
+  if (!ct_supported(ctx, d) || ct_env("OKL_CONV_TC2_WGRAD", 1) == 0) return false;
+  CtShape s;
+  ct_shape(d, s);
+  // measured (batch 1024): 64-channel inputs 197 vs 321 us and 77 vs 91 us against the first-generation kernel; for C >= 128 the
+  // first generation's N = 128 / 256 tiles still win (98 / 59 / 81 us vs 137 / 96 / 133 us) - those shapes stay there for now
+  if (s.C > 64 && ct_env("OKL_WG_ALL", 0) == 0) return false;
+  WgParams& p = pl.p;
+  memset(&p, 0, sizeof(p));
+  p.TW = ct_pow2_ceil(s.OW); if (p.TW > 32) p.TW = 32;
+  if (p.TW < 8) return false;
+  p.TH = ct_pow2_ceil(s.OH); if (p.TH > WG_PT / p.TW) p.TH = WG_PT / p.TW;
+  p.TN = WG_PT / (p.TW * p.TH);
+  if (p.TW * p.TH < 16) return false;
+  p.tw_sh = ct_ilog2(p.TW); p.pimg_sh = ct_ilog2(p.TW * p.TH);
+  p.KH = s.KH; p.KW = s.KW; p.cpc = s.C / 64; p.nchunks = s.KW * p.cpc; p.ph = s.PH; p.pw = s.PW;
+  p.row_bytes = p.TW * 128;
+  p.img_bytes = (p.TH + s.KH - 1) * p.row_bytes;
+  p.slab_bytes = p.TN * p.img_bytes;
+  if (p.slab_bytes > WG_SLOT) return false;
+  p.BN = s.O % 128 == 0 ? 128 : 64;
+  if (s.KH * p.BN > 512) p.BN = 64;
+  if (s.KH * p.BN > 512) return false;
+  p.MT = (2 * s.KH * p.BN <= 512 && p.nchunks > 2 && ct_env("OKL_WG_MT", 2) >= 2) ? 2 : 1;
+  const int slots = p.MT * 2;
+  p.tiles_mt = (p.nchunks + (want_db ? 1 : 0) + slots - 1) / slots;
+  // the ones slot gives db only when a chunk slot is free anyway; otherwise db is left to the caller
+  pl.db_fused = want_db && p.tiles_mt == (p.nchunks + slots - 1) / slots;
+  if (!pl.db_fused) p.tiles_mt = (p.nchunks + slots - 1) / slots;
+  p.has_db = pl.db_fused ? 1 : 0;
+  p.tiles_n = s.O / p.BN;
+  p.nreal_max = p.nchunks < slots ? p.nchunks : slots;
+  p.stage_bytes = p.nreal_max * WG_SLOT + (p.BN / 64) * WG_GCH;
+  p.stages = (225 * 1024 - WG_ONES - 1024 - 256) / p.stage_bytes;
+  if (p.stages > 4) p.stages = 4;
+  if (p.stages < 2) return false;
+  pl.smem = WG_ONES + p.stages * p.stage_bytes + 256 + 1024;
+  p.tiles_w = (s.OW + p.TW - 1) / p.TW; p.tiles_h = (s.OH + p.TH - 1) / p.TH;
+  p.ktiles = p.tiles_w * p.tiles_h * ((s.N + p.TN - 1) / p.TN);
+  const int tiles = p.tiles_mt * p.tiles_n;
+  p.splits = ctx->sm_count / tiles;
+  if (p.splits > p.ktiles) p.splits = p.ktiles;
+  if (p.splits < 1) p.splits = 1;
+  return true;
+}
+
+template <int BN>
+int wg_launch(okl_ctx* ctx, const CUtensorMap& tx, const CUtensorMap& tg, const WgPlan& pl) {
+  auto kern = conv_wgrad_tc_kernel<BN>;
+  static int attr_smem = 0;
+  if (attr_smem < pl.smem) {
+    OKL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_smem = 227 * 1024;
+  }
+  okl_launch(ctx, kern, dim3(pl.p.tiles_mt * pl.p.tiles_n * pl.p.splits), dim3(WG_THREADS), pl.smem, tx, tg, pl.p);
+  OKL_LAUNCHED(ctx, "conv_wgrad_tc_kernel");
+  return OKL_OK;
+}
+
+}  // namespace
+
+extern "C" int okl_channel_sum_bf16(okl_ctx* ctx, const void* g16, void* out, long long rows, int C);
+
+extern "C" int okl_conv2_wgrad_supported(okl_ctx* ctx, const okl_conv_desc* d) {
+  if (!ctx || !d) return 0;
+  WgPlan pl;
+  return wg_plan(ctx, d, false, pl) ? 1 : 0;
+}
+
+// dW (fp32, reference layout (O, C, *k)); db (fp32 [O], optional): produced by the same kernel when a chunk slot is free, else by
+// okl_channel_sum_bf16 on g16
+extern "C" int okl_conv2_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x16, const void* g16, void* dW, void* db) {
+  OKL_REQUIRE(ctx && d && x16 && g16 && dW, "NULL argument");
+  WgPlan pl;
+  OKL_REQUIRE(wg_plan(ctx, d, db != nullptr, pl), "okl_conv2_wgrad: unsupported shape / layout");
+  CtShape s;
+  ct_shape(d, s);
+  WgParams& p = pl.p;
+  const size_t ws_bytes = (size_t)p.splits * p.tiles_mt * p.tiles_n * p.MT * p.KH * 128 * p.BN * sizeof(float);
+  int st = okl_ensure_workspace(ctx, ws_bytes);
+  if (st != OKL_OK) return st;
+  p.ws = (float*)ctx->workspace;
+  CUtensorMap tx, tg;
+  st = ct_map_nhwc(&tx, x16, 2, s.C, s.W, s.H, s.N, 64, p.TW, p.TH + s.KH - 1, p.TN);
+  if (st != OKL_OK) return st;
+  st = ct_map_nhwc(&tg, g16, 2, s.O, s.OW, s.OH, s.N, 64, p.TW, p.TH, p.TN);
+  if (st != OKL_OK) return st;
+  st = p.BN == 128 ? wg_launch<128>(ctx, tx, tg, pl) : wg_launch<64>(ctx, tx, tg, pl);
+  if (st != OKL_OK) return st;
+  const size_t total = (size_t)(p.nchunks + (pl.db_fused ? 1 : 0)) * 64 * s.KH * s.O;
+  conv_wgrad_reduce_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>(p.ws, (float*)dW, pl.db_fused ? (float*)db : nullptr, s.O, s.C, s.KH,
+                                                                                 s.KW, p.cpc, p.nchunks, p.MT, p.BN, p.tiles_mt, p.tiles_n, p.splits);
+  OKL_LAUNCHED(ctx, "conv_wgrad_reduce");
+  if (db && !pl.db_fused) return okl_channel_sum_bf16(ctx, g16, db, (long long)s.N * s.OH * s.OW, s.O);
+  return OKL_OK;
+}
+
+// ================================================================================================ first layer (tiny C): K = C * taps < 32
+// Conv2DLayer(3, 64, 3, 1, 1) on the input images (okl.py:790-813 / 869-871): K = 27 is far too small for a TMA-fed implicit GEMM
+// (a k-block is 64 channels of ONE tap) and the FFMA kernels it used to run on took 16 % of the CIFAR step (ncu: 202 us forward at
+// 1.3 TB/s of fp32 output, 400 us weight gradient at 9 TFLOP/s).  Here the im2col operand of a 128-pixel tile - 32 bf16 per pixel:
+// the 27 taps, a constant 1 (bias / bias gradient ride in the same product) and padding - is BUILT in shared memory by the CTA's
+// threads from a staged fp32 input patch, directly in the 128-byte-swizzled UMMA layout, and consumed by tcgen05.mma:
+//   forward : D[128 pixels, O] = patch[128, 32] . [W | b][O, 32]^T, ReLU, bf16, TMA store into the channels-last output
+//   wgrad   : D[32, O] += patch[128, 32]^T . g[128, O]  over the CTA's pixel tiles (the SAME shared-memory image, read MN-major;
+//             the gradient tile arrives by TMA), row 27 of D is the bias gradient; split-K over CTAs, fixed-order reduce.
+namespace {
+
+constexpr int F1_THREADS = 256;
+constexpr int F1_KP = 32;              // padded reduction extent (taps + ones column + zero padding)
+
+struct F1Params {
+  const float* x; const float* W; const float* bias;
+  int N, C, H, Wd, O, KH, KW, ph, pw, OH, OW;
+  int TW, TH, tw_sh, tiles_w, tiles_h, ntiles;
+  int K, relu, RH, PH, PWp;
+  float* partial;                      // wgrad: [grid][32][O]
+};
+
+// tap k -> offset of (c, u, v) inside the staged patch [C][PH][PWp]; k == K: the ones column (-1); k > K: zero (-2)
+__device__ __forceinline__ void f1_build_ktab(int* ktab, const F1Params& p) {
+  for (int k = threadIdx.x; k < F1_KP; k += blockDim.x) {
+    int off = -2;
+    if (k < p.K) {
+      const int T = p.KH * p.KW, c = k / T, t = k - c * T, u = t / p.KW, v = t - u * p.KW;
+      off = (c * p.PH + u) * p.PWp + v;
+    } else if (k == p.K) off = -1;
+    ktab[k] = off;
+  }
+}
+
+__device__ __forceinline__ void f1_load_patch(float* patch, const F1Params& p, int n, int h0, int w0) {
+  const int per_c = p.PH * p.PWp, total = p.C * per_c;
+  for (int i = threadIdx.x; i < total; i += F1_THREADS) {
+    const int c = i / per_c, r2 = i - c * per_c, r = r2 / p.PWp, col = r2 - r * p.PWp;
+    const int ih = h0 - p.ph + r, iw = w0 - p.pw + col;
+    float v = 0.f;
+    if (n < p.N && ih >= 0 && ih < p.H && iw >= 0 && iw < p.Wd) v = __ldg(p.x + (((size_t)n * p.C + c) * p.H + ih) * p.Wd + iw);
+    patch[i] = v;
+  }
+}
+
+// thread (pixel m, half): 16 of the 32 k values of row m of the 128 x 32 patch operand, as two swizzled 16-byte chunks
+__device__ __forceinline__ void f1_build_rows(uint8_t* sA, const float* patch, const int* ktab, const F1Params& p, bool pixel_ok) {
+  const int m = threadIdx.x & 127, half = threadIdx.x >> 7;
+  const int base = (m >> p.tw_sh) * p.PWp + (m & (p.TW - 1));
+#pragma unroll
+  for (int jj = 0; jj < 2; jj++) {
+    const int j = half * 2 + jj;
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      float f[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int off = ktab[j * 8 + e * 2 + h];
+        f[h] = off >= 0 ? patch[off + base] : (off == -1 && pixel_ok ? 1.f : 0.f);
+      }
+      __nv_bfloat162 t = __floats2bfloat162_rn(f[0], f[1]);
+      pk[e] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    *reinterpret_cast<uint4*>(sA + m * 128 + ((j ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+template <int O_>
+__global__ void __launch_bounds__(F1_THREADS, O_ == 64 ? 3 : 2) conv_first_fprop_kernel(const __grid_constant__ CUtensorMap tmY16, const F1Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                       // 128 rows x 128 B (first 64 B of every row used)
+  uint8_t* sB = sA + 16384;                                 // O_ rows x 128 B
+  uint8_t* sStg = sB + O_ * 128;                            // 8 warps x 4 KB
+  uint64_t* mma_done = reinterpret_cast<uint64_t*>(sStg + 8 * CT_STG);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
+  int* ktab = reinterpret_cast<int*>(mma_done + 2);
+  float* patch = reinterpret_cast<float*>(ktab + F1_KP);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(mma_done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmY16);
+  }
+  if (warp == 0) tmem_alloc<O_>(tmem_slot);
+  f1_build_ktab(ktab, p);
+  for (int i = threadIdx.x; i < O_ * F1_KP; i += F1_THREADS) {      // [W | b | 0] as bf16, K-major, swizzled
+    const int o = i / F1_KP, k = i - o * F1_KP;
+    float v = 0.f;
+    if (o < p.O) v = k < p.K ? __ldg(p.W + (size_t)o * p.K + k) : (k == p.K && p.bias ? __ldg(p.bias + o) : 0.f);
+    *reinterpret_cast<__nv_bfloat16*>(sB + o * 128 + (((k >> 3) ^ (o & 7)) << 4) + (k & 7) * 2) = __float2bfloat16(v);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t idesc = make_idesc(1, false, false, 128, O_);
+  okl_pdl_sync();
+
+  const int q = warp & 3;
+  uint8_t* stg = sStg + warp * CT_STG;
+  const uint32_t sw = (uint32_t)(lane & 7);
+  uint32_t parity = 0;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const int wt = tile % p.tiles_w, r2 = tile / p.tiles_w;
+    const int ht = r2 % p.tiles_h, n = r2 / p.tiles_h;
+    const int w0 = wt * p.TW, h0 = ht * p.TH;
+    f1_load_patch(patch, p, n, h0, w0);
+    __syncthreads();                                        // patch complete; every thread is past the previous tile's accumulator reads
+    f1_build_rows(sA, patch, ktab, p, true);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint64_t adesc = make_smem_desc(smem_u32(sA), 16, 1024, 2);
+      const uint64_t bdesc = make_smem_desc(smem_u32(sB), 16, 1024, 2);
+      umma<1>(tmem_base, adesc, bdesc, idesc, 0u);
+      umma<1>(tmem_base, adesc + 2, bdesc + 2, idesc, 1u);
+      umma_commit(mma_done);
+    }
+    mbar_wait(mma_done, parity);
+    parity ^= 1;
+    tc_fence_after();
+    // epilogue: warp -> TMEM lane quarter q (32 pixels) and every second 64-channel chunk
+    const int pbase = q * 32;
+    const int bh = h0 + (pbase >> p.tw_sh);
+#pragma unroll 1
+    for (int ch = (warp >> 2); ch < O_ / 64; ch += 2) {
+      uint32_t v0[32], v1[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 64);
+      tmem_ld32(taddr, v0);
+      tmem_ld32(taddr + 32, v1);
+      tmem_ld_wait();
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint32_t* vv = j < 4 ? v0 : v1;
+        const int b = (j & 3) * 8;
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          float a = __uint_as_float(vv[b + 2 * e]), c = __uint_as_float(vv[b + 2 * e + 1]);
+          if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+          __nv_bfloat162 t = __floats2bfloat162_rn(a, c);
+          pk[e] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(&tmY16, stg, ch * 64, w0, bh, n);
+        tma_store_commit();
+      }
+    }
+    tc_fence_before();
+  }
+  if (lane == 0) tma_store_wait<0>();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<O_>(tmem_base);
+}
+
+template <int O_>
+__global__ void __launch_bounds__(F1_THREADS, O_ == 64 ? 3 : 2) conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const F1Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int GB = (O_ / 64) * 16384;
+  uint8_t* sA = smem;                                       // 2 x 16 KB patch operands
+  uint8_t* sG = sA + 2 * 16384;                             // 2 x gradient tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 2 * GB);
+  uint64_t* g_full = bars;                                  // [2]
+  uint64_t* st_free = bars + 2;                             // [2] the MMAs that read stage s are complete
+  uint64_t* done = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  int* ktab = reinterpret_cast<int*>(bars + 6);
+  float* patch = reinterpret_cast<float*>(ktab + F1_KP);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; s++) { mbar_init(&g_full[s], 1); mbar_init(&st_free[s], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmG);
+  }
+  if (warp == 0) tmem_alloc<O_>(tmem_slot);
+  f1_build_ktab(ktab, p);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t idesc = make_idesc(1, true, true, 128, O_);
+  okl_pdl_sync();
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it++) {
+    const int s = it & 1;
+    const uint32_t use = (uint32_t)(it >> 1);               // how many times stage s has been used before
+    const int wt = tile % p.tiles_w, r2 = tile / p.tiles_w;
+    const int ht = r2 % p.tiles_h, n = r2 / p.tiles_h;
+    const int w0 = wt * p.TW, h0 = ht * p.TH;
+    if (use > 0) mbar_wait(&st_free[s], (use - 1) & 1);     // everyone: stage s (patch operand AND gradient tile) is reusable
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&g_full[s], GB);
+#pragma unroll
+      for (int j = 0; j < O_ / 64; j++) tma_load_4d(&tmG, &g_full[s], sG + s * GB + j * 16384, j * 64, w0, h0, n);
+    }
+    f1_load_patch(patch, p, n, h0, w0);
+    __syncthreads();
+    {
+      const int m = threadIdx.x & 127;
+      const bool ok = (w0 + (m & (p.TW - 1))) < p.OW && (h0 + (m >> p.tw_sh)) < p.OH && n < p.N;
+      f1_build_rows(sA + s * 16384, patch, ktab, p, ok);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_wait(&g_full[s], use & 1);
+      tc_fence_after();
+      const uint32_t a = smem_u32(sA + s * 16384), g = smem_u32(sG + s * GB);
+#pragma unroll
+      for (int kk = 0; kk < 8; kk++) {
+        // A = patch^T, MN-major: 16 pixel rows per MMA; M rows 64..127 alias an in-bounds region (their results are never read)
+        const uint64_t adesc = make_smem_desc(a + (uint32_t)(kk * 2048), 1024, 1024, 2);
+        const uint64_t bdesc = make_smem_desc(g + (uint32_t)(kk * 2048), 16384, 1024, 2);
+        umma<1>(tmem_base, adesc, bdesc, idesc, (it | kk) ? 1u : 0u);
+      }
+      umma_commit(&st_free[s]);
+    }
+  }
+  if (threadIdx.x == 0) umma_commit(done);
+  mbar_wait(done, 0);
+  tc_fence_after();
+  if (warp == 0) {                                          // TMEM lanes 0..31 = k rows
+    float* dst = p.partial + ((size_t)blockIdx.x * F1_KP + lane) * O_;
+    const bool any = (int)blockIdx.x < p.ntiles;
+#pragma unroll 1
+    for (int c = 0; c < O_; c += 32) {
+      uint32_t v[32];
+      if (any) {
+        tmem_ld32(tmem_base + (uint32_t)c, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dst + c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<O_>(tmem_base);
+}
+
+// one warp per output element: lanes stride over the CTAs' partials, fixed-order shuffle tree
+__global__ void conv_first_wgrad_reduce(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ db, int O, int Opad, int K,
+                                        int nblk) {
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (idx >= (K + 1) * O) return;
+  const int k = idx / O, o = idx - k * O;
+  float s0 = 0.f, s1 = 0.f;
+  int b = lane;
+  for (; b + 32 < nblk; b += 64) {
+    s0 += partial[((size_t)b * F1_KP + k) * Opad + o];
+    s1 += partial[((size_t)(b + 32) * F1_KP + k) * Opad + o];
+  }
+  if (b < nblk) s0 += partial[((size_t)b * F1_KP + k) * Opad + o];
+  float s = s0 + s1;
+#pragma unroll
+  for (int sft = 16; sft > 0; sft >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sft);
+  if (lane == 0) {
+    if (k < K) dW[(size_t)o * K + k] = s;
+    else if (db) db[o] = s;
+  }
+}
+
+bool f1_plan(okl_ctx* ctx, const okl_conv_desc* d, F1Params& p, int& opad) {
+  if (ctx->cc < 100 || ct_env("OKL_CONV_FIRST_TC", 1) == 0) return false;
+  if (d->nd != 2 || d->s[0] != 1 || d->s[1] != 1 || d->x_layout != OKL_NCX || d->y_layout != OKL_NXC) return false;
+  memset(&p, 0, sizeof(p));
+  p.N = d->N; p.C = d->C; p.H = d->in[0]; p.Wd = d->in[1]; p.O = d->O; p.KH = d->k[0]; p.KW = d->k[1]; p.ph = d->p[0]; p.pw = d->p[1];
+  p.K = p.C * p.KH * p.KW;
+  if (p.K + 1 > F1_KP || p.O % 64 || p.O > 256 || p.N < 1) return false;
+  opad = p.O <= 64 ? 64 : (p.O <= 128 ? 128 : 256);
+  if (opad != p.O) return false;
+  p.OH = p.H + 2 * p.ph - p.KH + 1; p.OW = p.Wd + 2 * p.pw - p.KW + 1;
+  if (p.OH < 1 || p.OW < 1) return false;
+  p.TW = ct_pow2_ceil(p.OW); if (p.TW > 32) p.TW = 32;
+  if (p.TW < 8) return false;
+  p.TH = 128 / p.TW;
+  p.tw_sh = ct_ilog2(p.TW);
+  p.tiles_w = (p.OW + p.TW - 1) / p.TW; p.tiles_h = (p.OH + p.TH - 1) / p.TH;
+  p.ntiles = p.tiles_w * p.tiles_h * p.N;
+  p.RH = 32 / p.TW;
+  p.PH = p.TH + p.KH - 1; p.PWp = p.TW + p.KW - 1;
+  if (p.C * p.PH * p.PWp * 4 > 16384) return false;
+  return true;
+}
+
+}  // namespace
+
+extern "C" int okl_conv_first_supported(okl_ctx* ctx, const okl_conv_desc* d) {
+  if (!ctx || !d) return 0;
+  F1Params p;
+  int opad;
+  return f1_plan(ctx, d, p, opad) ? 1 : 0;
+}
+
+// y16 (N, OH, OW, O) bf16 = act(conv(x (N, C, H, W) fp32, W) + b); d->act NONE or RELU
+extern "C" int okl_conv_first_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* W, const void* bias, void* y16) {
+  OKL_REQUIRE(ctx && d && x && W && y16, "NULL argument");
+  F1Params p;
+  int opad;
+  OKL_REQUIRE(f1_plan(ctx, d, p, opad), "okl_conv_first_fprop: unsupported shape / layout");
+  OKL_REQUIRE(d->act == OKL_ACT_NONE || d->act == OKL_ACT_RELU, "okl_conv_first_fprop: only ReLU can be fused");
+  p.x = (const float*)x; p.W = (const float*)W; p.bias = (const float*)bias; p.relu = d->act == OKL_ACT_RELU;
+  CUtensorMap ty;
+  int s = ct_map_nhwc(&ty, y16, 2, p.O, p.OW, p.OH, p.N, 64, p.TW, p.RH, 1);
+  if (s != OKL_OK) return s;
+  const int per_sm = opad == 64 ? 3 : 2;
+  const int grid = p.ntiles < per_sm * ctx->sm_count ? p.ntiles : per_sm * ctx->sm_count;
+  const int smem = 16384 + opad * 128 + 8 * CT_STG + 64 + F1_KP * 4 + p.C * p.PH * p.PWp * 4 + 1024;
+#define F1_FP(OO)                                                                                                     \
+  {                                                                                                                   \
+    static int set = 0;                                                                                               \
+    if (set < smem) { OKL_CHECK_CUDA(cudaFuncSetAttribute(conv_first_fprop_kernel<OO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = 100 * 1024; } \
+    okl_launch(ctx, conv_first_fprop_kernel<OO>, dim3(grid), dim3(F1_THREADS), smem, ty, p);                           \
+  }
+  if (opad == 64) F1_FP(64) else if (opad == 128) F1_FP(128) else F1_FP(256)
+#undef F1_FP
+  OKL_LAUNCHED(ctx, "conv_first_fprop");
+  return OKL_OK;
+}
+
+// dW (O, C, KH, KW) fp32 and db (O) fp32 (optional) from x (N, C, H, W) fp32 and g16 (N, OH, OW, O) bf16
+extern "C" int okl_conv_first_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* g16, void* dW, void* db) {
+  OKL_REQUIRE(ctx && d && x && g16 && dW, "NULL argument");
+  F1Params p;
+  int opad;
+  OKL_REQUIRE(f1_plan(ctx, d, p, opad), "okl_conv_first_wgrad: unsupported shape / layout");
+  p.x = (const float*)x;
+  CUtensorMap tg;
+  int s = ct_map_nhwc(&tg, g16, 2, p.O, p.OW, p.OH, p.N, 64, p.TW, p.TH, 1);
+  if (s != OKL_OK) return s;
+  const int per_sm = opad == 64 ? 3 : 2;
+  const int grid = p.ntiles < per_sm * ctx->sm_count ? p.ntiles : per_sm * ctx->sm_count;
+  s = okl_ensure_workspace(ctx, (size_t)grid * F1_KP * opad * sizeof(float));
+  if (s != OKL_OK) return s;
+  p.partial = (float*)ctx->workspace;
+  const int smem = 2 * 16384 + 2 * (opad / 64) * 16384 + 64 + F1_KP * 4 + p.C * p.PH * p.PWp * 4 + 1024;
+#define F1_WG(OO)                                                                                                     \
+  {                                                                                                                   \
+    static int set = 0;                                                                                               \
+    if (set < smem) { OKL_CHECK_CUDA(cudaFuncSetAttribute(conv_first_wgrad_kernel<OO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = 200 * 1024; } \
+    okl_launch(ctx, conv_first_wgrad_kernel<OO>, dim3(grid), dim3(F1_THREADS), smem, tg, p);                           \
+  }
+  if (opad == 64) F1_WG(64) else if (opad == 128) F1_WG(128) else F1_WG(256)
+#undef F1_WG
+  OKL_LAUNCHED(ctx, "conv_first_wgrad");
+  const int total = (p.K + 1) * p.O;
+  conv_first_wgrad_reduce<<<(total * 32 + 255) / 256, 256, 0, ctx->stream>>>(p.partial, (float*)dW, (float*)db, p.O, opad, p.K, grid);
+  OKL_LAUNCHED(ctx, "conv_first_wgrad_reduce");
+  return OKL_OK;
+}

@@ -15,6 +15,8 @@ from ._lib import lib, check, get_ctx, ConvDesc, NCX, NXC, ACT_NONE, ACT_RELU, A
 from .tensor import Tensor, _DevBuf, _numel
 
 _ALIGN = 64          # floats: parameter sub-tensors start on 256-byte boundaries inside a bucket
+# BF16 mode: tensors between tensor-core layers are stored as channels-last bf16 only (OKL_BF16_ONLY=0 restores fp32 + bf16 shadow)
+_BF16_ONLY = __import__("os").environ.get("OKL_BF16_ONLY", "1") != "0"
 
 
 def _as_tensor(x):
@@ -455,10 +457,29 @@ class _ConvBase(_ParamLayer):
                 xl = NCX
             yl = getattr(self, "_out_layout", NCX)
         d, oe = self._desc(inputs.shape, xl, yl, self._fused_act)
-        out = Tensor._empty((inputs.shape[0], self.out_channels) + oe, self._np_dtype, layout=yl)
+        oshape = (inputs.shape[0], self.out_channels) + oe
+        self._first_tc = bool(ctx.precision == _lib.BF16 and _BF16_ONLY and xl == NCX and yl == NXC and inputs.shape[0] > 0 and
+                              self._fused_act in (ACT_NONE, ACT_RELU) and lib.okl_conv_first_supported(ctx.h, C.byref(d)))
+        if self._first_tc:                       # tiny-C first layer on tcgen05: fp32 images in, channels-last bf16 out
+            out = Tensor._empty_b16(oshape, self._np_dtype, NXC)
+            check(lib.okl_conv_first_fprop(ctx.h, C.byref(d), inputs._dptr(NCX), self._bucket.ptr(0), self._bucket.ptr(1), out._bf16.ptr))
+            self._fwd_layouts, self._bf16_path, self._conv2 = (xl, yl), False, False
+            return out
         self._bf16_path = bool(ctx.precision == _lib.BF16 and xl == NXC and yl == NXC and inputs.shape[0] > 0 and
                                lib.okl_conv_bf16_supported(ctx.h, C.byref(d)))
-        if self._bf16_path:                      # activations carry channels-last bf16 shadows: 2-byte operands, no conversions
+        self._conv2 = bool(self._bf16_path and self._fused_act in (ACT_NONE, ACT_RELU) and lib.okl_conv2_supported(ctx.h, C.byref(d)))
+        if self._conv2:                          # second-generation tcgen05 kernel (okl_conv_tc.cu): slab reuse, 256-pixel tiles, TMA stores
+            w2, _ = self._filter_banks(d)
+            if _BF16_ONLY:                       # the output exists as channels-last bf16 only; fp32 is converted if somebody asks
+                out = Tensor._empty_b16(oshape, self._np_dtype, NXC)
+                check(lib.okl_conv2_fprop(ctx.h, C.byref(d), inputs._b16(NXC), w2, self._bucket.ptr(1), None, out._bf16.ptr))
+            else:
+                out = Tensor._empty(oshape, self._np_dtype, layout=yl)
+                check(lib.okl_conv2_fprop(ctx.h, C.byref(d), inputs._b16(NXC), w2, self._bucket.ptr(1), out._ptr_raw(), out._new_b16()))
+            self._fwd_layouts = (xl, yl)
+            return out
+        out = Tensor._empty(oshape, self._np_dtype, layout=yl)
+        if self._bf16_path:                    # activations carry channels-last bf16 shadows: 2-byte operands, no conversions
             check(lib.okl_conv_fprop_bf16(ctx.h, C.byref(d), inputs._b16(NXC), self._bucket.ptr(0), self._bucket.ptr(1), out._ptr_raw(),
                                           out._new_b16()))
         else:
@@ -477,10 +498,16 @@ class _ConvBase(_ParamLayer):
         if dL_dout.shape != (x.shape[0], self.out_channels) + oe:
             raise ValueError(f"dL_dout shape {dL_dout.shape} does not match the layer output {(x.shape[0], self.out_channels) + oe}")
         b = self._bucket
-        g, xp, wp = dL_dout._dptr(yl), x._dptr(xl), b.ptr(0)
         need_dx = getattr(self, "_need_dx", True)
+        if getattr(self, "_first_tc", False) and ctx.precision == _lib.BF16 and not need_dx:
+            check(lib.okl_conv_first_wgrad(ctx.h, C.byref(d), x._dptr(NCX), dL_dout._b16(NXC), b.grad_ptr(0), b.grad_ptr(1)))
+            b.step(lr, self._defer_update)
+            return None
         aux = self._aux_lane and self._defer_update and need_dx
         b16 = getattr(self, "_bf16_path", False) and ctx.precision == _lib.BF16
+        if b16 and getattr(self, "_conv2", False):
+            return self._backward_conv2(dL_dout, lr, d, need_dx, aux)
+        g, xp, wp = dL_dout._dptr(yl), x._dptr(xl), b.ptr(0)
         if b16:
             x16, g16 = x._b16(NXC), dL_dout._b16(NXC)
         dX = None
@@ -505,6 +532,58 @@ class _ConvBase(_ParamLayer):
             if aux:
                 check(lib.okl_aux_end(ctx.h))
         return dX
+
+    def _backward_conv2(self, dL_dout, lr, d, need_dx, aux):
+        """Backward of the second-generation BF16 path: every operand and result is channels-last bf16 (no fp32 activation /
+        gradient tensors at all); dX first (critical path), dW / db on the auxiliary lane."""
+        ctx = get_ctx()
+        x, b = self.inputs, self._bucket
+        x16, g16 = x._b16(NXC), dL_dout._b16(NXC)
+        dX = None
+        if need_dx:
+            if aux:
+                check(lib.okl_aux_mark(ctx.h))
+            _, wf = self._filter_banks(d)
+            mask16 = x16 if self._dx_relu_mask else None
+            if _BF16_ONLY:
+                dX = Tensor._empty_b16(x.shape, self._dx_dtype(x), NXC)
+                check(lib.okl_conv2_dgrad(ctx.h, C.byref(d), g16, wf, None, dX._bf16.ptr, mask16))
+            else:
+                dX = Tensor._empty(x.shape, self._dx_dtype(x), layout=NXC)
+                check(lib.okl_conv2_dgrad(ctx.h, C.byref(d), g16, wf, dX._ptr_raw(), dX._new_b16(), mask16))
+        if aux:
+            check(lib.okl_aux_begin(ctx.h, self._aux_lane))
+        try:
+            db_done = getattr(dL_dout, "_db_done", None) is self          # the producer of dL_dout already reduced it (pool backward)
+            rows = _numel(dL_dout.shape) // self.out_channels
+            if _lib.HAVE_CONV2_WGRAD and lib.okl_conv2_wgrad_supported(ctx.h, C.byref(d)):
+                check(lib.okl_conv2_wgrad(ctx.h, C.byref(d), x16, g16, b.grad_ptr(0), None if db_done else b.grad_ptr(1)))
+            else:
+                check(lib.okl_conv_wgrad_bf16(ctx.h, C.byref(d), x16, g16, None, b.grad_ptr(0), None))
+                if not db_done:
+                    check(lib.okl_channel_sum_bf16(ctx.h, g16, b.grad_ptr(1), rows, self.out_channels))
+            b.step(lr, True if aux else self._defer_update)
+        finally:
+            if aux:
+                check(lib.okl_aux_end(ctx.h))
+        return dX
+
+    def _filter_banks(self, d):
+        """bf16 K-major filter banks of the tcgen05 convolution - [O][tap][C] for fprop, flipped [C][tap][O] for dgrad - refreshed by
+        ONE kernel whenever the fp32 master filters changed (once per train step, after the update)."""
+        ctx = get_ctx()
+        wt = self._bucket.tensors[0]
+        wp = self._bucket.ptr(0)                                   # flushes a pending host assignment first
+        # inside a captured step the refresh is recorded once per capture (forward) and replayed with the graph; outside, a graph
+        # replay (ctx.epoch) or an update (_dev_ver) since the last refresh makes the banks stale
+        ver = ("capture", id(getattr(ctx, "_capture_keep", None)), wt._dev_ver) if ctx.capturing else (wt._dev_ver, ctx.epoch)
+        if getattr(self, "_bank_bufs", None) is None or self._bank_bufs[0].nbytes < wt.size * 2:
+            self._bank_bufs = (_DevBuf(ctx, wt.size * 2), _DevBuf(ctx, wt.size * 2))
+            self._bank_ver = None
+        if self._bank_ver != ver:
+            check(lib.okl_conv2_filter_banks(ctx.h, C.byref(d), wp, self._bank_bufs[0].ptr, self._bank_bufs[1].ptr))
+            self._bank_ver = ver
+        return self._bank_bufs[0].ptr, self._bank_bufs[1].ptr
 
     def _dx_dtype(self, x):
         return np.float64 if self._nd == 2 else (x._np_dtype if x._np_dtype in (np.float32, np.float64) else np.float64)
@@ -1451,6 +1530,7 @@ class _Pool:
         self.stride = stride
 
     _in_fused_block = False      # NeuralNetwork planner: computed inside the preceding conv's fused kernel (pure pass-through)
+    _db_sink = None              # NeuralNetwork planner: conv layer whose bias gradient = channel sums of this layer's input gradient
 
     def forward(self, inputs):
         if self._in_fused_block:
@@ -1464,6 +1544,13 @@ class _Pool:
         if H < ps or W < ps:
             raise ValueError("pooling window larger than the input")
         OH, OW = (H - ps) // st + 1, (W - ps) // st + 1
+        self._b16_path = bool(self._kind == POOL_MAX and ps == 2 and st == 2 and inputs._b16_primary and inputs._layout == NXC and
+                              lib.okl_pool2_bf16_supported(Cc, H, W))
+        if self._b16_path:                     # channels-last bf16 in, channels-last bf16 out (BF16 tensor-core pipeline)
+            out = Tensor._empty_b16((N, Cc, OH, OW), np.float64, NXC)
+            check(lib.okl_pool2_bf16_fwd(ctx.h, inputs._b16(NXC), out._bf16.ptr, N, Cc, H, W))
+            self.inputs, self.output = inputs, out
+            return out
         src = inputs._dptr()
         lay = inputs._layout
         out = Tensor._empty((N, Cc, OH, OW), np.float64, layout=lay)
@@ -1481,6 +1568,16 @@ class _Pool:
         N, Cc, H, W = x.shape
         if dL_dout.shape != self.output.shape:
             raise ValueError(f"dL_dout shape {dL_dout.shape} does not match the layer output {self.output.shape}")
+        if getattr(self, "_b16_path", False) and x._b16_primary:
+            dx = Tensor._empty_b16(x.shape, np.float64, NXC)
+            sink = self._db_sink if (self._fused_relu_bwd and self._db_sink is not None and
+                                     getattr(self._db_sink, "_conv2", False) and self._db_sink.out_channels == Cc) else None
+            check(lib.okl_pool2_bf16_bwd(ctx.h, x._b16(NXC), dL_dout._b16(NXC), dx._bf16.ptr, N, Cc, H, W, 1 if self._fused_relu_bwd else 0,
+                                         sink._bucket.grad_ptr(1) if sink is not None else None))
+            if sink is not None:
+                dx._db_done = sink                 # the convolution in front already has its bias gradient: this kernel reduced it
+            _set_input_grad(x, dx)
+            return dx
         xp = x._dptr()
         lay = x._layout
         dx = Tensor._empty(x.shape, np.float64, layout=lay)

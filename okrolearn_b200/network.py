@@ -231,6 +231,7 @@ class NeuralNetwork:
             if isinstance(l, _Pool):
                 l._fused_relu_bwd = False
                 l._in_fused_block = False
+                l._db_sink = None
             if isinstance(l, SoftmaxActivationLayer):
                 l._fused_into_prev = False
         # layout planning: a convolution that feeds (through activations / pooling) a tensor-core-eligible convolution writes
@@ -271,6 +272,10 @@ class NeuralNetwork:
             for a, b in zip(ls, ls[1:]):                 # ReLU -> MaxPool: relu' applied inside the pooling backward
                 if isinstance(a, ReLUActivationLayer) and isinstance(b, MaxPoolingLayer):
                     a._bwd_fused_into_next, b._fused_relu_bwd = True, True
+            for cv, a, b in zip(ls, ls[1:], ls[2:]):     # Conv(+ReLU fused) -> ReLU -> MaxPool: the pooling backward's output IS the
+                if (isinstance(cv, _ConvBase) and isinstance(a, ReLUActivationLayer) and a._fused_into_prev and      # conv's output gradient;
+                        isinstance(b, MaxPoolingLayer) and b._fused_relu_bwd):                                     # it also reduces it to db
+                    b._db_sink = cv
         if self.skip_input_grad and ls and isinstance(ls[0], _ParamLayer):
             ls[0]._need_dx = False
         # first block Conv2D(3x3, s1) -> ReLU -> MaxPool(2,2) with no dX needed: one fused kernel each way, the un-pooled

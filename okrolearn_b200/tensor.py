@@ -155,6 +155,30 @@ class Tensor:
         t.backward_fn = None
         return t
 
+    # ------------------------------------------------------------------ bf16-primary tensors
+    _b16_primary = False            # True: the channels-last bf16 buffer is the storage of record, fp32 is converted on demand
+
+    @classmethod
+    def _empty_b16(cls, shape, np_dtype=np.float64, layout=NXC):
+        """Uninitialised device tensor stored as bf16 ONLY (activations / gradients between tensor-core layers in BF16 mode).  An
+        fp32 view (`_ptr_raw` / `_dptr` / `.data`) is converted from it on demand and cached per device version."""
+        t = cls._view(None, 0, shape, np_dtype, bound=False)
+        t._layout = layout
+        t._b16_primary = True
+        t._bf16 = _DevBuf(get_ctx(), max(t.size, 1) * 2)
+        t._bf16_ver = (t._dev_ver, layout)
+        t._f32_stamp = None
+        return t
+
+    def _f32_from_b16(self):
+        ctx = get_ctx()
+        stamp = (self._dev_ver, ctx.epoch)
+        if self._buf is None or self._f32_stamp != stamp:
+            if self._buf is None:
+                self._buf, self._off = _DevBuf(ctx, max(self.size, 1) * 4), 0
+            check(lib.okl_from_bf16(ctx.h, self._bf16.ptr, self._buf.ptr, self.size))
+            self._f32_stamp = stamp
+
     # ------------------------------------------------------------------ shape without touching the host
     @property
     def shape(self):
@@ -284,6 +308,8 @@ class Tensor:
 
     # ------------------------------------------------------------------ device side
     def _ptr_raw(self):
+        if self._b16_primary:
+            self._f32_from_b16()
         return self._buf.ptr + self._off
 
     def _touch(self):
@@ -331,6 +357,9 @@ class Tensor:
         """Device pointer of an up-to-date bf16 copy of this tensor in ``layout``; converted on demand, or supplied by the kernel
         that produced the tensor (``_new_b16``)."""
         ctx = get_ctx()
+        if (self._b16_primary and self._dev_valid and self._bf16_ver == (self._dev_ver, self._layout) and
+                (layout == self._layout or len(self._shape) < 3)):
+            return self._bf16.ptr                       # storage of record: no fp32 detour
         src = self._dptr(layout)
         if (getattr(self, "_bf16", None) is None or self._bf16_ver != (self._dev_ver, self._layout) or
                 self._bf16.nbytes < self.size * 2):
@@ -348,6 +377,8 @@ class Tensor:
 
     def _relayout(self, layout):
         ctx = get_ctx()
+        if self._b16_primary:
+            self._f32_from_b16()
         N, Cc, S = self._shape[0], self._shape[1], _numel(self._shape[2:])
         if Cc > 1 and S > 1 and N > 0:
             nb = _DevBuf(ctx, self.size * 4)
@@ -355,6 +386,7 @@ class Tensor:
             if self._bound:
                 raise RuntimeError("bound parameter views cannot change layout")
             self._buf, self._off = nb, 0
+        self._b16_primary = False                       # the re-laid-out fp32 copy is the storage of record from here on
         self._layout = layout
 
     # ------------------------------------------------------------------ reference ops (tensor.py:12-67, 117-140)

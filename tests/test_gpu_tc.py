@@ -184,7 +184,8 @@ def test_conv_implicit_gemm_bf16(okl, nd, N, C, sp, Oc, k, p):
         dW, db, dXo = O.conv_backward_fast(x64, W, g.astype(np.float64), 1, p)
         Wt = lay.weights if nd == 1 else lay.filters
         assert rel_err(dX.data, dXo) < 1.5e-2
-        assert rel_err(Wt.grad, dW) < 1.5e-2 and rel_err(lay.biases.grad, db) < 1e-5
+        # BF16 mode: the gradient tensor between tensor-core layers exists as bf16 only, so db sums bf16-rounded values
+        assert rel_err(Wt.grad, dW) < 1.5e-2 and rel_err(lay.biases.grad, db) < 1.5e-2
     finally:
         okl.set_precision("fp32")
 
