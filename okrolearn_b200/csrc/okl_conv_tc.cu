@@ -440,9 +440,6 @@ int conv_tc_run(okl_ctx* ctx, const void* x16, int N, int H, int W, int Cc, cons
   OKL_REQUIRE(y || y16, "conv_tc: no output requested");
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
-  int bn = ct_env("OKL_CT_BN", 0);
-  if (bn != 64 && bn != 128 && bn != 256) bn = Oc % 128 == 0 ? 128 : 64;
-  if (Oc % bn) bn = 64;
   p.TW = ct_pow2_ceil(OW); if (p.TW > 32) p.TW = 32;
   p.TH = ct_pow2_ceil(OH); if (p.TH > 256 / p.TW) p.TH = 256 / p.TW;
   p.TN = 256 / (p.TW * p.TH);
@@ -450,6 +447,14 @@ int conv_tc_run(okl_ctx* ctx, const void* x16, int N, int H, int W, int Cc, cons
   p.tiles_w = (OW + p.TW - 1) / p.TW; p.tiles_h = (OH + p.TH - 1) / p.TH;
   const int tiles_ng = (N + p.TN - 1) / p.TN;
   p.tiles_m = p.tiles_w * p.tiles_h * tiles_ng;
+  // N tile: as wide as the channel count allows (the wider the MMA, the less shared-memory bandwidth per flop: measured 1 239 vs
+  // 938 TFLOP/s for BN = 256 vs 128 on the 256 -> 256 layer) as long as the grid still fills the chip
+  int bn = ct_env("OKL_CT_BN", 0);
+  if (bn != 64 && bn != 128 && bn != 256) {
+    bn = Oc % 256 == 0 ? 256 : (Oc % 128 == 0 ? 128 : 64);
+    while (bn > 64 && (long long)p.tiles_m * (Oc / bn) * 4 < 3LL * ctx->sm_count) bn >>= 1;
+  }
+  if (Oc % bn) bn = 64;
   p.tiles_n = Oc / bn;
   p.KH = KH; p.KW = KW; p.cblocks = Cc / 64; p.C = Cc; p.ph = ph; p.pw = pw;
   p.row_bytes = p.TW * 128;

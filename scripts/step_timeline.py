@@ -19,7 +19,7 @@ rank, world = dist.init_data_parallel()
 ctx = okl.get_ctx()
 raw = C.CDLL(_lib.lib._name)
 w = bench.WORKLOADS[name]
-B = w["batch"]
+B = int(os.environ.get("TL_BATCH", w["batch"]))
 np.random.seed(1234)
 net = bench.build_net(okl, name)
 logging.getLogger("NeuralNetwork").setLevel(logging.CRITICAL)
