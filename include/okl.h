@@ -363,6 +363,17 @@ int okl_p2p_export(okl_ctx* ctx, void* out64);
 int okl_p2p_import(okl_ctx* ctx, int rank, const void* handle64);
 int okl_p2p_suballoc(okl_ctx* ctx, size_t bytes, void** out);
 /* sum-allreduce `count` fp32 at p on the comm stream, ordered after everything enqueued so far on the compute stream */
+/* NVLS (in-switch reduction): a gradient region bound to ONE multicast object per node.  Rank 0 okl_mc_create -> POSIX fd, passed to
+ * the other ranks (SCM_RIGHTS) -> okl_mc_import; every rank okl_mc_add_device, all-rank barrier, okl_mc_bind; gradient storage is
+ * carved out with okl_mc_suballoc (same call sequence on every rank).  okl_allreduce_async / _fork on such memory is ONE kernel of
+ * multimem.ld_reduce + multimem.st over 1/R of the bucket per rank.  Every call returns an error instead of aborting when the box
+ * has no multicast support; the caller then stays on the peer-memory path. */
+int okl_mc_supported(okl_ctx* ctx);
+int okl_mc_create(okl_ctx* ctx, size_t bytes, int* out_fd);
+int okl_mc_import(okl_ctx* ctx, int fd, size_t bytes);
+int okl_mc_add_device(okl_ctx* ctx);
+int okl_mc_bind(okl_ctx* ctx);
+int okl_mc_suballoc(okl_ctx* ctx, size_t bytes, void** out);
 int okl_allreduce_async(okl_ctx* ctx, void* p, size_t count);
 /* the same, but also ordered after the auxiliary lanes (where weight gradients are produced) and ALWAYS on the comm stream -
  * peer-memory kernel included - so that it overlaps what the caller enqueues next on the compute stream (early exchange of the

@@ -95,6 +95,12 @@ SIGNATURES = {
     "okl_conv_fprop_bf16": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "okl_conv_dgrad_bf16": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "okl_conv_wgrad_bf16": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
+    "okl_mc_supported": (_i, [_vp]),
+    "okl_mc_create": (_i, [_vp, _sz, _P(_i)]),
+    "okl_mc_import": (_i, [_vp, _i, _sz]),
+    "okl_mc_add_device": (_i, [_vp]),
+    "okl_mc_bind": (_i, [_vp]),
+    "okl_mc_suballoc": (_i, [_vp, _sz, _P(_vp)]),
     "okl_from_bf16": (_i, [_vp, _vp, _vp, _sz]),
     "okl_pool2_bf16_supported": (_i, [_i, _i, _i]),
     "okl_pool2_bf16_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),

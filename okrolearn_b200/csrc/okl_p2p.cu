@@ -119,11 +119,10 @@ __device__ __forceinline__ uint4* ll_slot(P2PHeader* h, unsigned par, int src, i
 // rank, so all ranks end with identical bits.  Staging alternates between two halves by sequence parity: a rank can only start
 // all-reduce s+2 after s+1 completed, which needed every peer's s+1 packets, which they sent after finishing s - so nobody still
 // reads the half that s+2 overwrites.
-__global__ void __launch_bounds__(1024) p2p_ll_allreduce_kernel(const P2PPeers peers, const int rank, const int nranks, const size_t off,
+__global__ void __launch_bounds__(1024) p2p_ll_allreduce_kernel(const P2PPeers peers, const int rank, const int nranks, float* mine,
                                                                 const int n) {
   P2PHeader* me = peers.hdr[rank];
   const unsigned s = me->ll_seq + 1, par = s & 1u;
-  float* mine = peers.data[rank] + off;
   const int npk = n >> 1;
   for (int i = threadIdx.x; i < npk; i += blockDim.x) {
     const float2 v = *reinterpret_cast<const float2*>(mine + 2 * i);
@@ -161,6 +160,137 @@ __global__ void __launch_bounds__(1024) p2p_ll_allreduce_kernel(const P2PPeers p
   }
   __syncthreads();
   if (threadIdx.x == 0) me->ll_seq = s;
+}
+
+
+// ------------------------------------------------------------------------------------------------ NVLS: in-switch reduction
+// The gradient arena can live in a region that every rank binds to ONE multicast object (cuMulticastCreate / cuMulticastBindMem,
+// driver API).  Through the multicast address, `multimem.ld_reduce` returns the sum of all ranks' copies of a 16-byte word - the
+// NVSwitch adds them on the way - and `multimem.st` writes a word into every rank's copy.  The all-reduce is then ONE pass over
+// 1/R of the bucket per rank (R x less NVLink traffic than the two-shot kernel's R peer loads + R peer stores per word, and a single
+// round trip); the ready / done flags are the same device-side sequence-number barriers as above (in the cudaIpc header).
+__device__ __forceinline__ float4 mm_ld_reduce_f32x4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mm_st_f32x4(float* mc, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) mc_allreduce_kernel(const P2PPeers peers, const int rank, const int nranks, float* __restrict__ mc,
+                                                                    const size_t n4) {
+  P2PHeader* me = peers.hdr[rank];
+  const unsigned s = me->seq + 1;
+  if (blockIdx.x == 0 && threadIdx.x < nranks) st_release_sys(&peers.hdr[threadIdx.x]->ready[rank], s);
+  if (threadIdx.x < nranks) spin_until(&me->ready[threadIdx.x], s);
+  __syncthreads();
+  const size_t chunk = (n4 + nranks - 1) / nranks;
+  const size_t beg = (size_t)rank * chunk, end = min(n4, beg + chunk);
+  for (size_t i = beg + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < end; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = mm_ld_reduce_f32x4(mc + 4 * i);       // sum over all ranks, added inside the switch
+    mm_st_f32x4(mc + 4 * i, v);                            // ... and broadcast to every rank's copy
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int is_last;
+  if (threadIdx.x == 0) is_last = (atomicAdd(&me->cta_count, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) {
+    if (threadIdx.x < nranks) st_release_sys(&peers.hdr[threadIdx.x]->done[rank], s);
+    if (threadIdx.x < nranks) spin_until(&me->done[threadIdx.x], s);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      me->cta_count = 0;
+      me->seq = s;
+      __threadfence();
+    }
+  }
+}
+
+
+// The driver API is resolved at run time (cudaGetDriverEntryPoint): the library must load on a machine without libcuda.so.1
+// (CPU-only build / test container), exactly like cuTensorMapEncodeTiled in the tcgen05 kernels.
+struct CuApi {
+  CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  CUresult (*CtxGetDevice)(CUdevice*) = nullptr;
+  CUresult (*DeviceGetAttribute)(int*, CUdevice_attribute, CUdevice) = nullptr;
+  CUresult (*MulticastGetGranularity)(size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags) = nullptr;
+  CUresult (*MulticastCreate)(CUmemGenericAllocationHandle*, const CUmulticastObjectProp*) = nullptr;
+  CUresult (*MulticastAddDevice)(CUmemGenericAllocationHandle, CUdevice) = nullptr;
+  CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long) = nullptr;
+  CUresult (*MemExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+  CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
+  CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*MemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  CUresult (*MemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  bool ok = false;
+};
+
+CuApi& cu_api() {
+  static CuApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  bool all = true;
+  auto get = [&](const char* name, void** out) {
+    cudaDriverEntryPointQueryResult qr;
+    void* p = nullptr;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !p) { all = false; cudaGetLastError(); return; }
+    *out = p;
+  };
+  get("cuGetErrorString", (void**)&api.GetErrorString);
+  get("cuCtxGetDevice", (void**)&api.CtxGetDevice);
+  get("cuDeviceGetAttribute", (void**)&api.DeviceGetAttribute);
+  get("cuMulticastGetGranularity", (void**)&api.MulticastGetGranularity);
+  get("cuMulticastCreate", (void**)&api.MulticastCreate);
+  get("cuMulticastAddDevice", (void**)&api.MulticastAddDevice);
+  get("cuMulticastBindMem", (void**)&api.MulticastBindMem);
+  get("cuMemExportToShareableHandle", (void**)&api.MemExportToShareableHandle);
+  get("cuMemImportFromShareableHandle", (void**)&api.MemImportFromShareableHandle);
+  get("cuMemCreate", (void**)&api.MemCreate);
+  get("cuMemGetAllocationGranularity", (void**)&api.MemGetAllocationGranularity);
+  get("cuMemAddressReserve", (void**)&api.MemAddressReserve);
+  get("cuMemMap", (void**)&api.MemMap);
+  get("cuMemSetAccess", (void**)&api.MemSetAccess);
+  api.ok = all;
+  return api;
+}
+
+struct McState {
+  CUmemGenericAllocationHandle mc = 0, mem = 0;
+  size_t size = 0, bump = 0;
+  CUdeviceptr uc = 0, mcva = 0;
+  bool added = false, ready = false;
+};
+std::map<okl_ctx*, McState> g_mc;
+
+#define OKL_CHECK_CU(expr)                                                                            \
+  do {                                                                                                \
+    CUresult _r = (expr);                                                                             \
+    if (_r != CUDA_SUCCESS) {                                                                         \
+      const char* _m = nullptr;                                                                       \
+      if (cu_api().GetErrorString) cu_api().GetErrorString(_r, &_m);                                                                    \
+      okl_set_error("%s failed: %s (CUresult %d)", #expr, _m ? _m : "?", (int)_r);                    \
+      return OKL_ERR_CUDA;                                                                            \
+    }                                                                                                 \
+  } while (0)
+
+int mc_props(okl_ctx* ctx, size_t bytes, CUmulticastObjectProp& prop, size_t& size) {
+  memset(&prop, 0, sizeof(prop));
+  prop.numDevices = (unsigned)ctx->nranks;
+  prop.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  prop.flags = 0;
+  prop.size = bytes;
+  size_t gran = 0;
+  OKL_CHECK_CU(cu_api().MulticastGetGranularity(&gran, &prop, CU_MULTICAST_GRANULARITY_RECOMMENDED));
+  if (gran == 0) gran = 2u << 20;
+  size = (bytes + gran - 1) / gran * gran;
+  prop.size = size;
+  return OKL_OK;
 }
 
 struct P2PState {
@@ -235,9 +365,18 @@ extern "C" int okl_p2p_suballoc(okl_ctx* ctx, size_t bytes, void** out) {
 }
 
 // 1 if [p, p + count floats) lies in the symmetric region, every peer is mapped and the peer-memory kernel applies.
+static bool mc_contains(okl_ctx* ctx, const void* p, size_t count) {
+  auto it = g_mc.find(ctx);
+  if (it == g_mc.end() || !it->second.ready) return false;
+  const char* lo = (const char*)it->second.uc;
+  const char* q = (const char*)p;
+  return q >= lo && q + count * 4 <= lo + it->second.size && ((q - lo) & 15) == 0 && (count & 3) == 0;
+}
+
 bool okl_p2p_applicable(okl_ctx* ctx, const void* p, size_t count) {
   auto it = g_p2p.find(ctx);
   if (it == g_p2p.end() || !it->second.base || it->second.nimported != ctx->nranks) return false;
+  if (mc_contains(ctx, p, count)) return true;            // multicast-bound arena: NVLS kernel (flags still live in the cudaIpc header)
   const P2PState& st = it->second;
   const char* lo = (const char*)st.base + P2P_HDR_BYTES;
   const char* q = (const char*)p;
@@ -256,13 +395,30 @@ int okl_p2p_allreduce(okl_ctx* ctx, void* p, size_t count) {
     peers.data[r] = (float*)((char*)st.peer_base[r] + P2P_HDR_BYTES);
   }
   if (count <= (size_t)LL_MAX_FLOATS) {                  // tiny bucket: one-shot packet exchange, one CTA
-    const size_t off = ((char*)p - ((char*)st.base + P2P_HDR_BYTES)) / 4;
     const int npk = (int)(count / 2);
     int threads = (npk + 31) / 32 * 32;
     if (threads > 1024) threads = 1024;
     if (threads < 32) threads = 32;
-    p2p_ll_allreduce_kernel<<<1, threads, 0, ctx->stream>>>(peers, ctx->rank, ctx->nranks, off, (int)count);
+    p2p_ll_allreduce_kernel<<<1, threads, 0, ctx->stream>>>(peers, ctx->rank, ctx->nranks, (float*)p, (int)count);
     OKL_LAUNCHED(ctx, "p2p_ll_allreduce");
+    return OKL_OK;
+  }
+  if (mc_contains(ctx, p, count)) {                      // NVLS: multimem.ld_reduce + multimem.st on the multicast mapping
+    const McState& mc = g_mc[ctx];
+    float* mcp = (float*)(mc.mcva + ((char*)p - (char*)mc.uc));
+    const size_t n4 = count / 4, chunk = (n4 + ctx->nranks - 1) / ctx->nranks;
+    if (ctx->comm_p2p_kind == 1 && ctx->stream == ctx->comm_stream && chunk <= (size_t)8 * 128 * ctx->sm_count) {
+      int grid = (int)((chunk + 127) / 128);
+      if (grid > ctx->sm_count) grid = ctx->sm_count;
+      if (grid < 1) grid = 1;
+      mc_allreduce_kernel<128, 16><<<grid, 128, 0, ctx->stream>>>(peers, ctx->rank, ctx->nranks, mcp, n4);
+    } else {
+      int grid = (int)((chunk + 511) / 512);
+      if (grid > 2 * ctx->sm_count) grid = 2 * ctx->sm_count;
+      if (grid < 1) grid = 1;
+      mc_allreduce_kernel<512, 1><<<grid, 512, 0, ctx->stream>>>(peers, ctx->rank, ctx->nranks, mcp, n4);
+    }
+    OKL_LAUNCHED(ctx, "mc_allreduce");
     return OKL_OK;
   }
   const size_t off4 = ((char*)p - ((char*)st.base + P2P_HDR_BYTES)) / 16, n4 = count / 4;
@@ -283,5 +439,110 @@ int okl_p2p_allreduce(okl_ctx* ctx, void* p, size_t count) {
   if (grid < 1) grid = 1;
   p2p_allreduce_kernel<512, 1><<<grid, 512, 0, ctx->stream>>>(peers, ctx->rank, ctx->nranks, off4, n4);
   OKL_LAUNCHED(ctx, "p2p_allreduce");
+  return OKL_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ NVLS multicast region (C ABI)
+// Bring-up (okrolearn_b200/dist.py): rank 0 okl_mc_create -> POSIX fd -> sent to the other ranks over a Unix socket (SCM_RIGHTS) ->
+// okl_mc_import; every rank okl_mc_add_device; barrier; every rank okl_mc_bind (physical memory, bind, unicast + multicast mappings).
+extern "C" int okl_mc_supported(okl_ctx* ctx) {
+  if (!ctx || !cu_api().ok) return 0;
+  CUdevice dev;
+  if (cu_api().CtxGetDevice(&dev) != CUDA_SUCCESS) {
+    cudaSetDevice(ctx->device);
+    cudaFree(0);
+    if (cu_api().CtxGetDevice(&dev) != CUDA_SUCCESS) return 0;
+  }
+  int v = 0;
+  if (cu_api().DeviceGetAttribute(&v, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev) != CUDA_SUCCESS) return 0;
+  return v ? 1 : 0;
+}
+
+extern "C" int okl_mc_create(okl_ctx* ctx, size_t bytes, int* out_fd) {
+  OKL_REQUIRE(ctx && out_fd && bytes > 0, "bad argument");
+  OKL_REQUIRE(cu_api().ok, "okl_mc_create: the CUDA driver lacks the multicast API");
+  McState& st = g_mc[ctx];
+  OKL_REQUIRE(st.mc == 0, "okl_mc_create: already created");
+  OKL_CHECK_CUDA(cudaSetDevice(ctx->device));
+  CUmulticastObjectProp prop;
+  int s = mc_props(ctx, bytes, prop, st.size);
+  if (s != OKL_OK) return s;
+  OKL_CHECK_CU(cu_api().MulticastCreate(&st.mc, &prop));
+  int fd = -1;
+  OKL_CHECK_CU(cu_api().MemExportToShareableHandle(&fd, st.mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+  *out_fd = fd;
+  return OKL_OK;
+}
+
+extern "C" int okl_mc_import(okl_ctx* ctx, int fd, size_t bytes) {
+  OKL_REQUIRE(ctx && fd >= 0 && bytes > 0, "bad argument");
+  OKL_REQUIRE(cu_api().ok, "okl_mc_import: the CUDA driver lacks the multicast API");
+  McState& st = g_mc[ctx];
+  OKL_REQUIRE(st.mc == 0, "okl_mc_import: already created");
+  OKL_CHECK_CUDA(cudaSetDevice(ctx->device));
+  CUmulticastObjectProp prop;
+  int s = mc_props(ctx, bytes, prop, st.size);
+  if (s != OKL_OK) return s;
+  OKL_CHECK_CU(cu_api().MemImportFromShareableHandle(&st.mc, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR));
+  return OKL_OK;
+}
+
+extern "C" int okl_mc_add_device(okl_ctx* ctx) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  McState& st = g_mc[ctx];
+  OKL_REQUIRE(st.mc != 0, "okl_mc_add_device: no multicast object");
+  CUdevice dev;
+  OKL_CHECK_CU(cu_api().CtxGetDevice(&dev));
+  OKL_CHECK_CU(cu_api().MulticastAddDevice(st.mc, dev));
+  st.added = true;
+  return OKL_OK;
+}
+
+extern "C" int okl_mc_bind(okl_ctx* ctx) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  McState& st = g_mc[ctx];
+  OKL_REQUIRE(st.mc != 0 && st.added, "okl_mc_bind: call okl_mc_add_device on every rank first");
+  CUdevice dev;
+  OKL_CHECK_CU(cu_api().CtxGetDevice(&dev));
+  CUmemAllocationProp ap;
+  memset(&ap, 0, sizeof(ap));
+  ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  ap.location.id = dev;
+  ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  size_t gran = 0;
+  OKL_CHECK_CU(cu_api().MemGetAllocationGranularity(&gran, &ap, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+  OKL_REQUIRE(gran == 0 || st.size % gran == 0, "okl_mc_bind: multicast size %zu is not a multiple of the allocation granularity %zu", st.size, gran);
+  OKL_CHECK_CU(cu_api().MemCreate(&st.mem, st.size, &ap, 0));
+  OKL_CHECK_CU(cu_api().MulticastBindMem(st.mc, 0, st.mem, 0, st.size, 0));
+  CUmemAccessDesc ad;
+  memset(&ad, 0, sizeof(ad));
+  ad.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  ad.location.id = dev;
+  ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  OKL_CHECK_CU(cu_api().MemAddressReserve(&st.uc, st.size, gran, 0, 0));
+  OKL_CHECK_CU(cu_api().MemMap(st.uc, st.size, 0, st.mem, 0));
+  OKL_CHECK_CU(cu_api().MemSetAccess(st.uc, st.size, &ad, 1));
+  OKL_CHECK_CU(cu_api().MemAddressReserve(&st.mcva, st.size, gran, 0, 0));
+  OKL_CHECK_CU(cu_api().MemMap(st.mcva, st.size, 0, st.mc, 0));
+  OKL_CHECK_CU(cu_api().MemSetAccess(st.mcva, st.size, &ad, 1));
+  OKL_CHECK_CUDA(cudaMemset((void*)st.uc, 0, st.size));
+  OKL_CHECK_CUDA(cudaDeviceSynchronize());
+  st.ready = true;
+  return OKL_OK;
+}
+
+extern "C" int okl_mc_suballoc(okl_ctx* ctx, size_t bytes, void** out) {
+  OKL_REQUIRE(ctx && out, "NULL argument");
+  McState& st = g_mc[ctx];
+  OKL_REQUIRE(st.ready, "okl_mc_suballoc: no multicast region");
+  size_t b = (bytes + 255) & ~size_t(255);
+  if (st.bump + b > st.size) {
+    okl_set_error("okl_mc_suballoc: multicast region exhausted (%zu + %zu > %zu)", st.bump, b, st.size);
+    return OKL_ERR_OOM;
+  }
+  *out = (void*)(st.uc + st.bump);
+  st.bump += b;
   return OKL_OK;
 }

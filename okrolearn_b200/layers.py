@@ -67,9 +67,12 @@ class ParamArena:
         self.param, self.gacc = _DevBuf(ctx, self.total * 4), _DevBuf(ctx, self.total * 4)
         self.grad = None
         if ctx.nranks > 1 and getattr(ctx, "p2p_ready", False):
-            # gradients live in the rank's symmetric (peer-mapped) buffer: their all-reduce is one NVLink kernel
+            # gradients live in the rank's multicast-bound region (NVLS: the switch reduces them) or, without multicast support, in
+            # its symmetric peer-mapped buffer: either way the all-reduce is one NVLink kernel
             p = C.c_void_p()
-            if lib.okl_p2p_suballoc(ctx.h, self.total * 4, C.byref(p)) == 0:
+            if getattr(ctx, "mc_ready", False) and lib.okl_mc_suballoc(ctx.h, self.total * 4, C.byref(p)) == 0:
+                self.grad = _BorrowedPtr(p.value, self.total * 4)
+            elif lib.okl_p2p_suballoc(ctx.h, self.total * 4, C.byref(p)) == 0:
                 self.grad = _BorrowedPtr(p.value, self.total * 4)
         if self.grad is None:
             self.grad = _DevBuf(ctx, self.total * 4)
