@@ -8,7 +8,7 @@ import sys
 
 so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "okrolearn_b200", "libokl_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-ops = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UTMAPF", "LDTM", "STTM", "UTCBAR", "SYNCS", "UBLKCP", "HMMA", "FFMA", "LDGSTS", "MULTIMEM", "RED", "ATOM"]
+ops = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UTMAPF", "LDTM", "STTM", "UTCBAR", "SYNCS", "UBLKCP", "HMMA", "FFMA", "LDGSTS", "LDGMC", "STGMC", "REDGMC", "RED", "ATOM"]
 per = collections.OrderedDict()
 cur = None
 arch = None
@@ -42,6 +42,6 @@ for (k, c), name in zip(per.items(), demangle):
     for o in c:
         if not o.startswith("arch:"):
             tot[o] += c[o]
-    if any(o.startswith(("UTC", "UTMA", "LDTM", "MULTIMEM")) for o in keys):
+    if any(o.startswith(("UTC", "UTMA", "LDTM", "LDGMC", "STGMC", "REDGMC")) for o in keys):
         print(f"{name:92s} instr {c['_instr']:6d}  " + "  ".join(f"{o}={c[o]}" for o in sorted(keys)))
 print("# totals over all kernels: " + "  ".join(f"{o}={tot[o]}" for o in sorted(tot) if not o.startswith("_")))
