@@ -318,6 +318,14 @@ int okl_timer_stop(okl_ctx* ctx, float* ms);     /* records, synchronises, retur
 /* write `bytes` of a scratch buffer larger than L2 (between timed iterations) */
 int okl_flush_l2(okl_ctx* ctx);
 
+/* Classifier head after a BF16 conv stack: FlattenLayer -> DenseLayer(K = C * S, N <= 16) -> SoftmaxActivationLayer ->
+ * CrossEntropyLoss (okl.py:643-651, 29-47, 364-393, 1389-1409) on the channels-last bf16 activation x16 (M, S, C).  Forward (P),
+ * mean CE (loss, also added to *loss_accum), dL/dP (grad), dL/dlogits (dZ), the input gradient dx16 as channels-last bf16
+ * (optional), dW (K, N) in the reference's row order k = c * S + s and db; wt_scratch = N * K bf16 of device scratch. */
+int okl_head_big_supported(int M, int C, int S, int N);
+int okl_head_big(okl_ctx* ctx, const void* x16, const void* W, const void* b, const void* targets_i32, void* P, void* loss, void* grad, void* dZ,
+                 void* dx16, void* dW, void* db, void* wt_scratch, int M, int C, int S, int N, float denom, void* loss_accum);
+
 /* Memory-bound companions of the BF16 tensor-core pipeline (csrc/okl_bf16_ops.cu): between tcgen05 layers activations and
  * gradients exist as channels-last bf16 only.  okl_from_bf16: bf16 -> fp32 when a host mirror / fp32 consumer asks.
  * okl_pool2_bf16_*: MaxPoolingLayer(2, 2) forward / backward on (N, H, W, C) bf16 (okl.py:1731-1772, tie rule R4); the backward

@@ -3,6 +3,7 @@
 // (+ bias, optionally + the SoftmaxActivationLayer that follows, okl.py:364-373) is ONE kernel and the whole backward
 // (dW = X^T G, db = sum_rows G, dX = G W^T with the preceding ReLU's mask, okl.py:35-37) is ONE kernel.  Exact fp32.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -344,5 +345,245 @@ extern "C" int okl_dense_softmax_ce(okl_ctx* ctx, const void* X, const void* W, 
     const int e = okl_aux_end(ctx);
     return s != OKL_OK ? s : e;
   }
+  return OKL_OK;
+}
+
+// ================================================================================================ classifier head after a conv stack
+// FlattenLayer -> DenseLayer(K = C * S up to a few thousand, N <= 16) -> SoftmaxActivationLayer -> CrossEntropyLoss (okl.py:643-651,
+// 29-47, 364-393, 1389-1409) fed by a channels-last bf16 activation (N, S, C).  Round 1 ran this as twelve launches (bf16 -> fp32,
+// channels-last -> NCHW permute, FFMA GEMM + split-K reduce, softmax, CE, two FFMA GEMMs + reduce, column sum, permute back,
+// fp32 -> bf16; ~170 us at batch 1024, ncu).  Here: the weights are re-indexed ONCE per step into the activation's own order
+// (k' = s * C + c instead of k = c * S + s) as a bf16 [N][K] bank, so nothing is ever permuted or widened:
+//   head_big_kernel : one warp per sample - logits from shared-memory weights, softmax, CE value and gradient, softmax backward, and
+//                     dX written straight back as channels-last bf16 (the pooling backward's input)
+//   head_dw_kernel  : dW partials over row chunks (fixed order), head_dw_reduce: dW in the reference's row order + db
+namespace {
+
+constexpr int HB_THREADS = 256;
+
+// Wt[n][k'] = bf16(W[k][n]),  k = c * S + s,  k' = s * C + c
+__global__ void head_bank_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt, int C, int S, int N) {
+  const int K = C * S;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * N; i += gridDim.x * blockDim.x) {
+    const int k = i / N, n = i - k * N;
+    const int c = k / S, s = k - c * S;
+    Wt[(size_t)n * K + s * C + c] = __float2bfloat16(W[i]);
+  }
+}
+
+__device__ __forceinline__ void hb_unpack8(const uint4& v, float* f) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+
+__global__ void __launch_bounds__(HB_THREADS) head_big_kernel(const uint4* __restrict__ x16, const uint4* __restrict__ Wt, const float* __restrict__ b,
+                                                              const int* __restrict__ t, float* __restrict__ P, float* __restrict__ grad,
+                                                              float* __restrict__ dZ, uint4* __restrict__ dx16, float* __restrict__ partial, int M,
+                                                              int K, int N, float inv_denom) {
+  extern __shared__ uint4 sW[];                    // [N][K / 8] uint4 = bf16 bank
+  __shared__ float wl[8];
+  okl_pdl_sync();
+  const int K8 = K >> 3;
+  for (int i = threadIdx.x; i < N * K8; i += HB_THREADS) sW[i] = __ldg(Wt + i);
+  __syncthreads();
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float lsum = 0.f;
+  for (int m = blockIdx.x * 8 + wib; m < M; m += gridDim.x * 8) {
+    const uint4* xr = x16 + (size_t)m * K8;
+    float acc[SN_MAXN];
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; n++) acc[n] = 0.f;
+    for (int i = lane; i < K8; i += 32) {
+      float xv[8];
+      hb_unpack8(__ldg(xr + i), xv);
+#pragma unroll
+      for (int n = 0; n < SN_MAXN; n++) {
+        if (n < N) {
+          float wv[8];
+          hb_unpack8(sW[n * K8 + i], wv);
+#pragma unroll
+          for (int j = 0; j < 8; j++) acc[n] = fmaf(xv[j], wv[j], acc[n]);
+        }
+      }
+    }
+    const int tc = __ldg(t + m);
+    float mx = -INFINITY, sum = 0.f;
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; n++) {
+      if (n < N) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], s);
+        if (b) acc[n] += __ldg(b + n);
+        mx = fmaxf(mx, acc[n]);
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; n++)
+      if (n < N) { acc[n] = expf(acc[n] - mx); sum += acc[n]; }
+    float dot = 0.f, pt = 1.f, gv[SN_MAXN];
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; n++) {
+      gv[n] = 0.f;
+      if (n < N) {
+        float v = acc[n] / sum;
+        v = isnan(v) ? 0.f : v;                      // nan_to_num, okl.py:370
+        acc[n] = v;
+        float g = fminf(fmaxf(v, 1e-12f), 1.0f);     // np.clip(p, 1e-12, 1 - 1e-12), okl.py:1391
+        if (n == tc) { pt = g; g -= 1.f; }
+        g *= inv_denom;
+        gv[n] = g;
+        dot += g * v;
+      }
+    }
+    lsum += -logf(pt);
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; n++)
+      if (n < N) {
+        const float dz = acc[n] * (gv[n] - dot);     // softmax backward of (clip(p) - onehot) / samples, okl.py:382-391
+        if (lane == n) {
+          P[(size_t)m * N + n] = acc[n];
+          grad[(size_t)m * N + n] = gv[n];
+          dZ[(size_t)m * N + n] = dz;
+        }
+        gv[n] = dz;
+      }
+    if (dx16) {
+      uint4* dr = dx16 + (size_t)m * K8;
+      for (int i = lane; i < K8; i += 32) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) o[j] = 0.f;
+#pragma unroll
+        for (int n = 0; n < SN_MAXN; n++) {
+          if (n < N) {
+            float wv[8];
+            hb_unpack8(sW[n * K8 + i], wv);
+#pragma unroll
+            for (int j = 0; j < 8; j++) o[j] = fmaf(gv[n], wv[j], o[j]);
+          }
+        }
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          __nv_bfloat162 q = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+          pk[e] = *reinterpret_cast<uint32_t*>(&q);
+        }
+        dr[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+  if (lane == 0) wl[wib] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; w++) s += wl[w];
+    partial[blockIdx.x] = s;
+  }
+}
+
+// part[rs][k'][n] = sum over the rows of chunk rs of x[row][k'] * dz[row][n]; thread = two adjacent k' (one 4-byte load per row)
+__global__ void __launch_bounds__(HB_THREADS) head_dw_kernel(const uint32_t* __restrict__ x16, const float* __restrict__ dZ, float* __restrict__ part,
+                                                             int M, int K, int N, int rows_per_chunk) {
+  extern __shared__ float sdz[];                   // [rows_per_chunk][N]
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
+  for (int i = threadIdx.x; i < (r1 - r0) * N; i += HB_THREADS) sdz[i] = dZ[(size_t)r0 * N + i];
+  __syncthreads();
+  const int kp = (blockIdx.x * HB_THREADS + threadIdx.x) * 2;
+  if (kp >= K) return;
+  float a0[SN_MAXN], a1[SN_MAXN];
+#pragma unroll
+  for (int n = 0; n < SN_MAXN; n++) a0[n] = a1[n] = 0.f;
+  const uint32_t* xp = x16 + (kp >> 1);
+  const int K2 = K >> 1;
+  for (int r = r0; r < r1; r++) {
+    const uint32_t v = __ldg(xp + (size_t)r * K2);
+    const float x0 = __uint_as_float(v << 16), x1 = __uint_as_float(v & 0xFFFF0000u);
+    const float* dz = sdz + (r - r0) * N;
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; n++)
+      if (n < N) { a0[n] = fmaf(x0, dz[n], a0[n]); a1[n] = fmaf(x1, dz[n], a1[n]); }
+  }
+  float* dst = part + ((size_t)blockIdx.y * K + kp) * N;
+#pragma unroll
+  for (int n = 0; n < SN_MAXN; n++)
+    if (n < N) { dst[n] = a0[n]; dst[N + n] = a1[n]; }
+}
+
+// dW[k][n] = sum_rs part[rs][k'(k)][n] (k = c * S + s <- k' = s * C + c);  db[n] = sum_rows dZ[row][n] (one warp per class)
+__global__ void head_dw_reduce(const float* __restrict__ part, const float* __restrict__ dZ, float* __restrict__ dW, float* __restrict__ db, int M,
+                               int C, int S, int N, int chunks) {
+  const int K = C * S;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K * N) {
+    const int k = i / N, n = i - k * N;
+    const int c = k / S, s = k - c * S;
+    const float* src = part + (size_t)(s * C + c) * N + n;
+    float a = 0.f;
+    for (int r = 0; r < chunks; r++) a += src[(size_t)r * K * N];
+    dW[i] = a;
+  }
+  if (db && blockIdx.x == 0) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int n = w; n < N; n += blockDim.x >> 5) {
+      float a = 0.f;
+      for (int r = lane; r < M; r += 32) a += dZ[(size_t)r * N + n];
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+      if (lane == 0) db[n] = a;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int okl_head_big_supported(int M, int C, int S, int N) {
+  const long long K = (long long)C * S;
+  return (M >= 1 && N >= 1 && N <= SN_MAXN && C % 8 == 0 && S >= 1 && K % 256 == 0 && K * N * 2 <= 160 * 1024) ? 1 : 0;
+}
+
+// x16: (M, S, C) channels-last bf16 view of the (M, C, S) activation the FlattenLayer flattens; W (C * S, N) and b (N) fp32 masters;
+// outputs: P (probabilities), loss (mean CE), grad (dL/dP), dZ (dL/dlogits) fp32; dx16 (M, S, C) bf16 (optional); dW, db fp32.
+// wt_scratch: N * K bf16 of device scratch for the re-indexed weight bank.
+extern "C" int okl_head_big(okl_ctx* ctx, const void* x16, const void* W, const void* b, const void* targets_i32, void* P, void* loss, void* grad,
+                            void* dZ, void* dx16, void* dW, void* db, void* wt_scratch, int M, int C, int S, int N, float denom, void* loss_accum) {
+  OKL_REQUIRE(ctx && x16 && W && targets_i32 && P && loss && grad && dZ && dW && wt_scratch, "NULL argument");
+  OKL_REQUIRE(okl_head_big_supported(M, C, S, N) && denom > 0.f, "okl_head_big: unsupported shape M=%d C=%d S=%d N=%d", M, C, S, N);
+  const int K = C * S;
+  if (!ctx->head_scratch) {
+    OKL_CHECK_CUDA(cudaMalloc(&ctx->head_scratch, 8192));
+    OKL_CHECK_CUDA(cudaMemset(ctx->head_scratch, 0, 8192));
+  }
+  float* partial = (float*)ctx->head_scratch + 16;
+  head_bank_kernel<<<okl_grid_1d(ctx, (size_t)K * N, 256), 256, 0, ctx->stream>>>((const float*)W, (__nv_bfloat16*)wt_scratch, C, S, N);
+  OKL_LAUNCHED(ctx, "head_bank");
+  int grid = (M + 7) / 8;
+  if (grid > 2 * ctx->sm_count) grid = 2 * ctx->sm_count;
+  const int smem = N * K * 2;
+  static int set = 0;
+  if (set < smem) { OKL_CHECK_CUDA(cudaFuncSetAttribute(head_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); set = 160 * 1024; }
+  okl_launch(ctx, head_big_kernel, dim3(grid), dim3(HB_THREADS), (size_t)smem, (const uint4*)x16, (const uint4*)wt_scratch, (const float*)b,
+             (const int*)targets_i32, (float*)P, (float*)grad, (float*)dZ, (uint4*)dx16, partial, M, K, N, 1.f / denom);
+  OKL_LAUNCHED(ctx, "head_big");
+  head_loss_finalize_kernel<<<1, 32, 0, ctx->stream>>>(partial, grid, M, (float*)loss, (float*)loss_accum);
+  OKL_LAUNCHED(ctx, "head_loss_finalize");
+  // weight gradient: row chunks so that the grid fills the chip; fixed-order second stage
+  int chunks = (2 * ctx->sm_count) / ((K / 2 + HB_THREADS - 1) / HB_THREADS);
+  if (chunks < 1) chunks = 1;
+  if (chunks > 32) chunks = 32;
+  int rpc = (M + chunks - 1) / chunks;
+  if (rpc > 512) rpc = 512;                         // shared-memory stage of dZ: rows_per_chunk * N floats
+  chunks = (M + rpc - 1) / rpc;
+  int s = okl_ensure_workspace(ctx, (size_t)chunks * K * N * sizeof(float));
+  if (s != OKL_OK) return s;
+  head_dw_kernel<<<dim3((K / 2 + HB_THREADS - 1) / HB_THREADS, chunks), HB_THREADS, (size_t)rpc * N * sizeof(float), ctx->stream>>>(
+      (const uint32_t*)x16, (const float*)dZ, (float*)ctx->workspace, M, K, N, rpc);
+  OKL_LAUNCHED(ctx, "head_dw");
+  head_dw_reduce<<<(K * N + 255) / 256, 256, 0, ctx->stream>>>((const float*)ctx->workspace, (const float*)dZ, (float*)dW, (float*)db, M, C, S, N,
+                                                              chunks);
+  OKL_LAUNCHED(ctx, "head_dw_reduce");
   return OKL_OK;
 }

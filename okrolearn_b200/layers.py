@@ -205,6 +205,7 @@ class _ParamLayer:
     _defer_update = False          # set by NeuralNetwork when updates are applied after the whole backward (DP overlap)
     _fused_act = ACT_NONE          # set by NeuralNetwork's planner: activation fused into this layer's epilogue
     _fused_head = False            # NeuralNetwork planner: last Dense(N<=16) -> Softmax; the loss's kernel computes the head
+    _big_head = False              # ... and that head follows Flatten of a channels-last bf16 conv stack (okl_head_big)
 
     def _finish_update(self):
         b = self._bucket
@@ -312,6 +313,9 @@ class DenseLayer(_ParamLayer):
         need_dx = getattr(self, "_need_dx", True)
         b = self._bucket
         pre, self._head_pre = getattr(self, "_head_pre", None), None
+        if pre is not None and pre[0] is dL_dout and len(pre) > 2 and pre[2]:
+            b.step(lr, self._defer_update)                   # big fused head: dX, dW and db were all produced with the loss
+            return pre[1]
         if pre is not None and pre[0] is dL_dout:            # fused classifier head: dX already produced with the loss
             dX = pre[1]
             aux = bool(self._aux_lane and self._defer_update)
@@ -1742,16 +1746,33 @@ class ReflectionPaddingLayer(PaddingLayer):
 class FlattenLayer:
     """okl.py:639-651: (N, ...) -> (N, -1) and back; a zero-copy view of the device block."""
 
+    _lazy_for_head = False       # NeuralNetwork planner: the fused classifier head reads the channels-last bf16 source directly
+
     def __init__(self):
         self.inputs_shape = None
 
     def forward(self, inputs: Tensor):
         inputs = _as_tensor(inputs)
         self.inputs_shape = inputs.shape
+        if self._lazy_for_head and inputs._b16_primary and inputs._layout == NXC and inputs.ndim >= 3:
+            # nothing is moved: the flat (N, C * S) tensor is materialised (bf16 -> fp32, channels-last -> reference order) only if
+            # somebody other than the fused head asks for it
+            out = Tensor._view(None, 0, (inputs.shape[0], _numel(inputs.shape[1:])), inputs._np_dtype, bound=False)
+            out._dev_valid = False
+            out._flat_src = inputs
+
+            def materialize(t, src=inputs):
+                flat = src.reshape((src.shape[0], -1))
+                t._buf, t._off, t._dev_ver, t._dev_valid = flat._buf, flat._off, flat._dev_ver, True
+            out._lazy_fn = materialize
+            return out
         return inputs.reshape((inputs.shape[0], -1))
 
     def backward(self, dL_dout: Tensor, lr: float):
-        return _as_tensor(dL_dout).reshape(self.inputs_shape)
+        dL_dout = _as_tensor(dL_dout)
+        if dL_dout.shape == tuple(self.inputs_shape):          # the fused head already produced the gradient in the source's shape
+            return dL_dout
+        return dL_dout.reshape(self.inputs_shape)
 
     def get_params(self):           # the reference lacks this (NeuralNetwork.save breaks on CNNs, okl.py:3022); harmless to add
         return None

@@ -126,8 +126,31 @@ class CrossEntropyLoss:
         if dz is not None and head is not None and getattr(outputs, "_lazy_fn", None) is not None and head.outputs is outputs:
             # the probabilities have not been computed yet: Dense -> Softmax -> CE forward and backward down to the dense
             # layer's dX in one kernel
-            outputs._lazy_fn = None
             x = head.inputs
+            src = getattr(x, "_flat_src", None)
+            if (getattr(head, "_big_head", False) and src is not None and getattr(x, "_lazy_fn", None) is not None and src._b16_primary and
+                    src._layout == _lib.NXC and lib.okl_head_big_supported(rows, src.shape[1], x.shape[1] // src.shape[1], cols)):
+                # Flatten -> Dense -> Softmax -> CE on a channels-last bf16 activation: forward, loss, every gradient (dX as bf16 in
+                # the activation's own layout, dW, db) in four small kernels; nothing is permuted or widened
+                outputs._lazy_fn = None
+                Cc, S_ = src.shape[1], x.shape[1] // src.shape[1]
+                need_dx = getattr(head, "_need_dx", True)
+                dx = Tensor._empty_b16(src.shape, np.float64, _lib.NXC) if need_dx else None
+                bk = head._bucket
+                if getattr(head, "_wt_scratch", None) is None or head._wt_scratch.nbytes < cols * x.shape[1] * 2:
+                    head._wt_scratch = _DevBuf(ctx, cols * x.shape[1] * 2)
+                outputs._buf, outputs._off = _DevBuf(ctx, rows * cols * 4), 0
+                check(lib.okl_head_big(ctx.h, src._b16(_lib.NXC), bk.ptr(0), bk.ptr(1), tptr, outputs._ptr_raw(), loss.ptr, grad._ptr_raw(),
+                                       dz._ptr_raw(), dx._bf16.ptr if dx is not None else None, bk.grad_ptr(0), bk.grad_ptr(1),
+                                       head._wt_scratch.ptr, rows, Cc, S_, cols, float(rows * ctx.nranks), self._loss_accum))
+                outputs._touch()
+                head._head_pre = (dz, dx, True)
+                sm._precomputed = (grad, dz)
+                self.outputs, self.targets = outputs, targets
+                self._grad = grad
+                self._loss = LossValue(loss)
+                return self._loss
+            outputs._lazy_fn = None
             K = x.shape[1]
             dx = Tensor._empty((rows, K), np.float64) if getattr(head, "_need_dx", True) else None
             xp = x._dptr(NCX)

@@ -33,7 +33,7 @@ from . import _lib
 from ._lib import lib, check, get_ctx, NCX, ACT_NONE
 from .tensor import Tensor, _DevBuf, _numel, pinned_empty, pinned_base
 from .layers import (apply_pending_updates, ParamArena, _ParamLayer, _Activation, _Pool, ReLUActivationLayer, SigmoidActivationLayer, SoftmaxActivationLayer,
-                     MaxPoolingLayer, DenseLayer, Conv2DLayer,
+                     MaxPoolingLayer, DenseLayer, Conv2DLayer, FlattenLayer,
                      _ConvBase)
 from .losses import CrossEntropyLoss, MSELoss, LossValue
 
@@ -220,7 +220,7 @@ class NeuralNetwork:
         for l in ls:
             if isinstance(l, _ParamLayer):
                 l._fused_act, l._need_dx, l._dx_relu_mask, l._aux_lane = ACT_NONE, True, False, 0
-                l._fused_head = False
+                l._fused_head = l._big_head = False
                 l._defer_update = fast or get_ctx().nranks > 1
             if isinstance(l, _ConvBase):
                 l._fused_pool = None
@@ -234,6 +234,8 @@ class NeuralNetwork:
                 l._db_sink = None
             if isinstance(l, SoftmaxActivationLayer):
                 l._fused_into_prev = False
+            if isinstance(l, FlattenLayer):
+                l._lazy_for_head = False
         # layout planning: a convolution that feeds (through activations / pooling) a tensor-core-eligible convolution writes
         # its output channels-last, so no permutation is needed between them
         tc_mode = get_ctx().precision != _lib.FP32
@@ -265,6 +267,14 @@ class NeuralNetwork:
                     a._fused_act, b._fused_into_prev = _lib.ACT_SOFTMAX, True
                     # ... and when that pair ends the network, a CrossEntropyLoss computes the whole head in its own kernel
                     a._fused_head = bool(self.fuse_head and b is ls[-1] and a.weights.shape[0] <= 256)
+            # ... Flatten -> Dense(K up to a few thousand, N <= 16) -> Softmax at the end of a BF16 conv stack: the big fused head
+            if (self.fuse_head and tc_mode and get_ctx().precision == _lib.BF16 and len(ls) >= 3 and isinstance(ls[-1], SoftmaxActivationLayer) and
+                    isinstance(ls[-2], DenseLayer) and isinstance(ls[-3], FlattenLayer) and ls[-2].weights.shape[1] <= 16 and
+                    256 < ls[-2].weights.shape[0] and ls[-2].weights.shape[0] % 256 == 0 and
+                    ls[-2].weights.shape[0] * ls[-2].weights.shape[1] * 2 <= 160 * 1024):
+                ls[-2]._fused_act, ls[-1]._fused_into_prev = _lib.ACT_SOFTMAX, True
+                ls[-2]._fused_head = ls[-2]._big_head = True
+                ls[-3]._lazy_for_head = True
             for a, r, b in zip(ls, ls[1:], ls[2:]):      # Param(+ReLU fused) -> Param: relu' applied in the second layer's dX epilogue
                 if (isinstance(a, _ParamLayer) and isinstance(r, ReLUActivationLayer) and r._fused_into_prev and
                         isinstance(b, _ParamLayer)):

@@ -172,3 +172,43 @@ def test_dense_8192_wide_layer(okl, prec, tol):
         assert rel_err(lay.biases.grad, g64.sum(0, keepdims=True)) < 1e-4
     finally:
         okl.set_precision("fp32")
+
+
+def test_big_fused_head_matches_unfused_and_oracle(okl):
+    """Flatten -> Dense(4096, 10) -> Softmax -> CE behind a BF16 conv stack (configs[2] tail): the fused head (okl_head_big: weights
+    re-indexed into the activation's channels-last order, dX written back as bf16) against the unfused layer chain and the oracle."""
+    okl.set_precision("bf16")
+    try:
+        rng = np.random.default_rng(17)
+        N = 32
+        X = rng.standard_normal((N, 64, 8, 8)).astype(np.float32)
+        T = rng.integers(0, 10, N)
+        Wc = rng.standard_normal((256, 64, 3, 3)) * (1.0 / np.sqrt(9 * 64))
+        Wd = rng.standard_normal((4096, 10)) * 0.02
+        res = {}
+        for fused in (True, False):
+            net = okl.NeuralNetwork()
+            net.fuse_head = fused
+            conv, d = okl.Conv2DLayer(64, 256, 3, 1, 1), okl.DenseLayer(4096, 10)
+            conv.filters.data, d.weights.data = Wc.copy(), Wd.copy()
+            for l in (conv, okl.ReLUActivationLayer(), okl.MaxPoolingLayer(2, 2), okl.FlattenLayer(), d, okl.SoftmaxActivationLayer()):
+                net.add(l)
+            ce = okl.CrossEntropyLoss()
+            out = net._forward(okl.Tensor(X), _fast=True)
+            ce._fuse_softmax = net.layers[-1]
+            loss = float(ce.forward(out, okl.Tensor(T)))
+            net._backward(ce.backward(out, None), 0.05)
+            assert d._big_head == fused
+            res[fused] = (loss, np.array(out.data), np.array(d.weights.grad), np.array(d.biases.grad), np.array(conv.filters.grad))
+        on = O.OracleNetwork([O.OracleConv(Wc, np.zeros((256, 1)), 1, 1, fast=True), O.OracleReLU(), O.OracleMaxPool(2, 2), O.OracleFlatten(),
+                              O.OracleDense(Wd, np.zeros((1, 10))), O.OracleSoftmax()])
+        ref = on.train_step(X.astype(np.float64), T, O.OracleCrossEntropy(), 0.05)
+        for fused in (True, False):
+            loss, p, dW, db, dWc = res[fused]
+            assert abs(loss - ref) <= 2e-2 * abs(ref), (fused, loss, ref)
+            assert rel_err(p, on.layers[-1].p) < 2e-2
+            assert rel_err(dW, on.layers[4].gW) < 2e-2 and rel_err(db, on.layers[4].gb) < 2e-2
+            assert rel_l2(dWc, on.layers[0].gW) < 0.15      # through the max-pool arg-max (see the two-step test above)
+        assert rel_err(res[True][2], res[False][2]) < 2e-2 and rel_l2(res[True][4], res[False][4]) < 5e-2
+    finally:
+        okl.set_precision("fp32")
