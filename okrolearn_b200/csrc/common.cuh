@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: a no-op unless a tool (nsys, ncu --nvtx) injects its library
+
 #include "../../include/okl.h"
 
 struct okl_graph {
@@ -102,7 +104,15 @@ void okl_set_error(const char* fmt, ...);
 
 // account one kernel launch and surface launch-configuration errors immediately
 void okl_timeline_stamp(okl_ctx* ctx, const char* what);
+// NVTX: every kernel enqueue leaves a named marker on the host timeline (OKL_NVTX=0 turns it off); the C-ABI entry points of a
+// train step additionally open ranges (okl_graph_launch: "okl:step").  SURVEY.md section 5 (tracing).
+static inline bool okl_nvtx_on() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("OKL_NVTX"); on = (e && *e == '0') ? 0 : 1; }
+  return on != 0;
+}
 static inline int okl_post_launch(okl_ctx* ctx, const char* what) {
+  if (okl_nvtx_on()) nvtxMarkA(what);
   if (ctx->capturing) ctx->capture_launches++; else ctx->launches++;
   if (ctx->tl_buf) okl_timeline_stamp(ctx, what);
   cudaError_t e = cudaPeekAtLastError();

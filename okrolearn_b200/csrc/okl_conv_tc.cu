@@ -706,37 +706,42 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 // threads walk o (the contiguous dimension of the partials).
 __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dW, float* __restrict__ db, int O, int C, int KH, int KW,
                                          int cpc, int nchunks, int MT, int BN, int tiles_mt, int tiles_n, int splits) {
+  // four threads per output element (adjacent lanes): each sums every fourth split with four loads in flight, then a fixed-order
+  // two-step shuffle - the loop is pure load latency, so the parallelism is what sets its time
   const int nq = nchunks + (db ? 1 : 0);
   const size_t total = (size_t)nq * 64 * KH * O;
   const int nacc = MT * KH;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int o = (int)(i % O);
-    size_t r = i / O;
+  const size_t gtid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const int part = (int)(gtid & 3);
+  for (size_t i = gtid >> 2; i < ((total + 7) & ~size_t(7)); i += ((size_t)gridDim.x * blockDim.x) >> 2) {
+    const bool live = i < total;
+    const size_t ii = live ? i : 0;
+    const int o = (int)(ii % O);
+    size_t r = ii / O;
     const int u = (int)(r % KH); r /= KH;
     const int m64 = (int)(r % 64);
     const int q = (int)(r / 64);
     const bool is_db = q == nchunks;
-    if (is_db && (m64 != 0 || u != 0)) continue;
     const int tmt = q / (2 * MT), slot = q - tmt * 2 * MT, t = slot >> 1, j = slot & 1;
     const int tn = o / BN, on = o - tn * BN;
     const int tile = tmt * tiles_n + tn;
     const size_t stride = (size_t)(tiles_mt * tiles_n) * nacc * 128 * BN;
     const float* src = ws + (((size_t)tile * nacc + (t * KH + u)) * 128 + (j * 64 + m64)) * (size_t)BN + on;
-    float acc[8];
-#pragma unroll
-    for (int e = 0; e < 8; e++) acc[e] = 0.f;
-    int k = 0;
-    for (; k + 7 < splits; k += 8) {                         // eight independent loads in flight per thread (the loop is pure latency)
-      float t[8];
-#pragma unroll
-      for (int e = 0; e < 8; e++) t[e] = __ldcs(src + (size_t)(k + e) * stride);
-#pragma unroll
-      for (int e = 0; e < 8; e++) acc[e] += t[e];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = part;
+    for (; k + 12 < splits; k += 16) {
+      const float t0 = __ldcs(src + (size_t)k * stride), t1 = __ldcs(src + (size_t)(k + 4) * stride);
+      const float t2 = __ldcs(src + (size_t)(k + 8) * stride), t3 = __ldcs(src + (size_t)(k + 12) * stride);
+      a0 += t0; a1 += t1; a2 += t2; a3 += t3;
     }
-    for (; k < splits; k++) acc[0] += __ldcs(src + (size_t)k * stride);
-    const float s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-    if (is_db) db[o] = s;
-    else {
+    for (; k < splits; k += 4) a0 += __ldcs(src + (size_t)k * stride);
+    float s = (a0 + a1) + (a2 + a3);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (!live || part != 0) continue;
+    if (is_db) {
+      if (m64 == 0 && u == 0) db[o] = s;
+    } else {
       const int v = q / cpc, c = (q - v * cpc) * 64 + m64;
       dW[(((size_t)o * C + c) * KH + u) * KW + v] = s;
     }
@@ -835,7 +840,7 @@ extern "C" int okl_conv2_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void*
   st = p.BN == 128 ? wg_launch<128>(ctx, tx, tg, pl) : wg_launch<64>(ctx, tx, tg, pl);
   if (st != OKL_OK) return st;
   const size_t total = (size_t)(p.nchunks + (pl.db_fused ? 1 : 0)) * 64 * s.KH * s.O;
-  conv_wgrad_reduce_kernel<<<okl_grid_1d(ctx, total, 256), 256, 0, ctx->stream>>>(p.ws, (float*)dW, pl.db_fused ? (float*)db : nullptr, s.O, s.C, s.KH,
+  conv_wgrad_reduce_kernel<<<okl_grid_1d(ctx, total * 4, 256, 16), 256, 0, ctx->stream>>>(p.ws, (float*)dW, pl.db_fused ? (float*)db : nullptr, s.O, s.C, s.KH,
                                                                                  s.KW, p.cpc, p.nchunks, p.MT, p.BN, p.tiles_mt, p.tiles_n, p.splits);
   OKL_LAUNCHED(ctx, "conv_wgrad_reduce");
   if (db && !pl.db_fused) return okl_channel_sum_bf16(ctx, g16, db, (long long)s.N * s.OH * s.OW, s.O);
@@ -885,6 +890,37 @@ __device__ __forceinline__ void f1_load_patch(float* patch, const F1Params& p, i
     if (n < p.N && ih >= 0 && ih < p.H && iw >= 0 && iw < p.Wd) v = __ldg(p.x + (((size_t)n * p.C + c) * p.H + ih) * p.Wd + iw);
     patch[i] = v;
   }
+}
+
+// Software pipelining of the patch: a tile's values are fetched into registers one tile ahead (while the previous tile's MMA and
+// epilogue run) and only copied to shared memory at the top of the tile - ncu had both kernels waiting on these global loads.
+constexpr int F1_PRE = 4;              // values per thread held ahead (patches up to 1024 floats; larger ones load directly)
+
+__device__ __forceinline__ void f1_fetch_patch(float* pre, const F1Params& p, int n, int h0, int w0) {
+  const int per_c = p.PH * p.PWp, total = p.C * per_c;
+#pragma unroll
+  for (int e = 0; e < F1_PRE; e++) {
+    const int i = threadIdx.x + e * F1_THREADS;
+    float v = 0.f;
+    if (i < total) {
+      const int c = i / per_c, r2 = i - c * per_c, r = r2 / p.PWp, col = r2 - r * p.PWp;
+      const int ih = h0 - p.ph + r, iw = w0 - p.pw + col;
+      if (n < p.N && ih >= 0 && ih < p.H && iw >= 0 && iw < p.Wd) v = __ldg(p.x + (((size_t)n * p.C + c) * p.H + ih) * p.Wd + iw);
+    }
+    pre[e] = v;
+  }
+}
+__device__ __forceinline__ void f1_store_patch(float* patch, const float* pre, int total) {
+#pragma unroll
+  for (int e = 0; e < F1_PRE; e++) {
+    const int i = threadIdx.x + e * F1_THREADS;
+    if (i < total) patch[i] = pre[e];
+  }
+}
+__device__ __forceinline__ void f1_tile_origin(const F1Params& p, int tile, int& n, int& h0, int& w0) {
+  const int wt = tile % p.tiles_w, r2 = tile / p.tiles_w;
+  const int ht = r2 % p.tiles_h;
+  n = r2 / p.tiles_h; w0 = wt * p.TW; h0 = ht * p.TH;
 }
 
 // thread (pixel m, half): 16 of the 32 k values of row m of the 128 x 32 patch operand, as two swizzled 16-byte chunks
@@ -948,16 +984,29 @@ __global__ void __launch_bounds__(F1_THREADS, O_ == 64 ? 3 : 2) conv_first_fprop
   uint8_t* stg = sStg + warp * CT_STG;
   const uint32_t sw = (uint32_t)(lane & 7);
   uint32_t parity = 0;
+  const int ptotal = p.C * p.PH * p.PWp;
+  const bool piped = ptotal <= F1_PRE * F1_THREADS;
+  float pre[F1_PRE];
+  if (piped && (int)blockIdx.x < p.ntiles) {
+    int n, h0, w0;
+    f1_tile_origin(p, blockIdx.x, n, h0, w0);
+    f1_fetch_patch(pre, p, n, h0, w0);
+  }
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-    const int wt = tile % p.tiles_w, r2 = tile / p.tiles_w;
-    const int ht = r2 % p.tiles_h, n = r2 / p.tiles_h;
-    const int w0 = wt * p.TW, h0 = ht * p.TH;
-    f1_load_patch(patch, p, n, h0, w0);
+    int n, h0, w0;
+    f1_tile_origin(p, tile, n, h0, w0);
+    if (piped) f1_store_patch(patch, pre, ptotal);
+    else f1_load_patch(patch, p, n, h0, w0);
     __syncthreads();                                        // patch complete; every thread is past the previous tile's accumulator reads
     f1_build_rows(sA, patch, ktab, p, true);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    if (piped && tile + (int)gridDim.x < p.ntiles) {        // next tile's patch: in flight during this tile's MMA and epilogue
+      int n2, h2, w2;
+      f1_tile_origin(p, tile + gridDim.x, n2, h2, w2);
+      f1_fetch_patch(pre, p, n2, h2, w2);
+    }
     if (threadIdx.x == 0) {
       tc_fence_after();
       const uint64_t adesc = make_smem_desc(smem_u32(sA), 16, 1024, 2);
@@ -1040,20 +1089,28 @@ __global__ void __launch_bounds__(F1_THREADS, O_ == 64 ? 3 : 2) conv_first_wgrad
   constexpr uint32_t idesc = make_idesc(1, true, true, 128, O_);
   okl_pdl_sync();
 
+  const int ptotal = p.C * p.PH * p.PWp;
+  const bool piped = ptotal <= F1_PRE * F1_THREADS;
+  float pre[F1_PRE];
+  if (piped && (int)blockIdx.x < p.ntiles) {
+    int n, h0, w0;
+    f1_tile_origin(p, blockIdx.x, n, h0, w0);
+    f1_fetch_patch(pre, p, n, h0, w0);
+  }
   int it = 0;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it++) {
     const int s = it & 1;
     const uint32_t use = (uint32_t)(it >> 1);               // how many times stage s has been used before
-    const int wt = tile % p.tiles_w, r2 = tile / p.tiles_w;
-    const int ht = r2 % p.tiles_h, n = r2 / p.tiles_h;
-    const int w0 = wt * p.TW, h0 = ht * p.TH;
+    int n, h0, w0;
+    f1_tile_origin(p, tile, n, h0, w0);
     if (use > 0) mbar_wait(&st_free[s], (use - 1) & 1);     // everyone: stage s (patch operand AND gradient tile) is reusable
     if (threadIdx.x == 0) {
       mbar_expect_tx(&g_full[s], GB);
 #pragma unroll
       for (int j = 0; j < O_ / 64; j++) tma_load_4d(&tmG, &g_full[s], sG + s * GB + j * 16384, j * 64, w0, h0, n);
     }
-    f1_load_patch(patch, p, n, h0, w0);
+    if (piped) f1_store_patch(patch, pre, ptotal);
+    else f1_load_patch(patch, p, n, h0, w0);
     __syncthreads();
     {
       const int m = threadIdx.x & 127;
@@ -1063,6 +1120,11 @@ __global__ void __launch_bounds__(F1_THREADS, O_ == 64 ? 3 : 2) conv_first_wgrad
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    if (piped && tile + (int)gridDim.x < p.ntiles) {
+      int n2, h2, w2;
+      f1_tile_origin(p, tile + gridDim.x, n2, h2, w2);
+      f1_fetch_patch(pre, p, n2, h2, w2);
+    }
     if (threadIdx.x == 0) {
       mbar_wait(&g_full[s], use & 1);
       tc_fence_after();

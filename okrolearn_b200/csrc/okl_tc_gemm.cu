@@ -119,6 +119,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int tm = t % p.tiles_m, tn = t / p.tiles_m;
         const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         const int m0 = tm * TC_BM, n0 = tn * BN;
+        // implicit-GEMM wgrad: the k-block index walks (w tile, h tile, image group); decoded once per work item and then advanced
+        // incrementally - the three divisions per k-block this used to cost (~400 dependent cycles in the single producer thread)
+        // were as long as the 4 MMAs of a k-block
+        int wg_wt = 0, wg_ht = 0, wg_ng = 0, wg_tap = 0, wg_c0 = 0, wg_u = 0, wg_v = 0;
+        int f_tap = 0, f_cb = 0, f_u = 0, f_v = 0, f_wt = 0, f_ht = 0, f_ng = 0;
+        if (MODE == 2) {
+          wg_wt = kb0 % p.cv_tiles_w;
+          const int r2 = kb0 / p.cv_tiles_w;
+          wg_ht = r2 % p.cv_tiles_h; wg_ng = r2 / p.cv_tiles_h;
+          wg_tap = n0 / p.cv_C; wg_c0 = n0 - wg_tap * p.cv_C;
+          wg_u = wg_tap / p.cv_kw; wg_v = wg_tap - wg_u * p.cv_kw;
+        }
         for (int kb = kb0; kb < kb1; kb++) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -128,18 +140,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (MODE == 1) {
             // implicit-GEMM fprop / dgrad: k-block = (filter tap, 32-channel chunk); the A tile is the TW x TH x TN pixel rectangle of
             // this M tile shifted by the tap - TMA zero-fills what falls outside the image, which IS the zero padding.
-            const int tap = kb / p.cv_cblocks, cb = kb - tap * p.cv_cblocks;
-            const int u = tap / p.cv_kw, v = tap - u * p.cv_kw;
-            const int wt = tm % p.cv_tiles_w, r2 = tm / p.cv_tiles_w;
-            const int ht = r2 % p.cv_tiles_h, ng = r2 / p.cv_tiles_h;
-            tma_load_4d(&tmA, &full_bar[stage], sa, cb * Cfg::BK, wt * p.cv_TW + v - p.cv_pw, ht * p.cv_TH + u - p.cv_ph, ng * p.cv_TN);
-            tma_load_2d(&tmB, &full_bar[stage], sb, tap * p.cv_C + cb * Cfg::BK, n0);
+            if (kb == kb0) {
+              f_tap = kb / p.cv_cblocks; f_cb = kb - f_tap * p.cv_cblocks;
+              f_u = f_tap / p.cv_kw; f_v = f_tap - f_u * p.cv_kw;
+              f_wt = tm % p.cv_tiles_w;
+              const int r2 = tm / p.cv_tiles_w;
+              f_ht = r2 % p.cv_tiles_h; f_ng = r2 / p.cv_tiles_h;
+            }
+            tma_load_4d(&tmA, &full_bar[stage], sa, f_cb * Cfg::BK, f_wt * p.cv_TW + f_v - p.cv_pw, f_ht * p.cv_TH + f_u - p.cv_ph, f_ng * p.cv_TN);
+            tma_load_2d(&tmB, &full_bar[stage], sb, f_tap * p.cv_C + f_cb * Cfg::BK, n0);
+            if (++f_cb == p.cv_cblocks) { f_cb = 0; f_tap++; if (++f_v == p.cv_kw) { f_v = 0; f_u++; } }
           } else if (MODE == 2) {
             // implicit-GEMM wgrad: M = O, N = (tap, c), k-block = 32 output pixels; A = g^T and B = shifted x, both MN-major
-            const int wt = kb % p.cv_tiles_w, r2 = kb / p.cv_tiles_w;
-            const int ht = r2 % p.cv_tiles_h, ng = r2 / p.cv_tiles_h;
-            const int tap = n0 / p.cv_C, c0 = n0 - tap * p.cv_C;
-            const int u = tap / p.cv_kw, v = tap - u * p.cv_kw;
+            const int wt = wg_wt, ht = wg_ht, ng = wg_ng, c0 = wg_c0, u = wg_u, v = wg_v;
 #pragma unroll
             for (int c = 0; c < TC_BM / Cfg::EPC; c++)
               tma_load_4d(&tmA, &full_bar[stage], sa + c * (Cfg::BK * 128), m0 + c * Cfg::EPC, wt * p.cv_TW, ht * p.cv_TH, ng * p.cv_TN);
@@ -147,6 +160,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c = 0; c < BN / Cfg::EPC; c++)
               tma_load_4d(&tmB, &full_bar[stage], sb + c * (Cfg::BK * 128), c0 + c * Cfg::EPC, wt * p.cv_TW + v - p.cv_pw,
                           ht * p.cv_TH + u - p.cv_ph, ng * p.cv_TN);
+            if (++wg_wt == p.cv_tiles_w) { wg_wt = 0; if (++wg_ht == p.cv_tiles_h) { wg_ht = 0; wg_ng++; } }
           } else {
           if (!A_MN) {
             tma_load_2d(&tmA, &full_bar[stage], sa, k0, m0);                       // box {BK, 128}: rows = m

@@ -452,12 +452,17 @@ class Tensor:
         a, b = self, other
 
         def backward_fn(grad):
+            # dA = G . B^T, dB = A^T . G (tensor.py:60-65) as device GEMMs: nothing of a backward pass runs on the host
+            g = grad if isinstance(grad, Tensor) else Tensor(np.asarray(grad, dtype=np.float64), requires_grad=False)
+            ctx_ = get_ctx()
             if a.requires_grad:
-                ga = np.dot(grad, b.data.T)
-                a.grad = ga if a.grad is None else a.grad + ga
+                ga = Tensor._empty((M, K), np.float64)
+                check(lib.okl_dense_bwd(ctx_.h, a._dptr(NCX), b._dptr(NCX), g._dptr(NCX), ga._ptr_raw(), None, None, M, K, N, None))
+                a._grad = ga if a._grad is None else (a._grad if isinstance(a._grad, Tensor) else Tensor(a._grad)) + ga
             if b.requires_grad:
-                gb = np.dot(a.data.T, grad)
-                b.grad = gb if b.grad is None else b.grad + gb
+                gb = Tensor._empty((K, N), np.float64)
+                check(lib.okl_dense_bwd(ctx_.h, a._dptr(NCX), b._dptr(NCX), g._dptr(NCX), None, gb._ptr_raw(), None, M, K, N, None))
+                b._grad = gb if b._grad is None else (b._grad if isinstance(b._grad, Tensor) else Tensor(b._grad)) + gb
 
         out.backward_fn = backward_fn
         return out
