@@ -26,6 +26,71 @@ constexpr int CT_NA = 3;
 constexpr int CT_STG = 4096;           // per epilogue warp: 32 rows x 128 B, swizzled like the TMA box it is stored from
 constexpr int CT_MAX_OC = 512;
 
+// ---- thread-block clusters.  (Tried first: clusters of 2 / 4 CTAs on different pixel tiles of the same output-channel tile with ONE
+// multicast TMA load per filter tile - parity-correct, but no faster at 2 and 2 x slower at 4 (lock-step coupling, 132 usable SMs):
+// the k loop is not bound by L2 -> SM traffic.  What it IS bound by, and the fix, follows below.)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+// ---- CTA pairs (tcgen05 cta_group::2): one MMA instruction, issued by the even CTA, computes a 256-row tile - 128 rows from each CTA's
+// A operand - against a filter tile whose N rows are split between the two CTAs' shared memories; each SM fetches its A rows plus HALF
+// of B per MMA.  The timelines showed the k loop bound by operand fetch from shared memory (~75 B/cycle/SM effective: 39 % of the
+// tensor peak at N = 64, 59 % at N = 128, 78 % at N = 256, matching (128 + N) x 32 B per 128 x N x 16 MMA), not by L2 traffic.
+constexpr uint32_t CT_PEER_MASK = 0xFEFFFFFFu;          // clears the CTA-pair rank bit of a shared-memory address: the EVEN CTA's copy
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all MMAs issued so far arrives on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// TMA loads of a CTA pair: the data lands in the executing CTA's shared memory, the bytes are counted on the EVEN CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & CT_PEER_MASK), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & CT_PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
+
 template <int BN>
 struct CtCfg {
   static constexpr int B_STAGE = BN * 128;
@@ -51,11 +116,12 @@ struct ConvTcParams {
   unsigned long long* dbg;
 };
 
-template <int BN>
+template <int BN, int PAIR>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY16,
                const __grid_constant__ CUtensorMap tmY32, const ConvTcParams p) {
   using Cfg = CtCfg<BN>;
+  constexpr int CS = PAIR ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -84,63 +150,79 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < CT_NA; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < Cfg::NB; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], 8); }
+    // pair mode: the even CTA's accumulator-free barrier collects the epilogue warps of BOTH CTAs
+    for (int a = 0; a < 2; a++) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], PAIR ? 16 : 8); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_cg2<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
   for (int i = threadIdx.x; i < CT_MAX_OC; i += CT_THREADS) bias_s[i] = (p.bias && i < p.Oc) ? __ldg(p.bias + i) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   okl_pdl_sync();
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  if (PAIR) cluster_sync_all();                             // both CTAs' barriers and TMEM exist before any cross-CTA signal
 
-  const int total = p.tiles_m * p.tiles_n;
+  // work units: (output-channel tile, group of CS consecutive pixel tiles); cluster c takes units c, c + #clusters, ...; CTA rank r
+  // of the pair takes pixel tile group * CS + r
+  const int total = (p.tiles_m / CS) * p.tiles_n;
+  const int unit0 = blockIdx.x / CS, unit_step = gridDim.x / CS;
 
   if (warp == 0) {
-    // ===================================================================== A producer: activation slabs / tap tiles
+    // ===================================================================== A producer: activation slabs / tap tiles (every CTA its own)
     if (elect_one()) {
       int st = 0;
       uint32_t ph_ = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        const int tm = w / p.tiles_n;
+      auto load = [&](int c0, int c1, int c2, int c3) {
+        mbar_wait(&a_empty[st], ph_ ^ 1);
+        if (PAIR) {
+          if (crank == 0) mbar_expect_tx(&a_full[st], 2 * p.a_bytes);       // both CTAs' boxes are counted on the even CTA's barrier
+          tma_load_4d_pair(&tmA, &a_full[st], sA + st * CT_A_STAGE, c0, c1, c2, c3);
+        } else {
+          mbar_expect_tx(&a_full[st], p.a_bytes);
+          tma_load_4d(&tmA, &a_full[st], sA + st * CT_A_STAGE, c0, c1, c2, c3);
+        }
+        if (++st == CT_NA) { st = 0; ph_ ^= 1; }
+      };
+      for (int w = unit0; w < total; w += unit_step) {
+        const int tm = (w / p.tiles_n) * CS + (int)crank;
         const int wt = tm % p.tiles_w, r2 = tm / p.tiles_w;
         const int ht = r2 % p.tiles_h, ng = r2 / p.tiles_h;
         const int w0 = wt * p.TW - p.pw, h0 = ht * p.TH - p.ph, n0 = ng * p.TN;
         for (int cb = 0; cb < p.cblocks; cb++) {
           for (int v = 0; v < p.KW; v++) {
-            if (p.slab) {
-              mbar_wait(&a_empty[st], ph_ ^ 1);
-              mbar_expect_tx(&a_full[st], p.a_bytes);
-              tma_load_4d(&tmA, &a_full[st], sA + st * CT_A_STAGE, cb * 64, w0 + v, h0, n0);
-              if (++st == CT_NA) { st = 0; ph_ ^= 1; }
-            } else {
-              for (int u = 0; u < p.KH; u++) {
-                mbar_wait(&a_empty[st], ph_ ^ 1);
-                mbar_expect_tx(&a_full[st], p.a_bytes);
-                tma_load_4d(&tmA, &a_full[st], sA + st * CT_A_STAGE, cb * 64, w0 + v, h0 + u, n0);
-                if (++st == CT_NA) { st = 0; ph_ ^= 1; }
-              }
-            }
+            if (p.slab) load(cb * 64, w0 + v, h0, n0);
+            else
+              for (int u = 0; u < p.KH; u++) load(cb * 64, w0 + v, h0 + u, n0);
           }
         }
       }
     }
   } else if (warp == 3) {
-    // ===================================================================== B producer: one filter tile per (chunk, tap)
+    // ===================================================================== B producer: one filter tile per (chunk, tap); in pair mode
+    // every CTA loads its half of the tile's N rows
     if (elect_one()) {
       int st = 0;
       uint32_t ph_ = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      for (int w = unit0; w < total; w += unit_step) {
         const int tn = w % p.tiles_n;
-        const int n_off = tn * BN;
+        const int n_off = tn * BN + (PAIR ? (int)crank * (BN / 2) : 0);
         for (int cb = 0; cb < p.cblocks; cb++) {
           for (int v = 0; v < p.KW; v++) {
             int kcol = v * p.C + cb * 64;                 // tap (u, v) -> column (u * KW + v) * C + cb * 64 of the K-major bank
             for (int u = 0; u < p.KH; u++, kcol += p.KW * p.C) {
               mbar_wait(&b_empty[st], ph_ ^ 1);
-              mbar_expect_tx(&b_full[st], Cfg::B_STAGE);
-              tma_load_2d(&tmB, &b_full[st], sB + st * Cfg::B_STAGE, kcol, n_off);
+              if (PAIR) {
+                if (crank == 0) mbar_expect_tx(&b_full[st], Cfg::B_STAGE);
+                tma_load_2d_pair(&tmB, &b_full[st], sB + st * Cfg::B_STAGE, kcol, n_off);
+              } else {
+                mbar_expect_tx(&b_full[st], Cfg::B_STAGE);
+                tma_load_2d(&tmB, &b_full[st], sB + st * Cfg::B_STAGE, kcol, n_off);
+              }
               if (++st == Cfg::NB) { st = 0; ph_ ^= 1; }
             }
           }
@@ -148,13 +230,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc(1, false, false, 128, BN);
+    // ===================================================================== MMA issuer (pair mode: the even CTA only, for both)
+    if (crank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc(1, false, false, PAIR ? 256 : 128, BN);
       int sa = 0, sb = 0, acc = 0;
       uint32_t pa = 0, pb = 0, pacc = 0;
       bool first_tile = true;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t accf) {
+        if (PAIR) umma_bf16_cg2(d, ad, bd, idesc, accf);
+        else umma<1>(d, ad, bd, idesc, accf);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (PAIR) umma_commit_pair(bar);
+        else umma_commit(bar);
+      };
+      for (int w = unit0; w < total; w += unit_step) {
         mbar_wait(&t_empty[acc], pacc ^ 1);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * BN);
@@ -179,24 +269,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint64_t bdesc = make_smem_desc(smem_u32(sB + sb * Cfg::B_STAGE), 16, 1024, 2);
 #pragma unroll
               for (int k = 0; k < 4; k++) {
-                umma<1>(d0, adesc0 + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum | (uint32_t)k);
-                umma<1>(d0 + BN, adesc1 + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum | (uint32_t)k);
+                mma(d0, adesc0 + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), accum | (uint32_t)k);
+                mma(d0 + BN, adesc1 + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), accum | (uint32_t)k);
               }
               accum = 1;
-              umma_commit(&b_empty[sb]);
+              commit(&b_empty[sb]);
               if (++sb == Cfg::NB) { sb = 0; pb ^= 1; }
               if (!p.slab) {
-                umma_commit(&a_empty[sa]);
+                commit(&a_empty[sa]);
                 if (++sa == CT_NA) { sa = 0; pa ^= 1; }
               }
             }
             if (p.slab) {
-              umma_commit(&a_empty[sa]);
+              commit(&a_empty[sa]);
               if (++sa == CT_NA) { sa = 0; pa ^= 1; }
             }
           }
         }
-        umma_commit(&t_full[acc]);
+        commit(&t_full[acc]);
         first_tile = false;
         if (Cfg::ACC == 2) { if (++acc == 2) { acc = 0; pacc ^= 1; } }
         else pacc ^= 1;
@@ -211,8 +301,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0, dbg_tile = 0;
     uint32_t pacc = 0;
     const uint32_t sw = (uint32_t)(lane & 7);
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
-      const int tm = w / p.tiles_n, tn = w - tm * p.tiles_n;
+    for (int w = unit0; w < total; w += unit_step) {
+      const int tn = w % p.tiles_n;
+      const int tm = (w / p.tiles_n) * CS + (int)crank;
       const int wt = tm % p.tiles_w, r2 = tm / p.tiles_w;
       const int ht = r2 % p.tiles_h, ng = r2 / p.tiles_h;
       const int w0 = wt * p.TW, h0 = ht * p.TH, n0 = ng * p.TN;
@@ -305,7 +396,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       dbg_tile++;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[acc]);
+      if (lane == 0) {
+        if (PAIR && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&t_empty[acc]), 0u));   // the issuing (even) CTA waits for both epilogues
+        else mbar_arrive(&t_empty[acc]);
+      }
       if (Cfg::ACC == 2) { if (++acc == 2) { acc = 0; pacc ^= 1; } }
       else pacc ^= 1;
     }
@@ -314,9 +408,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                             // no CTA leaves (or frees TMEM) while its peer may still signal it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc_cg2<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
   if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 3] = gtime();
 }
@@ -407,20 +503,38 @@ int ct_pow2_ceil(int v) { int q = 1; while (q < v) q <<= 1; return q; }
 int ct_ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 int ct_env(const char* name, int dflt) { const char* s = getenv(name); return s && *s ? atoi(s) : dflt; }
 
-template <int BN>
+template <int BN, int PAIR>
 int ct_launch(okl_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty16, const CUtensorMap& ty32, const ConvTcParams& p) {
   using Cfg = CtCfg<BN>;
-  auto kern = conv_tc_kernel<BN>;
+  constexpr int CS = PAIR ? 2 : 1;
+  auto kern = conv_tc_kernel<BN, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
     OKL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr_set = true;
   }
-  const int total = p.tiles_m * p.tiles_n;
-  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
-  okl_launch(ctx, kern, dim3(grid), dim3(CT_THREADS), Cfg::SMEM, ta, tb, ty16, ty32, p);
+  const int units = (p.tiles_m / CS) * p.tiles_n;
+  int clusters = ctx->sm_count / CS;
+  if (clusters > units) clusters = units;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(clusters * CS); cfg.blockDim = dim3(CT_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  memset(at, 0, sizeof(at));
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = PAIR ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, ta, tb, ty16, ty32, p);
   OKL_LAUNCHED(ctx, "conv_tc_kernel");
   return OKL_OK;
+}
+
+template <int BN>
+int ct_launch_cs(okl_ctx* ctx, int pair, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ty16, const CUtensorMap& ty32,
+                 const ConvTcParams& p) {
+  if (pair) return ct_launch<BN, 1>(ctx, ta, tb, ty16, ty32, p);
+  return ct_launch<BN, 0>(ctx, ta, tb, ty16, ty32, p);
 }
 
 struct CtShape { int N, C, O, H, W, KH, KW, PH, PW, OH, OW; };
@@ -467,10 +581,15 @@ int conv_tc_run(okl_ctx* ctx, const void* x16, int N, int H, int W, int Cc, cons
   p.bias = bias; p.relu = relu; p.mask = (const __nv_bfloat16*)mask16;
   p.want_f32 = y ? 1 : 0; p.want_b16 = y16 ? 1 : 0;
   p.dbg = (unsigned long long*)ctx->tc_dbg;
+  // CTA pairs (cta_group::2): two CTAs share every filter tile (each holds half of its rows); needs an even number of pixel tiles
+  // measured (batch 1024, us, pair vs single): 64->64 fprop 98 vs 120, dgrad 123 vs 160; 128->128 58 vs 70 (1 322 TFLOP/s), 68 vs 82;
+  // at BN = 256 the operand fetch is no longer the limit (61.7 single vs 64.5 pair) - those tiles stay single
+  int pair = ct_env("OKL_CT_PAIR", bn <= 128 ? 1 : 0) ? 1 : 0;
+  if (p.tiles_m % 2 != 0 || (p.tiles_m / 2) * p.tiles_n < ctx->sm_count / 4) pair = 0;
   CUtensorMap ta, tb, ty16, ty32;
   int s = ct_map_nhwc(&ta, x16, 2, Cc, W, H, N, 64, p.TW, p.slab ? p.TH + KH - 1 : p.TH, p.TN);
   if (s != OKL_OK) return s;
-  s = ct_map_2d(&tb, bank, (uint64_t)KH * KW * Cc, (uint64_t)Oc, 64, (uint32_t)bn);
+  s = ct_map_2d(&tb, bank, (uint64_t)KH * KW * Cc, (uint64_t)Oc, 64, (uint32_t)(pair ? bn / 2 : bn));
   if (s != OKL_OK) return s;
   // an absent output still needs a valid descriptor object (never dereferenced by the kernel): alias the other one
   s = ct_map_nhwc(&ty16, y16 ? y16 : (const void*)y, y16 ? 2 : 4, Oc, OW, OH, N, y16 ? 64 : 32, p.TW, p.RH, p.RN);
@@ -478,9 +597,9 @@ int conv_tc_run(okl_ctx* ctx, const void* x16, int N, int H, int W, int Cc, cons
   s = ct_map_nhwc(&ty32, y ? (const void*)y : y16, y ? 4 : 2, Oc, OW, OH, N, y ? 32 : 64, p.TW, p.RH, p.RN);
   if (s != OKL_OK) return s;
   switch (bn) {
-    case 64: return ct_launch<64>(ctx, ta, tb, ty16, ty32, p);
-    case 128: return ct_launch<128>(ctx, ta, tb, ty16, ty32, p);
-    default: return ct_launch<256>(ctx, ta, tb, ty16, ty32, p);
+    case 64: return ct_launch_cs<64>(ctx, pair, ta, tb, ty16, ty32, p);
+    case 128: return ct_launch_cs<128>(ctx, pair, ta, tb, ty16, ty32, p);
+    default: return ct_launch_cs<256>(ctx, pair, ta, tb, ty16, ty32, p);
   }
 }
 

@@ -59,8 +59,10 @@ PAR = [  # nd, N, C, spatial, O, k, p
 def parity():
     bad = 0
     for (nd, N, Cc, sp, Oc, k, p) in PAR:
-        for env in ({"OKL_CT_SLAB": "1"}, {"OKL_CT_SLAB": "0"}, {"OKL_CT_SLAB": "1", "OKL_CT_BN": "64"}, {"OKL_CT_SLAB": "1", "OKL_CT_BN": "256"}):
-            os.environ.pop("OKL_CT_BN", None)
+        for env in ({"OKL_CT_SLAB": "1"}, {"OKL_CT_SLAB": "0"}, {"OKL_CT_SLAB": "1", "OKL_CT_BN": "64"}, {"OKL_CT_SLAB": "1", "OKL_CT_BN": "256"},
+                    {"OKL_CT_SLAB": "1", "OKL_CT_PAIR": "0"}, {"OKL_CT_SLAB": "0", "OKL_CT_PAIR": "0"}, {"OKL_CT_SLAB": "0", "OKL_CT_PAIR": "1", "OKL_CT_BN": "64"}):
+            for k_ in ("OKL_CT_BN", "OKL_CT_CLUSTER", "OKL_CT_PAIR", "OKL_CT_SLAB"):
+                os.environ.pop(k_, None)
             os.environ.update(env)
             rng = np.random.default_rng(N * 100 + Cc + Oc)
             kt = O._tup(k, nd)
@@ -118,8 +120,8 @@ def parity():
             bad += not ok
             print(("ok  " if ok else "BAD ") + f"{nd}d N={N} C={Cc} sp={sp} O={Oc} k={k} p={p} {env}: fprop f32 {e32:.2e} b16 {e16:.2e} b16only {e16b:.2e} "
                   f"dgrad f32 {ed:.2e} b16only {ed16:.2e} wgrad dW {ew:.2e} db {eb:.2e}", flush=True)
-    os.environ.pop("OKL_CT_BN", None)
-    os.environ["OKL_CT_SLAB"] = "1"
+    for k_ in ("OKL_CT_BN", "OKL_CT_CLUSTER", "OKL_CT_PAIR", "OKL_CT_SLAB"):
+        os.environ.pop(k_, None)
     print("PARITY", "FAILED %d" % bad if bad else "all ok")
 
 
@@ -152,16 +154,17 @@ def perf():
         check(lib.okl_conv2_filter_banks(ctx.h, C.byref(d), W._dptr(), w2.ptr, wf.ptr))
         fl = 2.0 * N * S * S * Oc * Cc * 9
         row = f"L {Cc:3d}->{Oc:3d}@{S:2d}: "
-        for name, env in (("slab", {"OKL_CT_SLAB": "1"}), ("tap", {"OKL_CT_SLAB": "0"}), ("slab bn64", {"OKL_CT_SLAB": "1", "OKL_CT_BN": "64"}),
-                          ("slab bn256", {"OKL_CT_SLAB": "1", "OKL_CT_BN": "256"})):
-            os.environ.pop("OKL_CT_BN", None)
+        for name, env in (("slab", {"OKL_CT_SLAB": "1"}), ("tap", {"OKL_CT_SLAB": "0"}), ("slab single", {"OKL_CT_SLAB": "1", "OKL_CT_PAIR": "0"}),
+                          ("slab bn128", {"OKL_CT_SLAB": "1", "OKL_CT_BN": "128"}), ("slab bn128 single", {"OKL_CT_SLAB": "1", "OKL_CT_BN": "128", "OKL_CT_PAIR": "0"})):
+            for k_ in ("OKL_CT_BN", "OKL_CT_CLUSTER", "OKL_CT_PAIR", "OKL_CT_SLAB"):
+                os.environ.pop(k_, None)
             os.environ.update(env)
             t1 = timeit(lambda: check(lib.okl_conv2_fprop(ctx.h, C.byref(d), x16.ptr, w2.ptr, bias._dptr(), None, y16.ptr)))
             t2 = timeit(lambda: check(lib.okl_conv2_fprop(ctx.h, C.byref(d), x16.ptr, w2.ptr, bias._dptr(), y32.ptr, y16.ptr)))
             t3 = timeit(lambda: check(lib.okl_conv2_dgrad(ctx.h, C.byref(d0), g16.ptr, wf.ptr, None, dx16.ptr, x16.ptr)))
             t4 = timeit(lambda: check(lib.okl_conv2_dgrad(ctx.h, C.byref(d0), g16.ptr, wf.ptr, dx32.ptr, dx16.ptr, x16.ptr)))
             tw = -1.0
-            if name in ("slab", "tap"):
+            if name in ("slab", "tap") and lib.okl_conv2_wgrad_supported(ctx.h, C.byref(d0)):
                 os.environ["OKL_WG_MT"] = "2" if name == "slab" else "1"
                 dWb, dbb = _DevBuf(ctx, W.size * 4), _DevBuf(ctx, Oc * 4)
                 tw = timeit(lambda: check(lib.okl_conv2_wgrad(ctx.h, C.byref(d0), x16.ptr, g16.ptr, dWb.ptr, dbb.ptr)))
@@ -174,7 +177,7 @@ def perf():
 
 def timeline():
     lib.okl_debug_tc_timestamps.argtypes = [C.c_void_p, C.c_void_p]
-    N, Cc, Oc, S = 1024, 64, 64, 32
+    N, Cc, Oc, S = (int(v) for v in os.environ.get("TL_SHAPE", "1024,64,64,32").split(","))
     d = desc(2, N, Cc, Oc, (S, S), 3, 1, act=1)
     x16, y16 = _DevBuf(ctx, N * Cc * S * S * 2), _DevBuf(ctx, N * Oc * S * S * 2)
     check(lib.okl_memset(ctx.h, x16.ptr, 0x3c, x16.nbytes))
@@ -193,6 +196,7 @@ def timeline():
     check(lib.okl_d2h_async_raw(ctx.h, raw.ctypes.data, dbg.ptr, raw.nbytes)); ctx.sync()
     ts = raw[:148 * 8].reshape(148, 8).astype(np.int64)
     t0 = ts[:, 0][ts[:, 0] > 0].min()
+    print("shape", N, Cc, Oc, S)
     print("cta0 start / first A landed / end (us):", [(int(v) - t0) / 1e3 for v in ts[0, [0, 1, 3]]], " last CTA end", (ts[:, 3].max() - t0) / 1e3)
     tt = raw[148 * 8:148 * 8 + 48].astype(np.int64).reshape(24, 2)
     print("per-tile (acc_ready, epi_done) us, CTA 0:", [(round((a - t0) / 1e3, 2), round((b - t0) / 1e3, 2)) for a, b in tt if a][:14])
