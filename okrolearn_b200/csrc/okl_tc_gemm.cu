@@ -65,10 +65,13 @@ struct TcCfg {
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int KIND, bool A_MN, bool B_MN, int BN, int MODE = 0>
+// PAIR = 1 (bf16, MODE 0, no split-K): CTA pairs with tcgen05 cta_group::2 - one 256 x BN MMA per pair, every CTA holds its 128 rows of
+// A and HALF of the B tile, so the per-SM operand fetch from shared memory drops from (128 + BN) to (128 + BN / 2) rows per MMA.
+template <int KIND, bool A_MN, bool B_MN, int BN, int MODE = 0, int PAIR = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmParams p) {
   using Cfg = TcCfg<KIND, BN>;
+  static_assert(!PAIR || (KIND == 1 && MODE == 0), "pair mode: bf16 dense GEMM only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * Cfg::STAGE_BYTES);
@@ -94,29 +97,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 8);      // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], PAIR ? 16 : 8);      // one arrive per epilogue warp (pair mode: of both CTAs, on the even CTA)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_cg2<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   okl_pdl_sync();                          // barriers, TMEM and descriptor prefetch above overlap the predecessor's tail
   if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 1] = gtime();
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  if (PAIR) cluster_sync_all();
+  constexpr int CS = PAIR ? 2 : 1;
+  const int wstart = blockIdx.x / CS, wstep = gridDim.x / CS;       // pair mode: a work item is a PAIR of M tiles
 
-  const int total_work = p.tiles_m * p.tiles_n * p.splits;
+  const int total_work = (p.tiles_m / CS) * p.tiles_n * p.splits;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int split = w / (p.tiles_m * p.tiles_n);
-        const int t = w - split * (p.tiles_m * p.tiles_n);
-        const int tm = t % p.tiles_m, tn = t / p.tiles_m;
+      for (int w = wstart; w < total_work; w += wstep) {
+        const int tmg = p.tiles_m / CS;
+        const int split = w / (tmg * p.tiles_n);
+        const int t = w - split * (tmg * p.tiles_n);
+        const int tm = (t % tmg) * CS + (int)crank, tn = t / tmg;
         const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         const int m0 = tm * TC_BM, n0 = tn * BN;
         // implicit-GEMM wgrad: the k-block index walks (w tile, h tile, image group); decoded once per work item and then advanced
@@ -135,7 +146,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (!PAIR) mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          else if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::A_BYTES + Cfg::B_BYTES);
           const int k0 = kb * Cfg::BK;
           if (MODE == 1) {
             // implicit-GEMM fprop / dgrad: k-block = (filter tap, 32-channel chunk); the A tile is the TW x TH x TN pixel rectangle of
@@ -161,6 +173,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_4d(&tmB, &full_bar[stage], sb + c * (Cfg::BK * 128), c0 + c * Cfg::EPC, wt * p.cv_TW + v - p.cv_pw,
                           ht * p.cv_TH + u - p.cv_ph, ng * p.cv_TN);
             if (++wg_wt == p.cv_tiles_w) { wg_wt = 0; if (++wg_ht == p.cv_tiles_h) { wg_ht = 0; wg_ng++; } }
+          } else if (PAIR) {
+            // both CTAs' boxes are counted on the even CTA's barrier (armed there with the pair's total above); B: my half of the rows
+            if (!A_MN) {
+              tma_load_2d_pair(&tmA, &full_bar[stage], sa, k0, m0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < TC_BM / Cfg::EPC; c++) tma_load_2d_pair(&tmA, &full_bar[stage], sa + c * (Cfg::BK * 128), m0 + c * Cfg::EPC, k0);
+            }
+            if (!B_MN) {
+              tma_load_2d_pair(&tmB, &full_bar[stage], sb, k0, n0 + (int)crank * (BN / 2));      // tensor map box: BN / 2 rows
+            } else {
+              constexpr int HC = BN / Cfg::EPC / 2;
+#pragma unroll
+              for (int c = 0; c < HC; c++)
+                tma_load_2d_pair(&tmB, &full_bar[stage], sb + c * (Cfg::BK * 128), n0 + ((int)crank * HC + c) * Cfg::EPC, k0);
+            }
           } else {
           if (!A_MN) {
             tma_load_2d(&tmA, &full_bar[stage], sa, k0, m0);                       // box {BK, 128}: rows = m
@@ -183,8 +211,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc(KIND, A_MN, B_MN, TC_BM, BN);
+    if (crank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc(KIND, A_MN, B_MN, PAIR ? 2 * TC_BM : TC_BM, BN);
       // K-major: rows 128 B apart, 8-row groups 1024 B apart.  MN-major: 8 k-rows per 1024 B atom (SBO), next 128-byte
       // chunk along MN one region (BK rows x 128 B) further (LBO).
       constexpr uint32_t a_lbo = A_MN ? Cfg::BK * 128 : 16, b_lbo = B_MN ? Cfg::BK * 128 : 16;
@@ -196,8 +224,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int split = w / (p.tiles_m * p.tiles_n);
+      for (int w = wstart; w < total_work; w += wstep) {
+        const int split = w / ((p.tiles_m / CS) * p.tiles_n);
         const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -210,12 +238,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, a_lay);
           const uint64_t bdesc = make_smem_desc(sa + Cfg::A_BYTES, b_lbo, b_sbo, b_lay);
 #pragma unroll
-          for (int k = 0; k < Cfg::BK / Cfg::UMMA_K; k++)
-            umma<KIND>(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);                 // smem stage reusable once these MMAs have read it
+          for (int k = 0; k < Cfg::BK / Cfg::UMMA_K; k++) {
+            if (PAIR) umma_bf16_cg2(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma<KIND>(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          if (PAIR) umma_commit_pair(&empty_bar[stage]);  // both CTAs' producers
+          else umma_commit(&empty_bar[stage]);            // smem stage reusable once these MMAs have read it
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);                      // accumulator complete
+        if (PAIR) umma_commit_pair(&tfull_bar[acc]);
+        else umma_commit(&tfull_bar[acc]);                 // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -234,10 +266,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int c4 = (lane & 7) * 4, rsub = lane >> 3;
     constexpr int NCH = BN / 32;                     // 32-column chunks per tile
     constexpr int MYCH = (NCH + 1) / 2;              // chunks this warp may own
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      const int split = w / (p.tiles_m * p.tiles_n);
-      const int t = w - split * (p.tiles_m * p.tiles_n);
-      const int tm = t % p.tiles_m, tn = t / p.tiles_m;
+    for (int w = wstart; w < total_work; w += wstep) {
+      const int tmg = p.tiles_m / CS;
+      const int split = w / (tmg * p.tiles_n);
+      const int t = w - split * (tmg * p.tiles_n);
+      const int tm = (t % tmg) * CS + (int)crank, tn = t / tmg;
       const int n0 = tn * BN;
       const int m_base = tm * TC_BM + q * 32;
       // ---- accumulator-independent prefetch: bias values of my columns, output row of each of my 8 row slots
@@ -363,7 +396,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       dbg_tile++;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (PAIR && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0u));
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       if (p.splits > 1) {
         // Split-K fix-up without a second kernel.  All CTAs of a launch are co-resident (grid <= #SMs, one work item each
@@ -442,9 +478,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (p.dbg && threadIdx.x == 128) p.dbg[blockIdx.x * 8 + 4] = gtime();
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc_cg2<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
   if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 5] = gtime();
 }
@@ -518,6 +556,34 @@ int launch_cfg(okl_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const
   q.stages = total <= grid ? (kb < 2 ? 2 : (kb < Cfg::STAGES ? kb : Cfg::STAGES)) : Cfg::STAGES;   // one tile per CTA: no deeper than its K loop
   const int smem_bytes = Cfg::SMEM_BYTES - (Cfg::STAGES - q.stages) * Cfg::STAGE_BYTES;
   okl_launch(ctx, kern, dim3(grid), dim3(TC_THREADS), smem_bytes, ta, tb, q);
+  OKL_LAUNCHED(ctx, "tc_gemm_kernel");
+  return OKL_OK;
+}
+
+template <bool A_MN, bool B_MN, int BN>
+int launch_pair(okl_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const TcGemmParams& p) {
+  using Cfg = TcCfg<1, BN>;
+  auto kern = tc_gemm_kernel<1, A_MN, B_MN, BN, 0, 1>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OKL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int units = (p.tiles_m / 2) * p.tiles_n;
+  int clusters = ctx->sm_count / 2;
+  if (clusters > units) clusters = units;
+  TcGemmParams q = p;
+  q.stages = Cfg::STAGES;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(clusters * 2); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  memset(at, 0, sizeof(at));
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, ta, tb, q);
   OKL_LAUNCHED(ctx, "tc_gemm_kernel");
   return OKL_OK;
 }
@@ -608,7 +674,10 @@ int okl_tc_gemm_raw(okl_ctx* ctx, int kind, int a_mn, int b_mn, int M, int N, in
   if (!a_mn) s = make_map_2d(&ta, kind, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, bk, TC_BM);
   else s = make_map_2d(&ta, kind, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, epc, bk, kind == 0);
   if (s != OKL_OK) return s;
-  if (!b_mn) s = make_map_2d(&tb, kind, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, bk, bn);
+  // CTA pairs (cta_group::2) for the large bf16 products: full tiles only, an even number of M tiles, enough pairs to fill the chip
+  const bool pair = kind == 1 && splits == 1 && (bn == 128 || bn == 256) && tiles_m % 2 == 0 && N % bn == 0 && M % TC_BM == 0 &&
+                    (long long)(tiles_m / 2) * tiles_n >= ctx->sm_count / 2 && ctx->cur_lane == 0 && env_int("OKL_TC_PAIR", 1);
+  if (!b_mn) s = make_map_2d(&tb, kind, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, bk, pair ? bn / 2 : bn);
   else s = make_map_2d(&tb, kind, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, epc, bk, kind == 0);
   if (s != OKL_OK) return s;
 
@@ -630,6 +699,18 @@ int okl_tc_gemm_raw(okl_ctx* ctx, int kind, int a_mn, int b_mn, int M, int N, in
       OKL_CHECK_CUDA(cudaMemsetAsync(ctx->tile_counters, 0, 4096 * sizeof(int), ctx->stream));
     }
     p.counters = ctx->tile_counters;
+  }
+  if (pair) {
+    if (bn == 256) {
+      if (!a_mn && !b_mn) return launch_pair<false, false, 256>(ctx, ta, tb, p);
+      if (!a_mn && b_mn) return launch_pair<false, true, 256>(ctx, ta, tb, p);
+      if (a_mn && !b_mn) return launch_pair<true, false, 256>(ctx, ta, tb, p);
+      return launch_pair<true, true, 256>(ctx, ta, tb, p);
+    }
+    if (!a_mn && !b_mn) return launch_pair<false, false, 128>(ctx, ta, tb, p);
+    if (!a_mn && b_mn) return launch_pair<false, true, 128>(ctx, ta, tb, p);
+    if (a_mn && !b_mn) return launch_pair<true, false, 128>(ctx, ta, tb, p);
+    return launch_pair<true, true, 128>(ctx, ta, tb, p);
   }
   if (kind == 0) {
     if (!a_mn && !b_mn) s = launch_bn<0, false, false>(ctx, bn, ta, tb, p);

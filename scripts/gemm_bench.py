@@ -41,7 +41,7 @@ if __name__ == "__main__":
              (256, 128, 5408, 0, 0, 1), (5408, 128, 256, 0, 1, 1), (256, 5408, 128, 0, 0, 0)]
     out = []
     for (M, N, K, kind, a, b) in cases:
-        for env in ([{}] if M >= 4096 else [{}, {"OKL_TC_BN": "32"}, {"OKL_TC_BN": "64"}, {"OKL_TC_BN": "128"}]):
+        for env in ([{}, {"OKL_TC_PAIR": "0"}] if M >= 4096 else [{}, {"OKL_TC_BN": "32"}, {"OKL_TC_BN": "64"}, {"OKL_TC_BN": "128"}]):
             for k, v in env.items():
                 os.environ[k] = v
             try:

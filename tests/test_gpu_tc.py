@@ -29,7 +29,8 @@ def tc_gemm(okl, kind, a_mn, b_mn, A, B, bias=None, act=0):
 
 
 SHAPES = [(128, 128, 32), (128, 256, 64), (256, 128, 5408), (256, 5408, 128), (5408, 128, 256), (200, 72, 100), (1024, 1024, 1024),
-          (130, 36, 40), (64, 64, 64), (384, 640, 96), (8192, 512, 1024)]
+          (130, 36, 40), (64, 64, 64), (384, 640, 96), (8192, 512, 1024),
+          (4096, 2048, 256), (2048, 4096, 192)]      # enough 256-row tile pairs for the cta_group::2 path (bf16)
 
 
 @pytest.mark.parametrize("kind", [0, 1])
