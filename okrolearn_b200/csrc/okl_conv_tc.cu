@@ -691,28 +691,56 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       int st = 0;
       uint32_t ph_ = 0;
       uint32_t accum = 0;
+      // Everything of an A descriptor that does not change with the stage or the k group is fixed up front (leading-dimension offset
+      // = distance between the M tile's two chunk slots, start offset of slot and tap); the issue loop then costs an add, a shift and an
+      // OR per MMA - the first version rebuilt the descriptors in a triple loop and was issue-bound at N = 64 (32-cycle MMAs).
+      const uint32_t ones = smem_u32(sOnes);
+      const int nt = (nreal + p.has_db + 1) >> 1 < p.MT ? (nreal + p.has_db + 1) >> 1 : p.MT;     // M tiles with anything in them
+      uint64_t ahi[2];
+      uint32_t arel[2];
+      bool aabs[2];
+#pragma unroll
+      for (int t = 0; t < 2; t++) {
+        const bool r0 = 2 * t < nreal, r1 = 2 * t + 1 < nreal;
+        // slot 2t / 2t+1: real slabs (relative to the stage base) or the constant ones region (absolute)
+        const uint32_t a0 = r0 ? (uint32_t)(2 * t * WG_SLOT) : ones;
+        uint32_t lbo;
+        if (r0 && r1) lbo = WG_SLOT;
+        else if (r0) lbo = 0;                              // filled in per stage below: ones - (base + slot)
+        else lbo = 1024u;
+        aabs[t] = !r0;
+        arel[t] = a0;
+        ahi[t] = make_smem_desc(0, lbo, 1024, 2);
+      }
+      const uint64_t bhi = make_smem_desc(0, WG_GCH, 1024, 2);
       for (int kt = split; kt < p.ktiles; kt += p.splits) {
         mbar_wait(&full[st], ph_);
         tc_fence_after();
         const uint32_t base = smem_u32(sSt + st * p.stage_bytes);
         const uint32_t gb = base + (uint32_t)(p.nreal_max * WG_SLOT);
-        const uint32_t ones = smem_u32(sOnes);
+        uint64_t ah[2];
+        uint32_t ab[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+          ab[t] = aabs[t] ? arel[t] : base + arel[t];
+          const bool mixed = (2 * t < nreal) && !(2 * t + 1 < nreal);          // real slab + ones slot: the offset depends on the stage
+          ah[t] = mixed ? make_smem_desc(0, ones - ab[t], 1024, 2) : ahi[t];
+        }
         for (int kk = 0; kk < WG_PT / 16; kk++) {
           const int pix = kk * 16;
           const int img = pix >> p.pimg_sh, pin = pix & ((1 << p.pimg_sh) - 1);
           const uint32_t off0 = (uint32_t)(img * p.img_bytes + (pin >> p.tw_sh) * p.row_bytes + (pin & (p.TW - 1)) * 128);
-          const uint64_t bdesc = make_smem_desc(gb + (uint32_t)(kk * 2048), WG_GCH, 1024, 2);
-          for (int t = 0; t < p.MT; t++) {
-            if (2 * t >= nreal + p.has_db) break;          // nothing (not even the bias-gradient slot) lives in this M tile
-            // chunk slots 2t and 2t+1 of this CTA: real slabs or the ones region
-            const bool r0 = 2 * t < nreal, r1 = 2 * t + 1 < nreal;
-            const uint32_t a0 = r0 ? base + (uint32_t)(2 * t * WG_SLOT) : ones;
-            const uint32_t a1 = r1 ? base + (uint32_t)((2 * t + 1) * WG_SLOT) : (r0 ? ones : ones + 1024u);
-            const uint32_t lbo = a1 - a0;                  // same for every tap and k group (offsets are added to the start address)
-            for (int u = 0; u < p.KH; u++) {
-              const uint32_t off = off0 + (uint32_t)(u * p.row_bytes);
-              const uint64_t adesc = make_smem_desc(a0 + off, lbo, 1024, 2);
-              umma<1>(tmem_base + (uint32_t)((t * p.KH + u) * BN), adesc, bdesc, idesc, accum);
+          const uint64_t bdesc = bhi | (uint64_t)(((gb + (uint32_t)(kk * 2048)) & 0x3FFFFu) >> 4);
+#pragma unroll
+          for (int t = 0; t < 2; t++) {
+            if (t < nt) {
+#pragma unroll
+              for (int u = 0; u < 7; u++) {
+                if (u < p.KH) {
+                  const uint32_t addr = ab[t] + off0 + (uint32_t)(u * p.row_bytes);
+                  umma<1>(tmem_base + (uint32_t)((t * p.KH + u) * BN), ah[t] | (uint64_t)((addr & 0x3FFFFu) >> 4), bdesc, idesc, accum);
+                }
+              }
             }
           }
           accum = 1;

@@ -164,6 +164,7 @@ def perf():
             t3 = timeit(lambda: check(lib.okl_conv2_dgrad(ctx.h, C.byref(d0), g16.ptr, wf.ptr, None, dx16.ptr, x16.ptr)))
             t4 = timeit(lambda: check(lib.okl_conv2_dgrad(ctx.h, C.byref(d0), g16.ptr, wf.ptr, dx32.ptr, dx16.ptr, x16.ptr)))
             tw = -1.0
+            os.environ["OKL_WG_ALL"] = "1"
             if name in ("slab", "tap") and lib.okl_conv2_wgrad_supported(ctx.h, C.byref(d0)):
                 os.environ["OKL_WG_MT"] = "2" if name == "slab" else "1"
                 dWb, dbb = _DevBuf(ctx, W.size * 4), _DevBuf(ctx, Oc * 4)
