@@ -965,7 +965,7 @@ __device__ __forceinline__ void f1_build_ktab(int* ktab, const F1Params& p) {
 
 __device__ __forceinline__ void f1_load_patch(float* patch, const F1Params& p, int n, int h0, int w0) {
   const int per_c = p.PH * p.PWp, total = p.C * per_c;
-  for (int i = threadIdx.x; i < total; i += F1_THREADS) {
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int c = i / per_c, r2 = i - c * per_c, r = r2 / p.PWp, col = r2 - r * p.PWp;
     const int ih = h0 - p.ph + r, iw = w0 - p.pw + col;
     float v = 0.f;
@@ -976,13 +976,13 @@ __device__ __forceinline__ void f1_load_patch(float* patch, const F1Params& p, i
 
 // Software pipelining of the patch: a tile's values are fetched into registers one tile ahead (while the previous tile's MMA and
 // epilogue run) and only copied to shared memory at the top of the tile - ncu had both kernels waiting on these global loads.
-constexpr int F1_PRE = 4;              // values per thread held ahead (patches up to 1024 floats; larger ones load directly)
+constexpr int F1_PRE = 6;              // values per thread held ahead (patches up to 6 x threads floats; larger ones load directly)
 
 __device__ __forceinline__ void f1_fetch_patch(float* pre, const F1Params& p, int n, int h0, int w0) {
   const int per_c = p.PH * p.PWp, total = p.C * per_c;
 #pragma unroll
   for (int e = 0; e < F1_PRE; e++) {
-    const int i = threadIdx.x + e * F1_THREADS;
+    const int i = threadIdx.x + e * blockDim.x;
     float v = 0.f;
     if (i < total) {
       const int c = i / per_c, r2 = i - c * per_c, r = r2 / p.PWp, col = r2 - r * p.PWp;
@@ -995,7 +995,7 @@ __device__ __forceinline__ void f1_fetch_patch(float* pre, const F1Params& p, in
 __device__ __forceinline__ void f1_store_patch(float* patch, const float* pre, int total) {
 #pragma unroll
   for (int e = 0; e < F1_PRE; e++) {
-    const int i = threadIdx.x + e * F1_THREADS;
+    const int i = threadIdx.x + e * blockDim.x;
     if (i < total) patch[i] = pre[e];
   }
 }
@@ -1005,37 +1005,42 @@ __device__ __forceinline__ void f1_tile_origin(const F1Params& p, int tile, int&
   n = r2 / p.tiles_h; w0 = wt * p.TW; h0 = ht * p.TH;
 }
 
-// thread (pixel m, half): 16 of the 32 k values of row m of the 128 x 32 patch operand, as two swizzled 16-byte chunks
+// thread (pixel m, part): 32 / (threads / 128) of the 32 k values of row m of the 128 x 32 patch operand, as swizzled 16-byte chunks
 __device__ __forceinline__ void f1_build_rows(uint8_t* sA, const float* patch, const int* ktab, const F1Params& p, bool pixel_ok) {
-  const int m = threadIdx.x & 127, half = threadIdx.x >> 7;
+  const int m = threadIdx.x & 127, part = threadIdx.x >> 7;
+  const int cpt = 4 / (blockDim.x >> 7);                    // chunks per thread: 4 (128 threads) or 2 (256 threads)
   const int base = (m >> p.tw_sh) * p.PWp + (m & (p.TW - 1));
 #pragma unroll
-  for (int jj = 0; jj < 2; jj++) {
-    const int j = half * 2 + jj;
-    uint32_t pk[4];
+  for (int jj = 0; jj < 4; jj++) {
+    if (jj < cpt) {
+      const int j = part * cpt + jj;
+      uint32_t pk[4];
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      float f[2];
+      for (int e = 0; e < 4; e++) {
+        float f[2];
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int off = ktab[j * 8 + e * 2 + h];
-        f[h] = off >= 0 ? patch[off + base] : (off == -1 && pixel_ok ? 1.f : 0.f);
+        for (int h = 0; h < 2; h++) {
+          const int off = ktab[j * 8 + e * 2 + h];
+          f[h] = off >= 0 ? patch[off + base] : (off == -1 && pixel_ok ? 1.f : 0.f);
+        }
+        __nv_bfloat162 t = __floats2bfloat162_rn(f[0], f[1]);
+        pk[e] = *reinterpret_cast<uint32_t*>(&t);
       }
-      __nv_bfloat162 t = __floats2bfloat162_rn(f[0], f[1]);
-      pk[e] = *reinterpret_cast<uint32_t*>(&t);
+      *reinterpret_cast<uint4*>(sA + m * 128 + ((j ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
-    *reinterpret_cast<uint4*>(sA + m * 128 + ((j ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
-template <int O_>
-__global__ void __launch_bounds__(F1_THREADS, O_ == 64 ? 3 : 2) conv_first_fprop_kernel(const __grid_constant__ CUtensorMap tmY16, const F1Params p) {
+// NT = 128 (O = 64): small CTAs, five per SM - the tile loop is a chain of latencies (patch -> operand rows -> MMA -> TMEM -> store), and
+// more resident CTAs hide it better than more threads per CTA (three 256-thread CTAs: 80 us; ncu: "long scoreboard" on the patch)
+template <int O_, int NT>
+__global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) conv_first_fprop_kernel(const __grid_constant__ CUtensorMap tmY16, const F1Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                       // 128 rows x 128 B (first 64 B of every row used)
   uint8_t* sB = sA + 16384;                                 // O_ rows x 128 B
-  uint8_t* sStg = sB + O_ * 128;                            // 8 warps x 4 KB
-  uint64_t* mma_done = reinterpret_cast<uint64_t*>(sStg + 8 * CT_STG);
+  uint8_t* sStg = sB + O_ * 128;                            // one 4 KB staging tile per warp
+  uint64_t* mma_done = reinterpret_cast<uint64_t*>(sStg + (NT / 32) * CT_STG);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
   int* ktab = reinterpret_cast<int*>(mma_done + 2);
   float* patch = reinterpret_cast<float*>(ktab + F1_KP);
@@ -1048,7 +1053,7 @@ __global__ void __launch_bounds__(F1_THREADS, O_ == 64 ? 3 : 2) conv_first_fprop
   }
   if (warp == 0) tmem_alloc<O_>(tmem_slot);
   f1_build_ktab(ktab, p);
-  for (int i = threadIdx.x; i < O_ * F1_KP; i += F1_THREADS) {      // [W | b | 0] as bf16, K-major, swizzled
+  for (int i = threadIdx.x; i < O_ * F1_KP; i += NT) {      // [W | b | 0] as bf16, K-major, swizzled
     const int o = i / F1_KP, k = i - o * F1_KP;
     float v = 0.f;
     if (o < p.O) v = k < p.K ? __ldg(p.W + (size_t)o * p.K + k) : (k == p.K && p.bias ? __ldg(p.bias + o) : 0.f);
@@ -1067,7 +1072,7 @@ __global__ void __launch_bounds__(F1_THREADS, O_ == 64 ? 3 : 2) conv_first_fprop
   const uint32_t sw = (uint32_t)(lane & 7);
   uint32_t parity = 0;
   const int ptotal = p.C * p.PH * p.PWp;
-  const bool piped = ptotal <= F1_PRE * F1_THREADS;
+  const bool piped = ptotal <= F1_PRE * NT;
   float pre[F1_PRE];
   if (piped && (int)blockIdx.x < p.ntiles) {
     int n, h0, w0;
@@ -1104,7 +1109,7 @@ __global__ void __launch_bounds__(F1_THREADS, O_ == 64 ? 3 : 2) conv_first_fprop
     const int pbase = q * 32;
     const int bh = h0 + (pbase >> p.tw_sh);
 #pragma unroll 1
-    for (int ch = (warp >> 2); ch < O_ / 64; ch += 2) {
+    for (int ch = (warp >> 2); ch < O_ / 64; ch += NT / 128) {
       uint32_t v0[32], v1[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 64);
       tmem_ld32(taddr, v0);
@@ -1311,16 +1316,17 @@ extern "C" int okl_conv_first_fprop(okl_ctx* ctx, const okl_conv_desc* d, const 
   CUtensorMap ty;
   int s = ct_map_nhwc(&ty, y16, 2, p.O, p.OW, p.OH, p.N, 64, p.TW, p.RH, 1);
   if (s != OKL_OK) return s;
-  const int per_sm = opad == 64 ? 3 : 2;
+  const int nt = opad == 64 ? 128 : 256;
+  const int per_sm = opad == 64 ? 5 : 2;
   const int grid = p.ntiles < per_sm * ctx->sm_count ? p.ntiles : per_sm * ctx->sm_count;
-  const int smem = 16384 + opad * 128 + 8 * CT_STG + 64 + F1_KP * 4 + p.C * p.PH * p.PWp * 4 + 1024;
-#define F1_FP(OO)                                                                                                     \
+  const int smem = 16384 + opad * 128 + (nt / 32) * CT_STG + 64 + F1_KP * 4 + p.C * p.PH * p.PWp * 4 + 1024;
+#define F1_FP(OO, NT_)                                                                                                \
   {                                                                                                                   \
     static int set = 0;                                                                                               \
-    if (set < smem) { OKL_CHECK_CUDA(cudaFuncSetAttribute(conv_first_fprop_kernel<OO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = 100 * 1024; } \
-    okl_launch(ctx, conv_first_fprop_kernel<OO>, dim3(grid), dim3(F1_THREADS), smem, ty, p);                           \
+    if (set < smem) { OKL_CHECK_CUDA(cudaFuncSetAttribute(conv_first_fprop_kernel<OO, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = 100 * 1024; } \
+    okl_launch(ctx, conv_first_fprop_kernel<OO, NT_>, dim3(grid), dim3(NT_), smem, ty, p);                             \
   }
-  if (opad == 64) F1_FP(64) else if (opad == 128) F1_FP(128) else F1_FP(256)
+  if (opad == 64) F1_FP(64, 128) else if (opad == 128) F1_FP(128, 256) else F1_FP(256, 256)
 #undef F1_FP
   OKL_LAUNCHED(ctx, "conv_first_fprop");
   return OKL_OK;
