@@ -101,9 +101,10 @@ int okl_gather_batch(okl_ctx* ctx, void* x_dst, const void* x_src, long long x_r
  * okl_batch_prefetch: okl_gather_batch into input slot 0/1 on the copy stream, ordered after everything enqueued so far on the
  * compute stream (so the slot's previous consumer is finished); okl_batch_wait: the compute stream waits for that slot.
  * x_nxc_dst (optional): additionally a channels-last (N, S, C) copy of the gathered inputs, for a first layer that runs
- * channels-last on the tensor cores - its layout permutation then overlaps the previous step too. */
+ * channels-last on the tensor cores - its layout permutation then overlaps the previous step too; x_nxc_bf16 != 0: that copy
+ * is written as bf16 (okl_to_bf16_nxc: permutation and conversion in one pass), the operand format of the BF16 convolutions. */
 int okl_batch_prefetch(okl_ctx* ctx, int slot, void* x_dst, const void* x_src, long long x_row_elems, void* t_dst, const void* t_src,
-                       long long t_row_elems, const void* idx_i32, long long rows, void* x_nxc_dst, int x_channels);
+                       long long t_row_elems, const void* idx_i32, long long rows, void* x_nxc_dst, int x_channels, int x_nxc_bf16);
 int okl_batch_wait(okl_ctx* ctx, int slot);
 /* Per-step loss read-back (okl.py:2973 reads loss.data every batch) without stalling the device: _async copies the device scalar
  * to page-locked host memory in stream order (slot 0/1), _wait blocks the host until that copy has landed and returns it - called
@@ -336,6 +337,14 @@ int okl_pool2_bf16_supported(int C, int H, int W);
 int okl_pool2_bf16_fwd(okl_ctx* ctx, const void* x16, void* y16, int N, int C, int H, int W);
 int okl_pool2_bf16_bwd(okl_ctx* ctx, const void* x16, const void* g16, void* dx16, int N, int C, int H, int W, int relu_mask, void* db);
 int okl_channel_sum_bf16(okl_ctx* ctx, const void* g16, void* out, long long rows, int C);
+/* Crossing layout AND precision in one pass (32-channel x 128-position shared-memory tiles).  okl_to_bf16_nxc: the caller's fp32
+ * (N, C, S) tensor -> the bf16 (N, S, C) operand of the tensor-core convolutions (replaces okl_permute + okl_to_bf16: the im2col +
+ * cast of okl.py:691-699, 948-957 never exists).  okl_mse_fwd_bwd_nxc_bf16: MSELoss (okl.py:1833-1839) of bf16 (N, S, C) outputs
+ * against fp32 (N, C, S) targets; loss (fp32 scalar, mean over N*C*S), gradient 2 (o - t) / denom as bf16 (N, S, C), optionally
+ * with the backward of the ReLU that produced the outputs (okl.py:107).  C % 8 == 0. */
+int okl_to_bf16_nxc(okl_ctx* ctx, const void* src_ncx_f32, void* dst_nxc_bf16, int N, int C, long long S);
+int okl_mse_fwd_bwd_nxc_bf16(okl_ctx* ctx, const void* o16_nxc, const void* t_ncx, void* loss, void* grad16_nxc, int N, int C, long long S,
+                             float denom, void* loss_accum, int relu_outputs);
 
 /* BF16 implicit-GEMM convolution on tcgen05, second generation (csrc/okl_conv_tc.cu): replaces the contraction of
  * Conv1DLayer/Conv2DLayer.forward (okl.py:700-711, 801-811) and of their input-gradient loops (okl.py:722-740, 854-868 with repairs

@@ -13,6 +13,11 @@
 
 namespace {
 
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -172,7 +177,145 @@ __global__ void chansum_stage2(const float* __restrict__ partial, float* __restr
 
 bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+// ------------------------------------------------------------------------------------------------ layout-crossing kernels
+// The caller's tensors are fp32 (N, C, S) (reference layout); the tensor-core convolutions read and write bf16 (N, S, C).  These two
+// kernels cross both the layout and the precision in ONE pass through a shared-memory tile of 32 channels x 128 positions (512-byte
+// global rows on the fp32 side, 64-byte channel groups on the bf16 side; tile[c][s] with a 129-word pitch: the transposed reads of a
+// warp - 4 channel groups x 8 positions - hit 32 different banks).
+constexpr int XT_C = 32, XT_S = 128, XT_PITCH = XT_S + 1;
+
+// fills tile[c][s] with src[n][c0 + c][s0 + s] (zero outside the tensor); 256 threads
+__device__ __forceinline__ void xt_load_tile(float* tile, const float* __restrict__ src, size_t img, int Cc, long long S, int c0, long long s0, bool vec) {
+  if (vec) {
+#pragma unroll
+    for (int k = 0; k < XT_C * XT_S / 4 / 256; k++) {
+      const int idx = threadIdx.x + k * 256, c = idx >> 5, q = idx & 31;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c0 + c < Cc && s0 + q * 4 < S) v = __ldcs(reinterpret_cast<const float4*>(src + img + (size_t)(c0 + c) * S + s0 + q * 4));
+      float* d = tile + c * XT_PITCH + q * 4;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < XT_C * XT_S; idx += 256) {
+      const int c = idx >> 7, sp = idx & 127;
+      tile[c * XT_PITCH + sp] = (c0 + c < Cc && s0 + sp < S) ? __ldcs(src + img + (size_t)(c0 + c) * S + s0 + sp) : 0.f;
+    }
+  }
+}
+
+// x (N, C, S) fp32 -> x16 (N, S, C) bf16; C % 8 == 0
+__global__ void __launch_bounds__(256) to_bf16_nxc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int Cc, long long S, int vec) {
+  __shared__ float tile[XT_C * XT_PITCH];
+  const size_t img = (size_t)blockIdx.z * Cc * S;
+  const int c0 = blockIdx.x * XT_C;
+  const long long s0 = (long long)blockIdx.y * XT_S;
+  xt_load_tile(tile, x, img, Cc, S, c0, s0, vec != 0);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < XT_S * (XT_C / 8) / 256; k++) {
+    const int item = threadIdx.x + k * 256, sp = item >> 2, ch = item & 3;
+    if (s0 + sp < S && c0 + ch * 8 < Cc) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) f[j] = tile[(ch * 8 + j) * XT_PITCH + sp];
+      *reinterpret_cast<uint4*>(y + img + (size_t)(s0 + sp) * Cc + c0 + ch * 8) = pack8(f);
+    }
+  }
+}
+
+// MSELoss on the bf16 channels-last outputs of a tensor-core convolution against fp32 (N, C, S) targets (okl.py:1833-1839):
+// partial sums of (o - t)^2 and the gradient 2 (o - t) / denom as bf16 (N, S, C) - with RELU the backward of the ReLU that produced
+// the outputs (g * (o > 0), okl.py:107) is applied in the same pass.  Neither tensor is permuted or converted in memory.
+template <bool RELU>
+__global__ void __launch_bounds__(256) mse_nxc_bf16_kernel(const __nv_bfloat16* __restrict__ o, const float* __restrict__ t, float* __restrict__ partial,
+                                                           __nv_bfloat16* __restrict__ grad, int Cc, long long S, float scale, int vec) {
+  __shared__ float tile[XT_C * XT_PITCH];
+  __shared__ float sh[8];
+  const size_t img = (size_t)blockIdx.z * Cc * S;
+  const int c0 = blockIdx.x * XT_C;
+  const long long s0 = (long long)blockIdx.y * XT_S;
+  xt_load_tile(tile, t, img, Cc, S, c0, s0, vec != 0);
+  __syncthreads();
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < XT_S * (XT_C / 8) / 256; k++) {
+    const int item = threadIdx.x + k * 256, sp = item >> 2, ch = item & 3;
+    if (s0 + sp < S && c0 + ch * 8 < Cc) {
+      const size_t i = img + (size_t)(s0 + sp) * Cc + c0 + ch * 8;
+      float ov[8], g[8];
+      unpack8(__ldcs(reinterpret_cast<const uint4*>(o + i)), ov);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float d = ov[j] - tile[(ch * 8 + j) * XT_PITCH + sp];
+        acc += d * d;
+        g[j] = (RELU && !(ov[j] > 0.f)) ? 0.f : d * scale;
+      }
+      *reinterpret_cast<uint4*>(grad + i) = pack8(g);
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) tot += sh[w];                // fixed order
+    partial[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+  }
+}
+
+// loss = scale * sum(partial) in a fixed order (one block)
+__global__ void mse_final_sum_kernel(const float* __restrict__ partial, int count, float* __restrict__ out, float scale, float* __restrict__ acc) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) s += partial[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += sh[w];
+    out[0] = tot * scale;
+    if (acc) acc[0] += tot * scale;
+  }
+}
+
 }  // namespace
+
+extern "C" int okl_to_bf16_nxc(okl_ctx* ctx, const void* src_ncx_f32, void* dst_nxc_bf16, int N, int Cc, long long S) {
+  OKL_REQUIRE(ctx && src_ncx_f32 && dst_nxc_bf16, "NULL argument");
+  OKL_REQUIRE(N >= 1 && Cc >= 8 && Cc % 8 == 0 && S >= 1, "okl_to_bf16_nxc: C must be a multiple of 8 (N=%d C=%d)", N, Cc);
+  dim3 grid((unsigned)((Cc + XT_C - 1) / XT_C), (unsigned)((S + XT_S - 1) / XT_S), (unsigned)N);
+  OKL_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "okl_to_bf16_nxc: extent too large");
+  const int vec = (S % 4 == 0 && (reinterpret_cast<uintptr_t>(src_ncx_f32) & 15) == 0) ? 1 : 0;
+  to_bf16_nxc_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)src_ncx_f32, (__nv_bfloat16*)dst_nxc_bf16, Cc, S, vec);
+  OKL_LAUNCHED(ctx, "to_bf16_nxc");
+  return OKL_OK;
+}
+
+extern "C" int okl_mse_fwd_bwd_nxc_bf16(okl_ctx* ctx, const void* o16_nxc, const void* t_ncx, void* loss, void* grad16_nxc, int N, int Cc, long long S,
+                                        float denom, void* loss_accum, int relu_outputs) {
+  OKL_REQUIRE(ctx && o16_nxc && t_ncx && loss && grad16_nxc, "NULL argument");
+  OKL_REQUIRE(N >= 1 && Cc >= 8 && Cc % 8 == 0 && S >= 1 && denom > 0.f, "okl_mse_fwd_bwd_nxc_bf16: C must be a multiple of 8 (N=%d C=%d)", N, Cc);
+  dim3 grid((unsigned)((Cc + XT_C - 1) / XT_C), (unsigned)((S + XT_S - 1) / XT_S), (unsigned)N);
+  OKL_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "okl_mse_fwd_bwd_nxc_bf16: extent too large");
+  const size_t nblk = (size_t)grid.x * grid.y * grid.z;
+  OKL_REQUIRE(nblk < (1u << 30), "okl_mse_fwd_bwd_nxc_bf16: too many tiles");
+  int s = okl_ensure_workspace(ctx, nblk * sizeof(float));
+  if (s != OKL_OK) return s;
+  float* partial = (float*)ctx->workspace;
+  const int vec = (S % 4 == 0 && (reinterpret_cast<uintptr_t>(t_ncx) & 15) == 0) ? 1 : 0;
+  if (relu_outputs)
+    mse_nxc_bf16_kernel<true><<<grid, 256, 0, ctx->stream>>>((const __nv_bfloat16*)o16_nxc, (const float*)t_ncx, partial, (__nv_bfloat16*)grad16_nxc, Cc, S,
+                                                             2.f / denom, vec);
+  else
+    mse_nxc_bf16_kernel<false><<<grid, 256, 0, ctx->stream>>>((const __nv_bfloat16*)o16_nxc, (const float*)t_ncx, partial, (__nv_bfloat16*)grad16_nxc, Cc, S,
+                                                              2.f / denom, vec);
+  OKL_LAUNCHED(ctx, "mse_fwd_bwd_nxc_bf16");
+  mse_final_sum_kernel<<<1, 1024, 0, ctx->stream>>>((const float*)partial, (int)nblk, (float*)loss, 1.f / ((float)N * (float)Cc * (float)S), (float*)loss_accum);
+  OKL_LAUNCHED(ctx, "final_sum");
+  return OKL_OK;
+}
 
 extern "C" int okl_from_bf16(okl_ctx* ctx, const void* src_bf16, void* dst_f32, size_t n) {
   OKL_REQUIRE(ctx && (n == 0 || (src_bf16 && dst_f32)), "NULL argument");

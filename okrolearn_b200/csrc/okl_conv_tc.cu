@@ -70,6 +70,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* t_full = b_empty + Cfg::NB;
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  volatile uint32_t* loop_par = reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 256);
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
 
   const int warp = threadIdx.x >> 5;
@@ -94,6 +95,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   }
   for (int i = threadIdx.x; i < CT_MAX_OC; i += CT_THREADS) bias_s[i] = (p.bias && i < p.Oc) ? __ldg(p.bias + i) : 0.f;
+  if (threadIdx.x == 0) {
+    loop_par[0] = p.slab ? 1u : 0u;
+    loop_par[1] = (uint32_t)p.sub_bytes >> 4;
+    loop_par[2] = p.slab ? (uint32_t)p.row_bytes >> 4 : 0u;
+    loop_par[3] = (uint32_t)p.KH;
+    loop_par[4] = (uint32_t)(p.cblocks * p.KW);
+    loop_par[5] = p.dbg ? 1u : 0u;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -166,64 +175,73 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (pair mode: the even CTA only, for both)
+    // A lean single-thread loop: per tap one barrier wait, one multiply-add per descriptor low word, eight MMAs, one commit.  (The first
+    // version rebuilt three 64-bit descriptors per tap, re-read run-time flags from constant memory and fenced after every wait - ~100
+    // dependent scalar instructions per tap against 256 cycles of tensor work at N = 64: issuing every MMA twice cost only 13 %.)
     if (crank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc(1, false, false, PAIR ? 256 : 128, BN);
-      int sa = 0, sb = 0, acc = 0;
+      constexpr uint32_t HI = TC_DESC_HI_SW128;
+      constexpr uint32_t A16 = CT_A_STAGE >> 4, B16 = Cfg::B_STAGE >> 4;
+      const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);      // LBO = 16 B (unused by K-major swizzled operands)
+      const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t af0 = smem_u32(a_full), ae0 = smem_u32(a_empty), bf0 = smem_u32(b_full), be0 = smem_u32(b_empty);
+      const uint32_t tf0 = smem_u32(t_full), te0 = smem_u32(t_empty);
+      // run-time parameters of the loop come from shared memory (written in the prologue): read from the kernel parameters, ptxas
+      // re-loads them from constant memory in every iteration, and each of those loads stalls the chain
+      const bool slab = loop_par[0] != 0;
+      const uint32_t sub16 = loop_par[1], row16 = loop_par[2];
+      const int KH = (int)loop_par[3], nv = (int)loop_par[4];
+      uint32_t sa = 0, sb = 0, acc = 0;
       uint32_t pa = 0, pb = 0, pacc = 0;
-      bool first_tile = true;
-      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t accf) {
-        if (PAIR) umma_bf16_cg2(d, ad, bd, idesc, accf);
-        else umma<1>(d, ad, bd, idesc, accf);
-      };
-      auto commit = [&](uint64_t* bar) {
-        if (PAIR) umma_commit_pair(bar);
-        else umma_commit(bar);
+      bool want_ts = loop_par[5] != 0;                     // debug timeline: when the first activation slab landed
+      auto commit = [&](uint32_t bar) {
+        if (PAIR) umma_commit_pair_a(bar);
+        else umma_commit_a(bar);
       };
       for (int w = unit0; w < total; w += unit_step) {
-        mbar_wait(&t_empty[acc], pacc ^ 1);
+        mbar_wait_a(te0 + acc * 8, pacc ^ 1);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(acc * 2 * BN);
+        const uint32_t d0 = tmem_base + acc * (uint32_t)(2 * BN);
         uint32_t accum = 0;
-        for (int cb = 0; cb < p.cblocks; cb++) {
-          for (int v = 0; v < p.KW; v++) {
-            if (p.slab) {
-              mbar_wait(&a_full[sa], pa);
-              tc_fence_after();
-              if (p.dbg && first_tile && cb == 0 && v == 0) p.dbg[blockIdx.x * 8 + 1] = gtime();
-            }
-            for (int u = 0; u < p.KH; u++) {
-              if (!p.slab) {
-                mbar_wait(&a_full[sa], pa);
-                tc_fence_after();
-              }
-              mbar_wait(&b_full[sb], pb);
-              tc_fence_after();
-              const uint32_t a_addr = smem_u32(sA + sa * CT_A_STAGE) + (p.slab ? (uint32_t)(u * p.row_bytes) : 0u);
-              const uint64_t adesc0 = make_smem_desc(a_addr, 16, 1024, 2);
-              const uint64_t adesc1 = make_smem_desc(a_addr + (uint32_t)p.sub_bytes, 16, 1024, 2);
-              const uint64_t bdesc = make_smem_desc(smem_u32(sB + sb * Cfg::B_STAGE), 16, 1024, 2);
-#pragma unroll
-              for (int k = 0; k < 4; k++) {
-                mma(d0, adesc0 + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), accum | (uint32_t)k);
-                mma(d0 + BN, adesc1 + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), accum | (uint32_t)k);
-              }
-              accum = 1;
-              commit(&b_empty[sb]);
-              if (++sb == Cfg::NB) { sb = 0; pb ^= 1; }
-              if (!p.slab) {
-                commit(&a_empty[sa]);
-                if (++sa == CT_NA) { sa = 0; pa ^= 1; }
-              }
-            }
-            if (p.slab) {
-              commit(&a_empty[sa]);
-              if (++sa == CT_NA) { sa = 0; pa ^= 1; }
+#pragma unroll 1
+        for (int cv = 0; cv < nv; cv++) {                  // (channel chunk, horizontal tap)
+          uint32_t a_lo = a_lo0 + sa * A16;
+          if (slab) {
+            mbar_wait_a(af0 + sa * 8, pa);
+            if (want_ts) {
+              p.dbg[blockIdx.x * 8 + 1] = gtime();
+              want_ts = false;
             }
           }
+#pragma unroll 1
+          for (int u = 0; u < KH; u++) {
+            const uint32_t b_lo = b_lo0 + sb * B16;
+            if (!slab) {
+              a_lo = a_lo0 + sa * A16;
+              mbar_wait_a(af0 + sa * 8, pa);
+            }
+            mbar_wait_a(bf0 + sb * 8, pb);
+            const uint32_t al = a_lo + (uint32_t)u * row16;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              umma_bf16_words<PAIR>(d0, al + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), HI, idesc, k ? 1u : accum);
+              umma_bf16_words<PAIR>(d0 + BN, al + sub16 + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), HI, idesc, k ? 1u : accum);
+            }
+            accum = 1;
+            commit(be0 + sb * 8);
+            if (++sb == (uint32_t)Cfg::NB) { sb = 0; pb ^= 1; }
+            if (!slab) {
+              commit(ae0 + sa * 8);
+              if (++sa == (uint32_t)CT_NA) { sa = 0; pa ^= 1; }
+            }
+          }
+          if (slab) {
+            commit(ae0 + sa * 8);
+            if (++sa == (uint32_t)CT_NA) { sa = 0; pa ^= 1; }
+          }
         }
-        commit(&t_full[acc]);
-        first_tile = false;
-        if (Cfg::ACC == 2) { if (++acc == 2) { acc = 0; pacc ^= 1; } }
+        commit(tf0 + acc * 8);
+        if (Cfg::ACC == 2) { acc ^= 1; if (acc == 0) pacc ^= 1; }
         else pacc ^= 1;
       }
     }
@@ -249,14 +267,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int rw = w0 + (r & (p.TW - 1)), rh = h0 + ((r >> p.tw_sh) & (p.TH - 1)), rn = n0 + (r >> (p.tw_sh + p.th_sh));
         if (rw < p.OW && rh < p.OH && rn < p.NB) mrow = p.mask + (((size_t)rn * p.OH + rh) * p.OW + rw) * (size_t)p.Oc + ch0;
       }
+      // the ReLU mask of the first 64 channels is requested BEFORE the wait for the accumulator: its HBM latency hides behind the MMAs
+      uint4 mk[8];
+      if (p.mask) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) mk[j] = mrow ? __ldg(reinterpret_cast<const uint4*>(mrow) + j) : make_uint4(0u, 0u, 0u, 0u);
+      }
       mbar_wait(&t_full[acc], pacc);
       tc_fence_after();
       if (p.dbg && threadIdx.x == 128 && blockIdx.x == 0 && dbg_tile < 24) p.dbg[148 * 8 + 2 * dbg_tile] = gtime();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN + s * BN);
 #pragma unroll 1
       for (int ch = 0; ch < BN / 64; ch++) {
-        uint4 mk[8];
-        if (p.mask) {
+        if (p.mask && ch > 0) {
 #pragma unroll
           for (int j = 0; j < 8; j++) mk[j] = mrow ? __ldg(reinterpret_cast<const uint4*>(mrow + ch * 64) + j) : make_uint4(0u, 0u, 0u, 0u);
         }
@@ -623,7 +646,7 @@ struct WgParams {
   float* ws;                           // [split][tile][MT * KH][128][BN]
 };
 
-template <int BN>
+template <int BN, int KHT>               // KHT: vertical taps known at compile time (3: the issue loop is fully unrolled), 0: run time
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -687,66 +710,77 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
   } else if (warp == 1) {
     if (elect_one()) {
+      // Single-thread issue loop, kept to one 32-bit add per MMA: everything of a descriptor that does not change with the 16-pixel group
+      // is folded into one low word per (M tile, vertical tap) and stage, the per-group offsets are computed once.  (First version: a
+      // triple loop that rebuilt 64-bit descriptors - 14 dependent uniform-datapath instructions, ~100 cycles, per 32-cycle MMA; issuing
+      // every MMA twice cost 17 %.)
       constexpr uint32_t idesc = make_idesc(1, true, true, 128, BN);
-      int st = 0;
-      uint32_t ph_ = 0;
-      uint32_t accum = 0;
-      // Everything of an A descriptor that does not change with the stage or the k group is fixed up front (leading-dimension offset
-      // = distance between the M tile's two chunk slots, start offset of slot and tap); the issue loop then costs an add, a shift and an
-      // OR per MMA - the first version rebuilt the descriptors in a triple loop and was issue-bound at N = 64 (32-cycle MMAs).
-      const uint32_t ones = smem_u32(sOnes);
+      constexpr uint32_t HI = TC_DESC_HI_SW128;
+      const int KH = KHT ? KHT : p.KH;
+      const uint32_t ones16 = (smem_u32(sOnes) & 0x3FFFFu) >> 4;
+      const uint32_t st0_16 = (smem_u32(sSt) & 0x3FFFFu) >> 4, stage16 = (uint32_t)p.stage_bytes >> 4, row16 = (uint32_t)p.row_bytes >> 4;
       const int nt = (nreal + p.has_db + 1) >> 1 < p.MT ? (nreal + p.has_db + 1) >> 1 : p.MT;     // M tiles with anything in them
-      uint64_t ahi[2];
-      uint32_t arel[2];
-      bool aabs[2];
+      uint32_t off16[WG_PT / 16];
+#pragma unroll
+      for (int kk = 0; kk < WG_PT / 16; kk++) {
+        const int pix = kk * 16;
+        const int img = pix >> p.pimg_sh, pin = pix & ((1 << p.pimg_sh) - 1);
+        off16[kk] = (uint32_t)(img * p.img_bytes + (pin >> p.tw_sh) * p.row_bytes + (pin & (p.TW - 1)) * 128) >> 4;
+      }
+      // M tile t = chunk slots 2t, 2t + 1: two real slabs (LBO = slot distance), a real slab + the constant ones region (LBO depends on
+      // the stage), or ones only (absolute address)
+      uint32_t rel[2];
+      int kind[2];                                         // 0: two slabs, 1: slab + ones, 2: ones only
 #pragma unroll
       for (int t = 0; t < 2; t++) {
         const bool r0 = 2 * t < nreal, r1 = 2 * t + 1 < nreal;
-        // slot 2t / 2t+1: real slabs (relative to the stage base) or the constant ones region (absolute)
-        const uint32_t a0 = r0 ? (uint32_t)(2 * t * WG_SLOT) : ones;
-        uint32_t lbo;
-        if (r0 && r1) lbo = WG_SLOT;
-        else if (r0) lbo = 0;                              // filled in per stage below: ones - (base + slot)
-        else lbo = 1024u;
-        aabs[t] = !r0;
-        arel[t] = a0;
-        ahi[t] = make_smem_desc(0, lbo, 1024, 2);
+        kind[t] = r0 ? (r1 ? 0 : 1) : 2;
+        rel[t] = kind[t] == 0 ? (((uint32_t)(2 * t * WG_SLOT) >> 4) | ((uint32_t)(WG_SLOT >> 4) << 16))
+               : kind[t] == 1 ? ((uint32_t)(2 * t * WG_SLOT) >> 4)
+                              : (ones16 | ((1024u >> 4) << 16));
       }
-      const uint64_t bhi = make_smem_desc(0, WG_GCH, 1024, 2);
+      const uint32_t g_rel = ((uint32_t)(p.nreal_max * WG_SLOT) >> 4) | ((uint32_t)(WG_GCH >> 4) << 16);
+      const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+      uint32_t st = 0, ph_ = 0, accum = 0;
+#pragma unroll 1
       for (int kt = split; kt < p.ktiles; kt += p.splits) {
-        mbar_wait(&full[st], ph_);
-        tc_fence_after();
-        const uint32_t base = smem_u32(sSt + st * p.stage_bytes);
-        const uint32_t gb = base + (uint32_t)(p.nreal_max * WG_SLOT);
-        uint64_t ah[2];
-        uint32_t ab[2];
+        const uint32_t base16 = st0_16 + st * stage16;
+        uint32_t lo[2];
 #pragma unroll
         for (int t = 0; t < 2; t++) {
-          ab[t] = aabs[t] ? arel[t] : base + arel[t];
-          const bool mixed = (2 * t < nreal) && !(2 * t + 1 < nreal);          // real slab + ones slot: the offset depends on the stage
-          ah[t] = mixed ? make_smem_desc(0, ones - ab[t], 1024, 2) : ahi[t];
+          lo[t] = kind[t] == 2 ? rel[t] : base16 + rel[t];
+          if (kind[t] == 1) lo[t] |= (ones16 - lo[t]) << 16;                     // second chunk slot = the ones region
         }
-        for (int kk = 0; kk < WG_PT / 16; kk++) {
-          const int pix = kk * 16;
-          const int img = pix >> p.pimg_sh, pin = pix & ((1 << p.pimg_sh) - 1);
-          const uint32_t off0 = (uint32_t)(img * p.img_bytes + (pin >> p.tw_sh) * p.row_bytes + (pin & (p.TW - 1)) * 128);
-          const uint64_t bdesc = bhi | (uint64_t)(((gb + (uint32_t)(kk * 2048)) & 0x3FFFFu) >> 4);
+        const uint32_t g_lo = base16 + g_rel;
+        mbar_wait_a(full0 + st * 8, ph_);
+        if (KHT) {
 #pragma unroll
-          for (int t = 0; t < 2; t++) {
-            if (t < nt) {
+          for (int kk = 0; kk < WG_PT / 16; kk++) {
 #pragma unroll
-              for (int u = 0; u < 7; u++) {
-                if (u < p.KH) {
-                  const uint32_t addr = ab[t] + off0 + (uint32_t)(u * p.row_bytes);
-                  umma<1>(tmem_base + (uint32_t)((t * p.KH + u) * BN), ah[t] | (uint64_t)((addr & 0x3FFFFu) >> 4), bdesc, idesc, accum);
-                }
+            for (int t = 0; t < 2; t++) {
+              if (t < nt) {
+#pragma unroll
+                for (int u = 0; u < (KHT ? KHT : 1); u++)
+                  umma_bf16_words<0>(tmem_base + (uint32_t)((t * KHT + u) * BN), lo[t] + off16[kk] + (uint32_t)u * row16, g_lo + (uint32_t)(kk * 128), HI,
+                                     idesc, kk ? 1u : accum);
               }
             }
           }
-          accum = 1;
+        } else {
+#pragma unroll 1
+          for (int kk = 0; kk < WG_PT / 16; kk++) {
+            const uint32_t gl = g_lo + (uint32_t)(kk * 128);
+            uint32_t d = tmem_base;
+            for (int t = 0; t < nt; t++) {
+              uint32_t al = lo[t] + off16[kk];
+              for (int u = 0; u < KH; u++, al += row16, d += BN) umma_bf16_words<0>(d, al, gl, HI, idesc, accum);
+            }
+            accum = 1;
+          }
         }
-        umma_commit(&empty[st]);
-        if (++st == p.stages) { st = 0; ph_ ^= 1; }
+        accum = 1;
+        umma_commit_a(empty0 + st * 8);
+        if (++st == (uint32_t)p.stages) { st = 0; ph_ ^= 1; }
       }
       umma_commit(done);
     }
@@ -878,9 +912,9 @@ bool wg_plan(okl_ctx* ctx, const okl_conv_desc* d, bool want_db, WgPlan& pl) {
   return true;
 }
 
-template <int BN>
+template <int BN, int KHT>
 int wg_launch(okl_ctx* ctx, const CUtensorMap& tx, const CUtensorMap& tg, const WgPlan& pl) {
-  auto kern = conv_wgrad_tc_kernel<BN>;
+  auto kern = conv_wgrad_tc_kernel<BN, KHT>;
   static int attr_smem = 0;
   if (attr_smem < pl.smem) {
     OKL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -919,7 +953,8 @@ extern "C" int okl_conv2_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void*
   if (st != OKL_OK) return st;
   st = ct_map_nhwc(&tg, g16, 2, s.O, s.OW, s.OH, s.N, 64, p.TW, p.TH, p.TN);
   if (st != OKL_OK) return st;
-  st = p.BN == 128 ? wg_launch<128>(ctx, tx, tg, pl) : wg_launch<64>(ctx, tx, tg, pl);
+  if (s.KH == 3) st = p.BN == 128 ? wg_launch<128, 3>(ctx, tx, tg, pl) : wg_launch<64, 3>(ctx, tx, tg, pl);
+  else st = p.BN == 128 ? wg_launch<128, 0>(ctx, tx, tg, pl) : wg_launch<64, 0>(ctx, tx, tg, pl);
   if (st != OKL_OK) return st;
   const size_t total = (size_t)(p.nchunks + (pl.db_fused ? 1 : 0)) * 64 * s.KH * s.O;
   conv_wgrad_reduce_kernel<<<okl_grid_1d(ctx, total * 4, 256, 16), 256, 0, ctx->stream>>>(p.ws, (float*)dW, pl.db_fused ? (float*)db : nullptr, s.O, s.C, s.KH,
@@ -929,67 +964,70 @@ extern "C" int okl_conv2_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void*
   return OKL_OK;
 }
 
-// ================================================================================================ first layer (tiny C): K = C * taps < 32
-// Conv2DLayer(3, 64, 3, 1, 1) on the input images (okl.py:790-813 / 869-871): K = 27 is far too small for a TMA-fed implicit GEMM
-// (a k-block is 64 channels of ONE tap) and the FFMA kernels it used to run on took 16 % of the CIFAR step (ncu: 202 us forward at
-// 1.3 TB/s of fp32 output, 400 us weight gradient at 9 TFLOP/s).  Here the im2col operand of a 128-pixel tile - 32 bf16 per pixel:
-// the 27 taps, a constant 1 (bias / bias gradient ride in the same product) and padding - is BUILT in shared memory by the CTA's
-// threads from a staged fp32 input patch, directly in the 128-byte-swizzled UMMA layout, and consumed by tcgen05.mma:
-//   forward : D[128 pixels, O] = patch[128, 32] . [W | b][O, 32]^T, ReLU, bf16, TMA store into the channels-last output
-//   wgrad   : D[32, O] += patch[128, 32]^T . g[128, O]  over the CTA's pixel tiles (the SAME shared-memory image, read MN-major;
-//             the gradient tile arrives by TMA), row 27 of D is the bias gradient; split-K over CTAs, fixed-order reduce.
+// ================================================================================================ first layer (tiny C): K = C * taps < 128
+// Conv2DLayer(3, 64, 3, 1, 1) on the input images (okl.py:790-813 / 869-871) and Conv3DLayer(3, 64, 3, 1, 1) on video clips
+// (okl.py:948-985 / 1018-1031): K = 27 / 81 is far too small for a TMA-fed implicit GEMM (a k-block is 64 channels of ONE tap) and
+// the kernels these layers used to run on took 16 % of the CIFAR step (FFMA: 202 us forward at 1.3 TB/s of fp32 output, 400 us weight
+// gradient) and 0.86 of the 1.49 ms video step (sc_fprop / sc_wgrad: the im2col operand gathered tap by tap from L1 / L2).  Here the
+// im2col operand of a 128-pixel tile - KP = 16 * KS bf16 per pixel: the taps, a constant 1 (bias / bias gradient ride in the same
+// product) and zero padding - is BUILT in shared memory by the CTA's threads from a staged fp32 input patch (every input value is read
+// from global memory once per tile), directly in the 128-byte-swizzled UMMA layout, and consumed by tcgen05.mma:
+//   forward : D[128 pixels, O] = patch[128, KP] . [W | b][O, KP]^T, ReLU, bf16, TMA store into the channels-last output
+//   wgrad   : D[KP, O] += patch[128, KP]^T . g[128, O]  over the CTA's pixel tiles (the SAME shared-memory image, read MN-major;
+//             the gradient tile arrives by TMA), row K of D is the bias gradient; split-K over CTAs, fixed-order reduce.
+// A 3-D layer is the 2-D kernel with one more tap dimension: a tile lies in one output depth slice, (n, depth) is the tile's image
+// index (the channels-last output is a 4-D tensor (N * OD, OH, OW, O) for TMA), the patch holds the KD input slices around it.
 namespace {
 
 constexpr int F1_THREADS = 256;
-constexpr int F1_KP = 32;              // padded reduction extent (taps + ones column + zero padding)
+constexpr int F1_KPMAX = 128;          // padded reduction extent (taps + ones column + zero padding), two 64-element swizzle atoms at most
+constexpr int F1_ATOM = 16384;         // one 128-row x 128-byte swizzle-atom column of an operand
+constexpr int F1_PATCH_MAX = 16384;    // bytes of staged fp32 input per tile
 
 struct F1Params {
   const float* x; const float* W; const float* bias;
-  int N, C, H, Wd, O, KH, KW, ph, pw, OH, OW;
+  int N, C, D, H, Wd, O, KD, KH, KW, pd, ph, pw, OD, OH, OW;
   int TW, TH, tw_sh, tiles_w, tiles_h, ntiles;
-  int K, relu, RH, PH, PWp;
-  float* partial;                      // wgrad: [grid][32][O]
+  int K, KS, NA, relu, RH, PH, PWp;    // KS = 16-wide k-steps (KP = 16 KS), NA = swizzle-atom columns of the patch operand (1 or 2)
+  float* partial;                      // wgrad: [grid][KP][O]
 };
 
-// tap k -> offset of (c, u, v) inside the staged patch [C][PH][PWp]; k == K: the ones column (-1); k > K: zero (-2)
+// tap k -> offset of (c, t, u, v) inside the staged patch [C][KD][PH][PWp]; k == K: the ones column (-1); k > K: zero (-2)
 __device__ __forceinline__ void f1_build_ktab(int* ktab, const F1Params& p) {
-  for (int k = threadIdx.x; k < F1_KP; k += blockDim.x) {
+  for (int k = threadIdx.x; k < p.KS * 16; k += blockDim.x) {
     int off = -2;
     if (k < p.K) {
-      const int T = p.KH * p.KW, c = k / T, t = k - c * T, u = t / p.KW, v = t - u * p.KW;
-      off = (c * p.PH + u) * p.PWp + v;
+      const int T2 = p.KH * p.KW, T = p.KD * T2, c = k / T, r = k - c * T, t = r / T2, r2 = r - t * T2, u = r2 / p.KW, v = r2 - u * p.KW;
+      off = ((c * p.KD + t) * p.PH + u) * p.PWp + v;
     } else if (k == p.K) off = -1;
     ktab[k] = off;
   }
 }
 
-__device__ __forceinline__ void f1_load_patch(float* patch, const F1Params& p, int n, int h0, int w0) {
-  const int per_c = p.PH * p.PWp, total = p.C * per_c;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int c = i / per_c, r2 = i - c * per_c, r = r2 / p.PWp, col = r2 - r * p.PWp;
-    const int ih = h0 - p.ph + r, iw = w0 - p.pw + col;
-    float v = 0.f;
-    if (n < p.N && ih >= 0 && ih < p.H && iw >= 0 && iw < p.Wd) v = __ldg(p.x + (((size_t)n * p.C + c) * p.H + ih) * p.Wd + iw);
-    patch[i] = v;
-  }
+// patch element i = ((c * KD + t) * PH + r) * PWp + col  of the tile (image index nd = n * OD + od, origin (h0, w0))
+__device__ __forceinline__ float f1_patch_value(const F1Params& p, int i, int n, int od, int h0, int w0) {
+  const int per_t = p.PH * p.PWp;
+  const int ct = i / per_t, r2 = i - ct * per_t, r = r2 / p.PWp, col = r2 - r * p.PWp;
+  const int c = ct / p.KD, t = ct - c * p.KD;
+  const int id = od - p.pd + t, ih = h0 - p.ph + r, iw = w0 - p.pw + col;
+  float v = 0.f;
+  if (n < p.N && id >= 0 && id < p.D && ih >= 0 && ih < p.H && iw >= 0 && iw < p.Wd)
+    v = __ldg(p.x + ((((size_t)n * p.C + c) * p.D + id) * p.H + ih) * p.Wd + iw);
+  return v;
+}
+__device__ __forceinline__ void f1_load_patch(float* patch, const F1Params& p, int total, int n, int od, int h0, int w0) {
+  for (int i = threadIdx.x; i < total; i += blockDim.x) patch[i] = f1_patch_value(p, i, n, od, h0, w0);
 }
 
 // Software pipelining of the patch: a tile's values are fetched into registers one tile ahead (while the previous tile's MMA and
 // epilogue run) and only copied to shared memory at the top of the tile - ncu had both kernels waiting on these global loads.
-constexpr int F1_PRE = 6;              // values per thread held ahead (patches up to 6 x threads floats; larger ones load directly)
+constexpr int F1_PRE = 8;              // values per thread held ahead (patches up to 8 x threads floats; larger ones load directly)
 
-__device__ __forceinline__ void f1_fetch_patch(float* pre, const F1Params& p, int n, int h0, int w0) {
-  const int per_c = p.PH * p.PWp, total = p.C * per_c;
+__device__ __forceinline__ void f1_fetch_patch(float* pre, const F1Params& p, int total, int n, int od, int h0, int w0) {
 #pragma unroll
   for (int e = 0; e < F1_PRE; e++) {
     const int i = threadIdx.x + e * blockDim.x;
-    float v = 0.f;
-    if (i < total) {
-      const int c = i / per_c, r2 = i - c * per_c, r = r2 / p.PWp, col = r2 - r * p.PWp;
-      const int ih = h0 - p.ph + r, iw = w0 - p.pw + col;
-      if (n < p.N && ih >= 0 && ih < p.H && iw >= 0 && iw < p.Wd) v = __ldg(p.x + (((size_t)n * p.C + c) * p.H + ih) * p.Wd + iw);
-    }
-    pre[e] = v;
+    pre[e] = i < total ? f1_patch_value(p, i, n, od, h0, w0) : 0.f;
   }
 }
 __device__ __forceinline__ void f1_store_patch(float* patch, const float* pre, int total) {
@@ -999,52 +1037,52 @@ __device__ __forceinline__ void f1_store_patch(float* patch, const float* pre, i
     if (i < total) patch[i] = pre[e];
   }
 }
-__device__ __forceinline__ void f1_tile_origin(const F1Params& p, int tile, int& n, int& h0, int& w0) {
+// tile -> image index nd = n * OD + od (the TMA coordinate), (n, od) and the tile origin inside the slice
+__device__ __forceinline__ void f1_tile_origin(const F1Params& p, int tile, int& nd, int& n, int& od, int& h0, int& w0) {
   const int wt = tile % p.tiles_w, r2 = tile / p.tiles_w;
   const int ht = r2 % p.tiles_h;
-  n = r2 / p.tiles_h; w0 = wt * p.TW; h0 = ht * p.TH;
+  nd = r2 / p.tiles_h; w0 = wt * p.TW; h0 = ht * p.TH;
+  n = nd / p.OD; od = nd - n * p.OD;
 }
 
-// thread (pixel m, part): 32 / (threads / 128) of the 32 k values of row m of the 128 x 32 patch operand, as swizzled 16-byte chunks
+// row m of the 128 x KP patch operand as swizzled 16-byte chunks (8 k values each): chunk j -> atom column j / 8, position j % 8;
+// the CTA's threads split a row's 2 KS chunks between them (thread -> pixel m = tid % 128, chunks tid / 128, + threads / 128, ...)
 __device__ __forceinline__ void f1_build_rows(uint8_t* sA, const float* patch, const int* ktab, const F1Params& p, bool pixel_ok) {
-  const int m = threadIdx.x & 127, part = threadIdx.x >> 7;
-  const int cpt = 4 / (blockDim.x >> 7);                    // chunks per thread: 4 (128 threads) or 2 (256 threads)
+  const int m = threadIdx.x & 127, part = threadIdx.x >> 7, nparts = blockDim.x >> 7;
   const int base = (m >> p.tw_sh) * p.PWp + (m & (p.TW - 1));
+  for (int j = part; j < 2 * p.KS; j += nparts) {
+    uint32_t pk[4];
 #pragma unroll
-  for (int jj = 0; jj < 4; jj++) {
-    if (jj < cpt) {
-      const int j = part * cpt + jj;
-      uint32_t pk[4];
+    for (int e = 0; e < 4; e++) {
+      float f[2];
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        float f[2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const int off = ktab[j * 8 + e * 2 + h];
-          f[h] = off >= 0 ? patch[off + base] : (off == -1 && pixel_ok ? 1.f : 0.f);
-        }
-        __nv_bfloat162 t = __floats2bfloat162_rn(f[0], f[1]);
-        pk[e] = *reinterpret_cast<uint32_t*>(&t);
+      for (int h = 0; h < 2; h++) {
+        const int off = ktab[j * 8 + e * 2 + h];
+        f[h] = off >= 0 ? patch[off + base] : (off == -1 && pixel_ok ? 1.f : 0.f);
       }
-      *reinterpret_cast<uint4*>(sA + m * 128 + ((j ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      __nv_bfloat162 t = __floats2bfloat162_rn(f[0], f[1]);
+      pk[e] = *reinterpret_cast<uint32_t*>(&t);
     }
+    *reinterpret_cast<uint4*>(sA + (j >> 3) * F1_ATOM + m * 128 + (((j & 7) ^ (m & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
-// NT = 128 (O = 64): small CTAs, five per SM - the tile loop is a chain of latencies (patch -> operand rows -> MMA -> TMEM -> store), and
-// more resident CTAs hide it better than more threads per CTA (three 256-thread CTAs: 80 us; ncu: "long scoreboard" on the patch)
+// NT = 128 (O = 64, small patches): small CTAs, five per SM - the tile loop is a chain of latencies (patch -> operand rows -> MMA ->
+// TMEM -> store), and more resident CTAs hide it better than more threads per CTA (three 256-thread CTAs: 80 us vs 73 us at CIFAR
+// batch 1024; ncu: "long scoreboard" on the patch)
 template <int O_, int NT>
 __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) conv_first_fprop_kernel(const __grid_constant__ CUtensorMap tmY16, const F1Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;                                       // 128 rows x 128 B (first 64 B of every row used)
-  uint8_t* sB = sA + 16384;                                 // O_ rows x 128 B
-  uint8_t* sStg = sB + O_ * 128;                            // one 4 KB staging tile per warp
+  uint8_t* sA = smem;                                       // NA atom columns of 128 rows x 128 B
+  uint8_t* sB = sA + p.NA * F1_ATOM;                        // NA atom columns of O_ rows x 128 B
+  uint8_t* sStg = sB + p.NA * O_ * 128;                     // one 4 KB staging tile per warp
   uint64_t* mma_done = reinterpret_cast<uint64_t*>(sStg + (NT / 32) * CT_STG);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
   int* ktab = reinterpret_cast<int*>(mma_done + 2);
-  float* patch = reinterpret_cast<float*>(ktab + F1_KP);
+  float* patch = reinterpret_cast<float*>(ktab + F1_KPMAX);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KP = p.KS * 16;
 
   if (threadIdx.x == 0) {
     mbar_init(mma_done, 1);
@@ -1053,11 +1091,11 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) conv_first_fprop_kernel
   }
   if (warp == 0) tmem_alloc<O_>(tmem_slot);
   f1_build_ktab(ktab, p);
-  for (int i = threadIdx.x; i < O_ * F1_KP; i += NT) {      // [W | b | 0] as bf16, K-major, swizzled
-    const int o = i / F1_KP, k = i - o * F1_KP;
+  for (int i = threadIdx.x; i < O_ * KP; i += NT) {         // [W | b | 0] as bf16, K-major, swizzled
+    const int o = i / KP, k = i - o * KP;
     float v = 0.f;
     if (o < p.O) v = k < p.K ? __ldg(p.W + (size_t)o * p.K + k) : (k == p.K && p.bias ? __ldg(p.bias + o) : 0.f);
-    *reinterpret_cast<__nv_bfloat16*>(sB + o * 128 + (((k >> 3) ^ (o & 7)) << 4) + (k & 7) * 2) = __float2bfloat16(v);
+    *reinterpret_cast<__nv_bfloat16*>(sB + (k >> 6) * (O_ * 128) + o * 128 + ((((k >> 3) & 7) ^ (o & 7)) << 4) + (k & 7) * 2) = __float2bfloat16(v);
   }
   fence_proxy_async();
   tc_fence_before();
@@ -1071,41 +1109,41 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) conv_first_fprop_kernel
   uint8_t* stg = sStg + warp * CT_STG;
   const uint32_t sw = (uint32_t)(lane & 7);
   uint32_t parity = 0;
-  const int ptotal = p.C * p.PH * p.PWp;
+  const int ptotal = p.C * p.KD * p.PH * p.PWp;
   const bool piped = ptotal <= F1_PRE * NT;
   float pre[F1_PRE];
   if (piped && (int)blockIdx.x < p.ntiles) {
-    int n, h0, w0;
-    f1_tile_origin(p, blockIdx.x, n, h0, w0);
-    f1_fetch_patch(pre, p, n, h0, w0);
+    int nd, n, od, h0, w0;
+    f1_tile_origin(p, blockIdx.x, nd, n, od, h0, w0);
+    f1_fetch_patch(pre, p, ptotal, n, od, h0, w0);
   }
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-    int n, h0, w0;
-    f1_tile_origin(p, tile, n, h0, w0);
+    int nd, n, od, h0, w0;
+    f1_tile_origin(p, tile, nd, n, od, h0, w0);
     if (piped) f1_store_patch(patch, pre, ptotal);
-    else f1_load_patch(patch, p, n, h0, w0);
+    else f1_load_patch(patch, p, ptotal, n, od, h0, w0);
     __syncthreads();                                        // patch complete; every thread is past the previous tile's accumulator reads
     f1_build_rows(sA, patch, ktab, p, true);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (piped && tile + (int)gridDim.x < p.ntiles) {        // next tile's patch: in flight during this tile's MMA and epilogue
-      int n2, h2, w2;
-      f1_tile_origin(p, tile + gridDim.x, n2, h2, w2);
-      f1_fetch_patch(pre, p, n2, h2, w2);
+      int nd2, n2, od2, h2, w2;
+      f1_tile_origin(p, tile + gridDim.x, nd2, n2, od2, h2, w2);
+      f1_fetch_patch(pre, p, ptotal, n2, od2, h2, w2);
     }
     if (threadIdx.x == 0) {
       tc_fence_after();
-      const uint64_t adesc = make_smem_desc(smem_u32(sA), 16, 1024, 2);
-      const uint64_t bdesc = make_smem_desc(smem_u32(sB), 16, 1024, 2);
-      umma<1>(tmem_base, adesc, bdesc, idesc, 0u);
-      umma<1>(tmem_base, adesc + 2, bdesc + 2, idesc, 1u);
+      const uint32_t a_lo = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16), b_lo = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
+      for (int ks = 0; ks < p.KS; ks++)                     // k-step ks: atom column ks / 4, 32 bytes further inside its rows per step
+        umma_bf16_words<0>(tmem_base, a_lo + (uint32_t)((ks >> 2) * (F1_ATOM >> 4) + (ks & 3) * 2),
+                           b_lo + (uint32_t)((ks >> 2) * (O_ * 128 >> 4) + (ks & 3) * 2), TC_DESC_HI_SW128, idesc, ks ? 1u : 0u);
       umma_commit(mma_done);
     }
     mbar_wait(mma_done, parity);
     parity ^= 1;
     tc_fence_after();
-    // epilogue: warp -> TMEM lane quarter q (32 pixels) and every second 64-channel chunk
+    // epilogue: warp -> TMEM lane quarter q (32 pixels) and every (NT / 128)-th 64-channel chunk
     const int pbase = q * 32;
     const int bh = h0 + (pbase >> p.tw_sh);
 #pragma unroll 1
@@ -1134,7 +1172,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) conv_first_fprop_kernel
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        tma_store_4d(&tmY16, stg, ch * 64, w0, bh, n);
+        tma_store_4d(&tmY16, stg, ch * 64, w0, bh, nd);
         tma_store_commit();
       }
     }
@@ -1150,16 +1188,18 @@ __global__ void __launch_bounds__(F1_THREADS, O_ == 64 ? 3 : 2) conv_first_wgrad
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int GB = (O_ / 64) * 16384;
-  uint8_t* sA = smem;                                       // 2 x 16 KB patch operands
-  uint8_t* sG = sA + 2 * 16384;                             // 2 x gradient tiles
+  const int AB = p.NA * F1_ATOM;
+  uint8_t* sA = smem;                                       // 2 x patch operands (NA atom columns each)
+  uint8_t* sG = sA + 2 * AB;                                // 2 x gradient tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 2 * GB);
   uint64_t* g_full = bars;                                  // [2]
   uint64_t* st_free = bars + 2;                             // [2] the MMAs that read stage s are complete
   uint64_t* done = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
   int* ktab = reinterpret_cast<int*>(bars + 6);
-  float* patch = reinterpret_cast<float*>(ktab + F1_KP);
+  float* patch = reinterpret_cast<float*>(ktab + F1_KPMAX);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KP = p.KS * 16;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; s++) { mbar_init(&g_full[s], 1); mbar_init(&st_free[s], 1); }
@@ -1176,74 +1216,75 @@ __global__ void __launch_bounds__(F1_THREADS, O_ == 64 ? 3 : 2) conv_first_wgrad
   constexpr uint32_t idesc = make_idesc(1, true, true, 128, O_);
   okl_pdl_sync();
 
-  const int ptotal = p.C * p.PH * p.PWp;
+  const int ptotal = p.C * p.KD * p.PH * p.PWp;
   const bool piped = ptotal <= F1_PRE * F1_THREADS;
   float pre[F1_PRE];
   if (piped && (int)blockIdx.x < p.ntiles) {
-    int n, h0, w0;
-    f1_tile_origin(p, blockIdx.x, n, h0, w0);
-    f1_fetch_patch(pre, p, n, h0, w0);
+    int nd, n, od, h0, w0;
+    f1_tile_origin(p, blockIdx.x, nd, n, od, h0, w0);
+    f1_fetch_patch(pre, p, ptotal, n, od, h0, w0);
   }
   int it = 0;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it++) {
     const int s = it & 1;
     const uint32_t use = (uint32_t)(it >> 1);               // how many times stage s has been used before
-    int n, h0, w0;
-    f1_tile_origin(p, tile, n, h0, w0);
+    int nd, n, od, h0, w0;
+    f1_tile_origin(p, tile, nd, n, od, h0, w0);
     if (use > 0) mbar_wait(&st_free[s], (use - 1) & 1);     // everyone: stage s (patch operand AND gradient tile) is reusable
     if (threadIdx.x == 0) {
       mbar_expect_tx(&g_full[s], GB);
 #pragma unroll
-      for (int j = 0; j < O_ / 64; j++) tma_load_4d(&tmG, &g_full[s], sG + s * GB + j * 16384, j * 64, w0, h0, n);
+      for (int j = 0; j < O_ / 64; j++) tma_load_4d(&tmG, &g_full[s], sG + s * GB + j * 16384, j * 64, w0, h0, nd);
     }
     if (piped) f1_store_patch(patch, pre, ptotal);
-    else f1_load_patch(patch, p, n, h0, w0);
+    else f1_load_patch(patch, p, ptotal, n, od, h0, w0);
     __syncthreads();
     {
       const int m = threadIdx.x & 127;
       const bool ok = (w0 + (m & (p.TW - 1))) < p.OW && (h0 + (m >> p.tw_sh)) < p.OH && n < p.N;
-      f1_build_rows(sA + s * 16384, patch, ktab, p, ok);
+      f1_build_rows(sA + s * AB, patch, ktab, p, ok);
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (piped && tile + (int)gridDim.x < p.ntiles) {
-      int n2, h2, w2;
-      f1_tile_origin(p, tile + gridDim.x, n2, h2, w2);
-      f1_fetch_patch(pre, p, n2, h2, w2);
+      int nd2, n2, od2, h2, w2;
+      f1_tile_origin(p, tile + gridDim.x, nd2, n2, od2, h2, w2);
+      f1_fetch_patch(pre, p, ptotal, n2, od2, h2, w2);
     }
     if (threadIdx.x == 0) {
       mbar_wait(&g_full[s], use & 1);
       tc_fence_after();
-      const uint32_t a = smem_u32(sA + s * 16384), g = smem_u32(sG + s * GB);
+      // A = patch^T, MN-major: 16 pixel rows per MMA, M = the KP k values (64 per atom column, LBO = column distance); with one
+      // atom column M rows 64..127 alias an in-bounds region and their results are never read
+      const uint32_t a_lo = ((smem_u32(sA + s * AB) & 0x3FFFFu) >> 4) | ((uint32_t)((p.NA > 1 ? F1_ATOM : 1024) >> 4) << 16);
+      const uint32_t g_lo = ((smem_u32(sG + s * GB) & 0x3FFFFu) >> 4) | ((16384u >> 4) << 16);
 #pragma unroll
-      for (int kk = 0; kk < 8; kk++) {
-        // A = patch^T, MN-major: 16 pixel rows per MMA; M rows 64..127 alias an in-bounds region (their results are never read)
-        const uint64_t adesc = make_smem_desc(a + (uint32_t)(kk * 2048), 1024, 1024, 2);
-        const uint64_t bdesc = make_smem_desc(g + (uint32_t)(kk * 2048), 16384, 1024, 2);
-        umma<1>(tmem_base, adesc, bdesc, idesc, (it | kk) ? 1u : 0u);
-      }
+      for (int kk = 0; kk < 8; kk++)
+        umma_bf16_words<0>(tmem_base, a_lo + (uint32_t)(kk * 128), g_lo + (uint32_t)(kk * 128), TC_DESC_HI_SW128, idesc, (it | kk) ? 1u : 0u);
       umma_commit(&st_free[s]);
     }
   }
   if (threadIdx.x == 0) umma_commit(done);
   mbar_wait(done, 0);
   tc_fence_after();
-  if (warp == 0) {                                          // TMEM lanes 0..31 = k rows
-    float* dst = p.partial + ((size_t)blockIdx.x * F1_KP + lane) * O_;
+  if (warp < 4 && warp * 32 < KP) {                         // TMEM lanes = k rows: warp w reads lanes 32 w .. 32 w + 31
+    float* dst = p.partial + ((size_t)blockIdx.x * KP + warp * 32 + lane) * O_;
     const bool any = (int)blockIdx.x < p.ntiles;
 #pragma unroll 1
     for (int c = 0; c < O_; c += 32) {
       uint32_t v[32];
       if (any) {
-        tmem_ld32(tmem_base + (uint32_t)c, v);
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
         tmem_ld_wait();
       } else {
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = 0u;
       }
+      if (warp * 32 + lane < KP) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dst + c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dst + c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
     }
   }
   tc_fence_before();
@@ -1252,7 +1293,7 @@ __global__ void __launch_bounds__(F1_THREADS, O_ == 64 ? 3 : 2) conv_first_wgrad
 }
 
 // one warp per output element: lanes stride over the CTAs' partials, fixed-order shuffle tree
-__global__ void conv_first_wgrad_reduce(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ db, int O, int Opad, int K,
+__global__ void conv_first_wgrad_reduce(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ db, int O, int Opad, int K, int KP,
                                         int nblk) {
   const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (idx >= (K + 1) * O) return;
@@ -1260,10 +1301,10 @@ __global__ void conv_first_wgrad_reduce(const float* __restrict__ partial, float
   float s0 = 0.f, s1 = 0.f;
   int b = lane;
   for (; b + 32 < nblk; b += 64) {
-    s0 += partial[((size_t)b * F1_KP + k) * Opad + o];
-    s1 += partial[((size_t)(b + 32) * F1_KP + k) * Opad + o];
+    s0 += partial[((size_t)b * KP + k) * Opad + o];
+    s1 += partial[((size_t)(b + 32) * KP + k) * Opad + o];
   }
-  if (b < nblk) s0 += partial[((size_t)b * F1_KP + k) * Opad + o];
+  if (b < nblk) s0 += partial[((size_t)b * KP + k) * Opad + o];
   float s = s0 + s1;
 #pragma unroll
   for (int sft = 16; sft > 0; sft >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sft);
@@ -1275,24 +1316,40 @@ __global__ void conv_first_wgrad_reduce(const float* __restrict__ partial, float
 
 bool f1_plan(okl_ctx* ctx, const okl_conv_desc* d, F1Params& p, int& opad) {
   if (ctx->cc < 100 || ct_env("OKL_CONV_FIRST_TC", 1) == 0) return false;
-  if (d->nd != 2 || d->s[0] != 1 || d->s[1] != 1 || d->x_layout != OKL_NCX || d->y_layout != OKL_NXC) return false;
+  if ((d->nd != 2 && d->nd != 3) || d->x_layout != OKL_NCX || d->y_layout != OKL_NXC) return false;
+  for (int i = 0; i < d->nd; i++)
+    if (d->s[i] != 1) return false;
   memset(&p, 0, sizeof(p));
-  p.N = d->N; p.C = d->C; p.H = d->in[0]; p.Wd = d->in[1]; p.O = d->O; p.KH = d->k[0]; p.KW = d->k[1]; p.ph = d->p[0]; p.pw = d->p[1];
-  p.K = p.C * p.KH * p.KW;
-  if (p.K + 1 > F1_KP || p.O % 64 || p.O > 256 || p.N < 1) return false;
+  const int o3 = d->nd == 3 ? 1 : 0;                       // spatial index of H
+  p.N = d->N; p.C = d->C; p.O = d->O;
+  p.D = o3 ? d->in[0] : 1; p.KD = o3 ? d->k[0] : 1; p.pd = o3 ? d->p[0] : 0;
+  p.H = d->in[o3]; p.Wd = d->in[o3 + 1]; p.KH = d->k[o3]; p.KW = d->k[o3 + 1]; p.ph = d->p[o3]; p.pw = d->p[o3 + 1];
+  p.K = p.C * p.KD * p.KH * p.KW;
+  if (p.K + 1 > F1_KPMAX || p.O % 64 || p.O > 256 || p.N < 1) return false;
+  p.KS = (p.K + 1 + 15) / 16; if (p.KS < 2) p.KS = 2;
+  p.NA = p.KS > 4 ? 2 : 1;
   opad = p.O <= 64 ? 64 : (p.O <= 128 ? 128 : 256);
   if (opad != p.O) return false;
-  p.OH = p.H + 2 * p.ph - p.KH + 1; p.OW = p.Wd + 2 * p.pw - p.KW + 1;
-  if (p.OH < 1 || p.OW < 1) return false;
-  p.TW = ct_pow2_ceil(p.OW); if (p.TW > 32) p.TW = 32;
-  if (p.TW < 8) return false;
+  p.OD = p.D + 2 * p.pd - p.KD + 1; p.OH = p.H + 2 * p.ph - p.KH + 1; p.OW = p.Wd + 2 * p.pw - p.KW + 1;
+  if (p.OD < 1 || p.OH < 1 || p.OW < 1 || (long long)p.N * p.OD > 0x7fffffffLL) return false;
+  // pixel tile TW x (128 / TW) inside one slice: the candidate that covers the slice with the fewest out-of-range pixels
+  long long best = -1;
+  for (int tw = 32; tw >= 8; tw >>= 1) {
+    if (tw > 8 && tw / 2 >= p.OW) continue;                 // narrower images: the next candidate fits them without waste
+    const int th = 128 / tw;
+    const long long cover = (long long)((p.OW + tw - 1) / tw) * tw * ((p.OH + th - 1) / th) * th;
+    if ((p.C * p.KD * (th + p.KH - 1) * (tw + p.KW - 1)) * 4 > F1_PATCH_MAX) continue;
+    if (best < 0 || cover < best) { best = cover; p.TW = tw; }
+  }
+  if (best < 0) return false;
   p.TH = 128 / p.TW;
   p.tw_sh = ct_ilog2(p.TW);
   p.tiles_w = (p.OW + p.TW - 1) / p.TW; p.tiles_h = (p.OH + p.TH - 1) / p.TH;
-  p.ntiles = p.tiles_w * p.tiles_h * p.N;
+  const long long nt = (long long)p.tiles_w * p.tiles_h * p.N * p.OD;
+  if (nt > 0x7fffffffLL) return false;
+  p.ntiles = (int)nt;
   p.RH = 32 / p.TW;
   p.PH = p.TH + p.KH - 1; p.PWp = p.TW + p.KW - 1;
-  if (p.C * p.PH * p.PWp * 4 > 16384) return false;
   return true;
 }
 
@@ -1305,7 +1362,7 @@ extern "C" int okl_conv_first_supported(okl_ctx* ctx, const okl_conv_desc* d) {
   return f1_plan(ctx, d, p, opad) ? 1 : 0;
 }
 
-// y16 (N, OH, OW, O) bf16 = act(conv(x (N, C, H, W) fp32, W) + b); d->act NONE or RELU
+// y16 (N, *out, O) bf16 = act(conv(x (N, C, *in) fp32, W) + b); d->act NONE or RELU
 extern "C" int okl_conv_first_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* W, const void* bias, void* y16) {
   OKL_REQUIRE(ctx && d && x && W && y16, "NULL argument");
   F1Params p;
@@ -1314,25 +1371,28 @@ extern "C" int okl_conv_first_fprop(okl_ctx* ctx, const okl_conv_desc* d, const 
   OKL_REQUIRE(d->act == OKL_ACT_NONE || d->act == OKL_ACT_RELU, "okl_conv_first_fprop: only ReLU can be fused");
   p.x = (const float*)x; p.W = (const float*)W; p.bias = (const float*)bias; p.relu = d->act == OKL_ACT_RELU;
   CUtensorMap ty;
-  int s = ct_map_nhwc(&ty, y16, 2, p.O, p.OW, p.OH, p.N, 64, p.TW, p.RH, 1);
+  int s = ct_map_nhwc(&ty, y16, 2, p.O, p.OW, p.OH, p.N * p.OD, 64, p.TW, p.RH, 1);
   if (s != OKL_OK) return s;
-  const int nt = opad == 64 ? 128 : 256;
-  const int per_sm = opad == 64 ? 5 : 2;
+  const int ptotal = p.C * p.KD * p.PH * p.PWp;
+  const int nt = (opad == 64 && ptotal <= F1_PRE * 128 && p.NA == 1) ? 128 : 256;
+  const int smem = p.NA * F1_ATOM + p.NA * opad * 128 + (nt / 32) * CT_STG + 64 + F1_KPMAX * 4 + ptotal * 4 + 1024;
+  int per_sm = nt == 128 ? 5 : 2;
+  if (per_sm * (smem + 1024) > 227 * 1024) per_sm = (227 * 1024) / (smem + 1024);
+  if (per_sm < 1) per_sm = 1;
   const int grid = p.ntiles < per_sm * ctx->sm_count ? p.ntiles : per_sm * ctx->sm_count;
-  const int smem = 16384 + opad * 128 + (nt / 32) * CT_STG + 64 + F1_KP * 4 + p.C * p.PH * p.PWp * 4 + 1024;
 #define F1_FP(OO, NT_)                                                                                                \
   {                                                                                                                   \
     static int set = 0;                                                                                               \
-    if (set < smem) { OKL_CHECK_CUDA(cudaFuncSetAttribute(conv_first_fprop_kernel<OO, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); set = 100 * 1024; } \
+    if (set < smem) { OKL_CHECK_CUDA(cudaFuncSetAttribute(conv_first_fprop_kernel<OO, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); set = 160 * 1024; } \
     okl_launch(ctx, conv_first_fprop_kernel<OO, NT_>, dim3(grid), dim3(NT_), smem, ty, p);                             \
   }
-  if (opad == 64) F1_FP(64, 128) else if (opad == 128) F1_FP(128, 256) else F1_FP(256, 256)
+  if (opad == 64 && nt == 128) F1_FP(64, 128) else if (opad == 64) F1_FP(64, 256) else if (opad == 128) F1_FP(128, 256) else F1_FP(256, 256)
 #undef F1_FP
   OKL_LAUNCHED(ctx, "conv_first_fprop");
   return OKL_OK;
 }
 
-// dW (O, C, KH, KW) fp32 and db (O) fp32 (optional) from x (N, C, H, W) fp32 and g16 (N, OH, OW, O) bf16
+// dW (O, C, *k) fp32 and db (O) fp32 (optional) from x (N, C, *in) fp32 and g16 (N, *out, O) bf16
 extern "C" int okl_conv_first_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* g16, void* dW, void* db) {
   OKL_REQUIRE(ctx && d && x && g16 && dW, "NULL argument");
   F1Params p;
@@ -1340,14 +1400,17 @@ extern "C" int okl_conv_first_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const 
   OKL_REQUIRE(f1_plan(ctx, d, p, opad), "okl_conv_first_wgrad: unsupported shape / layout");
   p.x = (const float*)x;
   CUtensorMap tg;
-  int s = ct_map_nhwc(&tg, g16, 2, p.O, p.OW, p.OH, p.N, 64, p.TW, p.TH, 1);
+  int s = ct_map_nhwc(&tg, g16, 2, p.O, p.OW, p.OH, p.N * p.OD, 64, p.TW, p.TH, 1);
   if (s != OKL_OK) return s;
-  const int per_sm = opad == 64 ? 3 : 2;
+  const int KP = p.KS * 16;
+  const int smem = 2 * p.NA * F1_ATOM + 2 * (opad / 64) * 16384 + 64 + F1_KPMAX * 4 + p.C * p.KD * p.PH * p.PWp * 4 + 1024;
+  int per_sm = opad == 64 ? 3 : 2;
+  if (per_sm * (smem + 1024) > 227 * 1024) per_sm = (227 * 1024) / (smem + 1024);
+  if (per_sm < 1) per_sm = 1;
   const int grid = p.ntiles < per_sm * ctx->sm_count ? p.ntiles : per_sm * ctx->sm_count;
-  s = okl_ensure_workspace(ctx, (size_t)grid * F1_KP * opad * sizeof(float));
+  s = okl_ensure_workspace(ctx, (size_t)grid * KP * opad * sizeof(float));
   if (s != OKL_OK) return s;
   p.partial = (float*)ctx->workspace;
-  const int smem = 2 * 16384 + 2 * (opad / 64) * 16384 + 64 + F1_KP * 4 + p.C * p.PH * p.PWp * 4 + 1024;
 #define F1_WG(OO)                                                                                                     \
   {                                                                                                                   \
     static int set = 0;                                                                                               \
@@ -1358,7 +1421,7 @@ extern "C" int okl_conv_first_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const 
 #undef F1_WG
   OKL_LAUNCHED(ctx, "conv_first_wgrad");
   const int total = (p.K + 1) * p.O;
-  conv_first_wgrad_reduce<<<(total * 32 + 255) / 256, 256, 0, ctx->stream>>>(p.partial, (float*)dW, (float*)db, p.O, opad, p.K, grid);
+  conv_first_wgrad_reduce<<<(total * 32 + 255) / 256, 256, 0, ctx->stream>>>(p.partial, (float*)dW, (float*)db, p.O, opad, p.K, KP, grid);
   OKL_LAUNCHED(ctx, "conv_first_wgrad_reduce");
   return OKL_OK;
 }

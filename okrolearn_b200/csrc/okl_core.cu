@@ -155,7 +155,8 @@ static int ensure_pipeline(okl_ctx* ctx) {
 }
 
 extern "C" int okl_batch_prefetch(okl_ctx* ctx, int slot, void* x_dst, const void* x_src, long long x_row_elems, void* t_dst,
-                                  const void* t_src, long long t_row_elems, const void* idx, long long rows, void* x_nxc_dst, int x_channels) {
+                                  const void* t_src, long long t_row_elems, const void* idx, long long rows, void* x_nxc_dst, int x_channels,
+                                  int x_nxc_bf16) {
   OKL_REQUIRE(ctx && (slot == 0 || slot == 1), "okl_batch_prefetch: slot must be 0 or 1");
   OKL_REQUIRE(!ctx->capturing && ctx->cur_lane == 0, "okl_batch_prefetch: not inside a capture / auxiliary lane");
   int s = ensure_pipeline(ctx);
@@ -173,8 +174,10 @@ extern "C" int okl_batch_prefetch(okl_ctx* ctx, int slot, void* x_dst, const voi
   s = okl_gather_batch(ctx, x_dst, x_src, x_row_elems, t_dst, t_src, t_row_elems, idx, rows);
   // a channels-last first layer (tensor-core convolution): the (N, C, S) -> (N, S, C) permutation of the batch also happens here,
   // on the copy stream, instead of at the head of the step's critical path
-  if (s == OKL_OK && x_nxc_dst && x_channels > 1 && rows > 0 && x_row_elems % x_channels == 0)
-    s = okl_permute(ctx, x_nxc_dst, x_dst, (int)rows, x_channels, x_row_elems / x_channels, OKL_NCX);
+  if (s == OKL_OK && x_nxc_dst && x_channels > 1 && rows > 0 && x_row_elems % x_channels == 0) {
+    if (x_nxc_bf16) s = okl_to_bf16_nxc(ctx, x_dst, x_nxc_dst, (int)rows, x_channels, x_row_elems / x_channels);
+    else s = okl_permute(ctx, x_nxc_dst, x_dst, (int)rows, x_channels, x_row_elems / x_channels, OKL_NCX);
+  }
   ctx->stream = main_stream;
   if (s != OKL_OK) return s;
   OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_slot[slot], ctx->copy_stream));

@@ -196,7 +196,17 @@ class MSELoss:
         n = outputs.size
         relu = self._fuse_relu
         fuse = relu is not None and getattr(relu, "outputs", None) is outputs
-        if (outputs.ndim >= 3 and outputs._dev_valid and outputs._layout == _lib.NXC and outputs.shape[1] > 1 and
+        if (outputs.ndim >= 3 and outputs._dev_valid and outputs._layout == _lib.NXC and outputs._b16_primary and outputs.shape[1] % 8 == 0 and
+                0 < outputs.shape[0] <= 65535 and n // (outputs.shape[0] * outputs.shape[1]) > 1 and
+                outputs._bf16_ver == (outputs._dev_ver, _lib.NXC) and getattr(outputs, "_lazy_fn", None) is None):
+            # bf16 channels-last outputs of a BF16 tensor-core convolution: loss and gradient straight from / to that format against
+            # the caller's fp32 (N, C, ...) targets - no fp32 copy of the outputs, no fp32 gradient, nothing permuted
+            N_, C_ = outputs.shape[0], outputs.shape[1]
+            S_ = n // (N_ * C_)
+            grad = Tensor._empty_b16(outputs.shape, np.float64, _lib.NXC)
+            check(lib.okl_mse_fwd_bwd_nxc_bf16(ctx.h, outputs._bf16.ptr, targets._dptr(NCX), loss.ptr, grad._bf16.ptr, N_, C_, S_,
+                                               float(n * ctx.nranks), self._loss_accum, 1 if fuse else 0))
+        elif (outputs.ndim >= 3 and outputs._dev_valid and outputs._layout == _lib.NXC and outputs.shape[1] > 1 and
                 outputs.shape[0] <= 65535 and getattr(outputs, "_lazy_fn", None) is None):
             # channels-last outputs of a tensor-core convolution: loss and gradient are computed in that layout against the
             # caller's (N, C, ...) targets - neither tensor is permuted in memory

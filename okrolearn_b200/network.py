@@ -30,6 +30,7 @@ from typing import Callable
 import numpy as np
 
 from . import _lib
+from . import layers as _layers_mod
 from ._lib import lib, check, get_ctx, NCX, ACT_NONE
 from .tensor import Tensor, _DevBuf, _numel, pinned_empty, pinned_base
 from .layers import (apply_pending_updates, ParamArena, _ParamLayer, _Activation, _Pool, ReLUActivationLayer, SigmoidActivationLayer, SoftmaxActivationLayer,
@@ -545,10 +546,14 @@ class NeuralNetwork:
         first = self.layers[0] if self.layers else None
         x_nxc = bool(self.prefetch_batches and ctx.precision != _lib.FP32 and isinstance(first, _ConvBase) and first._tc_eligible() and
                      getattr(first, "_fused_pool", None) is None and len(sample_shape) >= 2 and sample_shape[0] > 1 and _numel(sample_shape[1:]) > 1)
+        # BF16 mode: that copy is written as bf16 (permutation + conversion in one pass on the copy stream) - the operand format of the
+        # second-generation convolution, which then reads the batch without any fp32 detour
+        x_b16 = bool(x_nxc and ctx.precision == _lib.BF16 and _layers_mod._BF16_ONLY and first.in_channels % 64 == 0 and
+                     first.out_channels % 64 == 0 and batch_size <= 65535)
         if x_nxc:
             for sl_ in st.slots:
-                if getattr(sl_, "xnxc", None) is None:
-                    sl_.xnxc = _DevBuf(ctx, max(batch_size * row_elems, 1) * 4)
+                if getattr(sl_, "xnxc", None) is None or sl_.xnxc.nbytes < max(batch_size * row_elems, 1) * (2 if x_b16 else 4):
+                    sl_.xnxc = _DevBuf(ctx, max(batch_size * row_elems, 1) * (2 if x_b16 else 4))
 
         def prefetch(batch):
             """gather batch `batch` of the current permutation into slot batch % 2 on the copy stream"""
@@ -556,7 +561,8 @@ class NeuralNetwork:
             rows = min(b0 + batch_size, num_samples) - b0
             sl = st.slots[batch & 1]
             check(lib.okl_batch_prefetch(ctx.h, batch & 1, sl.xbuf.ptr, x_src, row_elems, sl.tin.ptr, t_src, t_row,
-                                         idx_dev.ptr + b0 * 4, rows, sl.xnxc.ptr if x_nxc else None, sample_shape[0] if x_nxc else 0))
+                                         idx_dev.ptr + b0 * 4, rows, sl.xnxc.ptr if x_nxc else None, sample_shape[0] if x_nxc else 0,
+                                         1 if x_b16 else 0))
 
         lossf = C.c_float()
 
@@ -619,7 +625,11 @@ class NeuralNetwork:
                 else:
                     # a fresh view per step: a layer may re-lay-out ITS input tensor (channels-last for the tensor-core convs),
                     # which must never redirect or relabel the slot's own buffer - the gather keeps writing NC.. rows there
-                    if x_nxc and pipelined:
+                    if x_b16 and pipelined:
+                        bx = Tensor._view(None, 0, (rows,) + sample_shape, np.float32, bound=False)
+                        bx._layout, bx._b16_primary, bx._bf16, bx._f32_stamp = _lib.NXC, True, sl.xnxc, None
+                        bx._bf16_ver = (bx._dev_ver, _lib.NXC)
+                    elif x_nxc and pipelined:
                         bx = Tensor._view(sl.xnxc, 0, (rows,) + sample_shape, np.float32, bound=False)
                         bx._layout = _lib.NXC
                     else:

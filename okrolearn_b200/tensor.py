@@ -360,6 +360,17 @@ class Tensor:
         if (self._b16_primary and self._dev_valid and self._bf16_ver == (self._dev_ver, self._layout) and
                 (layout == self._layout or len(self._shape) < 3)):
             return self._bf16.ptr                       # storage of record: no fp32 detour
+        if (layout == NXC and len(self._shape) >= 3 and not self._b16_primary and self._shape[0] > 0 and self._shape[1] > 1 and
+                self._shape[1] % 8 == 0 and _numel(self._shape[2:]) > 1 and self._shape[0] <= 65535):
+            # fp32 in the caller's (N, C, S) layout -> bf16 (N, S, C) in ONE pass; the fp32 copy keeps its layout
+            src = self._dptr(None)
+            if self._layout == NCX:
+                if getattr(self, "_bf16", None) is None or self._bf16.nbytes < self.size * 2:
+                    self._bf16, self._bf16_ver = _DevBuf(ctx, max(self.size, 1) * 2), None
+                if self._bf16_ver != (self._dev_ver, "nxc-of-ncx"):
+                    check(lib.okl_to_bf16_nxc(ctx.h, src, self._bf16.ptr, self._shape[0], self._shape[1], _numel(self._shape[2:])))
+                    self._bf16_ver = (self._dev_ver, "nxc-of-ncx")
+                return self._bf16.ptr
         src = self._dptr(layout)
         if (getattr(self, "_bf16", None) is None or self._bf16_ver != (self._dev_ver, self._layout) or
                 self._bf16.nbytes < self.size * 2):

@@ -283,6 +283,45 @@ def first():
 
 if "first" in what:
     first()
+def diag():
+    """Where does the k loop's time go?  OKL_CT_DIAG / OKL_WG_DIAG: 1 = every MMA issued twice (time doubles only if the MMA / operand
+    fetch is the limit), 2 / 4 = A / B operands loaded once per stage slot (time drops only if L2 -> shared memory is the limit)"""
+    N = int(os.environ.get("PROBE_BATCH", "1024"))
+    rng = np.random.default_rng(0)
+    for (Cc, Oc, S) in LAYERS:
+        d = desc(2, N, Cc, Oc, (S, S), 3, 1, act=1)
+        d0 = desc(2, N, Cc, Oc, (S, S), 3, 1, act=0)
+        x16, y16, g16, dx16 = (_DevBuf(ctx, N * c * S * S * 2) for c in (Cc, Oc, Oc, Cc))
+        for bfr in (x16, g16):
+            check(lib.okl_memset(ctx.h, bfr.ptr, 0x3c, bfr.nbytes))
+        W = okl.Tensor((rng.standard_normal((Oc, Cc, 3, 3)) * 0.1).astype(np.float32))
+        bias = okl.Tensor(np.zeros(Oc, dtype=np.float32))
+        w2, wf = _DevBuf(ctx, W.size * 2), _DevBuf(ctx, W.size * 2)
+        check(lib.okl_conv2_filter_banks(ctx.h, C.byref(d), W._dptr(), w2.ptr, wf.ptr))
+        dWb, dbb = _DevBuf(ctx, W.size * 4), _DevBuf(ctx, Oc * 4)
+        os.environ["OKL_WG_ALL"] = "1"
+        row = f"L {Cc:3d}->{Oc:3d}@{S:2d}: "
+        for pair in ("1", "0"):
+            os.environ["OKL_CT_PAIR"] = pair
+            out = []
+            for dg in ((0, 1) if pair == "1" else (0, 1, 2, 4, 6, 7)):
+                os.environ["OKL_CT_DIAG"] = str(dg)
+                t1 = timeit(lambda: check(lib.okl_conv2_fprop(ctx.h, C.byref(d), x16.ptr, w2.ptr, bias._dptr(), None, y16.ptr)))
+                out.append(f"diag{dg} {t1:6.1f}")
+            os.environ["OKL_CT_DIAG"] = "0"
+            print(row + f"fprop pair={pair}  " + "  ".join(out), flush=True)
+        os.environ.pop("OKL_CT_PAIR", None)
+        out = []
+        for dg in (0, 1, 2, 3):
+            os.environ["OKL_WG_DIAG"] = str(dg)
+            tw = timeit(lambda: check(lib.okl_conv2_wgrad(ctx.h, C.byref(d0), x16.ptr, g16.ptr, dWb.ptr, dbb.ptr)))
+            out.append(f"diag{dg} {tw:6.1f}")
+        os.environ["OKL_WG_DIAG"] = "0"
+        print(row + "wgrad (gen 2)  " + "  ".join(out), flush=True)
+
+
+if "diag" in what:
+    diag()
 if "parity" in what:
     parity()
 if "misc" in what:

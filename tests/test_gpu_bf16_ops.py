@@ -1,0 +1,115 @@
+"""Layout- and precision-crossing kernels of the BF16 pipeline (okl_bf16_ops.cu) through the C ABI: fp32 (N, C, S) -> bf16 (N, S, C)
+in one pass, MSELoss on bf16 channels-last outputs against fp32 reference-layout targets; and the BF16 Conv1D train loop that uses
+both (BASELINE configs[3]a shape family) against the oracle network."""
+import ctypes as C
+import logging
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from oracle import okl_oracle as O
+
+pytestmark = pytest.mark.gpu
+logging.getLogger("NeuralNetwork").setLevel(logging.CRITICAL)
+
+
+def bf16_round(a):
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def fetch_bf16(lib, check, ctx, ptr, n):
+    raw = np.empty(n, dtype=np.uint16)
+    check(lib.okl_d2h_async_raw(ctx.h, raw.ctypes.data, ptr, n * 2))
+    ctx.sync()
+    return (raw.astype(np.uint32) << 16).view(np.float32)
+
+
+SHAPES = [(3, 64, (1024,)), (2, 8, (5, 7)), (4, 24, (130,)), (1, 64, (4, 6, 10)), (5, 40, (129,)), (2, 16, (2,))]
+
+
+@pytest.mark.parametrize("N,Cc,sp", SHAPES)
+def test_to_bf16_nxc_is_exact(okl, N, Cc, sp):
+    from okrolearn_b200 import _lib
+    from okrolearn_b200.tensor import _DevBuf
+    lib, check, ctx = _lib.lib, _lib.check, okl.get_ctx()
+    rng = np.random.default_rng(N * 7 + Cc)
+    x = rng.standard_normal((N, Cc) + sp).astype(np.float32)
+    S = int(np.prod(sp))
+    t = okl.Tensor(x)
+    out = _DevBuf(ctx, x.size * 2)
+    check(lib.okl_to_bf16_nxc(ctx.h, t._dptr(_lib.NCX), out.ptr, N, Cc, S))
+    got = fetch_bf16(lib, check, ctx, out.ptr, x.size).reshape(N, S, Cc)
+    want = np.moveaxis(bf16_round(x).reshape(N, Cc, S), 1, 2)
+    assert np.array_equal(got, want)
+    # the Tensor-level entry point (what a BF16 convolution calls on a reference-layout input) gives the same bits and keeps the
+    # fp32 copy in the caller's layout
+    p16 = t._b16(_lib.NXC)
+    assert t._layout == _lib.NCX
+    assert np.array_equal(fetch_bf16(lib, check, ctx, p16, x.size).reshape(N, S, Cc), want)
+
+
+@pytest.mark.parametrize("relu", [0, 1])
+@pytest.mark.parametrize("N,Cc,sp", SHAPES)
+def test_mse_bf16_channels_last_vs_oracle(okl, N, Cc, sp, relu):
+    from okrolearn_b200 import _lib
+    from okrolearn_b200.tensor import _DevBuf
+    lib, check, ctx = _lib.lib, _lib.check, okl.get_ctx()
+    rng = np.random.default_rng(N * 11 + Cc + relu)
+    o = bf16_round(rng.standard_normal((N, Cc) + sp).astype(np.float32))
+    if relu:
+        o = np.maximum(o, 0)
+    tg = rng.standard_normal((N, Cc) + sp).astype(np.float32)
+    S = int(np.prod(sp))
+    to, tt = okl.Tensor(o), okl.Tensor(tg)
+    loss, g16 = _DevBuf(ctx, 4), _DevBuf(ctx, o.size * 2)
+    check(lib.okl_mse_fwd_bwd_nxc_bf16(ctx.h, to._b16(_lib.NXC), tt._dptr(_lib.NCX), loss.ptr, g16.ptr, N, Cc, S, float(o.size), None, relu))
+    lv = np.empty(1, dtype=np.float32)
+    check(lib.okl_d2h_async_raw(ctx.h, lv.ctypes.data, loss.ptr, 4))
+    ctx.sync()
+    want_loss = O.mse_forward(o.astype(np.float64), tg.astype(np.float64))
+    want_g = O.mse_backward(o.astype(np.float64), tg.astype(np.float64))
+    if relu:
+        want_g = want_g * (o > 0)
+    got = np.moveaxis(fetch_bf16(lib, check, ctx, g16.ptr, o.size).reshape(N, S, Cc), 2, 1).reshape(o.shape)
+    assert abs(float(lv[0]) - want_loss) <= 1e-5 * abs(want_loss)
+    assert rel_err(got, want_g) < 5e-3                      # bf16 storage of the gradient: 2^-9 relative per element
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_bf16_conv1d_train_uses_bf16_batches_and_loss(okl, graph):
+    """Conv1D(64, 64, 3, 1, 1) + ReLU + MSE in BF16 mode: the prefetch hands the layer a bf16 channels-last batch, the loss consumes the
+    bf16 outputs and emits the bf16 gradient (no fp32 activation / gradient tensor on the path); two epochs with different batches,
+    graph replay and eager, against the oracle network."""
+    okl.set_precision("bf16")
+    try:
+        rng = np.random.default_rng(123)
+        N, B, L = 48, 8, 256
+        X = rng.standard_normal((N, 64, L)).astype(np.float32)
+        X.reshape(-1)[0] = abs(X.reshape(-1)[0]) + 0.1
+        T = rng.standard_normal((N, 64, L)).astype(np.float32)
+        W = (rng.standard_normal((64, 64, 3)) * 0.1).astype(np.float32)
+        net = okl.NeuralNetwork()
+        conv = okl.Conv1DLayer(64, 64, 3, 1, 1)
+        conv.weights.data = W.copy()
+        net.add(conv)
+        net.add(okl.ReLUActivationLayer())
+        net.use_graph = graph
+        np.random.seed(5)
+        ls = net.train(okl.Tensor(X.copy()), okl.Tensor(T.copy()), epochs=2, lr_scheduler=okl.LearningRateScheduler(0.05),
+                       optimizer=okl.SGDOptimizer(), batch_size=B, loss_function=okl.MSELoss())
+        on = O.OracleNetwork([O.OracleConv(W, np.zeros((64, 1)), 1, 1, fast=True), O.OracleReLU()])
+        np.random.seed(5)
+        Xo, To, ol = X.copy(), T.copy(), []
+        for ep in range(2):
+            idx = np.arange(N)
+            np.random.shuffle(idx)
+            Xo, To = Xo[idx], To[idx]
+            ol.append(sum(on.train_step(Xo[s:s + B], To[s:s + B], O.OracleMSE(), 0.05) for s in range(0, N, B)) / (N // B))
+        assert rel_err(ls, ol) < 1e-2
+        assert rel_err(conv.weights.data, on.layers[0].W) < 2e-2
+        assert rel_err(conv.biases.data, on.layers[0].b) < 2e-2
+    finally:
+        okl.set_precision("fp32")
