@@ -266,7 +266,7 @@ def ncu_traffic(profile, needle):
 CIFAR_LAYERS = [(3, 64, 32), (64, 64, 32), (64, 128, 16), (128, 128, 16), (128, 256, 8), (256, 256, 8)]
 
 
-def conv_cases(okl, ctx, nd, N, Cc, Oc, sp, k, pad, relu, label, prec, need_dx=True):
+def conv_cases(okl, ctx, nd, N, Cc, Oc, sp, k, pad, relu, label, prec, need_dx=True, first_nxc=False):
     """fprop / dgrad / wgrad of one convolution layer through the C ABI (the calls the layer makes), on synthetic tensors."""
     import ctypes as C
     from okrolearn_b200 import _lib
@@ -274,6 +274,10 @@ def conv_cases(okl, ctx, nd, N, Cc, Oc, sp, k, pad, relu, label, prec, need_dx=T
     rng = np.random.default_rng(0)
     lay = {1: okl.Conv1DLayer, 2: okl.Conv2DLayer, 3: okl.Conv3DLayer}[nd](Cc, Oc, k, 1, pad)
     lay._fused_act = 1 if relu else 0
+    if not need_dx:                                       # what the train-step planner sets for a small-K first / only layer
+        lay._need_dx, lay._out_nxc_if_first = False, True
+        if first_nxc:
+            lay._out_layout = _lib.NXC
     x = okl.Tensor(rng.standard_normal((N, Cc) + sp, dtype=np.float32))
     y = lay.forward(x)                                   # decides layouts / bf16 path exactly as the training step does
     g = okl.Tensor(rng.standard_normal(y.shape, dtype=np.float32))
@@ -287,7 +291,20 @@ def conv_cases(okl, ctx, nd, N, Cc, Oc, sp, k, pad, relu, label, prec, need_dx=T
     es = 2 if getattr(lay, "_bf16_path", False) else 4
     xb, yb, wb = N * Cc * int(np.prod(sp)), N * Oc * So, Oc * Cc * taps
     dx = okl.Tensor._empty(x.shape, np.float32, layout=xl)
-    if getattr(lay, "_conv2", False):
+    if getattr(lay, "_first_tc", False):
+        # small-K tcgen05 kernels (first layer of an image network, the video block): fp32 reference-layout input, bf16 channels-last
+        # output / output gradient; the operand is built in shared memory, bias and bias gradient ride in the product
+        g16 = g._b16(_lib.NXC)
+        y16 = okl.Tensor._empty_b16(y.shape, np.float32)
+        keep_extra = (y16,)
+        xp = x._dptr(_lib.NCX)
+        f_fp = lambda: check(lib.okl_conv_first_fprop(ctx.h, C.byref(d), xp, None, b.ptr(0), b.ptr(1), y16._bf16.ptr))                # noqa: E731
+        f_wg = lambda: check(lib.okl_conv_first_wgrad(ctx.h, C.byref(d0), xp, None, g16, b.grad_ptr(0), b.grad_ptr(1)))               # noqa: E731
+        f_dg = None
+        by_fp = 4.0 * (xb + wb) + 2.0 * yb
+        by_dg = 0.0
+        by_wg = 4.0 * (xb + wb) + 2.0 * yb
+    elif getattr(lay, "_conv2", False):
         # second-generation BF16 path (okl_conv_tc.cu): every operand and result is channels-last bf16, exactly the calls the layer makes
         w2, wf = lay._filter_banks(d)
         x16, g16 = x._b16(_lib.NXC), g._b16(_lib.NXC)
@@ -336,8 +353,10 @@ def kernel_rooflines(okl, ctx, name, batch, peaks, prec):
     cases = []
     if name == "cifar6":
         for i, (c, o, s) in enumerate(CIFAR_LAYERS):
-            if i == 0:
-                continue                                  # 3 -> 64 first layer: fused conv+relu(+pool-less) small-K kernels, HBM-bound
+            if i == 0:                                    # 3 -> 64 first layer: small-K kernels, HBM-bound (bf16 output written / gradient read)
+                if prec == "bf16":
+                    cases += conv_cases(okl, ctx, 2, batch, c, o, (s, s), 3, 1, True, f"conv1 {c}->{o}@{s}x{s}", prec, need_dx=False, first_nxc=True)
+                continue
             cases += conv_cases(okl, ctx, 2, batch, c, o, (s, s), 3, 1, True, f"conv{i + 1} {c}->{o}@{s}x{s}", prec)
     elif name == "conv1d_seq":
         cases += conv_cases(okl, ctx, 1, batch, 64, 64, (1024,), 3, 1, True, "conv1d 64->64 L1024", prec, need_dx=False)
@@ -738,7 +757,7 @@ def main():
         for wl in second:
             if wl == name:
                 continue
-            prec = "bf16" if wl in ("mlp8192",) else "tf32"
+            prec = "tf32" if wl in ("mnist_cnn", "conv2d_single") else "bf16"
             kk = {"mnist_cnn": 200, "conv2d_single": 200, "conv1d_seq": 10, "conv3d_video": 10, "mlp8192": 4}[wl]
             try:
                 r = run_workload(okl, ctx, wl, WORKLOADS[wl]["batch"], kk, 3, prec, rank, world, want_e2e=(world == 1 and wl in ("mnist_cnn",)),

@@ -102,9 +102,13 @@ int okl_gather_batch(okl_ctx* ctx, void* x_dst, const void* x_src, long long x_r
  * compute stream (so the slot's previous consumer is finished); okl_batch_wait: the compute stream waits for that slot.
  * x_nxc_dst (optional): additionally a channels-last (N, S, C) copy of the gathered inputs, for a first layer that runs
  * channels-last on the tensor cores - its layout permutation then overlaps the previous step too; x_nxc_bf16 != 0: that copy
- * is written as bf16 (okl_to_bf16_nxc: permutation and conversion in one pass), the operand format of the BF16 convolutions. */
+ * is written as bf16 (okl_to_bf16_nxc: permutation and conversion in one pass), the operand format of the BF16 convolutions.
+ * Gather-free parts: a NULL x_dst / t_dst skips that gather - its consumer reads the dataset rows through the index itself (the
+ * *_rows_i32 arguments of okl_to_bf16_nxc, okl_conv_first_*, okl_mse_fwd_bwd_nxc_bf16); idx_dst (optional) receives the batch's
+ * index slice at a fixed per-slot address for those consumers (and for graph replay). */
 int okl_batch_prefetch(okl_ctx* ctx, int slot, void* x_dst, const void* x_src, long long x_row_elems, void* t_dst, const void* t_src,
-                       long long t_row_elems, const void* idx_i32, long long rows, void* x_nxc_dst, int x_channels, int x_nxc_bf16);
+                       long long t_row_elems, const void* idx_i32, long long rows, void* x_nxc_dst, int x_channels, int x_nxc_bf16,
+                       void* idx_dst);
 int okl_batch_wait(okl_ctx* ctx, int slot);
 /* Per-step loss read-back (okl.py:2973 reads loss.data every batch) without stalling the device: _async copies the device scalar
  * to page-locked host memory in stream order (slot 0/1), _wait blocks the host until that copy has landed and returns it - called
@@ -341,10 +345,11 @@ int okl_channel_sum_bf16(okl_ctx* ctx, const void* g16, void* out, long long row
  * (N, C, S) tensor -> the bf16 (N, S, C) operand of the tensor-core convolutions (replaces okl_permute + okl_to_bf16: the im2col +
  * cast of okl.py:691-699, 948-957 never exists).  okl_mse_fwd_bwd_nxc_bf16: MSELoss (okl.py:1833-1839) of bf16 (N, S, C) outputs
  * against fp32 (N, C, S) targets; loss (fp32 scalar, mean over N*C*S), gradient 2 (o - t) / denom as bf16 (N, S, C), optionally
- * with the backward of the ReLU that produced the outputs (okl.py:107).  C % 8 == 0. */
-int okl_to_bf16_nxc(okl_ctx* ctx, const void* src_ncx_f32, void* dst_nxc_bf16, int N, int C, long long S);
-int okl_mse_fwd_bwd_nxc_bf16(okl_ctx* ctx, const void* o16_nxc, const void* t_ncx, void* loss, void* grad16_nxc, int N, int C, long long S,
-                             float denom, void* loss_accum, int relu_outputs);
+ * with the backward of the ReLU that produced the outputs (okl.py:107).  C % 8 == 0.  *_rows_i32 (optional): sample n is row
+ * rows[n] of the fp32 tensor - the batch of a shuffled epoch (okl.py:2957-2967) is read straight from the dataset, no gathered copy. */
+int okl_to_bf16_nxc(okl_ctx* ctx, const void* src_ncx_f32, const void* src_rows_i32, void* dst_nxc_bf16, int N, int C, long long S);
+int okl_mse_fwd_bwd_nxc_bf16(okl_ctx* ctx, const void* o16_nxc, const void* t_ncx, const void* t_rows_i32, void* loss, void* grad16_nxc, int N, int C,
+                             long long S, float denom, void* loss_accum, int relu_outputs);
 
 /* BF16 implicit-GEMM convolution on tcgen05, second generation (csrc/okl_conv_tc.cu): replaces the contraction of
  * Conv1DLayer/Conv2DLayer.forward (okl.py:700-711, 801-811) and of their input-gradient loops (okl.py:722-740, 854-868 with repairs
@@ -357,12 +362,14 @@ int okl_conv2_supported(okl_ctx* ctx, const okl_conv_desc* d);
 int okl_conv2_filter_banks(okl_ctx* ctx, const okl_conv_desc* d, const void* W, void* w2_16, void* wf_16);
 int okl_conv2_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void* x16, const void* w2_16, const void* bias, void* y, void* y16);
 int okl_conv2_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* g16, const void* wf_16, void* dx, void* dx16, const void* relu_mask16);
-/* First layer of an image network (tiny C: C * taps < 32, e.g. Conv2DLayer(3, 64, 3, 1, 1); okl.py:790-813, 869-871): x is the fp32
- * (N, C, H, W) batch, y16 / g16 are channels-last bf16; the im2col operand is built in shared memory in the UMMA layout and consumed
- * by tcgen05.mma; bias and bias gradient ride in the same product as a constant-one tap. */
+/* Small-K convolution (C * taps < 128): the first layer of an image network, e.g. Conv2DLayer(3, 64, 3, 1, 1) (okl.py:790-813,
+ * 869-871), and the video block Conv3DLayer(3, 64, 3, 1, 1) (okl.py:948-985, 1018-1031).  x is the fp32 (N, C, *spatial) batch -
+ * or, with x_rows_i32, the rows x_rows[n] of the whole dataset; y16 / g16 are channels-last bf16; the im2col operand is built in
+ * shared memory in the UMMA layout from a staged input patch and consumed by tcgen05.mma; bias and bias gradient ride in the same
+ * product as a constant-one tap.  2-D and 3-D, unit stride, O in {64, 128, 256}. */
 int okl_conv_first_supported(okl_ctx* ctx, const okl_conv_desc* d);
-int okl_conv_first_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* W, const void* bias, void* y16);
-int okl_conv_first_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* g16, void* dW, void* db);
+int okl_conv_first_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* x_rows_i32, const void* W, const void* bias, void* y16);
+int okl_conv_first_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* x_rows_i32, const void* g16, void* dW, void* db);
 /* filter gradient (okl.py:739-741, 869-871) and, optionally, the bias gradient (okl.py:721, 870 with repair R2): dW fp32 in the
  * reference layout (O, C, *k); both operands channels-last bf16; split-K over the SMs with a fixed-order second stage. */
 int okl_conv2_wgrad_supported(okl_ctx* ctx, const okl_conv_desc* d);

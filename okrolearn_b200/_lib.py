@@ -82,7 +82,7 @@ SIGNATURES = {
     "okl_unfold_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i]),
     "okl_fold_permute": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _i]),
     "okl_gather_batch": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll]),
-    "okl_batch_prefetch": (_i, [_vp, _i, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _i, _i]),
+    "okl_batch_prefetch": (_i, [_vp, _i, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _i, _i, _vp]),
     "okl_batch_wait": (_i, [_vp, _i]),
     "okl_loss_fetch_async": (_i, [_vp, _i, _vp]),
     "okl_loss_fetch_wait": (_i, [_vp, _i, C.POINTER(C.c_float)]),
@@ -108,15 +108,15 @@ SIGNATURES = {
     "okl_pool2_bf16_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
     "okl_pool2_bf16_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "okl_channel_sum_bf16": (_i, [_vp, _vp, _vp, _ll, _i]),
-    "okl_to_bf16_nxc": (_i, [_vp, _vp, _vp, _i, _i, _ll]),
-    "okl_mse_fwd_bwd_nxc_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _f, _vp, _i]),
+    "okl_to_bf16_nxc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _ll]),
+    "okl_mse_fwd_bwd_nxc_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _f, _vp, _i]),
     "okl_conv2_supported": (_i, [_vp, _P(ConvDesc)]),
     "okl_conv2_filter_banks": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp]),
     "okl_conv2_fprop": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "okl_conv2_dgrad": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "okl_conv_first_supported": (_i, [_vp, _P(ConvDesc)]),
-    "okl_conv_first_fprop": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp]),
-    "okl_conv_first_wgrad": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp]),
+    "okl_conv_first_fprop": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
+    "okl_conv_first_wgrad": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "okl_conv2_wgrad_supported": (_i, [_vp, _P(ConvDesc)]),
     "okl_conv2_wgrad": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp]),
     "okl_tc_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _i]),

@@ -204,12 +204,14 @@ __device__ __forceinline__ void xt_load_tile(float* tile, const float* __restric
 }
 
 // x (N, C, S) fp32 -> x16 (N, S, C) bf16; C % 8 == 0
-__global__ void __launch_bounds__(256) to_bf16_nxc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int Cc, long long S, int vec) {
+// rows (optional): sample n of the output is row rows[n] of x - the batch of a shuffled epoch is read straight from the dataset
+__global__ void __launch_bounds__(256) to_bf16_nxc_kernel(const float* __restrict__ x, const int* __restrict__ rows, __nv_bfloat16* __restrict__ y, int Cc,
+                                                          long long S, int vec) {
   __shared__ float tile[XT_C * XT_PITCH];
   const size_t img = (size_t)blockIdx.z * Cc * S;
   const int c0 = blockIdx.x * XT_C;
   const long long s0 = (long long)blockIdx.y * XT_S;
-  xt_load_tile(tile, x, img, Cc, S, c0, s0, vec != 0);
+  xt_load_tile(tile, x, rows ? (size_t)rows[blockIdx.z] * Cc * S : img, Cc, S, c0, s0, vec != 0);
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < XT_S * (XT_C / 8) / 256; k++) {
@@ -227,14 +229,15 @@ __global__ void __launch_bounds__(256) to_bf16_nxc_kernel(const float* __restric
 // partial sums of (o - t)^2 and the gradient 2 (o - t) / denom as bf16 (N, S, C) - with RELU the backward of the ReLU that produced
 // the outputs (g * (o > 0), okl.py:107) is applied in the same pass.  Neither tensor is permuted or converted in memory.
 template <bool RELU>
-__global__ void __launch_bounds__(256) mse_nxc_bf16_kernel(const __nv_bfloat16* __restrict__ o, const float* __restrict__ t, float* __restrict__ partial,
-                                                           __nv_bfloat16* __restrict__ grad, int Cc, long long S, float scale, int vec) {
+__global__ void __launch_bounds__(256) mse_nxc_bf16_kernel(const __nv_bfloat16* __restrict__ o, const float* __restrict__ t, const int* __restrict__ t_rows,
+                                                           float* __restrict__ partial, __nv_bfloat16* __restrict__ grad, int Cc, long long S, float scale,
+                                                           int vec) {
   __shared__ float tile[XT_C * XT_PITCH];
   __shared__ float sh[8];
   const size_t img = (size_t)blockIdx.z * Cc * S;
   const int c0 = blockIdx.x * XT_C;
   const long long s0 = (long long)blockIdx.y * XT_S;
-  xt_load_tile(tile, t, img, Cc, S, c0, s0, vec != 0);
+  xt_load_tile(tile, t, t_rows ? (size_t)t_rows[blockIdx.z] * Cc * S : img, Cc, S, c0, s0, vec != 0);
   __syncthreads();
   float acc = 0.f;
 #pragma unroll
@@ -282,19 +285,19 @@ __global__ void mse_final_sum_kernel(const float* __restrict__ partial, int coun
 
 }  // namespace
 
-extern "C" int okl_to_bf16_nxc(okl_ctx* ctx, const void* src_ncx_f32, void* dst_nxc_bf16, int N, int Cc, long long S) {
+extern "C" int okl_to_bf16_nxc(okl_ctx* ctx, const void* src_ncx_f32, const void* src_rows_i32, void* dst_nxc_bf16, int N, int Cc, long long S) {
   OKL_REQUIRE(ctx && src_ncx_f32 && dst_nxc_bf16, "NULL argument");
   OKL_REQUIRE(N >= 1 && Cc >= 8 && Cc % 8 == 0 && S >= 1, "okl_to_bf16_nxc: C must be a multiple of 8 (N=%d C=%d)", N, Cc);
   dim3 grid((unsigned)((Cc + XT_C - 1) / XT_C), (unsigned)((S + XT_S - 1) / XT_S), (unsigned)N);
   OKL_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "okl_to_bf16_nxc: extent too large");
   const int vec = (S % 4 == 0 && (reinterpret_cast<uintptr_t>(src_ncx_f32) & 15) == 0) ? 1 : 0;
-  to_bf16_nxc_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)src_ncx_f32, (__nv_bfloat16*)dst_nxc_bf16, Cc, S, vec);
+  to_bf16_nxc_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)src_ncx_f32, (const int*)src_rows_i32, (__nv_bfloat16*)dst_nxc_bf16, Cc, S, vec);
   OKL_LAUNCHED(ctx, "to_bf16_nxc");
   return OKL_OK;
 }
 
-extern "C" int okl_mse_fwd_bwd_nxc_bf16(okl_ctx* ctx, const void* o16_nxc, const void* t_ncx, void* loss, void* grad16_nxc, int N, int Cc, long long S,
-                                        float denom, void* loss_accum, int relu_outputs) {
+extern "C" int okl_mse_fwd_bwd_nxc_bf16(okl_ctx* ctx, const void* o16_nxc, const void* t_ncx, const void* t_rows_i32, void* loss, void* grad16_nxc, int N,
+                                        int Cc, long long S, float denom, void* loss_accum, int relu_outputs) {
   OKL_REQUIRE(ctx && o16_nxc && t_ncx && loss && grad16_nxc, "NULL argument");
   OKL_REQUIRE(N >= 1 && Cc >= 8 && Cc % 8 == 0 && S >= 1 && denom > 0.f, "okl_mse_fwd_bwd_nxc_bf16: C must be a multiple of 8 (N=%d C=%d)", N, Cc);
   dim3 grid((unsigned)((Cc + XT_C - 1) / XT_C), (unsigned)((S + XT_S - 1) / XT_S), (unsigned)N);
@@ -306,11 +309,11 @@ extern "C" int okl_mse_fwd_bwd_nxc_bf16(okl_ctx* ctx, const void* o16_nxc, const
   float* partial = (float*)ctx->workspace;
   const int vec = (S % 4 == 0 && (reinterpret_cast<uintptr_t>(t_ncx) & 15) == 0) ? 1 : 0;
   if (relu_outputs)
-    mse_nxc_bf16_kernel<true><<<grid, 256, 0, ctx->stream>>>((const __nv_bfloat16*)o16_nxc, (const float*)t_ncx, partial, (__nv_bfloat16*)grad16_nxc, Cc, S,
-                                                             2.f / denom, vec);
+    mse_nxc_bf16_kernel<true><<<grid, 256, 0, ctx->stream>>>((const __nv_bfloat16*)o16_nxc, (const float*)t_ncx, (const int*)t_rows_i32, partial,
+                                                             (__nv_bfloat16*)grad16_nxc, Cc, S, 2.f / denom, vec);
   else
-    mse_nxc_bf16_kernel<false><<<grid, 256, 0, ctx->stream>>>((const __nv_bfloat16*)o16_nxc, (const float*)t_ncx, partial, (__nv_bfloat16*)grad16_nxc, Cc, S,
-                                                              2.f / denom, vec);
+    mse_nxc_bf16_kernel<false><<<grid, 256, 0, ctx->stream>>>((const __nv_bfloat16*)o16_nxc, (const float*)t_ncx, (const int*)t_rows_i32, partial,
+                                                              (__nv_bfloat16*)grad16_nxc, Cc, S, 2.f / denom, vec);
   OKL_LAUNCHED(ctx, "mse_fwd_bwd_nxc_bf16");
   mse_final_sum_kernel<<<1, 1024, 0, ctx->stream>>>((const float*)partial, (int)nblk, (float*)loss, 1.f / ((float)N * (float)Cc * (float)S), (float*)loss_accum);
   OKL_LAUNCHED(ctx, "final_sum");

@@ -986,6 +986,7 @@ constexpr int F1_PATCH_MAX = 16384;    // bytes of staged fp32 input per tile
 
 struct F1Params {
   const float* x; const float* W; const float* bias;
+  const int* xrows;                    // optional: sample n of the batch is row xrows[n] of x (a shuffled epoch read straight from the dataset)
   int N, C, D, H, Wd, O, KD, KH, KW, pd, ph, pw, OD, OH, OW;
   int TW, TH, tw_sh, tiles_w, tiles_h, ntiles;
   int K, KS, NA, relu, RH, PH, PWp;    // KS = 16-wide k-steps (KP = 16 KS), NA = swizzle-atom columns of the patch operand (1 or 2)
@@ -1004,53 +1005,91 @@ __device__ __forceinline__ void f1_build_ktab(int* ktab, const F1Params& p) {
   }
 }
 
+// GEN = 0: the 2-D layers with K < 32 (two k-steps, one atom column, no depth taps) - the hot first layer of an image network, with
+// everything that can be fixed at compile time fixed; GEN = 1: the general form (3-D, K < 128).
 // patch element i = ((c * KD + t) * PH + r) * PWp + col  of the tile (image index nd = n * OD + od, origin (h0, w0))
+template <int GEN>
 __device__ __forceinline__ float f1_patch_value(const F1Params& p, int i, int n, int od, int h0, int w0) {
   const int per_t = p.PH * p.PWp;
   const int ct = i / per_t, r2 = i - ct * per_t, r = r2 / p.PWp, col = r2 - r * p.PWp;
-  const int c = ct / p.KD, t = ct - c * p.KD;
-  const int id = od - p.pd + t, ih = h0 - p.ph + r, iw = w0 - p.pw + col;
+  const int c = GEN ? ct / p.KD : ct, t = GEN ? ct - c * p.KD : 0;
+  const int id = GEN ? od - p.pd + t : 0, ih = h0 - p.ph + r, iw = w0 - p.pw + col;
   float v = 0.f;
-  if (n < p.N && id >= 0 && id < p.D && ih >= 0 && ih < p.H && iw >= 0 && iw < p.Wd)
-    v = __ldg(p.x + ((((size_t)n * p.C + c) * p.D + id) * p.H + ih) * p.Wd + iw);
+  if (n < p.N && (!GEN || (id >= 0 && id < p.D)) && ih >= 0 && ih < p.H && iw >= 0 && iw < p.Wd) {
+    const size_t row = p.xrows ? (size_t)__ldg(p.xrows + n) : (size_t)n;
+    v = __ldg(p.x + (((row * p.C + c) * (GEN ? p.D : 1) + id) * p.H + ih) * p.Wd + iw);
+  }
   return v;
 }
+template <int GEN>
 __device__ __forceinline__ void f1_load_patch(float* patch, const F1Params& p, int total, int n, int od, int h0, int w0) {
-  for (int i = threadIdx.x; i < total; i += blockDim.x) patch[i] = f1_patch_value(p, i, n, od, h0, w0);
+  for (int i = threadIdx.x; i < total; i += blockDim.x) patch[i] = f1_patch_value<GEN>(p, i, n, od, h0, w0);
 }
 
 // Software pipelining of the patch: a tile's values are fetched into registers one tile ahead (while the previous tile's MMA and
 // epilogue run) and only copied to shared memory at the top of the tile - ncu had both kernels waiting on these global loads.
-constexpr int F1_PRE = 8;              // values per thread held ahead (patches up to 8 x threads floats; larger ones load directly)
+template <int GEN> struct F1Pre { static constexpr int N = GEN ? 8 : 6; };     // values per thread held ahead (larger patches load directly)
 
-__device__ __forceinline__ void f1_fetch_patch(float* pre, const F1Params& p, int total, int n, int od, int h0, int w0) {
+// Which patch elements a thread fetches never changes from tile to tile - only the tile origin does.  The element's offset relative to
+// the origin and its (t, r, col) position (for the padding test) are therefore decoded ONCE per kernel; the per-tile fetch is an add and
+// three range checks per value (the first version re-did four integer divisions per value and tile: ~800 instructions per thread).
+template <int GEN>
+__device__ __forceinline__ void f1_patch_plan(int* rel, int* trc, const F1Params& p, int total) {
+  const int per_t = p.PH * p.PWp;
 #pragma unroll
-  for (int e = 0; e < F1_PRE; e++) {
+  for (int e = 0; e < F1Pre<GEN>::N; e++) {
     const int i = threadIdx.x + e * blockDim.x;
-    pre[e] = i < total ? f1_patch_value(p, i, n, od, h0, w0) : 0.f;
+    rel[e] = 0; trc[e] = -1;
+    if (i < total) {
+      const int ct = i / per_t, r2 = i - ct * per_t, r = r2 / p.PWp, col = r2 - r * p.PWp;
+      const int c = GEN ? ct / p.KD : ct, t = GEN ? ct - c * p.KD : 0;
+      rel[e] = ((c * (GEN ? p.D : 1) + t) * p.H + r) * p.Wd + col;
+      trc[e] = (t << 20) | (r << 10) | col;
+    }
   }
 }
+template <int GEN>
+__device__ __forceinline__ void f1_fetch_patch(float* pre, const F1Params& p, const int* rel, const int* trc, int n, int od, int h0, int w0) {
+  const int d0 = GEN ? od - p.pd : 0, hh = h0 - p.ph, ww = w0 - p.pw;
+  const long long row = (p.xrows && n < p.N) ? (long long)__ldg(p.xrows + n) : (long long)n;
+  const float* org = p.x + ((row * p.C * (GEN ? p.D : 1) + d0) * p.H + hh) * (long long)p.Wd + ww;
+#pragma unroll
+  for (int e = 0; e < F1Pre<GEN>::N; e++) {
+    const int t = trc[e] >> 20, r = (trc[e] >> 10) & 1023, col = trc[e] & 1023;
+    const bool ok = trc[e] >= 0 && n < p.N && (!GEN || (unsigned)(d0 + t) < (unsigned)p.D) && (unsigned)(hh + r) < (unsigned)p.H &&
+                    (unsigned)(ww + col) < (unsigned)p.Wd;
+    pre[e] = ok ? __ldg(org + rel[e]) : 0.f;
+  }
+}
+template <int GEN>
 __device__ __forceinline__ void f1_store_patch(float* patch, const float* pre, int total) {
 #pragma unroll
-  for (int e = 0; e < F1_PRE; e++) {
+  for (int e = 0; e < F1Pre<GEN>::N; e++) {
     const int i = threadIdx.x + e * blockDim.x;
     if (i < total) patch[i] = pre[e];
   }
 }
 // tile -> image index nd = n * OD + od (the TMA coordinate), (n, od) and the tile origin inside the slice
+template <int GEN>
 __device__ __forceinline__ void f1_tile_origin(const F1Params& p, int tile, int& nd, int& n, int& od, int& h0, int& w0) {
   const int wt = tile % p.tiles_w, r2 = tile / p.tiles_w;
   const int ht = r2 % p.tiles_h;
   nd = r2 / p.tiles_h; w0 = wt * p.TW; h0 = ht * p.TH;
-  n = nd / p.OD; od = nd - n * p.OD;
+  if (GEN) { n = nd / p.OD; od = nd - n * p.OD; }
+  else { n = nd; od = 0; }
 }
 
 // row m of the 128 x KP patch operand as swizzled 16-byte chunks (8 k values each): chunk j -> atom column j / 8, position j % 8;
 // the CTA's threads split a row's 2 KS chunks between them (thread -> pixel m = tid % 128, chunks tid / 128, + threads / 128, ...)
+template <int GEN>
 __device__ __forceinline__ void f1_build_rows(uint8_t* sA, const float* patch, const int* ktab, const F1Params& p, bool pixel_ok) {
   const int m = threadIdx.x & 127, part = threadIdx.x >> 7, nparts = blockDim.x >> 7;
   const int base = (m >> p.tw_sh) * p.PWp + (m & (p.TW - 1));
-  for (int j = part; j < 2 * p.KS; j += nparts) {
+  const int nchunks = GEN ? 2 * p.KS : 4;
+#pragma unroll
+  for (int j0 = 0; j0 < (GEN ? 16 : 4); j0++) {
+    const int j = part + j0 * nparts;
+    if (j >= nchunks) break;
     uint32_t pk[4];
 #pragma unroll
     for (int e = 0; e < 4; e++) {
@@ -1070,19 +1109,21 @@ __device__ __forceinline__ void f1_build_rows(uint8_t* sA, const float* patch, c
 // NT = 128 (O = 64, small patches): small CTAs, five per SM - the tile loop is a chain of latencies (patch -> operand rows -> MMA ->
 // TMEM -> store), and more resident CTAs hide it better than more threads per CTA (three 256-thread CTAs: 80 us vs 73 us at CIFAR
 // batch 1024; ncu: "long scoreboard" on the patch)
-template <int O_, int NT>
+template <int O_, int NT, int GEN>
 __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) conv_first_fprop_kernel(const __grid_constant__ CUtensorMap tmY16, const F1Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                       // NA atom columns of 128 rows x 128 B
-  uint8_t* sB = sA + p.NA * F1_ATOM;                        // NA atom columns of O_ rows x 128 B
-  uint8_t* sStg = sB + p.NA * O_ * 128;                     // one 4 KB staging tile per warp
+  const int NA = GEN ? p.NA : 1;
+  uint8_t* sB = sA + NA * F1_ATOM;                          // NA atom columns of O_ rows x 128 B
+  uint8_t* sStg = sB + NA * O_ * 128;                       // one 4 KB staging tile per warp
   uint64_t* mma_done = reinterpret_cast<uint64_t*>(sStg + (NT / 32) * CT_STG);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
   int* ktab = reinterpret_cast<int*>(mma_done + 2);
   float* patch = reinterpret_cast<float*>(ktab + F1_KPMAX);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KP = p.KS * 16;
+  const int KP = GEN ? p.KS * 16 : 32;
+  constexpr int PRE = F1Pre<GEN>::N;
 
   if (threadIdx.x == 0) {
     mbar_init(mma_done, 1);
@@ -1110,32 +1151,35 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) conv_first_fprop_kernel
   const uint32_t sw = (uint32_t)(lane & 7);
   uint32_t parity = 0;
   const int ptotal = p.C * p.KD * p.PH * p.PWp;
-  const bool piped = ptotal <= F1_PRE * NT;
-  float pre[F1_PRE];
+  const bool piped = ptotal <= PRE * NT;
+  float pre[PRE];
+  int rel[PRE], trc[PRE];
+  if (piped) f1_patch_plan<GEN>(rel, trc, p, ptotal);
   if (piped && (int)blockIdx.x < p.ntiles) {
     int nd, n, od, h0, w0;
-    f1_tile_origin(p, blockIdx.x, nd, n, od, h0, w0);
-    f1_fetch_patch(pre, p, ptotal, n, od, h0, w0);
+    f1_tile_origin<GEN>(p, blockIdx.x, nd, n, od, h0, w0);
+    f1_fetch_patch<GEN>(pre, p, rel, trc, n, od, h0, w0);
   }
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
     int nd, n, od, h0, w0;
-    f1_tile_origin(p, tile, nd, n, od, h0, w0);
-    if (piped) f1_store_patch(patch, pre, ptotal);
-    else f1_load_patch(patch, p, ptotal, n, od, h0, w0);
+    f1_tile_origin<GEN>(p, tile, nd, n, od, h0, w0);
+    if (piped) f1_store_patch<GEN>(patch, pre, ptotal);
+    else f1_load_patch<GEN>(patch, p, ptotal, n, od, h0, w0);
     __syncthreads();                                        // patch complete; every thread is past the previous tile's accumulator reads
-    f1_build_rows(sA, patch, ktab, p, true);
+    f1_build_rows<GEN>(sA, patch, ktab, p, true);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (piped && tile + (int)gridDim.x < p.ntiles) {        // next tile's patch: in flight during this tile's MMA and epilogue
       int nd2, n2, od2, h2, w2;
-      f1_tile_origin(p, tile + gridDim.x, nd2, n2, od2, h2, w2);
-      f1_fetch_patch(pre, p, ptotal, n2, od2, h2, w2);
+      f1_tile_origin<GEN>(p, tile + gridDim.x, nd2, n2, od2, h2, w2);
+      f1_fetch_patch<GEN>(pre, p, rel, trc, n2, od2, h2, w2);
     }
     if (threadIdx.x == 0) {
       tc_fence_after();
       const uint32_t a_lo = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16), b_lo = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
-      for (int ks = 0; ks < p.KS; ks++)                     // k-step ks: atom column ks / 4, 32 bytes further inside its rows per step
+      const int nks = GEN ? p.KS : 2;
+      for (int ks = 0; ks < nks; ks++)                      // k-step ks: atom column ks / 4, 32 bytes further inside its rows per step
         umma_bf16_words<0>(tmem_base, a_lo + (uint32_t)((ks >> 2) * (F1_ATOM >> 4) + (ks & 3) * 2),
                            b_lo + (uint32_t)((ks >> 2) * (O_ * 128 >> 4) + (ks & 3) * 2), TC_DESC_HI_SW128, idesc, ks ? 1u : 0u);
       umma_commit(mma_done);
@@ -1183,12 +1227,13 @@ __global__ void __launch_bounds__(NT, NT == 128 ? 5 : 2) conv_first_fprop_kernel
   if (warp == 0) tmem_dealloc<O_>(tmem_base);
 }
 
-template <int O_>
+template <int O_, int GEN>
 __global__ void __launch_bounds__(F1_THREADS, O_ == 64 ? 3 : 2) conv_first_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const F1Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int GB = (O_ / 64) * 16384;
-  const int AB = p.NA * F1_ATOM;
+  const int NA = GEN ? p.NA : 1;
+  const int AB = NA * F1_ATOM;
   uint8_t* sA = smem;                                       // 2 x patch operands (NA atom columns each)
   uint8_t* sG = sA + 2 * AB;                                // 2 x gradient tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 2 * GB);
@@ -1199,7 +1244,8 @@ __global__ void __launch_bounds__(F1_THREADS, O_ == 64 ? 3 : 2) conv_first_wgrad
   int* ktab = reinterpret_cast<int*>(bars + 6);
   float* patch = reinterpret_cast<float*>(ktab + F1_KPMAX);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KP = p.KS * 16;
+  const int KP = GEN ? p.KS * 16 : 32;
+  constexpr int PRE = F1Pre<GEN>::N;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; s++) { mbar_init(&g_full[s], 1); mbar_init(&st_free[s], 1); }
@@ -1217,47 +1263,49 @@ __global__ void __launch_bounds__(F1_THREADS, O_ == 64 ? 3 : 2) conv_first_wgrad
   okl_pdl_sync();
 
   const int ptotal = p.C * p.KD * p.PH * p.PWp;
-  const bool piped = ptotal <= F1_PRE * F1_THREADS;
-  float pre[F1_PRE];
+  const bool piped = ptotal <= PRE * F1_THREADS;
+  float pre[PRE];
+  int rel[PRE], trc[PRE];
+  if (piped) f1_patch_plan<GEN>(rel, trc, p, ptotal);
   if (piped && (int)blockIdx.x < p.ntiles) {
     int nd, n, od, h0, w0;
-    f1_tile_origin(p, blockIdx.x, nd, n, od, h0, w0);
-    f1_fetch_patch(pre, p, ptotal, n, od, h0, w0);
+    f1_tile_origin<GEN>(p, blockIdx.x, nd, n, od, h0, w0);
+    f1_fetch_patch<GEN>(pre, p, rel, trc, n, od, h0, w0);
   }
   int it = 0;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, it++) {
     const int s = it & 1;
     const uint32_t use = (uint32_t)(it >> 1);               // how many times stage s has been used before
     int nd, n, od, h0, w0;
-    f1_tile_origin(p, tile, nd, n, od, h0, w0);
+    f1_tile_origin<GEN>(p, tile, nd, n, od, h0, w0);
     if (use > 0) mbar_wait(&st_free[s], (use - 1) & 1);     // everyone: stage s (patch operand AND gradient tile) is reusable
     if (threadIdx.x == 0) {
       mbar_expect_tx(&g_full[s], GB);
 #pragma unroll
       for (int j = 0; j < O_ / 64; j++) tma_load_4d(&tmG, &g_full[s], sG + s * GB + j * 16384, j * 64, w0, h0, nd);
     }
-    if (piped) f1_store_patch(patch, pre, ptotal);
-    else f1_load_patch(patch, p, ptotal, n, od, h0, w0);
+    if (piped) f1_store_patch<GEN>(patch, pre, ptotal);
+    else f1_load_patch<GEN>(patch, p, ptotal, n, od, h0, w0);
     __syncthreads();
     {
       const int m = threadIdx.x & 127;
       const bool ok = (w0 + (m & (p.TW - 1))) < p.OW && (h0 + (m >> p.tw_sh)) < p.OH && n < p.N;
-      f1_build_rows(sA + s * AB, patch, ktab, p, ok);
+      f1_build_rows<GEN>(sA + s * AB, patch, ktab, p, ok);
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (piped && tile + (int)gridDim.x < p.ntiles) {
       int nd2, n2, od2, h2, w2;
-      f1_tile_origin(p, tile + gridDim.x, nd2, n2, od2, h2, w2);
-      f1_fetch_patch(pre, p, ptotal, n2, od2, h2, w2);
+      f1_tile_origin<GEN>(p, tile + gridDim.x, nd2, n2, od2, h2, w2);
+      f1_fetch_patch<GEN>(pre, p, rel, trc, n2, od2, h2, w2);
     }
     if (threadIdx.x == 0) {
       mbar_wait(&g_full[s], use & 1);
       tc_fence_after();
       // A = patch^T, MN-major: 16 pixel rows per MMA, M = the KP k values (64 per atom column, LBO = column distance); with one
       // atom column M rows 64..127 alias an in-bounds region and their results are never read
-      const uint32_t a_lo = ((smem_u32(sA + s * AB) & 0x3FFFFu) >> 4) | ((uint32_t)((p.NA > 1 ? F1_ATOM : 1024) >> 4) << 16);
+      const uint32_t a_lo = ((smem_u32(sA + s * AB) & 0x3FFFFu) >> 4) | ((uint32_t)((NA > 1 ? F1_ATOM : 1024) >> 4) << 16);
       const uint32_t g_lo = ((smem_u32(sG + s * GB) & 0x3FFFFu) >> 4) | ((16384u >> 4) << 16);
 #pragma unroll
       for (int kk = 0; kk < 8; kk++)
@@ -1363,42 +1411,47 @@ extern "C" int okl_conv_first_supported(okl_ctx* ctx, const okl_conv_desc* d) {
 }
 
 // y16 (N, *out, O) bf16 = act(conv(x (N, C, *in) fp32, W) + b); d->act NONE or RELU
-extern "C" int okl_conv_first_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* W, const void* bias, void* y16) {
+extern "C" int okl_conv_first_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* x_rows_i32, const void* W, const void* bias, void* y16) {
   OKL_REQUIRE(ctx && d && x && W && y16, "NULL argument");
   F1Params p;
   int opad;
   OKL_REQUIRE(f1_plan(ctx, d, p, opad), "okl_conv_first_fprop: unsupported shape / layout");
   OKL_REQUIRE(d->act == OKL_ACT_NONE || d->act == OKL_ACT_RELU, "okl_conv_first_fprop: only ReLU can be fused");
-  p.x = (const float*)x; p.W = (const float*)W; p.bias = (const float*)bias; p.relu = d->act == OKL_ACT_RELU;
+  p.x = (const float*)x; p.xrows = (const int*)x_rows_i32; p.W = (const float*)W; p.bias = (const float*)bias; p.relu = d->act == OKL_ACT_RELU;
   CUtensorMap ty;
   int s = ct_map_nhwc(&ty, y16, 2, p.O, p.OW, p.OH, p.N * p.OD, 64, p.TW, p.RH, 1);
   if (s != OKL_OK) return s;
   const int ptotal = p.C * p.KD * p.PH * p.PWp;
-  const int nt = (opad == 64 && ptotal <= F1_PRE * 128 && p.NA == 1) ? 128 : 256;
+  const int gen = (p.KS > 2 || p.KD > 1 || p.D > 1) ? 1 : 0;
+  const int nt = (opad == 64 && ptotal <= (gen ? 8 : 6) * 128 && p.NA == 1) ? 128 : 256;
   const int smem = p.NA * F1_ATOM + p.NA * opad * 128 + (nt / 32) * CT_STG + 64 + F1_KPMAX * 4 + ptotal * 4 + 1024;
   int per_sm = nt == 128 ? 5 : 2;
   if (per_sm * (smem + 1024) > 227 * 1024) per_sm = (227 * 1024) / (smem + 1024);
   if (per_sm < 1) per_sm = 1;
   const int grid = p.ntiles < per_sm * ctx->sm_count ? p.ntiles : per_sm * ctx->sm_count;
-#define F1_FP(OO, NT_)                                                                                                \
+#define F1_FP(OO, NT_, G_)                                                                                            \
   {                                                                                                                   \
     static int set = 0;                                                                                               \
-    if (set < smem) { OKL_CHECK_CUDA(cudaFuncSetAttribute(conv_first_fprop_kernel<OO, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); set = 160 * 1024; } \
-    okl_launch(ctx, conv_first_fprop_kernel<OO, NT_>, dim3(grid), dim3(NT_), smem, ty, p);                             \
+    if (set < smem) { OKL_CHECK_CUDA(cudaFuncSetAttribute(conv_first_fprop_kernel<OO, NT_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); set = 160 * 1024; } \
+    okl_launch(ctx, conv_first_fprop_kernel<OO, NT_, G_>, dim3(grid), dim3(NT_), smem, ty, p);                         \
   }
-  if (opad == 64 && nt == 128) F1_FP(64, 128) else if (opad == 64) F1_FP(64, 256) else if (opad == 128) F1_FP(128, 256) else F1_FP(256, 256)
+  if (gen) {
+    if (opad == 64 && nt == 128) F1_FP(64, 128, 1) else if (opad == 64) F1_FP(64, 256, 1) else if (opad == 128) F1_FP(128, 256, 1) else F1_FP(256, 256, 1)
+  } else {
+    if (opad == 64 && nt == 128) F1_FP(64, 128, 0) else if (opad == 64) F1_FP(64, 256, 0) else if (opad == 128) F1_FP(128, 256, 0) else F1_FP(256, 256, 0)
+  }
 #undef F1_FP
   OKL_LAUNCHED(ctx, "conv_first_fprop");
   return OKL_OK;
 }
 
 // dW (O, C, *k) fp32 and db (O) fp32 (optional) from x (N, C, *in) fp32 and g16 (N, *out, O) bf16
-extern "C" int okl_conv_first_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* g16, void* dW, void* db) {
+extern "C" int okl_conv_first_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* x_rows_i32, const void* g16, void* dW, void* db) {
   OKL_REQUIRE(ctx && d && x && g16 && dW, "NULL argument");
   F1Params p;
   int opad;
   OKL_REQUIRE(f1_plan(ctx, d, p, opad), "okl_conv_first_wgrad: unsupported shape / layout");
-  p.x = (const float*)x;
+  p.x = (const float*)x; p.xrows = (const int*)x_rows_i32;
   CUtensorMap tg;
   int s = ct_map_nhwc(&tg, g16, 2, p.O, p.OW, p.OH, p.N * p.OD, 64, p.TW, p.TH, 1);
   if (s != OKL_OK) return s;
@@ -1411,13 +1464,18 @@ extern "C" int okl_conv_first_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const 
   s = okl_ensure_workspace(ctx, (size_t)grid * KP * opad * sizeof(float));
   if (s != OKL_OK) return s;
   p.partial = (float*)ctx->workspace;
-#define F1_WG(OO)                                                                                                     \
+  const int gen = (p.KS > 2 || p.KD > 1 || p.D > 1) ? 1 : 0;
+#define F1_WG(OO, G_)                                                                                                 \
   {                                                                                                                   \
     static int set = 0;                                                                                               \
-    if (set < smem) { OKL_CHECK_CUDA(cudaFuncSetAttribute(conv_first_wgrad_kernel<OO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = 200 * 1024; } \
-    okl_launch(ctx, conv_first_wgrad_kernel<OO>, dim3(grid), dim3(F1_THREADS), smem, tg, p);                           \
+    if (set < smem) { OKL_CHECK_CUDA(cudaFuncSetAttribute(conv_first_wgrad_kernel<OO, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); set = 200 * 1024; } \
+    okl_launch(ctx, conv_first_wgrad_kernel<OO, G_>, dim3(grid), dim3(F1_THREADS), smem, tg, p);                       \
   }
-  if (opad == 64) F1_WG(64) else if (opad == 128) F1_WG(128) else F1_WG(256)
+  if (gen) {
+    if (opad == 64) F1_WG(64, 1) else if (opad == 128) F1_WG(128, 1) else F1_WG(256, 1)
+  } else {
+    if (opad == 64) F1_WG(64, 0) else if (opad == 128) F1_WG(128, 0) else F1_WG(256, 0)
+  }
 #undef F1_WG
   OKL_LAUNCHED(ctx, "conv_first_wgrad");
   const int total = (p.K + 1) * p.O;

@@ -156,7 +156,7 @@ static int ensure_pipeline(okl_ctx* ctx) {
 
 extern "C" int okl_batch_prefetch(okl_ctx* ctx, int slot, void* x_dst, const void* x_src, long long x_row_elems, void* t_dst,
                                   const void* t_src, long long t_row_elems, const void* idx, long long rows, void* x_nxc_dst, int x_channels,
-                                  int x_nxc_bf16) {
+                                  int x_nxc_bf16, void* idx_dst) {
   OKL_REQUIRE(ctx && (slot == 0 || slot == 1), "okl_batch_prefetch: slot must be 0 or 1");
   OKL_REQUIRE(!ctx->capturing && ctx->cur_lane == 0, "okl_batch_prefetch: not inside a capture / auxiliary lane");
   int s = ensure_pipeline(ctx);
@@ -171,13 +171,19 @@ extern "C" int okl_batch_prefetch(okl_ctx* ctx, int slot, void* x_dst, const voi
   OKL_CHECK_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_fork, 0));
   cudaStream_t main_stream = ctx->stream;
   ctx->stream = ctx->copy_stream;
+  // A channels-last first layer (tensor-core convolution): the (N, C, S) -> (N, S, C) permutation of the batch also happens here, on
+  // the copy stream, instead of at the head of the step's critical path.  As bf16 it is produced straight from the dataset rows
+  // (through the index) when no fp32 copy of the batch is wanted (x_dst NULL).
+  const bool nxc = x_nxc_dst && x_channels > 1 && rows > 0 && x_row_elems % x_channels == 0;
   s = okl_gather_batch(ctx, x_dst, x_src, x_row_elems, t_dst, t_src, t_row_elems, idx, rows);
-  // a channels-last first layer (tensor-core convolution): the (N, C, S) -> (N, S, C) permutation of the batch also happens here,
-  // on the copy stream, instead of at the head of the step's critical path
-  if (s == OKL_OK && x_nxc_dst && x_channels > 1 && rows > 0 && x_row_elems % x_channels == 0) {
-    if (x_nxc_bf16) s = okl_to_bf16_nxc(ctx, x_dst, x_nxc_dst, (int)rows, x_channels, x_row_elems / x_channels);
-    else s = okl_permute(ctx, x_nxc_dst, x_dst, (int)rows, x_channels, x_row_elems / x_channels, OKL_NCX);
+  if (s == OKL_OK && nxc) {
+    if (x_nxc_bf16) s = okl_to_bf16_nxc(ctx, x_dst ? x_dst : x_src, x_dst ? nullptr : idx, x_nxc_dst, (int)rows, x_channels, x_row_elems / x_channels);
+    else if (x_dst) s = okl_permute(ctx, x_nxc_dst, x_dst, (int)rows, x_channels, x_row_elems / x_channels, OKL_NCX);
+    else { okl_set_error("okl_batch_prefetch: the fp32 channels-last copy needs the gathered batch (x_dst)"); s = OKL_ERR_INVALID; }
   }
+  // consumers that read dataset rows through the index (okl_*_rows arguments) get the batch's index slice at a fixed per-slot address
+  if (s == OKL_OK && idx_dst && rows > 0)
+    s = cudaMemcpyAsync(idx_dst, idx, (size_t)rows * sizeof(int), cudaMemcpyDeviceToDevice, ctx->copy_stream) == cudaSuccess ? OKL_OK : OKL_ERR_CUDA;
   ctx->stream = main_stream;
   if (s != OKL_OK) return s;
   OKL_CHECK_CUDA(cudaEventRecord(ctx->ev_slot[slot], ctx->copy_stream));

@@ -1201,8 +1201,15 @@ extern "C" int okl_gather_rows(okl_ctx* ctx, void* dst, const void* src, const v
 
 extern "C" int okl_gather_batch(okl_ctx* ctx, void* x_dst, const void* x_src, long long x_row_elems, void* t_dst, const void* t_src,
                                 long long t_row_elems, const void* idx, long long rows) {
-  OKL_REQUIRE(ctx && (rows == 0 || (x_dst && x_src && t_dst && t_src && idx)), "NULL argument");
+  OKL_REQUIRE(ctx && (rows == 0 || idx), "NULL argument");
   if (rows <= 0) return OKL_OK;
+  // a part whose consumer reads the dataset rows through the index itself (okl_*_rows entry points) is not gathered: x_dst / t_dst NULL
+  if (!x_dst || !t_dst) {
+    if (x_dst) { OKL_REQUIRE(x_src, "NULL argument"); return okl_gather_rows(ctx, x_dst, x_src, idx, rows, x_row_elems); }
+    if (t_dst) { OKL_REQUIRE(t_src, "NULL argument"); return okl_gather_rows(ctx, t_dst, t_src, idx, rows, t_row_elems); }
+    return OKL_OK;
+  }
+  OKL_REQUIRE(x_src && t_src, "NULL argument");
   if (x_row_elems > 0 && t_row_elems > 0 && (x_row_elems & 3) == 0 && aligned16(x_dst) && aligned16(x_src)) {
     const size_t total = (size_t)rows * (x_row_elems / 4 + t_row_elems);
     // the gather runs NEXT TO the compute kernels of the previous step (copy stream): few, small blocks with many loads in flight

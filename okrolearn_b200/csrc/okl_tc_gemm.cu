@@ -80,6 +80,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
   uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+  volatile uint32_t* issue_par = reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 192);   // loop parameters of the MMA issuer
   float* stage_base = reinterpret_cast<float*>(smem + p.stages * Cfg::STAGE_BYTES + 256);   // 4 warps x 32 rows x 36 floats
 
   const int warp = threadIdx.x >> 5;
@@ -104,6 +105,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) {
     if (PAIR) tmem_alloc_cg2<Cfg::TMEM_COLS>(tmem_slot);
     else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
+  if (threadIdx.x == 96) {
+    issue_par[0] = (uint32_t)p.stages;
+    issue_par[1] = p.dbg ? 1u : 0u;
   }
   tc_fence_before();
   __syncthreads();
@@ -220,35 +225,43 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t a_lay = (A_MN && KIND == 0) ? 1 : 2, b_lay = (B_MN && KIND == 0) ? 1 : 2;
       constexpr uint32_t a_sbo = (A_MN && KIND == 0) ? 512 : 1024, b_sbo = (B_MN && KIND == 0) ? 512 : 1024;
       constexpr uint32_t a_adv = A_MN ? (Cfg::UMMA_K * 128) >> 4 : 32 >> 4, b_adv = B_MN ? (Cfg::UMMA_K * 128) >> 4 : 32 >> 4;
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      // lean issue loop (see umma_bf16_words in tc_ptx.cuh): descriptor low words by one multiply-add per k-block, the high words are
+      // compile-time constants, run-time loop parameters are read from shared memory once, no fence per k-block
+      constexpr uint32_t a_hi = (a_sbo >> 4) | (1u << 14) | (a_lay << 29), b_hi = (b_sbo >> 4) | (1u << 14) | (b_lay << 29);
+      constexpr uint32_t ST16 = Cfg::STAGE_BYTES >> 4;
+      const uint32_t a_lo0 = ((smem_u32(smem) & 0x3FFFFu) >> 4) | ((a_lbo >> 4) << 16);
+      const uint32_t b_lo0 = (((smem_u32(smem) + Cfg::A_BYTES) & 0x3FFFFu) >> 4) | ((b_lbo >> 4) << 16);
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
+      const uint32_t nstages = issue_par[0];
+      bool want_ts = issue_par[1] != 0;
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int w = wstart; w < total_work; w += wstep) {
         const int split = w / ((p.tiles_m / CS) * p.tiles_n);
         const int kb0 = split * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        mbar_wait_a(tempty0 + acc * 8, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t accum = 0;
+#pragma unroll 1
         for (int kb = kb0; kb < kb1; kb++) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          if (p.dbg && kb == kb0) p.dbg[blockIdx.x * 8 + 2] = gtime();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t adesc = make_smem_desc(sa, a_lbo, a_sbo, a_lay);
-          const uint64_t bdesc = make_smem_desc(sa + Cfg::A_BYTES, b_lbo, b_sbo, b_lay);
-#pragma unroll
-          for (int k = 0; k < Cfg::BK / Cfg::UMMA_K; k++) {
-            if (PAIR) umma_bf16_cg2(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma<KIND>(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          const uint32_t a_lo = a_lo0 + stage * ST16, b_lo = b_lo0 + stage * ST16;
+          mbar_wait_a(full0 + stage * 8, phase);
+          if (want_ts) {
+            p.dbg[blockIdx.x * 8 + 2] = gtime();
+            want_ts = false;
           }
-          if (PAIR) umma_commit_pair(&empty_bar[stage]);  // both CTAs' producers
-          else umma_commit(&empty_bar[stage]);            // smem stage reusable once these MMAs have read it
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / Cfg::UMMA_K; k++)
+            umma_words2<KIND, PAIR>(d_tmem, a_lo + (uint32_t)(k * a_adv), a_hi, b_lo + (uint32_t)(k * b_adv), b_hi, idesc, k ? 1u : accum);
+          accum = 1;
+          if (PAIR) umma_commit_pair_a(empty0 + stage * 8);  // both CTAs' producers
+          else umma_commit_a(empty0 + stage * 8);            // smem stage reusable once these MMAs have read it
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        if (PAIR) umma_commit_pair(&tfull_bar[acc]);
-        else umma_commit(&tfull_bar[acc]);                 // accumulator complete
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (PAIR) umma_commit_pair_a(tfull0 + acc * 8);
+        else umma_commit_a(tfull0 + acc * 8);                // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
     }
   } else if (warp >= 4) {

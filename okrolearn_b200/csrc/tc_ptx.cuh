@@ -174,6 +174,30 @@ __device__ __forceinline__ void umma_bf16_words(uint32_t d_tmem, uint32_t alo, u
         : "memory");
   }
 }
+// general form: operand-specific high words (swizzle mode / SBO may differ between A and B), tf32 or bf16, one CTA or a CTA pair
+template <int KIND, int PAIR>
+__device__ __forceinline__ void umma_words2(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t accumulate) {
+#define OKL_UMMA_W2(CG, KD)                                                                    \
+  asm volatile(                                                                                \
+      "{\n\t"                                                                                  \
+      ".reg .pred p;\n\t"                                                                      \
+      ".reg .b64 da, db;\n\t"                                                                  \
+      "mov.b64 da, {%1, %2};\n\t"                                                              \
+      "mov.b64 db, {%3, %4};\n\t"                                                              \
+      "setp.ne.b32 p, %6, 0;\n\t"                                                              \
+      "tcgen05.mma.cta_group::" CG ".kind::" KD " [%0], da, db, %5, p;\n\t"                     \
+      "}" ::"r"(d_tmem),                                                                       \
+      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)                       \
+      : "memory")
+  if (PAIR) {
+    if (KIND == 0) OKL_UMMA_W2("2", "tf32");
+    else OKL_UMMA_W2("2", "f16");
+  } else {
+    if (KIND == 0) OKL_UMMA_W2("1", "tf32");
+    else OKL_UMMA_W2("1", "f16");
+  }
+#undef OKL_UMMA_W2
+}
 // make the mbarrier track completion of all tcgen05 ops issued so far by this thread (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

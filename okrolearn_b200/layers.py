@@ -463,13 +463,22 @@ class _ConvBase(_ParamLayer):
             if xl == NXC and self.in_channels > 1 and self._nd == 3:
                 xl = NCX
             yl = getattr(self, "_out_layout", NCX)
+            if (yl == NCX and getattr(self, "_out_nxc_if_first", False) and xl == NCX and ctx.precision == _lib.BF16 and _BF16_ONLY and
+                    inputs.shape[0] > 0 and self._fused_act in (ACT_NONE, ACT_RELU) and not getattr(self, "_need_dx", True)):
+                # last parametric layer of a network (only activations and the loss follow): if the small-K tcgen05 kernels take the
+                # shape, the output is written channels-last bf16 and the loss consumes it in that format
+                dd, _ = self._desc(inputs.shape, NCX, NXC, self._fused_act)
+                if lib.okl_conv_first_supported(ctx.h, C.byref(dd)):
+                    yl = NXC
         d, oe = self._desc(inputs.shape, xl, yl, self._fused_act)
         oshape = (inputs.shape[0], self.out_channels) + oe
         self._first_tc = bool(ctx.precision == _lib.BF16 and _BF16_ONLY and xl == NCX and yl == NXC and inputs.shape[0] > 0 and
                               self._fused_act in (ACT_NONE, ACT_RELU) and lib.okl_conv_first_supported(ctx.h, C.byref(d)))
         if self._first_tc:                       # tiny-C first layer on tcgen05: fp32 images in, channels-last bf16 out
             out = Tensor._empty_b16(oshape, self._np_dtype, NXC)
-            check(lib.okl_conv_first_fprop(ctx.h, C.byref(d), inputs._dptr(NCX), self._bucket.ptr(0), self._bucket.ptr(1), out._bf16.ptr))
+            xr = inputs._rows_pending()                   # gather-free batch: the kernel reads the dataset rows through the index
+            xp, xi = xr if xr is not None else (inputs._dptr(NCX), None)
+            check(lib.okl_conv_first_fprop(ctx.h, C.byref(d), xp, xi, self._bucket.ptr(0), self._bucket.ptr(1), out._bf16.ptr))
             self._fwd_layouts, self._bf16_path, self._conv2 = (xl, yl), False, False
             return out
         self._bf16_path = bool(ctx.precision == _lib.BF16 and xl == NXC and yl == NXC and inputs.shape[0] > 0 and
@@ -507,7 +516,9 @@ class _ConvBase(_ParamLayer):
         b = self._bucket
         need_dx = getattr(self, "_need_dx", True)
         if getattr(self, "_first_tc", False) and ctx.precision == _lib.BF16 and not need_dx:
-            check(lib.okl_conv_first_wgrad(ctx.h, C.byref(d), x._dptr(NCX), dL_dout._b16(NXC), b.grad_ptr(0), b.grad_ptr(1)))
+            xr = x._rows_pending()
+            xp, xi = xr if xr is not None else (x._dptr(NCX), None)
+            check(lib.okl_conv_first_wgrad(ctx.h, C.byref(d), xp, xi, dL_dout._b16(NXC), b.grad_ptr(0), b.grad_ptr(1)))
             b.step(lr, self._defer_update)
             return None
         aux = self._aux_lane and self._defer_update and need_dx

@@ -204,7 +204,9 @@ class MSELoss:
             N_, C_ = outputs.shape[0], outputs.shape[1]
             S_ = n // (N_ * C_)
             grad = Tensor._empty_b16(outputs.shape, np.float64, _lib.NXC)
-            check(lib.okl_mse_fwd_bwd_nxc_bf16(ctx.h, outputs._bf16.ptr, targets._dptr(NCX), loss.ptr, grad._bf16.ptr, N_, C_, S_,
+            tr = targets._rows_pending() if isinstance(targets, Tensor) else None     # gather-free batch: dataset rows through the index
+            tp, ti = tr if tr is not None else (targets._dptr(NCX), None)
+            check(lib.okl_mse_fwd_bwd_nxc_bf16(ctx.h, outputs._bf16.ptr, tp, ti, loss.ptr, grad._bf16.ptr, N_, C_, S_,
                                                float(n * ctx.nranks), self._loss_accum, 1 if fuse else 0))
         elif (outputs.ndim >= 3 and outputs._dev_valid and outputs._layout == _lib.NXC and outputs.shape[1] > 1 and
                 outputs.shape[0] <= 65535 and getattr(outputs, "_lazy_fn", None) is None):

@@ -46,6 +46,7 @@ class _Slot:
         self.xin = Tensor._empty((batch_size,) + tuple(sample_shape), np.float32)
         self.xbuf = self.xin._buf                  # the slot's own storage (layers only ever see views of it)
         self.tin = _DevBuf(ctx, max(batch_size * t_row, 1) * 4)
+        self.idx = _DevBuf(ctx, max(batch_size, 1) * 4)   # the batch's slice of the epoch permutation (gather-free consumers)
         self.graph = None
 
 
@@ -243,6 +244,8 @@ class NeuralNetwork:
         for i, l in enumerate(ls):
             if isinstance(l, _ConvBase):
                 l._out_layout = NCX
+                # a small-K convolution that ends the network (e.g. the Conv3D video block): candidate for the first-layer tcgen05 kernels
+                l._out_nxc_if_first = bool(tc_mode and all(isinstance(n, _Activation) for n in ls[i + 1:]) and not l._tc_eligible())
                 if tc_mode:
                     for nxt in ls[i + 1:]:
                         if isinstance(nxt, (_Activation, _Pool)):
@@ -511,6 +514,25 @@ class NeuralNetwork:
         if idx_dev is None or idx_dev.nbytes < max(num_samples, 1) * 4:
             idx_dev = self._idx_dev = _DevBuf(ctx, max(int(num_samples * 1.5), 1024) * 4)
 
+        # ---- gather-free batches (device-resident dataset, BF16 convolution stacks): a consumer that can address dataset rows through
+        # the batch's index slice reads them in place - the batch is never copied.  Decided per part: x for a first layer on the
+        # small-K tcgen05 kernels (or converted to bf16 channels-last by the prefetch, straight from the dataset), targets for MSELoss
+        # on bf16 channels-last outputs.  A consumer that turns out not to be index-aware gathers the rows on first use (Tensor._row_view).
+        self._plan(fast)
+        first = self.layers[0] if self.layers else None
+        bf16_stack = bool(ctx.precision == _lib.BF16 and _layers_mod._BF16_ONLY and self.prefetch_batches and not stream and
+                          os.environ.get("OKL_ROW_VIEWS", "1") != "0" and isinstance(first, _ConvBase) and batch_size <= 65535)
+        x_rows = t_rows = False
+        if bf16_stack and fast and not first._tc_eligible() and not getattr(first, "_need_dx", True) and first._fused_pool is None and \
+                (getattr(first, "_out_layout", NCX) == _lib.NXC or getattr(first, "_out_nxc_if_first", False)) and len(sample_shape) == first._nd + 1:
+            dd, _ = first._desc((batch_size,) + sample_shape, NCX, _lib.NXC)
+            x_rows = bool(lib.okl_conv_first_supported(ctx.h, C.byref(dd)))
+        if bf16_stack and fast and isinstance(loss_function, MSELoss) and len(t_shape) >= 2 and t_shape[0] % 8 == 0:
+            last = next((l for l in reversed(self.layers) if isinstance(l, _ParamLayer)), None)
+            t_rows = bool(isinstance(last, _ConvBase) and (x_rows or last._tc_eligible()) and
+                          all(isinstance(l, _Activation) for l in self.layers[self.layers.index(last) + 1:]))
+        rows_key = (x_src if (x_rows or bf16_stack) else 0, t_src if t_rows else 0)     # captured steps reference the dataset itself
+
         # ---- per-(batch shape, loss) step state: static input buffers + the captured graph
         # the stock losses are stateless: a fresh CrossEntropyLoss() / MSELoss() per train() call (the usual way to call it) reuses
         # the captured step instead of capturing - and keeping alive - a new set of graphs and activation buffers every time
@@ -518,7 +540,8 @@ class NeuralNetwork:
         skey = (batch_size, sample_shape, t_shape, loss_key, tuple(id(l) for l in self.layers), fast,
                 self.fuse_activations, self.skip_input_grad, ctx.precision, bool(self.prefetch_batches), self.fuse_head,
                 self.fuse_conv_pool, self.use_aux_lanes, self.early_exchange, ctx.nranks,
-                float(self.temperature))         # 1/temperature is baked into the captured step by value
+                float(self.temperature),         # 1/temperature is baked into the captured step by value
+                x_rows, t_rows, rows_key)
         st = self._graphs.pop(skey, None)
         if st is None:
             st = _StepState(ctx, batch_size, sample_shape, t_row)
@@ -534,16 +557,17 @@ class NeuralNetwork:
         if not custom_loss:
             loss_function._loss_accum = st.eloss.ptr
 
-        def make_targets(rows, slot):
+        def make_targets(rows, slot, pipelined=False):
             if is_ce:
                 t = Tensor(np.zeros((0,)), requires_grad=False)
                 t._shape = (rows,) + t_shape
                 t._i32_dev = slot.tin.ptr
                 return t
+            if t_rows and pipelined:
+                return Tensor._row_view(t_src, slot.idx.ptr, (rows,) + t_shape, np.float32, slot.tin)
             return Tensor._view(slot.tin, 0, (rows,) + t_shape, np.float32, bound=False)
 
         # a first layer that runs channels-last on the tensor cores gets its batch in that layout straight from the prefetch
-        first = self.layers[0] if self.layers else None
         x_nxc = bool(self.prefetch_batches and ctx.precision != _lib.FP32 and isinstance(first, _ConvBase) and first._tc_eligible() and
                      getattr(first, "_fused_pool", None) is None and len(sample_shape) >= 2 and sample_shape[0] > 1 and _numel(sample_shape[1:]) > 1)
         # BF16 mode: that copy is written as bf16 (permutation + conversion in one pass on the copy stream) - the operand format of the
@@ -560,9 +584,10 @@ class NeuralNetwork:
             b0 = batch * batch_size
             rows = min(b0 + batch_size, num_samples) - b0
             sl = st.slots[batch & 1]
-            check(lib.okl_batch_prefetch(ctx.h, batch & 1, sl.xbuf.ptr, x_src, row_elems, sl.tin.ptr, t_src, t_row,
-                                         idx_dev.ptr + b0 * 4, rows, sl.xnxc.ptr if x_nxc else None, sample_shape[0] if x_nxc else 0,
-                                         1 if x_b16 else 0))
+            x_skip = x_rows or (x_b16 and bf16_stack)     # bf16 channels-last batch converted straight from the dataset rows
+            check(lib.okl_batch_prefetch(ctx.h, batch & 1, None if x_skip else sl.xbuf.ptr, x_src, row_elems, None if t_rows else sl.tin.ptr, t_src,
+                                         t_row, idx_dev.ptr + b0 * 4, rows, sl.xnxc.ptr if x_nxc else None, sample_shape[0] if x_nxc else 0,
+                                         1 if x_b16 else 0, sl.idx.ptr if (x_rows or t_rows) else None))
 
         lossf = C.c_float()
 
@@ -625,7 +650,9 @@ class NeuralNetwork:
                 else:
                     # a fresh view per step: a layer may re-lay-out ITS input tensor (channels-last for the tensor-core convs),
                     # which must never redirect or relabel the slot's own buffer - the gather keeps writing NC.. rows there
-                    if x_b16 and pipelined:
+                    if x_rows and pipelined:
+                        bx = Tensor._row_view(x_src, sl.idx.ptr, (rows,) + sample_shape, np.float32, sl.xbuf)
+                    elif x_b16 and pipelined:
                         bx = Tensor._view(None, 0, (rows,) + sample_shape, np.float32, bound=False)
                         bx._layout, bx._b16_primary, bx._bf16, bx._f32_stamp = _lib.NXC, True, sl.xnxc, None
                         bx._bf16_ver = (bx._dev_ver, _lib.NXC)
@@ -634,7 +661,7 @@ class NeuralNetwork:
                         bx._layout = _lib.NXC
                     else:
                         bx = Tensor._view(sl.xbuf, 0, (rows,) + sample_shape, np.float32, bound=False)
-                    bt = make_targets(rows, sl)
+                    bt = make_targets(rows, sl, pipelined)
                     if graph_ok and full and st.warm:
                         keep = []
                         ctx._capture_keep = keep

@@ -155,6 +155,29 @@ class Tensor:
         t.backward_fn = None
         return t
 
+    # ------------------------------------------------------------------ indexed row views (gather-free batches)
+    _rows = None                    # (dataset pointer, int32 row-index pointer): this tensor IS rows idx[0..N) of that dataset
+
+    @classmethod
+    def _row_view(cls, src_ptr, idx_ptr, shape, np_dtype, buf):
+        """The batch of a shuffled epoch WITHOUT a gathered copy: consumers that address dataset rows through the index themselves
+        (first-layer convolution, fp32 -> bf16 conversion, MSE: the ``*_rows_i32`` arguments of the C ABI) read ``_rows``; any other
+        consumer asks for ``_dptr()`` / ``.data`` and the rows are gathered into ``buf`` then (once)."""
+        t = cls._view(buf, 0, shape, np_dtype, bound=False)
+        t._rows = (int(src_ptr), int(idx_ptr))
+
+        def gather(tt):
+            rows = tt._shape[0]
+            if rows:
+                check(lib.okl_gather_rows(get_ctx().h, tt._buf.ptr + tt._off, tt._rows[0], tt._rows[1], rows, tt.size // rows))
+            tt._touch()
+        t._lazy_fn = gather
+        return t
+
+    def _rows_pending(self):
+        """(dataset pointer, index pointer) while the rows have not been gathered, else None."""
+        return self._rows if (self._rows is not None and getattr(self, "_lazy_fn", None) is not None) else None
+
     # ------------------------------------------------------------------ bf16-primary tensors
     _b16_primary = False            # True: the channels-last bf16 buffer is the storage of record, fp32 is converted on demand
 
@@ -368,7 +391,7 @@ class Tensor:
                 if getattr(self, "_bf16", None) is None or self._bf16.nbytes < self.size * 2:
                     self._bf16, self._bf16_ver = _DevBuf(ctx, max(self.size, 1) * 2), None
                 if self._bf16_ver != (self._dev_ver, "nxc-of-ncx"):
-                    check(lib.okl_to_bf16_nxc(ctx.h, src, self._bf16.ptr, self._shape[0], self._shape[1], _numel(self._shape[2:])))
+                    check(lib.okl_to_bf16_nxc(ctx.h, src, None, self._bf16.ptr, self._shape[0], self._shape[1], _numel(self._shape[2:])))
                     self._bf16_ver = (self._dev_ver, "nxc-of-ncx")
                 return self._bf16.ptr
         src = self._dptr(layout)

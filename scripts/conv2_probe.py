@@ -236,34 +236,40 @@ def misc():
 
 
 def first():
-    for (N, Cc, H, W, Oc, k, pd) in ((8, 3, 32, 32, 64, 3, 1), (3, 3, 30, 27, 128, 3, 1), (2, 1, 28, 28, 64, 5, 0), (4, 3, 16, 16, 256, 3, 1)):
-        rng = np.random.default_rng(N + Oc)
-        x = rng.standard_normal((N, Cc, H, W)).astype(np.float32)
-        Wt = (rng.standard_normal((Oc, Cc, k, k)) * 0.2).astype(np.float32)
+    cases = [((8, 3, 32, 32), 64, 3, 1), ((3, 3, 30, 27), 128, 3, 1), ((2, 1, 28, 28), 64, 5, 0), ((4, 3, 16, 16), 256, 3, 1),
+             ((2, 3, 4, 10, 12), 64, 3, 1), ((1, 3, 5, 40, 36), 64, 3, 1), ((2, 2, 6, 9, 16), 128, (3, 3, 3), (0, 1, 1)), ((1, 3, 3, 112, 112), 64, 3, 1),
+             ((2, 4, 20, 24), 64, 5, 2)]
+    for (xs, Oc, k, pd) in cases:
+        nd = len(xs) - 2
+        N, Cc = xs[0], xs[1]
+        rng = np.random.default_rng(N + Oc + nd)
+        kt, pt = O._tup(k, nd), O._tup(pd, nd)
+        x = rng.standard_normal(xs).astype(np.float32)
+        Wt = (rng.standard_normal((Oc, Cc) + kt) * 0.2).astype(np.float32)
         b = (rng.standard_normal((Oc, 1)) * 0.1).astype(np.float32)
         d = _lib.ConvDesc()
-        d.nd, d.N, d.C, d.O = 2, N, Cc, Oc
-        for i, e in enumerate((H, W)):
-            d.inp[i], d.k[i], d.s[i], d.p[i] = e, k, 1, pd
+        d.nd, d.N, d.C, d.O = nd, N, Cc, Oc
+        for i in range(nd):
+            d.inp[i], d.k[i], d.s[i], d.p[i] = xs[2 + i], kt[i], 1, pt[i]
         d.act, d.x_layout, d.y_layout = 1, _lib.NCX, _lib.NXC
         if not lib.okl_conv_first_supported(ctx.h, C.byref(d)):
-            print("first-layer kernel unsupported for", N, Cc, H, W, Oc, k, pd)
+            print("first-layer kernel unsupported for", xs, Oc, k, pd)
             continue
         tx, tW, tb = okl.Tensor(x), okl.Tensor(Wt), okl.Tensor(b.reshape(-1))
         xr, Wr, br = bf16_round(x).astype(np.float64), bf16_round(Wt).astype(np.float64), bf16_round(b).astype(np.float64)
         yo = np.maximum(O.conv_forward_fast(xr, Wr, br, 1, pd, dtype=np.float64), 0)
         y16 = _DevBuf(ctx, yo.size * 2)
-        check(lib.okl_conv_first_fprop(ctx.h, C.byref(d), tx._dptr(), tW._dptr(), tb._dptr(), y16.ptr))
+        check(lib.okl_conv_first_fprop(ctx.h, C.byref(d), tx._dptr(), None, tW._dptr(), tb._dptr(), y16.ptr))
         e1 = rel(fetch16(y16.ptr, (N,) + yo.shape[2:] + (Oc,)), yo)
         g = bf16_round(rng.standard_normal(yo.shape).astype(np.float32))
         tg = okl.Tensor(g)
         dWo, dbo, _ = O.conv_backward_fast(xr, Wr, g.astype(np.float64), 1, pd)
         dW, db = okl.Tensor._empty(Wt.shape, np.float32), okl.Tensor._empty((Oc,), np.float32)
         d.act = 0
-        check(lib.okl_conv_first_wgrad(ctx.h, C.byref(d), tx._dptr(), tg._b16(_lib.NXC), dW._ptr_raw(), db._ptr_raw()))
+        check(lib.okl_conv_first_wgrad(ctx.h, C.byref(d), tx._dptr(), None, tg._b16(_lib.NXC), dW._ptr_raw(), db._ptr_raw()))
         dW._touch(); db._touch()
         e2, e3 = rel(dW.data, dWo), rel(db.data, dbo.reshape(-1))
-        print(("ok  " if e1 < 1e-2 and e2 < 2e-3 and e3 < 2e-3 else "BAD ") + f"first layer N={N} C={Cc} {H}x{W} O={Oc} k={k} p={pd}: fprop {e1:.2e} dW {e2:.2e} db {e3:.2e}", flush=True)
+        print(("ok  " if e1 < 1e-2 and e2 < 2e-3 and e3 < 2e-3 else "BAD ") + f"first layer x={xs} O={Oc} k={k} p={pd}: fprop {e1:.2e} dW {e2:.2e} db {e3:.2e}", flush=True)
     # timing at the bench shape
     N = int(os.environ.get("PROBE_BATCH", "1024"))
     d = _lib.ConvDesc()
@@ -276,9 +282,24 @@ def first():
     y16, g16 = _DevBuf(ctx, N * 64 * 1024 * 2), _DevBuf(ctx, N * 64 * 1024 * 2)
     check(lib.okl_memset(ctx.h, g16.ptr, 0x3c, g16.nbytes))
     dW, db = _DevBuf(ctx, 64 * 27 * 4), _DevBuf(ctx, 256)
-    t1 = timeit(lambda: check(lib.okl_conv_first_fprop(ctx.h, C.byref(d), x._dptr(), Wt._dptr(), bb._dptr(), y16.ptr)))
-    t2 = timeit(lambda: check(lib.okl_conv_first_wgrad(ctx.h, C.byref(d), x._dptr(), g16.ptr, dW.ptr, db.ptr)))
+    t1 = timeit(lambda: check(lib.okl_conv_first_fprop(ctx.h, C.byref(d), x._dptr(), None, Wt._dptr(), bb._dptr(), y16.ptr)))
+    t2 = timeit(lambda: check(lib.okl_conv_first_wgrad(ctx.h, C.byref(d), x._dptr(), None, g16.ptr, dW.ptr, db.ptr)))
     print(f"first layer 3->64@32 batch {N}: fprop {t1:.1f} us ({N * 65536 * 2 / t1 / 1e3:.0f} GB/s written), wgrad+db {t2:.1f} us ({N * 65536 * 2 / t2 / 1e3:.0f} GB/s read)")
+    # the video layer of BASELINE configs[3]: Conv3D(3, 64, 3, 1, 1) on 8 x 3 x 16 x 112 x 112
+    d = _lib.ConvDesc()
+    d.nd, d.N, d.C, d.O = 3, 8, 3, 64
+    for i, e in enumerate((16, 112, 112)):
+        d.inp[i], d.k[i], d.s[i], d.p[i] = e, 3, 1, 1
+    d.act, d.x_layout, d.y_layout = 1, _lib.NCX, _lib.NXC
+    x = okl.Tensor(np.random.default_rng(0).standard_normal((8, 3, 16, 112, 112), dtype=np.float32))
+    Wt, bb = okl.Tensor(np.ones((64, 3, 3, 3, 3), dtype=np.float32)), okl.Tensor(np.zeros(64, dtype=np.float32))
+    nout = 8 * 16 * 112 * 112 * 64
+    y16, g16 = _DevBuf(ctx, nout * 2), _DevBuf(ctx, nout * 2)
+    check(lib.okl_memset(ctx.h, g16.ptr, 0x3c, g16.nbytes))
+    dW, db = _DevBuf(ctx, 64 * 81 * 4), _DevBuf(ctx, 256)
+    t1 = timeit(lambda: check(lib.okl_conv_first_fprop(ctx.h, C.byref(d), x._dptr(), None, Wt._dptr(), bb._dptr(), y16.ptr)))
+    t2 = timeit(lambda: check(lib.okl_conv_first_wgrad(ctx.h, C.byref(d), x._dptr(), None, g16.ptr, dW.ptr, db.ptr)))
+    print(f"video layer 3->64 k3 @16x112x112 batch 8: fprop {t1:.1f} us ({nout * 2 / t1 / 1e3:.0f} GB/s written), wgrad+db {t2:.1f} us ({nout * 2 / t2 / 1e3:.0f} GB/s read)")
 
 
 if "first" in what:
