@@ -925,12 +925,369 @@ int wg_launch(okl_ctx* ctx, const CUtensorMap& tx, const CUtensorMap& tg, const 
   return OKL_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ weight gradient, taps stacked along N
+// The kernel above issues one 128 x 64 (or 128) x 16 MMA per (M tile, vertical tap): at N = 64 an MMA fetches (128 + 64) x 32 B of
+// operands for 32 cycles of tensor work - 192 B/cycle against the SM's 128 B/cycle of shared memory - and a quarter of the M rows of
+// the 64-channel layers is the ones slot: 43 % of the tensor peak measured, 50 % possible.  Here the vertical taps move to the OTHER
+// operand.  With h' = h + u - ph (an INPUT row):
+//     dW[o][c][u][v] = sum_{n,h',w} x[n, h', w + v - pw, c] * g[n, h' - u + ph, w, o]
+// so a k-block is a tile of 128 (or 64) input pixels: A = one plain x box per (v, 64-channel chunk) (M = 128 = two chunk slots), and
+// B = ONE gradient slab of TH + KH - 1 rows whose KH row-shifted views are the KH 64-column groups of a single N = 64 KH operand: the
+// leading-dimension offset of the MN-major descriptor (the distance between 64-element groups along N) is simply one slab row.  One
+// 128 x 192 x 16 MMA replaces three 128 x 64 x 16 ones: (128 + 192) x 32 B per 96 cycles = 107 B/cycle.  TMA's zero fill supplies the
+// gradient rows outside the image.  Column group j of an accumulator is tap u = KH - 1 - j.  A CTA owns MT M tiles x NO 64-channel
+// output chunks (MT x NO <= 2 accumulators of 256 TMEM columns); split-K over the SMs, fixed-order second stage as before.  A free
+// chunk slot reads the all-ones region: row 64 of that accumulator, column group u = ph, is the bias gradient.
+constexpr int GS_THREADS = 256;        // warp 0: TMA producer, 1: MMA issuer, 2: TMEM allocator, 4-7: epilogue
+constexpr int GS_MAXST = 6;
+
+struct GsParams {
+  int tiles_mt, tiles_n, splits, ktiles;
+  int tiles_w, tiles_h;
+  int PT, TW, TH, TN, tw_sh, pimg_sh;  // k-block = TW x TH pixels of TN images = PT (64 or 128)
+  int KH, KW, cpc, nchunks;            // cpc = C / 64; nchunks = KW * cpc real (v, channel chunk) slots
+  int MT, NO;                          // per CTA: M tiles (two chunk slots each), 64-channel output chunks
+  int ph, pw;
+  int xbox_bytes, gslab_bytes, row_bytes, gimg_bytes;
+  int stages, stage_bytes, nreal_max;
+  int has_db, ones_bytes;
+  int epi_bufs;                        // staging images that fit the operand stages (1 or 2)
+  int diag;                            // probe only (OKL_WG_DIAG): 1 = every MMA issued twice, 2 = operands loaded once per stage slot
+  float* ws;                           // [split][tile][MT * NO][128][64 KH]
+};
+
+__global__ void __launch_bounds__(GS_THREADS, 1)
+conv_wgrad_gs_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const GsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sSt = smem;
+  uint8_t* sOnes = sSt + p.stages * p.stage_bytes;          // after the stages: "ones - box" is a positive leading-dimension offset
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + p.ones_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + GS_MAXST;
+  uint64_t* done = bars + 2 * GS_MAXST;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GS_MAXST + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmG);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  for (int i = threadIdx.x; i < p.ones_bytes / 16; i += GS_THREADS)
+    reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  okl_pdl_sync();
+
+  const int tile = blockIdx.x / p.splits, split = blockIdx.x - tile * p.splits;
+  const int tmt = tile / p.tiles_n, tn = tile - tmt * p.tiles_n;
+  const int q0 = tmt * p.MT * 2;                           // first chunk slot (flattened (v, channel chunk)) of this CTA
+  int nreal = p.nchunks - q0;
+  if (nreal > p.MT * 2) nreal = p.MT * 2;
+  const int nslots = nreal + ((p.has_db && q0 + nreal == p.nchunks && nreal < p.MT * 2) ? 1 : 0);      // + the ones slot
+  const int nt = (nslots + 1) >> 1;                        // M tiles with anything in them
+  const int NC = p.KH * 64;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t tx_bytes = (uint32_t)(nreal * p.xbox_bytes + p.NO * p.gslab_bytes);
+      int st = 0;
+      uint32_t ph_ = 0;
+      for (int kt = split; kt < ((p.diag & 4) ? 0 : p.ktiles); kt += p.splits) {
+        const int wt = kt % p.tiles_w, r2 = kt / p.tiles_w;
+        const int ht = r2 % p.tiles_h, ng = r2 / p.tiles_h;
+        const int w0 = wt * p.TW, h0 = ht * p.TH, n0 = ng * p.TN;
+        mbar_wait(&empty[st], ph_ ^ 1);
+        if ((p.diag & 2) && kt >= split + p.stages * p.splits) {
+          mbar_arrive(&full[st]);
+          if (++st == p.stages) { st = 0; ph_ ^= 1; }
+          continue;
+        }
+        mbar_expect_tx(&full[st], tx_bytes);
+        uint8_t* base = sSt + st * p.stage_bytes;
+        for (int j = 0; j < nreal; j++) {
+          const int q = q0 + j, v = q / p.cpc, cc = q - v * p.cpc;
+          tma_load_4d(&tmX, &full[st], base + j * p.xbox_bytes, cc * 64, w0 + v - p.pw, h0, n0);
+        }
+        uint8_t* gb = base + p.nreal_max * p.xbox_bytes;
+        for (int j = 0; j < p.NO; j++)
+          tma_load_4d(&tmG, &full[st], gb + j * p.gslab_bytes, (tn * p.NO + j) * 64, w0, h0 + p.ph - (p.KH - 1), n0);
+        if (++st == p.stages) { st = 0; ph_ ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(1, true, true, 128, (p.diag & 32) ? 64 : NC);
+      constexpr uint32_t HI = TC_DESC_HI_SW128;
+      const uint32_t ones16 = (smem_u32(sOnes) & 0x3FFFFu) >> 4;
+      const uint32_t st0_16 = (smem_u32(sSt) & 0x3FFFFu) >> 4, stage16 = (uint32_t)p.stage_bytes >> 4, xbox16 = (uint32_t)p.xbox_bytes >> 4;
+      const uint32_t g0_16 = (uint32_t)(p.nreal_max * p.xbox_bytes) >> 4, gslab16 = (uint32_t)p.gslab_bytes >> 4;
+      const uint32_t row_lbo = ((uint32_t)p.row_bytes >> 4) << 16;
+      const int nk = p.PT >> 4, NO = p.NO;
+      uint32_t goff16[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; kk++) {
+        const int pix = kk * 16;
+        const int img = pix >> p.pimg_sh, pin = pix & ((1 << p.pimg_sh) - 1);
+        goff16[kk] = (uint32_t)(img * p.gimg_bytes + (pin >> p.tw_sh) * p.row_bytes + (pin & (p.TW - 1)) * 128) >> 4;
+      }
+      // M tile t = chunk slots 2t, 2t + 1: two x boxes (LBO = box size), or a box + the ones region (LBO depends on the stage), or a box
+      // alone (its second 64 rows repeat the first and are never read back)
+      int kind[2];
+#pragma unroll
+      for (int t = 0; t < 2; t++) kind[t] = 2 * t + 1 < nreal ? 0 : (2 * t + 1 < nslots ? 1 : 2);
+      const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+      uint32_t st = 0, ph_ = 0, accum = 0;
+#pragma unroll 1
+      for (int rep = 0; rep < ((p.diag & 256) ? 2 : 1); rep++)
+#pragma unroll 1
+      for (int kt = split; kt < p.ktiles; kt += p.splits) {
+        const uint32_t base16 = st0_16 + st * stage16;
+        uint32_t alo[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+          const uint32_t a0 = base16 + (uint32_t)(2 * t) * xbox16;
+          alo[t] = a0 | ((kind[t] == 0 ? xbox16 : kind[t] == 1 ? ones16 - a0 : 0u) << 16);
+          if (p.diag & 64) alo[t] = a0;
+        }
+        const uint32_t glo = (base16 + g0_16) | row_lbo;
+        if (!(p.diag & 4)) mbar_wait_a(full0 + st * 8, ph_);
+        tc_fence_after();
+        const uint32_t dmul = (p.diag & 8) ? 0u : 256u;
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {
+          if (kk < nk) {
+            const uint32_t ak = (uint32_t)kk * (2048u >> 4), gk = goff16[kk];
+#pragma unroll
+            for (int t = 0; t < 2; t++)
+#pragma unroll
+              for (int j = 0; j < 2; j++)
+                if (t < nt && j < NO) {
+                  umma_bf16_words<0>(tmem_base + (uint32_t)(t * NO + j) * dmul, alo[t] + ak, glo + (uint32_t)j * gslab16 + gk, HI, idesc, accum);
+                  if (p.diag & 1)
+                    umma_bf16_words<0>(tmem_base + (uint32_t)(t * NO + j) * dmul, alo[t] + ak, glo + (uint32_t)j * gslab16 + gk, HI, idesc, 1u);
+                }
+            accum = 1;
+          }
+        }
+        umma_commit_a(empty0 + st * 8);
+        if (++st == (uint32_t)p.stages) { st = 0; ph_ ^= 1; }
+      }
+      umma_commit(done);
+    }
+  }
+  // ===================================================================== epilogue (all eight warps): accumulators -> fp32 partials
+  // Partials of a unit are one 128 x 64 KH fp32 image, contiguous in the workspace.  Scattered 16-byte stores straight from the TMEM
+  // registers cost 12.6 us per CTA (probe); instead the image is staged in the (now idle) operand stages - segment (32-column chunk c,
+  // row r) at ((c * 128 + r) * 128 B, its 16-byte pieces XOR-swizzled with the row so that a warp's stores hit all banks - and leaves
+  // with ONE bulk copy per unit.  The second-stage kernel reads the same swizzled image.
+  __syncwarp();
+  {
+    const int q = warp & 3, par = warp >> 2;               // TMEM lane quarter; chunks of parity par
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const int nunits = p.MT * p.NO, nch = NC >> 5;
+    const uint32_t unit_bytes = (uint32_t)(128 * NC * 4);
+    float* dst0 = p.ws + (((size_t)split * (p.tiles_mt * p.tiles_n) + tile) * nunits) * (size_t)(128 * NC);
+    const int r = q * 32 + lane;
+    const int nu = (p.diag & 128) ? 0 : nt * p.NO;
+    for (int a = 0; a < nu; a++) {
+      uint8_t* img = sSt + (size_t)(a & (p.epi_bufs - 1)) * unit_bytes;
+      if (a >= p.epi_bufs) {                               // single staging buffer: the previous unit's copy must have read it
+        if (threadIdx.x == 0) tma_store_wait_read<0>();
+        __syncthreads();
+      }
+#pragma unroll 1
+      for (int c = par; c < nch; c += 2) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 256 + c * 32), v);
+        tmem_ld_wait();
+        uint4* seg = reinterpret_cast<uint4*>(img + ((size_t)(c * 128 + r) << 7));
+#pragma unroll
+        for (int j = 0; j < 8; j++) seg[j ^ (r & 7)] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      fence_proxy_async();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst0 + (size_t)a * 128 * NC), "r"(smem_u32(img)), "r"(unit_bytes)
+                     : "memory");
+        tma_store_commit();
+      }
+    }
+    if (threadIdx.x == 0) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// Second stage: dW[o][c][u][v] = sum over splits, in fixed order, of the partial images; db[o] from the ones slot (column group u = ph).
+// A warp owns one 128-byte segment (tile, unit, row, 32-column chunk) and every G-th split of it (coalesced loads, all in flight); the G
+// warps of a segment sit in one block, the first adds their sums in order and scatters into the reference's (O, C, KH, KW) layout.
+__global__ void __launch_bounds__(256) conv_wgrad_gs_reduce(const float* __restrict__ ws, float* __restrict__ dW, float* __restrict__ db, int O, int C,
+                                                            int KH, int KW, int cpc, int nchunks, int MT, int NO, int tiles_mt, int tiles_n,
+                                                            int splits, int ph, int G, int nseg) {
+  __shared__ float part[8][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NC = KH * 64, nch = NC >> 5, nunits = MT * NO;
+  const int g = warp & (G - 1);
+  int b = blockIdx.x * (8 / G) + warp / G;
+  const bool in_range = b < nseg;
+  if (!in_range) b = 0;
+  const int c = b % nch; b /= nch;
+  const int row = b & 127; b >>= 7;
+  const int unit = b % nunits, tile = b / nunits;
+  const int tmt = tile / tiles_n, tn = tile - tmt * tiles_n;
+  const int t = unit / NO, jo = unit - t * NO;
+  const int q = tmt * 2 * MT + 2 * t + (row >> 6), m64 = row & 63;      // chunk slot of this row
+  const bool is_db = db && q == nchunks && m64 == 0;
+  const bool live = in_range && (q < nchunks || is_db);
+  float sum = 0.f;
+  if (live) {
+    const size_t stride = (size_t)(tiles_mt * tiles_n) * nunits * 128 * NC;
+    const float* src = ws + ((size_t)tile * nunits + unit) * 128 * NC + ((size_t)(c * 128 + row) << 5) + ((((lane >> 2) ^ (row & 7)) << 2) | (lane & 3));
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = g;
+    for (; k + 7 * G < splits; k += 8 * G) {
+      float tv[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) tv[i] = __ldcs(src + (size_t)(k + i * G) * stride);
+      a0 += tv[0]; a1 += tv[1]; a2 += tv[2]; a3 += tv[3];
+      a0 += tv[4]; a1 += tv[5]; a2 += tv[6]; a3 += tv[7];
+    }
+    for (; k + 3 * G < splits; k += 4 * G) {
+      const float t0 = __ldcs(src + (size_t)k * stride), t1 = __ldcs(src + (size_t)(k + G) * stride);
+      const float t2 = __ldcs(src + (size_t)(k + 2 * G) * stride), t3 = __ldcs(src + (size_t)(k + 3 * G) * stride);
+      a0 += t0; a1 += t1; a2 += t2; a3 += t3;
+    }
+    for (; k < splits; k += G) a0 += __ldcs(src + (size_t)k * stride);
+    sum = (a0 + a1) + (a2 + a3);
+  }
+  part[warp][lane] = sum;
+  __syncthreads();
+  if (!live || g != 0) return;
+  float s = 0.f;
+  for (int w = 0; w < G; w++) s += part[warp + w][lane];
+  const int col = c * 32 + lane, u = KH - 1 - (col >> 6), o = (tn * NO + jo) * 64 + (col & 63);
+  if (q == nchunks) {
+    if (u == ph) db[o] = s;
+  } else {
+    const int v = q / cpc, ch = (q - v * cpc) * 64 + m64;
+    dW[(((size_t)o * C + ch) * KH + u) * KW + v] = s;
+  }
+}
+
+struct GsPlan { GsParams p; int smem; bool db_fused; };
+
+bool gs_plan(okl_ctx* ctx, const okl_conv_desc* d, bool want_db, GsPlan& pl) {
+  if (!ct_supported(ctx, d) || ct_env("OKL_CONV_TC2_WGRAD", 1) == 0 || ct_env("OKL_WG_GS", 1) == 0) return false;
+  CtShape s;
+  ct_shape(d, s);
+  if (s.KH < 2 || s.KH > 4) return false;                  // N = 64 KH must be a real gain and fit one MMA
+  // measured (batch 1024, whole call incl. second stage, us): 64->64@32 98 vs 105 (with db) / 93 vs 104 (db from the pooling backward);
+  // 64->128@16 61 vs 60; C >= 128: 84 / 58 / 87 (+ channel sum) vs the first generation's 128 x 256 tiles 94 / 62 / 95 incl. db - its
+  // N = 256 MMAs fetch fewer operand bytes per flop.  So: C = O = 64 only, unless OKL_WG_ALL asks for every shape (parity tests, probes).
+  if ((s.C != 64 || s.O != 64) && ct_env("OKL_WG_ALL", 0) == 0) return false;
+  GsParams& p = pl.p;
+  memset(&p, 0, sizeof(p));
+  p.KH = s.KH; p.KW = s.KW; p.cpc = s.C / 64; p.nchunks = s.KW * p.cpc; p.ph = s.PH; p.pw = s.PW;
+  const int ochunks = s.O / 64;
+  // bias gradient for free when a chunk slot is empty anyway and column group u = ph sees every gradient row (H >= OH)
+  pl.db_fused = want_db && (p.nchunks & 1) && 2 * s.PH <= s.KH - 1;
+  p.has_db = pl.db_fused ? 1 : 0;
+  const int S = p.nchunks + p.has_db;
+  if (S > 2 && S <= 4) { p.MT = 2; p.NO = 1; }
+  else if (ochunks % 2 == 0) { p.MT = 1; p.NO = 2; }
+  else { p.MT = 1; p.NO = 1; }
+  p.tiles_mt = (S + 2 * p.MT - 1) / (2 * p.MT);
+  p.tiles_n = ochunks / p.NO;
+  p.nreal_max = p.nchunks < 2 * p.MT ? p.nchunks : 2 * p.MT;
+  p.ones_bytes = p.has_db ? 16384 : 0;
+  int pt_env = ct_env("OKL_WG_PT", 0);
+  bool ok = false;
+  for (int pt = 128; pt >= 64 && !ok; pt >>= 1) {
+    if (pt_env && pt != pt_env) continue;
+    p.PT = pt;
+    p.TW = ct_pow2_ceil(s.OW); if (p.TW > 32) p.TW = 32;
+    if (p.TW < 8) return false;
+    p.TH = ct_pow2_ceil(s.H); if (p.TH > pt / p.TW) p.TH = pt / p.TW;
+    p.TN = pt / (p.TW * p.TH);
+    if (p.TW * p.TH < 16) continue;
+    p.tw_sh = ct_ilog2(p.TW); p.pimg_sh = ct_ilog2(p.TW * p.TH);
+    p.row_bytes = p.TW * 128;
+    p.gimg_bytes = (p.TH + s.KH - 1) * p.row_bytes;
+    p.gslab_bytes = p.TN * p.gimg_bytes;
+    p.xbox_bytes = pt * 128;
+    if (p.TH + s.KH - 1 > 256) continue;
+    p.stage_bytes = p.nreal_max * p.xbox_bytes + p.NO * p.gslab_bytes;
+    p.stages = (226 * 1024 - p.ones_bytes - 1024 - 256) / p.stage_bytes;
+    if (p.stages > GS_MAXST) p.stages = GS_MAXST;
+    const int want = ct_env("OKL_WG_MINST", 2);
+    if (p.stages >= want || (pt == 64 && p.stages >= 2) || (pt_env && p.stages >= 2)) ok = true;
+  }
+  if (!ok) return false;
+  pl.smem = p.ones_bytes + p.stages * p.stage_bytes + 256 + 1024;
+  p.diag = ct_env("OKL_WG_DIAG", 0);
+  p.epi_bufs = (p.MT * p.NO > 1 && p.stages * p.stage_bytes >= 2 * 128 * s.KH * 64 * 4) ? 2 : 1;
+  if (p.stages * p.stage_bytes < 128 * s.KH * 64 * 4) return false;
+  p.tiles_w = (s.OW + p.TW - 1) / p.TW; p.tiles_h = (s.H + p.TH - 1) / p.TH;
+  p.ktiles = p.tiles_w * p.tiles_h * ((s.N + p.TN - 1) / p.TN);
+  const int tiles = p.tiles_mt * p.tiles_n;
+  p.splits = ctx->sm_count / tiles;
+  if (p.splits > p.ktiles) p.splits = p.ktiles;
+  if (p.splits < 1) p.splits = 1;
+  return true;
+}
+
+int gs_run(okl_ctx* ctx, const okl_conv_desc* d, GsPlan& pl, const void* x16, const void* g16, void* dW, void* db) {
+  CtShape s;
+  ct_shape(d, s);
+  GsParams& p = pl.p;
+  const size_t ws_bytes = (size_t)p.splits * p.tiles_mt * p.tiles_n * p.MT * p.NO * 128 * (p.KH * 64) * sizeof(float);
+  int st = okl_ensure_workspace(ctx, ws_bytes);
+  if (st != OKL_OK) return st;
+  p.ws = (float*)ctx->workspace;
+  CUtensorMap tx, tg;
+  st = ct_map_nhwc(&tx, x16, 2, s.C, s.W, s.H, s.N, 64, p.TW, p.TH, p.TN);
+  if (st != OKL_OK) return st;
+  st = ct_map_nhwc(&tg, g16, 2, s.O, s.OW, s.OH, s.N, 64, p.TW, p.TH + s.KH - 1, p.TN);
+  if (st != OKL_OK) return st;
+  static int attr_smem = 0;
+  if (attr_smem < pl.smem) {
+    OKL_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_gs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_smem = 227 * 1024;
+  }
+  okl_launch(ctx, conv_wgrad_gs_kernel, dim3(p.tiles_mt * p.tiles_n * p.splits), dim3(GS_THREADS), pl.smem, tx, tg, p);
+  OKL_LAUNCHED(ctx, "conv_wgrad_gs_kernel");
+  const int nseg = p.tiles_mt * p.tiles_n * p.MT * p.NO * 128 * (s.KH * 2);
+  const int G = p.splits >= 32 ? 8 : (p.splits >= 16 ? 4 : (p.splits >= 8 ? 2 : 1));
+  conv_wgrad_gs_reduce<<<(nseg + 8 / G - 1) / (8 / G), 256, 0, ctx->stream>>>(p.ws, (float*)dW, pl.db_fused ? (float*)db : nullptr, s.O, s.C, s.KH, s.KW,
+                                                                                 p.cpc, p.nchunks, p.MT, p.NO, p.tiles_mt, p.tiles_n, p.splits, p.ph, G, nseg);
+  OKL_LAUNCHED(ctx, "conv_wgrad_gs_reduce");
+  return OKL_OK;
+}
+
 }  // namespace
 
 extern "C" int okl_channel_sum_bf16(okl_ctx* ctx, const void* g16, void* out, long long rows, int C);
 
 extern "C" int okl_conv2_wgrad_supported(okl_ctx* ctx, const okl_conv_desc* d) {
   if (!ctx || !d) return 0;
+  GsPlan gp;
+  if (gs_plan(ctx, d, false, gp)) return 1;
   WgPlan pl;
   return wg_plan(ctx, d, false, pl) ? 1 : 0;
 }
@@ -939,10 +1296,17 @@ extern "C" int okl_conv2_wgrad_supported(okl_ctx* ctx, const okl_conv_desc* d) {
 // okl_channel_sum_bf16 on g16
 extern "C" int okl_conv2_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x16, const void* g16, void* dW, void* db) {
   OKL_REQUIRE(ctx && d && x16 && g16 && dW, "NULL argument");
-  WgPlan pl;
-  OKL_REQUIRE(wg_plan(ctx, d, db != nullptr, pl), "okl_conv2_wgrad: unsupported shape / layout");
   CtShape s;
   ct_shape(d, s);
+  GsPlan gp;
+  if (gs_plan(ctx, d, db != nullptr, gp)) {
+    int st = gs_run(ctx, d, gp, x16, g16, dW, db);
+    if (st != OKL_OK) return st;
+    if (db && !gp.db_fused) return okl_channel_sum_bf16(ctx, g16, db, (long long)s.N * s.OH * s.OW, s.O);
+    return OKL_OK;
+  }
+  WgPlan pl;
+  OKL_REQUIRE(wg_plan(ctx, d, db != nullptr, pl), "okl_conv2_wgrad: unsupported shape / layout");
   WgParams& p = pl.p;
   const size_t ws_bytes = (size_t)p.splits * p.tiles_mt * p.tiles_n * p.MT * p.KH * 128 * p.BN * sizeof(float);
   int st = okl_ensure_workspace(ctx, ws_bytes);

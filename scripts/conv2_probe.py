@@ -341,6 +341,82 @@ def diag():
         print(row + "wgrad (gen 2)  " + "  ".join(out), flush=True)
 
 
+WG_PAR = PAR + [(2, 3, 128, (12, 12), 64, 3, 1), (2, 2, 192, (8, 8), 128, 3, 1), (2, 5, 64, (10, 14), 64, (2, 3), (0, 1)), (2, 3, 64, (16, 16), 192, (4, 3), (1, 1)),
+                (2, 2, 64, (16, 16), 64, 3, 2), (2, 7, 256, (8, 8), 64, 3, 1), (2, 2, 64, (33, 30), 128, 3, 1), (2, 17, 128, (4, 8), 128, 3, 1)]
+
+
+def wgrad():
+    """parity of okl_conv2_wgrad (gradient-slab kernel at both k-block sizes, the first slab kernel) + timing at the CIFAR layer shapes"""
+    bad = 0
+    for (nd, N, Cc, sp, Oc, k, p) in ([] if os.environ.get('PROBE_SKIP_PARITY') else WG_PAR):
+        rng = np.random.default_rng(N * 100 + Cc + Oc)
+        kt = O._tup(k, nd)
+        x = bf16_round(rng.standard_normal((N, Cc) + sp).astype(np.float32))
+        Wr = np.zeros((Oc, Cc) + kt)
+        d0 = desc(nd, N, Cc, Oc, sp, k, p, act=0)
+        if not lib.okl_conv2_supported(ctx.h, C.byref(d0)):
+            continue
+        oshape = O.conv_forward_fast(x[:1].astype(np.float64), Wr, np.zeros((Oc, 1)), 1, p, dtype=np.float64).shape
+        g = bf16_round(rng.standard_normal((N,) + oshape[1:]).astype(np.float32))
+        dWo, dbo, _ = O.conv_backward_fast(x.astype(np.float64), Wr, g.astype(np.float64), 1, p)
+        tx, tg = okl.Tensor(x), okl.Tensor(g)
+        for env in ({}, {"OKL_WG_ALL": "1"}, {"OKL_WG_ALL": "1", "OKL_WG_PT": "64"}, {"OKL_WG_ALL": "1", "OKL_WG_PT": "128"}, {"OKL_WG_GS": "0", "OKL_WG_ALL": "1"}):
+            for k_ in ("OKL_WG_PT", "OKL_WG_GS", "OKL_WG_ALL"):
+                os.environ.pop(k_, None)
+            os.environ.update(env)
+            if not lib.okl_conv2_wgrad_supported(ctx.h, C.byref(d0)):
+                print(f"    {nd}d N={N} C={Cc} sp={sp} O={Oc} k={k} p={p} {env}: unsupported")
+                continue
+            for want_db in (True, False):
+                dW = okl.Tensor._empty(Wr.shape, np.float32)
+                db = okl.Tensor._empty((Oc,), np.float32)
+                check(lib.okl_memset(ctx.h, dW._ptr_raw(), 0xff, dW.size * 4))
+                check(lib.okl_memset(ctx.h, db._ptr_raw(), 0xff, Oc * 4))
+                check(lib.okl_conv2_wgrad(ctx.h, C.byref(d0), tx._b16(_lib.NXC), tg._b16(_lib.NXC), dW._ptr_raw(), db._ptr_raw() if want_db else None))
+                dW._touch(); db._touch()
+                ew = rel(dW.data, dWo)
+                eb = rel(db.data, dbo.reshape(-1)) if want_db else 0.0
+                ok = ew < 2e-3 and eb < 2e-3
+                bad += not ok
+                print(("ok  " if ok else "BAD ") + f"wgrad {nd}d N={N} C={Cc} sp={sp} O={Oc} k={k} p={p} {env} db={want_db}: dW {ew:.2e} db {eb:.2e}", flush=True)
+    for k_ in ("OKL_WG_PT", "OKL_WG_GS", "OKL_WG_ALL"):
+        os.environ.pop(k_, None)
+    print("WGRAD PARITY", "FAILED %d" % bad if bad else "all ok")
+    N = int(os.environ.get("PROBE_BATCH", "1024"))
+    for (Cc, Oc, S) in LAYERS:
+        d0 = desc(2, N, Cc, Oc, (S, S), 3, 1, act=0)
+        x16, g16 = _DevBuf(ctx, N * Cc * S * S * 2), _DevBuf(ctx, N * Oc * S * S * 2)
+        for bfr in (x16, g16):
+            check(lib.okl_memset(ctx.h, bfr.ptr, 0x3c, bfr.nbytes))
+        dWb, dbb = _DevBuf(ctx, Oc * Cc * 9 * 4), _DevBuf(ctx, Oc * 4)
+        fl = 2.0 * N * S * S * Oc * Cc * 9
+        out = []
+        for name, env in (("default", {}), ("gs auto", {"OKL_WG_ALL": "1"}), ("gs pt64", {"OKL_WG_ALL": "1", "OKL_WG_PT": "64"}), ("gs pt128", {"OKL_WG_ALL": "1", "OKL_WG_PT": "128"}),
+                          ("slab-x (old)", {"OKL_WG_GS": "0", "OKL_WG_ALL": "1"})):
+            for k_ in ("OKL_WG_PT", "OKL_WG_GS", "OKL_WG_ALL"):
+                os.environ.pop(k_, None)
+            os.environ.update(env)
+            if not lib.okl_conv2_wgrad_supported(ctx.h, C.byref(d0)):
+                continue
+            tw = timeit(lambda: check(lib.okl_conv2_wgrad(ctx.h, C.byref(d0), x16.ptr, g16.ptr, dWb.ptr, dbb.ptr)))
+            out.append(f"{name} {tw:6.1f} us {fl / tw / 1e6:5.0f} TF")
+        for k_ in ("OKL_WG_PT", "OKL_WG_GS", "OKL_WG_ALL"):
+            os.environ.pop(k_, None)
+        print(f"L {Cc:3d}->{Oc:3d}@{S:2d} wgrad+db: " + " | ".join(out), flush=True)
+        out = []
+        os.environ["OKL_WG_ALL"] = "1"
+        for dg in (0, 4, 132):        # 1: MMAs issued twice, 2: operands loaded once per stage slot, 4: no loads / waits, 8: one accumulator, 32: N = 64, 64: A LBO = 0
+            os.environ["OKL_WG_DIAG"] = str(dg)
+            tw = timeit(lambda: check(lib.okl_conv2_wgrad(ctx.h, C.byref(d0), x16.ptr, g16.ptr, dWb.ptr, None)))
+            out.append(f"diag{dg} {tw:6.1f}")
+        os.environ.pop("OKL_WG_DIAG", None)
+        os.environ.pop("OKL_WG_ALL", None)
+        print(f"L {Cc:3d}->{Oc:3d}@{S:2d} wgrad, no db: " + "  ".join(out), flush=True)
+
+
+if "wgrad" in what:
+    wgrad()
+
 if "diag" in what:
     diag()
 if "parity" in what:

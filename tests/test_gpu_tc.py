@@ -270,3 +270,60 @@ def test_train_with_tensor_core_first_layer_sees_every_batch(okl, graph):
         assert rel_err(conv.weights.data, on.layers[0].W) < 2e-2
     finally:
         okl.set_precision("fp32")
+
+
+WGRAD_SHAPES = [  # N, C, spatial, O, k, p
+    (8, 64, (32, 32), 64, 3, 1), (4, 64, (16, 16), 128, 3, 1), (3, 128, (16, 16), 128, 3, 1), (5, 256, (8, 8), 256, 3, 1),
+    (3, 64, (13, 11), 64, 3, 0), (2, 64, (9, 20), 128, (3, 5), (1, 2)), (5, 64, (10, 14), 64, (2, 3), (0, 1)), (3, 64, (16, 16), 192, (4, 3), (1, 1)),
+    (2, 192, (8, 8), 128, 3, 1), (2, 64, (33, 30), 128, 3, 1), (17, 128, (4, 8), 128, 3, 1),
+]
+
+
+@pytest.mark.parametrize("env", [{}, {"OKL_WG_ALL": "1"}, {"OKL_WG_ALL": "1", "OKL_WG_PT": "64"}, {"OKL_WG_ALL": "1", "OKL_WG_GS": "0"}],
+                         ids=["default", "gslab", "gslab-pt64", "xslab"])
+@pytest.mark.parametrize("N,Cc,sp,Oc,k,p", WGRAD_SHAPES)
+def test_conv2_wgrad_kernels_vs_oracle(okl, monkeypatch, env, N, Cc, sp, Oc, k, p):
+    """okl_conv2_wgrad (okl.py:869-871: filter + bias gradient of Conv2D) on bf16 channels-last operands, every kernel variant: the
+    gradient-slab kernel (vertical taps stacked along N, both k-block sizes), the activation-slab kernel, and the default routing.
+    Inputs are bf16-exact, so the only error is fp32 accumulation order."""
+    import ctypes as C
+    from okrolearn_b200 import _lib
+    lib, check = _lib.lib, _lib.check
+    for k_ in ("OKL_WG_ALL", "OKL_WG_PT", "OKL_WG_GS"):
+        monkeypatch.delenv(k_, raising=False)
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    okl.set_precision("bf16")
+    try:
+        ctx = okl.get_ctx()
+        rng = np.random.default_rng(N * 100 + Cc + Oc)
+        kt, pt = O._tup(k, 2), O._tup(p, 2)
+
+        def bf16_round(a):
+            u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+            u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+            return u.astype(np.uint32).view(np.float32)
+
+        x = bf16_round(rng.standard_normal((N, Cc) + sp).astype(np.float32))
+        oshape = (N, Oc) + tuple(sp[i] + 2 * pt[i] - kt[i] + 1 for i in range(2))
+        g = bf16_round(rng.standard_normal(oshape).astype(np.float32))
+        d = _lib.ConvDesc()
+        d.nd, d.N, d.C, d.O = 2, N, Cc, Oc
+        for i in range(2):
+            d.inp[i], d.k[i], d.s[i], d.p[i] = sp[i], kt[i], 1, pt[i]
+        d.act, d.x_layout, d.y_layout = 0, _lib.NXC, _lib.NXC
+        if not lib.okl_conv2_wgrad_supported(ctx.h, C.byref(d)):
+            pytest.skip("shape not taken by this kernel variant")
+        dWo, dbo, _ = O.conv_backward_fast(x.astype(np.float64), np.zeros((Oc, Cc) + kt), g.astype(np.float64), 1, p)
+        tx, tg = okl.Tensor(x), okl.Tensor(g)
+        for want_db in (True, False):
+            dW, db = okl.Tensor._empty((Oc, Cc) + kt, np.float32), okl.Tensor._empty((Oc,), np.float32)
+            check(lib.okl_memset(ctx.h, dW._ptr_raw(), 0xff, dW.size * 4))
+            check(lib.okl_memset(ctx.h, db._ptr_raw(), 0xff, Oc * 4))
+            check(lib.okl_conv2_wgrad(ctx.h, C.byref(d), tx._b16(_lib.NXC), tg._b16(_lib.NXC), dW._ptr_raw(), db._ptr_raw() if want_db else None))
+            dW._touch(); db._touch()
+            assert rel_err(dW.data, dWo) < 2e-3
+            if want_db:
+                assert rel_err(db.data, dbo.reshape(-1)) < 2e-3
+    finally:
+        okl.set_precision("fp32")
