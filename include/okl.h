@@ -326,10 +326,11 @@ int okl_flush_l2(okl_ctx* ctx);
 /* Classifier head after a BF16 conv stack: FlattenLayer -> DenseLayer(K = C * S, N <= 16) -> SoftmaxActivationLayer ->
  * CrossEntropyLoss (okl.py:643-651, 29-47, 364-393, 1389-1409) on the channels-last bf16 activation x16 (M, S, C).  Forward (P),
  * mean CE (loss, also added to *loss_accum), dL/dP (grad), dL/dlogits (dZ), the input gradient dx16 as channels-last bf16
- * (optional), dW (K, N) in the reference's row order k = c * S + s and db; wt_scratch = N * K bf16 of device scratch. */
+ * (optional), dW (K, N) in the reference's row order k = c * S + s and db; wt_scratch = N * K bf16 of device scratch.  aux_lane 1 / 2:
+ * the leaves (loss value, dW, db) are enqueued on that auxiliary lane (okl_aux_join before they are consumed); 0: everything in order. */
 int okl_head_big_supported(int M, int C, int S, int N);
 int okl_head_big(okl_ctx* ctx, const void* x16, const void* W, const void* b, const void* targets_i32, void* P, void* loss, void* grad, void* dZ,
-                 void* dx16, void* dW, void* db, void* wt_scratch, int M, int C, int S, int N, float denom, void* loss_accum);
+                 void* dx16, void* dW, void* db, void* wt_scratch, int M, int C, int S, int N, float denom, void* loss_accum, int aux_lane);
 
 /* Memory-bound companions of the BF16 tensor-core pipeline (csrc/okl_bf16_ops.cu): between tcgen05 layers activations and
  * gradients exist as channels-last bf16 only.  okl_from_bf16: bf16 -> fp32 when a host mirror / fp32 consumer asks.

@@ -96,7 +96,7 @@ SIGNATURES = {
     "okl_conv_dgrad_bf16": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "okl_conv_wgrad_bf16": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "okl_head_big_supported": (_i, [_i, _i, _i, _i]),
-    "okl_head_big": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "okl_head_big": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _i]),
     "okl_mc_supported": (_i, [_vp]),
     "okl_mc_create": (_i, [_vp, _sz, _P(_i)]),
     "okl_mc_import": (_i, [_vp, _i, _sz]),

@@ -380,45 +380,58 @@ __device__ __forceinline__ void hb_unpack8(const uint4& v, float* f) {
   }
 }
 
-__global__ void __launch_bounds__(HB_THREADS) head_big_kernel(const uint4* __restrict__ x16, const uint4* __restrict__ Wt, const float* __restrict__ b,
-                                                              const int* __restrict__ t, float* __restrict__ P, float* __restrict__ grad,
-                                                              float* __restrict__ dZ, uint4* __restrict__ dx16, float* __restrict__ partial, int M,
-                                                              int K, int N, float inv_denom) {
-  extern __shared__ uint4 sW[];                    // [N][K / 8] uint4 = bf16 bank
-  __shared__ float wl[8];
+// One block per sample at a time, the reduction split over its eight warps (a warp-per-sample version with the bank staged in shared
+// memory left most of the chip idle at batch 1024: 128 blocks, 80 KB of weights staged per block, 37 us).  The bank (N * K bf16, 80 KB
+// for Dense(4096, 10)) is read through L1 instead.  Every sum has a fixed order: lanes by shuffle tree, warps in index order.
+__global__ void __launch_bounds__(HB_THREADS, 4) head_big_kernel(const uint4* __restrict__ x16, const uint4* __restrict__ Wt, const float* __restrict__ b,
+                                                                 const int* __restrict__ t, float* __restrict__ P, float* __restrict__ grad,
+                                                                 float* __restrict__ dZ, uint4* __restrict__ dx16, float* __restrict__ partial, int M,
+                                                                 int K, int N, float inv_denom) {
+  __shared__ float red[2][8][SN_MAXN];
   okl_pdl_sync();
   const int K8 = K >> 3;
-  for (int i = threadIdx.x; i < N * K8; i += HB_THREADS) sW[i] = __ldg(Wt + i);
-  __syncthreads();
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = (K8 + 7) >> 3, i0 = wib * per, i1 = min(K8, i0 + per);          // this warp's slice of the reduction
   float lsum = 0.f;
-  for (int m = blockIdx.x * 8 + wib; m < M; m += gridDim.x * 8) {
+  int it = 0;
+  for (int m = blockIdx.x; m < M; m += gridDim.x, it ^= 1) {
     const uint4* xr = x16 + (size_t)m * K8;
     float acc[SN_MAXN];
 #pragma unroll
     for (int n = 0; n < SN_MAXN; n++) acc[n] = 0.f;
-    for (int i = lane; i < K8; i += 32) {
+    for (int i = i0 + lane; i < i1; i += 32) {
       float xv[8];
       hb_unpack8(__ldg(xr + i), xv);
 #pragma unroll
       for (int n = 0; n < SN_MAXN; n++) {
         if (n < N) {
           float wv[8];
-          hb_unpack8(sW[n * K8 + i], wv);
+          hb_unpack8(__ldg(Wt + (size_t)n * K8 + i), wv);
 #pragma unroll
           for (int j = 0; j < 8; j++) acc[n] = fmaf(xv[j], wv[j], acc[n]);
         }
       }
     }
-    const int tc = __ldg(t + m);
-    float mx = -INFINITY, sum = 0.f;
 #pragma unroll
     for (int n = 0; n < SN_MAXN; n++) {
       if (n < N) {
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], s);
-        if (b) acc[n] += __ldg(b + n);
-        mx = fmaxf(mx, acc[n]);
+        if (lane == 0) red[it][wib][n] = acc[n];
+      }
+    }
+    __syncthreads();                                   // red[it] is rewritten two samples later: one barrier per sample is enough
+    const int tc = __ldg(t + m);
+    float mx = -INFINITY, sum = 0.f;
+#pragma unroll
+    for (int n = 0; n < SN_MAXN; n++) {
+      if (n < N) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) a += red[it][w][n];
+        if (b) a += __ldg(b + n);
+        acc[n] = a;
+        mx = fmaxf(mx, a);
       }
     }
 #pragma unroll
@@ -439,12 +452,12 @@ __global__ void __launch_bounds__(HB_THREADS) head_big_kernel(const uint4* __res
         dot += g * v;
       }
     }
-    lsum += -logf(pt);
+    if (wib == 0) lsum += -logf(pt);
 #pragma unroll
     for (int n = 0; n < SN_MAXN; n++)
       if (n < N) {
         const float dz = acc[n] * (gv[n] - dot);     // softmax backward of (clip(p) - onehot) / samples, okl.py:382-391
-        if (lane == n) {
+        if (wib == 0 && lane == n) {
           P[(size_t)m * N + n] = acc[n];
           grad[(size_t)m * N + n] = gv[n];
           dZ[(size_t)m * N + n] = dz;
@@ -453,7 +466,7 @@ __global__ void __launch_bounds__(HB_THREADS) head_big_kernel(const uint4* __res
       }
     if (dx16) {
       uint4* dr = dx16 + (size_t)m * K8;
-      for (int i = lane; i < K8; i += 32) {
+      for (int i = i0 + lane; i < i1; i += 32) {
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) o[j] = 0.f;
@@ -461,7 +474,7 @@ __global__ void __launch_bounds__(HB_THREADS) head_big_kernel(const uint4* __res
         for (int n = 0; n < SN_MAXN; n++) {
           if (n < N) {
             float wv[8];
-            hb_unpack8(sW[n * K8 + i], wv);
+            hb_unpack8(__ldg(Wt + (size_t)n * K8 + i), wv);
 #pragma unroll
             for (int j = 0; j < 8; j++) o[j] = fmaf(gv[n], wv[j], o[j]);
           }
@@ -476,13 +489,7 @@ __global__ void __launch_bounds__(HB_THREADS) head_big_kernel(const uint4* __res
       }
     }
   }
-  if (lane == 0) wl[wib] = lsum;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int w = 0; w < 8; w++) s += wl[w];
-    partial[blockIdx.x] = s;
-  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = lsum;
 }
 
 // part[rs][k'][n] = sum over the rows of chunk rs of x[row][k'] * dz[row][n]; thread = two adjacent k' (one 4-byte load per row)
@@ -540,6 +547,9 @@ __global__ void head_dw_reduce(const float* __restrict__ part, const float* __re
 
 }  // namespace
 
+int head_big_leaves(okl_ctx* ctx, const void* x16, void* loss, void* dZ, void* dW, void* db, float* partial, int grid, int M, int C, int S, int N,
+                    void* loss_accum);
+
 extern "C" int okl_head_big_supported(int M, int C, int S, int N) {
   const long long K = (long long)C * S;
   return (M >= 1 && N >= 1 && N <= SN_MAXN && C % 8 == 0 && S >= 1 && K % 256 == 0 && K * N * 2 <= 160 * 1024) ? 1 : 0;
@@ -549,7 +559,8 @@ extern "C" int okl_head_big_supported(int M, int C, int S, int N) {
 // outputs: P (probabilities), loss (mean CE), grad (dL/dP), dZ (dL/dlogits) fp32; dx16 (M, S, C) bf16 (optional); dW, db fp32.
 // wt_scratch: N * K bf16 of device scratch for the re-indexed weight bank.
 extern "C" int okl_head_big(okl_ctx* ctx, const void* x16, const void* W, const void* b, const void* targets_i32, void* P, void* loss, void* grad,
-                            void* dZ, void* dx16, void* dW, void* db, void* wt_scratch, int M, int C, int S, int N, float denom, void* loss_accum) {
+                            void* dZ, void* dx16, void* dW, void* db, void* wt_scratch, int M, int C, int S, int N, float denom, void* loss_accum,
+                            int aux_lane) {
   OKL_REQUIRE(ctx && x16 && W && targets_i32 && P && loss && grad && dZ && dW && wt_scratch, "NULL argument");
   OKL_REQUIRE(okl_head_big_supported(M, C, S, N) && denom > 0.f, "okl_head_big: unsupported shape M=%d C=%d S=%d N=%d", M, C, S, N);
   const int K = C * S;
@@ -560,14 +571,30 @@ extern "C" int okl_head_big(okl_ctx* ctx, const void* x16, const void* W, const 
   float* partial = (float*)ctx->head_scratch + 16;
   head_bank_kernel<<<okl_grid_1d(ctx, (size_t)K * N, 256), 256, 0, ctx->stream>>>((const float*)W, (__nv_bfloat16*)wt_scratch, C, S, N);
   OKL_LAUNCHED(ctx, "head_bank");
-  int grid = (M + 7) / 8;
-  if (grid > 2 * ctx->sm_count) grid = 2 * ctx->sm_count;
-  const int smem = N * K * 2;
-  static int set = 0;
-  if (set < smem) { OKL_CHECK_CUDA(cudaFuncSetAttribute(head_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); set = 160 * 1024; }
-  okl_launch(ctx, head_big_kernel, dim3(grid), dim3(HB_THREADS), (size_t)smem, (const uint4*)x16, (const uint4*)wt_scratch, (const float*)b,
+  int grid = M;
+  if (grid > 4 * ctx->sm_count) grid = 4 * ctx->sm_count;
+  okl_launch(ctx, head_big_kernel, dim3(grid), dim3(HB_THREADS), (size_t)0, (const uint4*)x16, (const uint4*)wt_scratch, (const float*)b,
              (const int*)targets_i32, (float*)P, (float*)grad, (float*)dZ, (uint4*)dx16, partial, M, K, N, 1.f / denom);
   OKL_LAUNCHED(ctx, "head_big");
+  // only dX is on the step's critical path: the loss value, dW and db are leaves and go to an auxiliary lane when the caller has one
+  // (joined with the other leaves before the update / gradient exchange)
+  const bool aux = aux_lane >= 1 && aux_lane <= 2 && ctx->cur_lane == 0;
+  if (aux) {
+    int s0 = okl_aux_mark(ctx);
+    if (s0 == OKL_OK) s0 = okl_aux_begin(ctx, aux_lane);
+    if (s0 != OKL_OK) return s0;
+  }
+  const int st = head_big_leaves(ctx, x16, loss, dZ, dW, db, partial, grid, M, C, S, N, loss_accum);
+  if (aux) {
+    const int e = okl_aux_end(ctx);
+    return st != OKL_OK ? st : e;
+  }
+  return st;
+}
+
+int head_big_leaves(okl_ctx* ctx, const void* x16, void* loss, void* dZ, void* dW, void* db, float* partial, int grid, int M, int C, int S, int N,
+                    void* loss_accum) {
+  const int K = C * S;
   head_loss_finalize_kernel<<<1, 32, 0, ctx->stream>>>(partial, grid, M, (float*)loss, (float*)loss_accum);
   OKL_LAUNCHED(ctx, "head_loss_finalize");
   // weight gradient: row chunks so that the grid fills the chip; fixed-order second stage

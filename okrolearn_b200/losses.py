@@ -142,7 +142,8 @@ class CrossEntropyLoss:
                 outputs._buf, outputs._off = _DevBuf(ctx, rows * cols * 4), 0
                 check(lib.okl_head_big(ctx.h, src._b16(_lib.NXC), bk.ptr(0), bk.ptr(1), tptr, outputs._ptr_raw(), loss.ptr, grad._ptr_raw(),
                                        dz._ptr_raw(), dx._bf16.ptr if dx is not None else None, bk.grad_ptr(0), bk.grad_ptr(1),
-                                       head._wt_scratch.ptr, rows, Cc, S_, cols, float(rows * ctx.nranks), self._loss_accum))
+                                       head._wt_scratch.ptr, rows, Cc, S_, cols, float(rows * ctx.nranks), self._loss_accum,
+                                       int(head._aux_lane) if (head._aux_lane and head._defer_update) else 0))
                 outputs._touch()
                 head._head_pre = (dz, dx, True)
                 sm._precomputed = (grad, dz)
