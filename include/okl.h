@@ -340,7 +340,8 @@ int okl_head_big(okl_ctx* ctx, const void* x16, const void* W, const void* b, co
 int okl_from_bf16(okl_ctx* ctx, const void* src_bf16, void* dst_f32, size_t n);
 int okl_pool2_bf16_supported(int C, int H, int W);
 int okl_pool2_bf16_fwd(okl_ctx* ctx, const void* x16, void* y16, int N, int C, int H, int W);
-int okl_pool2_bf16_bwd(okl_ctx* ctx, const void* x16, const void* g16, void* dx16, int N, int C, int H, int W, int relu_mask, void* db);
+int okl_pool2_bf16_bwd(okl_ctx* ctx, const void* x16, const void* g16, void* dx16, int N, int C, int H, int W, int relu_mask, void* db,
+                       int aux_lane);   /* aux_lane 1 / 2: the second stage of db runs on that auxiliary lane (okl_aux_join before db is read) */
 int okl_channel_sum_bf16(okl_ctx* ctx, const void* g16, void* out, long long rows, int C);
 /* Crossing layout AND precision in one pass (32-channel x 128-position shared-memory tiles).  okl_to_bf16_nxc: the caller's fp32
  * (N, C, S) tensor -> the bf16 (N, S, C) operand of the tensor-core convolutions (replaces okl_permute + okl_to_bf16: the im2col +

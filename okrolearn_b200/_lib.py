@@ -106,7 +106,7 @@ SIGNATURES = {
     "okl_from_bf16": (_i, [_vp, _vp, _vp, _sz]),
     "okl_pool2_bf16_supported": (_i, [_i, _i, _i]),
     "okl_pool2_bf16_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
-    "okl_pool2_bf16_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "okl_pool2_bf16_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i]),
     "okl_channel_sum_bf16": (_i, [_vp, _vp, _vp, _ll, _i]),
     "okl_to_bf16_nxc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _ll]),
     "okl_mse_fwd_bwd_nxc_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _f, _vp, _i]),

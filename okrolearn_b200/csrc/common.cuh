@@ -48,6 +48,8 @@ struct okl_ctx {
   int* tile_counters = nullptr;         // split-K arrival counters of the tcgen05 GEMM (all zero between launches)
   void* bf16_scratch = nullptr;         // bf16 copies of GEMM operands (OKL_BF16 mode)
   void* head_scratch = nullptr;         // arrival counter + per-block loss partials of the fused classifier head
+  void* leaf_scratch = nullptr;         // ring of partial sums handed from a main-lane kernel to a second stage on an auxiliary lane
+  size_t leaf_off = 0;
   size_t bf16_scratch_bytes = 0;
   // auxiliary lanes: independent branches of a step (weight / bias gradients are leaves of the backward chain) run on their own
   // streams with their own scratch; the fields above (stream, workspace, tile_counters, bf16_scratch) always describe the CURRENT lane

@@ -346,14 +346,30 @@ extern "C" int okl_pool2_bf16_fwd(okl_ctx* ctx, const void* x16, void* y16, int 
 
 // dx16 = gradient routed to the window maxima (x16 = the pooling layer's input; relu_mask: that input is a ReLU output whose backward is
 // applied here).  db (optional, fp32 [C]) = per-channel sum of dx16's values before bf16 rounding.
-extern "C" int okl_pool2_bf16_bwd(okl_ctx* ctx, const void* x16, const void* g16, void* dx16, int N, int C, int H, int W, int relu_mask, void* db) {
+constexpr size_t LEAF_RING = 8u << 20;
+
+extern "C" int okl_pool2_bf16_bwd(okl_ctx* ctx, const void* x16, const void* g16, void* dx16, int N, int C, int H, int W, int relu_mask, void* db,
+                                  int aux_lane) {
   OKL_REQUIRE(ctx && x16 && g16 && dx16, "NULL argument");
   OKL_REQUIRE(okl_pool2_bf16_supported(C, H, W), "okl_pool2_bf16_bwd: unsupported shape C=%d H=%d W=%d", C, H, W);
   const size_t total8 = (size_t)N * (H / 2) * (W / 2) * (C / 8);
   if (total8 == 0) return OKL_OK;
   int grid = okl_grid_1d(ctx, total8, PB_THREADS, 4);
   float* partial = nullptr;
-  if (db) {
+  // db is a leaf of the backward chain: with an auxiliary lane its second stage leaves the critical path (~7 us per pooling layer).  The
+  // partials then live in a ring of their own - the lane's second stage may still be pending when later main-lane kernels reuse the
+  // workspace; a step's pooling layers take different slices, and the step's okl_aux_join precedes the next step's writes.
+  const size_t pbytes = ((size_t)grid * C * sizeof(float) + 255) & ~size_t(255);
+  const bool aux = db && aux_lane >= 1 && aux_lane <= 2 && ctx->cur_lane == 0 && pbytes <= LEAF_RING / 4;
+  if (db && aux) {
+    if (!ctx->leaf_scratch) {
+      OKL_REQUIRE(!ctx->capturing, "okl_pool2_bf16_bwd: scratch ring needed during graph capture (run one eager step first)");
+      OKL_CHECK_CUDA(cudaMalloc(&ctx->leaf_scratch, LEAF_RING));
+    }
+    if (ctx->leaf_off + pbytes > LEAF_RING) ctx->leaf_off = 0;
+    partial = (float*)((char*)ctx->leaf_scratch + ctx->leaf_off);
+    ctx->leaf_off += pbytes;
+  } else if (db) {
     int s = okl_ensure_workspace(ctx, (size_t)grid * C * sizeof(float));
     if (s != OKL_OK) return s;
     partial = (float*)ctx->workspace;
@@ -362,8 +378,18 @@ extern "C" int okl_pool2_bf16_bwd(okl_ctx* ctx, const void* x16, const void* g16
                                                              relu_mask, partial);
   OKL_LAUNCHED(ctx, "pool2_bf16_bwd");
   if (db) {
+    if (aux) {
+      int s = okl_aux_mark(ctx);
+      if (s == OKL_OK) s = okl_aux_begin(ctx, aux_lane);
+      if (s != OKL_OK) return s;
+    }
     chansum_stage2<<<(C * 32 + 255) / 256, 256, 0, ctx->stream>>>(partial, (float*)db, grid, C);
-    OKL_LAUNCHED(ctx, "chansum_stage2");
+    const int st = okl_post_launch(ctx, "chansum_stage2");
+    if (aux) {
+      const int e = okl_aux_end(ctx);
+      return st != OKL_OK ? st : e;
+    }
+    return st;
   }
   return OKL_OK;
 }

@@ -266,6 +266,7 @@ extern "C" int okl_ctx_destroy(okl_ctx* ctx) {
   cudaStreamSynchronize(ctx->comm_stream);
   okl_comm_destroy(ctx);
   for (auto& kv : ctx->live) cudaFree(kv.first);
+  if (ctx->leaf_scratch) cudaFree(ctx->leaf_scratch);
   if (ctx->workspace) cudaFree(ctx->workspace);
   if (ctx->staging) cudaFree(ctx->staging);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);

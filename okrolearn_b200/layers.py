@@ -590,6 +590,7 @@ class _ConvBase(_ParamLayer):
         """bf16 K-major filter banks of the tcgen05 convolution - [O][tap][C] for fprop, flipped [C][tap][O] for dgrad - refreshed by
         ONE kernel whenever the fp32 master filters changed (once per train step, after the update)."""
         ctx = get_ctx()
+        self._bank_desc = d
         wt = self._bucket.tensors[0]
         wp = self._bucket.ptr(0)                                   # flushes a pending host assignment first
         # inside a captured step the refresh is recorded once per capture (forward) and replayed with the graph; outside, a graph
@@ -1591,7 +1592,8 @@ class _Pool:
             sink = self._db_sink if (self._fused_relu_bwd and self._db_sink is not None and
                                      getattr(self._db_sink, "_conv2", False) and self._db_sink.out_channels == Cc) else None
             check(lib.okl_pool2_bf16_bwd(ctx.h, x._b16(NXC), dL_dout._b16(NXC), dx._bf16.ptr, N, Cc, H, W, 1 if self._fused_relu_bwd else 0,
-                                         sink._bucket.grad_ptr(1) if sink is not None else None))
+                                         sink._bucket.grad_ptr(1) if sink is not None else None,
+                                         int(sink._aux_lane) if (sink is not None and sink._aux_lane and sink._defer_update) else 0))
             if sink is not None:
                 dx._db_done = sink                 # the convolution in front already has its bias gradient: this kernel reduced it
             _set_input_grad(x, dx)

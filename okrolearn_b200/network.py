@@ -320,9 +320,15 @@ class NeuralNetwork:
         self._plan(_fast)
         self._run_hooks('pre_forward', inputs)
         self.layer_outputs = []
+        pending_banks = self._prefetch_filter_banks() if _fast else False
         for i, layer in enumerate(self.layers):
+            if pending_banks and getattr(layer, "_conv2", False):
+                check(lib.okl_aux_join(get_ctx().h))           # the banks were refreshed beside the first layer's forward
+                pending_banks = False
             inputs = layer.forward(inputs)
             self._log_layer_output(i, inputs)
+        if pending_banks:
+            check(lib.okl_aux_join(get_ctx().h))
         if self.temperature != 1.0:
             # okl.py:2890 `inputs.data = inputs.data / self.temperature` - in place on the last layer's output Tensor
             ctx = get_ctx()
@@ -330,6 +336,22 @@ class NeuralNetwork:
             inputs._touch()
         self._run_hooks('post_forward', inputs)
         return inputs
+
+    def _prefetch_filter_banks(self):
+        """BF16 tensor-core stacks: the bf16 filter banks of every convolution (one small kernel each, refreshed once per step after
+        the update) are produced on an auxiliary lane while the first layer's forward runs, instead of one by one in front of
+        their layers on the critical path.  Returns True when something was enqueued (the caller joins before the first use)."""
+        lays = [l for l in self.layers[1:] if getattr(l, "_conv2", False) and getattr(l, "_bank_desc", None) is not None and l._aux_lane]
+        if len(lays) < 2 or not getattr(self.layers[0], "_first_tc", False):
+            return False
+        ctx = get_ctx()
+        check(lib.okl_aux_begin(ctx.h, 2))
+        try:
+            for l in lays:
+                l._filter_banks(l._bank_desc)
+        finally:
+            check(lib.okl_aux_end(ctx.h))
+        return True
 
     def backward(self, loss_gradient: 'Tensor', lr: float):
         self._check_breakpoint('backward', loss_gradient, lr)

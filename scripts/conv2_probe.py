@@ -217,7 +217,7 @@ def misc():
         yo = O.maxpool_forward(x.astype(np.float64), 2, 2)
         e1 = rel(fetch16(y16.ptr, (N, H // 2, W // 2, Cc)), yo)
         for relu in (0, 1):
-            check(lib.okl_pool2_bf16_bwd(ctx.h, tx._b16(_lib.NXC), tg._b16(_lib.NXC), dx16.ptr, N, Cc, H, W, relu, db._ptr_raw()))
+            check(lib.okl_pool2_bf16_bwd(ctx.h, tx._b16(_lib.NXC), tg._b16(_lib.NXC), dx16.ptr, N, Cc, H, W, relu, db._ptr_raw(), 0))
             db._touch()
             gg = g.astype(np.float64) * ((yo > 0) if relu else 1.0)
             dxo = O.maxpool_backward(x.astype(np.float64), gg, 2, 2)
