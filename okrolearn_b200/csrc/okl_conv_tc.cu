@@ -269,9 +269,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       // the ReLU mask of the first 64 channels is requested BEFORE the wait for the accumulator: its HBM latency hides behind the MMAs
       uint4 mk[8];
+      const int crem = p.Oc - ch0;                         // output channels left from this tile's first one (partial last tile)
       if (p.mask) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) mk[j] = mrow ? __ldg(reinterpret_cast<const uint4*>(mrow) + j) : make_uint4(0u, 0u, 0u, 0u);
+        for (int j = 0; j < 8; j++) mk[j] = (mrow && j * 8 < crem) ? __ldg(reinterpret_cast<const uint4*>(mrow) + j) : make_uint4(0u, 0u, 0u, 0u);
       }
       mbar_wait(&t_full[acc], pacc);
       tc_fence_after();
@@ -281,7 +282,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int ch = 0; ch < BN / 64; ch++) {
         if (p.mask && ch > 0) {
 #pragma unroll
-          for (int j = 0; j < 8; j++) mk[j] = mrow ? __ldg(reinterpret_cast<const uint4*>(mrow + ch * 64) + j) : make_uint4(0u, 0u, 0u, 0u);
+          for (int j = 0; j < 8; j++)
+            mk[j] = (mrow && ch * 64 + j * 8 < crem) ? __ldg(reinterpret_cast<const uint4*>(mrow + ch * 64) + j) : make_uint4(0u, 0u, 0u, 0u);
         }
         uint32_t v0[32], v1[32];
         tmem_ld32(taddr + (uint32_t)(ch * 64), v0);
@@ -496,6 +498,7 @@ int ct_launch_cs(okl_ctx* ctx, int pair, const CUtensorMap& ta, const CUtensorMa
 }
 
 struct CtShape { int N, C, O, H, W, KH, KW, PH, PW, OH, OW; };
+bool gs_feasible(okl_ctx* ctx, const okl_conv_desc* d);
 
 void ct_shape(const okl_conv_desc* d, CtShape& s) {
   s.N = d->N; s.C = d->C; s.O = d->O;
@@ -508,7 +511,7 @@ void ct_shape(const okl_conv_desc* d, CtShape& s) {
 // y[N, OH, OW, Oc] = act(conv(x16[N, H, W, Cc], bank[Oc][T * Cc]) + bias) (* mask > 0), stride 1, padding (ph, pw), channels-last
 int conv_tc_run(okl_ctx* ctx, const void* x16, int N, int H, int W, int Cc, const void* bank, int Oc, int KH, int KW, int ph, int pw, int OH, int OW,
                 const float* bias, int relu, float* y, void* y16, const void* mask16) {
-  OKL_REQUIRE(Cc % 64 == 0 && Oc % 64 == 0 && Oc <= CT_MAX_OC, "conv_tc: channel counts must be multiples of 64 (C=%d O=%d)", Cc, Oc);
+  OKL_REQUIRE(Cc % 8 == 0 && Oc % 8 == 0 && Oc <= CT_MAX_OC, "conv_tc: channel counts must be multiples of 8 (C=%d O=%d)", Cc, Oc);
   OKL_REQUIRE(y || y16, "conv_tc: no output requested");
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
@@ -527,8 +530,8 @@ int conv_tc_run(okl_ctx* ctx, const void* x16, int N, int H, int W, int Cc, cons
     while (bn > 64 && (long long)p.tiles_m * (Oc / bn) * 4 < 3LL * ctx->sm_count) bn >>= 1;
   }
   if (Oc % bn) bn = 64;
-  p.tiles_n = Oc / bn;
-  p.KH = KH; p.KW = KW; p.cblocks = Cc / 64; p.C = Cc; p.ph = ph; p.pw = pw;
+  p.tiles_n = (Oc + bn - 1) / bn;
+  p.KH = KH; p.KW = KW; p.cblocks = (Cc + 63) / 64; p.C = Cc; p.ph = ph; p.pw = pw;
   p.row_bytes = p.TW * 128;
   p.slab = (p.TN == 1 && KH > 1 && p.TW >= 8 && (p.TH + KH - 1) * p.TW * 128 <= CT_A_STAGE && ct_env("OKL_CT_SLAB", 1)) ? 1 : 0;
   p.sub_bytes = p.slab ? (p.TH / 2) * p.row_bytes : 128 * 128;
@@ -566,11 +569,15 @@ bool ct_supported(okl_ctx* ctx, const okl_conv_desc* d) {
   if (d->nd > 2 || d->x_layout != OKL_NXC || d->y_layout != OKL_NXC) return false;
   for (int i = 0; i < d->nd; i++)
     if (d->s[i] != 1) return false;
-  if (d->C % 64 || d->O % 64 || d->C > CT_MAX_OC || d->O > CT_MAX_OC || d->N < 1) return false;
+  if (d->C % 8 || d->O % 8 || d->C > CT_MAX_OC || d->O > CT_MAX_OC || d->N < 1) return false;
   CtShape s;
   ct_shape(d, s);
   if (s.OH < 1 || s.OW < 1 || s.KH > 7 || s.KW > 7) return false;
   if (s.PH > s.KH - 1 || s.PW > s.KW - 1) return false;
+  // Channel counts that are multiples of 8 but not of 64 (16-byte rows for TMA): the 64-channel boxes run past the tensor's channel
+  // extent and TMA's zero fill pads the reduction; partial output-channel tiles are clipped by the TMA stores.  Those shapes need the
+  // gradient-slab weight-gradient kernel (the other wgrad kernels assume whole 64-channel chunks), so they are taken only with it.
+  if ((d->C % 64 || d->O % 64) && (ct_env("OKL_CT_ANYC", 1) == 0 || !gs_feasible(ctx, d))) return false;
   return true;
 }
 
@@ -873,6 +880,7 @@ bool wg_plan(okl_ctx* ctx, const okl_conv_desc* d, bool want_db, WgPlan& pl) {
   // measured (batch 1024): 64-channel inputs 197 vs 321 us and 77 vs 91 us against the first-generation kernel; for C >= 128 the
   // first generation's N = 128 / 256 tiles still win (98 / 59 / 81 us vs 137 / 96 / 133 us) - those shapes stay there for now
   if (s.C > 64 && ct_env("OKL_WG_ALL", 0) == 0) return false;
+  if (s.C % 64 || s.O % 64) return false;                  // whole 64-channel chunks only (the gradient-slab kernel takes the rest)
   WgParams& p = pl.p;
   memset(&p, 0, sizeof(p));
   p.TW = ct_pow2_ceil(s.OW); if (p.TW > 32) p.TW = 32;
@@ -1182,11 +1190,12 @@ __global__ void __launch_bounds__(256) conv_wgrad_gs_reduce(const float* __restr
   float s = 0.f;
   for (int w = 0; w < G; w++) s += part[warp + w][lane];
   const int col = c * 32 + lane, u = KH - 1 - (col >> 6), o = (tn * NO + jo) * 64 + (col & 63);
+  if (o >= O) return;                                      // partial last 64-channel chunk
   if (q == nchunks) {
     if (u == ph) db[o] = s;
   } else {
     const int v = q / cpc, ch = (q - v * cpc) * 64 + m64;
-    dW[(((size_t)o * C + ch) * KH + u) * KW + v] = s;
+    if (ch < C) dW[(((size_t)o * C + ch) * KH + u) * KW + v] = s;
   }
 }
 
@@ -1200,11 +1209,12 @@ bool gs_plan(okl_ctx* ctx, const okl_conv_desc* d, bool want_db, GsPlan& pl) {
   // measured (batch 1024, whole call incl. second stage, us): 64->64@32 98 vs 105 (with db) / 93 vs 104 (db from the pooling backward);
   // 64->128@16 61 vs 60; C >= 128: 84 / 58 / 87 (+ channel sum) vs the first generation's 128 x 256 tiles 94 / 62 / 95 incl. db - its
   // N = 256 MMAs fetch fewer operand bytes per flop.  So: C = O = 64 only, unless OKL_WG_ALL asks for every shape (parity tests, probes).
-  if ((s.C != 64 || s.O != 64) && ct_env("OKL_WG_ALL", 0) == 0) return false;
+  const bool partial_chunks = s.C % 64 || s.O % 64;        // only this kernel handles those (zero-filled channel boxes, guarded second stage)
+  if ((s.C != 64 || s.O != 64) && !partial_chunks && ct_env("OKL_WG_ALL", 0) == 0) return false;
   GsParams& p = pl.p;
   memset(&p, 0, sizeof(p));
-  p.KH = s.KH; p.KW = s.KW; p.cpc = s.C / 64; p.nchunks = s.KW * p.cpc; p.ph = s.PH; p.pw = s.PW;
-  const int ochunks = s.O / 64;
+  p.KH = s.KH; p.KW = s.KW; p.cpc = (s.C + 63) / 64; p.nchunks = s.KW * p.cpc; p.ph = s.PH; p.pw = s.PW;
+  const int ochunks = (s.O + 63) / 64;
   // bias gradient for free when a chunk slot is empty anyway and column group u = ph sees every gradient row (H >= OH)
   pl.db_fused = want_db && (p.nchunks & 1) && 2 * s.PH <= s.KH - 1;
   p.has_db = pl.db_fused ? 1 : 0;
@@ -1249,6 +1259,23 @@ bool gs_plan(okl_ctx* ctx, const okl_conv_desc* d, bool want_db, GsPlan& pl) {
   p.splits = ctx->sm_count / tiles;
   if (p.splits > p.ktiles) p.splits = p.ktiles;
   if (p.splits < 1) p.splits = 1;
+  return true;
+}
+
+// shapes with partial 64-channel chunks: this kernel must take them, and the bias gradient must come either from its ones slot or from
+// okl_channel_sum_bf16 (channel counts of 8 x a power of two)
+bool gs_feasible(okl_ctx* ctx, const okl_conv_desc* d) {
+  if (d->nd > 2 || d->x_layout != OKL_NXC || d->y_layout != OKL_NXC || d->C % 8 || d->O % 8) return false;
+  CtShape s;
+  ct_shape(d, s);
+  if (s.KH < 2 || s.KH > 4 || s.OH < 1 || s.OW < 1) return false;
+  if (ct_env("OKL_CONV_TC2_WGRAD", 1) == 0 || ct_env("OKL_WG_GS", 1) == 0) return false;
+  const int nchunks = s.KW * ((s.C + 63) / 64);
+  const bool db_fused = (nchunks & 1) && 2 * s.PH <= s.KH - 1;
+  const int o8 = s.O / 8;
+  if (!db_fused && !((o8 & (o8 - 1)) == 0 && o8 <= 256)) return false;
+  const int tw = ct_pow2_ceil(s.OW) > 32 ? 32 : ct_pow2_ceil(s.OW);
+  if (tw < 8 || tw * ct_pow2_ceil(s.H) < 16) return false;
   return true;
 }
 

@@ -17,6 +17,7 @@ from .tensor import Tensor, _DevBuf, _numel
 _ALIGN = 64          # floats: parameter sub-tensors start on 256-byte boundaries inside a bucket
 # BF16 mode: tensors between tensor-core layers are stored as channels-last bf16 only (OKL_BF16_ONLY=0 restores fp32 + bf16 shadow)
 _BF16_ONLY = __import__("os").environ.get("OKL_BF16_ONLY", "1") != "0"
+_ANY_C = __import__("os").environ.get("OKL_CT_ANYC", "1") != "0"       # BF16 tcgen05 convolutions for channel counts that are multiples of 8
 
 
 def _as_tensor(x):
@@ -402,10 +403,20 @@ class _ConvBase(_ParamLayer):
         return d, tuple(out[i] for i in range(nd))
 
     def _tc_eligible(self):
-        """Shapes the tcgen05 implicit-GEMM convolution takes (okl_tc_conv_supported): 1-D/2-D, unit stride, channel counts
-        that are multiples of 32, padding <= k-1.  Those layers run channels-last in TF32/BF16 mode."""
-        return (self._nd <= 2 and all(s == 1 for s in self._s) and self.in_channels % 32 == 0 and self.out_channels % 32 == 0 and
-                all(p <= k - 1 for p, k in zip(self._p, self._k)))
+        """Shapes the tcgen05 implicit-GEMM convolution takes (okl_tc_conv_supported / okl_conv2_supported): 1-D/2-D, unit stride,
+        padding <= k-1, channel counts that are multiples of 32 - or, in BF16 mode, 2-D layers with 2..4 filter rows and channel
+        counts that are multiples of 8 (TMA zero-fills the partial 64-channel chunks; the bias gradient needs a free chunk slot of
+        the weight-gradient kernel or 8 x 2^n output channels).  Those layers run channels-last in TF32/BF16 mode."""
+        if not (self._nd <= 2 and all(s == 1 for s in self._s) and all(p <= k - 1 for p, k in zip(self._p, self._k))):
+            return False
+        Cc, Oc = self.in_channels, self.out_channels
+        if Cc % 32 == 0 and Oc % 32 == 0:
+            return True
+        if get_ctx().precision != _lib.BF16 or self._nd != 2 or Cc % 8 or Oc % 8 or not (2 <= self._k[0] <= 4) or not _ANY_C:
+            return False
+        free_slot = (self._k[1] * ((Cc + 63) // 64)) % 2 == 1 and 2 * self._p[0] <= self._k[0] - 1
+        o8 = Oc // 8
+        return bool(free_slot or (o8 & (o8 - 1)) == 0)
 
     _fused_pool = None             # NeuralNetwork planner: (relu, pool) layers fused into this conv (first block, no dX needed)
 
@@ -481,9 +492,9 @@ class _ConvBase(_ParamLayer):
             check(lib.okl_conv_first_fprop(ctx.h, C.byref(d), xp, xi, self._bucket.ptr(0), self._bucket.ptr(1), out._bf16.ptr))
             self._fwd_layouts, self._bf16_path, self._conv2 = (xl, yl), False, False
             return out
-        self._bf16_path = bool(ctx.precision == _lib.BF16 and xl == NXC and yl == NXC and inputs.shape[0] > 0 and
-                               lib.okl_conv_bf16_supported(ctx.h, C.byref(d)))
-        self._conv2 = bool(self._bf16_path and self._fused_act in (ACT_NONE, ACT_RELU) and lib.okl_conv2_supported(ctx.h, C.byref(d)))
+        b16_ok = bool(ctx.precision == _lib.BF16 and xl == NXC and yl == NXC and inputs.shape[0] > 0)
+        self._conv2 = bool(b16_ok and self._fused_act in (ACT_NONE, ACT_RELU) and lib.okl_conv2_supported(ctx.h, C.byref(d)))
+        self._bf16_path = bool(self._conv2 or (b16_ok and lib.okl_conv_bf16_supported(ctx.h, C.byref(d))))
         if self._conv2:                          # second-generation tcgen05 kernel (okl_conv_tc.cu): slab reuse, 256-pixel tiles, TMA stores
             w2, _ = self._filter_banks(d)
             if _BF16_ONLY:                       # the output exists as channels-last bf16 only; fp32 is converted if somebody asks

@@ -162,7 +162,10 @@ def test_cifar_block_channels_last_pipeline(okl):
 
 
 @pytest.mark.parametrize("nd,N,C,sp,Oc,k,p", [(2, 8, 64, (32, 32), 64, 3, 1), (2, 4, 64, (16, 16), 128, 3, 1), (2, 6, 128, (8, 8), 256, 3, 1),
-                                              (2, 3, 64, (13, 11), 64, 3, 0), (1, 4, 64, (256,), 64, 3, 1)])
+                                              (2, 3, 64, (13, 11), 64, 3, 0), (1, 4, 64, (256,), 64, 3, 1),
+                                              # channel counts that are multiples of 8 only (TMA zero-fills the partial 64-channel chunks)
+                                              (2, 6, 16, (24, 24), 32, 3, 1), (2, 4, 24, (16, 20), 48, 3, 1), (2, 3, 96, (12, 12), 16, 3, 1),
+                                              (2, 5, 8, (18, 16), 8, (2, 3), (0, 1)), (2, 2, 160, (8, 8), 72, 3, 1), (2, 3, 32, (16, 16), 32, 4, 1)])
 def test_conv_implicit_gemm_bf16(okl, nd, N, C, sp, Oc, k, p):
     """BF16 implicit-GEMM convolution with channels-last bf16 shadows vs the fp64 oracle (north_star tolerance 2e-2)."""
     okl.set_precision("bf16")
@@ -177,6 +180,8 @@ def test_conv_implicit_gemm_bf16(okl, nd, N, C, sp, Oc, k, p):
         lay.biases.data = b.copy()
         y = lay.forward(okl.Tensor(x))
         assert lay._bf16_path
+        if C % 64 or Oc % 64:
+            assert lay._conv2                      # the second-generation tcgen05 kernels took the partial-chunk shape
         x64 = x.astype(np.float64)
         yo = O.conv_forward_fast(x64, W, b, 1, p, dtype=np.float64)
         assert rel_err(y.data, yo) < 1.5e-2
@@ -276,6 +281,7 @@ WGRAD_SHAPES = [  # N, C, spatial, O, k, p
     (8, 64, (32, 32), 64, 3, 1), (4, 64, (16, 16), 128, 3, 1), (3, 128, (16, 16), 128, 3, 1), (5, 256, (8, 8), 256, 3, 1),
     (3, 64, (13, 11), 64, 3, 0), (2, 64, (9, 20), 128, (3, 5), (1, 2)), (5, 64, (10, 14), 64, (2, 3), (0, 1)), (3, 64, (16, 16), 192, (4, 3), (1, 1)),
     (2, 192, (8, 8), 128, 3, 1), (2, 64, (33, 30), 128, 3, 1), (17, 128, (4, 8), 128, 3, 1),
+    (6, 16, (24, 24), 32, 3, 1), (4, 24, (16, 20), 48, 3, 1), (3, 96, (12, 12), 16, 3, 1), (2, 160, (8, 8), 72, 3, 1), (5, 8, (18, 16), 8, (2, 3), (0, 1)),
 ]
 
 
