@@ -17,13 +17,14 @@ set -- $SKIP
 echo "skip $1 count $2"
 ncu --set full --clock-control none --import-source on -s $1 -c $2 -f -o /tmp/prof/cifar6_step $CMD > gpurun_out/ncu_full1.log 2>&1; echo "full cifar6 exit $?"
 python scripts/ncu_summary.py /tmp/prof/cifar6_step.ncu-rep gpurun_out/r2_ncu_cifar6_kernels.json cifar6 "$CMD" > gpurun_out/r2_ncu_cifar6_kernels.txt 2>&1
-for k in "conv_tc_kernel<\(int\)64" "conv_wgrad_tc_kernel<\(int\)64" "conv_first_fprop" "conv_first_wgrad_kernel"; do
+rm -f gpurun_out/r2_ncu_cifar6_stalls.txt
+for k in "conv_tc_kernel<\(int\)64" "conv_wgrad_gs_kernel" "conv_wgrad_tc_kernel<\(int\)128" "conv_first_fprop" "conv_first_wgrad_kernel" "head_big_kernel"; do
   python scripts/ncu_top.py /tmp/prof/cifar6_step.ncu-rep "$k" 0 18 >> gpurun_out/r2_ncu_cifar6_stalls.txt 2>&1
 done
 CMD2="python scripts/gemm_bench.py 8192 8192 8192 1 0 1"
 ncu --set full --clock-control none -k regex:tc_gemm_kernel -s 3 -c 1 -f -o /tmp/prof/gemm8192 $CMD2 > gpurun_out/ncu_full2.log 2>&1; echo "full gemm exit $?"
 python scripts/ncu_summary.py /tmp/prof/gemm8192.ncu-rep gpurun_out/r2_ncu_gemm8192_bf16.json plain "$CMD2" > gpurun_out/r2_ncu_gemm8192_bf16.txt 2>&1
-CMD3="python bench.py --workload conv3d_video --precision tf32 --steps 2 --warmup 3 --no-configs --no-cpu-baseline --no-e2e --no-roofline"
-ncu --set full --clock-control none -k regex:sc_ -s 6 -c 2 -f -o /tmp/prof/conv3d $CMD3 > gpurun_out/ncu_full3.log 2>&1; echo "full conv3d exit $?"
-python scripts/ncu_summary.py /tmp/prof/conv3d.ncu-rep gpurun_out/r2_ncu_conv3d_smallc.json plain "$CMD3" > gpurun_out/r2_ncu_conv3d_smallc.txt 2>&1
+CMD3="python bench.py --workload conv3d_video --precision bf16 --steps 2 --warmup 3 --no-configs --no-cpu-baseline --no-e2e --no-roofline"
+ncu --set full --clock-control none --import-source on -k regex:"conv_first|mse_nxc" -s 9 -c 3 -f -o /tmp/prof/conv3d_bf16 $CMD3 > gpurun_out/ncu_full3.log 2>&1; echo "full conv3d exit $?"
+python scripts/ncu_summary.py /tmp/prof/conv3d_bf16.ncu-rep gpurun_out/r2_ncu_conv3d_bf16.json plain "$CMD3" > gpurun_out/r2_ncu_conv3d_bf16.txt 2>&1
 du -sh gpurun_out
