@@ -296,6 +296,10 @@ int okl_accum_update(okl_ctx* ctx, void* w, void* gacc, const void* g, size_t n,
 /* the same rule applied to `count` parameter buckets in one launch (host arrays of device pointers / element counts) */
 int okl_accum_update_multi(okl_ctx* ctx, int count, void* const* w, void* const* gacc, const void* const* g, const size_t* n,
                            float lr, const void* lr_dev);
+/* ... and, in the same pass, the first n16[i] parameters of bucket i (the weight matrix the BF16 GEMMs read) are written as bf16 to
+ * w16[i] (NULL entry: none): the shadow is refreshed by the kernel that changes the master instead of a separate conversion pass */
+int okl_accum_update_multi16(okl_ctx* ctx, int count, void* const* w, void* const* gacc, const void* const* g, const size_t* n,
+                             void* const* w16, const size_t* n16, float lr, const void* lr_dev);
 /* optimizers.py:140-144: v = mu v - lr g ; w += v */
 int okl_sgd_update(okl_ctx* ctx, void* w, void* v, const void* g, size_t n, float lr, float momentum);
 /* optimizers.py:28-42 with t supplied by the caller (it increments per update call) */

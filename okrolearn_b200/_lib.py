@@ -146,6 +146,7 @@ SIGNATURES = {
     "okl_read_scalar": (_i, [_vp, _vp, _P(_f)]),
     "okl_accum_update": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _vp]),
     "okl_accum_update_multi": (_i, [_vp, _i, _P(_vp), _P(_vp), _P(_vp), _P(_sz), _f, _vp]),
+    "okl_accum_update_multi16": (_i, [_vp, _i, _P(_vp), _P(_vp), _P(_vp), _P(_sz), _P(_vp), _P(_sz), _f, _vp]),
     "okl_sgd_update": (_i, [_vp, _vp, _vp, _vp, _sz, _f, _f]),
     "okl_adam_update": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _i]),
     "okl_graph_begin": (_i, [_vp]),

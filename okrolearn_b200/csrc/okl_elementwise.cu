@@ -3,6 +3,7 @@
 // 128-bit accesses where alignment allows, grid-stride over a grid capped at a few waves of the 148 SMs, and
 // reduce with warp shuffles in a fixed order (deterministic).  Reference citations per entry point are in okl.h.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -674,6 +675,8 @@ struct MultiUpd {
   float* gacc[16];
   const float* g[16];
   unsigned long long n[16];
+  __nv_bfloat16* w16[16];                 // optional bf16 shadow of the first n16 parameters (the weights the BF16 GEMMs read)
+  unsigned long long n16[16];
 };
 // every parameter bucket of the network in one launch: blockIdx.y selects the bucket
 __global__ void accum_update_multi_kernel(const MultiUpd mu, float lr, const float* __restrict__ lr_dev) {
@@ -683,6 +686,8 @@ __global__ void accum_update_multi_kernel(const MultiUpd mu, float lr, const flo
   float* __restrict__ ga = mu.gacc[b];
   const float* __restrict__ g = mu.g[b];
   const size_t n = mu.n[b], n4 = n >> 2;
+  __nv_bfloat16* __restrict__ w16 = mu.w16[b];
+  const size_t n16_4 = mu.n16[b] >> 2;
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
   for (size_t j = i; j < n4; j += st) {
     float4 a = reinterpret_cast<float4*>(ga)[j], q = reinterpret_cast<const float4*>(g)[j], ww = reinterpret_cast<float4*>(w)[j];
@@ -690,6 +695,10 @@ __global__ void accum_update_multi_kernel(const MultiUpd mu, float lr, const flo
     ww.x -= lr * a.x; ww.y -= lr * a.y; ww.z -= lr * a.z; ww.w -= lr * a.w;
     reinterpret_cast<float4*>(ga)[j] = a;
     reinterpret_cast<float4*>(w)[j] = ww;
+    if (w16 && j < n16_4) {                 // the shadow is refreshed by the kernel that changes the master: no separate 6 B/param pass
+      __nv_bfloat162 lo = __floats2bfloat162_rn(ww.x, ww.y), hi = __floats2bfloat162_rn(ww.z, ww.w);
+      reinterpret_cast<uint2*>(w16)[j] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
   }
   for (size_t j = (n4 << 2) + i; j < n; j += st) { float a = ga[j] + g[j]; ga[j] = a; w[j] -= lr * a; }
 }
@@ -1614,9 +1623,19 @@ extern "C" int okl_accum_update(okl_ctx* ctx, void* w, void* gacc, const void* g
   return OKL_OK;
 }
 
+extern "C" int okl_accum_update_multi16(okl_ctx* ctx, int count, void* const* w, void* const* gacc, const void* const* g, const size_t* n,
+                                        void* const* w16, const size_t* n16, float lr, const void* lr_dev);
+
 extern "C" int okl_accum_update_multi(okl_ctx* ctx, int count, void* const* w, void* const* gacc, const void* const* g, const size_t* n,
                                       float lr, const void* lr_dev) {
+  return okl_accum_update_multi16(ctx, count, w, gacc, g, n, nullptr, nullptr, lr, lr_dev);
+}
+
+// the same, and bucket i's first n16[i] parameters (a multiple of 4) are also written as bf16 to w16[i] (NULL entries: no shadow)
+extern "C" int okl_accum_update_multi16(okl_ctx* ctx, int count, void* const* w, void* const* gacc, const void* const* g, const size_t* n,
+                                        void* const* w16, const size_t* n16, float lr, const void* lr_dev) {
   OKL_REQUIRE(ctx && (count == 0 || (w && gacc && g && n)), "NULL argument");
+  OKL_REQUIRE((w16 == nullptr) == (n16 == nullptr), "w16 and n16 go together");
   OKL_REQUIRE(count >= 0, "bad count");
   for (int base = 0; base < count; base += 16) {
     MultiUpd mu;
@@ -1625,6 +1644,10 @@ extern "C" int okl_accum_update_multi(okl_ctx* ctx, int count, void* const* w, v
     for (int i = 0; i < 16; i++) {
       int j = base + (i < c ? i : 0);
       mu.w[i] = (float*)w[j]; mu.gacc[i] = (float*)gacc[j]; mu.g[i] = (const float*)g[j]; mu.n[i] = i < c ? n[j] : 0;
+      mu.w16[i] = (w16 && i < c) ? (__nv_bfloat16*)w16[j] : nullptr;
+      mu.n16[i] = mu.w16[i] ? n16[j] : 0;
+      OKL_REQUIRE(mu.n16[i] % 4 == 0 && mu.n16[i] <= mu.n[i] && (reinterpret_cast<uintptr_t>(mu.w16[i]) & 7) == 0,
+                  "okl_accum_update_multi16: shadow extent must be a multiple of 4 inside the bucket, 8-byte aligned");
       OKL_REQUIRE(aligned16(mu.w[i]) && aligned16(mu.gacc[i]) && aligned16(mu.g[i]), "okl_accum_update_multi: buckets must be 16-byte aligned");
       if (mu.n[i] > nmax) nmax = mu.n[i];
     }

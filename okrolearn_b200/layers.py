@@ -157,6 +157,15 @@ class _ParamBucket:
         """bf16 shadow of parameter i, refreshed when the fp32 master changed (after every update)."""
         return self.tensors[i]._b16()
 
+    def _live_shadow(self):
+        """The weight tensor (parameter 0, at the bucket's start) if its bf16 shadow is current and can be rewritten in place by the
+        update kernel; None otherwise."""
+        t = self.tensors[0]
+        if (self.offs[0] == 0 and t.size % 4 == 0 and t.size > 0 and not t._b16_primary and getattr(t, "_bf16", None) is not None and
+                t._dev_valid and t._bf16_ver == (t._dev_ver, t._layout) and t._bf16.nbytes >= t.size * 2 and len(t._shape) == 2):
+            return t
+        return None
+
     def _sync_user_grads(self):
         """``layer.weights.grad = None`` / ``= ndarray`` by the user replaces the accumulator."""
         ctx = get_ctx()
@@ -247,13 +256,28 @@ def apply_pending_updates(layers):
         ga = (C.c_void_p * n)(*[b.gacc.ptr for b in bs])
         g = (C.c_void_p * n)(*[b.grad.ptr for b in bs])
         cnt = (C.c_size_t * n)(*[b.total for b in bs])
-        check(lib.okl_accum_update_multi(ctx.h, n, w, ga, g, cnt, lrf, lrp))
+        # BF16 mode: a weight matrix whose bf16 shadow is live (the GEMMs of this step read it) gets the shadow rewritten by the
+        # update kernel itself - no separate fp32 -> bf16 pass over the parameters after every step
+        shadowed = [b._live_shadow() if ctx.precision == _lib.BF16 else None for b in bs]
+        if any(t is not None for t in shadowed):
+            w16 = (C.c_void_p * n)(*[t._bf16.ptr if t is not None else None for t in shadowed])
+            n16 = (C.c_size_t * n)(*[t.size if t is not None else 0 for t in shadowed])
+            check(lib.okl_accum_update_multi16(ctx.h, n, w, ga, g, cnt, w16, n16, lrf, lrp))
+        else:
+            shadowed = [None] * n
+            check(lib.okl_accum_update_multi(ctx.h, n, w, ga, g, cnt, lrf, lrp))
+        for b, t16 in zip(bs, shadowed):
+            b._fresh_shadow = t16
     for b in bs:
         b._stepped = True
         for t, gv in zip(b.tensors, b.gviews):
             t._touch()
             gv._touch()
             t._grad = gv
+        t16 = getattr(b, "_fresh_shadow", None)
+        if t16 is not None:
+            t16._bf16_ver = (t16._dev_ver, t16._layout)         # written together with the master
+        b._fresh_shadow = None
         b._pending_lr = None
 
 
