@@ -106,6 +106,10 @@ int okl_gather_batch(okl_ctx* ctx, void* x_dst, const void* x_src, long long x_r
  * Gather-free parts: a NULL x_dst / t_dst skips that gather - its consumer reads the dataset rows through the index itself (the
  * *_rows_i32 arguments of okl_to_bf16_nxc, okl_conv_first_*, okl_mse_fwd_bwd_nxc_bf16); idx_dst (optional) receives the batch's
  * index slice at a fixed per-slot address for those consumers (and for graph replay). */
+/* Stream mode (dataset in page-locked host memory): a host copy of the NEXT okl_batch_prefetch's row indices (int32, valid until
+ * that call returns).  With it the rows are gathered by host threads into a page-locked staging ring and cross PCIe as ONE DMA copy
+ * per part, instead of a zero-copy gather kernel that competes with the step's kernels for SM resources. */
+int okl_batch_host_index(okl_ctx* ctx, const void* idx_host_i32);
 int okl_batch_prefetch(okl_ctx* ctx, int slot, void* x_dst, const void* x_src, long long x_row_elems, void* t_dst, const void* t_src,
                        long long t_row_elems, const void* idx_i32, long long rows, void* x_nxc_dst, int x_channels, int x_nxc_bf16,
                        void* idx_dst);

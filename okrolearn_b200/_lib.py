@@ -82,6 +82,7 @@ SIGNATURES = {
     "okl_unfold_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i]),
     "okl_fold_permute": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _i]),
     "okl_gather_batch": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll]),
+    "okl_batch_host_index": (_i, [_vp, _vp]),
     "okl_batch_prefetch": (_i, [_vp, _i, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _i, _i, _vp]),
     "okl_batch_wait": (_i, [_vp, _i]),
     "okl_loss_fetch_async": (_i, [_vp, _i, _vp]),

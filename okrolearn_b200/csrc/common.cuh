@@ -82,6 +82,10 @@ struct okl_ctx {
   unsigned loss_seq[2] = {0, 0};
   cudaEvent_t ev_flow[8] = {};
   unsigned long long flow_next = 0;
+  // stream mode: host copy of the next batch's row indices (set by okl_batch_host_index, consumed by the next okl_batch_prefetch) and
+  // the page-locked staging ring the host gathers the rows into ([inputs / targets][batch the host may run ahead])
+  const int* host_idx_next = nullptr;
+  void* stage[2][OKL_FLOW_DEPTH] = {}; size_t stage_bytes[2][OKL_FLOW_DEPTH] = {};
   int pdl = 0;                          // programmatic dependent launch: 0 off (default: measured no gain), 1 on except while an aux lane is forked, 2 always
 };
 

@@ -1,6 +1,11 @@
 // Context, memory pool, host<->device transfer with dtype conversion, CUDA graphs, timing and the
 // NCCL data-parallel exchange of libokl_b200.  See include/okl.h for the contract of each entry point.
 #include "common.cuh"
+#include <mutex>
+#include <vector>
+#include <functional>
+#include <condition_variable>
+#include <thread>
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -154,6 +159,116 @@ static int ensure_pipeline(okl_ctx* ctx) {
   return OKL_OK;
 }
 
+// ---- stream mode: the batch crosses PCIe on the COPY ENGINES.  The gather kernel reads page-locked host memory zero-copy - and needs
+// SM resources to do so: beside the persistent tensor-core kernels of a step (384 threads x 168 registers = the whole register file
+// of an SM) none of its blocks becomes resident, so it ran BETWEEN them and delayed them by the PCIe time of a batch (cifar6, batch
+// 1024: 1.45 ms per step end to end against 1.24 ms device-resident, independent of the step count and of the loss read-back;
+// capping those kernels at 128 registers to make room cost more than it gave).  With the batch's row indices also known on the host,
+// a few host threads gather the rows into a page-locked staging ring (one entry per batch the host may run ahead of the device) and ONE
+// cudaMemcpyAsync per part moves them: DMA, no SM involved.  The gather of batch s+1 runs on the host while the device computes step s.
+extern "C" int okl_batch_host_index(okl_ctx* ctx, const void* idx_host_i32) {
+  OKL_REQUIRE(ctx, "ctx is NULL");
+  ctx->host_idx_next = (const int*)idx_host_i32;
+  return OKL_OK;
+}
+
+static bool is_host_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+namespace {
+// a handful of persistent worker threads for row gathers (std::thread creation per batch would cost as much as the gather)
+class HostPool {
+ public:
+  explicit HostPool(int n) : stop_(false), gen_(0), pending_(0) {
+    for (int i = 0; i < n; i++) workers_.emplace_back([this, i] { run(i); });
+  }
+  ~HostPool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; gen_++; }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  int size() const { return (int)workers_.size(); }
+  // fn(worker) on every worker, returns when all are done
+  void run_all(const std::function<void(int)>& fn) {
+    std::unique_lock<std::mutex> lk(mu_);
+    fn_ = &fn; pending_ = (int)workers_.size(); gen_++;
+    cv_.notify_all();
+    done_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+ private:
+  void run(int id) {
+    unsigned long long seen = 0;
+    for (;;) {
+      const std::function<void(int)>* f;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        f = fn_;
+      }
+      if (f) (*f)(id);
+      { std::lock_guard<std::mutex> lk(mu_); if (--pending_ == 0) done_.notify_all(); }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  bool stop_;
+  unsigned long long gen_;
+  int pending_;
+};
+
+HostPool* host_pool() {
+  static HostPool* pool = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int n = 6;
+    if (const char* e = getenv("OKL_HOST_GATHER_THREADS")) n = atoi(e);
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && n > hw - 1) n = hw - 1;
+    if (n >= 1) pool = new HostPool(n);
+  });
+  return pool;
+}
+}  // namespace
+
+// rows idx[0 .. rows) of the host array src (row_bytes each) -> page-locked staging -> dst with one DMA copy; OKL_OK, or a negative
+// value when staging is unavailable (the caller falls back to the gather kernel)
+static int staged_gather_rows(okl_ctx* ctx, int ring, int part, void* dst, const void* src, size_t row_bytes, const int* idx, long long rows) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("OKL_DMA_GATHER"); enabled = e ? atoi(e) : 1; }
+  const size_t bytes = row_bytes * (size_t)rows;
+  if (!enabled || bytes > (size_t(256) << 20)) return -1;
+  void*& stg = ctx->stage[part][ring];
+  size_t& cap = ctx->stage_bytes[part][ring];
+  if (cap < bytes) {
+    if (stg) cudaFreeHost(stg);
+    stg = nullptr; cap = 0;
+    if (cudaMallocHost(&stg, bytes) != cudaSuccess) { cudaGetLastError(); stg = nullptr; return -1; }
+    cap = bytes;
+  }
+  char* out = (char*)stg;
+  const char* in = (const char*)src;
+  HostPool* pool = bytes >= (size_t(1) << 20) ? host_pool() : nullptr;
+  if (pool) {
+    const int nw = pool->size();
+    pool->run_all([&](int w) {
+      const long long r0 = rows * w / nw, r1 = rows * (w + 1) / nw;
+      for (long long i = r0; i < r1; i++) memcpy(out + (size_t)i * row_bytes, in + (size_t)idx[i] * row_bytes, row_bytes);
+    });
+  } else {
+    for (long long i = 0; i < rows; i++) memcpy(out + (size_t)i * row_bytes, in + (size_t)idx[i] * row_bytes, row_bytes);
+  }
+  if (cudaMemcpyAsync(dst, stg, bytes, cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return OKL_OK;
+}
+
 extern "C" int okl_batch_prefetch(okl_ctx* ctx, int slot, void* x_dst, const void* x_src, long long x_row_elems, void* t_dst,
                                   const void* t_src, long long t_row_elems, const void* idx, long long rows, void* x_nxc_dst, int x_channels,
                                   int x_nxc_bf16, void* idx_dst) {
@@ -175,7 +290,21 @@ extern "C" int okl_batch_prefetch(okl_ctx* ctx, int slot, void* x_dst, const voi
   // the copy stream, instead of at the head of the step's critical path.  As bf16 it is produced straight from the dataset rows
   // (through the index) when no fp32 copy of the batch is wanted (x_dst NULL).
   const bool nxc = x_nxc_dst && x_channels > 1 && rows > 0 && x_row_elems % x_channels == 0;
-  s = okl_gather_batch(ctx, x_dst, x_src, x_row_elems, t_dst, t_src, t_row_elems, idx, rows);
+  const int* hidx = ctx->host_idx_next;
+  ctx->host_idx_next = nullptr;
+  bool x_done = false;
+  // stream mode with host-side indices, batches of at least 1 MB (small batches belong to short steps of small kernels, which the
+  // gather kernel runs beside without trouble, and the host has only tens of microseconds per step there): staged DMA
+  if (hidx && rows > 0 && (size_t)x_row_elems * 4 * (size_t)rows >= (size_t(1) << 20)) {
+    // ring entry fi is free: the flow-control wait above covered the copy that last read it
+    if (x_dst && x_src && x_row_elems > 0 && is_host_ptr(x_src) &&
+        staged_gather_rows(ctx, fi, 0, x_dst, x_src, (size_t)x_row_elems * 4, hidx, rows) == OKL_OK)
+      x_done = true;                                         // the kernel below skips this part
+    if (t_dst && t_src && t_row_elems > 0 && is_host_ptr(t_src) &&
+        staged_gather_rows(ctx, fi, 1, t_dst, t_src, (size_t)t_row_elems * 4, hidx, rows) == OKL_OK)
+      t_dst = nullptr;
+  }
+  s = okl_gather_batch(ctx, x_done ? nullptr : x_dst, x_src, x_row_elems, t_dst, t_src, t_row_elems, idx, rows);
   if (s == OKL_OK && nxc) {
     if (x_nxc_bf16) s = okl_to_bf16_nxc(ctx, x_dst ? x_dst : x_src, x_dst ? nullptr : idx, x_nxc_dst, (int)rows, x_channels, x_row_elems / x_channels);
     else if (x_dst) s = okl_permute(ctx, x_nxc_dst, x_dst, (int)rows, x_channels, x_row_elems / x_channels, OKL_NCX);
@@ -267,6 +396,8 @@ extern "C" int okl_ctx_destroy(okl_ctx* ctx) {
   okl_comm_destroy(ctx);
   for (auto& kv : ctx->live) cudaFree(kv.first);
   if (ctx->leaf_scratch) cudaFree(ctx->leaf_scratch);
+  for (int p = 0; p < 2; p++)
+    for (int i = 0; i < OKL_FLOW_DEPTH; i++) if (ctx->stage[p][i]) cudaFreeHost(ctx->stage[p][i]);
   if (ctx->workspace) cudaFree(ctx->workspace);
   if (ctx->staging) cudaFree(ctx->staging);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);

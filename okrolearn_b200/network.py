@@ -607,10 +607,13 @@ class NeuralNetwork:
             rows = min(b0 + batch_size, num_samples) - b0
             sl = st.slots[batch & 1]
             x_skip = x_rows or (x_b16 and bf16_stack)     # bf16 channels-last batch converted straight from the dataset rows
+            if stream and host_idx[0] is not None:        # rows move on the copy engines: they need the indices on the host too
+                check(lib.okl_batch_host_index(ctx.h, host_idx[0] + b0 * 4))
             check(lib.okl_batch_prefetch(ctx.h, batch & 1, None if x_skip else sl.xbuf.ptr, x_src, row_elems, None if t_rows else sl.tin.ptr, t_src,
                                          t_row, idx_dev.ptr + b0 * 4, rows, sl.xnxc.ptr if x_nxc else None, sample_shape[0] if x_nxc else 0,
                                          1 if x_b16 else 0, sl.idx.ptr if (x_rows or t_rows) else None))
 
+        host_idx = [None]                                 # address of the epoch's permutation in page-locked host memory (int32)
         lossf = C.c_float()
 
         def collect(slot_idx):
@@ -646,6 +649,7 @@ class NeuralNetwork:
             np.random.shuffle(indices)
             perm_total = perm_total[indices]
             np.copyto(pin[1][:num_samples], perm_total, casting="unsafe")
+            host_idx[0] = pin[1].ctypes.data if pin[1].dtype == np.int32 else None
             if num_samples:
                 check(lib.okl_h2d_async_raw(ctx.h, idx_dev.ptr, pin[1].ctypes.data, num_samples * 4))
 
