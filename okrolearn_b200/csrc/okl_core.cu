@@ -244,7 +244,7 @@ static int staged_gather_rows(okl_ctx* ctx, int ring, int part, void* dst, const
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("OKL_DMA_GATHER"); enabled = e ? atoi(e) : 1; }
   const size_t bytes = row_bytes * (size_t)rows;
-  if (!enabled || bytes > (size_t(256) << 20)) return -1;
+  if (!enabled || bytes > (size_t(64) << 20)) return -1;   // beyond that the host gather itself (memory-bound threads) would be the bottleneck
   void*& stg = ctx->stage[part][ring];
   size_t& cap = ctx->stage_bytes[part][ring];
   if (cap < bytes) {

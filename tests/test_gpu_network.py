@@ -492,3 +492,37 @@ def test_epoch_hook_assignment_survives_graph_replay(okl):
                   okl.CrossEntropyLoss())
         res[mode] = (d1.weights.data.copy(), d2.weights.data.copy())
     assert rel_err(res["graph"][0], res["eager"][0]) < 1e-6 and rel_err(res["graph"][1], res["eager"][1]) < 1e-6
+
+
+def test_stream_mode_staged_gather_matches_resident_dataset(okl):
+    """Batches of >= 1 MB in stream mode cross PCIe through the host-gathered staging ring (okl_batch_host_index + one DMA copy per part)
+    instead of the zero-copy gather kernel: two epochs incl. a short last batch and a wrap of the staging ring must leave exactly the
+    parameters, losses and reordered dataset of the device-resident run (same seed, same shuffles, FP32 mode: bit-identical kernels)."""
+    rng = np.random.default_rng(5)
+    n, feat, classes, B = 1100, 4096, 10, 100               # 100 x 4096 x 4 B = 1.6 MB per batch, 11 batches per epoch > ring of 8
+    X = rng.standard_normal((n, feat)).astype(np.float32)
+    T = rng.integers(0, classes, n).astype(np.int32)
+    W1, W2 = rng.standard_normal((feat, 32)) * 0.02, rng.standard_normal((32, classes)) * 0.1
+    results = []
+    for stream in (False, True):
+        net = okl.NeuralNetwork()
+        d1, d2 = okl.DenseLayer(feat, 32), okl.DenseLayer(32, classes)
+        d1.weights.data, d2.weights.data = W1.copy(), W2.copy()
+        for l in (d1, okl.TanhActivationLayer(), d2, okl.SoftmaxActivationLayer()):
+            net.add(l)
+        net.stream_inputs, net.sync_loss_every_step = stream, stream
+        if stream:
+            pX, pT = okl.pinned_empty(X.shape, np.float32), okl.pinned_empty(T.shape, np.int32)
+            pX[...], pT[...] = X, T
+            tX, tT = okl.Tensor.wrap(pX), okl.Tensor.wrap(pT)
+        else:
+            tX, tT = okl.Tensor(X.copy()), okl.Tensor(T.copy())
+        np.random.seed(3)
+        losses = net.train(tX, tT, epochs=2, lr_scheduler=okl.LearningRateScheduler(0.05), optimizer=okl.SGDOptimizer(lr=0.05), batch_size=B,
+                           loss_function=okl.CrossEntropyLoss())
+        results.append((np.asarray(losses), d1.weights.data.copy(), d2.weights.data.copy(), np.asarray(tX.data).copy(), np.asarray(tT.data).copy(),
+                        list(net.last_step_losses)))
+    a, b = results
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[4].astype(int), b[4].astype(int))
+    assert len(b[5]) == 2 * 11                               # every step's loss reached the host
