@@ -377,3 +377,29 @@ def test_conv2_wgrad_kernels_vs_oracle(okl, monkeypatch, env, N, Cc, sp, Oc, k, 
                 assert rel_err(db.data, dbo.reshape(-1)) < 2e-3
     finally:
         okl.set_precision("fp32")
+
+
+@pytest.mark.parametrize("N,C,sp,Oc,k,p", [(3, 16, (4, 4), 24, 3, 1), (2, 24, (6, 5), 40, 3, 1), (2, 8, (3, 20), 8, 3, 1)])
+def test_partial_chunk_shapes_the_tensor_core_kernels_reject_still_match(okl, N, C, sp, Oc, k, p):
+    """BF16 mode, channel counts that are multiples of 8, but an image too small for the gradient-slab weight gradient (rows narrower
+    than 8 pixels / fewer than 16 pixels per tile row group): the layer is planned channels-last and must fall back to the FFMA
+    implicit GEMM with identical semantics (FP32 accuracy)."""
+    okl.set_precision("bf16")
+    try:
+        rng = np.random.default_rng(N + C + Oc)
+        x = rng.standard_normal((N, C) + sp).astype(np.float32)
+        W = rng.standard_normal((Oc, C, k, k)) * 0.1
+        b = rng.standard_normal((Oc, 1)) * 0.1
+        lay = okl.Conv2DLayer(C, Oc, k, 1, p)
+        lay.filters.data, lay.biases.data = W.copy(), b.copy()
+        y = lay.forward(okl.Tensor(x))
+        x64 = x.astype(np.float64)
+        yo = O.conv_forward_fast(x64, W, b, 1, p, dtype=np.float64)
+        assert rel_err(y.data, yo) < 1.5e-2
+        g = rng.standard_normal(yo.shape).astype(np.float32)
+        dX = lay.backward(okl.Tensor(g), 0.05)
+        dW, db, dXo = O.conv_backward_fast(x64, W, g.astype(np.float64), 1, p)
+        assert rel_err(dX.data, dXo) < 1.5e-2
+        assert rel_err(lay.filters.grad, dW) < 1.5e-2 and rel_err(lay.biases.grad, db) < 1.5e-2
+    finally:
+        okl.set_precision("fp32")
