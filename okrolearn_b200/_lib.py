@@ -193,6 +193,11 @@ def check(status: int):
         raise ValueError(msg)
     if status == OKL_ERR_OOM:
         raise MemoryError(msg)
+    low = msg.lower()
+    if any(k in low for k in ("unspecified launch failure", "illegal memory access", "illegal instruction", "launch failed", "trap",
+                              "device-side assert", "misaligned address")):
+        # a kernel fault (incl. the bounded-wait traps of the tensor-core kernels) poisons the CUDA context: every later call fails too
+        msg += "  [the CUDA context of this process is no longer usable after a kernel fault: restart the process]"
     raise RuntimeError(msg)
 
 
