@@ -382,6 +382,16 @@ int okl_conv_first_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void* x, co
 int okl_conv_first_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* x_rows_i32, const void* g16, void* dW, void* db);
 /* filter gradient (okl.py:739-741, 869-871) and, optionally, the bias gradient (okl.py:721, 870 with repair R2): dW fp32 in the
  * reference layout (O, C, *k); both operands channels-last bf16; split-K over the SMs with a fixed-order second stage. */
+/* First layer with the horizontal taps pre-expanded into channels (C * KW <= 16, 2..4 filter rows, unit stride; okl.py:790-813 /
+ * 869-871): okl_conv_vexp_expand writes xe16[n, h, ow, c * KW + v] = x[n, c, h, ow + v - pw] (bf16, 16 channels) from the fp32
+ * (N, C, H, W) images (optionally rows x_rows_i32[n] of a dataset); okl_conv_vexp_desc gives the channels-last convolution the layer
+ * then is (16 channels, KH x 1 filter) for okl_conv2_fprop / okl_conv2_wgrad; okl_conv_vexp_bank its filter bank (O, KH, 16) from the
+ * (O, C, KH, KW) masters; okl_conv_vexp_dw maps that convolution's filter gradient (O, 16, KH, 1) back to (O, C, KH, KW). */
+int okl_conv_vexp_supported(okl_ctx* ctx, const okl_conv_desc* d);
+int okl_conv_vexp_desc(okl_ctx* ctx, const okl_conv_desc* d, okl_conv_desc* out);
+int okl_conv_vexp_expand(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* x_rows_i32, void* xe16);
+int okl_conv_vexp_bank(okl_ctx* ctx, const okl_conv_desc* d, const void* W, void* w2e16);
+int okl_conv_vexp_dw(okl_ctx* ctx, const okl_conv_desc* d, const void* dWe, void* dW);
 int okl_conv2_wgrad_supported(okl_ctx* ctx, const okl_conv_desc* d);
 int okl_conv2_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* x16, const void* g16, void* dW, void* db);
 

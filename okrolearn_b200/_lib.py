@@ -118,6 +118,11 @@ SIGNATURES = {
     "okl_conv_first_supported": (_i, [_vp, _P(ConvDesc)]),
     "okl_conv_first_fprop": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "okl_conv_first_wgrad": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
+    "okl_conv_vexp_supported": (_i, [_vp, _P(ConvDesc)]),
+    "okl_conv_vexp_desc": (_i, [_vp, _P(ConvDesc), _P(ConvDesc)]),
+    "okl_conv_vexp_expand": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp]),
+    "okl_conv_vexp_bank": (_i, [_vp, _P(ConvDesc), _vp, _vp]),
+    "okl_conv_vexp_dw": (_i, [_vp, _P(ConvDesc), _vp, _vp]),
     "okl_conv2_wgrad_supported": (_i, [_vp, _P(ConvDesc)]),
     "okl_conv2_wgrad": (_i, [_vp, _P(ConvDesc), _vp, _vp, _vp, _vp]),
     "okl_tc_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _i]),

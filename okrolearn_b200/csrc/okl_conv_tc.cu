@@ -48,6 +48,7 @@ struct ConvTcParams {
   int relu;
   const __nv_bfloat16* mask;           // optional, indexed like the output: out = 0 where mask <= 0 (backward of a preceding ReLU)
   int want_f32, want_b16;
+  int diag;                            // probe only (OKL_CT_DIAG): 1 = epilogue does nothing, 2 = no MMAs, 4 = activation operand loaded once per stage
   unsigned long long* dbg;
 };
 
@@ -57,6 +58,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmY32, const ConvTcParams p) {
   using Cfg = CtCfg<BN>;
   constexpr int CS = PAIR ? 2 : 1;
+  // filter-tile ring: in pair mode a CTA holds only half of every tile's rows, so the same shared memory gives twice the stages.
+  // (Probes, scripts/exp/ct_diag.py + commit_bench.cu: with no MMAs, no epilogue and no loads at all the 64 -> 64 layer still takes 57 of
+  // its 94 us - the single issuing thread pays ~200-300 cycles per tcgen05.commit and ~85 per mbarrier wait, 12 of each per tile; the
+  // ring depth is not what limits it.)
+  constexpr int NBK = PAIR ? 2 * Cfg::NB : Cfg::NB;
+  constexpr int BST = PAIR ? Cfg::B_STAGE / 2 : Cfg::B_STAGE;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -66,11 +73,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + CT_NA;
   uint64_t* b_full = a_empty + CT_NA;
-  uint64_t* b_empty = b_full + Cfg::NB;
-  uint64_t* t_full = b_empty + Cfg::NB;
+  uint64_t* b_empty = b_full + NBK;
+  uint64_t* t_full = b_empty + NBK;
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-  volatile uint32_t* loop_par = reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  volatile uint32_t* loop_par = reinterpret_cast<volatile uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 384);   // up to 34 barriers + the TMEM slot before it
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
 
   const int warp = threadIdx.x >> 5;
@@ -85,7 +92,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < CT_NA; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < Cfg::NB; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < NBK; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     // pair mode: the even CTA's accumulator-free barrier collects the epilogue warps of BOTH CTAs
     for (int a = 0; a < 2; a++) { mbar_init(&t_full[a], 1); mbar_init(&t_empty[a], PAIR ? 16 : 8); }
     fence_barrier_init();
@@ -102,6 +109,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     loop_par[3] = (uint32_t)p.KH;
     loop_par[4] = (uint32_t)(p.cblocks * p.KW);
     loop_par[5] = p.dbg ? 1u : 0u;
+    loop_par[6] = (uint32_t)p.diag;
   }
   tc_fence_before();
   __syncthreads();
@@ -121,8 +129,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       int st = 0;
       uint32_t ph_ = 0;
+      int nloads = 0;
       auto load = [&](int c0, int c1, int c2, int c3) {
         mbar_wait(&a_empty[st], ph_ ^ 1);
+        if ((p.diag & 4) && nloads++ >= CT_NA) {
+          if (!PAIR || crank == 0) mbar_arrive(&a_full[st]);
+          if (++st == CT_NA) { st = 0; ph_ ^= 1; }
+          return;
+        }
         if (PAIR) {
           if (crank == 0) mbar_expect_tx(&a_full[st], 2 * p.a_bytes);       // both CTAs' boxes are counted on the even CTA's barrier
           tma_load_4d_pair(&tmA, &a_full[st], sA + st * CT_A_STAGE, c0, c1, c2, c3);
@@ -159,15 +173,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int v = 0; v < p.KW; v++) {
             int kcol = v * p.C + cb * 64;                 // tap (u, v) -> column (u * KW + v) * C + cb * 64 of the K-major bank
             for (int u = 0; u < p.KH; u++, kcol += p.KW * p.C) {
+              if (p.diag & 8) continue;                    // probe: no filter-tile ring at all (neither loads nor its barriers)
               mbar_wait(&b_empty[st], ph_ ^ 1);
               if (PAIR) {
                 if (crank == 0) mbar_expect_tx(&b_full[st], Cfg::B_STAGE);
-                tma_load_2d_pair(&tmB, &b_full[st], sB + st * Cfg::B_STAGE, kcol, n_off);
+                tma_load_2d_pair(&tmB, &b_full[st], sB + st * BST, kcol, n_off);
               } else {
                 mbar_expect_tx(&b_full[st], Cfg::B_STAGE);
-                tma_load_2d(&tmB, &b_full[st], sB + st * Cfg::B_STAGE, kcol, n_off);
+                tma_load_2d(&tmB, &b_full[st], sB + st * BST, kcol, n_off);
               }
-              if (++st == Cfg::NB) { st = 0; ph_ ^= 1; }
+              if (++st == NBK) { st = 0; ph_ ^= 1; }
             }
           }
         }
@@ -181,7 +196,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (crank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc(1, false, false, PAIR ? 256 : 128, BN);
       constexpr uint32_t HI = TC_DESC_HI_SW128;
-      constexpr uint32_t A16 = CT_A_STAGE >> 4, B16 = Cfg::B_STAGE >> 4;
+      constexpr uint32_t A16 = CT_A_STAGE >> 4, B16 = BST >> 4;
       const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);      // LBO = 16 B (unused by K-major swizzled operands)
       const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t af0 = smem_u32(a_full), ae0 = smem_u32(a_empty), bf0 = smem_u32(b_full), be0 = smem_u32(b_empty);
@@ -194,6 +209,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t sa = 0, sb = 0, acc = 0;
       uint32_t pa = 0, pb = 0, pacc = 0;
       bool want_ts = loop_par[5] != 0;                     // debug timeline: when the first activation slab landed
+      const bool nomma = (loop_par[6] & 2u) != 0, nobring = (loop_par[6] & 8u) != 0;
       auto commit = [&](uint32_t bar) {
         if (PAIR) umma_commit_pair_a(bar);
         else umma_commit_a(bar);
@@ -220,16 +236,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               a_lo = a_lo0 + sa * A16;
               mbar_wait_a(af0 + sa * 8, pa);
             }
-            mbar_wait_a(bf0 + sb * 8, pb);
+            if (!nobring) mbar_wait_a(bf0 + sb * 8, pb);
             const uint32_t al = a_lo + (uint32_t)u * row16;
+            if (!nomma) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-              umma_bf16_words<PAIR>(d0, al + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), HI, idesc, k ? 1u : accum);
-              umma_bf16_words<PAIR>(d0 + BN, al + sub16 + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), HI, idesc, k ? 1u : accum);
+              for (int k = 0; k < 4; k++) {
+                umma_bf16_words<PAIR>(d0, al + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), HI, idesc, k ? 1u : accum);
+                umma_bf16_words<PAIR>(d0 + BN, al + sub16 + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), HI, idesc, k ? 1u : accum);
+              }
             }
             accum = 1;
-            commit(be0 + sb * 8);
-            if (++sb == (uint32_t)Cfg::NB) { sb = 0; pb ^= 1; }
+            if (!nobring) commit(be0 + sb * 8);
+            if (++sb == (uint32_t)NBK) { sb = 0; pb ^= 1; }
             if (!slab) {
               commit(ae0 + sa * 8);
               if (++sa == (uint32_t)CT_NA) { sa = 0; pa ^= 1; }
@@ -279,7 +297,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.dbg && threadIdx.x == 128 && blockIdx.x == 0 && dbg_tile < 24) p.dbg[148 * 8 + 2 * dbg_tile] = gtime();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN + s * BN);
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 64; ch++) {
+      for (int ch = 0; ch < ((p.diag & 1) ? 0 : BN / 64); ch++) {
         if (p.mask && ch > 0) {
 #pragma unroll
           for (int j = 0; j < 8; j++)
@@ -541,6 +559,7 @@ int conv_tc_run(okl_ctx* ctx, const void* x16, int N, int H, int W, int Cc, cons
   p.RN = 32 / (p.TW * p.RH);
   p.bias = bias; p.relu = relu; p.mask = (const __nv_bfloat16*)mask16;
   p.want_f32 = y ? 1 : 0; p.want_b16 = y16 ? 1 : 0;
+  p.diag = ct_env("OKL_CT_DIAG", 0);
   p.dbg = (unsigned long long*)ctx->tc_dbg;
   // CTA pairs (cta_group::2): two CTAs share every filter tile (each holds half of its rows); needs an even number of pixel tiles
   // measured (batch 1024, us, pair vs single): 64->64 fprop 98 vs 120, dgrad 123 vs 160; 128->128 58 vs 70 (1 322 TFLOP/s), 68 vs 82;
@@ -1872,5 +1891,126 @@ extern "C" int okl_conv_first_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const 
   const int total = (p.K + 1) * p.O;
   conv_first_wgrad_reduce<<<(total * 32 + 255) / 256, 256, 0, ctx->stream>>>(p.partial, (float*)dW, (float*)db, p.O, opad, p.K, KP, grid);
   OKL_LAUNCHED(ctx, "conv_first_wgrad_reduce");
+  return OKL_OK;
+}
+
+// ================================================================================================ first layer, horizontal taps pre-expanded
+// Conv2DLayer(3, 64, 3, 1, 1) on the input images (okl.py:790-813 / 869-871) once more.  The small-K kernels above build the im2col
+// operand of every pixel tile in software (~600 instructions per pixel and tile: 61 + 70 us at batch 1024, issue-bound at 0.32-0.37 of
+// HBM).  With C . KW <= 16 the horizontal taps fit the channel dimension instead: ONE memory-bound pass writes
+//     xe[n, h, ow, c * KW + v] = x[n, c, h, ow + v - pw]        (bf16, channels-last, 16 channels of which C . KW are real)
+// and the layer becomes an ordinary channels-last convolution with 16 input channels, a KH x 1 filter and padding (ph, 0) - the
+// TMA-fed implicit GEMM (conv_tc_kernel: one 64-channel box per pixel, zero-filled past channel 16) and the gradient-slab weight
+// gradient take it as they take any layer with a partial channel chunk; bias gradient from the ones slot.  Nothing is gathered per tap.
+// filters: w2e[o][u][c * KW + v] = bf16(W[o][c][u][v]); dW[o][c][u][v] = dWe[o][c * KW + v][u].
+namespace {
+
+constexpr int VX_C = 16;
+
+__global__ void vexp_expand_kernel(const float* __restrict__ x, const int* __restrict__ rows, uint4* __restrict__ xe, int N, int C, int H, int W, int OW, int KW,
+                                   int pw) {
+  // one thread per output pixel: 16 bf16 = two 16-byte stores; the reads of a warp are KW . C shifted, coalesced row segments
+  const size_t total = (size_t)N * H * OW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(i % OW);
+    const size_t r = i / OW;
+    const int h = (int)(r % H), n = (int)(r / H);
+    const size_t row = rows ? (size_t)__ldg(rows + n) : (size_t)n;
+    const float* src = x + (row * C * H + h) * (size_t)W;
+    float f[VX_C];
+#pragma unroll
+    for (int k = 0; k < VX_C; k++) f[k] = 0.f;
+    for (int c = 0; c < C; c++)
+      for (int v = 0; v < KW; v++) {
+        const int iw = ow + v - pw;
+        if (iw >= 0 && iw < W) f[c * KW + v] = __ldg(src + (size_t)c * H * W + iw);
+      }
+    uint32_t pk[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+      pk[k] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    xe[2 * i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    xe[2 * i + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}
+
+__global__ void vexp_bank_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ w2e, int O, int C, int KH, int KW) {
+  const int total = O * KH * VX_C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ce = i % VX_C, u = (i / VX_C) % KH, o = i / (VX_C * KH);
+    const int c = ce / KW, v = ce - c * KW;
+    w2e[i] = __float2bfloat16(c < C ? W[(((size_t)o * C + c) * KH + u) * KW + v] : 0.f);
+  }
+}
+
+__global__ void vexp_dw_kernel(const float* __restrict__ dWe, float* __restrict__ dW, int O, int C, int KH, int KW) {
+  const int total = O * C * KH * KW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int v = i % KW, u = (i / KW) % KH, c = (i / (KW * KH)) % C, o = i / (KW * KH * C);
+    dW[i] = dWe[((size_t)o * VX_C + c * KW + v) * KH + u];
+  }
+}
+
+// the channels-last convolution the layer turns into
+bool vexp_desc(const okl_conv_desc* d, okl_conv_desc& e) {
+  if (d->nd != 2 || d->s[0] != 1 || d->s[1] != 1 || d->x_layout != OKL_NCX || d->y_layout != OKL_NXC) return false;
+  if (d->C < 1 || d->C * d->k[1] > VX_C || d->k[0] < 2 || d->k[0] > 4 || d->k[1] < 1 || d->p[1] > d->k[1] - 1 || d->N < 1) return false;
+  const int OW = d->in[1] + 2 * d->p[1] - d->k[1] + 1;
+  if (OW < 1) return false;
+  e = *d;
+  e.C = VX_C;
+  e.in[1] = OW; e.k[1] = 1; e.p[1] = 0;
+  e.x_layout = OKL_NXC;
+  return true;
+}
+
+}  // namespace
+
+extern "C" int okl_conv_vexp_supported(okl_ctx* ctx, const okl_conv_desc* d) {
+  if (!ctx || !d || ct_env("OKL_CONV_VEXP", 1) == 0) return 0;
+  okl_conv_desc e;
+  if (!vexp_desc(d, e) || !ct_supported(ctx, &e)) return 0;
+  GsPlan gp;
+  return (gs_plan(ctx, &e, true, gp) && gp.db_fused) ? 1 : 0;
+}
+
+// the derived channels-last descriptor (16 input channels, KH x 1 filter) for okl_conv2_fprop / okl_conv2_wgrad
+extern "C" int okl_conv_vexp_desc(okl_ctx* ctx, const okl_conv_desc* d, okl_conv_desc* out) {
+  OKL_REQUIRE(ctx && d && out, "NULL argument");
+  OKL_REQUIRE(vexp_desc(d, *out), "okl_conv_vexp_desc: unsupported shape / layout");
+  return OKL_OK;
+}
+
+// xe16 (N, H, OW, 16) bf16 from x (N, C, H, W) fp32 (optionally rows x_rows_i32[n] of a dataset)
+extern "C" int okl_conv_vexp_expand(okl_ctx* ctx, const okl_conv_desc* d, const void* x, const void* x_rows_i32, void* xe16) {
+  OKL_REQUIRE(ctx && d && x && xe16, "NULL argument");
+  okl_conv_desc e;
+  OKL_REQUIRE(vexp_desc(d, e), "okl_conv_vexp_expand: unsupported shape / layout");
+  const size_t total = (size_t)d->N * d->in[0] * e.in[1];
+  vexp_expand_kernel<<<okl_grid_1d(ctx, total, 256, 16), 256, 0, ctx->stream>>>((const float*)x, (const int*)x_rows_i32, (uint4*)xe16, d->N, d->C, d->in[0], d->in[1],
+                                                                               e.in[1], d->k[1], d->p[1]);
+  OKL_LAUNCHED(ctx, "conv_vexp_expand");
+  return OKL_OK;
+}
+
+// w2e16 (O, KH, 16) bf16: the K-major filter bank of the derived convolution
+extern "C" int okl_conv_vexp_bank(okl_ctx* ctx, const okl_conv_desc* d, const void* W, void* w2e16) {
+  OKL_REQUIRE(ctx && d && W && w2e16, "NULL argument");
+  okl_conv_desc e;
+  OKL_REQUIRE(vexp_desc(d, e), "okl_conv_vexp_bank: unsupported shape / layout");
+  vexp_bank_kernel<<<okl_grid_1d(ctx, (size_t)d->O * d->k[0] * VX_C, 256), 256, 0, ctx->stream>>>((const float*)W, (__nv_bfloat16*)w2e16, d->O, d->C, d->k[0], d->k[1]);
+  OKL_LAUNCHED(ctx, "conv_vexp_bank");
+  return OKL_OK;
+}
+
+// dW (O, C, KH, KW) fp32 from the derived convolution's filter gradient dWe (O, 16, KH, 1)
+extern "C" int okl_conv_vexp_dw(okl_ctx* ctx, const okl_conv_desc* d, const void* dWe, void* dW) {
+  OKL_REQUIRE(ctx && d && dWe && dW, "NULL argument");
+  okl_conv_desc e;
+  OKL_REQUIRE(vexp_desc(d, e), "okl_conv_vexp_dw: unsupported shape / layout");
+  vexp_dw_kernel<<<okl_grid_1d(ctx, (size_t)d->O * d->C * d->k[0] * d->k[1], 256), 256, 0, ctx->stream>>>((const float*)dWe, (float*)dW, d->O, d->C, d->k[0], d->k[1]);
+  OKL_LAUNCHED(ctx, "conv_vexp_dw");
   return OKL_OK;
 }

@@ -17,6 +17,10 @@ from .tensor import Tensor, _DevBuf, _numel
 _ALIGN = 64          # floats: parameter sub-tensors start on 256-byte boundaries inside a bucket
 # BF16 mode: tensors between tensor-core layers are stored as channels-last bf16 only (OKL_BF16_ONLY=0 restores fp32 + bf16 shadow)
 _BF16_ONLY = __import__("os").environ.get("OKL_BF16_ONLY", "1") != "0"
+# first layer with the horizontal taps expanded into channels (okl_conv_vexp_*): parity-tested, but measured SLOWER than the small-K
+# kernels at the CIFAR shape (expand 25 + fprop 97 + wgrad 63 + remap 6 us against 61 + 70 us: the implicit-GEMM kernel has a per-tile
+# floor of ~2.5 us whatever the reduction length - see DESIGN.md) - off unless asked for
+_VEXP = __import__("os").environ.get("OKL_CONV_VEXP_LAYER", "0") != "0"
 _ANY_C = __import__("os").environ.get("OKL_CT_ANYC", "1") != "0"       # BF16 tcgen05 convolutions for channel counts that are multiples of 8
 
 
@@ -513,7 +517,18 @@ class _ConvBase(_ParamLayer):
             out = Tensor._empty_b16(oshape, self._np_dtype, NXC)
             xr = inputs._rows_pending()                   # gather-free batch: the kernel reads the dataset rows through the index
             xp, xi = xr if xr is not None else (inputs._dptr(NCX), None)
-            check(lib.okl_conv_first_fprop(ctx.h, C.byref(d), xp, xi, self._bucket.ptr(0), self._bucket.ptr(1), out._bf16.ptr))
+            self._vexp = None
+            if _VEXP and lib.okl_conv_vexp_supported(ctx.h, C.byref(d)):
+                # C * KW <= 16: the horizontal taps are expanded into 16 bf16 channels by one memory-bound pass and the layer runs as
+                # a channels-last convolution with a KH x 1 filter on the TMA-fed implicit-GEMM kernels (no software im2col)
+                de = ConvDesc()
+                check(lib.okl_conv_vexp_desc(ctx.h, C.byref(d), C.byref(de)))
+                xe = _DevBuf(ctx, max(inputs.shape[0] * de.inp[0] * de.inp[1], 1) * 32)
+                check(lib.okl_conv_vexp_expand(ctx.h, C.byref(d), xp, xi, xe.ptr))
+                check(lib.okl_conv2_fprop(ctx.h, C.byref(de), xe.ptr, self._vexp_bank(d), self._bucket.ptr(1), None, out._bf16.ptr))
+                self._vexp = (de, xe)
+            else:
+                check(lib.okl_conv_first_fprop(ctx.h, C.byref(d), xp, xi, self._bucket.ptr(0), self._bucket.ptr(1), out._bf16.ptr))
             self._fwd_layouts, self._bf16_path, self._conv2 = (xl, yl), False, False
             return out
         b16_ok = bool(ctx.precision == _lib.BF16 and xl == NXC and yl == NXC and inputs.shape[0] > 0)
@@ -551,9 +566,17 @@ class _ConvBase(_ParamLayer):
         b = self._bucket
         need_dx = getattr(self, "_need_dx", True)
         if getattr(self, "_first_tc", False) and ctx.precision == _lib.BF16 and not need_dx:
-            xr = x._rows_pending()
-            xp, xi = xr if xr is not None else (x._dptr(NCX), None)
-            check(lib.okl_conv_first_wgrad(ctx.h, C.byref(d), xp, xi, dL_dout._b16(NXC), b.grad_ptr(0), b.grad_ptr(1)))
+            vx = getattr(self, "_vexp", None)
+            if vx is not None:                            # filter + bias gradient of the expanded convolution, mapped back to (O, C, KH, KW)
+                de, xe = vx
+                dwe = _DevBuf(ctx, self.out_channels * 16 * self._k[0] * 4)
+                check(lib.okl_conv2_wgrad(ctx.h, C.byref(de), xe.ptr, dL_dout._b16(NXC), dwe.ptr, b.grad_ptr(1)))
+                check(lib.okl_conv_vexp_dw(ctx.h, C.byref(d), dwe.ptr, b.grad_ptr(0)))
+                self._vexp = None
+            else:
+                xr = x._rows_pending()
+                xp, xi = xr if xr is not None else (x._dptr(NCX), None)
+                check(lib.okl_conv_first_wgrad(ctx.h, C.byref(d), xp, xi, dL_dout._b16(NXC), b.grad_ptr(0), b.grad_ptr(1)))
             b.step(lr, self._defer_update)
             return None
         aux = self._aux_lane and self._defer_update and need_dx
@@ -620,6 +643,20 @@ class _ConvBase(_ParamLayer):
             if aux:
                 check(lib.okl_aux_end(ctx.h))
         return dX
+
+    def _vexp_bank(self, d):
+        """bf16 filter bank (O, KH, 16) of the first layer's expanded form, refreshed when the fp32 masters changed (see _filter_banks)."""
+        ctx = get_ctx()
+        wt = self._bucket.tensors[0]
+        wp = self._bucket.ptr(0)
+        ver = ("capture", id(getattr(ctx, "_capture_keep", None)), wt._dev_ver) if ctx.capturing else (wt._dev_ver, ctx.epoch)
+        n = self.out_channels * self._k[0] * 16 * 2
+        if getattr(self, "_vbank_buf", None) is None or self._vbank_buf.nbytes < n:
+            self._vbank_buf, self._vbank_ver = _DevBuf(ctx, n), None
+        if self._vbank_ver != ver:
+            check(lib.okl_conv_vexp_bank(ctx.h, C.byref(d), wp, self._vbank_buf.ptr))
+            self._vbank_ver = ver
+        return self._vbank_buf.ptr
 
     def _filter_banks(self, d):
         """bf16 K-major filter banks of the tcgen05 convolution - [O][tap][C] for fprop, flipped [C][tap][O] for dgrad - refreshed by

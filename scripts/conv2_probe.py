@@ -179,10 +179,11 @@ def perf():
 def timeline():
     lib.okl_debug_tc_timestamps.argtypes = [C.c_void_p, C.c_void_p]
     N, Cc, Oc, S = (int(v) for v in os.environ.get("TL_SHAPE", "1024,64,64,32").split(","))
-    d = desc(2, N, Cc, Oc, (S, S), 3, 1, act=1)
+    kk = tuple(int(v) for v in os.environ.get("TL_K", "3,3").split(","))
+    d = desc(2, N, Cc, Oc, (S, S), kk, (kk[0] // 2, kk[1] // 2), act=1)
     x16, y16 = _DevBuf(ctx, N * Cc * S * S * 2), _DevBuf(ctx, N * Oc * S * S * 2)
     check(lib.okl_memset(ctx.h, x16.ptr, 0x3c, x16.nbytes))
-    W = okl.Tensor((np.random.default_rng(0).standard_normal((Oc, Cc, 3, 3)) * 0.1).astype(np.float32))
+    W = okl.Tensor((np.random.default_rng(0).standard_normal((Oc, Cc) + kk) * 0.1).astype(np.float32))
     bias = okl.Tensor(np.zeros(Oc, dtype=np.float32))
     w2 = _DevBuf(ctx, W.size * 2)
     check(lib.okl_conv2_filter_banks(ctx.h, C.byref(d), W._dptr(), w2.ptr, None))
@@ -416,6 +417,48 @@ def wgrad():
 
 if "wgrad" in what:
     wgrad()
+
+def vexp():
+    """timing of the expanded-taps first layer (CIFAR shape) piece by piece against the small-K kernels"""
+    N = int(os.environ.get("PROBE_BATCH", "1024"))
+    d = _lib.ConvDesc()
+    d.nd, d.N, d.C, d.O = 2, N, 3, 64
+    for i in range(2):
+        d.inp[i], d.k[i], d.s[i], d.p[i] = 32, 3, 1, 1
+    d.act, d.x_layout, d.y_layout = 1, _lib.NCX, _lib.NXC
+    de = _lib.ConvDesc()
+    check(lib.okl_conv_vexp_desc(ctx.h, C.byref(d), C.byref(de)))
+    x = okl.Tensor(np.random.default_rng(0).standard_normal((N, 3, 32, 32), dtype=np.float32))
+    Wt, bb = okl.Tensor(np.ones((64, 3, 3, 3), dtype=np.float32)), okl.Tensor(np.zeros(64, dtype=np.float32))
+    xe, w2e = _DevBuf(ctx, N * 32 * 32 * 32), _DevBuf(ctx, 64 * 3 * 32)
+    y16, g16 = _DevBuf(ctx, N * 64 * 1024 * 2), _DevBuf(ctx, N * 64 * 1024 * 2)
+    check(lib.okl_memset(ctx.h, g16.ptr, 0x3c, g16.nbytes))
+    dwe, dW, db = _DevBuf(ctx, 64 * 16 * 3 * 4), _DevBuf(ctx, 64 * 27 * 4), _DevBuf(ctx, 256)
+    t0 = timeit(lambda: check(lib.okl_conv_vexp_expand(ctx.h, C.byref(d), x._dptr(), None, xe.ptr)))
+    tb = timeit(lambda: check(lib.okl_conv_vexp_bank(ctx.h, C.byref(d), Wt._dptr(), w2e.ptr)))
+    for env in ({}, {"OKL_CT_PAIR": "0"}, {"OKL_CT_SLAB": "0"}):
+        for k_ in ("OKL_CT_PAIR", "OKL_CT_SLAB"):
+            os.environ.pop(k_, None)
+        os.environ.update(env)
+        t1 = timeit(lambda: check(lib.okl_conv2_fprop(ctx.h, C.byref(de), xe.ptr, w2e.ptr, bb._dptr(), None, y16.ptr)))
+        print(f"vexp fprop {env}: {t1:.1f} us")
+    for k_ in ("OKL_CT_PAIR", "OKL_CT_SLAB"):
+        os.environ.pop(k_, None)
+    de.act = 0
+    for env in ({}, {"OKL_WG_PT": "64"}, {"OKL_WG_PT": "128"}):
+        os.environ.pop("OKL_WG_PT", None)
+        os.environ.update(env)
+        t2 = timeit(lambda: check(lib.okl_conv2_wgrad(ctx.h, C.byref(de), xe.ptr, g16.ptr, dwe.ptr, db.ptr)))
+        print(f"vexp wgrad {env}: {t2:.1f} us")
+    os.environ.pop("OKL_WG_PT", None)
+    t3 = timeit(lambda: check(lib.okl_conv_vexp_dw(ctx.h, C.byref(d), dwe.ptr, dW.ptr)))
+    f1 = timeit(lambda: check(lib.okl_conv_first_fprop(ctx.h, C.byref(d), x._dptr(), None, Wt._dptr(), bb._dptr(), y16.ptr)))
+    f2 = timeit(lambda: check(lib.okl_conv_first_wgrad(ctx.h, C.byref(d), x._dptr(), None, g16.ptr, dW.ptr, db.ptr)))
+    print(f"vexp: expand {t0:.1f} us, bank {tb:.1f} us, dW remap {t3:.1f} us | small-K kernels: fprop {f1:.1f} us, wgrad+db {f2:.1f} us")
+
+
+if "vexp" in what:
+    vexp()
 
 if "diag" in what:
     diag()

@@ -403,3 +403,65 @@ def test_partial_chunk_shapes_the_tensor_core_kernels_reject_still_match(okl, N,
         assert rel_err(lay.filters.grad, dW) < 1.5e-2 and rel_err(lay.biases.grad, db) < 1.5e-2
     finally:
         okl.set_precision("fp32")
+
+
+@pytest.mark.parametrize("xs,Oc,k,p", [((8, 3, 32, 32), 64, 3, 1), ((3, 3, 30, 27), 128, 3, 1), ((4, 3, 16, 16), 256, 3, 1), ((2, 4, 20, 24), 64, (3, 3), (1, 1)),
+                                       ((2, 5, 12, 40), 72, (2, 3), (0, 0)), ((5, 1, 28, 28), 32, (4, 5), (1, 2)), ((2, 2, 9, 70), 64, (3, 7), (1, 3))])
+def test_first_layer_with_expanded_horizontal_taps(okl, xs, Oc, k, p):
+    """okl_conv_vexp_* + okl_conv2_fprop / okl_conv2_wgrad (okl.py:790-813, 869-871): the first layer as a channels-last convolution
+    over 16 bf16 channels holding (c, horizontal tap), through the C ABI, incl. the dataset-row-index form, vs the fp64 oracle on
+    bf16-rounded operands."""
+    import ctypes as C
+    from okrolearn_b200 import _lib
+    from okrolearn_b200.tensor import _DevBuf
+    lib, check = _lib.lib, _lib.check
+    okl.set_precision("bf16")
+    try:
+        ctx = okl.get_ctx()
+        N, Cc = xs[0], xs[1]
+        rng = np.random.default_rng(N + Oc)
+        kt, pt = O._tup(k, 2), O._tup(p, 2)
+
+        def bf16_round(a):
+            u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+            u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+            return u.astype(np.uint32).view(np.float32)
+
+        data = rng.standard_normal((N + 3,) + xs[1:]).astype(np.float32)           # a "dataset"; the batch is rows `sel` of it
+        sel = rng.permutation(N + 3)[:N].astype(np.int32)
+        x = data[sel]
+        W = (rng.standard_normal((Oc, Cc) + kt) * 0.2).astype(np.float32)
+        b = (rng.standard_normal((Oc, 1)) * 0.1).astype(np.float32)
+        d = _lib.ConvDesc()
+        d.nd, d.N, d.C, d.O = 2, N, Cc, Oc
+        for i in range(2):
+            d.inp[i], d.k[i], d.s[i], d.p[i] = xs[2 + i], kt[i], 1, pt[i]
+        d.act, d.x_layout, d.y_layout = 1, _lib.NCX, _lib.NXC
+        assert lib.okl_conv_vexp_supported(ctx.h, C.byref(d))
+        de = _lib.ConvDesc()
+        check(lib.okl_conv_vexp_desc(ctx.h, C.byref(d), C.byref(de)))
+        xr, Wr = bf16_round(x).astype(np.float64), bf16_round(W).astype(np.float64)
+        yo = np.maximum(O.conv_forward_fast(xr, Wr, b.astype(np.float64), 1, p, dtype=np.float64), 0)
+        tD, tW, tb, tsel = okl.Tensor(data), okl.Tensor(W), okl.Tensor(b.reshape(-1)), _DevBuf(ctx, N * 4)
+        check(lib.okl_h2d_async_raw(ctx.h, tsel.ptr, sel.ctypes.data, N * 4))
+        xe, w2e = _DevBuf(ctx, N * de.inp[0] * de.inp[1] * 32), _DevBuf(ctx, Oc * kt[0] * 32)
+        y16 = _DevBuf(ctx, yo.size * 2)
+        check(lib.okl_conv_vexp_expand(ctx.h, C.byref(d), tD._dptr(_lib.NCX), tsel.ptr, xe.ptr))
+        check(lib.okl_conv_vexp_bank(ctx.h, C.byref(d), tW._dptr(), w2e.ptr))
+        check(lib.okl_conv2_fprop(ctx.h, C.byref(de), xe.ptr, w2e.ptr, tb._dptr(), None, y16.ptr))
+        raw = np.empty(yo.size, dtype=np.uint16)
+        check(lib.okl_d2h_async_raw(ctx.h, raw.ctypes.data, y16.ptr, yo.size * 2))
+        ctx.sync()
+        y = np.moveaxis((raw.astype(np.uint32) << 16).view(np.float32).reshape((N,) + yo.shape[2:] + (Oc,)), -1, 1)
+        assert rel_err(y, yo) < 1e-2
+        g = bf16_round(rng.standard_normal(yo.shape).astype(np.float32))
+        dWo, dbo, _ = O.conv_backward_fast(xr, Wr, g.astype(np.float64), 1, p)
+        tg = okl.Tensor(g)
+        dwe, dW, db = _DevBuf(ctx, Oc * 16 * kt[0] * 4), okl.Tensor._empty(W.shape, np.float32), okl.Tensor._empty((Oc,), np.float32)
+        de.act = 0
+        check(lib.okl_conv2_wgrad(ctx.h, C.byref(de), xe.ptr, tg._b16(_lib.NXC), dwe.ptr, db._ptr_raw()))
+        check(lib.okl_conv_vexp_dw(ctx.h, C.byref(d), dwe.ptr, dW._ptr_raw()))
+        dW._touch(); db._touch()
+        assert rel_err(dW.data, dWo) < 2e-3 and rel_err(db.data, dbo.reshape(-1)) < 2e-3
+    finally:
+        okl.set_precision("fp32")
