@@ -48,6 +48,8 @@ struct ConvTcParams {
   int relu;
   const __nv_bfloat16* mask;           // optional, indexed like the output: out = 0 where mask <= 0 (backward of a preceding ReLU)
   int want_f32, want_b16;
+  int gdepth;                          // > 0: grouped stages (slab mode): ring depth shared by the slab ring and the filter-group ring
+  int a_stage;                         // bytes between activation stages (grouped mode packs them to make room for a third filter group)
   int diag;                            // probe only (OKL_CT_DIAG): 1 = epilogue does nothing, 2 = no MMAs, 4 = activation operand loaded once per stage
   unsigned long long* dbg;
 };
@@ -67,8 +69,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = sA + CT_NA * CT_A_STAGE;
-  uint8_t* sStg = sB + Cfg::NB * Cfg::B_STAGE;
+  uint8_t* sB = sA + CT_NA * p.a_stage;
+  uint8_t* sStg = sA + CT_NA * CT_A_STAGE + Cfg::NB * Cfg::B_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + 8 * CT_STG);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + CT_NA;
@@ -110,6 +112,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     loop_par[4] = (uint32_t)(p.cblocks * p.KW);
     loop_par[5] = p.dbg ? 1u : 0u;
     loop_par[6] = (uint32_t)p.diag;
+    loop_par[7] = (uint32_t)p.gdepth;
+    loop_par[8] = (uint32_t)p.a_stage >> 4;
   }
   tc_fence_before();
   __syncthreads();
@@ -130,21 +134,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int st = 0;
       uint32_t ph_ = 0;
       int nloads = 0;
+      const int adepth = p.gdepth > 0 ? p.gdepth : CT_NA;
       auto load = [&](int c0, int c1, int c2, int c3) {
         mbar_wait(&a_empty[st], ph_ ^ 1);
         if ((p.diag & 4) && nloads++ >= CT_NA) {
           if (!PAIR || crank == 0) mbar_arrive(&a_full[st]);
-          if (++st == CT_NA) { st = 0; ph_ ^= 1; }
+          if (++st == adepth) { st = 0; ph_ ^= 1; }
           return;
         }
         if (PAIR) {
           if (crank == 0) mbar_expect_tx(&a_full[st], 2 * p.a_bytes);       // both CTAs' boxes are counted on the even CTA's barrier
-          tma_load_4d_pair(&tmA, &a_full[st], sA + st * CT_A_STAGE, c0, c1, c2, c3);
+          tma_load_4d_pair(&tmA, &a_full[st], sA + st * p.a_stage, c0, c1, c2, c3);
         } else {
           mbar_expect_tx(&a_full[st], p.a_bytes);
-          tma_load_4d(&tmA, &a_full[st], sA + st * CT_A_STAGE, c0, c1, c2, c3);
+          tma_load_4d(&tmA, &a_full[st], sA + st * p.a_stage, c0, c1, c2, c3);
         }
-        if (++st == CT_NA) { st = 0; ph_ ^= 1; }
+        if (++st == adepth) { st = 0; ph_ ^= 1; }
       };
       for (int w = unit0; w < total; w += unit_step) {
         const int tm = (w / p.tiles_n) * CS + (int)crank;
@@ -172,6 +177,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int cb = 0; cb < p.cblocks; cb++) {
           for (int v = 0; v < p.KW; v++) {
             int kcol = v * p.C + cb * 64;                 // tap (u, v) -> column (u * KW + v) * C + cb * 64 of the K-major bank
+            if (p.gdepth > 0) {
+              // grouped stages: the KH filter tiles of this (chunk, v) land in ONE group slot, counted on one barrier; the slot is
+              // released together with the activation slab of the same iteration (the slab ring's empty barrier)
+              mbar_wait(&a_empty[st], ph_ ^ 1);
+              if (!PAIR || crank == 0) mbar_expect_tx(&b_full[st], (uint32_t)(p.KH * Cfg::B_STAGE));
+              uint8_t* dst = sB + st * (p.KH * BST);
+              for (int u = 0; u < p.KH; u++, kcol += p.KW * p.C) {
+                if (PAIR) tma_load_2d_pair(&tmB, &b_full[st], dst + u * BST, kcol, n_off);
+                else tma_load_2d(&tmB, &b_full[st], dst + u * BST, kcol, n_off);
+              }
+              if (++st == p.gdepth) { st = 0; ph_ ^= 1; }
+              continue;
+            }
             for (int u = 0; u < p.KH; u++, kcol += p.KW * p.C) {
               if (p.diag & 8) continue;                    // probe: no filter-tile ring at all (neither loads nor its barriers)
               mbar_wait(&b_empty[st], ph_ ^ 1);
@@ -196,7 +214,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (crank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc(1, false, false, PAIR ? 256 : 128, BN);
       constexpr uint32_t HI = TC_DESC_HI_SW128;
-      constexpr uint32_t A16 = CT_A_STAGE >> 4, B16 = BST >> 4;
+      constexpr uint32_t B16 = BST >> 4;
+      const uint32_t A16 = loop_par[8];
       const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);      // LBO = 16 B (unused by K-major swizzled operands)
       const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t af0 = smem_u32(a_full), ae0 = smem_u32(a_empty), bf0 = smem_u32(b_full), be0 = smem_u32(b_empty);
@@ -210,6 +229,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t pa = 0, pb = 0, pacc = 0;
       bool want_ts = loop_par[5] != 0;                     // debug timeline: when the first activation slab landed
       const bool nomma = (loop_par[6] & 2u) != 0, nobring = (loop_par[6] & 8u) != 0;
+      const uint32_t gdepth = loop_par[7], g16 = (uint32_t)KH * B16;
       auto commit = [&](uint32_t bar) {
         if (PAIR) umma_commit_pair_a(bar);
         else umma_commit_a(bar);
@@ -219,6 +239,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t d0 = tmem_base + acc * (uint32_t)(2 * BN);
         uint32_t accum = 0;
+        if (gdepth) {
+          // grouped stages (slab mode): per (chunk, v) iteration two waits (slab, filter group), KH x 8 MMAs and ONE commit that frees
+          // slab and filter group together - the issuing thread pays ~200-300 cycles per tcgen05.commit and ~85 per barrier wait
+          // (scripts/exp/commit_bench.cu), which the per-tap protocol below spends 12 times per 3 x 3 tile
+#pragma unroll 1
+          for (int cv = 0; cv < nv; cv++) {
+            const uint32_t a_lo = a_lo0 + sa * A16, bg = b_lo0 + sa * g16;
+            mbar_wait_a(af0 + sa * 8, pa);
+            mbar_wait_a(bf0 + sa * 8, pa);
+            if (want_ts) {
+              p.dbg[blockIdx.x * 8 + 1] = gtime();
+              want_ts = false;
+            }
+#pragma unroll 1
+            for (int u = 0; u < KH; u++) {
+              const uint32_t al = a_lo + (uint32_t)u * row16, b_lo = bg + (uint32_t)u * B16;
+              if (!nomma) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                  umma_bf16_words<PAIR>(d0, al + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), HI, idesc, k ? 1u : accum);
+                  umma_bf16_words<PAIR>(d0 + BN, al + sub16 + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), HI, idesc, k ? 1u : accum);
+                }
+              }
+              accum = 1;
+            }
+            commit(ae0 + sa * 8);
+            if (++sa == gdepth) { sa = 0; pa ^= 1; }
+          }
+        } else
 #pragma unroll 1
         for (int cv = 0; cv < nv; cv++) {                  // (channel chunk, horizontal tap)
           uint32_t a_lo = a_lo0 + sa * A16;
@@ -566,6 +615,17 @@ int conv_tc_run(okl_ctx* ctx, const void* x16, int N, int H, int W, int Cc, cons
   // at BN = 256 the operand fetch is no longer the limit (61.7 single vs 64.5 pair) - those tiles stay single
   int pair = ct_env("OKL_CT_PAIR", bn <= 128 ? 1 : 0) ? 1 : 0;
   if (p.tiles_m % 2 != 0 || (p.tiles_m / 2) * p.tiles_n < ctx->sm_count / 4) pair = 0;
+  // grouped stages: slab mode, and at least two filter groups (KH tiles of this CTA's rows) fit the filter ring
+  // (measured, batch 1024: 64 -> 64 @ 32 x 32 96 -> 88 us; with only two groups the 128 -> 128 layer got slower, 55 -> 60 us, so
+  // three are required - the activation stages are packed to their real size to make room for the third)
+  p.gdepth = 0;
+  p.a_stage = CT_A_STAGE;
+  if (p.slab && ct_env("OKL_CT_GROUP", 1) && !(p.diag & 8)) {
+    const int bst = bn * 128 / (pair ? 2 : 1);
+    const int a_stage = (p.a_bytes + 1023) & ~1023;
+    const int ring = (bn == 64 ? 6 : (bn == 128 ? 4 : 2)) * bn * 128 + CT_NA * (CT_A_STAGE - a_stage);
+    if (ring / (KH * bst) >= CT_NA) { p.gdepth = CT_NA; p.a_stage = a_stage; }
+  }
   CUtensorMap ta, tb, ty16, ty32;
   int s = ct_map_nhwc(&ta, x16, 2, Cc, W, H, N, 64, p.TW, p.slab ? p.TH + KH - 1 : p.TH, p.TN);
   if (s != OKL_OK) return s;

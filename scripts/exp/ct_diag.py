@@ -26,7 +26,7 @@ for (Cc, Oc, S, k) in ((64, 64, 32, (3, 1)), (64, 64, 32, (3, 3)), (128, 128, 16
     out = []
     for pair in ("1", "0"):
         os.environ["OKL_CT_PAIR"] = pair
-        for dg in (0, 7, 15, 8, 9):
+        for dg in (0, 1, 2, 7):
             os.environ["OKL_CT_DIAG"] = str(dg)
             t = timeit(lambda: check(lib.okl_conv2_fprop(ctx.h, C.byref(d), x16.ptr, w2.ptr, bias._dptr(), None, y16.ptr)))
             out.append(f"p{pair}d{dg} {t:6.1f}")
