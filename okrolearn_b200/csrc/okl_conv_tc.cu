@@ -870,31 +870,55 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       }
       umma_commit(done);
     }
-  } else if (warp >= 4) {
-    // ===================================================================== epilogue: accumulators -> fp32 partials of this (tile, split)
-    const int q = warp & 3;
+  }
+  // ===================================================================== epilogue (all eight warps): accumulators -> fp32 partials
+  // As in the gradient-slab kernel below: scattered 16-byte stores straight from the TMEM registers ran at ~15 GB/s per SM (12.6 us per
+  // 196 KB, probe), so every 128 x BN accumulator image is staged in the idle operand stages + ones region - segment (32-column chunk
+  // c, row r) at (c * 128 + r) * 128 B, 16-byte pieces XOR-swizzled with the row - and leaves with one bulk copy; the second stage
+  // reads the same swizzled image.
+  __syncwarp();
+  {
+    const int q = warp & 3, par = warp >> 2;
     mbar_wait(done, 0);
     tc_fence_after();
     const bool any = split < p.ktiles;
-    const int nacc = p.MT * p.KH;
+    const int nacc = p.MT * p.KH, nch = BN >> 5;
+    const uint32_t img_bytes = (uint32_t)(128 * BN * 4);
+    const int nbuf = (int)(((uint32_t)(p.stages * p.stage_bytes) + (uint32_t)WG_ONES) / img_bytes);      // >= 1 (checked by the plan)
     float* dst0 = p.ws + (((size_t)split * (p.tiles_mt * p.tiles_n) + tile) * nacc) * (size_t)(128 * BN);
-    for (int a = 0; a < nacc; a++) {
-      if (2 * (a / p.KH) >= nreal + p.has_db) break;       // M tiles the MMA loop skipped
-      float* row = dst0 + ((size_t)a * 128 + q * 32 + lane) * BN;
+    const int r = q * 32 + lane;
+    int na = 0;
+    for (int a = 0; a < nacc; a++)
+      if (2 * (a / p.KH) < nreal + p.has_db) na = a + 1;   // accumulators of the M tiles the MMA loop touched
+    for (int a = 0; a < na; a++) {
+      uint8_t* img = sSt + (size_t)(a % nbuf) * img_bytes;
+      if (a >= nbuf) {                                     // the copy that last used this buffer must have read it
+        if (threadIdx.x == 0) tma_store_wait_read<0>();
+        __syncthreads();
+      }
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = par; c < nch; c += 2) {
         uint32_t v[32];
         if (any) {
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c), v);
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c * 32), v);
           tmem_ld_wait();
         } else {
 #pragma unroll
           for (int j = 0; j < 32; j++) v[j] = 0u;
         }
+        uint4* seg = reinterpret_cast<uint4*>(img + ((size_t)(c * 128 + r) << 7));
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(row + c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < 8; j++) seg[j ^ (r & 7)] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      fence_proxy_async();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst0 + (size_t)a * 128 * BN), "r"(smem_u32(img)), "r"(img_bytes)
+                     : "memory");
+        tma_store_commit();
       }
     }
+    if (threadIdx.x == 0) tma_store_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -928,7 +952,9 @@ __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ ws, float* __
     const int tn = o / BN, on = o - tn * BN;
     const int tile = tmt * tiles_n + tn;
     const size_t stride = (size_t)(tiles_mt * tiles_n) * nacc * 128 * BN;
-    const float* src = ws + (((size_t)tile * nacc + (t * KH + u)) * 128 + (j * 64 + m64)) * (size_t)BN + on;
+    const int row = j * 64 + m64;                           // swizzled segment image written by the kernel's epilogue
+    const float* src = ws + ((size_t)tile * nacc + (t * KH + u)) * (size_t)(128 * BN) + ((size_t)((on >> 5) * 128 + row) << 5) +
+                       (((((on & 31) >> 2) ^ (row & 7)) << 2) | (on & 3));
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int k = part;
     for (; k + 12 < splits; k += 16) {
