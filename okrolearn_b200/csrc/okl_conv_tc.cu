@@ -39,6 +39,8 @@ struct ConvTcParams {
   int tiles_m, tiles_n, tiles_w, tiles_h;
   int TW, TH, TN, tw_sh, th_sh;        // CTA tile: TW x TH pixels of TN images = 256 output pixels (all powers of two)
   int KH, KW, cblocks, C;              // taps; 64-channel chunks of the reduction; channels of the input tensor
+  int KD, pd, OD;                      // Conv3D (okl.py:948-985): depth taps, depth padding, output depth - an "image" of the tile decode is
+                                       // one (sample, output depth) slice, the depth taps are one more loop around the reduction
   int ph, pw;
   int slab;                            // 1: A = one slab per (chunk, v), vertical taps are row offsets into it; 0: one tile per tap
   int sub_bytes, row_bytes, a_bytes;   // second sub-tile / one tap row inside an A stage; bytes of one A transaction
@@ -109,7 +111,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     loop_par[1] = (uint32_t)p.sub_bytes >> 4;
     loop_par[2] = p.slab ? (uint32_t)p.row_bytes >> 4 : 0u;
     loop_par[3] = (uint32_t)p.KH;
-    loop_par[4] = (uint32_t)(p.cblocks * p.KW);
+    loop_par[4] = (uint32_t)(p.KD * p.cblocks * p.KW);
     loop_par[5] = p.dbg ? 1u : 0u;
     loop_par[6] = (uint32_t)p.diag;
     loop_par[7] = (uint32_t)p.gdepth;
@@ -135,7 +137,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t ph_ = 0;
       int nloads = 0;
       const int adepth = p.gdepth > 0 ? p.gdepth : CT_NA;
-      auto load = [&](int c0, int c1, int c2, int c3) {
+      auto load = [&](int c0, int c1, int c2, int c3, int c4) {
         mbar_wait(&a_empty[st], ph_ ^ 1);
         if ((p.diag & 4) && nloads++ >= CT_NA) {
           if (!PAIR || crank == 0) mbar_arrive(&a_full[st]);
@@ -144,10 +146,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (PAIR) {
           if (crank == 0) mbar_expect_tx(&a_full[st], 2 * p.a_bytes);       // both CTAs' boxes are counted on the even CTA's barrier
-          tma_load_4d_pair(&tmA, &a_full[st], sA + st * p.a_stage, c0, c1, c2, c3);
+          if (p.OD > 0) tma_load_5d_pair(&tmA, &a_full[st], sA + st * p.a_stage, c0, c1, c2, c3, c4);
+          else tma_load_4d_pair(&tmA, &a_full[st], sA + st * p.a_stage, c0, c1, c2, c3);
         } else {
           mbar_expect_tx(&a_full[st], p.a_bytes);
-          tma_load_4d(&tmA, &a_full[st], sA + st * p.a_stage, c0, c1, c2, c3);
+          if (p.OD > 0) tma_load_5d(&tmA, &a_full[st], sA + st * p.a_stage, c0, c1, c2, c3, c4);
+          else tma_load_4d(&tmA, &a_full[st], sA + st * p.a_stage, c0, c1, c2, c3);
         }
         if (++st == adepth) { st = 0; ph_ ^= 1; }
       };
@@ -156,11 +160,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int wt = tm % p.tiles_w, r2 = tm / p.tiles_w;
         const int ht = r2 % p.tiles_h, ng = r2 / p.tiles_h;
         const int w0 = wt * p.TW - p.pw, h0 = ht * p.TH - p.ph, n0 = ng * p.TN;
-        for (int cb = 0; cb < p.cblocks; cb++) {
-          for (int v = 0; v < p.KW; v++) {
-            if (p.slab) load(cb * 64, w0 + v, h0, n0);
-            else
-              for (int u = 0; u < p.KH; u++) load(cb * 64, w0 + v, h0 + u, n0);
+        // 3-D: image group -> (sample, first output depth); the 5-D box takes TN consecutive depths of that sample (TN divides OD)
+        const int smp = p.OD > 0 ? n0 / p.OD : 0, d0 = p.OD > 0 ? n0 - smp * p.OD - p.pd : 0;
+        for (int t = 0; t < p.KD; t++) {
+          for (int cb = 0; cb < p.cblocks; cb++) {
+            for (int v = 0; v < p.KW; v++) {
+              if (p.slab) load(cb * 64, w0 + v, h0, p.OD > 0 ? d0 + t : n0, smp);
+              else
+                for (int u = 0; u < p.KH; u++) load(cb * 64, w0 + v, h0 + u, p.OD > 0 ? d0 + t : n0, smp);
+            }
           }
         }
       }
@@ -174,9 +182,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int w = unit0; w < total; w += unit_step) {
         const int tn = w % p.tiles_n;
         const int n_off = tn * BN + (PAIR ? (int)crank * (BN / 2) : 0);
+        for (int t = 0; t < p.KD; t++)
         for (int cb = 0; cb < p.cblocks; cb++) {
           for (int v = 0; v < p.KW; v++) {
-            int kcol = v * p.C + cb * 64;                 // tap (u, v) -> column (u * KW + v) * C + cb * 64 of the K-major bank
+            int kcol = (t * p.KH * p.KW + v) * p.C + cb * 64;     // tap (t, u, v) -> column ((t * KH + u) * KW + v) * C + cb * 64 of the K-major bank
             if (p.gdepth > 0) {
               // grouped stages: the KH filter tiles of this (chunk, v) land in ONE group slot, counted on one barrier; the slot is
               // released together with the activation slab of the same iteration (the slab ring's empty barrier)
@@ -505,6 +514,27 @@ int ct_map_nhwc(CUtensorMap* map, const void* base, int es, int C, int W, int H,
   return OKL_OK;
 }
 
+// 5-D map over a channels-last bf16 tensor (N, D, H, W, C): dims {C, W, H, D, N}; one box = box_d depth slices of one sample
+int ct_map_ndhwc(CUtensorMap* map, const void* base, int C, int W, int H, int D, int N, int box_c, int box_w, int box_h, int box_d) {
+  CtEncodeFn fn = ct_encode_fn();
+  if (!fn) {
+    okl_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return OKL_ERR_CUDA;
+  }
+  cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t gstride[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)D * H * W * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_d, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    okl_set_error("cuTensorMapEncodeTiled(ndhwc) failed with CUresult %d (C=%d W=%d H=%d D=%d N=%d box=%d,%d,%d,%d)", (int)r, C, W, H, D, N, box_c, box_w,
+                  box_h, box_d);
+    return OKL_ERR_CUDA;
+  }
+  return OKL_OK;
+}
+
 // 2-D map over a row-major bf16 matrix [outer][inner]
 int ct_map_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner, uint32_t box_outer) {
   CtEncodeFn fn = ct_encode_fn();
@@ -564,24 +594,45 @@ int ct_launch_cs(okl_ctx* ctx, int pair, const CUtensorMap& ta, const CUtensorMa
   return ct_launch<BN, 0>(ctx, ta, tb, ty16, ty32, p);
 }
 
-struct CtShape { int N, C, O, H, W, KH, KW, PH, PW, OH, OW; };
+struct CtShape { int N, C, O, H, W, KH, KW, PH, PW, OH, OW; int D, KD, PD, OD; };   // D = KD = OD = 1, PD = 0 for 1-D / 2-D layers
 bool gs_feasible(okl_ctx* ctx, const okl_conv_desc* d);
 
 void ct_shape(const okl_conv_desc* d, CtShape& s) {
   s.N = d->N; s.C = d->C; s.O = d->O;
+  s.D = s.KD = s.OD = 1; s.PD = 0;
   if (d->nd == 1) { s.H = 1; s.W = d->in[0]; s.KH = 1; s.KW = d->k[0]; s.PH = 0; s.PW = d->p[0]; }
-  else { s.H = d->in[0]; s.W = d->in[1]; s.KH = d->k[0]; s.KW = d->k[1]; s.PH = d->p[0]; s.PW = d->p[1]; }
+  else if (d->nd == 2) { s.H = d->in[0]; s.W = d->in[1]; s.KH = d->k[0]; s.KW = d->k[1]; s.PH = d->p[0]; s.PW = d->p[1]; }
+  else {
+    s.D = d->in[0]; s.H = d->in[1]; s.W = d->in[2]; s.KD = d->k[0]; s.KH = d->k[1]; s.KW = d->k[2]; s.PD = d->p[0]; s.PH = d->p[1]; s.PW = d->p[2];
+    s.OD = s.D + 2 * s.PD - s.KD + 1;
+  }
   s.OH = s.H + 2 * s.PH - s.KH + 1;
   s.OW = s.W + 2 * s.PW - s.KW + 1;
 }
 
 // y[N, OH, OW, Oc] = act(conv(x16[N, H, W, Cc], bank[Oc][T * Cc]) + bias) (* mask > 0), stride 1, padding (ph, pw), channels-last
+// images per 256-pixel tile of an OH x OW output (1 when the tile lies inside one image)
+int ct_tile_images(int OH, int OW) {
+  int tw = ct_pow2_ceil(OW); if (tw > 32) tw = 32;
+  int th = ct_pow2_ceil(OH); if (th > 256 / tw) th = 256 / tw;
+  return 256 / (tw * th);
+}
+
+// vol3 != NULL: Conv3D - {D, KD, pd, OD}: input depth, depth taps, depth padding, output depth; N then counts SAMPLES and every
+// (sample, output depth) slice is an image of the tile decode
 int conv_tc_run(okl_ctx* ctx, const void* x16, int N, int H, int W, int Cc, const void* bank, int Oc, int KH, int KW, int ph, int pw, int OH, int OW,
-                const float* bias, int relu, float* y, void* y16, const void* mask16) {
+                const float* bias, int relu, float* y, void* y16, const void* mask16, const int* vol3 = nullptr) {
   OKL_REQUIRE(Cc % 8 == 0 && Oc % 8 == 0 && Oc <= CT_MAX_OC, "conv_tc: channel counts must be multiples of 8 (C=%d O=%d)", Cc, Oc);
   OKL_REQUIRE(y || y16, "conv_tc: no output requested");
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
+  const int D3 = vol3 ? vol3[0] : 1, KD = vol3 ? vol3[1] : 1, pd3 = vol3 ? vol3[2] : 0, OD = vol3 ? vol3[3] : 1;
+  const int samples = N;
+  p.KD = KD; p.pd = pd3; p.OD = vol3 ? OD : 0;
+  if (vol3) {
+    OKL_REQUIRE(OD % ct_tile_images(OH, OW) == 0, "conv_tc (3-D): the images of a tile must be depth slices of one sample (OD=%d)", OD);
+    N = samples * OD;                                        // images of the tile decode and of the (dense) output
+  }
   p.TW = ct_pow2_ceil(OW); if (p.TW > 32) p.TW = 32;
   p.TH = ct_pow2_ceil(OH); if (p.TH > 256 / p.TW) p.TH = 256 / p.TW;
   p.TN = 256 / (p.TW * p.TH);
@@ -627,9 +678,10 @@ int conv_tc_run(okl_ctx* ctx, const void* x16, int N, int H, int W, int Cc, cons
     if (ring / (KH * bst) >= CT_NA) { p.gdepth = CT_NA; p.a_stage = a_stage; }
   }
   CUtensorMap ta, tb, ty16, ty32;
-  int s = ct_map_nhwc(&ta, x16, 2, Cc, W, H, N, 64, p.TW, p.slab ? p.TH + KH - 1 : p.TH, p.TN);
+  int s = vol3 ? ct_map_ndhwc(&ta, x16, Cc, W, H, D3, samples, 64, p.TW, p.slab ? p.TH + KH - 1 : p.TH, p.TN)
+               : ct_map_nhwc(&ta, x16, 2, Cc, W, H, N, 64, p.TW, p.slab ? p.TH + KH - 1 : p.TH, p.TN);
   if (s != OKL_OK) return s;
-  s = ct_map_2d(&tb, bank, (uint64_t)KH * KW * Cc, (uint64_t)Oc, 64, (uint32_t)(pair ? bn / 2 : bn));
+  s = ct_map_2d(&tb, bank, (uint64_t)KD * KH * KW * Cc, (uint64_t)Oc, 64, (uint32_t)(pair ? bn / 2 : bn));
   if (s != OKL_OK) return s;
   // an absent output still needs a valid descriptor object (never dereferenced by the kernel): alias the other one
   s = ct_map_nhwc(&ty16, y16 ? y16 : (const void*)y, y16 ? 2 : 4, Oc, OW, OH, N, y16 ? 64 : 32, p.TW, p.RH, p.RN);
@@ -645,7 +697,7 @@ int conv_tc_run(okl_ctx* ctx, const void* x16, int N, int H, int W, int Cc, cons
 
 bool ct_supported(okl_ctx* ctx, const okl_conv_desc* d) {
   if (ctx->cc < 100 || ct_env("OKL_CONV_TC2", 1) == 0) return false;
-  if (d->nd > 2 || d->x_layout != OKL_NXC || d->y_layout != OKL_NXC) return false;
+  if (d->nd > 3 || d->x_layout != OKL_NXC || d->y_layout != OKL_NXC) return false;
   for (int i = 0; i < d->nd; i++)
     if (d->s[i] != 1) return false;
   if (d->C % 8 || d->O % 8 || d->C > CT_MAX_OC || d->O > CT_MAX_OC || d->N < 1) return false;
@@ -653,6 +705,13 @@ bool ct_supported(okl_ctx* ctx, const okl_conv_desc* d) {
   ct_shape(d, s);
   if (s.OH < 1 || s.OW < 1 || s.KH > 7 || s.KW > 7) return false;
   if (s.PH > s.KH - 1 || s.PW > s.KW - 1) return false;
+  if (d->nd == 3) {
+    // Conv3D: a tile's images are depth slices of ONE sample, in the forward (output depth) and in the input gradient (input depth);
+    // the weight gradient comes from the gradient-slab kernel, one depth tap per CTA group
+    if (ct_env("OKL_CT_3D", 1) == 0 || s.OD < 1 || s.KD > 7 || s.PD > s.KD - 1) return false;
+    if (s.OD % ct_tile_images(s.OH, s.OW) || s.D % ct_tile_images(s.H, s.W)) return false;
+    if (!gs_feasible(ctx, d)) return false;
+  }
   // Channel counts that are multiples of 8 but not of 64 (16-byte rows for TMA): the 64-channel boxes run past the tensor's channel
   // extent and TMA's zero fill pads the reduction; partial output-channel tiles are clipped by the TMA stores.  Those shapes need the
   // gradient-slab weight-gradient kernel (the other wgrad kernels assume whole 64-channel chunks), so they are taken only with it.
@@ -685,8 +744,9 @@ extern "C" int okl_conv2_fprop(okl_ctx* ctx, const okl_conv_desc* d, const void*
   OKL_REQUIRE(d->act == OKL_ACT_NONE || d->act == OKL_ACT_RELU, "okl_conv2_fprop: only ReLU can be fused (act=%d)", d->act);
   CtShape s;
   ct_shape(d, s);
+  const int vol3[4] = {s.D, s.KD, s.PD, s.OD};
   return conv_tc_run(ctx, x16, s.N, s.H, s.W, s.C, w2_16, s.O, s.KH, s.KW, s.PH, s.PW, s.OH, s.OW, (const float*)bias, d->act == OKL_ACT_RELU ? 1 : 0,
-                     (float*)y, y16, nullptr);
+                     (float*)y, y16, nullptr, d->nd == 3 ? vol3 : nullptr);
 }
 
 extern "C" int okl_conv2_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const void* g16, const void* wf_16, void* dx, void* dx16,
@@ -696,8 +756,9 @@ extern "C" int okl_conv2_dgrad(okl_ctx* ctx, const okl_conv_desc* d, const void*
   CtShape s;
   ct_shape(d, s);
   // dx = conv(g, flip(W)^T) with padding k - 1 - p: the same kernel with the roles of C and O exchanged
+  const int vol3[4] = {s.OD, s.KD, s.KD - 1 - s.PD, s.D};     // the gradient's depth is the "input" depth of this convolution
   return conv_tc_run(ctx, g16, s.N, s.OH, s.OW, s.O, wf_16, s.C, s.KH, s.KW, s.KH - 1 - s.PH, s.KW - 1 - s.PW, s.H, s.W, nullptr, 0, (float*)dx, dx16,
-                     relu_mask16);
+                     relu_mask16, d->nd == 3 ? vol3 : nullptr);
 }
 
 // ================================================================================================ weight gradient
@@ -985,7 +1046,7 @@ bool wg_plan(okl_ctx* ctx, const okl_conv_desc* d, bool want_db, WgPlan& pl) {
   // measured (batch 1024): 64-channel inputs 197 vs 321 us and 77 vs 91 us against the first-generation kernel; for C >= 128 the
   // first generation's N = 128 / 256 tiles still win (98 / 59 / 81 us vs 137 / 96 / 133 us) - those shapes stay there for now
   if (s.C > 64 && ct_env("OKL_WG_ALL", 0) == 0) return false;
-  if (s.C % 64 || s.O % 64) return false;                  // whole 64-channel chunks only (the gradient-slab kernel takes the rest)
+  if (s.C % 64 || s.O % 64 || d->nd == 3) return false;    // whole 64-channel chunks, 1-D / 2-D only (the gradient-slab kernel takes the rest)
   WgParams& p = pl.p;
   memset(&p, 0, sizeof(p));
   p.TW = ct_pow2_ceil(s.OW); if (p.TW > 32) p.TW = 32;
@@ -1065,6 +1126,8 @@ struct GsParams {
   int xbox_bytes, gslab_bytes, row_bytes, gimg_bytes;
   int stages, stage_bytes, nreal_max;
   int has_db, ones_bytes;
+  int KD, pd, D;                       // Conv3D: depth taps (one per CTA group: tile = (depth tap, M tile group, N tile)), depth padding, input
+                                       // depth; D = 0 for 1-D / 2-D layers.  An image of the k-tile decode is one (sample, input depth) slice.
   int epi_bufs;                        // staging images that fit the operand stages (1 or 2)
   int diag;                            // probe only (OKL_WG_DIAG): 1 = every MMA issued twice, 2 = operands loaded once per stage slot
   float* ws;                           // [split][tile][MT * NO][128][64 KH]
@@ -1103,7 +1166,8 @@ conv_wgrad_gs_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   okl_pdl_sync();
 
   const int tile = blockIdx.x / p.splits, split = blockIdx.x - tile * p.splits;
-  const int tmt = tile / p.tiles_n, tn = tile - tmt * p.tiles_n;
+  const int tt = tile / (p.tiles_mt * p.tiles_n), tile2 = tile - tt * (p.tiles_mt * p.tiles_n);        // depth tap of this CTA (0 for 2-D)
+  const int tmt = tile2 / p.tiles_n, tn = tile2 - tmt * p.tiles_n;
   const int q0 = tmt * p.MT * 2;                           // first chunk slot (flattened (v, channel chunk)) of this CTA
   int nreal = p.nchunks - q0;
   if (nreal > p.MT * 2) nreal = p.MT * 2;
@@ -1128,13 +1192,18 @@ conv_wgrad_gs_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
         mbar_expect_tx(&full[st], tx_bytes);
         uint8_t* base = sSt + st * p.stage_bytes;
+        // 3-D: image group -> (sample, first input depth); the gradient slab of depth tap tt sits tt - pd slices before it (zero fill outside)
+        const int smp = p.D > 0 ? n0 / p.D : 0, d0 = p.D > 0 ? n0 - smp * p.D : 0;
         for (int j = 0; j < nreal; j++) {
           const int q = q0 + j, v = q / p.cpc, cc = q - v * p.cpc;
-          tma_load_4d(&tmX, &full[st], base + j * p.xbox_bytes, cc * 64, w0 + v - p.pw, h0, n0);
+          if (p.D > 0) tma_load_5d(&tmX, &full[st], base + j * p.xbox_bytes, cc * 64, w0 + v - p.pw, h0, d0, smp);
+          else tma_load_4d(&tmX, &full[st], base + j * p.xbox_bytes, cc * 64, w0 + v - p.pw, h0, n0);
         }
         uint8_t* gb = base + p.nreal_max * p.xbox_bytes;
-        for (int j = 0; j < p.NO; j++)
-          tma_load_4d(&tmG, &full[st], gb + j * p.gslab_bytes, (tn * p.NO + j) * 64, w0, h0 + p.ph - (p.KH - 1), n0);
+        for (int j = 0; j < p.NO; j++) {
+          if (p.D > 0) tma_load_5d(&tmG, &full[st], gb + j * p.gslab_bytes, (tn * p.NO + j) * 64, w0, h0 + p.ph - (p.KH - 1), d0 - tt + p.pd, smp);
+          else tma_load_4d(&tmG, &full[st], gb + j * p.gslab_bytes, (tn * p.NO + j) * 64, w0, h0 + p.ph - (p.KH - 1), n0);
+        }
         if (++st == p.stages) { st = 0; ph_ ^= 1; }
       }
     }
@@ -1211,7 +1280,8 @@ conv_wgrad_gs_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     tc_fence_after();
     const int nunits = p.MT * p.NO, nch = NC >> 5;
     const uint32_t unit_bytes = (uint32_t)(128 * NC * 4);
-    float* dst0 = p.ws + (((size_t)split * (p.tiles_mt * p.tiles_n) + tile) * nunits) * (size_t)(128 * NC);
+    const int ntiles = (p.D > 0 ? p.KD : 1) * p.tiles_mt * p.tiles_n;
+    float* dst0 = p.ws + (((size_t)split * ntiles + tile) * nunits) * (size_t)(128 * NC);
     const int r = q * 32 + lane;
     const int nu = (p.diag & 128) ? 0 : nt * p.NO;
     for (int a = 0; a < nu; a++) {
@@ -1252,7 +1322,7 @@ conv_wgrad_gs_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 // warps of a segment sit in one block, the first adds their sums in order and scatters into the reference's (O, C, KH, KW) layout.
 __global__ void __launch_bounds__(256) conv_wgrad_gs_reduce(const float* __restrict__ ws, float* __restrict__ dW, float* __restrict__ db, int O, int C,
                                                             int KH, int KW, int cpc, int nchunks, int MT, int NO, int tiles_mt, int tiles_n,
-                                                            int splits, int ph, int G, int nseg) {
+                                                            int splits, int ph, int G, int nseg, int KD, int pd) {
   __shared__ float part[8][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NC = KH * 64, nch = NC >> 5, nunits = MT * NO;
@@ -1263,14 +1333,15 @@ __global__ void __launch_bounds__(256) conv_wgrad_gs_reduce(const float* __restr
   const int c = b % nch; b /= nch;
   const int row = b & 127; b >>= 7;
   const int unit = b % nunits, tile = b / nunits;
-  const int tmt = tile / tiles_n, tn = tile - tmt * tiles_n;
+  const int tt = tile / (tiles_mt * tiles_n), tile2 = tile - tt * (tiles_mt * tiles_n);      // depth tap (0 for 2-D)
+  const int tmt = tile2 / tiles_n, tn = tile2 - tmt * tiles_n;
   const int t = unit / NO, jo = unit - t * NO;
   const int q = tmt * 2 * MT + 2 * t + (row >> 6), m64 = row & 63;      // chunk slot of this row
-  const bool is_db = db && q == nchunks && m64 == 0;
+  const bool is_db = db && q == nchunks && m64 == 0 && tt == pd;
   const bool live = in_range && (q < nchunks || is_db);
   float sum = 0.f;
   if (live) {
-    const size_t stride = (size_t)(tiles_mt * tiles_n) * nunits * 128 * NC;
+    const size_t stride = (size_t)(KD * tiles_mt * tiles_n) * nunits * 128 * NC;
     const float* src = ws + ((size_t)tile * nunits + unit) * 128 * NC + ((size_t)(c * 128 + row) << 5) + ((((lane >> 2) ^ (row & 7)) << 2) | (lane & 3));
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int k = g;
@@ -1300,7 +1371,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_gs_reduce(const float* __restr
     if (u == ph) db[o] = s;
   } else {
     const int v = q / cpc, ch = (q - v * cpc) * 64 + m64;
-    if (ch < C) dW[(((size_t)o * C + ch) * KH + u) * KW + v] = s;
+    if (ch < C) dW[((((size_t)o * C + ch) * KD + tt) * KH + u) * KW + v] = s;
   }
 }
 
@@ -1315,13 +1386,15 @@ bool gs_plan(okl_ctx* ctx, const okl_conv_desc* d, bool want_db, GsPlan& pl) {
   // 64->128@16 61 vs 60; C >= 128: 84 / 58 / 87 (+ channel sum) vs the first generation's 128 x 256 tiles 94 / 62 / 95 incl. db - its
   // N = 256 MMAs fetch fewer operand bytes per flop.  So: C = O = 64 only, unless OKL_WG_ALL asks for every shape (parity tests, probes).
   const bool partial_chunks = s.C % 64 || s.O % 64;        // only this kernel handles those (zero-filled channel boxes, guarded second stage)
-  if ((s.C != 64 || s.O != 64) && !partial_chunks && ct_env("OKL_WG_ALL", 0) == 0) return false;
+  const bool vol = d->nd == 3;                             // ... and Conv3D (okl.py:1018-1031): one depth tap per CTA group
+  if ((s.C != 64 || s.O != 64) && !partial_chunks && !vol && ct_env("OKL_WG_ALL", 0) == 0) return false;
   GsParams& p = pl.p;
   memset(&p, 0, sizeof(p));
+  p.KD = vol ? s.KD : 1; p.pd = s.PD; p.D = vol ? s.D : 0;
   p.KH = s.KH; p.KW = s.KW; p.cpc = (s.C + 63) / 64; p.nchunks = s.KW * p.cpc; p.ph = s.PH; p.pw = s.PW;
   const int ochunks = (s.O + 63) / 64;
   // bias gradient for free when a chunk slot is empty anyway and column group u = ph sees every gradient row (H >= OH)
-  pl.db_fused = want_db && (p.nchunks & 1) && 2 * s.PH <= s.KH - 1;
+  pl.db_fused = want_db && (p.nchunks & 1) && 2 * s.PH <= s.KH - 1 && 2 * s.PD <= s.KD - 1;
   p.has_db = pl.db_fused ? 1 : 0;
   const int S = p.nchunks + p.has_db;
   if (S > 2 && S <= 4) { p.MT = 2; p.NO = 1; }
@@ -1341,6 +1414,7 @@ bool gs_plan(okl_ctx* ctx, const okl_conv_desc* d, bool want_db, GsPlan& pl) {
     p.TH = ct_pow2_ceil(s.H); if (p.TH > pt / p.TW) p.TH = pt / p.TW;
     p.TN = pt / (p.TW * p.TH);
     if (p.TW * p.TH < 16) continue;
+    if (vol && s.D % p.TN) continue;                       // the images of a k-block are depth slices of one sample
     p.tw_sh = ct_ilog2(p.TW); p.pimg_sh = ct_ilog2(p.TW * p.TH);
     p.row_bytes = p.TW * 128;
     p.gimg_bytes = (p.TH + s.KH - 1) * p.row_bytes;
@@ -1359,8 +1433,8 @@ bool gs_plan(okl_ctx* ctx, const okl_conv_desc* d, bool want_db, GsPlan& pl) {
   p.epi_bufs = (p.MT * p.NO > 1 && p.stages * p.stage_bytes >= 2 * 128 * s.KH * 64 * 4) ? 2 : 1;
   if (p.stages * p.stage_bytes < 128 * s.KH * 64 * 4) return false;
   p.tiles_w = (s.OW + p.TW - 1) / p.TW; p.tiles_h = (s.H + p.TH - 1) / p.TH;
-  p.ktiles = p.tiles_w * p.tiles_h * ((s.N + p.TN - 1) / p.TN);
-  const int tiles = p.tiles_mt * p.tiles_n;
+  p.ktiles = p.tiles_w * p.tiles_h * ((s.N * s.D + p.TN - 1) / p.TN);
+  const int tiles = p.KD * p.tiles_mt * p.tiles_n;
   p.splits = ctx->sm_count / tiles;
   if (p.splits > p.ktiles) p.splits = p.ktiles;
   if (p.splits < 1) p.splits = 1;
@@ -1370,13 +1444,19 @@ bool gs_plan(okl_ctx* ctx, const okl_conv_desc* d, bool want_db, GsPlan& pl) {
 // shapes with partial 64-channel chunks: this kernel must take them, and the bias gradient must come either from its ones slot or from
 // okl_channel_sum_bf16 (channel counts of 8 x a power of two)
 bool gs_feasible(okl_ctx* ctx, const okl_conv_desc* d) {
-  if (d->nd > 2 || d->x_layout != OKL_NXC || d->y_layout != OKL_NXC || d->C % 8 || d->O % 8) return false;
+  if (d->nd > 3 || d->x_layout != OKL_NXC || d->y_layout != OKL_NXC || d->C % 8 || d->O % 8) return false;
   CtShape s;
   ct_shape(d, s);
   if (s.KH < 2 || s.KH > 4 || s.OH < 1 || s.OW < 1) return false;
   if (ct_env("OKL_CONV_TC2_WGRAD", 1) == 0 || ct_env("OKL_WG_GS", 1) == 0) return false;
   const int nchunks = s.KW * ((s.C + 63) / 64);
-  const bool db_fused = (nchunks & 1) && 2 * s.PH <= s.KH - 1;
+  const bool db_fused = (nchunks & 1) && 2 * s.PH <= s.KH - 1 && 2 * s.PD <= s.KD - 1;
+  if (d->nd == 3) {                                        // k-blocks of 64 pixels at least: their images must be slices of one sample
+    const int tw3 = ct_pow2_ceil(s.OW) > 32 ? 32 : ct_pow2_ceil(s.OW);
+    int th3 = ct_pow2_ceil(s.H); if (th3 > 64 / tw3) th3 = 64 / tw3 > 0 ? 64 / tw3 : 1;
+    const int tn3 = 64 / (tw3 * th3) > 0 ? 64 / (tw3 * th3) : 1;
+    if (s.D % tn3) return false;
+  }
   const int o8 = s.O / 8;
   if (!db_fused && !((o8 & (o8 - 1)) == 0 && o8 <= 256)) return false;
   const int tw = ct_pow2_ceil(s.OW) > 32 ? 32 : ct_pow2_ceil(s.OW);
@@ -1388,26 +1468,27 @@ int gs_run(okl_ctx* ctx, const okl_conv_desc* d, GsPlan& pl, const void* x16, co
   CtShape s;
   ct_shape(d, s);
   GsParams& p = pl.p;
-  const size_t ws_bytes = (size_t)p.splits * p.tiles_mt * p.tiles_n * p.MT * p.NO * 128 * (p.KH * 64) * sizeof(float);
+  const size_t ws_bytes = (size_t)p.splits * p.KD * p.tiles_mt * p.tiles_n * p.MT * p.NO * 128 * (p.KH * 64) * sizeof(float);
   int st = okl_ensure_workspace(ctx, ws_bytes);
   if (st != OKL_OK) return st;
   p.ws = (float*)ctx->workspace;
   CUtensorMap tx, tg;
-  st = ct_map_nhwc(&tx, x16, 2, s.C, s.W, s.H, s.N, 64, p.TW, p.TH, p.TN);
+  st = p.D > 0 ? ct_map_ndhwc(&tx, x16, s.C, s.W, s.H, s.D, s.N, 64, p.TW, p.TH, p.TN) : ct_map_nhwc(&tx, x16, 2, s.C, s.W, s.H, s.N, 64, p.TW, p.TH, p.TN);
   if (st != OKL_OK) return st;
-  st = ct_map_nhwc(&tg, g16, 2, s.O, s.OW, s.OH, s.N, 64, p.TW, p.TH + s.KH - 1, p.TN);
+  st = p.D > 0 ? ct_map_ndhwc(&tg, g16, s.O, s.OW, s.OH, s.OD, s.N, 64, p.TW, p.TH + s.KH - 1, p.TN)
+               : ct_map_nhwc(&tg, g16, 2, s.O, s.OW, s.OH, s.N, 64, p.TW, p.TH + s.KH - 1, p.TN);
   if (st != OKL_OK) return st;
   static int attr_smem = 0;
   if (attr_smem < pl.smem) {
     OKL_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_gs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_smem = 227 * 1024;
   }
-  okl_launch(ctx, conv_wgrad_gs_kernel, dim3(p.tiles_mt * p.tiles_n * p.splits), dim3(GS_THREADS), pl.smem, tx, tg, p);
+  okl_launch(ctx, conv_wgrad_gs_kernel, dim3(p.KD * p.tiles_mt * p.tiles_n * p.splits), dim3(GS_THREADS), pl.smem, tx, tg, p);
   OKL_LAUNCHED(ctx, "conv_wgrad_gs_kernel");
-  const int nseg = p.tiles_mt * p.tiles_n * p.MT * p.NO * 128 * (s.KH * 2);
+  const int nseg = p.KD * p.tiles_mt * p.tiles_n * p.MT * p.NO * 128 * (s.KH * 2);
   const int G = p.splits >= 32 ? 8 : (p.splits >= 16 ? 4 : (p.splits >= 8 ? 2 : 1));
   conv_wgrad_gs_reduce<<<(nseg + 8 / G - 1) / (8 / G), 256, 0, ctx->stream>>>(p.ws, (float*)dW, pl.db_fused ? (float*)db : nullptr, s.O, s.C, s.KH, s.KW,
-                                                                                 p.cpc, p.nchunks, p.MT, p.NO, p.tiles_mt, p.tiles_n, p.splits, p.ph, G, nseg);
+                                                                                 p.cpc, p.nchunks, p.MT, p.NO, p.tiles_mt, p.tiles_n, p.splits, p.ph, G, nseg, p.KD, p.pd);
   OKL_LAUNCHED(ctx, "conv_wgrad_gs_reduce");
   return OKL_OK;
 }
@@ -1434,7 +1515,7 @@ extern "C" int okl_conv2_wgrad(okl_ctx* ctx, const okl_conv_desc* d, const void*
   if (gs_plan(ctx, d, db != nullptr, gp)) {
     int st = gs_run(ctx, d, gp, x16, g16, dW, db);
     if (st != OKL_OK) return st;
-    if (db && !gp.db_fused) return okl_channel_sum_bf16(ctx, g16, db, (long long)s.N * s.OH * s.OW, s.O);
+    if (db && !gp.db_fused) return okl_channel_sum_bf16(ctx, g16, db, (long long)s.N * s.OD * s.OH * s.OW, s.O);
     return OKL_OK;
   }
   WgPlan pl;

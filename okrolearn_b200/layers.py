@@ -21,6 +21,7 @@ _BF16_ONLY = __import__("os").environ.get("OKL_BF16_ONLY", "1") != "0"
 # kernels at the CIFAR shape (expand 25 + fprop 97 + wgrad 63 + remap 6 us against 61 + 70 us: the implicit-GEMM kernel has a per-tile
 # floor of ~2.5 us whatever the reduction length - see DESIGN.md) - off unless asked for
 _VEXP = __import__("os").environ.get("OKL_CONV_VEXP_LAYER", "0") != "0"
+_CT_3D = __import__("os").environ.get("OKL_CT_3D", "1") != "0"          # Conv3D with >= 8 channels on the BF16 tcgen05 kernels
 _ANY_C = __import__("os").environ.get("OKL_CT_ANYC", "1") != "0"       # BF16 tcgen05 convolutions for channel counts that are multiples of 8
 
 
@@ -435,9 +436,17 @@ class _ConvBase(_ParamLayer):
         padding <= k-1, channel counts that are multiples of 32 - or, in BF16 mode, 2-D layers with 2..4 filter rows and channel
         counts that are multiples of 8 (TMA zero-fills the partial 64-channel chunks; the bias gradient needs a free chunk slot of
         the weight-gradient kernel or 8 x 2^n output channels).  Those layers run channels-last in TF32/BF16 mode."""
-        if not (self._nd <= 2 and all(s == 1 for s in self._s) and all(p <= k - 1 for p, k in zip(self._p, self._k))):
+        if not (all(s == 1 for s in self._s) and all(p <= k - 1 for p, k in zip(self._p, self._k))):
             return False
         Cc, Oc = self.in_channels, self.out_channels
+        if self._nd == 3:
+            # Conv3D on the BF16 kernels (5-D TMA boxes, one more tap loop; the weight gradient one depth tap per CTA group).  Whether
+            # the tiles fit the volume is only known with the input shape: _forward asks okl_conv2_supported and falls back.
+            if get_ctx().precision != _lib.BF16 or not _CT_3D or Cc % 8 or Oc % 8 or not (2 <= self._k[1] <= 4):
+                return False
+            free_slot = ((self._k[2] * ((Cc + 63) // 64)) % 2 == 1 and 2 * self._p[1] <= self._k[1] - 1 and 2 * self._p[0] <= self._k[0] - 1)
+            o8 = Oc // 8
+            return bool(free_slot or (o8 & (o8 - 1)) == 0)
         if Cc % 32 == 0 and Oc % 32 == 0:
             return True
         if get_ctx().precision != _lib.BF16 or self._nd != 2 or Cc % 8 or Oc % 8 or not (2 <= self._k[0] <= 4) or not _ANY_C:
@@ -495,7 +504,11 @@ class _ConvBase(_ParamLayer):
             pooled, full = self._forward_fused_pool(inputs)
             self._fused_out = pooled
             return full
-        if ctx.precision != _lib.FP32 and self._tc_eligible():
+        tc = ctx.precision != _lib.FP32 and self._tc_eligible()
+        if tc and self._nd == 3:                 # 3-D: the tile / volume fit is shape dependent
+            dd, _ = self._desc(inputs.shape, NXC, NXC, self._fused_act)
+            tc = bool(inputs.shape[0] > 0 and self._fused_act in (ACT_NONE, ACT_RELU) and lib.okl_conv2_supported(ctx.h, C.byref(dd)))
+        if tc:
             xl = yl = NXC
         else:
             xl = inputs._layout if inputs.ndim >= 3 and inputs._dev_valid else NCX

@@ -590,7 +590,7 @@ class NeuralNetwork:
             return Tensor._view(slot.tin, 0, (rows,) + t_shape, np.float32, bound=False)
 
         # a first layer that runs channels-last on the tensor cores gets its batch in that layout straight from the prefetch
-        x_nxc = bool(self.prefetch_batches and ctx.precision != _lib.FP32 and isinstance(first, _ConvBase) and first._tc_eligible() and
+        x_nxc = bool(self.prefetch_batches and ctx.precision != _lib.FP32 and isinstance(first, _ConvBase) and first._nd <= 2 and first._tc_eligible() and
                      getattr(first, "_fused_pool", None) is None and len(sample_shape) >= 2 and sample_shape[0] > 1 and _numel(sample_shape[1:]) > 1)
         # BF16 mode: that copy is written as bf16 (permutation + conversion in one pass on the copy stream) - the operand format of the
         # second-generation convolution, which then reads the batch without any fp32 detour

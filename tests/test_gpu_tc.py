@@ -465,3 +465,36 @@ def test_first_layer_with_expanded_horizontal_taps(okl, xs, Oc, k, p):
         assert rel_err(dW.data, dWo) < 2e-3 and rel_err(db.data, dbo.reshape(-1)) < 2e-3
     finally:
         okl.set_precision("fp32")
+
+
+CONV3D_TC = [  # N, C, (D, H, W), O, k, p
+    (2, 64, (4, 16, 16), 64, 3, 1), (1, 32, (6, 16, 32), 64, 3, 1), (2, 64, (8, 8, 8), 128, 3, 1), (1, 128, (4, 16, 16), 64, (1, 3, 3), (0, 1, 1)),
+    (2, 16, (3, 12, 20), 32, (2, 3, 3), (0, 1, 1)), (1, 64, (5, 32, 32), 64, 3, (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("N,Cc,sp,Oc,k,p", CONV3D_TC)
+def test_conv3d_on_the_bf16_tensor_core_kernels(okl, N, Cc, sp, Oc, k, p):
+    """Conv3DLayer (okl.py:948-1033) with >= 8 channels in BF16 mode: forward, input gradient (5-D TMA boxes, the depth taps as one more
+    reduction loop) and filter / bias gradient (one depth tap per CTA group of the gradient-slab kernel) vs the fp64 oracle."""
+    okl.set_precision("bf16")
+    try:
+        rng = np.random.default_rng(N * 100 + Cc + Oc)
+        kt = O._tup(k, 3)
+        x = rng.standard_normal((N, Cc) + sp).astype(np.float32)
+        W = (rng.standard_normal((Oc, Cc) + kt) * 0.1).astype(np.float32)
+        b = (rng.standard_normal((Oc, 1)) * 0.1).astype(np.float32)
+        lay = okl.Conv3DLayer(Cc, Oc, kt, 1, p)
+        lay.filters.data, lay.biases.data = W.copy(), b.copy()
+        y = lay.forward(okl.Tensor(x))
+        assert lay._conv2, "the 3-D shape was not taken by the tcgen05 kernels"
+        x64 = x.astype(np.float64)
+        yo = O.conv_forward_fast(x64, W.astype(np.float64), b.astype(np.float64), 1, p, dtype=np.float64)
+        assert rel_err(y.data, yo) < 1.5e-2
+        g = rng.standard_normal(yo.shape).astype(np.float32)
+        dX = lay.backward(okl.Tensor(g), 0.05)
+        dW, db, dXo = O.conv_backward_fast(x64, W.astype(np.float64), g.astype(np.float64), 1, p)
+        assert rel_err(dX.data, dXo) < 1.5e-2
+        assert rel_err(lay.filters.grad, dW) < 1.5e-2 and rel_err(lay.biases.grad, db) < 1.5e-2
+    finally:
+        okl.set_precision("fp32")
