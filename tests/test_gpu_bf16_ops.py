@@ -242,3 +242,47 @@ def test_gather_free_train_follows_a_new_dataset(okl):
         assert rel_err(conv.filters.data, on.layers[0].W) < 2e-2
     finally:
         okl.set_precision("fp32")
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_bf16_conv3d_stack_train_vs_oracle(okl, graph):
+    """A Conv3D stack whose inner layers run on the BF16 tensor-core kernels - Conv3D(3, 16) [small-K kernels] -> ReLU -> Conv3D(16, 32)
+    -> ReLU -> Conv3D(32, 8) + MSE - through NeuralNetwork.train (fusion planner, CUDA-graph replay, auxiliary lanes) against the oracle
+    network on the same shuffled batches; loss and every layer's updated parameters within the BF16 tolerance."""
+    okl.set_precision("bf16")
+    try:
+        rng = np.random.default_rng(21)
+        N, B, shape = 8, 4, (3, 4, 16, 16)
+        X = rng.standard_normal((N,) + shape).astype(np.float32)
+        X.reshape(-1)[0] = abs(X.reshape(-1)[0]) + 0.1
+        T = rng.standard_normal((N, 8) + shape[1:]).astype(np.float32)
+        Ws = [(rng.standard_normal((16, 3, 3, 3, 3)) * 0.2).astype(np.float32), (rng.standard_normal((32, 16, 3, 3, 3)) * 0.07).astype(np.float32),
+              (rng.standard_normal((8, 32, 3, 3, 3)) * 0.05).astype(np.float32)]
+        net = okl.NeuralNetwork()
+        net.use_graph = graph
+        convs = [okl.Conv3DLayer(3, 16, 3, 1, 1), okl.Conv3DLayer(16, 32, 3, 1, 1), okl.Conv3DLayer(32, 8, 3, 1, 1)]
+        for c, W in zip(convs, Ws):
+            c.filters.data = W.copy()
+        for l in (convs[0], okl.ReLUActivationLayer(), convs[1], okl.ReLUActivationLayer(), convs[2]):
+            net.add(l)
+        np.random.seed(5)
+        ls = net.train(okl.Tensor(X.copy()), okl.Tensor(T.copy()), epochs=2, lr_scheduler=okl.LearningRateScheduler(0.02),
+                       optimizer=okl.SGDOptimizer(), batch_size=B, loss_function=okl.MSELoss())
+        assert convs[1]._conv2 and convs[2]._conv2, "the inner Conv3D layers were not taken by the tcgen05 kernels"
+        z = lambda n: np.zeros((n, 1))                                   # noqa: E731
+        on = O.OracleNetwork([O.OracleConv(Ws[0].astype(np.float64), z(16), 1, 1, fast=True), O.OracleReLU(),
+                              O.OracleConv(Ws[1].astype(np.float64), z(32), 1, 1, fast=True), O.OracleReLU(),
+                              O.OracleConv(Ws[2].astype(np.float64), z(8), 1, 1, fast=True)])
+        np.random.seed(5)
+        Xo, To, ol = X.copy(), T.copy(), []
+        for ep in range(2):
+            idx = np.arange(N)
+            np.random.shuffle(idx)
+            Xo, To = Xo[idx], To[idx]
+            ol.append(sum(on.train_step(Xo[s:s + B], To[s:s + B], O.OracleMSE(), 0.02) for s in range(0, N, B)) / (N // B))
+        assert rel_err(ls, ol) < 2e-2
+        for c, k in zip(convs, (0, 2, 4)):
+            assert rel_err(c.filters.data, on.layers[k].W) < 2e-2
+            assert rel_err(c.biases.data, on.layers[k].b) < 5e-2
+    finally:
+        okl.set_precision("fp32")
