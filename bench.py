@@ -9,7 +9,7 @@ A "step" is one train step (forward + loss + backward + in-layer accumulated-gra
 data.  Default workload = BASELINE.json configs[2]: the CIFAR-shaped 6-conv network at batch 1024 per GPU (weak scaling: N=1 runs
 the named batch 1024; at N>1 the strong-scaling variant - GLOBAL batch 1024 split over the ranks, 128 per GPU at N=8 - is measured in
 the same run and reported under "other_scaling"), BF16 operands / FP32 accumulate.  The other BASELINE configs are
-measured in the same run and reported under "configs" (N=1: all of them; N>1: the two that name a multi-GPU run), the TF32 and
+measured in the same run and reported under "configs" (all of them at every N, weak scaling), the TF32 and
 FP32-FFMA modes of the headline workload under "modes".
 """
 from __future__ import annotations
@@ -753,7 +753,10 @@ def main():
     # ------------------------------------------------------------------ the other BASELINE configs (same process, same GPUs)
     configs = {}
     if not args.no_configs:
-        second = ["mnist_cnn", "conv2d_single", "conv1d_seq", "conv3d_video", "mlp8192"] if world == 1 else ["mnist_cnn", "mlp8192"]
+        # every BASELINE config at every N (north_star: "reported at 1, 2, 4 and 8 GPUs"): weak scaling, each rank its own batch
+        second = ["mnist_cnn", "conv2d_single", "conv1d_seq", "conv3d_video", "mlp8192"]
+        if world > 1 and os.environ.get("OKL_BENCH_ALL_CONFIGS", "1") == "0":
+            second = ["mnist_cnn", "mlp8192"]
         for wl in second:
             if wl == name:
                 continue
