@@ -19,7 +19,7 @@ constexpr size_t P2P_FLAGS_BYTES = 4096;    // flags + counters at the start of 
 // one-shot "LL" exchange for tiny buckets (NCCL's low-latency protocol): a 16-byte packet carries two floats and two copies of the
 // sequence number and is written with ONE store, so the receiver needs no separate flag, fence or barrier - it polls the packet
 // itself.  Latency = one one-way NVLink trip instead of the four of the two-shot kernel (ready, pull, push-ack, done).
-constexpr int LL_MAX_FLOATS = 4096;
+constexpr int LL_MAX_FLOATS = 16384;          // one-shot packet exchange up to 64 KB (a single small conv layer: 49 KB)
 constexpr int LL_PKTS = LL_MAX_FLOATS / 2;
 constexpr size_t LL_BYTES = (size_t)2 * P2P_MAX_RANKS * LL_PKTS * 16;   // [parity][source rank][packet]
 constexpr size_t P2P_HDR_BYTES = P2P_FLAGS_BYTES + LL_BYTES;
